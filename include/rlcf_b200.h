@@ -1,0 +1,150 @@
+/* rlcf_b200.h -- C ABI of librlcf_b200.so: the sm_100a kernels behind the RLCF test-time-adaptation hot path.
+ *
+ * The reference (mzhaoshuai/RLCF) is pure Python over PyTorch and has no FFI of its own; every entry point
+ * below replaces the ATen / cuBLAS / cuDNN library call that the cited reference line dispatches to
+ * (SURVEY.md section 2.2, rows K1-K15).  Conventions:
+ *   - plain device pointers + int sizes + a cudaStream_t (passed as void*); no torch types;
+ *   - every function returns 0 on success or an RLCF_ERR_* code; rlcf_last_error() gives the message;
+ *   - stateless: the caller owns all memory (PyTorch in the shipped host code); kernels are enqueued on the
+ *     caller's stream and never synchronise; safe for one host thread per device;
+ *   - matrices are row-major; "fp16" is IEEE binary16; accumulations and the residual stream are fp32.
+ *
+ * Row / parameter-set convention for the LayerNorm-family kernels: rows are grouped in contiguous runs of
+ * `rows_per_set`; run g uses the affine parameters at gamma + g*param_stride (param_stride = 0 shares one
+ * set).  This is how one batched launch serves many test images that each own a private copy of the
+ * LayerNorm parameters (the reference adapts one image at a time, TPT/tune_cls_rl.py:192-222).
+ */
+#ifndef RLCF_B200_H_
+#define RLCF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLCF_ABI_VERSION 1
+
+enum { RLCF_OK = 0, RLCF_ERR_ARG = 1, RLCF_ERR_CUDA = 2, RLCF_ERR_DRIVER = 3 };
+
+/* GEMM epilogues */
+enum {
+  RLCF_EPI_F16 = 0,          /* out16 = alpha*acc + bias                                   */
+  RLCF_EPI_GELU_F16 = 1,     /* u = alpha*acc + bias; aux_out16 = u; out16 = u*sigmoid(1.702u)  (model.py:166-168) */
+  RLCF_EPI_RESID_F32 = 2,    /* out32 = alpha*acc + bias + resid32                         (model.py:190-191) */
+  RLCF_EPI_GELU_BWD_F16 = 3, /* out16 = alpha*acc * quickgelu'(aux_in16)                   */
+  RLCF_EPI_F32 = 4           /* out32 = alpha*acc + bias                                   */
+};
+
+int rlcf_abi_version(void);
+const char* rlcf_last_error(void);
+/* Number of kernels this library has enqueued since load (bench.py's gpu_launches). */
+uint64_t rlcf_launch_count(void);
+/* 1 = one CTA per tile (UMMA 128x256), 2 = CTA pair per tile (cta_group::2, UMMA 256x256). Returns the value set. */
+int rlcf_set_gemm_cta_group(int cta_group);
+
+/* D[M,N] = A[M,K] * B[N,K]^T, fp16 operands (K contiguous), fp32 accumulate on tcgen05 tensor cores.
+ * Replaces: nn.Conv2d patch embedding (TPT/clip/model.py:224), nn.MultiheadAttention in_proj / out_proj
+ * (model.py:175,187), mlp.c_fc / c_proj (model.py:177-181) and their autograd dgrad (tpt_cls_rl.py:77).
+ * N % 32 == 0, K % 8 == 0, lda/ldb/ldo % 8 == 0, 16-byte aligned pointers. */
+int rlcf_gemm_f16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epilogue, float alpha,
+                  const float* bias, const float* resid, const void* aux_in, void* aux_out, void* out, int ldo,
+                  void* stream);
+
+/* images fp32 [*,C,H,W] -> patch rows fp16 [n_views*(H/p)*(W/p), k_pad] (column = c*p*p + ky*p + kx, zero padded
+ * to k_pad); view_idx (device int32 [n_views], may be NULL = identity) picks the source views.
+ * Together with rlcf_gemm_f16 replaces conv1 (model.py:224) and the inputs[selected_idx] gather (tpt_cls_rl.py:55,59). */
+int rlcf_im2col_f16(const float* images, const int32_t* view_idx, int n_views, int C, int H, int W, int patch,
+                    int k_pad, void* out, void* stream);
+
+/* Token assembly + ln_pre (model.py:225-229): row (v,t) = LN((t==0 ? cls : patch_out[v*(L-1)+t-1]) + pos[t]).
+ * x_pre (may be NULL) receives the pre-LN rows (needed by rlcf_layernorm_bwd for ln_pre). */
+int rlcf_embed_lnpre(const float* patch_out, const float* cls, const float* pos, const float* gamma,
+                     const float* beta, int64_t param_stride, int rows_per_set, int n_views, int L, int d, float eps,
+                     float* x_pre, float* x, void* stream);
+
+/* Text-side token assembly (model.py:343-345): x[(c,t)] = tok_emb[tokens[c,t]] + pos[t]. */
+int rlcf_embed_text(const int64_t* tokens, const float* tok_emb, const float* pos, int n_seq, int L, int d, float* x,
+                    void* stream);
+
+/* Row LayerNorm in fp32 (model.py:157-163), eps inside the sqrt.  x rows are ldx floats apart.
+ * out16 / out32 may each be NULL. */
+int rlcf_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, int64_t param_stride,
+                       int rows_per_set, int M, int d, float eps, void* out16, float* out32, void* stream);
+
+/* LayerNorm backward.  dy is fp16 (dy_is_f32 = 0) or fp32 rows lddy apart; x is the saved LN input.
+ *   dx_accum != NULL : dx_accum[row] (+)= dLN/dx   (accumulate = 1 adds to the residual-stream gradient)
+ *   partials         : [n_sets, n_slots, p_total] fp32; block b of set g writes d(gamma) at
+ *                      partials[g][b][p_off .. p_off+d) and d(beta) at [p_off+d .. p_off+2d).
+ * n_slots blocks are launched per set. */
+int rlcf_layernorm_bwd(const void* dy, int dy_is_f32, int64_t lddy, const float* x, int64_t ldx, const float* gamma,
+                       int64_t param_stride, int rows_per_set, int n_sets, int d, float eps, float* dx_accum,
+                       int64_t lddx, int accumulate, float* partials, int n_slots, int64_t p_total, int64_t p_off,
+                       void* stream);
+
+/* Fused multi-head attention core (nn.MultiheadAttention, model.py:185-187): qkv fp16 [n_seq*L, 3d] packed
+ * q|k|v, head h = columns [h*64,(h+1)*64) of each third; out fp16 [n_seq*L, d].  causal != 0 applies the
+ * text tower's additive -inf upper-triangular mask (model.py:328-334).  lse (may be NULL) receives the
+ * per-row log-sum-exp [n_seq, heads, L] needed by the backward. head_dim is fixed at 64 (CLIP ViT/text). */
+int rlcf_attention_fwd(const void* qkv, int n_seq, int L, int heads, int causal, void* out, float* lse, void* stream);
+int rlcf_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int n_seq, int L,
+                       int heads, int causal, void* dqkv, void* stream);
+
+/* Head: LN(x[row]) @ proj -> L2 normalise -> logits = logit_scale * f . class_feat^T
+ * (model.py:235-238, custom_clip.py:423-432 / clip_reward.py:130-137).
+ * row of sequence v is row_idx[v] if row_idx != NULL else v*row_stride (in rows of d floats).
+ * feat [n,E] gets the normalised features, inv_norm [n] 1/|f| (both may be NULL), logits [n,C] (NULL to skip). */
+int rlcf_head_fwd(const float* x, const int32_t* row_idx, int64_t row_stride, const float* gamma, const float* beta,
+                  int64_t param_stride, int seqs_per_set, const float* proj, const float* class_feat, float logit_scale,
+                  int n, int d, int E, int C, float eps, float* feat, float* inv_norm, float* logits, void* stream);
+
+/* select_confident_samples (tpt_cls_rl.py:32-35): per image, entropy of softmax(logits[v,:]) for its V views,
+ * ascending order, first S kept.  sel [n_img,S] = view index inside the image; sel_global = img*V + sel;
+ * entropy [n_img,V] (may be NULL). */
+int rlcf_entropy_select(const float* logits, int n_img, int V, int C, int S, int32_t* sel, int32_t* sel_global,
+                        float* entropy, void* stream);
+
+/* top-K sampling + CLIPScore + reward post-processing + reward-weighted CE and its gradient
+ * (tpt_cls_rl.py:63-71, clip_reward.py:111-128,152-165).  logits rows: row_idx[i] (NULL = i) for the
+ * n_img*S selected views.  reward_img [n_img*S, Er] and reward_cls [C, Er] are L2-normalised.
+ * dlogits [n_img*S, C] = loss_scale * dL/dlogits with L = mean over the image's S*K samples.
+ * Optional outputs: topk_idx [n_img*S,K] int32, scores / rewards [n_img*S,K], loss [n_img]. */
+int rlcf_reward_loss(const float* logits, const int32_t* row_idx, const float* reward_img, const float* reward_cls,
+                     int n_img, int S, int K, int C, int Er, float clipscore_weight, int reward_process,
+                     int process_batch, int amplify, float loss_scale, float* dlogits, int32_t* topk_idx,
+                     float* scores, float* rewards, float* loss, void* stream);
+
+/* TPT loss (config 1): marginal entropy of the S selected views (tpt_cls_rl.py:38-44) and its gradient. */
+int rlcf_avg_entropy_loss(const float* logits, const int32_t* row_idx, int n_img, int S, int C, float loss_scale,
+                          float* dlogits, float* loss, void* stream);
+
+/* Backward of rlcf_head_fwd for the selected views of each image (one block per image, S views each):
+ * dlogits -> d feat -> d(LN out) -> ln_post backward.  Writes dx into dres rows (row_idx as in head_fwd) and
+ * the ln_post d(gamma), d(beta) into partials[g][0][p_off..p_off+2d). */
+int rlcf_head_bwd(const float* dlogits, const float* x, const int32_t* row_idx, int64_t row_stride,
+                  const float* gamma, int64_t param_stride, const float* proj, const float* class_feat,
+                  float logit_scale, const float* feat, const float* inv_norm, int n_img, int S, int d, int E, int C,
+                  float eps, float* dres, float* partials, int n_slots, int64_t p_total, int64_t p_off, void* stream);
+
+/* Fused gradient reduction + AdamW (torch.optim.AdamW semantics, tune_cls_rl.py:79-81, tpt_cls_rl.py:76-79):
+ * g = sum over slots of partials / loss_scale; decoupled weight decay; bias-corrected moments.
+ * params/m/v: [n_sets, p_total]; grad_out (may be NULL) receives g. */
+int rlcf_adamw_step(float* params, float* m, float* v, const float* partials, int n_sets, int n_slots,
+                    int64_t p_total, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                    float loss_scale, float* grad_out, void* stream);
+
+/* model.reset() + optimizer.load_state_dict (tune_cls_rl.py:210-213) for the trainable slice only:
+ * params[g] = init for every set g; m = v = 0. */
+int rlcf_reset_params(const float* init, float* params, float* m, float* v, int n_sets, int64_t p_total,
+                      void* stream);
+
+/* fp32 -> fp16 with optional zero padding of each row from cols to ld_out (weight preparation). */
+int rlcf_cast_f16(const float* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
+                  void* stream);
+/* out16[c, r] = in32[r, c]  (W^T copies used as the B operand of dgrad GEMMs). */
+int rlcf_transpose_cast_f16(const float* in, int rows, int cols, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLCF_B200_H_ */

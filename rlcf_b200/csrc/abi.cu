@@ -1,0 +1,217 @@
+// extern "C" surface of librlcf_b200.so (declared in include/rlcf_b200.h) plus the small amount of
+// process-wide state the library keeps: last-error text, launch counter, GEMM CTA-group mode.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "rlcf_internal.h"
+
+namespace rlcf {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_cta_group{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int gemm_cta_group() {
+  int v = g_cta_group.load(std::memory_order_relaxed);
+  if (v == 0) {
+    const char* e = getenv("RLCF_GEMM_CTA_GROUP");
+    v = (e != nullptr && atoi(e) == 1) ? 1 : 2;
+    g_cta_group.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+PFN_encodeTiled get_encode_tiled() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+  return reinterpret_cast<PFN_encodeTiled>(fn);
+}
+
+// implemented in kernels.cu / attention.cu
+int im2col_f16(const float*, const int32_t*, int, int, int, int, int, int, __half*, cudaStream_t);
+int embed_lnpre(const float*, const float*, const float*, const float*, const float*, long long, int, int, int, int,
+                float, float*, float*, cudaStream_t);
+int embed_text(const long long*, const float*, const float*, int, int, int, float*, cudaStream_t);
+int layernorm_fwd(const float*, long long, const float*, const float*, long long, int, int, int, float, __half*,
+                  float*, cudaStream_t);
+int layernorm_bwd(const void*, int, long long, const float*, long long, const float*, long long, int, int, int, float,
+                  float*, long long, int, float*, int, long long, long long, cudaStream_t);
+int attention_fwd(const __half*, int, int, int, int, __half*, float*, cudaStream_t);
+int attention_bwd(const __half*, const __half*, const __half*, const float*, int, int, int, int, __half*,
+                  cudaStream_t);
+int head_fwd(const float*, const int32_t*, long long, const float*, const float*, long long, int, const float*,
+             const float*, float, int, int, int, int, float, float*, float*, float*, cudaStream_t);
+int entropy_select(const float*, int, int, int, int, int32_t*, int32_t*, float*, cudaStream_t);
+int reward_loss(const float*, const int32_t*, const float*, const float*, int, int, int, int, int, float, int, int,
+                int, float, float*, int32_t*, float*, float*, float*, cudaStream_t);
+int avg_entropy_loss(const float*, const int32_t*, int, int, int, float, float*, float*, cudaStream_t);
+int head_bwd(const float*, const float*, const int32_t*, long long, const float*, long long, const float*,
+             const float*, float, const float*, const float*, int, int, int, int, int, float, float*, float*, int,
+             long long, long long, cudaStream_t);
+int adamw_step(float*, float*, float*, const float*, int, int, long long, float, float, float, float, float, int,
+               float, float*, cudaStream_t);
+int reset_params(const float*, float*, float*, float*, int, long long, cudaStream_t);
+int cast_f16(const float*, long long, long long, long long, __half*, long long, cudaStream_t);
+int transpose_cast_f16(const float*, int, int, __half*, cudaStream_t);
+
+}  // namespace rlcf
+
+using namespace rlcf;
+#define S(x) static_cast<cudaStream_t>(x)
+#define H(x) static_cast<__half*>(x)
+#define CH(x) static_cast<const __half*>(x)
+
+extern "C" {
+
+int rlcf_abi_version(void) { return RLCF_ABI_VERSION; }
+const char* rlcf_last_error(void) { return g_err; }
+uint64_t rlcf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int rlcf_set_gemm_cta_group(int cta_group) {
+  if (cta_group == 1 || cta_group == 2) g_cta_group.store(cta_group, std::memory_order_relaxed);
+  return gemm_cta_group();
+}
+
+int rlcf_gemm_f16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epilogue, float alpha,
+                  const float* bias, const float* resid, const void* aux_in, void* aux_out, void* out, int ldo,
+                  void* stream) {
+  if (A == nullptr || B == nullptr || out == nullptr) return set_error(RLCF_ERR_ARG, "gemm: null pointer");
+  return gemm_f16(CH(A), lda, CH(B), ldb, M, N, K, epilogue, alpha, bias, resid, CH(aux_in), H(aux_out), out, ldo,
+                  S(stream));
+}
+
+int rlcf_im2col_f16(const float* images, const int32_t* view_idx, int n_views, int C, int H_, int W, int patch,
+                    int k_pad, void* out, void* stream) {
+  if (images == nullptr || out == nullptr) return set_error(RLCF_ERR_ARG, "im2col: null pointer");
+  return im2col_f16(images, view_idx, n_views, C, H_, W, patch, k_pad, H(out), S(stream));
+}
+
+int rlcf_embed_lnpre(const float* patch_out, const float* cls, const float* pos, const float* gamma,
+                     const float* beta, int64_t param_stride, int rows_per_set, int n_views, int L, int d, float eps,
+                     float* x_pre, float* x, void* stream) {
+  if (!patch_out || !cls || !pos || !gamma || !beta || !x) return set_error(RLCF_ERR_ARG, "embed_lnpre: null pointer");
+  return embed_lnpre(patch_out, cls, pos, gamma, beta, param_stride, rows_per_set, n_views, L, d, eps, x_pre, x,
+                     S(stream));
+}
+
+int rlcf_embed_text(const int64_t* tokens, const float* tok_emb, const float* pos, int n_seq, int L, int d, float* x,
+                    void* stream) {
+  if (!tokens || !tok_emb || !pos || !x) return set_error(RLCF_ERR_ARG, "embed_text: null pointer");
+  return embed_text(reinterpret_cast<const long long*>(tokens), tok_emb, pos, n_seq, L, d, x, S(stream));
+}
+
+int rlcf_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, int64_t param_stride,
+                       int rows_per_set, int M, int d, float eps, void* out16, float* out32, void* stream) {
+  if (!x || !gamma || !beta || (!out16 && !out32)) return set_error(RLCF_ERR_ARG, "layernorm_fwd: null pointer");
+  return layernorm_fwd(x, ldx, gamma, beta, param_stride, rows_per_set, M, d, eps, H(out16), out32, S(stream));
+}
+
+int rlcf_layernorm_bwd(const void* dy, int dy_is_f32, int64_t lddy, const float* x, int64_t ldx, const float* gamma,
+                       int64_t param_stride, int rows_per_set, int n_sets, int d, float eps, float* dx_accum,
+                       int64_t lddx, int accumulate, float* partials, int n_slots, int64_t p_total, int64_t p_off,
+                       void* stream) {
+  if (!dy || !x || !gamma) return set_error(RLCF_ERR_ARG, "layernorm_bwd: null pointer");
+  return layernorm_bwd(dy, dy_is_f32, lddy, x, ldx, gamma, param_stride, rows_per_set, n_sets, d, eps, dx_accum, lddx,
+                       accumulate, partials, n_slots, p_total, p_off, S(stream));
+}
+
+int rlcf_attention_fwd(const void* qkv, int n_seq, int L, int heads, int causal, void* out, float* lse,
+                       void* stream) {
+  if (!qkv || !out) return set_error(RLCF_ERR_ARG, "attention_fwd: null pointer");
+  return attention_fwd(CH(qkv), n_seq, L, heads, causal, H(out), lse, S(stream));
+}
+
+int rlcf_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int n_seq, int L,
+                       int heads, int causal, void* dqkv, void* stream) {
+  if (!qkv || !out || !dout || !dqkv) return set_error(RLCF_ERR_ARG, "attention_bwd: null pointer");
+  return attention_bwd(CH(qkv), CH(out), CH(dout), lse, n_seq, L, heads, causal, H(dqkv), S(stream));
+}
+
+int rlcf_head_fwd(const float* x, const int32_t* row_idx, int64_t row_stride, const float* gamma, const float* beta,
+                  int64_t param_stride, int seqs_per_set, const float* proj, const float* class_feat, float logit_scale,
+                  int n, int d, int E, int C, float eps, float* feat, float* inv_norm, float* logits, void* stream) {
+  if (!x || !gamma || !beta || !proj) return set_error(RLCF_ERR_ARG, "head_fwd: null pointer");
+  return head_fwd(x, row_idx, row_stride, gamma, beta, param_stride, seqs_per_set, proj, class_feat, logit_scale, n, d,
+                  E, C, eps, feat, inv_norm, logits, S(stream));
+}
+
+int rlcf_entropy_select(const float* logits, int n_img, int V, int C, int S_, int32_t* sel, int32_t* sel_global,
+                        float* entropy, void* stream) {
+  if (!logits || !sel) return set_error(RLCF_ERR_ARG, "entropy_select: null pointer");
+  return entropy_select(logits, n_img, V, C, S_, sel, sel_global, entropy, S(stream));
+}
+
+int rlcf_reward_loss(const float* logits, const int32_t* row_idx, const float* reward_img, const float* reward_cls,
+                     int n_img, int S_, int K, int C, int Er, float clipscore_weight, int reward_process,
+                     int process_batch, int amplify, float loss_scale, float* dlogits, int32_t* topk_idx,
+                     float* scores, float* rewards, float* loss, void* stream) {
+  if (!logits || !reward_img || !reward_cls || !dlogits) return set_error(RLCF_ERR_ARG, "reward_loss: null pointer");
+  return reward_loss(logits, row_idx, reward_img, reward_cls, n_img, S_, K, C, Er, clipscore_weight, reward_process,
+                     process_batch, amplify, loss_scale, dlogits, topk_idx, scores, rewards, loss, S(stream));
+}
+
+int rlcf_avg_entropy_loss(const float* logits, const int32_t* row_idx, int n_img, int S_, int C, float loss_scale,
+                          float* dlogits, float* loss, void* stream) {
+  if (!logits || !dlogits) return set_error(RLCF_ERR_ARG, "avg_entropy_loss: null pointer");
+  return avg_entropy_loss(logits, row_idx, n_img, S_, C, loss_scale, dlogits, loss, S(stream));
+}
+
+int rlcf_head_bwd(const float* dlogits, const float* x, const int32_t* row_idx, int64_t row_stride,
+                  const float* gamma, int64_t param_stride, const float* proj, const float* class_feat,
+                  float logit_scale, const float* feat, const float* inv_norm, int n_img, int S_, int d, int E, int C,
+                  float eps, float* dres, float* partials, int n_slots, int64_t p_total, int64_t p_off, void* stream) {
+  if (!dlogits || !x || !gamma || !proj || !class_feat || !feat || !inv_norm || !dres || !partials)
+    return set_error(RLCF_ERR_ARG, "head_bwd: null pointer");
+  return head_bwd(dlogits, x, row_idx, row_stride, gamma, param_stride, proj, class_feat, logit_scale, feat, inv_norm,
+                  n_img, S_, d, E, C, eps, dres, partials, n_slots, p_total, p_off, S(stream));
+}
+
+int rlcf_adamw_step(float* params, float* m, float* v, const float* partials, int n_sets, int n_slots,
+                    int64_t p_total, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                    float loss_scale, float* grad_out, void* stream) {
+  if (!params || !m || !v || !partials) return set_error(RLCF_ERR_ARG, "adamw_step: null pointer");
+  return adamw_step(params, m, v, partials, n_sets, n_slots, p_total, lr, beta1, beta2, eps, weight_decay, step,
+                    loss_scale, grad_out, S(stream));
+}
+
+int rlcf_reset_params(const float* init, float* params, float* m, float* v, int n_sets, int64_t p_total,
+                      void* stream) {
+  if (!init || !params) return set_error(RLCF_ERR_ARG, "reset_params: null pointer");
+  return reset_params(init, params, m, v, n_sets, p_total, S(stream));
+}
+
+int rlcf_cast_f16(const float* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
+                  void* stream) {
+  if (!in || !out) return set_error(RLCF_ERR_ARG, "cast_f16: null pointer");
+  return cast_f16(in, rows, cols, ld_in, H(out), ld_out, S(stream));
+}
+
+int rlcf_transpose_cast_f16(const float* in, int rows, int cols, void* out, void* stream) {
+  if (!in || !out) return set_error(RLCF_ERR_ARG, "transpose_cast_f16: null pointer");
+  return transpose_cast_f16(in, rows, cols, H(out), S(stream));
+}
+
+}  // extern "C"

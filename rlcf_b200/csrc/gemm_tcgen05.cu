@@ -1,0 +1,334 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[M,N] = A[M,K] (fp16, K-major) x B[N,K]^T (fp16, K-major), fp32 accumulation in TMEM,
+//   fused epilogues (bias / QuickGELU / residual / QuickGELU-backward).
+//
+// This one kernel carries every dense contraction of the RLCF hot path (SURVEY.md 2.2 rows K1,K3,K5,K6,K7
+// and their dgrad counterparts in K12): the reference reaches them through nn.Conv2d / nn.MultiheadAttention
+// in-proj+out-proj / nn.Linear (TPT/clip/model.py:175-181,224) and autograd.
+//
+// Structure (one CTA per SM, 256 threads):
+//   warp 0      TMA producer   : cp.async.bulk.tensor 2-D tiles (128B swizzle) into a kStages-deep smem ring
+//   warp 1      MMA issuer     : one thread issues tcgen05.mma (UMMA 128x256x16 or, as a CTA pair, 256x256x16)
+//   warp 2      TMEM allocator
+//   warps 4..7  epilogue       : tcgen05.ld accumulator -> registers -> fused epilogue -> 16-byte global stores
+// The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
+// main loop of tile i+1.  kCtaGroup == 2 pairs two SMs (cta_group::2): each CTA stages its own 128 rows of A
+// and half (128 rows) of B, halving the shared-memory and L2 traffic per FLOP.
+#include "ptx.cuh"
+#include "rlcf_internal.h"
+
+namespace rlcf {
+
+constexpr int kBM = 128;      // accumulator rows per CTA (TMEM lanes)
+constexpr int kBN = 256;      // accumulator columns per tile
+constexpr int kBK = 64;       // K elements per stage (= 128 bytes = one swizzle atom)
+constexpr int kUmmaK = 16;    // K per tcgen05.mma for 16-bit inputs
+constexpr int kGemmThreads = 256;
+
+template <int kCtaGroup>
+struct GemmCfg {
+  static constexpr int kBRows = kBN / kCtaGroup;                 // B rows staged by each CTA
+  static constexpr int kABytes = kBM * kBK * 2;                  // 16 KB
+  static constexpr int kBBytes = kBRows * kBK * 2;               // 32 KB / 16 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = kCtaGroup == 1 ? 4 : 6;         // 192 KB ring either way
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmArgs {
+  int M, N, K;
+  int epi;
+  const float* bias;     // [N] or null
+  const float* resid;    // EPI_RESID_F32: [M, ldo] fp32 (may alias out)
+  const __half* aux_in;  // EPI_GELU_BWD_F16: pre-activation u [M, ldo] fp16
+  __half* aux_out;       // EPI_GELU_F16: optional pre-activation save [M, ldo] fp16
+  void* out;             // fp16 or fp32 [M, ldo]
+  int ldo;               // leading dimension of out / resid / aux (elements)
+  float alpha;           // scale applied to the accumulator before the epilogue
+};
+
+template <int kCtaGroup>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs p) {
+  using Cfg = GemmCfg<kCtaGroup>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled UMMA/TMA tiles need 1024-byte alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                       // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = kCtaGroup == 2 ? cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+
+  const int tile_m = kBM * kCtaGroup;
+  const int m_tiles = (p.M + tile_m - 1) / tile_m;
+  const int n_tiles = (p.N + kBN - 1) / kBN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (p.K + kBK - 1) / kBK;
+  const int worker = blockIdx.x / kCtaGroup;
+  const int num_workers = gridDim.x / kCtaGroup;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4 * kCtaGroup);  // one arrive per epilogue warp per CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<kCtaGroup>(tmem_slot, 512);
+  tc_fence_before();
+  if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      // In a CTA pair every load signals the leader's barrier (same smem offset, peer bit cleared).
+      const uint32_t peer_mask = 0xFEFFFFFFu;
+      for (int t = worker; t < num_tiles; t += num_workers) {
+        const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+        const int m0 = m_blk * tile_m + static_cast<int>(cta_rank) * kBM;
+        const int n0 = n_blk * kBN + static_cast<int>(cta_rank) * Cfg::kBRows;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          if constexpr (kCtaGroup == 1) {
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBK, m0);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBK, n0);
+          } else {
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            const uint32_t bar = smem_u32(&full_bar[stage]) & peer_mask;
+            tma_load_2d_cg2(sa, &tmA, bar, kb * kBK, m0);
+            tma_load_2d_cg2(sb, &tmB, bar, kb * kBK, n0);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kBM * kCtaGroup, kBN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = worker; t < num_tiles; t += num_workers, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + as * kBN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t da = umma_desc_k_sw128(sa);
+          const uint64_t db = umma_desc_k_sw128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            // advance 32 bytes (16 fp16) along K inside the swizzle atom: +2 in the >>4 address field
+            umma_f16_ss<kCtaGroup>(tacc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          if constexpr (kCtaGroup == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_cg2(&empty_bar[stage], 0b11);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        if constexpr (kCtaGroup == 1) umma_commit(&tfull_bar[as]);
+        else umma_commit_cg2(&tfull_bar[as], 0b11);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (128 threads, one row each)
+    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int t = worker; t < num_tiles; t += num_workers, ++it) {
+      const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int row = m_blk * tile_m + static_cast<int>(cta_rank) * kBM + ew * 32 + lane;
+      const bool row_ok = row < p.M;
+      const size_t row_off = static_cast<size_t>(row) * p.ldo;
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * kBN;
+#pragma unroll 1
+      for (int c = 0; c < kBN / 32; ++c) {
+        const int col0 = n_blk * kBN + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32(tacc + c * 32, r);
+        tmem_ld_wait();
+        if (row_ok) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        if (p.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        if (p.epi == EPI_RESID_F32 || p.epi == EPI_F32) {
+          float* o = reinterpret_cast<float*>(p.out) + row_off + col0;
+          if (p.epi == EPI_RESID_F32) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.resid + row_off + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 q = r4[j];
+              v[4 * j + 0] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+            }
+          }
+          float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          if (p.epi == EPI_GELU_F16) {
+            if (p.aux_out != nullptr) {
+              uint4* a4 = reinterpret_cast<uint4*>(p.aux_out + row_off + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                __half2 h0 = __floats2half2_rn(v[8 * j + 0], v[8 * j + 1]);
+                __half2 h1 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
+                __half2 h2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
+                __half2 h3 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
+                a4[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                   *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+          } else if (p.epi == EPI_GELU_BWD_F16) {
+            const uint4* u4 = reinterpret_cast<const uint4*>(p.aux_in + row_off + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 q = u4[j];
+              const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h[e]);
+                v[8 * j + 2 * e + 0] *= quick_gelu_grad(f.x);
+                v[8 * j + 2 * e + 1] *= quick_gelu_grad(f.y);
+              }
+            }
+          }
+          uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + row_off + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __half2 h0 = __floats2half2_rn(v[8 * j + 0], v[8 * j + 1]);
+            __half2 h1 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
+            __half2 h2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
+            __half2 h3 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
+            o4[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                               *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+          }
+        }
+        }  // row_ok
+        __syncwarp();  // reconverge before the next .sync.aligned TMEM load
+      }
+      // all of this warp's TMEM reads are complete -> hand the accumulator back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kCtaGroup == 1) mbar_arrive(&tempty_bar[as]);
+        else mbar_arrive_cluster(&tempty_bar[as], 0);
+      }
+    }
+  }
+
+  __syncwarp();  // role branches diverge inside warps 0/1; the barriers below are .aligned
+  tc_fence_before();
+  if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc<kCtaGroup>(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static int make_tmap_2d_f16(CUtensorMap* map, const void* base, int rows, int cols, int ld_elems, int box_rows) {
+  static PFN_encodeTiled encode = get_encode_tiled();
+  if (encode == nullptr) return set_error(RLCF_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not found");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld_elems % 8) != 0)
+    return set_error(RLCF_ERR_ARG, "gemm operand must be 16-byte aligned with a leading dimension multiple of 8");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(RLCF_ERR_DRIVER, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  return 0;
+}
+
+template <int kCtaGroup>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
+  using Cfg = GemmCfg<kCtaGroup>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<kCtaGroup>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_error(RLCF_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int tile_m = kBM * kCtaGroup;
+  const int tiles = ((args.M + tile_m - 1) / tile_m) * ((args.N + kBN - 1) / kBN);
+  const int sms = sm_count();
+  int workers = tiles < sms / kCtaGroup ? tiles : sms / kCtaGroup;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(workers * kCtaGroup);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtaGroup;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_f16_kernel<kCtaGroup>, ta, tb, args);
+  if (e != cudaSuccess) return set_error(RLCF_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+
+int gemm_f16(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, int epi, float alpha,
+             const float* bias, const float* resid, const __half* aux_in, __half* aux_out, void* out, int ldo,
+             cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(RLCF_ERR_ARG, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  if (N % 32 != 0) return set_error(RLCF_ERR_ARG, "gemm: N=%d must be a multiple of 32", N);
+  if (K % 8 != 0) return set_error(RLCF_ERR_ARG, "gemm: K=%d must be a multiple of 8", K);
+  if (ldo % 8 != 0) return set_error(RLCF_ERR_ARG, "gemm: ldo=%d must be a multiple of 8", ldo);
+  if (epi < 0 || epi >= EPI_COUNT) return set_error(RLCF_ERR_ARG, "gemm: unknown epilogue %d", epi);
+  if (epi == EPI_RESID_F32 && resid == nullptr) return set_error(RLCF_ERR_ARG, "gemm: residual epilogue needs resid");
+  if (epi == EPI_GELU_BWD_F16 && aux_in == nullptr) return set_error(RLCF_ERR_ARG, "gemm: gelu-bwd needs aux_in");
+  const int cg = gemm_cta_group();
+  CUtensorMap ta, tb;
+  if (int rc = make_tmap_2d_f16(&ta, A, M, K, lda, kBM)) return rc;
+  if (int rc = make_tmap_2d_f16(&tb, B, N, K, ldb, kBN / cg)) return rc;
+  GemmArgs args{M, N, K, epi, bias, resid, aux_in, aux_out, out, ldo, alpha};
+  return cg == 2 ? launch_gemm<2>(ta, tb, args, stream) : launch_gemm<1>(ta, tb, args, stream);
+}
+
+}  // namespace rlcf

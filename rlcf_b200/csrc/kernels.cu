@@ -1,0 +1,867 @@
+// Bandwidth/latency-bound kernels of the RLCF hot path: im2col, token assembly + ln_pre, LayerNorm fwd/bwd,
+// head (ln_post + proj + L2-norm + logits) fwd/bwd, entropy selection, top-K/CLIPScore/reward/CE-gradient,
+// fused gradient-reduce + AdamW.  Warp-shuffle reductions, 128-bit global accesses where the layout allows.
+// Reference lines are cited per kernel; see include/rlcf_b200.h for the ABI contract.
+#include "ptx.cuh"
+#include "rlcf_internal.h"
+
+namespace rlcf {
+
+// ------------------------------------------------------------------------------------------------ block reduce
+template <int kThreads>
+__device__ __forceinline__ float block_sum(float v, float* scratch /* >= kThreads/32 + 1 floats */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect scratch from the previous use
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < kThreads / 32; ++i) t += scratch[i];  // same order in every thread -> deterministic
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------ im2col
+// conv1 with stride == kernel (TPT/clip/model.py:224) is a GEMM over non-overlapping patches.
+__global__ void im2col_kernel(const float* __restrict__ img, const int32_t* __restrict__ view_idx, int n_views, int C,
+                              int H, int W, int p, int k_pad, __half* __restrict__ out) {
+  const int gw = W / p, gh = H / p;
+  const int k_real = C * p * p;
+  const int chunks = k_pad / 8;
+  const long long total = static_cast<long long>(n_views) * gh * gw * chunks;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int chunk = static_cast<int>(i % chunks);
+    const long long row = i / chunks;
+    const int px = static_cast<int>(row % gw);
+    const int py = static_cast<int>((row / gw) % gh);
+    const int v = static_cast<int>(row / (gw * gh));
+    const int src = view_idx ? view_idx[v] : v;
+    const float* base = img + static_cast<size_t>(src) * C * H * W;
+    __align__(16) __half h[8];
+    const int k0 = chunk * 8;
+    if ((p % 8) == 0 && k0 + 8 <= k_real) {
+      const int c = k0 / (p * p), rem = k0 % (p * p), ky = rem / p, kx = rem % p;
+      const float4* s = reinterpret_cast<const float4*>(base + (static_cast<size_t>(c) * H + py * p + ky) * W + px * p + kx);
+      const float4 a = __ldg(s), b = __ldg(s + 1);
+      h[0] = __float2half_rn(a.x); h[1] = __float2half_rn(a.y); h[2] = __float2half_rn(a.z); h[3] = __float2half_rn(a.w);
+      h[4] = __float2half_rn(b.x); h[5] = __float2half_rn(b.y); h[6] = __float2half_rn(b.z); h[7] = __float2half_rn(b.w);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = k0 + e;
+        float val = 0.f;
+        if (k < k_real) {
+          const int c = k / (p * p), rem = k % (p * p), ky = rem / p, kx = rem % p;
+          val = __ldg(base + (static_cast<size_t>(c) * H + py * p + ky) * W + px * p + kx);
+        }
+        h[e] = __float2half_rn(val);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + row * k_pad + k0) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+
+int im2col_f16(const float* images, const int32_t* view_idx, int n_views, int C, int H, int W, int patch, int k_pad,
+               __half* out, cudaStream_t stream) {
+  if (n_views <= 0) return set_error(RLCF_ERR_ARG, "im2col: n_views=%d", n_views);
+  if (H % patch || W % patch) return set_error(RLCF_ERR_ARG, "im2col: %dx%d not divisible by patch %d", H, W, patch);
+  if (k_pad % 8 || k_pad < C * patch * patch) return set_error(RLCF_ERR_ARG, "im2col: bad k_pad=%d", k_pad);
+  if ((patch % 8) == 0 && (W % 4) != 0) return set_error(RLCF_ERR_ARG, "im2col: W must be a multiple of 4");
+  const long long total = static_cast<long long>(n_views) * (H / patch) * (W / patch) * (k_pad / 8);
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  im2col_kernel<<<static_cast<int>(blocks), threads, 0, stream>>>(images, view_idx, n_views, C, H, W, patch, k_pad, out);
+  RLCF_CHECK_LAUNCH("im2col");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm fwd
+// One warp per row, row kept in registers (d = 128*NV floats), two-pass mean / variance in fp32
+// (TPT/clip/model.py:157-163: nn.LayerNorm on x.float(), eps = 1e-5).
+template <int NV>
+__device__ __forceinline__ void ln_row_stats(const float4 (&v)[NV], int d, float eps, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  mean = warp_sum(s) / d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + e * e);
+  }
+  rstd = 1.0f / sqrtf(warp_sum(q) / d + eps);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+              const float* __restrict__ beta, long long pstride, int rows_per_set, int M, float eps,
+              __half* __restrict__ out16, float* __restrict__ out32) {
+  constexpr int d = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+  float mean, rstd;
+  ln_row_stats<NV>(v, d, eps, mean, rstd);
+  const long long po = static_cast<long long>(row / rows_per_set) * pstride;
+  const float4* g4 = reinterpret_cast<const float4*>(gamma + po);
+  const float4* b4 = reinterpret_cast<const float4*>(beta + po);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(g4 + lane + 32 * i), b = __ldg(b4 + lane + 32 * i);
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * g.x + b.x;
+    y.y = (v[i].y - mean) * rstd * g.y + b.y;
+    y.z = (v[i].z - mean) * rstd * g.z + b.z;
+    y.w = (v[i].w - mean) * rstd * g.w + b.w;
+    const size_t o = static_cast<size_t>(row) * d + (lane + 32 * i) * 4;
+    if (out16) {
+      __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
+      *reinterpret_cast<uint2*>(out16 + o) =
+          make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+    }
+    if (out32) *reinterpret_cast<float4*>(out32 + o) = y;
+  }
+}
+
+#define RLCF_DISPATCH_NV(d, CALL)                         \
+  switch ((d) / 128) {                                    \
+    case 1: { constexpr int NV = 1; CALL; } break;        \
+    case 2: { constexpr int NV = 2; CALL; } break;        \
+    case 3: { constexpr int NV = 3; CALL; } break;        \
+    case 4: { constexpr int NV = 4; CALL; } break;        \
+    case 5: { constexpr int NV = 5; CALL; } break;        \
+    case 6: { constexpr int NV = 6; CALL; } break;        \
+    case 7: { constexpr int NV = 7; CALL; } break;        \
+    case 8: { constexpr int NV = 8; CALL; } break;        \
+    default: return set_error(RLCF_ERR_ARG, "width %d unsupported (need multiple of 128, <= 1024)", (d)); \
+  }
+
+static int check_width(int d, const char* who) {
+  if (d <= 0 || d % 128 != 0 || d > 1024)
+    return set_error(RLCF_ERR_ARG, "%s: width %d unsupported (need multiple of 128, <= 1024)", who, d);
+  return 0;
+}
+
+int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, long long pstride,
+                  int rows_per_set, int M, int d, float eps, __half* out16, float* out32, cudaStream_t stream) {
+  if (int rc = check_width(d, "layernorm_fwd")) return rc;
+  if (M <= 0 || rows_per_set <= 0 || ldx % 4) return set_error(RLCF_ERR_ARG, "layernorm_fwd: bad M/rows_per_set/ldx");
+  const int blocks = (M + 7) / 8;
+  RLCF_DISPATCH_NV(d, (ln_fwd_kernel<NV><<<blocks, 256, 0, stream>>>(x, ldx, gamma, beta, pstride, rows_per_set, M,
+                                                                      eps, out16, out32)));
+  RLCF_CHECK_LAUNCH("layernorm_fwd");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ embed + ln_pre
+// TPT/clip/model.py:225-229: cat(class_embedding, patches) + positional_embedding, then ln_pre.
+template <int NV>
+__global__ void __launch_bounds__(256)
+embed_lnpre_kernel(const float* __restrict__ patch_out, const float* __restrict__ cls, const float* __restrict__ pos,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, long long pstride,
+                   int rows_per_set, int M, int L, float eps, float* __restrict__ x_pre, float* __restrict__ x) {
+  constexpr int d = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int v = row / L, t = row % L;
+  const float4* src = t == 0 ? reinterpret_cast<const float4*>(cls)
+                             : reinterpret_cast<const float4*>(patch_out + (static_cast<size_t>(v) * (L - 1) + t - 1) * d);
+  const float4* p4 = reinterpret_cast<const float4*>(pos + static_cast<size_t>(t) * d);
+  float4 val[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 a = src[lane + 32 * i], b = __ldg(p4 + lane + 32 * i);
+    val[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+  if (x_pre) {
+    float4* o = reinterpret_cast<float4*>(x_pre + static_cast<size_t>(row) * d);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) o[lane + 32 * i] = val[i];
+  }
+  float mean, rstd;
+  ln_row_stats<NV>(val, d, eps, mean, rstd);
+  const long long po = static_cast<long long>(row / rows_per_set) * pstride;
+  const float4* g4 = reinterpret_cast<const float4*>(gamma + po);
+  const float4* b4 = reinterpret_cast<const float4*>(beta + po);
+  float4* o = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * d);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(g4 + lane + 32 * i), b = __ldg(b4 + lane + 32 * i);
+    o[lane + 32 * i] = make_float4((val[i].x - mean) * rstd * g.x + b.x, (val[i].y - mean) * rstd * g.y + b.y,
+                                   (val[i].z - mean) * rstd * g.z + b.z, (val[i].w - mean) * rstd * g.w + b.w);
+  }
+}
+
+int embed_lnpre(const float* patch_out, const float* cls, const float* pos, const float* gamma, const float* beta,
+                long long pstride, int rows_per_set, int n_views, int L, int d, float eps, float* x_pre, float* x,
+                cudaStream_t stream) {
+  if (int rc = check_width(d, "embed_lnpre")) return rc;
+  if (n_views <= 0 || L < 2 || rows_per_set <= 0) return set_error(RLCF_ERR_ARG, "embed_lnpre: bad shape");
+  const int M = n_views * L;
+  const int blocks = (M + 7) / 8;
+  RLCF_DISPATCH_NV(d, (embed_lnpre_kernel<NV><<<blocks, 256, 0, stream>>>(patch_out, cls, pos, gamma, beta, pstride,
+                                                                           rows_per_set, M, L, eps, x_pre, x)));
+  RLCF_CHECK_LAUNCH("embed_lnpre");
+  return 0;
+}
+
+// TPT/clip/model.py:343-345: token_embedding(text) + positional_embedding
+__global__ void embed_text_kernel(const long long* __restrict__ tokens, const float* __restrict__ emb,
+                                  const float* __restrict__ pos, int n_rows, int L, int d4, float* __restrict__ x) {
+  const long long total = static_cast<long long>(n_rows) * d4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % d4);
+    const long long row = i / d4;
+    const int t = static_cast<int>(row % L);
+    const long long tok = tokens[row];
+    const float4 a = __ldg(reinterpret_cast<const float4*>(emb) + tok * d4 + c);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(pos) + static_cast<long long>(t) * d4 + c);
+    reinterpret_cast<float4*>(x)[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+
+int embed_text(const long long* tokens, const float* tok_emb, const float* pos, int n_seq, int L, int d, float* x,
+               cudaStream_t stream) {
+  if (n_seq <= 0 || L <= 0 || d % 4) return set_error(RLCF_ERR_ARG, "embed_text: bad shape");
+  const long long total = static_cast<long long>(n_seq) * L * (d / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  embed_text_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(tokens, tok_emb, pos, n_seq * L, L, d / 4, x);
+  RLCF_CHECK_LAUNCH("embed_text");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm bwd
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma = sum dy * xhat;  dbeta = sum dy.
+// grid (n_slots, n_sets): block b of set s reduces its contiguous chunk of the set's rows and writes one
+// deterministic partial; the AdamW kernel sums the slots.
+template <int NV, bool kDyF32>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* __restrict__ x, long long ldx,
+              const float* __restrict__ gamma, long long pstride, int rows_per_set, float eps,
+              float* __restrict__ dx, long long lddx, int accumulate, float* __restrict__ partials,
+              long long p_total, long long p_off) {
+  constexpr int d = NV * 128;
+  __shared__ float red[8][d];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int set = blockIdx.y, slot = blockIdx.x, n_slots = gridDim.x;
+  const int rpb = (rows_per_set + n_slots - 1) / n_slots;
+  const int r_begin = slot * rpb;
+  const int r_end = min(rows_per_set, r_begin + rpb);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma + set * pstride);
+  float4 gam[NV], dg[NV], db[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    gam[i] = __ldg(g4 + lane + 32 * i);
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int r = r_begin + warp; r < r_end; r += 8) {
+    const long long row = static_cast<long long>(set) * rows_per_set + r;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+    float4 v[NV], g[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+    if constexpr (kDyF32) {
+      const float4* dr = reinterpret_cast<const float4*>(static_cast<const float*>(dy_) + row * lddy);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) g[i] = dr[lane + 32 * i];
+    } else {
+      const uint2* dr = reinterpret_cast<const uint2*>(static_cast<const __half*>(dy_) + row * lddy);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const uint2 q = dr[lane + 32 * i];
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+        g[i] = make_float4(a.x, a.y, b.x, b.y);
+      }
+    }
+    float mean, rstd;
+    ln_row_stats<NV>(v, d, eps, mean, rstd);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i].x = (v[i].x - mean) * rstd; v[i].y = (v[i].y - mean) * rstd;
+      v[i].z = (v[i].z - mean) * rstd; v[i].w = (v[i].w - mean) * rstd;
+      dg[i].x += g[i].x * v[i].x; dg[i].y += g[i].y * v[i].y; dg[i].z += g[i].z * v[i].z; dg[i].w += g[i].w * v[i].w;
+      db[i].x += g[i].x; db[i].y += g[i].y; db[i].z += g[i].z; db[i].w += g[i].w;
+      g[i].x *= gam[i].x; g[i].y *= gam[i].y; g[i].z *= gam[i].z; g[i].w *= gam[i].w;
+      s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      s2 += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+    if (dx) {
+      float4* o = reinterpret_cast<float4*>(dx + row * lddx);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float4 t;
+        t.x = rstd * (g[i].x - s1 - v[i].x * s2); t.y = rstd * (g[i].y - s1 - v[i].y * s2);
+        t.z = rstd * (g[i].z - s1 - v[i].z * s2); t.w = rstd * (g[i].w - s1 - v[i].w * s2);
+        if (accumulate) {
+          const float4 old = o[lane + 32 * i];
+          t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
+        }
+        o[lane + 32 * i] = t;
+      }
+    }
+  }
+  float* part = partials + (static_cast<long long>(set) * n_slots + slot) * p_total + p_off;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      reinterpret_cast<float4*>(red[warp])[lane + 32 * i] = pass == 0 ? dg[i] : db[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += 256) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][c];
+      part[pass * d + c] = s;
+    }
+  }
+}
+
+int layernorm_bwd(const void* dy, int dy_is_f32, long long lddy, const float* x, long long ldx, const float* gamma,
+                  long long pstride, int rows_per_set, int n_sets, int d, float eps, float* dx, long long lddx,
+                  int accumulate, float* partials, int n_slots, long long p_total, long long p_off,
+                  cudaStream_t stream) {
+  if (int rc = check_width(d, "layernorm_bwd")) return rc;
+  if (rows_per_set <= 0 || n_sets <= 0 || n_slots <= 0 || partials == nullptr)
+    return set_error(RLCF_ERR_ARG, "layernorm_bwd: bad shape");
+  dim3 grid(n_slots, n_sets);
+  if (dy_is_f32) {
+    RLCF_DISPATCH_NV(d, (ln_bwd_kernel<NV, true><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, gamma, pstride,
+                                                                            rows_per_set, eps, dx, lddx, accumulate,
+                                                                            partials, p_total, p_off)));
+  } else {
+    RLCF_DISPATCH_NV(d, (ln_bwd_kernel<NV, false><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, gamma, pstride,
+                                                                             rows_per_set, eps, dx, lddx, accumulate,
+                                                                             partials, p_total, p_off)));
+  }
+  RLCF_CHECK_LAUNCH("layernorm_bwd");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ head fwd
+// ln_post(x[:,0]) @ proj (model.py:235-238) -> f/|f| -> logit_scale * f @ class_feat^T (custom_clip.py:423-432).
+// One block per sequence. Dynamic smem: y[d] + f[E] + scratch[16].
+constexpr int kHeadThreads = 256;
+__global__ void __launch_bounds__(kHeadThreads)
+head_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_idx, long long row_stride,
+                const float* __restrict__ gamma, const float* __restrict__ beta, long long pstride, int seqs_per_set,
+                const float* __restrict__ proj, const float* __restrict__ cls_feat, float logit_scale, int d, int E,
+                int C, float eps, float* __restrict__ feat, float* __restrict__ inv_norm, float* __restrict__ logits) {
+  extern __shared__ float sm[];
+  float* y = sm;
+  float* f = sm + d;
+  float* scratch = f + E;
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long row = row_idx ? row_idx[n] : n * row_stride;
+  const float* xr = x + row * d;
+  float s = 0.f;
+  for (int i = tid; i < d; i += kHeadThreads) { y[i] = xr[i]; s += y[i]; }
+  const float mean = block_sum<kHeadThreads>(s, scratch) / d;
+  float q = 0.f;
+  for (int i = tid; i < d; i += kHeadThreads) { const float a = y[i] - mean; q += a * a; }
+  const float rstd = 1.0f / sqrtf(block_sum<kHeadThreads>(q, scratch) / d + eps);
+  const long long po = static_cast<long long>(n / seqs_per_set) * pstride;
+  for (int i = tid; i < d; i += kHeadThreads) y[i] = (y[i] - mean) * rstd * gamma[po + i] + beta[po + i];
+  __syncthreads();
+  float ss = 0.f;
+  for (int j = tid; j < E; j += kHeadThreads) {
+    float acc = 0.f;
+    for (int i = 0; i < d; ++i) acc = fmaf(y[i], __ldg(proj + static_cast<size_t>(i) * E + j), acc);
+    f[j] = acc;
+    ss += acc * acc;
+  }
+  const float inv = 1.0f / sqrtf(block_sum<kHeadThreads>(ss, scratch));
+  for (int j = tid; j < E; j += kHeadThreads) {
+    f[j] *= inv;
+    if (feat) feat[static_cast<size_t>(n) * E + j] = f[j];
+  }
+  if (inv_norm && tid == 0) inv_norm[n] = inv;
+  __syncthreads();
+  if (logits) {
+    for (int c = warp; c < C; c += kHeadThreads / 32) {
+      const float* t = cls_feat + static_cast<size_t>(c) * E;
+      float acc = 0.f;
+      for (int j = lane; j < E; j += 32) acc = fmaf(f[j], __ldg(t + j), acc);
+      acc = warp_sum(acc);
+      if (lane == 0) logits[static_cast<size_t>(n) * C + c] = logit_scale * acc;
+    }
+  }
+}
+
+int head_fwd(const float* x, const int32_t* row_idx, long long row_stride, const float* gamma, const float* beta,
+             long long pstride, int seqs_per_set, const float* proj, const float* cls_feat, float logit_scale, int n,
+             int d, int E, int C, float eps, float* feat, float* inv_norm, float* logits, cudaStream_t stream) {
+  if (n <= 0 || d <= 0 || E <= 0 || seqs_per_set <= 0) return set_error(RLCF_ERR_ARG, "head_fwd: bad shape");
+  if (logits && (cls_feat == nullptr || C <= 0)) return set_error(RLCF_ERR_ARG, "head_fwd: logits need class_feat");
+  const size_t smem = (d + E + 16) * sizeof(float);
+  head_fwd_kernel<<<n, kHeadThreads, smem, stream>>>(x, row_idx, row_stride, gamma, beta, pstride, seqs_per_set, proj,
+                                                     cls_feat, logit_scale, d, E, C, eps, feat, inv_norm, logits);
+  RLCF_CHECK_LAUNCH("head_fwd");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ entropy select
+// tpt_cls_rl.py:32-35: H = -(softmax * log_softmax).sum(1); argsort ascending; keep the first S.
+__global__ void __launch_bounds__(256)
+entropy_select_kernel(const float* __restrict__ logits, int V, int C, int S, int32_t* __restrict__ sel,
+                      int32_t* __restrict__ sel_global, float* __restrict__ entropy) {
+  extern __shared__ float Hs[];  // [V]
+  const int img = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int v = warp; v < V; v += 8) {
+    const float* r = logits + (static_cast<size_t>(img) * V + v) * C;
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, r[c]);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int c = lane; c < C; c += 32) se += expf(r[c] - mx);
+    const float lse = logf(warp_sum(se));
+    float h = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float lp = r[c] - mx - lse;
+      h += expf(lp) * lp;
+    }
+    h = -warp_sum(h);
+    if (lane == 0) {
+      Hs[v] = h;
+      if (entropy) entropy[static_cast<size_t>(img) * V + v] = h;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float hi = Hs[i];
+    int rank = 0;
+    for (int j = 0; j < V; ++j) {
+      const float hj = Hs[j];
+      rank += (hj < hi) || (hj == hi && j < i);
+    }
+    if (rank < S) {
+      sel[img * S + rank] = i;
+      if (sel_global) sel_global[img * S + rank] = img * V + i;
+    }
+  }
+}
+
+int entropy_select(const float* logits, int n_img, int V, int C, int S, int32_t* sel, int32_t* sel_global,
+                   float* entropy, cudaStream_t stream) {
+  if (n_img <= 0 || V <= 0 || C <= 0 || S <= 0 || S > V) return set_error(RLCF_ERR_ARG, "entropy_select: bad shape");
+  entropy_select_kernel<<<n_img, 256, V * sizeof(float), stream>>>(logits, V, C, S, sel, sel_global, entropy);
+  RLCF_CHECK_LAUNCH("entropy_select");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ reward + loss
+// tpt_cls_rl.py:63-71 and clip_reward.py:111-128,152-165.  One block per image, one warp per selected view.
+constexpr int kMaxK = 8;
+__global__ void __launch_bounds__(256)
+reward_loss_kernel(const float* __restrict__ logits, const int32_t* __restrict__ row_idx,
+                   const float* __restrict__ r_img, const float* __restrict__ r_cls, int S, int K, int C, int Er,
+                   float w, int reward_process, int process_batch, int amplify, float loss_scale,
+                   float* __restrict__ dlogits, int32_t* __restrict__ topk_idx, float* __restrict__ scores_out,
+                   float* __restrict__ rewards_out, float* __restrict__ loss_out) {
+  extern __shared__ float smf[];
+  float* sc = smf;                  // [S*K] scores, then rewards
+  float* lse_s = sc + S * K;        // [S]
+  float* mx_s = lse_s + S;          // [S]
+  float* ce = mx_s + S;             // [S*K]
+  int* idx = reinterpret_cast<int*>(ce + S * K);  // [S*K]
+  const int img = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int s = warp; s < S; s += 8) {
+    const int n = img * S + s;
+    const float* r = logits + static_cast<size_t>(row_idx ? row_idx[n] : n) * C;
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, r[c]);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int c = lane; c < C; c += 32) se += expf(r[c] - mx);
+    const float lse = logf(warp_sum(se));
+    int chosen[kMaxK];
+    for (int k = 0; k < K; ++k) {
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int c = lane; c < C; c += 32) {
+        bool taken = false;
+        for (int j = 0; j < k; ++j) taken |= (chosen[j] == c);
+        const float val = r[c];
+        if (!taken && (val > bv || (val == bv && c < bi))) { bv = val; bi = c; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      chosen[k] = bi;
+      // CLIPScore = max(0, w * <t_cls, f_img>)   (clip_reward.py:119-126)
+      const float* t = r_cls + static_cast<size_t>(bi) * Er;
+      const float* f = r_img + static_cast<size_t>(n) * Er;
+      float acc = 0.f;
+      for (int j = lane; j < Er; j += 32) acc = fmaf(__ldg(t + j), __ldg(f + j), acc);
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        sc[s * K + k] = fmaxf(w * acc, 0.f);
+        ce[s * K + k] = (mx + lse) - bv;
+        idx[s * K + k] = bi;
+      }
+    }
+    if (lane == 0) { lse_s[s] = lse; mx_s[s] = mx; }
+  }
+  __syncthreads();
+  if (scores_out)
+    for (int i = threadIdx.x; i < S * K; i += blockDim.x) scores_out[static_cast<size_t>(img) * S * K + i] = sc[i];
+  __syncthreads();
+  // rewards_post_process (clip_reward.py:152-165); torch.std is the unbiased estimator
+  if (threadIdx.x == 0 && reward_process) {
+    if (process_batch) {
+      const int n = S * K;
+      if (n > 1) {
+        float m = 0.f;
+        for (int i = 0; i < n; ++i) m += sc[i];
+        m /= n;
+        float sd = 1.f;
+        if (amplify) {
+          float q = 0.f;
+          for (int i = 0; i < n; ++i) q += (sc[i] - m) * (sc[i] - m);
+          sd = sqrtf(q / (n - 1)) + 1e-5f;
+        }
+        for (int i = 0; i < n; ++i) sc[i] = (sc[i] - m) / sd;
+      }
+    } else if (K > 1) {
+      for (int s = 0; s < S; ++s) {
+        float m = 0.f;
+        for (int k = 0; k < K; ++k) m += sc[s * K + k];
+        m /= K;
+        float sd = 1.f;
+        if (amplify) {
+          float q = 0.f;
+          for (int k = 0; k < K; ++k) q += (sc[s * K + k] - m) * (sc[s * K + k] - m);
+          sd = sqrtf(q / (K - 1)) + 1e-5f;
+        }
+        for (int k = 0; k < K; ++k) sc[s * K + k] = (sc[s * K + k] - m) / sd;
+      }
+    }
+  }
+  __syncthreads();
+  const float inv_n = 1.f / (S * K);
+  if (threadIdx.x == 0 && loss_out) {
+    float l = 0.f;
+    for (int i = 0; i < S * K; ++i) l += sc[i] * ce[i];
+    loss_out[img] = l * inv_n;
+  }
+  for (int i = threadIdx.x; i < S * K; i += blockDim.x) {
+    if (rewards_out) rewards_out[static_cast<size_t>(img) * S * K + i] = sc[i];
+    if (topk_idx) topk_idx[static_cast<size_t>(img) * S * K + i] = idx[i];
+  }
+  // dL/dlogit[s,c] = (1/(S K)) * sum_k r[s,k] * (softmax[s,c] - [c == idx[s,k]])
+  for (int s = warp; s < S; s += 8) {
+    const int n = img * S + s;
+    const float* r = logits + static_cast<size_t>(row_idx ? row_idx[n] : n) * C;
+    float rs = 0.f;
+    for (int k = 0; k < K; ++k) rs += sc[s * K + k];
+    const float off = mx_s[s] + lse_s[s];
+    float* o = dlogits + static_cast<size_t>(n) * C;
+    for (int c = lane; c < C; c += 32) {
+      float g = rs * expf(r[c] - off);
+      for (int k = 0; k < K; ++k) g -= (idx[s * K + k] == c) ? sc[s * K + k] : 0.f;
+      o[c] = g * inv_n * loss_scale;
+    }
+  }
+}
+
+int reward_loss(const float* logits, const int32_t* row_idx, const float* r_img, const float* r_cls, int n_img, int S,
+                int K, int C, int Er, float w, int reward_process, int process_batch, int amplify, float loss_scale,
+                float* dlogits, int32_t* topk_idx, float* scores, float* rewards, float* loss, cudaStream_t stream) {
+  if (n_img <= 0 || S <= 0 || K <= 0 || K > kMaxK || K > C || Er <= 0)
+    return set_error(RLCF_ERR_ARG, "reward_loss: bad shape (K must be 1..%d)", kMaxK);
+  const size_t smem = (static_cast<size_t>(3) * S * K + 2 * S) * sizeof(float);
+  if (smem > 48 * 1024) return set_error(RLCF_ERR_ARG, "reward_loss: S*K too large");
+  reward_loss_kernel<<<n_img, 256, smem, stream>>>(logits, row_idx, r_img, r_cls, S, K, C, Er, w, reward_process,
+                                                   process_batch, amplify, loss_scale, dlogits, topk_idx, scores,
+                                                   rewards, loss);
+  RLCF_CHECK_LAUNCH("reward_loss");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ TPT entropy loss
+// tpt_cls_rl.py:38-44: avg_logits = logsumexp_s(log_softmax(x_s)) - log S ; loss = -(avg * exp(avg)).sum()
+// With p[s,c] = softmax, Pbar[c] = sum_s p[s,c]: exp(avg_c) = Pbar_c / S and
+// d loss / d x[s,c] = p[s,c] * (G_c / Pbar_c - sum_c' G_c' p[s,c'] / Pbar_c'),  G_c = -(1 + avg_c) * Pbar_c / S.
+__global__ void __launch_bounds__(256)
+avg_entropy_kernel(const float* __restrict__ logits, const int32_t* __restrict__ row_idx, int S, int C,
+                   float loss_scale, float* __restrict__ dlogits, float* __restrict__ loss_out) {
+  extern __shared__ float smf[];
+  float* off = smf;        // [S]  max + lse per view
+  float* q = off + S;      // [C]  G_c / Pbar_c
+  float* t2 = q + C;       // [S]
+  float* scratch = t2 + S; // [16]
+  const int img = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int s = warp; s < S; s += 8) {
+    const int n = img * S + s;
+    const float* r = logits + static_cast<size_t>(row_idx ? row_idx[n] : n) * C;
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, r[c]);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int c = lane; c < C; c += 32) se += expf(r[c] - mx);
+    se = warp_sum(se);
+    if (lane == 0) off[s] = mx + logf(se);
+  }
+  __syncthreads();
+  float lsum = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float pb = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const int n = img * S + s;
+      pb += expf(logits[static_cast<size_t>(row_idx ? row_idx[n] : n) * C + c] - off[s]);
+    }
+    const float e = pb / S;
+    const float avg = fmaxf(logf(e), -3.402823466e38f);
+    lsum -= avg * e;
+    q[c] = pb > 0.f ? -(1.f + avg) / S : 0.f;
+  }
+  const float total = block_sum<256>(lsum, scratch);
+  if (threadIdx.x == 0 && loss_out) loss_out[img] = total;
+  __syncthreads();
+  for (int s = warp; s < S; s += 8) {
+    const int n = img * S + s;
+    const float* r = logits + static_cast<size_t>(row_idx ? row_idx[n] : n) * C;
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a += q[c] * expf(r[c] - off[s]);
+    a = warp_sum(a);
+    if (lane == 0) t2[s] = a;
+  }
+  __syncthreads();
+  for (int s = warp; s < S; s += 8) {
+    const int n = img * S + s;
+    const float* r = logits + static_cast<size_t>(row_idx ? row_idx[n] : n) * C;
+    float* o = dlogits + static_cast<size_t>(n) * C;
+    for (int c = lane; c < C; c += 32) o[c] = loss_scale * expf(r[c] - off[s]) * (q[c] - t2[s]);
+  }
+}
+
+int avg_entropy_loss(const float* logits, const int32_t* row_idx, int n_img, int S, int C, float loss_scale,
+                     float* dlogits, float* loss, cudaStream_t stream) {
+  if (n_img <= 0 || S <= 0 || C <= 0) return set_error(RLCF_ERR_ARG, "avg_entropy_loss: bad shape");
+  const size_t smem = (static_cast<size_t>(2) * S + C + 16) * sizeof(float);
+  avg_entropy_kernel<<<n_img, 256, smem, stream>>>(logits, row_idx, S, C, loss_scale, dlogits, loss);
+  RLCF_CHECK_LAUNCH("avg_entropy_loss");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ head bwd
+// Reverse of head_fwd for the S selected views of one image (one block per image; views in sequence so the
+// ln_post parameter gradient is reduced in a fixed order).
+__global__ void __launch_bounds__(kHeadThreads)
+head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ x, const int32_t* __restrict__ row_idx,
+                long long row_stride, const float* __restrict__ gamma, long long pstride,
+                const float* __restrict__ proj, const float* __restrict__ cls_feat, float logit_scale,
+                const float* __restrict__ feat, const float* __restrict__ inv_norm, int S, int d, int E, int C,
+                float eps, float* __restrict__ dres, float* __restrict__ partials, int n_slots, long long p_total,
+                long long p_off) {
+  extern __shared__ float sm[];
+  float* dl = sm;            // [C]
+  float* df = dl + C;        // [E]
+  float* dy = df + E;        // [d]
+  float* xh = dy + d;        // [d]
+  float* scratch = xh + d;   // [16]
+  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* gam = gamma + img * pstride;
+  float dg[4] = {0.f, 0.f, 0.f, 0.f}, db[4] = {0.f, 0.f, 0.f, 0.f};  // d <= 1024 -> <= 4 columns per thread
+  for (int s = 0; s < S; ++s) {
+    const int n = img * S + s;
+    __syncthreads();
+    for (int c = tid; c < C; c += kHeadThreads) dl[c] = dlogits[static_cast<size_t>(n) * C + c];
+    __syncthreads();
+    // d fhat = logit_scale * dlogits @ class_feat
+    float dot = 0.f;
+    for (int j = tid; j < E; j += kHeadThreads) {
+      float acc = 0.f;
+      for (int c = 0; c < C; ++c) acc = fmaf(dl[c], __ldg(cls_feat + static_cast<size_t>(c) * E + j), acc);
+      acc *= logit_scale;
+      df[j] = acc;
+      dot += acc * feat[static_cast<size_t>(n) * E + j];
+    }
+    dot = block_sum<kHeadThreads>(dot, scratch);
+    const float inv = inv_norm[n];
+    // d f = (d fhat - fhat * <fhat, d fhat>) / |f|
+    for (int j = tid; j < E; j += kHeadThreads) df[j] = (df[j] - feat[static_cast<size_t>(n) * E + j] * dot) * inv;
+    __syncthreads();
+    // d y = d f @ proj^T
+    for (int i = warp; i < d; i += kHeadThreads / 32) {
+      const float* pr = proj + static_cast<size_t>(i) * E;
+      float acc = 0.f;
+      for (int j = lane; j < E; j += 32) acc = fmaf(df[j], __ldg(pr + j), acc);
+      acc = warp_sum(acc);
+      if (lane == 0) dy[i] = acc;
+    }
+    // ln_post backward on the class-token row
+    const long long row = row_idx ? row_idx[n] : n * row_stride;
+    const float* xr = x + row * d;
+    float sx = 0.f;
+    for (int i = tid; i < d; i += kHeadThreads) { xh[i] = xr[i]; sx += xh[i]; }
+    const float mean = block_sum<kHeadThreads>(sx, scratch) / d;
+    float sq = 0.f;
+    for (int i = tid; i < d; i += kHeadThreads) { const float a = xh[i] - mean; sq += a * a; }
+    const float rstd = 1.0f / sqrtf(block_sum<kHeadThreads>(sq, scratch) / d + eps);
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = tid; i < d; i += kHeadThreads) {
+      xh[i] = (xh[i] - mean) * rstd;
+      const float g = dy[i] * gam[i];
+      s1 += g;
+      s2 += g * xh[i];
+    }
+    s1 = block_sum<kHeadThreads>(s1, scratch) / d;
+    s2 = block_sum<kHeadThreads>(s2, scratch) / d;
+    float* o = dres + row * d;
+    int q = 0;
+    for (int i = tid; i < d; i += kHeadThreads, ++q) {
+      const float g = dy[i] * gam[i];
+      o[i] = rstd * (g - s1 - xh[i] * s2);
+      dg[q] += dy[i] * xh[i];
+      db[q] += dy[i];
+    }
+  }
+  float* part = partials + (static_cast<long long>(img) * n_slots) * p_total + p_off;
+  int q = 0;
+  for (int i = tid; i < d; i += kHeadThreads, ++q) {
+    part[i] = dg[q];
+    part[d + i] = db[q];
+  }
+}
+
+int head_bwd(const float* dlogits, const float* x, const int32_t* row_idx, long long row_stride, const float* gamma,
+             long long pstride, const float* proj, const float* cls_feat, float logit_scale, const float* feat,
+             const float* inv_norm, int n_img, int S, int d, int E, int C, float eps, float* dres, float* partials,
+             int n_slots, long long p_total, long long p_off, cudaStream_t stream) {
+  if (n_img <= 0 || S <= 0 || d <= 0 || d > 1024 || E <= 0 || C <= 0)
+    return set_error(RLCF_ERR_ARG, "head_bwd: bad shape");
+  const size_t smem = (static_cast<size_t>(C) + E + 2 * d + 16) * sizeof(float);
+  if (smem > 48 * 1024) return set_error(RLCF_ERR_ARG, "head_bwd: C too large for shared memory");
+  head_bwd_kernel<<<n_img, kHeadThreads, smem, stream>>>(dlogits, x, row_idx, row_stride, gamma, pstride, proj,
+                                                         cls_feat, logit_scale, feat, inv_norm, S, d, E, C, eps, dres,
+                                                         partials, n_slots, p_total, p_off);
+  RLCF_CHECK_LAUNCH("head_bwd");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ AdamW
+// torch.optim.AdamW single-tensor update order (decoupled decay first, then bias-corrected Adam).
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ partials,
+             int n_slots, long long p_total, long long total, float lr, float b1, float b2, float eps, float wd,
+             float bc1, float bc2_sqrt, float inv_scale, float* __restrict__ grad_out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long set = i / p_total, j = i % p_total;
+    const float* pp = partials + set * n_slots * p_total + j;
+    float g = 0.f;
+    for (int s = 0; s < n_slots; ++s) g += pp[s * p_total];
+    g *= inv_scale;
+    if (grad_out) grad_out[i] = g;
+    float w = p[i] * (1.f - lr * wd);
+    const float mi = m[i] + (g - m[i]) * (1.f - b1);  // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v[i] * b2 + (1.f - b2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    w -= (lr / bc1) * (mi / denom);
+    p[i] = w;
+  }
+}
+
+int adamw_step(float* params, float* m, float* v, const float* partials, int n_sets, int n_slots, long long p_total,
+               float lr, float b1, float b2, float eps, float wd, int step, float loss_scale, float* grad_out,
+               cudaStream_t stream) {
+  if (n_sets <= 0 || n_slots <= 0 || p_total <= 0 || step < 1) return set_error(RLCF_ERR_ARG, "adamw: bad shape");
+  const long long total = n_sets * p_total;
+  const double bc1 = 1.0 - pow(static_cast<double>(b1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(b2), step);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adamw_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(params, m, v, partials, n_slots, p_total, total, lr, b1,
+                                                             b2, eps, wd, static_cast<float>(bc1),
+                                                             static_cast<float>(sqrt(bc2)), 1.f / loss_scale, grad_out);
+  RLCF_CHECK_LAUNCH("adamw");
+  return 0;
+}
+
+__global__ void reset_params_kernel(const float* __restrict__ init, float* __restrict__ p, float* __restrict__ m,
+                                    float* __restrict__ v, long long p_total, long long total) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    p[i] = init[i % p_total];
+    if (m) m[i] = 0.f;
+    if (v) v[i] = 0.f;
+  }
+}
+
+int reset_params(const float* init, float* params, float* m, float* v, int n_sets, long long p_total,
+                 cudaStream_t stream) {
+  if (n_sets <= 0 || p_total <= 0) return set_error(RLCF_ERR_ARG, "reset_params: bad shape");
+  const long long total = n_sets * p_total;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  reset_params_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(init, params, m, v, p_total, total);
+  RLCF_CHECK_LAUNCH("reset_params");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ weight prep
+__global__ void cast_f16_kernel(const float* __restrict__ in, long long rows, long long cols, long long ld_in,
+                                __half* __restrict__ out, long long ld_out) {
+  const long long total = rows * ld_out;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / ld_out, c = i % ld_out;
+    out[i] = __float2half_rn(c < cols ? in[r * ld_in + c] : 0.f);
+  }
+}
+
+int cast_f16(const float* in, long long rows, long long cols, long long ld_in, __half* out, long long ld_out,
+             cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0 || ld_out < cols) return set_error(RLCF_ERR_ARG, "cast_f16: bad shape");
+  long long blocks = (rows * ld_out + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cast_f16_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(in, rows, cols, ld_in, out, ld_out);
+  RLCF_CHECK_LAUNCH("cast_f16");
+  return 0;
+}
+
+__global__ void transpose_cast_kernel(const float* __restrict__ in, int rows, int cols, __half* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? in[static_cast<size_t>(r) * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) out[static_cast<size_t>(c) * rows + r] = __float2half_rn(tile[threadIdx.x][j]);
+  }
+}
+
+int transpose_cast_f16(const float* in, int rows, int cols, __half* out, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return set_error(RLCF_ERR_ARG, "transpose_cast_f16: bad shape");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_cast_kernel<<<grid, block, 0, stream>>>(in, rows, cols, out);
+  RLCF_CHECK_LAUNCH("transpose_cast_f16");
+  return 0;
+}
+
+}  // namespace rlcf

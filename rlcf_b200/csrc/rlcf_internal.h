@@ -1,0 +1,45 @@
+// Internal declarations shared by the .cu translation units of librlcf_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+
+#include "../../include/rlcf_b200.h"
+
+namespace rlcf {
+
+// Error codes (RLCF_OK, RLCF_ERR_*) and epilogue ids (RLCF_EPI_*) come from the public header.
+enum : int {
+  EPI_F16 = RLCF_EPI_F16,
+  EPI_GELU_F16 = RLCF_EPI_GELU_F16,
+  EPI_RESID_F32 = RLCF_EPI_RESID_F32,
+  EPI_GELU_BWD_F16 = RLCF_EPI_GELU_BWD_F16,
+  EPI_F32 = RLCF_EPI_F32,
+  EPI_COUNT = 5,
+};
+
+int set_error(int code, const char* fmt, ...);
+void count_launch();
+int sm_count();
+int gemm_cta_group();
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_tiled();
+
+int gemm_f16(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, int epi, float alpha,
+             const float* bias, const float* resid, const __half* aux_in, __half* aux_out, void* out, int ldo,
+             cudaStream_t stream);
+
+// Checks the launch of the kernel that was just enqueued.
+#define RLCF_CHECK_LAUNCH(name)                                                                 \
+  do {                                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                                       \
+    if (e__ != cudaSuccess) return ::rlcf::set_error(RLCF_ERR_CUDA, name ": %s", cudaGetErrorString(e__)); \
+    ::rlcf::count_launch();                                                                     \
+  } while (0)
+
+}  // namespace rlcf

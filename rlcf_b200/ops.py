@@ -1,0 +1,166 @@
+"""Tensor-level wrappers over the C ABI (one Python function per exported kernel).
+
+These only validate devices/dtypes/contiguity and forward raw pointers; all arithmetic happens in
+librlcf_b200.so on the current CUDA stream.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import EPI_F16, EPI_F32, EPI_GELU_BWD_F16, EPI_GELU_F16, EPI_RESID_F32, call, ptr, stream  # noqa: F401
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise _lib.RlcfError(f"{name} must be a CUDA tensor (rlcf_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.RlcfError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.RlcfError(f"{name} must be contiguous")
+
+
+def gemm(a, b, out, epilogue=EPI_F16, bias=None, resid=None, aux_in=None, aux_out=None, alpha=1.0, M=None):
+    """out[M,N] = epilogue(alpha * a[M,K] @ b[N,K]^T).  a, b fp16 row-major; M may restrict the rows used."""
+    _chk(a, torch.float16, "a"); _chk(b, torch.float16, "b")
+    _chk(bias, torch.float32, "bias"); _chk(resid, torch.float32, "resid")
+    _chk(aux_in, torch.float16, "aux_in"); _chk(aux_out, torch.float16, "aux_out")
+    m = a.shape[0] if M is None else M
+    k = a.shape[1]
+    n = b.shape[0]
+    if b.shape[1] != k:
+        raise _lib.RlcfError(f"gemm: K mismatch {a.shape} vs {b.shape}")
+    want = torch.float32 if epilogue in (EPI_RESID_F32, EPI_F32) else torch.float16
+    _chk(out, want, "out")
+    if out.shape[-1] != n or out.shape[0] < m:
+        raise _lib.RlcfError(f"gemm: out shape {tuple(out.shape)} does not fit [{m},{n}]")
+    call("rlcf_gemm_f16", ptr(a), a.stride(0), ptr(b), b.stride(0), m, n, k, epilogue, float(alpha), ptr(bias),
+         ptr(resid), ptr(aux_in), ptr(aux_out), ptr(out), out.stride(0), stream())
+    return out
+
+
+def im2col(images, view_idx, n_views, patch, k_pad, out):
+    _chk(images, torch.float32, "images"); _chk(view_idx, torch.int32, "view_idx"); _chk(out, torch.float16, "out")
+    _, c, h, w = images.shape
+    call("rlcf_im2col_f16", ptr(images), ptr(view_idx), n_views, c, h, w, patch, k_pad, ptr(out), stream())
+    return out
+
+
+def embed_lnpre(patch_out, cls, pos, gamma, beta, param_stride, rows_per_set, n_views, L, d, x, x_pre=None, eps=1e-5):
+    _chk(patch_out, torch.float32, "patch_out"); _chk(x, torch.float32, "x"); _chk(x_pre, torch.float32, "x_pre")
+    call("rlcf_embed_lnpre", ptr(patch_out), ptr(cls), ptr(pos), ptr(gamma), ptr(beta), param_stride, rows_per_set,
+         n_views, L, d, eps, ptr(x_pre), ptr(x), stream())
+    return x
+
+
+def embed_text(tokens, tok_emb, pos, x):
+    _chk(tokens, torch.int64, "tokens"); _chk(tok_emb, torch.float32, "tok_emb"); _chk(x, torch.float32, "x")
+    n, L = tokens.shape
+    call("rlcf_embed_text", ptr(tokens), ptr(tok_emb), ptr(pos), n, L, tok_emb.shape[1], ptr(x), stream())
+    return x
+
+
+def layernorm_fwd(x, gamma, beta, M, d, out16=None, out32=None, ldx=None, param_stride=0, rows_per_set=None,
+                  eps=1e-5):
+    _chk(x, torch.float32, "x"); _chk(out16, torch.float16, "out16"); _chk(out32, torch.float32, "out32")
+    call("rlcf_layernorm_fwd", ptr(x), d if ldx is None else ldx, ptr(gamma), ptr(beta), param_stride,
+         M if rows_per_set is None else rows_per_set, M, d, eps, ptr(out16), ptr(out32), stream())
+
+
+def layernorm_bwd(dy, x, gamma, rows_per_set, n_sets, d, partials, n_slots, p_total, p_off, dx=None, accumulate=True,
+                  param_stride=0, lddy=None, ldx=None, lddx=None, eps=1e-5):
+    _chk(x, torch.float32, "x"); _chk(partials, torch.float32, "partials"); _chk(dx, torch.float32, "dx")
+    is32 = dy.dtype == torch.float32
+    call("rlcf_layernorm_bwd", ptr(dy), int(is32), d if lddy is None else lddy, ptr(x), d if ldx is None else ldx,
+         ptr(gamma), param_stride, rows_per_set, n_sets, d, eps, ptr(dx), d if lddx is None else lddx,
+         int(accumulate), ptr(partials), n_slots, p_total, p_off, stream())
+
+
+def attention_fwd(qkv, n_seq, L, heads, out, causal=False, lse=None):
+    _chk(qkv, torch.float16, "qkv"); _chk(out, torch.float16, "out"); _chk(lse, torch.float32, "lse")
+    call("rlcf_attention_fwd", ptr(qkv), n_seq, L, heads, int(causal), ptr(out), ptr(lse), stream())
+    return out
+
+
+def attention_bwd(qkv, out, dout, lse, n_seq, L, heads, dqkv, causal=False):
+    _chk(qkv, torch.float16, "qkv"); _chk(out, torch.float16, "out"); _chk(dout, torch.float16, "dout")
+    _chk(lse, torch.float32, "lse"); _chk(dqkv, torch.float16, "dqkv")
+    call("rlcf_attention_bwd", ptr(qkv), ptr(out), ptr(dout), ptr(lse), n_seq, L, heads, int(causal), ptr(dqkv),
+         stream())
+    return dqkv
+
+
+def head_fwd(x, gamma, beta, proj, n, d, E, feat=None, inv_norm=None, logits=None, class_feat=None, logit_scale=1.0,
+             row_idx=None, row_stride=1, param_stride=0, seqs_per_set=None, eps=1e-5):
+    _chk(x, torch.float32, "x"); _chk(proj, torch.float32, "proj"); _chk(class_feat, torch.float32, "class_feat")
+    _chk(row_idx, torch.int32, "row_idx"); _chk(feat, torch.float32, "feat"); _chk(logits, torch.float32, "logits")
+    C = 0 if class_feat is None else class_feat.shape[0]
+    call("rlcf_head_fwd", ptr(x), ptr(row_idx), row_stride, ptr(gamma), ptr(beta), param_stride,
+         n if seqs_per_set is None else seqs_per_set, ptr(proj), ptr(class_feat), float(logit_scale), n, d, E, C, eps,
+         ptr(feat), ptr(inv_norm), ptr(logits), stream())
+
+
+def entropy_select(logits, n_img, V, C, S, sel, sel_global=None, entropy=None):
+    _chk(logits, torch.float32, "logits"); _chk(sel, torch.int32, "sel"); _chk(sel_global, torch.int32, "sel_global")
+    call("rlcf_entropy_select", ptr(logits), n_img, V, C, S, ptr(sel), ptr(sel_global), ptr(entropy), stream())
+
+
+def reward_loss(logits, row_idx, reward_img, reward_cls, n_img, S, K, C, dlogits, clipscore_weight=2.5,
+                reward_process=True, process_batch=False, amplify=False, loss_scale=1.0, topk_idx=None, scores=None,
+                rewards=None, loss=None):
+    _chk(logits, torch.float32, "logits"); _chk(row_idx, torch.int32, "row_idx")
+    _chk(reward_img, torch.float32, "reward_img"); _chk(reward_cls, torch.float32, "reward_cls")
+    _chk(dlogits, torch.float32, "dlogits"); _chk(topk_idx, torch.int32, "topk_idx")
+    call("rlcf_reward_loss", ptr(logits), ptr(row_idx), ptr(reward_img), ptr(reward_cls), n_img, S, K, C,
+         reward_cls.shape[1], float(clipscore_weight), int(bool(reward_process)), int(bool(process_batch)),
+         int(bool(amplify)), float(loss_scale), ptr(dlogits), ptr(topk_idx), ptr(scores), ptr(rewards), ptr(loss),
+         stream())
+
+
+def avg_entropy_loss(logits, row_idx, n_img, S, C, dlogits, loss=None, loss_scale=1.0):
+    _chk(logits, torch.float32, "logits"); _chk(dlogits, torch.float32, "dlogits")
+    call("rlcf_avg_entropy_loss", ptr(logits), ptr(row_idx), n_img, S, C, float(loss_scale), ptr(dlogits), ptr(loss),
+         stream())
+
+
+def head_bwd(dlogits, x, gamma, proj, class_feat, logit_scale, feat, inv_norm, n_img, S, d, E, C, dres, partials,
+             n_slots, p_total, p_off, row_idx=None, row_stride=1, param_stride=0, eps=1e-5):
+    _chk(dlogits, torch.float32, "dlogits"); _chk(x, torch.float32, "x"); _chk(dres, torch.float32, "dres")
+    call("rlcf_head_bwd", ptr(dlogits), ptr(x), ptr(row_idx), row_stride, ptr(gamma), param_stride, ptr(proj),
+         ptr(class_feat), float(logit_scale), ptr(feat), ptr(inv_norm), n_img, S, d, E, C, eps, ptr(dres),
+         ptr(partials), n_slots, p_total, p_off, stream())
+
+
+def adamw_step(params, m, v, partials, n_sets, n_slots, p_total, lr, step, beta1=0.9, beta2=0.999, eps=1e-8,
+               weight_decay=1e-2, loss_scale=1.0, grad_out=None):
+    for t, nm in ((params, "params"), (m, "m"), (v, "v"), (partials, "partials"), (grad_out, "grad_out")):
+        _chk(t, torch.float32, nm)
+    call("rlcf_adamw_step", ptr(params), ptr(m), ptr(v), ptr(partials), n_sets, n_slots, p_total, float(lr),
+         float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(loss_scale), ptr(grad_out),
+         stream())
+
+
+def reset_params(init, params, m, v, n_sets, p_total):
+    _chk(init, torch.float32, "init"); _chk(params, torch.float32, "params")
+    call("rlcf_reset_params", ptr(init), ptr(params), ptr(m), ptr(v), n_sets, p_total, stream())
+
+
+def cast_f16(src, k_pad=None):
+    """fp32 [rows, cols] -> fp16 [rows, k_pad] (zero padded)."""
+    _chk(src, torch.float32, "src")
+    rows, cols = src.shape
+    ld = cols if k_pad is None else k_pad
+    out = torch.empty(rows, ld, dtype=torch.float16, device=src.device)
+    call("rlcf_cast_f16", ptr(src), rows, cols, cols, ptr(out), ld, stream())
+    return out
+
+
+def transpose_cast_f16(src):
+    """fp32 [rows, cols] -> fp16 [cols, rows]."""
+    _chk(src, torch.float32, "src")
+    rows, cols = src.shape
+    out = torch.empty(cols, rows, dtype=torch.float16, device=src.device)
+    call("rlcf_transpose_cast_f16", ptr(src), rows, cols, ptr(out), stream())
+    return out

@@ -1,0 +1,340 @@
+"""Per-kernel numerics: every exported CUDA kernel against a plain PyTorch fp32 restatement of the same op.
+
+Tolerances: fp16-operand tensor-core kernels are compared with an fp32 reference computed from the SAME
+fp16-rounded inputs, so the only differences are accumulation order and the final fp16 rounding of the output
+(<= 2^-10 relative); pure-fp32 kernels are held to 1e-5.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from rlcf_b200 import _lib, ops  # noqa: E402
+
+
+import os
+
+_CGS = [int(c) for c in os.environ.get("RLCF_TEST_CG", "1,2").split(",") if c]
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-12)).item()
+
+
+def quick_gelu(x):
+    return x * torch.sigmoid(1.702 * x)
+
+
+GEMM_SHAPES = [
+    (128, 256, 64), (256, 256, 128), (300, 768, 768), (1182, 2304, 768), (197, 768, 3072), (1542, 1024, 4096),
+    (64, 512, 640), (12608, 768, 768), (5000, 3072, 768), (1000, 32, 64), (4096, 96, 256),
+]
+
+
+@pytest.mark.parametrize("cg", _CGS)
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_plain(cg, M, N, K):
+    torch.manual_seed(M + N + K)
+    assert _lib.set_gemm_cta_group(cg) == cg
+    a = torch.randn(M, K, device=_dev()).half()
+    b = torch.randn(N, K, device=_dev()).half()
+    out = torch.empty(M, N, device=_dev(), dtype=torch.float32)
+    ops.gemm(a, b, out, epilogue=ops.EPI_F32)
+    ref = a.float() @ b.float().t()
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 2e-5, (cg, M, N, K)
+
+
+@pytest.mark.parametrize("cg", _CGS)
+def test_gemm_epilogues(cg):
+    torch.manual_seed(0)
+    _lib.set_gemm_cta_group(cg)
+    M, N, K = 700, 512, 256
+    a = (torch.randn(M, K, device=_dev()) * 0.5).half()
+    b = (torch.randn(N, K, device=_dev()) * 0.1).half()
+    bias = torch.randn(N, device=_dev())
+    resid = torch.randn(M, N, device=_dev())
+    acc = a.float() @ b.float().t()
+    # bias -> fp16
+    out16 = torch.empty(M, N, device=_dev(), dtype=torch.float16)
+    ops.gemm(a, b, out16, epilogue=ops.EPI_F16, bias=bias)
+    assert _rel(out16, acc + bias) < 1e-3
+    # alpha
+    ops.gemm(a, b, out16, epilogue=ops.EPI_F16, alpha=0.25)
+    assert _rel(out16, 0.25 * acc) < 1e-3
+    # QuickGELU with pre-activation save
+    pre = torch.empty_like(out16)
+    ops.gemm(a, b, out16, epilogue=ops.EPI_GELU_F16, bias=bias, aux_out=pre)
+    assert _rel(pre, acc + bias) < 1e-3
+    assert _rel(out16, quick_gelu(acc + bias)) < 1e-3
+    # residual fp32 (in place)
+    x = resid.clone()
+    ops.gemm(a, b, x, epilogue=ops.EPI_RESID_F32, bias=bias, resid=x)
+    assert _rel(x, acc + bias + resid) < 1e-5
+    # QuickGELU backward
+    u = torch.randn(M, N, device=_dev()).half()
+    uf = u.float().requires_grad_(True)
+    quick_gelu(uf).backward(acc)
+    ops.gemm(a, b, out16, epilogue=ops.EPI_GELU_BWD_F16, aux_in=u)
+    assert _rel(out16, uf.grad) < 2e-3
+    # row-limited launch into a larger buffer with a leading dimension
+    big = torch.zeros(M + 50, N, device=_dev(), dtype=torch.float32)
+    ops.gemm(a, b, big, epilogue=ops.EPI_F32, M=M)
+    assert _rel(big[:M], acc) < 2e-5 and big[M:].abs().max().item() == 0.0
+
+
+def test_gemm_rejects_bad_shapes():
+    a = torch.zeros(8, 64, device=_dev(), dtype=torch.float16)
+    b = torch.zeros(24, 64, device=_dev(), dtype=torch.float16)
+    out = torch.zeros(8, 24, device=_dev(), dtype=torch.float32)
+    with pytest.raises(_lib.RlcfError):
+        ops.gemm(a, b, out, epilogue=ops.EPI_F32)  # N % 32 != 0
+
+
+@pytest.mark.parametrize("d", [128, 512, 768, 1024])
+def test_layernorm_fwd_bwd(d):
+    torch.manual_seed(d)
+    n_sets, rows_per_set = 3, 37
+    M = n_sets * rows_per_set
+    x = torch.randn(M, d, device=_dev()) * 2 + 0.5
+    params = torch.randn(n_sets, 2 * d, device=_dev())
+    out16 = torch.empty(M, d, device=_dev(), dtype=torch.float16)
+    out32 = torch.empty(M, d, device=_dev())
+    ops.layernorm_fwd(x, params, params[:, d:], M, d, out16=out16, out32=out32, param_stride=2 * d,
+                      rows_per_set=rows_per_set)
+    xr = x.view(n_sets, rows_per_set, d).clone().requires_grad_(True)
+    pr = params.clone().requires_grad_(True)
+    ref = torch.stack([torch.nn.functional.layer_norm(xr[s], (d,), pr[s, :d], pr[s, d:], 1e-5) for s in range(n_sets)])
+    assert _rel(out32, ref.view(M, d)) < 1e-5
+    assert _rel(out16, ref.view(M, d)) < 1e-3
+    # backward, fp32 dy, accumulate into an existing residual gradient
+    dy = torch.randn(M, d, device=_dev())
+    ref.backward(dy.view(n_sets, rows_per_set, d))
+    n_slots, p_total, p_off = 4, 2 * d + 256, 128
+    partials = torch.zeros(n_sets, n_slots, p_total, device=_dev())
+    dres0 = torch.randn(M, d, device=_dev())
+    dres = dres0.clone()
+    ops.layernorm_bwd(dy, x, params, rows_per_set, n_sets, d, partials, n_slots, p_total, p_off, dx=dres,
+                      accumulate=True, param_stride=2 * d)
+    assert _rel(dres - dres0, xr.grad.view(M, d)) < 2e-5
+    g = partials.sum(1)
+    assert _rel(g[:, p_off:p_off + d], pr.grad[:, :d]) < 2e-5
+    assert _rel(g[:, p_off + d:p_off + 2 * d], pr.grad[:, d:]) < 2e-5
+    assert g[:, :p_off].abs().max().item() == 0 and g[:, p_off + 2 * d:].abs().max().item() == 0
+    # fp16 dy, overwrite
+    dy16 = dy.half()
+    xr.grad = None
+    ref2 = torch.stack([torch.nn.functional.layer_norm(xr[s], (d,), pr[s, :d], pr[s, d:], 1e-5) for s in range(n_sets)])
+    ref2.backward(dy16.float().view(n_sets, rows_per_set, d))
+    dx = torch.empty(M, d, device=_dev())
+    ops.layernorm_bwd(dy16, x, params, rows_per_set, n_sets, d, partials, n_slots, p_total, p_off, dx=dx,
+                      accumulate=False, param_stride=2 * d)
+    assert _rel(dx, xr.grad.view(M, d)) < 2e-5
+
+
+def _ref_attention(qkv, n_seq, L, heads, causal):
+    d = heads * 64
+    q, k, v = qkv.float().view(n_seq, L, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    if causal:
+        s = s + torch.full((L, L), float("-inf"), device=qkv.device).triu(1)
+    p = s.softmax(-1)
+    o = (p @ v).permute(0, 2, 1, 3).reshape(n_seq * L, d)
+    return o, torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("L,heads,causal", [(197, 12, False), (257, 16, False), (77, 8, True), (50, 2, False),
+                                            (16, 1, True), (5, 2, False)])
+def test_attention_fwd_bwd(L, heads, causal):
+    torch.manual_seed(L)
+    n_seq, d = 3, heads * 64
+    qkv = torch.randn(n_seq * L, 3 * d, device=_dev()).half()
+    out = torch.empty(n_seq * L, d, device=_dev(), dtype=torch.float16)
+    lse = torch.empty(n_seq, heads, L, device=_dev())
+    ops.attention_fwd(qkv, n_seq, L, heads, out, causal=causal, lse=lse)
+    qf = qkv.float().requires_grad_(True)
+    ref, ref_lse = _ref_attention(qf, n_seq, L, heads, causal)
+    assert _rel(out, ref) < 2e-3
+    assert (lse - ref_lse).abs().max().item() < 1e-3
+    dout = (torch.randn(n_seq * L, d, device=_dev()) * 0.1).half()
+    ref.backward(dout.float())
+    dqkv = torch.full((n_seq * L, 3 * d), float("nan"), device=_dev(), dtype=torch.float16)
+    ops.attention_bwd(qkv, out, dout, lse, n_seq, L, heads, dqkv, causal=causal)
+    assert torch.isfinite(dqkv).all()
+    assert _rel(dqkv, qf.grad) < 5e-3
+
+
+@pytest.mark.parametrize("patch,res,k_pad", [(16, 224, 768), (14, 224, 640), (32, 224, 3072), (8, 32, 192)])
+def test_im2col(patch, res, k_pad):
+    torch.manual_seed(patch)
+    n = 5
+    img = torch.randn(n, 3, res, res, device=_dev())
+    idx = torch.tensor([3, 0, 4], device=_dev(), dtype=torch.int32)
+    g = res // patch
+    out = torch.empty(3 * g * g, k_pad, device=_dev(), dtype=torch.float16)
+    ops.im2col(img, idx, 3, patch, k_pad, out)
+    ref = torch.nn.functional.unfold(img[idx.long()], patch, stride=patch).transpose(1, 2).reshape(3 * g * g, -1)
+    k = 3 * patch * patch
+    assert torch.equal(out[:, :k], ref.half())
+    assert out[:, k:].abs().max().item() == 0 if k_pad > k else True
+    out2 = torch.empty(n * g * g, k_pad, device=_dev(), dtype=torch.float16)
+    ops.im2col(img, None, n, patch, k_pad, out2)
+    ref2 = torch.nn.functional.unfold(img, patch, stride=patch).transpose(1, 2).reshape(n * g * g, -1)
+    assert torch.equal(out2[:, :k], ref2.half())
+
+
+def test_embed_lnpre_and_text():
+    torch.manual_seed(1)
+    V, L, d = 4, 10, 256
+    patch_out = torch.randn(V * (L - 1), d, device=_dev())
+    cls, pos = torch.randn(d, device=_dev()), torch.randn(L, d, device=_dev())
+    params = torch.randn(2, 2 * d, device=_dev())
+    x = torch.empty(V * L, d, device=_dev())
+    x_pre = torch.empty(V * L, d, device=_dev())
+    ops.embed_lnpre(patch_out, cls, pos, params, params[:, d:], 2 * d, 2 * L, V, L, d, x, x_pre=x_pre)
+    pre = torch.cat([cls.expand(V, 1, d), patch_out.view(V, L - 1, d)], 1) + pos
+    assert _rel(x_pre, pre.view(V * L, d)) < 1e-6
+    ref = torch.cat([torch.nn.functional.layer_norm(pre[2 * s:2 * s + 2], (d,), params[s, :d], params[s, d:], 1e-5)
+                     for s in range(2)])
+    assert _rel(x, ref.view(V * L, d)) < 1e-5
+    tokens = torch.randint(0, 100, (6, 7), device=_dev())
+    emb, pos_t = torch.randn(100, d, device=_dev()), torch.randn(7, d, device=_dev())
+    xt = torch.empty(6 * 7, d, device=_dev())
+    ops.embed_text(tokens, emb, pos_t, xt)
+    assert torch.equal(xt.view(6, 7, d), emb[tokens] + pos_t)
+
+
+def _head_ref(xrows, gamma, beta, proj, T, scale):
+    y = torch.nn.functional.layer_norm(xrows, (xrows.shape[-1],), gamma, beta, 1e-5)
+    f = y @ proj
+    fh = f / f.norm(dim=-1, keepdim=True)
+    return fh, scale * fh @ T.t()
+
+
+def test_head_fwd_bwd():
+    torch.manual_seed(2)
+    n_img, S, L, d, E, C = 3, 4, 5, 768, 512, 200
+    n = n_img * S
+    x = torch.randn(n * L, d, device=_dev())
+    params = torch.randn(n_img, 2 * d, device=_dev())
+    proj = torch.randn(d, E, device=_dev()) * d ** -0.5
+    T = torch.nn.functional.normalize(torch.randn(C, E, device=_dev()), dim=-1)
+    feat = torch.empty(n, E, device=_dev()); inv = torch.empty(n, device=_dev()); logits = torch.empty(n, C, device=_dev())
+    ops.head_fwd(x, params, params[:, d:], proj, n, d, E, feat=feat, inv_norm=inv, logits=logits, class_feat=T,
+                 logit_scale=100.0, row_stride=L, param_stride=2 * d, seqs_per_set=S)
+    xr = x.view(n, L, d)[:, 0].clone().requires_grad_(True)
+    pr = params.clone().requires_grad_(True)
+    fh, lg = zip(*[_head_ref(xr[i * S:(i + 1) * S], pr[i, :d], pr[i, d:], proj, T, 100.0) for i in range(n_img)])
+    fh, lg = torch.cat(fh), torch.cat(lg)
+    assert _rel(feat, fh) < 1e-5 and _rel(logits, lg) < 1e-5
+    dlog = torch.randn(n, C, device=_dev()) * 0.01
+    lg.backward(dlog)
+    p_total, n_slots, p_off = 4 * d, 3, 2 * d
+    partials = torch.zeros(n_img, n_slots, p_total, device=_dev())
+    dres = torch.zeros(n * L, d, device=_dev())
+    ops.head_bwd(dlog, x, params, proj, T, 100.0, feat, inv, n_img, S, d, E, C, dres, partials, n_slots, p_total,
+                 p_off, row_stride=L, param_stride=2 * d)
+    assert _rel(dres.view(n, L, d)[:, 0], xr.grad) < 1e-4
+    assert dres.view(n, L, d)[:, 1:].abs().max().item() == 0
+    g = partials.sum(1)
+    assert _rel(g[:, p_off:p_off + d], pr.grad[:, :d]) < 1e-4
+    assert _rel(g[:, p_off + d:p_off + 2 * d], pr.grad[:, d:]) < 1e-4
+
+
+def test_entropy_select_and_reward_loss():
+    torch.manual_seed(3)
+    n_img, V, C, S, K, Er = 3, 64, 200, 6, 3, 768
+    logits = torch.randn(n_img * V, C, device=_dev()) * 2
+    sel = torch.empty(n_img, S, device=_dev(), dtype=torch.int32)
+    selg = torch.empty(n_img, S, device=_dev(), dtype=torch.int32)
+    ent = torch.empty(n_img, V, device=_dev())
+    ops.entropy_select(logits, n_img, V, C, S, sel, selg, ent)
+    lv = logits.view(n_img, V, C)
+    ref_ent = -(lv.softmax(-1) * lv.log_softmax(-1)).sum(-1)
+    assert (ent - ref_ent).abs().max().item() < 1e-5
+    ref_sel = torch.argsort(ref_ent, dim=1)[:, :S]
+    assert torch.equal(sel.long(), ref_sel)
+    assert torch.equal(selg.long(), ref_sel + torch.arange(n_img, device=_dev())[:, None] * V)
+
+    r_img = torch.nn.functional.normalize(torch.randn(n_img * S, Er, device=_dev()), dim=-1)
+    r_cls = torch.nn.functional.normalize(torch.randn(C, Er, device=_dev()), dim=-1)
+    for process_batch, amplify, reward_process in [(0, 0, 1), (0, 1, 1), (1, 0, 1), (1, 1, 1), (0, 0, 0)]:
+        dl = torch.empty(n_img * S, C, device=_dev())
+        tk = torch.empty(n_img * S, K, device=_dev(), dtype=torch.int32)
+        sc = torch.empty(n_img * S, K, device=_dev()); rw = torch.empty_like(sc); loss = torch.empty(n_img, device=_dev())
+        ops.reward_loss(logits, selg.view(-1), r_img, r_cls, n_img, S, K, C, dl, reward_process=reward_process,
+                        process_batch=process_batch, amplify=amplify, loss_scale=8.0, topk_idx=tk, scores=sc,
+                        rewards=rw, loss=loss)
+        for i in range(n_img):
+            out = logits[selg[i].long()].clone().requires_grad_(True)
+            val, index = torch.topk(out, K, dim=-1)
+            flat = index.flatten()
+            tf = r_cls[flat]
+            imf = torch.repeat_interleave(r_img[i * S:(i + 1) * S], K, dim=0)
+            score = torch.clamp(2.5 * (tf * imf).sum(-1), min=0)
+            cs = score if process_batch else score.reshape(S, -1)
+            if cs.shape[-1] > 1 and reward_process:
+                mean = cs.mean(-1, keepdim=True)
+                std = cs.std(-1, keepdim=True) + 1e-5 if amplify else 1.0
+                cs = (cs - mean) / std
+            rewards = cs.flatten()
+            ce = torch.nn.functional.cross_entropy(torch.repeat_interleave(out, K, dim=0), flat, reduction="none")
+            l = torch.mean(rewards * ce)
+            l.backward()
+            assert torch.equal(tk[i * S:(i + 1) * S].long(), index)
+            assert (sc[i * S:(i + 1) * S].flatten() - score).abs().max().item() < 1e-5
+            assert (rw[i * S:(i + 1) * S].flatten() - rewards).abs().max().item() < 1e-3 * max(1.0, rewards.abs().max().item())
+            assert abs(loss[i].item() - l.item()) < 1e-4 * max(1.0, abs(l.item()))
+            assert _rel(dl[i * S:(i + 1) * S] / 8.0, out.grad) < 1e-3
+
+
+def test_avg_entropy_loss():
+    torch.manual_seed(4)
+    n_img, S, C = 2, 4, 32
+    logits = torch.randn(n_img * S, C, device=_dev()) * 3
+    dl = torch.empty_like(logits); loss = torch.empty(n_img, device=_dev())
+    ops.avg_entropy_loss(logits, None, n_img, S, C, dl, loss=loss)
+    for i in range(n_img):
+        o = logits[i * S:(i + 1) * S].clone().requires_grad_(True)
+        lg = o - o.logsumexp(-1, keepdim=True)
+        avg = lg.logsumexp(0) - math.log(S)
+        l = -(avg * avg.exp()).sum()
+        l.backward()
+        assert abs(loss[i].item() - l.item()) < 1e-5
+        assert _rel(dl[i * S:(i + 1) * S], o.grad) < 1e-4
+
+
+def test_adamw_matches_torch():
+    torch.manual_seed(5)
+    n_sets, n_slots, P = 3, 4, 1000
+    init = torch.randn(P, device=_dev())
+    params = torch.empty(n_sets, P, device=_dev()); m = torch.empty_like(params); v = torch.empty_like(params)
+    ops.reset_params(init, params, m, v, n_sets, P)
+    assert torch.equal(params, init.expand(n_sets, P)) and m.abs().max().item() == 0 and v.abs().max().item() == 0
+    refs = [torch.nn.Parameter(init.clone()) for _ in range(n_sets)]
+    opts = [torch.optim.AdamW([r], lr=5e-3, weight_decay=5e-4) for r in refs]
+    for step in (1, 2, 3):
+        partials = torch.randn(n_sets, n_slots, P, device=_dev())
+        gout = torch.empty(n_sets, P, device=_dev())
+        ops.adamw_step(params, m, v, partials, n_sets, n_slots, P, 5e-3, step, weight_decay=5e-4, loss_scale=4.0,
+                       grad_out=gout)
+        g = partials.sum(1) / 4.0
+        assert _rel(gout, g) < 1e-6
+        for s in range(n_sets):
+            refs[s].grad = g[s].clone()
+            opts[s].step()
+            assert (params[s] - refs[s].data).abs().max().item() < 2e-6
+
+
+def test_cast_helpers():
+    torch.manual_seed(6)
+    w = torch.randn(70, 50, device=_dev())
+    assert torch.equal(ops.transpose_cast_f16(w), w.t().contiguous().half())
+    c = ops.cast_f16(w, k_pad=64)
+    assert torch.equal(c[:, :50], w.half()) and c[:, 50:].abs().max().item() == 0
