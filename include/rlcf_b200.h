@@ -74,13 +74,14 @@ int rlcf_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const fl
 
 /* LayerNorm backward.  dy is fp16 (dy_is_f32 = 0) or fp32 rows lddy apart; x is the saved LN input.
  *   dx_accum != NULL : dx_accum[row] (+)= dLN/dx   (accumulate = 1 adds to the residual-stream gradient)
+ *   dx16 != NULL     : fp16 copy [rows, d] of the updated dx_accum rows (A operand of the next dgrad GEMM)
  *   partials         : [n_sets, n_slots, p_total] fp32; block b of set g writes d(gamma) at
  *                      partials[g][b][p_off .. p_off+d) and d(beta) at [p_off+d .. p_off+2d).
  * n_slots blocks are launched per set. */
 int rlcf_layernorm_bwd(const void* dy, int dy_is_f32, int64_t lddy, const float* x, int64_t ldx, const float* gamma,
                        int64_t param_stride, int rows_per_set, int n_sets, int d, float eps, float* dx_accum,
-                       int64_t lddx, int accumulate, float* partials, int n_slots, int64_t p_total, int64_t p_off,
-                       void* stream);
+                       int64_t lddx, int accumulate, void* dx16, float* partials, int n_slots, int64_t p_total,
+                       int64_t p_off, void* stream);
 
 /* Fused multi-head attention core (nn.MultiheadAttention, model.py:185-187): qkv fp16 [n_seq*L, 3d] packed
  * q|k|v, head h = columns [h*64,(h+1)*64) of each third; out fp16 [n_seq*L, d].  causal != 0 applies the

@@ -1,0 +1,160 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference/TPT) on deterministic inputs.
+
+Run in the build container only (the reference does not travel to the GPU box):
+    python oracle/make_golden.py [case ...]
+
+What is reference code here: clip.model.build_model / CLIP, clip.custom_clip.CLIPCLS_TTA, clip_reward.get_reward_model /
+CLIPRewards, tpt_cls_rl.test_time_tuning / select_confident_samples, exactly as the eval driver
+TPT/tune_cls_rl.py:183-222 strings them together.  What is substituted: the checkpoint download
+(clip.load -> build_model on seeded synthetic weights), the BPE tokenizer (-> seeded synthetic token ids), the
+missing `ftfy` module and the hard-coded DOWNLOAD_ROOT existence check.  None of these touch the arithmetic.
+"""
+from __future__ import annotations
+
+import argparse
+import copy
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from oracle import rlcf_oracle as O  # noqa: E402
+
+REF = "/root/reference/TPT"
+
+CASES = {
+    # name: dict(policy, reward, seeds, V, rho, K, C, steps, lr, flags..., n_img)
+    "tiny_rlcf_1step": dict(policy="tiny-A", reward="tiny-B", V=16, rho=0.25, K=3, C=10, steps=1, lr=5e-3, n_img=2),
+    "tiny_rlcf_3step_amplify": dict(policy="tiny-A", reward="tiny-B", V=16, rho=0.25, K=3, C=10, steps=3, lr=5e-3,
+                                    n_img=2, reward_amplify=1),
+    "tiny_rlcf_process_batch": dict(policy="tiny-A", reward="tiny-B", V=16, rho=0.5, K=2, C=10, steps=2, lr=1e-3,
+                                    n_img=1, process_batch=1),
+    "b32_cfg1_shape": dict(policy="ViT-B/32", reward="ViT-B/32", V=8, rho=0.5, K=3, C=32, steps=1, lr=5e-3, n_img=1),
+    "b16_l14_cfg2": dict(policy="ViT-B/16", reward="ViT-L/14", V=64, rho=0.1, K=3, C=200, steps=1, lr=5e-3, n_img=1),
+}
+POLICY_SEED, REWARD_SEED, VIEW_SEED, TOKEN_SEED = 0, 1, 11, 7
+
+
+def import_reference():
+    sys.modules.setdefault("ftfy", types.SimpleNamespace(fix_text=lambda s: s))
+    real_exists = os.path.exists
+    os.path.exists = lambda p: True if p == "/YOUR/PATH" else real_exists(p)
+    sys.path.insert(0, REF)
+    argv, sys.argv = sys.argv, ["x"]
+    try:
+        import clip.custom_clip as custom_clip
+        import clip.model as clip_model
+        import clip_reward
+        import tpt_cls_rl
+    finally:
+        os.path.exists = real_exists
+        sys.argv = argv
+    return custom_clip, clip_model, clip_reward, tpt_cls_rl
+
+
+def run_case(name: str, cfg: dict, mods) -> dict:
+    custom_clip, clip_model, clip_reward, tpt_cls_rl = mods
+    sds = {cfg["policy"]: O.make_clip_state_dict(cfg["policy"], POLICY_SEED)}
+    sd_reward = O.make_clip_state_dict(cfg["reward"], REWARD_SEED)
+    vocab_p = O.ARCHS[cfg["policy"]][6]
+    vocab_r = O.ARCHS[cfg["reward"]][6]
+    res = O.ARCHS[cfg["policy"]][1]
+    tokens_p = O.make_tokens(cfg["C"], vocab_p, seed=TOKEN_SEED)
+    tokens_r = O.make_tokens(cfg["C"], vocab_r, seed=TOKEN_SEED)
+
+    def fake_load(sd):
+        def load(arch, device="cpu", jit=False, download_root=None):
+            model = clip_model.build_model({k: v.clone() for k, v in sd.items()}).to(device).float()
+            return model, sd["text_projection"].shape[1], None
+        return load
+
+    custom_clip.load = fake_load(sds[cfg["policy"]])
+    custom_clip.tokenize = lambda prompts: tokens_p.clone()
+    clip_reward.clip.load = fake_load(sd_reward)
+
+    args = argparse.Namespace(
+        tta_steps=cfg["steps"], selection_p=cfg["rho"], min_entropy_reg=False, min_entropy_w=0.0,
+        multiple_reward_models=0, reward_arch=cfg["reward"], reward_amplify=cfg.get("reward_amplify", 0),
+        sample_k=cfg["K"], reward_process=cfg.get("reward_process", 1), process_batch=cfg.get("process_batch", 0))
+    classnames = [f"class {i}" for i in range(cfg["C"])]
+    model = custom_clip.CLIPCLS_TTA("cpu", classnames, arch=cfg["policy"], prompt_prefix="a photo of a",
+                                    only_norm=True)
+    optimizer = torch.optim.AdamW(model.parameters(), cfg["lr"], weight_decay=5e-4)   # tune_cls_rl.py:79-81
+    optim_state = copy.deepcopy(optimizer.state_dict())
+    reward_model = clip_reward.get_reward_model("cpu", args)
+    reward_model.set_class_features(tokenized_classes=tokens_r)                        # tune_cls_rl.py:142-143
+    scaler = torch.cuda.amp.GradScaler(init_scale=1000)                                # tune_cls_rl.py:87
+
+    rec = {}
+    orig_select = tpt_cls_rl.select_confident_samples
+    orig_score, orig_post = reward_model.CLIPScore, reward_model.rewards_post_process
+
+    def select(logits, top):
+        out, idx = orig_select(logits, top)
+        rec["logits_all"], rec["selected_idx"] = logits.detach().clone(), idx.clone()
+        return out, idx
+
+    def score(class_index, **kw):
+        s = orig_score(class_index=class_index, **kw)
+        rec.setdefault("topk_idx", []).append(class_index.clone())
+        rec.setdefault("scores", []).append(s.clone())
+        return s
+
+    def post(cs):
+        r = orig_post(cs)
+        rec.setdefault("rewards", []).append(r.clone())
+        return r
+
+    tpt_cls_rl.select_confident_samples = select
+    reward_model.CLIPScore, reward_model.rewards_post_process = score, post
+
+    views = O.make_views(cfg["n_img"], cfg["V"], res, VIEW_SEED)
+    names = O.ln_param_names(sds[cfg["policy"]])
+    named = dict(model.clip_model.named_parameters())
+    out = {}
+    try:
+        for i in range(cfg["n_img"]):
+            rec.clear()
+            images = views[i * cfg["V"]:(i + 1) * cfg["V"]]
+            model.reset()                                                              # tune_cls_rl.py:210
+            optimizer.load_state_dict(optim_state)                                     # tune_cls_rl.py:213
+            model.train()
+            tpt_cls_rl.test_time_tuning(model, images, optimizer, scaler, args, reward_model=reward_model)
+            model.eval()
+            with torch.no_grad():
+                final = model(images[:1])                                              # tune_cls_rl.py:220-222
+            S, K = int(cfg["V"] * cfg["rho"]), cfg["K"]
+            out[f"img{i}.logits_all"] = rec["logits_all"].numpy()
+            out[f"img{i}.selected_idx"] = rec["selected_idx"].numpy()
+            out[f"img{i}.topk_idx"] = torch.stack([t.reshape(S, K) for t in rec["topk_idx"]]).numpy()
+            out[f"img{i}.scores"] = torch.stack([t.reshape(S, K) for t in rec["scores"]]).numpy()
+            out[f"img{i}.rewards"] = torch.stack([t.reshape(S, K) for t in rec["rewards"]]).numpy()
+            out[f"img{i}.logits_final"] = final.numpy()
+            out[f"img{i}.params"] = torch.cat([named[n].detach().flatten() for n in names]).numpy()
+    finally:
+        tpt_cls_rl.select_confident_samples = orig_select
+    out["class_feat"] = model.class_features.numpy()
+    out["reward_cls"] = reward_model.class_features.numpy()
+    out["meta"] = np.array(repr(cfg))
+    return out
+
+
+def main():
+    which = sys.argv[1:] or list(CASES)
+    torch.manual_seed(0)
+    mods = import_reference()
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    for name in which:
+        out = run_case(name, CASES[name], mods)
+        path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+        np.savez_compressed(path, **out)
+        print(name, "->", path, {k: v.shape for k, v in out.items() if k.startswith("img0")})
+
+
+if __name__ == "__main__":
+    main()

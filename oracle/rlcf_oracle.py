@@ -1,0 +1,309 @@
+"""CPU oracle for the RLCF test-time-adaptation hot path.  TEST INFRASTRUCTURE ONLY.
+
+This is a plain PyTorch fp32 restatement of the reference algorithm (mzhaoshuai/RLCF, TPT/), written from the
+reference's behaviour, with every function citing the file:line it follows.  It is the checker for the CUDA
+path: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import it.
+The product (rlcf_b200/) never does.
+
+Pinning: the reference ships no tests or golden vectors, so the oracle is pinned against
+OUTPUTS OF THE REFERENCE ITSELF, run in the build container from /root/reference by oracle/make_golden.py on
+identical deterministic weights and inputs; the resulting vectors are committed under tests/golden/ and
+tests/test_oracle_golden.py holds the oracle to them (<= 1e-5 abs on logits/rewards, identical indices).
+
+State-dict key layout is the one of TPT/clip/model.py.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------------------------------------------
+# deterministic synthetic CLIP weights (no OpenAI checkpoints offline; SURVEY.md 8(c) "Weights")
+# --------------------------------------------------------------------------------------------------------------
+ARCHS = {
+    # name: (embed_dim, resolution, vision_layers, vision_width, patch, ctx_len, vocab, text_width, text_heads, text_layers)
+    "ViT-B/32": (512, 224, 12, 768, 32, 77, 49408, 512, 8, 12),
+    "ViT-B/16": (512, 224, 12, 768, 16, 77, 49408, 512, 8, 12),
+    "ViT-L/14": (768, 224, 24, 1024, 14, 77, 49408, 768, 12, 12),
+    # small towers for fast CPU tests / golden vectors (same code paths: head_dim 64, odd token counts)
+    "tiny-A": (128, 64, 2, 128, 16, 77, 512, 128, 2, 2),     # 17 image tokens
+    "tiny-B": (256, 64, 3, 256, 8, 77, 512, 128, 2, 2),      # 65 image tokens (reward model in tests)
+}
+
+
+def make_clip_state_dict(arch: str, seed: int, logit_scale: float = math.log(100.0)) -> dict:
+    """Random CLIP weights with the scales of CLIP.initialize_parameters (TPT/clip/model.py:299-326) and the
+    VisionTransformer constructor (model.py:212-221), drawn from one seeded CPU generator in a fixed key order."""
+    E, res, vl, vw, p, ctx, vocab, tw, th, tl = ARCHS[arch]
+    g = torch.Generator().manual_seed(seed)
+
+    def rn(*shape, std=1.0):
+        return torch.randn(*shape, generator=g) * std
+
+    sd = {}
+    L = (res // p) ** 2 + 1
+    sd["visual.conv1.weight"] = rn(vw, 3, p, p, std=(3 * p * p) ** -0.5)
+    sd["visual.class_embedding"] = rn(vw, std=vw ** -0.5)
+    sd["visual.positional_embedding"] = rn(L, vw, std=vw ** -0.5)
+    sd["visual.proj"] = rn(vw, E, std=vw ** -0.5)
+
+    def ln(prefix, width):
+        # non-trivial affine parameters so that d(gamma), d(beta) and the per-image slices are exercised
+        sd[prefix + ".weight"] = 1.0 + rn(width, std=0.05)
+        sd[prefix + ".bias"] = rn(width, std=0.05)
+
+    def blocks(prefix, width, layers):
+        proj_std = (width ** -0.5) * ((2 * layers) ** -0.5)
+        attn_std = width ** -0.5
+        fc_std = (2 * width) ** -0.5
+        for l in range(layers):
+            rb = f"{prefix}transformer.resblocks.{l}."
+            sd[rb + "attn.in_proj_weight"] = rn(3 * width, width, std=attn_std)
+            sd[rb + "attn.in_proj_bias"] = rn(3 * width, std=0.02)
+            sd[rb + "attn.out_proj.weight"] = rn(width, width, std=proj_std)
+            sd[rb + "attn.out_proj.bias"] = rn(width, std=0.02)
+            ln(rb + "ln_1", width)
+            sd[rb + "mlp.c_fc.weight"] = rn(4 * width, width, std=fc_std)
+            sd[rb + "mlp.c_fc.bias"] = rn(4 * width, std=0.02)
+            sd[rb + "mlp.c_proj.weight"] = rn(width, 4 * width, std=proj_std)
+            sd[rb + "mlp.c_proj.bias"] = rn(width, std=0.02)
+            ln(rb + "ln_2", width)
+
+    ln("visual.ln_pre", vw)
+    blocks("visual.", vw, vl)
+    ln("visual.ln_post", vw)
+    sd["token_embedding.weight"] = rn(vocab, tw, std=0.02)
+    sd["positional_embedding"] = rn(ctx, tw, std=0.01)
+    blocks("", tw, tl)
+    ln("ln_final", tw)
+    sd["text_projection"] = rn(tw, E, std=tw ** -0.5)
+    sd["logit_scale"] = torch.tensor(float(logit_scale))
+    return sd
+
+
+def make_views(n_img: int, n_views: int, res: int, seed: int) -> torch.Tensor:
+    """Synthetic augmented views [n_img*n_views, 3, res, res]: a per-image low-frequency base pattern plus
+    per-view noise of varying strength, so that view entropies and class margins are well separated
+    (SURVEY.md section 7 'Discrete decisions amplify noise')."""
+    g = torch.Generator().manual_seed(seed)
+    out = torch.empty(n_img, n_views, 3, res, res)
+    for i in range(n_img):
+        base = F.interpolate(torch.randn(1, 3, 7, 7, generator=g), size=(res, res), mode="bilinear",
+                             align_corners=False)[0] * 1.5
+        for v in range(n_views):
+            strength = 0.15 + 1.2 * (v / max(1, n_views - 1))
+            out[i, v] = base + strength * torch.randn(3, res, res, generator=g)
+    return out.view(n_img * n_views, 3, res, res)
+
+
+def make_tokens(n_cls: int, vocab: int, ctx: int = 77, seed: int = 7) -> torch.Tensor:
+    """Synthetic tokenised prompts [n_cls, ctx]: SOT, 3..8 body tokens, EOT (= largest id, vocab-1, so that
+    argmax finds it as in TPT/clip/model.py:354), zero padding -- the shape clip.tokenize produces (clip.py:197-233)."""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.zeros(n_cls, ctx, dtype=torch.long)
+    for c in range(n_cls):
+        n = int(torch.randint(3, 9, (1,), generator=g))
+        t[c, 0] = vocab - 2
+        t[c, 1:1 + n] = torch.randint(1, vocab - 2, (n,), generator=g)
+        t[c, 1 + n] = vocab - 1
+    return t
+
+
+# --------------------------------------------------------------------------------------------------------------
+# towers
+# --------------------------------------------------------------------------------------------------------------
+def _block(x, sd, rb, heads, mask):
+    """ResidualAttentionBlock.forward (TPT/clip/model.py:189-192) on x [N, L, d] (batch-first restatement of the
+    reference's seq-first nn.MultiheadAttention call, model.py:185-187)."""
+    N, L, d = x.shape
+    hd = d // heads
+    h = F.layer_norm(x, (d,), sd[rb + "ln_1.weight"], sd[rb + "ln_1.bias"], 1e-5)          # model.py:157-163
+    qkv = h @ sd[rb + "attn.in_proj_weight"].t() + sd[rb + "attn.in_proj_bias"]
+    q, k, v = qkv.view(N, L, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    s = (q * hd ** -0.5) @ k.transpose(-1, -2)
+    if mask is not None:
+        s = s + mask
+    a = (s.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(N, L, d)
+    x = x + a @ sd[rb + "attn.out_proj.weight"].t() + sd[rb + "attn.out_proj.bias"]
+    h = F.layer_norm(x, (d,), sd[rb + "ln_2.weight"], sd[rb + "ln_2.bias"], 1e-5)
+    u = h @ sd[rb + "mlp.c_fc.weight"].t() + sd[rb + "mlp.c_fc.bias"]
+    u = u * torch.sigmoid(1.702 * u)                                                        # QuickGELU, model.py:166-168
+    return x + u @ sd[rb + "mlp.c_proj.weight"].t() + sd[rb + "mlp.c_proj.bias"]
+
+
+def _n_layers(sd, prefix):
+    return len([k for k in sd if k.startswith(prefix + "transformer.resblocks.") and k.endswith("attn.in_proj_weight")])
+
+
+def encode_image(sd: dict, images: torch.Tensor) -> torch.Tensor:
+    """VisionTransformer.forward (TPT/clip/model.py:223-240): un-normalised image features [N, E]."""
+    w = sd["visual.conv1.weight"]
+    d, p = w.shape[0], w.shape[-1]
+    x = F.conv2d(images, w, stride=p)                                                       # model.py:224
+    x = x.reshape(x.shape[0], d, -1).permute(0, 2, 1)
+    x = torch.cat([sd["visual.class_embedding"].expand(x.shape[0], 1, d), x], dim=1)        # model.py:227
+    x = x + sd["visual.positional_embedding"]
+    x = F.layer_norm(x, (d,), sd["visual.ln_pre.weight"], sd["visual.ln_pre.bias"], 1e-5)
+    for l in range(_n_layers(sd, "visual.")):
+        x = _block(x, sd, f"visual.transformer.resblocks.{l}.", d // 64, None)
+    x = F.layer_norm(x[:, 0, :], (d,), sd["visual.ln_post.weight"], sd["visual.ln_post.bias"], 1e-5)
+    return x @ sd["visual.proj"]                                                            # model.py:237-238
+
+
+def encode_text(sd: dict, tokens: torch.Tensor) -> torch.Tensor:
+    """CLIP.encode_text (TPT/clip/model.py:342-356): un-normalised text features [N, E]."""
+    x = sd["token_embedding.weight"][tokens] + sd["positional_embedding"]
+    L, d = x.shape[1], x.shape[2]
+    mask = torch.full((L, L), float("-inf")).triu_(1)                                       # model.py:328-334
+    for l in range(_n_layers(sd, "")):
+        x = _block(x, sd, f"transformer.resblocks.{l}.", d // 64, mask)
+    x = F.layer_norm(x, (d,), sd["ln_final.weight"], sd["ln_final.bias"], 1e-5)
+    x = x[torch.arange(x.shape[0]), tokens.argmax(dim=-1)] @ sd["text_projection"]          # model.py:354
+    return x
+
+
+def class_features(sd: dict, tokens: torch.Tensor) -> torch.Tensor:
+    """CLIPCLS_TTA.get_class_features (TPT/clip/custom_clip.py:404-408) / CLIPRewards.extract_text_features
+    (TPT/clip_reward.py:139-150): L2-normalised text features."""
+    with torch.no_grad():
+        f = encode_text(sd, tokens)
+        return f / f.norm(dim=-1, keepdim=True)
+
+
+def policy_logits(sd: dict, class_feat: torch.Tensor, images: torch.Tensor) -> torch.Tensor:
+    """CLIPCLS_TTA.forward (TPT/clip/custom_clip.py:423-432)."""
+    f = encode_image(sd, images)
+    f = f / f.norm(dim=-1, keepdim=True)
+    return sd["logit_scale"].exp() * f @ class_feat.t()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# TTA loop
+# --------------------------------------------------------------------------------------------------------------
+def select_confident_samples(logits, top):
+    """TPT/tpt_cls_rl.py:32-35."""
+    batch_entropy = -(logits.softmax(1) * logits.log_softmax(1)).sum(1)
+    idx = torch.argsort(batch_entropy, descending=False)[:int(batch_entropy.size()[0] * top)]
+    return logits[idx], idx, batch_entropy
+
+
+def avg_entropy(outputs):
+    """TPT/tpt_cls_rl.py:38-44."""
+    logits = outputs - outputs.logsumexp(dim=-1, keepdim=True)
+    avg_logits = logits.logsumexp(dim=0) - np.log(logits.shape[0])
+    avg_logits = torch.clamp(avg_logits, min=torch.finfo(avg_logits.dtype).min)
+    return -(avg_logits * torch.exp(avg_logits)).sum(dim=-1)
+
+
+def reward_image_features(sd_reward: dict, images: torch.Tensor) -> torch.Tensor:
+    """CLIPRewards.extract_image_features (TPT/clip_reward.py:130-137); the bicubic resize branch (133-134) is
+    not taken because every configured reward tower runs at the default 224 resolution."""
+    with torch.no_grad():
+        f = encode_image(sd_reward, images).float()
+        return f / f.norm(dim=1, keepdim=True)
+
+
+def clip_score(reward_cls, reward_img, class_index, sample_k, weight=2.5):
+    """CLIPRewards.CLIPScore with pairwise=False (TPT/clip_reward.py:111-128)."""
+    text_features = reward_cls[class_index]
+    image_features = torch.repeat_interleave(reward_img, sample_k, dim=0)
+    similarity = weight * torch.sum(text_features * image_features, dim=-1)
+    return torch.maximum(similarity, torch.zeros_like(similarity)).squeeze()
+
+
+def rewards_post_process(clip_score_, reward_process=True, amplify=False):
+    """CLIPRewards.rewards_post_process (TPT/clip_reward.py:152-165)."""
+    if clip_score_.shape[-1] > 1 and reward_process:
+        mean = torch.mean(clip_score_, dim=-1, keepdim=True)
+        std = torch.std(clip_score_, dim=-1, keepdim=True) + 1e-5 if amplify else 1.0
+        clip_score_ = (clip_score_ - mean) / std
+    return clip_score_.flatten()
+
+
+@dataclass
+class OracleConfig:
+    n_views: int = 64
+    selection_p: float = 0.1
+    tta_steps: int = 1
+    sample_k: int = 3
+    lr: float = 5e-3
+    weight_decay: float = 5e-4
+    reward_process: bool = True
+    process_batch: bool = False
+    reward_amplify: bool = False
+    loss: str = "rlcf"        # "rlcf" | "tpt"
+
+
+def ln_param_names(sd: dict) -> list:
+    """CLIPCLS_TTA.parameters with only_norm=True (TPT/clip/custom_clip.py:477-485): visual parameters whose name
+    contains 'ln' (there is no BatchNorm in a ViT), in named_parameters order."""
+    order = ["visual.ln_pre.weight", "visual.ln_pre.bias"]
+    for l in range(_n_layers(sd, "visual.")):
+        rb = f"visual.transformer.resblocks.{l}."
+        order += [rb + "ln_1.weight", rb + "ln_1.bias", rb + "ln_2.weight", rb + "ln_2.bias"]
+    order += ["visual.ln_post.weight", "visual.ln_post.bias"]
+    return order
+
+
+def adapt_one_image(sd_policy: dict, class_feat: torch.Tensor, views: torch.Tensor, cfg: OracleConfig,
+                    sd_reward: dict | None = None, reward_cls: torch.Tensor | None = None) -> dict:
+    """One iteration of the per-image loop of TPT/tune_cls_rl.py:192-222 in LayerNorm-tuning mode
+    (--tune_norm 1): reset -> test_time_tuning (TPT/tpt_cls_rl.py:47-79) -> adapted prediction on views[0].
+    fp32 on CPU: torch.cuda.amp.autocast and GradScaler are no-ops without CUDA, so the scaler lines
+    (tpt_cls_rl.py:77-79) reduce to loss.backward(); optimizer.step()."""
+    names = ln_param_names(sd_policy)
+    sd = {k: v.clone() for k, v in sd_policy.items()}                    # model.reset(), tune_cls_rl.py:210
+    params = [sd[n].requires_grad_(True) for n in names]
+    opt = torch.optim.AdamW(params, cfg.lr, weight_decay=cfg.weight_decay)   # fresh state, tune_cls_rl.py:80,213
+    out = {"losses": [], "grads": []}
+    selected_idx = None
+    for _ in range(cfg.tta_steps):
+        if selected_idx is not None:
+            output = policy_logits(sd, class_feat, views[selected_idx])                      # tpt_cls_rl.py:55
+        else:
+            logits_all = policy_logits(sd, class_feat, views)                                # tpt_cls_rl.py:57
+            output, selected_idx, ent = select_confident_samples(logits_all, cfg.selection_p)
+            out["logits_all"], out["entropy"], out["selected_idx"] = logits_all.detach(), ent.detach(), selected_idx
+            if cfg.loss == "rlcf":
+                reward_img = reward_image_features(sd_reward, views[selected_idx])           # tpt_cls_rl.py:59
+                out["reward_img"] = reward_img
+        bs = output.shape[0]
+        if cfg.loss == "rlcf":
+            _, index = torch.topk(output, cfg.sample_k, dim=-1)                              # tpt_cls_rl.py:63
+            flat = index.flatten()
+            score = clip_score(reward_cls, reward_img, flat, cfg.sample_k)                   # tpt_cls_rl.py:66
+            rewards = rewards_post_process(score if cfg.process_batch else score.reshape(bs, -1),
+                                           cfg.reward_process, cfg.reward_amplify)           # tpt_cls_rl.py:67
+            rep = torch.repeat_interleave(output, cfg.sample_k, dim=0)
+            all_loss = F.cross_entropy(rep, flat, reduction="none")                          # tpt_cls_rl.py:70
+            loss = torch.mean(rewards * all_loss)                                            # tpt_cls_rl.py:71
+            out.setdefault("topk_idx", []).append(index)
+            out.setdefault("scores", []).append(score.reshape(bs, -1))
+            out.setdefault("rewards", []).append(rewards.reshape(bs, -1))
+        else:
+            loss = avg_entropy(output)                                                       # tpt_cls.py:49-78
+        opt.zero_grad()
+        loss.backward()
+        out["grads"].append(torch.cat([p.grad.flatten() for p in params]).clone())
+        opt.step()
+        out["losses"].append(float(loss))
+    with torch.no_grad():
+        out["logits_final"] = policy_logits(sd, class_feat, views[:1])                       # tune_cls_rl.py:218-222
+    out["params"] = torch.cat([p.detach().flatten() for p in params])
+    return out
+
+
+def flat_ln_params(sd: dict) -> torch.Tensor:
+    return torch.cat([sd[n].detach().flatten() for n in ln_param_names(sd)])
+
+
+def accuracy(output, target, topk=(1,)):
+    """TPT/utils/tools.py:84-98."""
+    maxk = max(topk)
+    _, pred = output.topk(maxk, 1, True, True)
+    correct = pred.t().eq(target.view(1, -1).expand_as(pred.t()))
+    return [correct[:k].reshape(-1).float().sum(0, keepdim=True).mul_(100.0 / target.size(0)) for k in topk]

@@ -30,8 +30,8 @@ _PROTOS = {
     "rlcf_embed_lnpre": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _f, _vp, _vp, _vp],
     "rlcf_embed_text": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "rlcf_layernorm_fwd": [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _f, _vp, _vp, _vp],
-    "rlcf_layernorm_bwd": [_vp, _i, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _f, _vp, _i64, _i, _vp, _i, _i64, _i64,
-                           _vp],
+    "rlcf_layernorm_bwd": [_vp, _i, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _f, _vp, _i64, _i, _vp, _vp, _i, _i64,
+                           _i64, _vp],
     "rlcf_attention_fwd": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "rlcf_attention_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "rlcf_head_fwd": [_vp, _vp, _i64, _vp, _vp, _i64, _i, _vp, _vp, _f, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp],

@@ -59,7 +59,7 @@ int embed_text(const long long*, const float*, const float*, int, int, int, floa
 int layernorm_fwd(const float*, long long, const float*, const float*, long long, int, int, int, float, __half*,
                   float*, cudaStream_t);
 int layernorm_bwd(const void*, int, long long, const float*, long long, const float*, long long, int, int, int, float,
-                  float*, long long, int, float*, int, long long, long long, cudaStream_t);
+                  float*, long long, int, __half*, float*, int, long long, long long, cudaStream_t);
 int attention_fwd(const __half*, int, int, int, int, __half*, float*, cudaStream_t);
 int attention_bwd(const __half*, const __half*, const __half*, const float*, int, int, int, int, __half*,
                   cudaStream_t);
@@ -131,11 +131,11 @@ int rlcf_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const fl
 
 int rlcf_layernorm_bwd(const void* dy, int dy_is_f32, int64_t lddy, const float* x, int64_t ldx, const float* gamma,
                        int64_t param_stride, int rows_per_set, int n_sets, int d, float eps, float* dx_accum,
-                       int64_t lddx, int accumulate, float* partials, int n_slots, int64_t p_total, int64_t p_off,
-                       void* stream) {
+                       int64_t lddx, int accumulate, void* dx16, float* partials, int n_slots, int64_t p_total,
+                       int64_t p_off, void* stream) {
   if (!dy || !x || !gamma) return set_error(RLCF_ERR_ARG, "layernorm_bwd: null pointer");
   return layernorm_bwd(dy, dy_is_f32, lddy, x, ldx, gamma, param_stride, rows_per_set, n_sets, d, eps, dx_accum, lddx,
-                       accumulate, partials, n_slots, p_total, p_off, S(stream));
+                       accumulate, H(dx16), partials, n_slots, p_total, p_off, S(stream));
 }
 
 int rlcf_attention_fwd(const void* qkv, int n_seq, int L, int heads, int causal, void* out, float* lse,

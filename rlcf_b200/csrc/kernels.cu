@@ -249,8 +249,8 @@ template <int NV, bool kDyF32>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* __restrict__ x, long long ldx,
               const float* __restrict__ gamma, long long pstride, int rows_per_set, float eps,
-              float* __restrict__ dx, long long lddx, int accumulate, float* __restrict__ partials,
-              long long p_total, long long p_off) {
+              float* __restrict__ dx, long long lddx, int accumulate, __half* __restrict__ dx16,
+              float* __restrict__ partials, long long p_total, long long p_off) {
   constexpr int d = NV * 128;
   __shared__ float red[8][d];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -313,6 +313,11 @@ ln_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* __restr
           t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
         }
         o[lane + 32 * i] = t;
+        if (dx16) {  // fp16 copy of the updated residual gradient = A operand of the next dgrad GEMM
+          __half2 h0 = __floats2half2_rn(t.x, t.y), h1 = __floats2half2_rn(t.z, t.w);
+          *reinterpret_cast<uint2*>(dx16 + row * static_cast<long long>(d) + (lane + 32 * i) * 4) =
+              make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        }
       }
     }
   }
@@ -335,20 +340,21 @@ ln_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* __restr
 
 int layernorm_bwd(const void* dy, int dy_is_f32, long long lddy, const float* x, long long ldx, const float* gamma,
                   long long pstride, int rows_per_set, int n_sets, int d, float eps, float* dx, long long lddx,
-                  int accumulate, float* partials, int n_slots, long long p_total, long long p_off,
+                  int accumulate, __half* dx16, float* partials, int n_slots, long long p_total, long long p_off,
                   cudaStream_t stream) {
   if (int rc = check_width(d, "layernorm_bwd")) return rc;
   if (rows_per_set <= 0 || n_sets <= 0 || n_slots <= 0 || partials == nullptr)
     return set_error(RLCF_ERR_ARG, "layernorm_bwd: bad shape");
+  if (dx16 != nullptr && dx == nullptr) return set_error(RLCF_ERR_ARG, "layernorm_bwd: dx16 needs dx_accum");
   dim3 grid(n_slots, n_sets);
   if (dy_is_f32) {
     RLCF_DISPATCH_NV(d, (ln_bwd_kernel<NV, true><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, gamma, pstride,
                                                                             rows_per_set, eps, dx, lddx, accumulate,
-                                                                            partials, p_total, p_off)));
+                                                                            dx16, partials, p_total, p_off)));
   } else {
     RLCF_DISPATCH_NV(d, (ln_bwd_kernel<NV, false><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, gamma, pstride,
                                                                              rows_per_set, eps, dx, lddx, accumulate,
-                                                                             partials, p_total, p_off)));
+                                                                             dx16, partials, p_total, p_off)));
   }
   RLCF_CHECK_LAUNCH("layernorm_bwd");
   return 0;

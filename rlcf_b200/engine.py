@@ -1,0 +1,522 @@
+"""Host-side orchestration of the sm_100a kernels: transformer towers and the batched RLCF adaptation step.
+
+Layout in HBM (all row-major):
+  * token rows: row = sequence * L + token, residual stream fp32 [rows, d]; GEMM operands fp16
+  * frozen GEMM weights fp16 [out, in] (PyTorch Linear layout = K-major "B" operand) plus, when a backward is
+    needed, a transposed fp16 copy [in, out] that serves as the B operand of the dgrad GEMM
+  * trainable LayerNorm slice: one flat fp32 vector per parameter set,
+        [ln_pre.w, ln_pre.b, (ln_1.w, ln_1.b, ln_2.w, ln_2.b) x layers, ln_post.w, ln_post.b]
+    (39 936 floats for ViT-B/16); `n_sets` copies when every test image owns its parameters.
+
+Reference call stack being replaced: TPT/tpt_cls_rl.py:47-79 (test_time_tuning), TPT/clip/model.py:171-240.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import torch
+
+from . import ops
+from ._lib import EPI_F16, EPI_F32, EPI_GELU_BWD_F16, EPI_GELU_F16, EPI_RESID_F32, RlcfError
+
+N_SLOTS = 8  # gradient partial slots per parameter set (deterministic two-stage reduction)
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+@dataclass
+class LayerWeights:
+    wqkv: torch.Tensor  # fp16 [3d, d]
+    bqkv: torch.Tensor  # fp32 [3d]
+    wo: torch.Tensor    # fp16 [d, d]
+    bo: torch.Tensor
+    wfc: torch.Tensor   # fp16 [4d, d]
+    bfc: torch.Tensor
+    wproj: torch.Tensor  # fp16 [d, 4d]
+    bproj: torch.Tensor
+    # transposed copies (dgrad B operands), only when prepared with need_grad
+    wqkv_t: torch.Tensor | None = None  # [d, 3d]
+    wo_t: torch.Tensor | None = None    # [d, d]
+    wfc_t: torch.Tensor | None = None   # [d, 4d]
+    wproj_t: torch.Tensor | None = None  # [4d, d]
+
+
+@dataclass
+class TowerWeights:
+    """Device-resident, kernel-ready weights of one transformer tower (visual or text)."""
+    kind: str            # "visual" | "text"
+    d: int
+    heads: int
+    n_layers: int
+    L: int               # tokens per sequence
+    E: int               # output embedding dim
+    layers: list = field(default_factory=list)
+    proj: torch.Tensor | None = None      # fp32 [d, E]
+    ln_flat: torch.Tensor | None = None   # fp32 [P]
+    has_ln_pre: bool = True
+    # visual only
+    patch: int = 0
+    resolution: int = 0
+    k_pad: int = 0
+    conv_w: torch.Tensor | None = None    # fp16 [d, k_pad]
+    cls: torch.Tensor | None = None       # fp32 [d]
+    pos: torch.Tensor | None = None       # fp32 [L, d]
+    # text only
+    tok_emb: torch.Tensor | None = None   # fp32 [vocab, d]
+
+    @property
+    def P(self):
+        return self.ln_flat.numel()
+
+    def ln_off(self, name: str, layer: int = 0) -> int:
+        """Offset (floats) of a LayerNorm's gamma inside the flat vector; beta follows at +d."""
+        base = 2 * self.d if self.has_ln_pre else 0
+        if name == "ln_pre":
+            if not self.has_ln_pre:
+                raise RlcfError("tower has no ln_pre")
+            return 0
+        if name == "ln_1":
+            return base + layer * 4 * self.d
+        if name == "ln_2":
+            return base + layer * 4 * self.d + 2 * self.d
+        if name in ("ln_post", "ln_final"):
+            return base + self.n_layers * 4 * self.d
+        raise KeyError(name)
+
+    def ln_names(self, prefix: str):
+        """(state_dict key, offset) pairs in flat order, for packing/unpacking."""
+        out = []
+        if self.has_ln_pre:
+            out += [(f"{prefix}ln_pre.weight", 0), (f"{prefix}ln_pre.bias", self.d)]
+        for l in range(self.n_layers):
+            o1, o2 = self.ln_off("ln_1", l), self.ln_off("ln_2", l)
+            rb = f"{prefix}transformer.resblocks.{l}."
+            out += [(rb + "ln_1.weight", o1), (rb + "ln_1.bias", o1 + self.d),
+                    (rb + "ln_2.weight", o2), (rb + "ln_2.bias", o2 + self.d)]
+        last = "ln_post" if self.kind == "visual" else "ln_final"
+        o = self.ln_off("ln_post")
+        out += [(f"{prefix}{last}.weight", o), (f"{prefix}{last}.bias", o + self.d)]
+        return out
+
+
+def _prep_layers(sd, prefix, n_layers, need_grad):
+    layers = []
+    for l in range(n_layers):
+        rb = f"{prefix}transformer.resblocks.{l}."
+        f32 = lambda k: sd[rb + k].detach().float().contiguous()  # noqa: E731
+        wqkv, wo = f32("attn.in_proj_weight"), f32("attn.out_proj.weight")
+        wfc, wproj = f32("mlp.c_fc.weight"), f32("mlp.c_proj.weight")
+        lw = LayerWeights(
+            wqkv=ops.cast_f16(wqkv), bqkv=f32("attn.in_proj_bias"), wo=ops.cast_f16(wo), bo=f32("attn.out_proj.bias"),
+            wfc=ops.cast_f16(wfc), bfc=f32("mlp.c_fc.bias"), wproj=ops.cast_f16(wproj), bproj=f32("mlp.c_proj.bias"))
+        if need_grad:
+            lw.wqkv_t, lw.wo_t = ops.transpose_cast_f16(wqkv), ops.transpose_cast_f16(wo)
+            lw.wfc_t, lw.wproj_t = ops.transpose_cast_f16(wfc), ops.transpose_cast_f16(wproj)
+        layers.append(lw)
+    return layers
+
+
+def prepare_visual(sd: dict, prefix: str = "visual.", need_grad: bool = False) -> TowerWeights:
+    """Builds kernel-ready weights from a CLIP state_dict (key layout of TPT/clip/model.py)."""
+    conv = sd[prefix + "conv1.weight"].detach().float()
+    d, _, p, _ = conv.shape
+    pos = sd[prefix + "positional_embedding"].detach().float().contiguous()
+    L = pos.shape[0]
+    n_layers = len([k for k in sd if k.startswith(prefix) and k.endswith(".attn.in_proj_weight")])
+    proj = sd[prefix + "proj"].detach().float().contiguous()
+    k_real = 3 * p * p
+    w = TowerWeights(kind="visual", d=d, heads=d // 64, n_layers=n_layers, L=L, E=proj.shape[1], patch=p,
+                     resolution=p * int(round(math.sqrt(L - 1))), k_pad=_round_up(k_real, 64))
+    w.conv_w = ops.cast_f16(conv.reshape(d, k_real).contiguous(), k_pad=w.k_pad)
+    w.cls = sd[prefix + "class_embedding"].detach().float().contiguous()
+    w.pos, w.proj = pos, proj
+    w.layers = _prep_layers(sd, prefix, n_layers, need_grad)
+    w.ln_flat = torch.empty((4 * n_layers + 4) * d, dtype=torch.float32, device=conv.device)
+    for key, off in w.ln_names(prefix):
+        w.ln_flat[off:off + d].copy_(sd[key].detach().float())
+    return w
+
+
+def prepare_text(sd: dict, need_grad: bool = False) -> TowerWeights:
+    emb = sd["token_embedding.weight"].detach().float().contiguous()
+    pos = sd["positional_embedding"].detach().float().contiguous()
+    d = emb.shape[1]
+    n_layers = len([k for k in sd if k.startswith("transformer.resblocks.") and k.endswith(".attn.in_proj_weight")])
+    proj = sd["text_projection"].detach().float().contiguous()
+    w = TowerWeights(kind="text", d=d, heads=d // 64, n_layers=n_layers, L=pos.shape[0], E=proj.shape[1],
+                     has_ln_pre=False)
+    w.tok_emb, w.pos, w.proj = emb, pos, proj
+    w.layers = _prep_layers(sd, "", n_layers, need_grad)
+    w.ln_flat = torch.empty((4 * n_layers + 2) * d, dtype=torch.float32, device=emb.device)
+    for key, off in w.ln_names(""):
+        w.ln_flat[off:off + d].copy_(sd[key].detach().float())
+    return w
+
+
+class ActStore:
+    """Activations one training-mode forward keeps for the backward (per layer, for `rows` token rows)."""
+
+    def __init__(self, w: TowerWeights, n_seq: int, device):
+        d, L, nl = w.d, w.L, w.n_layers
+        rows = n_seq * L
+        f32 = dict(dtype=torch.float32, device=device)
+        f16 = dict(dtype=torch.float16, device=device)
+        self.n_seq, self.rows = n_seq, rows
+        self.x_pre = torch.empty(rows, d, **f32) if w.has_ln_pre else None
+        self.x_in = torch.empty(nl + 1, rows, d, **f32)   # x_in[l] = input of block l; x_in[nl] = tower output
+        self.x_mid = torch.empty(nl, rows, d, **f32)      # after the attention residual
+        self.qkv = torch.empty(nl, rows, 3 * d, **f16)
+        self.attn = torch.empty(nl, rows, d, **f16)
+        self.lse = torch.empty(nl, n_seq, w.heads, L, **f32)
+        self.u = torch.empty(nl, rows, 4 * d, **f16)      # QuickGELU pre-activation
+
+
+class TowerRunner:
+    """Runs one tower's forward (and LayerNorm-parameter backward) on preallocated workspaces."""
+
+    def __init__(self, w: TowerWeights, max_seq: int):
+        self.w = w
+        self.max_seq = max_seq
+        dev = w.ln_flat.device
+        d, L = w.d, w.L
+        rows = max_seq * L
+        f32 = dict(dtype=torch.float32, device=dev)
+        f16 = dict(dtype=torch.float16, device=dev)
+        self.x = torch.empty(rows, d, **f32)
+        self.a = torch.empty(rows, d, **f16)        # LayerNorm output / attention output
+        self.qkv = torch.empty(rows, 3 * d, **f16)
+        self.h = torch.empty(rows, 4 * d, **f16)
+        if w.kind == "visual":
+            self.patches = torch.empty(max_seq * (L - 1), w.k_pad, **f16)
+            self.patch_out = torch.empty(max_seq * (L - 1), d, **f32)
+        # backward workspaces are allocated lazily by reserve_backward()
+        self.g16 = self.gh = self.gqkv = self.dres = self.dres16 = None
+
+    def reserve_backward(self, n_seq: int):
+        w = self.w
+        dev = w.ln_flat.device
+        rows = n_seq * w.L
+        if self.dres is not None and self.dres.shape[0] >= rows:
+            return
+        f16 = dict(dtype=torch.float16, device=dev)
+        self.dres = torch.empty(rows, w.d, dtype=torch.float32, device=dev)
+        self.dres16 = torch.empty(rows, w.d, **f16)
+        self.g16 = torch.empty(rows, w.d, **f16)
+        self.gh = torch.empty(rows, 4 * w.d, **f16)
+        self.gqkv = torch.empty(rows, 3 * w.d, **f16)
+
+    # ------------------------------------------------------------------ forward
+    def _embed_visual(self, images, view_idx, n_seq, ln, pstride, rows_per_set, store):
+        w = self.w
+        P = w.L - 1
+        if images.shape[-1] != w.resolution or images.shape[-2] != w.resolution:
+            raise RlcfError(f"expected {w.resolution}x{w.resolution} input, got {tuple(images.shape)}")
+        ops.im2col(images, view_idx, n_seq, w.patch, w.k_pad, self.patches)
+        ops.gemm(self.patches, w.conv_w, self.patch_out, epilogue=EPI_F32, M=n_seq * P)
+        x = store.x_in[0] if store is not None else self.x
+        ops.embed_lnpre(self.patch_out, w.cls, w.pos, ln, ln[w.d:], pstride, rows_per_set, n_seq, w.L, w.d, x,
+                        x_pre=None if store is None else store.x_pre)
+        return x
+
+    def forward(self, n_seq, ln, pstride=0, seqs_per_set=None, images=None, view_idx=None, tokens=None, store=None,
+                causal=None):
+        """Returns the fp32 residual stream after the last block ([n_seq*L, d]).
+
+        ln: flat LayerNorm parameters, [P] (pstride 0) or [n_sets, P] (pstride P, seqs_per_set sequences per set).
+        store: ActStore to keep activations for backward() (training-mode forward), else None.
+        """
+        w = self.w
+        if n_seq > self.max_seq:
+            raise RlcfError(f"n_seq {n_seq} exceeds reserved {self.max_seq}")
+        d, L = w.d, w.L
+        rows = n_seq * L
+        rows_per_set = rows if seqs_per_set is None else seqs_per_set * L
+        lnv = ln.view(-1)
+        causal = (w.kind == "text") if causal is None else causal
+
+        def gb(off):  # gamma, beta views at a flat offset
+            return lnv[off:], lnv[off + d:]
+
+        if w.kind == "visual":
+            x = self._embed_visual(images, view_idx, n_seq, lnv, pstride, rows_per_set, store)
+        else:
+            x = store.x_in[0] if store is not None else self.x
+            ops.embed_text(tokens, w.tok_emb, w.pos, x)
+        for l, lw in enumerate(w.layers):
+            qkv = store.qkv[l] if store is not None else self.qkv
+            attn = store.attn[l] if store is not None else self.a
+            g, b = gb(w.ln_off("ln_1", l))
+            ops.layernorm_fwd(x, g, b, rows, d, out16=self.a, param_stride=pstride, rows_per_set=rows_per_set)
+            ops.gemm(self.a, lw.wqkv, qkv, epilogue=EPI_F16, bias=lw.bqkv, M=rows)
+            ops.attention_fwd(qkv, n_seq, L, w.heads, attn, causal=causal,
+                              lse=None if store is None else store.lse[l])
+            x_mid = store.x_mid[l] if store is not None else x
+            ops.gemm(attn, lw.wo, x_mid, epilogue=EPI_RESID_F32, bias=lw.bo, resid=x, M=rows)
+            g, b = gb(w.ln_off("ln_2", l))
+            ops.layernorm_fwd(x_mid, g, b, rows, d, out16=self.a, param_stride=pstride, rows_per_set=rows_per_set)
+            ops.gemm(self.a, lw.wfc, self.h, epilogue=EPI_GELU_F16, bias=lw.bfc, M=rows,
+                     aux_out=None if store is None else store.u[l])
+            x_next = store.x_in[l + 1] if store is not None else x
+            ops.gemm(self.h, lw.wproj, x_next, epilogue=EPI_RESID_F32, bias=lw.bproj, resid=x_mid, M=rows)
+            x = x_next
+        return x
+
+    def head(self, x, n_seq, ln, pstride=0, seqs_per_set=None, row_idx=None, class_feat=None, logit_scale=1.0,
+             feat=None, inv_norm=None, logits=None):
+        """ln_post/ln_final on one row per sequence -> projection -> L2 normalise (-> logits)."""
+        w = self.w
+        lnv = ln.view(-1)
+        off = w.ln_off("ln_post")
+        ops.head_fwd(x, lnv[off:], lnv[off + w.d:], w.proj, n_seq, w.d, w.E, feat=feat, inv_norm=inv_norm,
+                     logits=logits, class_feat=class_feat, logit_scale=logit_scale, row_idx=row_idx, row_stride=w.L,
+                     param_stride=pstride, seqs_per_set=seqs_per_set)
+
+    # ------------------------------------------------------------------ backward (LayerNorm parameters only)
+    def backward(self, store: ActStore, n_sets, seqs_per_set, ln, pstride, partials):
+        """Propagates self.dres (gradient w.r.t. the tower output rows, fp32, already filled by head_bwd) down to
+        ln_pre, writing every LayerNorm's d(gamma), d(beta) partials.  GEMM weights are frozen: dgrad only."""
+        w = self.w
+        d, L = w.d, w.L
+        n_seq = n_sets * seqs_per_set
+        rows = n_seq * L
+        rows_per_set = seqs_per_set * L
+        lnv = ln.view(-1)
+        P = w.P
+        dres, dres16 = self.dres, self.dres16
+        ops.cast_f16(dres, out=dres16, rows=rows)
+        for l in range(w.n_layers - 1, -1, -1):
+            lw = w.layers[l]
+            # MLP branch: d u = (d x_out @ Wproj) * gelu'(u);  d a2 = d u @ Wfc
+            ops.gemm(dres16, lw.wproj_t, self.gh, epilogue=EPI_GELU_BWD_F16, aux_in=store.u[l], M=rows)
+            ops.gemm(self.gh, lw.wfc_t, self.g16, epilogue=EPI_F16, M=rows)
+            off = w.ln_off("ln_2", l)
+            ops.layernorm_bwd(self.g16, store.x_mid[l], lnv[off:], rows_per_set, n_sets, d, partials, N_SLOTS, P, off,
+                              dx=dres, accumulate=True, param_stride=pstride, dx16=dres16)
+            # attention branch
+            ops.gemm(dres16, lw.wo_t, self.g16, epilogue=EPI_F16, M=rows)
+            ops.attention_bwd(store.qkv[l], store.attn[l], self.g16, store.lse[l], n_seq, L, w.heads, self.gqkv,
+                              causal=(w.kind == "text"))
+            ops.gemm(self.gqkv, lw.wqkv_t, self.g16, epilogue=EPI_F16, M=rows)
+            off = w.ln_off("ln_1", l)
+            ops.layernorm_bwd(self.g16, store.x_in[l], lnv[off:], rows_per_set, n_sets, d, partials, N_SLOTS, P, off,
+                              dx=dres, accumulate=True, param_stride=pstride, dx16=dres16)
+        if w.has_ln_pre:
+            ops.layernorm_bwd(dres, store.x_pre, lnv, rows_per_set, n_sets, d, partials, N_SLOTS, P, 0, dx=None,
+                              param_stride=pstride)
+
+
+@dataclass
+class RlcfConfig:
+    """Hyper-parameters of the TTA loop; names follow TPT/params.py:23-73."""
+    n_views: int = 64            # --batch_size (views per test image, first one is the clean view)
+    selection_p: float = 0.1     # --selection_p
+    tta_steps: int = 1           # --tta_steps
+    sample_k: int = 3            # --sample_k
+    lr: float = 5e-3             # --lr
+    weight_decay: float = 5e-4   # --weight_decay
+    betas: tuple = (0.9, 0.999)
+    eps: float = 1e-8
+    clipscore_weight: float = 2.5
+    reward_process: bool = True  # --reward_process
+    process_batch: bool = False  # --process_batch
+    reward_amplify: bool = False  # --reward_amplify
+    loss_scale: float = 1024.0   # static gradient scale for the fp16 dgrad operands (the reference's GradScaler(1000))
+    loss: str = "rlcf"           # "rlcf" (tpt_cls_rl.py:63-71) | "tpt" (avg_entropy, tpt_cls_rl.py:38-44)
+
+    @property
+    def n_selected(self):
+        return int(self.n_views * self.selection_p)  # tpt_cls_rl.py:34
+
+
+class RlcfEngine:
+    """Batched LN-only RLCF adaptation (TPT/tune_cls_rl.py --tune_norm 1): `n_img` independent test images per call.
+
+    Every image restarts from the same initial LayerNorm parameters and an empty Adam state
+    (tune_cls_rl.py:210-213), so images are independent and can share the frozen GEMM weights in one launch
+    sequence; each owns a private [P] slice of LayerNorm parameters, Adam moments and gradient partials.
+    """
+
+    def __init__(self, policy: TowerWeights, class_feat: torch.Tensor, logit_scale: float, cfg: RlcfConfig,
+                 n_img: int, reward: TowerWeights | None = None, reward_class_feat: torch.Tensor | None = None):
+        if policy.layers[0].wqkv_t is None:
+            raise RlcfError("policy weights must be prepared with need_grad=True")
+        self.cfg, self.n_img = cfg, n_img
+        self.policy, self.reward = policy, reward
+        self.class_feat = class_feat.float().contiguous()
+        self.logit_scale = float(logit_scale)
+        self.reward_class_feat = None if reward_class_feat is None else reward_class_feat.float().contiguous()
+        dev = policy.ln_flat.device
+        V, S, C = cfg.n_views, cfg.n_selected, self.class_feat.shape[0]
+        if S < 1:
+            raise RlcfError(f"int(n_views * selection_p) = {S}: no view would be selected (tpt_cls_rl.py:34)")
+        if cfg.loss == "rlcf" and (reward is None or self.reward_class_feat is None):
+            raise RlcfError("RLCF loss needs a reward tower and reward class features")
+        B, P = n_img, policy.P
+        self.run = TowerRunner(policy, B * V)
+        self.run.reserve_backward(B * S)
+        self.store = ActStore(policy, B * S, dev)
+        self.rrun = TowerRunner(reward, B * S) if reward is not None else None
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.init_params = policy.ln_flat.clone()
+        self.params = torch.empty(B, P, **f32)
+        self.m = torch.empty(B, P, **f32)
+        self.v = torch.empty(B, P, **f32)
+        self.partials = torch.empty(B, N_SLOTS, P, **f32)
+        self.grad = torch.empty(B, P, **f32)
+        self.logits_all = torch.empty(B * V, C, **f32)
+        self.entropy = torch.empty(B, V, **f32)
+        self.sel = torch.empty(B, S, **i32)
+        self.sel_global = torch.empty(B * S, **i32)
+        self.first_view = (torch.arange(B, device=dev, dtype=torch.int32) * V).contiguous()
+        self.logits_sel = torch.empty(B * S, C, **f32)
+        self.feat_sel = torch.empty(B * S, policy.E, **f32)
+        self.inv_norm_sel = torch.empty(B * S, **f32)
+        self.dlogits = torch.empty(B * S, C, **f32)
+        self.topk_idx = torch.empty(B * S, cfg.sample_k, **i32)
+        self.scores = torch.empty(B * S, cfg.sample_k, **f32)
+        self.rewards = torch.empty(B * S, cfg.sample_k, **f32)
+        self.loss = torch.empty(cfg.tta_steps, B, **f32)
+        self.logits_final = torch.empty(B, C, **f32)
+        self.reward_feat = torch.empty(B * S, reward.E, **f32) if reward is not None else None
+        self._graph = None
+        self._static_images = None
+
+    # ------------------------------------------------------------------
+    def adapt(self, images: torch.Tensor) -> torch.Tensor:
+        """images: fp32 [n_img * n_views, 3, H, W] (view 0 of each image is the clean view).
+        Runs reset -> tta_steps x (select, sample, reward, weighted-CE backward, AdamW) -> adapted 1-view logits.
+        Returns logits_final [n_img, C] (a workspace tensor that the next call overwrites)."""
+        cfg, B = self.cfg, self.n_img
+        V, S, K, C = cfg.n_views, cfg.n_selected, cfg.sample_k, self.class_feat.shape[0]
+        pol, P = self.policy, self.policy.P
+        if images.shape[0] != B * V:
+            raise RlcfError(f"expected {B * V} views, got {images.shape[0]}")
+        # model.reset(); optimizer.load_state_dict(optim_state)      (tune_cls_rl.py:210-213)
+        ops.reset_params(self.init_params, self.params, self.m, self.v, B, P)
+        # step 0: all views with the shared initial parameters       (tpt_cls_rl.py:57)
+        x = self.run.forward(B * V, self.init_params, images=images)
+        self.run.head(x, B * V, self.init_params, class_feat=self.class_feat, logit_scale=self.logit_scale,
+                      logits=self.logits_all)
+        # select_confident_samples                                    (tpt_cls_rl.py:58)
+        ops.entropy_select(self.logits_all, B, V, C, S, self.sel, self.sel_global, self.entropy)
+        # reward_model.set_image_features(inputs[selected_idx])       (tpt_cls_rl.py:59)
+        if cfg.loss == "rlcf":
+            xr = self.rrun.forward(B * S, self.reward.ln_flat, images=images, view_idx=self.sel_global)
+            self.rrun.head(xr, B * S, self.reward.ln_flat, feat=self.reward_feat)
+        for step in range(1, cfg.tta_steps + 1):
+            # training-mode forward of the selected views with each image's own parameters (tpt_cls_rl.py:55)
+            xs = self.run.forward(B * S, self.params, pstride=P, seqs_per_set=S, images=images,
+                                  view_idx=self.sel_global, store=self.store)
+            self.run.head(xs, B * S, self.params, pstride=P, seqs_per_set=S, class_feat=self.class_feat,
+                          logit_scale=self.logit_scale, feat=self.feat_sel, inv_norm=self.inv_norm_sel,
+                          logits=self.logits_sel)
+            if cfg.loss == "rlcf":
+                ops.reward_loss(self.logits_sel, None, self.reward_feat, self.reward_class_feat, B, S, K, C,
+                                self.dlogits, clipscore_weight=cfg.clipscore_weight,
+                                reward_process=cfg.reward_process, process_batch=cfg.process_batch,
+                                amplify=cfg.reward_amplify, loss_scale=cfg.loss_scale, topk_idx=self.topk_idx,
+                                scores=self.scores, rewards=self.rewards, loss=self.loss[step - 1])
+            else:
+                ops.avg_entropy_loss(self.logits_sel, None, B, S, C, self.dlogits, loss=self.loss[step - 1],
+                                     loss_scale=cfg.loss_scale)
+            self.partials.zero_()
+            self.run.dres[:B * S * pol.L].zero_()
+            off = pol.ln_off("ln_post")
+            ops.head_bwd(self.dlogits, xs, self.params.view(-1)[off:], pol.proj, self.class_feat, self.logit_scale,
+                         self.feat_sel, self.inv_norm_sel, B, S, pol.d, pol.E, C, self.run.dres, self.partials,
+                         N_SLOTS, P, off, row_stride=pol.L, param_stride=P)
+            self.run.backward(self.store, B, S, self.params, P, self.partials)
+            ops.adamw_step(self.params, self.m, self.v, self.partials, B, N_SLOTS, P, cfg.lr, step,
+                           beta1=cfg.betas[0], beta2=cfg.betas[1], eps=cfg.eps, weight_decay=cfg.weight_decay,
+                           loss_scale=cfg.loss_scale, grad_out=self.grad)
+        # adapted prediction on the clean view                        (tune_cls_rl.py:218-222)
+        xf = self.run.forward(B, self.params, pstride=P, seqs_per_set=1, images=images, view_idx=self.first_view)
+        self.run.head(xf, B, self.params, pstride=P, seqs_per_set=1, class_feat=self.class_feat,
+                      logit_scale=self.logit_scale, logits=self.logits_final)
+        return self.logits_final
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the whole step
+    def capture(self, images_like: torch.Tensor):
+        """Captures adapt() into a CUDA graph reading from a static input buffer (launch-bound otherwise:
+        ~450 kernels per step)."""
+        self._static_images = torch.empty_like(images_like)
+        self._static_images.copy_(images_like)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):  # warm-up outside capture (lazy cudaFuncSetAttribute, tensor-map entry point)
+                self.adapt(self._static_images)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.adapt(self._static_images)
+        self._graph = g
+        return g
+
+    def adapt_graph(self, images: torch.Tensor) -> torch.Tensor:
+        if self._graph is None:
+            self.capture(images)
+        self._static_images.copy_(images, non_blocking=True)
+        self._graph.replay()
+        return self.logits_final
+
+    # FLOP accounting (2*MACs), SURVEY.md 8(d)
+    @staticmethod
+    def tower_fwd_flops(w: TowerWeights) -> float:
+        L, d, n, E = w.L, w.d, w.n_layers, w.E
+        conv = 2 * (L - 1) * d * 3 * w.patch * w.patch if w.kind == "visual" else 0
+        return conv + n * (24 * L * d * d + 4 * L * L * d) + 2 * d * E
+
+    @staticmethod
+    def tower_dgrad_flops(w: TowerWeights) -> float:
+        L, d, n = w.L, w.d, w.n_layers
+        return n * (24 * L * d * d + 8 * L * L * d)
+
+    def algorithmic_flops_per_image(self) -> float:
+        cfg = self.cfg
+        V, S = cfg.n_views, cfg.n_selected
+        f = self.tower_fwd_flops(self.policy)
+        total = V * f + S * self.tower_dgrad_flops(self.policy) + f
+        total += (cfg.tta_steps - 1) * S * (f + self.tower_dgrad_flops(self.policy))
+        if self.reward is not None and cfg.loss == "rlcf":
+            total += S * self.tower_fwd_flops(self.reward)
+        return float(total)
+
+
+def text_features(w: TowerWeights, tokens: torch.Tensor, chunk: int = 256) -> torch.Tensor:
+    """L2-normalised text features [n, E] of tokenised prompts [n, ctx] (CLIP.encode_text, TPT/clip/model.py:342-356,
+    followed by the normalisation of custom_clip.py:404-408 / clip_reward.py:139-150)."""
+    if w.kind != "text":
+        raise RlcfError("text_features needs a text tower")
+    n, L = tokens.shape
+    if L != w.L:
+        raise RlcfError(f"context length {L} != {w.L}")
+    tokens = tokens.to(device=w.ln_flat.device, dtype=torch.int64).contiguous()
+    run = TowerRunner(w, min(chunk, n))
+    out = torch.empty(n, w.E, dtype=torch.float32, device=w.ln_flat.device)
+    eot = tokens.argmax(dim=-1).to(torch.int32)   # eot_token is the highest id in each sequence (model.py:352-354)
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        tk = tokens[s:e].contiguous()
+        x = run.forward(e - s, w.ln_flat, tokens=tk)
+        rows = (torch.arange(e - s, device=tk.device, dtype=torch.int32) * L + eot[s:e]).contiguous()
+        run.head(x, e - s, w.ln_flat, row_idx=rows, feat=out[s:e])
+    return out
+
+
+def image_features(w: TowerWeights, images: torch.Tensor, chunk: int = 256) -> torch.Tensor:
+    """L2-normalised image features [n, E] (VisionTransformer.forward + normalisation, model.py:223-240)."""
+    n = images.shape[0]
+    images = images.float().contiguous()
+    run = TowerRunner(w, min(chunk, n))
+    out = torch.empty(n, w.E, dtype=torch.float32, device=w.ln_flat.device)
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        x = run.forward(e - s, w.ln_flat, images=images[s:e])
+        run.head(x, e - s, w.ln_flat, feat=out[s:e])
+    return out

@@ -70,12 +70,13 @@ def layernorm_fwd(x, gamma, beta, M, d, out16=None, out32=None, ldx=None, param_
 
 
 def layernorm_bwd(dy, x, gamma, rows_per_set, n_sets, d, partials, n_slots, p_total, p_off, dx=None, accumulate=True,
-                  param_stride=0, lddy=None, ldx=None, lddx=None, eps=1e-5):
+                  param_stride=0, lddy=None, ldx=None, lddx=None, eps=1e-5, dx16=None):
     _chk(x, torch.float32, "x"); _chk(partials, torch.float32, "partials"); _chk(dx, torch.float32, "dx")
+    _chk(dx16, torch.float16, "dx16")
     is32 = dy.dtype == torch.float32
     call("rlcf_layernorm_bwd", ptr(dy), int(is32), d if lddy is None else lddy, ptr(x), d if ldx is None else ldx,
          ptr(gamma), param_stride, rows_per_set, n_sets, d, eps, ptr(dx), d if lddx is None else lddx,
-         int(accumulate), ptr(partials), n_slots, p_total, p_off, stream())
+         int(accumulate), ptr(dx16), ptr(partials), n_slots, p_total, p_off, stream())
 
 
 def attention_fwd(qkv, n_seq, L, heads, out, causal=False, lse=None):
@@ -147,12 +148,14 @@ def reset_params(init, params, m, v, n_sets, p_total):
     call("rlcf_reset_params", ptr(init), ptr(params), ptr(m), ptr(v), n_sets, p_total, stream())
 
 
-def cast_f16(src, k_pad=None):
+def cast_f16(src, k_pad=None, out=None, rows=None):
     """fp32 [rows, cols] -> fp16 [rows, k_pad] (zero padded)."""
-    _chk(src, torch.float32, "src")
-    rows, cols = src.shape
+    _chk(src, torch.float32, "src"); _chk(out, torch.float16, "out")
+    cols = src.shape[1]
+    rows = src.shape[0] if rows is None else rows
     ld = cols if k_pad is None else k_pad
-    out = torch.empty(rows, ld, dtype=torch.float16, device=src.device)
+    if out is None:
+        out = torch.empty(rows, ld, dtype=torch.float16, device=src.device)
     call("rlcf_cast_f16", ptr(src), rows, cols, cols, ptr(out), ld, stream())
     return out
 

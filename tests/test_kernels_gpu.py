@@ -120,9 +120,11 @@ def test_layernorm_fwd_bwd(d):
     partials = torch.zeros(n_sets, n_slots, p_total, device=_dev())
     dres0 = torch.randn(M, d, device=_dev())
     dres = dres0.clone()
+    dres16 = torch.empty(M, d, device=_dev(), dtype=torch.float16)
     ops.layernorm_bwd(dy, x, params, rows_per_set, n_sets, d, partials, n_slots, p_total, p_off, dx=dres,
-                      accumulate=True, param_stride=2 * d)
+                      accumulate=True, param_stride=2 * d, dx16=dres16)
     assert _rel(dres - dres0, xr.grad.view(M, d)) < 2e-5
+    assert torch.equal(dres16, dres.half())
     g = partials.sum(1)
     assert _rel(g[:, p_off:p_off + d], pr.grad[:, :d]) < 2e-5
     assert _rel(g[:, p_off + d:p_off + 2 * d], pr.grad[:, d:]) < 2e-5

@@ -1,0 +1,180 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the committed reference golden vectors.
+
+Tolerances (north_star: <= 1e-3 relative on final logits, identical top-1):
+  * logits:  max|cuda - oracle| <= 1e-3 * max|oracle|   (fp16 tensor-core operands, fp32 accumulate/residual)
+  * discrete decisions (selected views, sampled classes, top-1) must be identical unless the oracle's own margin
+    is below the measured logit error, in which case the test reports a near-tie instead of failing
+  * updated LayerNorm parameters: within 2% of one AdamW step (|delta| ~ lr per step)
+"""
+import ast
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import rlcf_oracle as O  # noqa: E402
+from rlcf_b200 import engine as E  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+POLICY_SEED, REWARD_SEED, VIEW_SEED, TOKEN_SEED = 0, 1, 11, 7
+DEV = "cuda:0"
+LOGIT_TOL = 1e-3
+
+
+def to_dev(sd):
+    return {k: v.to(DEV) for k, v in sd.items()}
+
+
+def build_engine(cfg, n_img, loss="rlcf"):
+    sd_p = O.make_clip_state_dict(cfg["policy"], POLICY_SEED)
+    sd_r = O.make_clip_state_dict(cfg["reward"], REWARD_SEED)
+    tok_p = O.make_tokens(cfg["C"], O.ARCHS[cfg["policy"]][6], seed=TOKEN_SEED)
+    tok_r = O.make_tokens(cfg["C"], O.ARCHS[cfg["reward"]][6], seed=TOKEN_SEED)
+    sdp_d, sdr_d = to_dev(sd_p), to_dev(sd_r)
+    pol = E.prepare_visual(sdp_d, need_grad=True)
+    rew = E.prepare_visual(sdr_d)
+    cf = E.text_features(E.prepare_text(sdp_d), tok_p)
+    rc = E.text_features(E.prepare_text(sdr_d), tok_r)
+    rcfg = E.RlcfConfig(n_views=cfg["V"], selection_p=cfg["rho"], tta_steps=cfg["steps"], sample_k=cfg["K"],
+                        lr=cfg["lr"], reward_process=bool(cfg.get("reward_process", 1)),
+                        process_batch=bool(cfg.get("process_batch", 0)),
+                        reward_amplify=bool(cfg.get("reward_amplify", 0)), loss=loss)
+    eng = E.RlcfEngine(pol, cf, float(sd_p["logit_scale"].exp()), rcfg, n_img, reward=rew, reward_class_feat=rc)
+    return eng, (sd_p, sd_r, tok_p, tok_r, cf, rc)
+
+
+def check_image(eng, i, ref, cfg, tag):
+    """ref: dict with logits_all, selected_idx, topk_idx [steps,S,K], rewards, logits_final, params (numpy)."""
+    V, S = cfg["V"], int(cfg["V"] * cfg["rho"])
+    la = eng.logits_all[i * V:(i + 1) * V].cpu().numpy()
+    scale = np.abs(ref["logits_all"]).max()
+    err = np.abs(la - ref["logits_all"]).max()
+    assert err <= LOGIT_TOL * scale, f"{tag}: step-0 logits err {err:.3e} vs scale {scale:.3f}"
+    # selection: identical, or differing only across an entropy gap smaller than the entropy error
+    sel = eng.sel[i].cpu().numpy()
+    ent = -(torch.tensor(ref["logits_all"]).softmax(1) * torch.tensor(ref["logits_all"]).log_softmax(1)).sum(1).numpy()
+    ent_err = np.abs(eng.entropy[i].cpu().numpy() - ent).max()
+    if not np.array_equal(sel, ref["selected_idx"]):
+        order = np.argsort(ent)
+        gap = ent[order[S]] - ent[order[S - 1]] if S < V else np.inf
+        inner = np.diff(ent[order[:S]]).min() if S > 1 else np.inf
+        assert min(gap, inner) < 4 * ent_err, (
+            f"{tag}: selection differs ({sel} vs {ref['selected_idx']}) although margins {gap:.2e}/{inner:.2e} "
+            f"exceed the entropy error {ent_err:.2e}")
+        pytest.skip(f"{tag}: near-tie in view selection (margin {min(gap, inner):.2e} < 4x error {ent_err:.2e})")
+    assert np.array_equal(eng.topk_idx[i * S:(i + 1) * S].cpu().numpy(), ref["topk_idx"][-1]), f"{tag}: top-K differs"
+    rw = ref["rewards"][-1]
+    assert np.abs(eng.rewards[i * S:(i + 1) * S].cpu().numpy() - rw).max() <= 2e-3 * max(1.0, np.abs(rw).max()), tag
+    lf = eng.logits_final[i].cpu().numpy()
+    errf = np.abs(lf - ref["logits_final"][0]).max()
+    assert errf <= LOGIT_TOL * scale, f"{tag}: final logits err {errf:.3e} vs scale {scale:.3f}"
+    top2 = np.sort(ref["logits_final"][0])[-2:]
+    if top2[1] - top2[0] > 2 * errf:
+        assert lf.argmax() == ref["logits_final"][0].argmax(), f"{tag}: top-1 differs"
+    perr = np.abs(eng.params[i].cpu().numpy() - ref["params"]).max()
+    assert perr <= 0.02 * cfg["lr"] * cfg["steps"] + 1e-7, f"{tag}: LN params err {perr:.3e}"
+    return err / scale, errf / scale
+
+
+def golden_cases():
+    return [f[:-4] for f in sorted(os.listdir(GOLDEN)) if f.endswith(".npz")]
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_cuda_matches_reference_golden(name):
+    """CUDA path vs outputs of the reference itself (committed fixtures)."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cfg = ast.literal_eval(str(z["meta"]))
+    eng, (_, _, _, _, cf, rc) = build_engine(cfg, cfg["n_img"])
+    assert np.abs(cf.cpu().numpy() - z["class_feat"]).max() < 2e-3
+    assert np.abs(rc.cpu().numpy() - z["reward_cls"]).max() < 2e-3
+    views = O.make_views(cfg["n_img"], cfg["V"], O.ARCHS[cfg["policy"]][1], VIEW_SEED).to(DEV)
+    eng.adapt(views)
+    torch.cuda.synchronize()
+    for i in range(cfg["n_img"]):
+        ref = {k.split(".", 1)[1]: z[k] for k in z.files if k.startswith(f"img{i}.")}
+        e0, e1 = check_image(eng, i, ref, cfg, f"{name}/img{i}")
+        print(f"{name}/img{i}: step-0 logits rel err {e0:.2e}, final {e1:.2e}")
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(policy="tiny-A", reward="tiny-B", V=16, rho=0.25, K=3, C=10, steps=2, lr=5e-3, n_img=3),
+    dict(policy="tiny-B", reward="tiny-A", V=8, rho=0.5, K=2, C=37, steps=1, lr=1e-3, n_img=2, reward_amplify=1),
+    dict(policy="ViT-B/32", reward="ViT-B/32", V=8, rho=0.5, K=3, C=200, steps=1, lr=5e-3, n_img=2),
+], ids=["tinyA-3img-2step", "tinyB-amplify", "b32-2img"])
+def test_cuda_matches_oracle_batched(cfg):
+    """Several images adapted in ONE batched launch sequence must each equal the oracle's one-at-a-time result,
+    eagerly and through CUDA-graph replay."""
+    eng, (sd_p, sd_r, tok_p, tok_r, _, _) = build_engine(cfg, cfg["n_img"])
+    cf, rc = O.class_features(sd_p, tok_p), O.class_features(sd_r, tok_r)
+    V = cfg["V"]
+    views = O.make_views(cfg["n_img"], V, O.ARCHS[cfg["policy"]][1], VIEW_SEED + 1)
+    ocfg = O.OracleConfig(n_views=V, selection_p=cfg["rho"], tta_steps=cfg["steps"], sample_k=cfg["K"], lr=cfg["lr"],
+                          reward_amplify=bool(cfg.get("reward_amplify", 0)))
+    refs = []
+    for i in range(cfg["n_img"]):
+        o = O.adapt_one_image(sd_p, cf, views[i * V:(i + 1) * V], ocfg, sd_r, rc)
+        refs.append(dict(logits_all=o["logits_all"].numpy(), selected_idx=o["selected_idx"].numpy(),
+                         topk_idx=torch.stack(o["topk_idx"]).numpy(), rewards=torch.stack(o["rewards"]).numpy(),
+                         logits_final=o["logits_final"].numpy(), params=o["params"].numpy(), grads=o["grads"]))
+    dviews = views.to(DEV)
+    eng.adapt(dviews)
+    torch.cuda.synchronize()
+    eager = eng.logits_final.clone()
+    for i in range(cfg["n_img"]):
+        check_image(eng, i, refs[i], cfg, f"img{i}")
+    if cfg["steps"] == 1:
+        # gradient of the LayerNorm slice vs autograd (relative to its largest entry)
+        for i in range(cfg["n_img"]):
+            g, gr = eng.grad[i].cpu(), refs[i]["grads"][0]
+            assert (g - gr).abs().max() <= 2e-2 * gr.abs().max(), f"img{i}: grad err {(g - gr).abs().max():.3e}"
+    out = eng.adapt_graph(dviews).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager), "graph replay differs from eager execution"
+    # a second replay on permuted images must permute the results (no state leaks between images)
+    perm = torch.arange(cfg["n_img"] - 1, -1, -1)
+    pv = dviews.view(cfg["n_img"], V, *dviews.shape[1:])[perm].reshape(dviews.shape).contiguous()
+    out2 = eng.adapt_graph(pv).clone()
+    assert torch.equal(out2, eager[perm.to(DEV)])
+
+
+def test_text_and_image_towers_match_oracle():
+    for arch, seed in (("tiny-A", 0), ("ViT-B/32", 2)):
+        sd = O.make_clip_state_dict(arch, seed)
+        tok = O.make_tokens(9, O.ARCHS[arch][6], seed=3)
+        tok[0, 1:76] = 5
+        tok[0, 76] = O.ARCHS[arch][6] - 1      # a prompt that fills the whole context (EOT in the last slot)
+        ref_t = O.class_features(sd, tok)
+        got_t = E.text_features(E.prepare_text(to_dev(sd)), tok)
+        assert (got_t.cpu() - ref_t).abs().max() < 2e-3
+        img = O.make_views(1, 5, O.ARCHS[arch][1], 5)
+        with torch.no_grad():
+            f = O.encode_image(sd, img)
+            ref_i = f / f.norm(dim=-1, keepdim=True)
+        got_i = E.image_features(E.prepare_visual(to_dev(sd)), img.to(DEV))
+        assert (got_i.cpu() - ref_i).abs().max() < 2e-3
+
+
+def test_tpt_entropy_loss_path():
+    """Config-1 plumbing: marginal-entropy loss (tpt_cls_rl.py:38-44) on the LayerNorm slice."""
+    cfg = dict(policy="tiny-A", reward="tiny-B", V=8, rho=0.5, K=3, C=32, steps=1, lr=5e-3, n_img=2)
+    eng, (sd_p, _, tok_p, _, _, _) = build_engine(cfg, 2, loss="tpt")
+    cf = O.class_features(sd_p, tok_p)
+    views = O.make_views(2, 8, 64, 21)
+    eng.adapt(views.to(DEV))
+    ocfg = O.OracleConfig(n_views=8, selection_p=0.5, tta_steps=1, lr=5e-3, loss="tpt")
+    for i in range(2):
+        o = O.adapt_one_image(sd_p, cf, views[i * 8:(i + 1) * 8], ocfg)
+        assert abs(eng.loss[0, i].item() - o["losses"][0]) < 2e-3 * max(1.0, abs(o["losses"][0]))
+        assert (eng.params[i].cpu() - o["params"]).abs().max() < 0.02 * 5e-3
+        scale = o["logits_all"].abs().max()
+        assert (eng.logits_final[i].cpu() - o["logits_final"][0]).abs().max() < LOGIT_TOL * scale
+
+
+def test_engine_rejects_empty_selection():
+    cfg = dict(policy="tiny-A", reward="tiny-B", V=8, rho=0.1, K=3, C=10, steps=1, lr=5e-3, n_img=1)
+    with pytest.raises(Exception):
+        build_engine(cfg, 1)
