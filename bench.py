@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- adapted images/sec of the RLCF test-time-adaptation hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU (oracle port)
+
+Workload (BASELINE.json configs[1]): policy ViT-B/16, reward ViT-L/14, 64 views per image,
+rho = 0.1 -> 6 selected views, K = 3 sampled classes, C = 200 classes, 1 TTA step, LayerNorm-only tuning,
+synthetic 224x224 views and random-init CLIP weights (no datasets / checkpoints offline).
+One "step" adapts `--images-per-step` independent test images in one batched launch sequence (CUDA graph):
+reset -> 64-view policy forward -> entropy selection -> reward forward on the selected views -> top-K/CLIPScore/
+reward-weighted CE -> backward to the LayerNorm parameters -> AdamW -> adapted 1-view prediction.
+Prints ONE JSON line on rank 0 (see the task contract for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "adapted images/sec (ViT-B/16, 64 views, 1 TTA step)"
+UNIT = "images/s"
+WORKLOAD = dict(policy="ViT-B/16", reward="ViT-L/14", n_views=64, selection_p=0.1, sample_k=3, n_classes=200,
+                tta_steps=1, lr=5e-3, mode="LayerNorm-only (--tune_norm 1)")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--images-per-step", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded CPU-baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(tflops_burst=p["bf16_tflops"], tflops_sustained=p["bf16_tflops_sustained"], hbm_gbs=p["hbm_gbs"],
+                    source="MEASURED_PEAKS.json")
+    return dict(tflops_burst=1590.0, tflops_sustained=1400.0, hbm_gbs=6650.0, source="B200_PROFILING.md fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference algorithm (CPU, fp32, all host threads) through the oracle port: one image per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import rlcf_oracle as O
+    K = args.steps if args.steps is not None else 2
+    W = args.warmup if args.warmup is not None else 1
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wl = WORKLOAD
+    sd_p = O.make_clip_state_dict(wl["policy"], 0)
+    sd_r = O.make_clip_state_dict(wl["reward"], 1)
+    cf = O.class_features(sd_p, O.make_tokens(wl["n_classes"], 49408))
+    rc = O.class_features(sd_r, O.make_tokens(wl["n_classes"], 49408))
+    cfg = O.OracleConfig(n_views=wl["n_views"], selection_p=wl["selection_p"], tta_steps=wl["tta_steps"],
+                         sample_k=wl["sample_k"], lr=wl["lr"])
+    views = O.make_views(1, wl["n_views"], 224, 11)
+    for _ in range(W):
+        O.adapt_one_image(sd_p, cf, views, cfg, sd_r, rc)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        O.adapt_one_image(sd_p, cf, views, cfg, sd_r, rc)
+    dt = time.perf_counter() - t0
+    value = K / dt
+    sample = f"{K} images x full config-2 sizes (64 views, B/16 policy + L/14 reward), one image per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ViT-B/16 RLCF cls, 64 views, 1 step, reward ViT-L/14 (config 2), LN-only", **wl,
+                   "images_per_step": 1},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg():
+    """Bounded CPU baseline on rank 0: the oracle port on ONE full-size image (about 10-30 s of host work)."""
+    from oracle import rlcf_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wl = WORKLOAD
+    sd_p = O.make_clip_state_dict(wl["policy"], 0)
+    sd_r = O.make_clip_state_dict(wl["reward"], 1)
+    cf = O.class_features(sd_p, O.make_tokens(wl["n_classes"], 49408))
+    rc = O.class_features(sd_r, O.make_tokens(wl["n_classes"], 49408))
+    cfg = O.OracleConfig(n_views=wl["n_views"], selection_p=wl["selection_p"], tta_steps=wl["tta_steps"],
+                         sample_k=wl["sample_k"], lr=wl["lr"])
+    views = O.make_views(1, wl["n_views"], 224, 11)
+    t0 = time.perf_counter()
+    O.adapt_one_image(sd_p, cf, views, cfg, sd_r, rc)
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "1 image at full config-2 sizes (64 views, 6 selected, B/16 policy + L/14 reward), no warm-up"}
+
+
+# ------------------------------------------------------------------------------------------------ CUDA arm
+def run_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the rlcf_b200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from rlcf_b200 import _lib, engine as E, ops, synthetic as S
+
+    K = args.steps if args.steps is not None else 10
+    W = max(3, args.warmup if args.warmup is not None else 3)
+    B = args.images_per_step
+    wl = WORKLOAD
+    sd_p = S.make_state_dict(wl["policy"], 0, dev)
+    sd_r = S.make_state_dict(wl["reward"], 1, dev)
+    pol = E.prepare_visual(sd_p, need_grad=True)
+    rew = E.prepare_visual(sd_r)
+    tok = S.make_tokens(wl["n_classes"], 49408)
+    cf = E.text_features(E.prepare_text(sd_p), tok)
+    rc = E.text_features(E.prepare_text(sd_r), tok)
+    logit_scale = float(sd_p["logit_scale"].exp())
+    del sd_p, sd_r
+    cfg = E.RlcfConfig(n_views=wl["n_views"], selection_p=wl["selection_p"], tta_steps=wl["tta_steps"],
+                       sample_k=wl["sample_k"], lr=wl["lr"])
+    eng = E.RlcfEngine(pol, cf, logit_scale, cfg, B, reward=rew, reward_class_feat=rc)
+    V = wl["n_views"]
+    # two different resident input batches, alternated: 2 x B x 38.5 MB (> 126 MB L2 for B >= 2)
+    batches = [S.make_views(B, V, 224, 1000 + 17 * rank + i, device=dev) for i in range(2)]
+    labels = torch.randint(0, wl["n_classes"], (B,), device=dev)
+    in_bytes = batches[0].numel() * 4
+
+    l0 = _lib.launch_count()
+    if args.no_graph:
+        step = eng.adapt
+        eng.adapt(batches[0])
+        launches_per_step = _lib.launch_count() - l0
+    else:
+        eng.capture(batches[0])
+        launches_per_step = (_lib.launch_count() - l0) // 3   # 2 eager warm-ups + 1 capture
+        step = eng.adapt_graph
+    for i in range(W):
+        step(batches[i % 2])
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`)
+    sampler = ClockSampler(local)
+    hits = torch.zeros(3, device=dev, dtype=torch.int64)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    e0.record()
+    for i in range(K):
+        logits = step(batches[i % 2])
+        # accuracy counters as tools.accuracy (TPT/utils/tools.py:84-98): top-1 / top-5 hits, count
+        top5 = logits.topk(5, dim=1).indices
+        hits[0] += (top5[:, 0] == labels).sum()
+        hits[1] += (top5 == labels[:, None]).any(1).sum()
+        hits[2] += B
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(hits, op=dist.ReduceOp.SUM)   # the only collective: final accuracy counters
+    ms_total = float(ms.item())
+    value = world * B * K / (ms_total / 1e3)
+
+    # ---------------- end-to-end with host buffers (`e2e`): pinned H2D of every step's views + D2H of the logits
+    host_in = [b.cpu().pin_memory() for b in batches]
+    host_out = torch.empty(B, wl["n_classes"], dtype=torch.float32).pin_memory()
+    for i in range(2):
+        eng.adapt_host(host_in[i % 2], host_out) if not args.no_graph else None
+    barrier()
+    e0.record()
+    for i in range(K):
+        if args.no_graph:
+            host_out.copy_(eng.adapt(host_in[i % 2].to(dev, non_blocking=True)), non_blocking=True)
+        else:
+            eng.adapt_host(host_in[i % 2], host_out)
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / (float(ms2.item()) / 1e3)
+
+    # ---------------- roofline of the dominant kernel (the tcgen05 GEMM), timed live per launch with CUDA events
+    pk = peaks()
+    ops.GEMM_TIMER = []
+    eng.adapt(batches[0])
+    torch.cuda.synchronize()
+    recs, ops.GEMM_TIMER = ops.GEMM_TIMER, None
+    g_ms = sum(a.elapsed_time(b) for (_, _, _, a, b) in recs)
+    g_flops = sum(2.0 * m * n * k for (m, n, k, _, _) in recs)
+    achieved = g_flops / (g_ms / 1e3) / 1e12
+    flops_img = eng.algorithmic_flops_per_image()
+    step_tflops = flops_img * value / world / 1e12
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_f16_kernel (tcgen05/TMA, all %d launches of one step)" % len(recs),
+        "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
+        "traffic": None, "peak_source": pk["source"] + " (sustained bf16 dense, of measured)",
+        "avg_launch_us": 1e3 * g_ms / len(recs), "gemm_share_of_step": g_ms / (ms_total / K),
+        "flops_per_launch": g_flops / len(recs),
+        "whole_step": {"algorithmic_gflop_per_image": flops_img / 1e9, "achieved_tflops": step_tflops,
+                       "frac": step_tflops / pk["tflops_sustained"]},
+    }
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic",
+        "config": {"workload": "ViT-B/16 RLCF cls, 64 views, 1 step, reward ViT-L/14 (config 2), LN-only", **wl,
+                   "images_per_step": B, "parallelism": f"dp{world} (independent images, no data-path collective)",
+                   "l2": "inputs larger than L2: two alternating resident batches of %.0f MB" % (in_bytes / 1e6),
+                   "cuda_graph": not args.no_graph, "gemm_cta_group": _lib.set_gemm_cta_group(0)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": host_out.numel() * 4},
+        "gpu_launches": int(launches_per_step * K),
+        "roofline": roofline,
+        "accuracy_counters": {"top1_hits": int(hits[0]), "top5_hits": int(hits[1]), "count": int(hits[2]),
+                              "note": "random labels on synthetic data; summed over ranks with one NCCL all-reduce"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_leg()
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -465,6 +465,17 @@ class RlcfEngine:
         self._graph.replay()
         return self.logits_final
 
+    def adapt_host(self, images_pinned: torch.Tensor, out_pinned: torch.Tensor) -> torch.Tensor:
+        """End-to-end call with HOST buffers: pinned fp32 views in, adapted logits [n_img, C] out (pinned).
+        The H2D copy, the graph replay and the D2H copy are enqueued on the current stream; the caller
+        synchronises (or keeps several calls in flight)."""
+        if self._graph is None:
+            self.capture(images_pinned.to(self.logits_final.device))
+        self._static_images.copy_(images_pinned, non_blocking=True)
+        self._graph.replay()
+        out_pinned.copy_(self.logits_final, non_blocking=True)
+        return out_pinned
+
     # FLOP accounting (2*MACs), SURVEY.md 8(d)
     @staticmethod
     def tower_fwd_flops(w: TowerWeights) -> float:

@@ -22,6 +22,11 @@ def _chk(t, dtype, name):
         raise _lib.RlcfError(f"{name} must be contiguous")
 
 
+# When set to a list, every gemm() launch is bracketed by CUDA events on the launching stream and
+# (M, N, K, start_event, end_event) is appended: bench.py's live per-launch timing of the dominant kernel.
+GEMM_TIMER = None
+
+
 def gemm(a, b, out, epilogue=EPI_F16, bias=None, resid=None, aux_in=None, aux_out=None, alpha=1.0, M=None):
     """out[M,N] = epilogue(alpha * a[M,K] @ b[N,K]^T).  a, b fp16 row-major; M may restrict the rows used."""
     _chk(a, torch.float16, "a"); _chk(b, torch.float16, "b")
@@ -36,8 +41,14 @@ def gemm(a, b, out, epilogue=EPI_F16, bias=None, resid=None, aux_in=None, aux_ou
     _chk(out, want, "out")
     if out.shape[-1] != n or out.shape[0] < m:
         raise _lib.RlcfError(f"gemm: out shape {tuple(out.shape)} does not fit [{m},{n}]")
+    if GEMM_TIMER is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     call("rlcf_gemm_f16", ptr(a), a.stride(0), ptr(b), b.stride(0), m, n, k, epilogue, float(alpha), ptr(bias),
          ptr(resid), ptr(aux_in), ptr(aux_out), ptr(out), out.stride(0), stream())
+    if GEMM_TIMER is not None:
+        e1.record()
+        GEMM_TIMER.append((m, n, k, e0, e1))
     return out
 
 

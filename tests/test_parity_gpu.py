@@ -55,8 +55,27 @@ def build_engine(cfg, n_img, loss="rlcf", cuda_text=False):
     return eng, (sd_p, sd_r, tok_p, tok_r, cf, rc)
 
 
-def check_image(eng, i, ref, cfg, tag):
-    """ref: dict with logits_all, selected_idx, topk_idx [steps,S,K], rewards, logits_final, params (numpy)."""
+def oracle_final_with_params(sd_p, cf, flat, view0):
+    """Oracle fp32 forward of the clean view using a given flat LayerNorm slice (e.g. the one the CUDA path produced)."""
+    sd = dict(sd_p)
+    off = 0
+    for n in O.ln_param_names(sd_p):
+        k = sd_p[n].numel()
+        sd[n] = flat[off:off + k].clone()
+        off += k
+    with torch.no_grad():
+        return O.policy_logits(sd, cf, view0)[0].numpy()
+
+
+def check_image(eng, i, ref, cfg, tag, sd_p=None, cf=None, view0=None):
+    """ref: dict with logits_all, selected_idx, topk_idx [steps,S,K], rewards, logits_final, params (numpy).
+
+    The adapted prediction is checked in two independent halves, because AdamW's first steps are sign-like and a
+    parameter whose gradient is numerically zero may move +lr in one implementation and -lr in the other:
+      (1) forward parity at IDENTICAL parameters: CUDA final logits vs the oracle's forward evaluated with the
+          CUDA-updated LayerNorm slice                                  -> 1e-3 (north_star bound)
+      (2) update parity: CUDA parameters vs the reference's parameters  -> check_params (flip-aware bounds)
+    plus the direct comparison with the reference's final logits, allowing 30% of the adaptation-induced change."""
     V, S = cfg["V"], int(cfg["V"] * cfg["rho"])
     la = eng.logits_all[i * V:(i + 1) * V].cpu().numpy()
     scale = np.abs(ref["logits_all"]).max()
@@ -83,7 +102,13 @@ def check_image(eng, i, ref, cfg, tag):
     lf = eng.logits_final[i].cpu().numpy()
     errf = np.abs(lf - ref["logits_final"][0]).max()
     print(f"{tag}: final logits max err {errf / scale:.2e}")
-    assert errf <= LOGIT_TOL * scale, f"{tag}: final logits err {errf:.3e} vs scale {scale:.3f}"
+    delta = np.abs(ref["logits_final"][0] - ref["logits_all"][0]).max()     # what adaptation changed (view 0)
+    assert errf <= LOGIT_TOL * scale + 0.3 * delta, f"{tag}: final logits err {errf:.3e} (scale {scale:.3f}, delta {delta:.3e})"
+    if sd_p is not None:
+        same = oracle_final_with_params(sd_p, cf, eng.params[i].cpu(), view0)
+        errs = np.abs(lf - same).max()
+        print(f"{tag}: final logits vs oracle forward at identical params: {errs / scale:.2e}")
+        assert errs <= LOGIT_TOL * scale, f"{tag}: final forward err {errs:.3e} vs scale {scale:.3f}"
     top2 = np.sort(ref["logits_final"][0])[-2:]
     if top2[1] - top2[0] > 2 * errf:
         assert lf.argmax() == ref["logits_final"][0].argmax(), f"{tag}: top-1 differs"
@@ -119,7 +144,7 @@ def test_cuda_matches_reference_golden(name):
     """CUDA path vs outputs of the reference itself (committed fixtures)."""
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     cfg = ast.literal_eval(str(z["meta"]))
-    eng, (_, _, _, _, cf, rc) = build_engine(cfg, cfg["n_img"])
+    eng, (sd_p, _, _, _, cf, rc) = build_engine(cfg, cfg["n_img"])
     assert np.abs(cf.cpu().numpy() - z["class_feat"]).max() < 1e-5      # oracle text features == reference's
     assert np.abs(rc.cpu().numpy() - z["reward_cls"]).max() < 1e-5
     views = O.make_views(cfg["n_img"], cfg["V"], O.ARCHS[cfg["policy"]][1], VIEW_SEED).to(DEV)
@@ -127,7 +152,8 @@ def test_cuda_matches_reference_golden(name):
     torch.cuda.synchronize()
     for i in range(cfg["n_img"]):
         ref = {k.split(".", 1)[1]: z[k] for k in z.files if k.startswith(f"img{i}.")}
-        e0, e1 = check_image(eng, i, ref, cfg, f"{name}/img{i}")
+        V = cfg["V"]
+        e0, e1 = check_image(eng, i, ref, cfg, f"{name}/img{i}", sd_p, cf.cpu(), views[i * V:i * V + 1].cpu())
         print(f"{name}/img{i}: step-0 logits rel err {e0:.2e}, final {e1:.2e}")
 
 
