@@ -7,11 +7,11 @@
 // and their dgrad counterparts in K12): the reference reaches them through nn.Conv2d / nn.MultiheadAttention
 // in-proj+out-proj / nn.Linear (TPT/clip/model.py:175-181,224) and autograd.
 //
-// Structure (one CTA per SM, 256 threads):
+// Structure (one CTA per SM, 384 threads):
 //   warp 0      TMA producer   : cp.async.bulk.tensor 2-D tiles (128B swizzle) into a kStages-deep smem ring
 //   warp 1      MMA issuer     : one thread issues tcgen05.mma (UMMA 128x256x16 or, as a CTA pair, 256x256x16)
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue       : tcgen05.ld accumulator -> registers -> fused epilogue -> 16-byte global stores
+//   warps 4..11 epilogue       : tcgen05.ld accumulator -> registers -> smem transpose -> coalesced global I/O
 // The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.  kCtaGroup == 2 pairs two SMs (cta_group::2): each CTA stages its own 128 rows of A
 // and half (128 rows) of B, halving the shared-memory and L2 traffic per FLOP.
@@ -24,7 +24,9 @@ constexpr int kBM = 128;      // accumulator rows per CTA (TMEM lanes)
 constexpr int kBN = 256;      // accumulator columns per tile
 constexpr int kBK = 64;       // K elements per stage (= 128 bytes = one swizzle atom)
 constexpr int kUmmaK = 16;    // K per tcgen05.mma for 16-bit inputs
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;   // 4 control warps + 8 epilogue warps
+constexpr int kBarrierBytes = 256;
+constexpr int kStagingBytes = 8 * 4096;  // epilogue transpose buffers, 32 x 32 fp32 per epilogue warp
 
 template <int kCtaGroup>
 struct GemmCfg {
@@ -33,7 +35,7 @@ struct GemmCfg {
   static constexpr int kBBytes = kBRows * kBK * 2;               // 32 KB / 16 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = kCtaGroup == 1 ? 4 : 6;         // 192 KB ring either way
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + kBarrierBytes + kStagingBytes;
 };
 
 struct GemmArgs {
@@ -86,7 +88,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4 * kCtaGroup);  // one arrive per epilogue warp per CTA
+      mbar_init(&tempty_bar[s], 8 * kCtaGroup);  // one arrive per epilogue warp per CTA
     }
     fence_barrier_init();
   }
@@ -158,8 +160,16 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue (128 threads, one row each)
-    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------ epilogue (8 warps)
+    // Warp w reads TMEM lane quarter (w & 3) and column half ((w - 4) >> 2) of the 128 x 256 accumulator in four
+    // 32-column chunks.  Each chunk goes registers -> swizzled smem staging (4 KB per warp) -> registers in a
+    // transposed assignment where 8 consecutive lanes cover 128 contiguous bytes of one output row, so that every
+    // global access (residual / pre-activation read, output write) is fully coalesced.
+    const int ew = warp & 3;
+    const int half_id = (warp - 4) >> 2;
+    float4* stg = reinterpret_cast<float4*>(smem + Cfg::kStages * Cfg::kStageBytes + kBarrierBytes) + (warp - 4) * 256;
+    const int tr = lane >> 3;  // row within a group of 4 rows (transposed phase)
+    const int tj = lane & 7;   // float4 column chunk (transposed phase)
     int it = 0;
     for (int t = worker; t < num_tiles; t += num_workers, ++it) {
       const int m_blk = t / n_tiles, n_blk = t % n_tiles;
@@ -167,18 +177,34 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const int row = m_blk * tile_m + static_cast<int>(cta_rank) * kBM + ew * 32 + lane;
-      const bool row_ok = row < p.M;
-      const size_t row_off = static_cast<size_t>(row) * p.ldo;
-      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * kBN;
+      const int row0 = m_blk * tile_m + static_cast<int>(cta_rank) * kBM + ew * 32;
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * kBN + half_id * 128;
+      const int col_base = n_blk * kBN + half_id * 128;
+      const int n_chunks = max(0, min(4, (p.N - col_base + 31) / 32));  // warp-uniform
+      if (n_chunks == 0) {  // this warp's column half lies entirely beyond N: nothing to read, release at once
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kCtaGroup == 1) mbar_arrive(&tempty_bar[as]);
+          else mbar_arrive_cluster(&tempty_bar[as], 0);
+        }
+      }
 #pragma unroll 1
-      for (int c = 0; c < kBN / 32; ++c) {
-        const int col0 = n_blk * kBN + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
+      for (int c = 0; c < n_chunks; ++c) {
+        const int col0 = col_base + c * 32;
         uint32_t r[32];
         tmem_ld_32x32(tacc + c * 32, r);
         tmem_ld_wait();
-        if (row_ok) {
+        if (c == n_chunks - 1) {
+          // last TMEM read of this tile by this warp: hand the accumulator back before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kCtaGroup == 1) mbar_arrive(&tempty_bar[as]);
+            else mbar_arrive_cluster(&tempty_bar[as], 0);
+          }
+        }
+        // phase 1 (thread = row): alpha, bias, QuickGELU forward
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
@@ -190,69 +216,48 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
           }
         }
-        if (p.epi == EPI_RESID_F32 || p.epi == EPI_F32) {
-          float* o = reinterpret_cast<float*>(p.out) + row_off + col0;
-          if (p.epi == EPI_RESID_F32) {
-            const float4* r4 = reinterpret_cast<const float4*>(p.resid + row_off + col0);
+        if (p.epi == EPI_GELU_F16 && p.aux_out == nullptr) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 q = r4[j];
-              v[4 * j + 0] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
-            }
-          }
-          float4* o4 = reinterpret_cast<float4*>(o);
+          for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+        }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-          if (p.epi == EPI_GELU_F16) {
-            if (p.aux_out != nullptr) {
-              uint4* a4 = reinterpret_cast<uint4*>(p.aux_out + row_off + col0);
+        for (int j = 0; j < 8; ++j)
+          stg[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        // phase 2 (8 lanes = one 128-byte row segment): global traffic
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                __half2 h0 = __floats2half2_rn(v[8 * j + 0], v[8 * j + 1]);
-                __half2 h1 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
-                __half2 h2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
-                __half2 h3 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
-                a4[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                                   *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+        for (int i = 0; i < 8; ++i) {
+          const int rr = tr + 4 * i;
+          const int grow = row0 + rr;
+          float4 q = stg[rr * 8 + (tj ^ (rr & 7))];
+          if (grow < p.M) {
+            const size_t off = static_cast<size_t>(grow) * p.ldo + col0 + tj * 4;
+            if (p.epi == EPI_RESID_F32 || p.epi == EPI_F32) {
+              if (p.epi == EPI_RESID_F32) {
+                const float4 z = *reinterpret_cast<const float4*>(p.resid + off);
+                q.x += z.x; q.y += z.y; q.z += z.z; q.w += z.w;
               }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
-          } else if (p.epi == EPI_GELU_BWD_F16) {
-            const uint4* u4 = reinterpret_cast<const uint4*>(p.aux_in + row_off + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 q = u4[j];
-              const __half2* h = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(h[e]);
-                v[8 * j + 2 * e + 0] *= quick_gelu_grad(f.x);
-                v[8 * j + 2 * e + 1] *= quick_gelu_grad(f.y);
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = q;
+            } else {
+              if (p.epi == EPI_GELU_F16 && p.aux_out != nullptr) {
+                __half2 u0 = __floats2half2_rn(q.x, q.y), u1 = __floats2half2_rn(q.z, q.w);
+                *reinterpret_cast<uint2*>(p.aux_out + off) =
+                    make_uint2(*reinterpret_cast<uint32_t*>(&u0), *reinterpret_cast<uint32_t*>(&u1));
+                q.x = quick_gelu(q.x); q.y = quick_gelu(q.y); q.z = quick_gelu(q.z); q.w = quick_gelu(q.w);
+              } else if (p.epi == EPI_GELU_BWD_F16) {
+                const uint2 uu = *reinterpret_cast<const uint2*>(p.aux_in + off);
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&uu.x));
+                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&uu.y));
+                q.x *= quick_gelu_grad(a.x); q.y *= quick_gelu_grad(a.y);
+                q.z *= quick_gelu_grad(b.x); q.w *= quick_gelu_grad(b.y);
               }
+              __half2 h0 = __floats2half2_rn(q.x, q.y), h1 = __floats2half2_rn(q.z, q.w);
+              *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + off) =
+                  make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
             }
-          }
-          uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + row_off + col0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            __half2 h0 = __floats2half2_rn(v[8 * j + 0], v[8 * j + 1]);
-            __half2 h1 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
-            __half2 h2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
-            __half2 h3 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
-            o4[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                               *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
           }
         }
-        }  // row_ok
-        __syncwarp();  // reconverge before the next .sync.aligned TMEM load
-      }
-      // all of this warp's TMEM reads are complete -> hand the accumulator back to the MMA issuer
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (kCtaGroup == 1) mbar_arrive(&tempty_bar[as]);
-        else mbar_arrive_cluster(&tempty_bar[as], 0);
+        __syncwarp();  // staging buffer is reused by the next chunk; also reconverges for the .aligned TMEM load
       }
     }
   }

@@ -225,9 +225,9 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ float quick_gelu(float x) { return x / (1.f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float quick_gelu(float x) { return __fdividef(x, 1.f + __expf(-1.702f * x)); }
 __device__ __forceinline__ float quick_gelu_grad(float x) {
-  float s = 1.f / (1.f + __expf(-1.702f * x));
+  float s = __fdividef(1.f, 1.f + __expf(-1.702f * x));
   return s * (1.f + 1.702f * x * (1.f - s));
 }
 
