@@ -15,6 +15,8 @@
 // The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.  kCtaGroup == 2 pairs two SMs (cta_group::2): each CTA stages its own 128 rows of A
 // and half (128 rows) of B, halving the shared-memory and L2 traffic per FLOP.
+#include <cstdlib>
+
 #include "ptx.cuh"
 #include "rlcf_internal.h"
 
@@ -48,9 +50,10 @@ struct GemmArgs {
   void* out;             // fp16 or fp32 [M, ldo]
   int ldo;               // leading dimension of out / resid / aux (elements)
   float alpha;           // scale applied to the accumulator before the epilogue
+  int debug_nostore;     // RLCF_GEMM_DEBUG_NOSTORE=1: skip the epilogue's global traffic (timing probe only)
 };
 
-template <int kCtaGroup>
+template <int kCtaGroup, int kEpi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs p) {
   using Cfg = GemmCfg<kCtaGroup>;
@@ -175,12 +178,17 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int m_blk = t / n_tiles, n_blk = t % n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
       const int row0 = m_blk * tile_m + static_cast<int>(cta_rank) * kBM + ew * 32;
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * kBN + half_id * 128;
       const int col_base = n_blk * kBN + half_id * 128;
       const int n_chunks = max(0, min(4, (p.N - col_base + 31) / 32));  // warp-uniform
+      // This warp's 128 bias values live in registers (4 per lane) and are broadcast by shuffle: with ~230 KB of
+      // shared memory per CTA there is no L1 left, so per-chunk bias loads would each pay an L2 round trip.
+      float4 breg = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias != nullptr && col_base + 4 * lane < p.N)
+        breg = __ldg(reinterpret_cast<const float4*>(p.bias + col_base) + lane);
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
       if (n_chunks == 0) {  // this warp's column half lies entirely beyond N: nothing to read, release at once
         tc_fence_before();
         __syncwarp();
@@ -189,9 +197,27 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           else mbar_arrive_cluster(&tempty_bar[as], 0);
         }
       }
+      // per-lane global offsets of the coalesced phase: row (row0 + tr + 4 i), columns col_base + 32 c + 4 tj .. +3
+      const size_t goff0 = static_cast<size_t>(row0 + tr) * p.ldo + col_base + tj * 4;
+      const size_t gstep = static_cast<size_t>(4) * p.ldo;
+      const int rows_left = p.M - (row0 + tr);  // row i of this lane is valid iff 4 i < rows_left
 #pragma unroll 1
       for (int c = 0; c < n_chunks; ++c) {
-        const int col0 = col_base + c * 32;
+        const size_t goff = goff0 + c * 32;
+        // prefetch what the coalesced phase needs from global memory; the latency overlaps the TMEM load
+        float4 z[kEpi == EPI_RESID_F32 ? 8 : 1];
+        uint2 zu[kEpi == EPI_GELU_BWD_F16 ? 8 : 1];
+        if constexpr (kEpi == EPI_RESID_F32) {
+          const float* rp = p.resid + goff;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            z[i] = 4 * i < rows_left ? *reinterpret_cast<const float4*>(rp + i * gstep) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if constexpr (kEpi == EPI_GELU_BWD_F16) {
+          const __half* ap = p.aux_in + goff;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            zu[i] = 4 * i < rows_left ? *reinterpret_cast<const uint2*>(ap + i * gstep) : make_uint2(0u, 0u);
+        }
         uint32_t r[32];
         tmem_ld_32x32(tacc + c * 32, r);
         tmem_ld_wait();
@@ -204,55 +230,47 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             else mbar_arrive_cluster(&tempty_bar[as], 0);
           }
         }
-        // phase 1 (thread = row): alpha, bias, QuickGELU forward
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-        if (p.bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
-            v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-          }
-        }
-        if (p.epi == EPI_GELU_F16 && p.aux_out == nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
-        }
+        if (p.debug_nostore) { __syncwarp(); continue; }  // bring-up probe: main loop + TMEM drain only
+        // phase 1 (thread = row): stage the raw accumulator chunk
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          stg[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          stg[lane * 8 + (j ^ (lane & 7))] =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                          __uint_as_float(r[4 * j + 3]));
+        // bias of this lane's 4 columns in the coalesced phase
+        float4 b4;
+        b4.x = __shfl_sync(0xffffffffu, breg.x, c * 8 + tj);
+        b4.y = __shfl_sync(0xffffffffu, breg.y, c * 8 + tj);
+        b4.z = __shfl_sync(0xffffffffu, breg.z, c * 8 + tj);
+        b4.w = __shfl_sync(0xffffffffu, breg.w, c * 8 + tj);
         __syncwarp();
-        // phase 2 (8 lanes = one 128-byte row segment): global traffic
+        // phase 2 (8 lanes = one 128-byte row segment): epilogue math + coalesced global stores
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = tr + 4 * i;
-          const int grow = row0 + rr;
           float4 q = stg[rr * 8 + (tj ^ (rr & 7))];
-          if (grow < p.M) {
-            const size_t off = static_cast<size_t>(grow) * p.ldo + col0 + tj * 4;
-            if (p.epi == EPI_RESID_F32 || p.epi == EPI_F32) {
-              if (p.epi == EPI_RESID_F32) {
-                const float4 z = *reinterpret_cast<const float4*>(p.resid + off);
-                q.x += z.x; q.y += z.y; q.z += z.z; q.w += z.w;
-              }
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = q;
+          q.x = fmaf(q.x, p.alpha, b4.x); q.y = fmaf(q.y, p.alpha, b4.y);
+          q.z = fmaf(q.z, p.alpha, b4.z); q.w = fmaf(q.w, p.alpha, b4.w);
+          if (4 * i < rows_left) {
+            if constexpr (kEpi == EPI_RESID_F32 || kEpi == EPI_F32) {
+              if constexpr (kEpi == EPI_RESID_F32) { q.x += z[i].x; q.y += z[i].y; q.z += z[i].z; q.w += z[i].w; }
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + goff + i * gstep) = q;
             } else {
-              if (p.epi == EPI_GELU_F16 && p.aux_out != nullptr) {
-                __half2 u0 = __floats2half2_rn(q.x, q.y), u1 = __floats2half2_rn(q.z, q.w);
-                *reinterpret_cast<uint2*>(p.aux_out + off) =
-                    make_uint2(*reinterpret_cast<uint32_t*>(&u0), *reinterpret_cast<uint32_t*>(&u1));
+              if constexpr (kEpi == EPI_GELU_F16) {
+                if (p.aux_out != nullptr) {
+                  __half2 u0 = __floats2half2_rn(q.x, q.y), u1 = __floats2half2_rn(q.z, q.w);
+                  *reinterpret_cast<uint2*>(p.aux_out + goff + i * gstep) =
+                      make_uint2(*reinterpret_cast<uint32_t*>(&u0), *reinterpret_cast<uint32_t*>(&u1));
+                }
                 q.x = quick_gelu(q.x); q.y = quick_gelu(q.y); q.z = quick_gelu(q.z); q.w = quick_gelu(q.w);
-              } else if (p.epi == EPI_GELU_BWD_F16) {
-                const uint2 uu = *reinterpret_cast<const uint2*>(p.aux_in + off);
-                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&uu.x));
-                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&uu.y));
-                q.x *= quick_gelu_grad(a.x); q.y *= quick_gelu_grad(a.y);
-                q.z *= quick_gelu_grad(b.x); q.w *= quick_gelu_grad(b.y);
+              } else if constexpr (kEpi == EPI_GELU_BWD_F16) {
+                const float2 ua = __half22float2(*reinterpret_cast<const __half2*>(&zu[i].x));
+                const float2 ub = __half22float2(*reinterpret_cast<const __half2*>(&zu[i].y));
+                q.x *= quick_gelu_grad(ua.x); q.y *= quick_gelu_grad(ua.y);
+                q.z *= quick_gelu_grad(ub.x); q.w *= quick_gelu_grad(ub.y);
               }
               __half2 h0 = __floats2half2_rn(q.x, q.y), h1 = __floats2half2_rn(q.z, q.w);
-              *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + off) =
+              *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + goff + i * gstep) =
                   make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
             }
           }
@@ -286,12 +304,12 @@ static int make_tmap_2d_f16(CUtensorMap* map, const void* base, int rows, int co
   return 0;
 }
 
-template <int kCtaGroup>
+template <int kCtaGroup, int kEpi>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
   using Cfg = GemmCfg<kCtaGroup>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<kCtaGroup>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<kCtaGroup, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return set_error(RLCF_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
     configured = true;
@@ -312,7 +330,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_f16_kernel<kCtaGroup>, ta, tb, args);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_f16_kernel<kCtaGroup, kEpi>, ta, tb, args);
   if (e != cudaSuccess) return set_error(RLCF_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   count_launch();
   return 0;
@@ -332,8 +350,19 @@ int gemm_f16(const __half* A, int lda, const __half* B, int ldb, int M, int N, i
   CUtensorMap ta, tb;
   if (int rc = make_tmap_2d_f16(&ta, A, M, K, lda, kBM)) return rc;
   if (int rc = make_tmap_2d_f16(&tb, B, N, K, ldb, kBN / cg)) return rc;
-  GemmArgs args{M, N, K, epi, bias, resid, aux_in, aux_out, out, ldo, alpha};
-  return cg == 2 ? launch_gemm<2>(ta, tb, args, stream) : launch_gemm<1>(ta, tb, args, stream);
+  static const int debug_nostore = getenv("RLCF_GEMM_DEBUG_NOSTORE") != nullptr;
+  GemmArgs args{M, N, K, epi, bias, resid, aux_in, aux_out, out, ldo, alpha, debug_nostore};
+  switch (epi) {
+#define RLCF_GEMM_CASE(E) \
+  case E: return cg == 2 ? launch_gemm<2, E>(ta, tb, args, stream) : launch_gemm<1, E>(ta, tb, args, stream);
+    RLCF_GEMM_CASE(EPI_F16)
+    RLCF_GEMM_CASE(EPI_GELU_F16)
+    RLCF_GEMM_CASE(EPI_RESID_F32)
+    RLCF_GEMM_CASE(EPI_GELU_BWD_F16)
+    RLCF_GEMM_CASE(EPI_F32)
+#undef RLCF_GEMM_CASE
+  }
+  return set_error(RLCF_ERR_ARG, "gemm: unknown epilogue %d", epi);
 }
 
 }  // namespace rlcf

@@ -41,13 +41,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Arrive on the barrier at the same smem offset inside CTA `cta` of this cluster.
+// Arrive on the barrier at the same smem offset inside CTA `cta` of this cluster.  Relaxed: the barrier only
+// hands TMEM back to the MMA issuer (ordered by the tcgen05 fences); a release at cluster scope would make the
+// warp wait for all of its earlier global stores (an ERRBAR in SASS) before the accumulator is freed.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
