@@ -42,6 +42,8 @@ const char* rlcf_last_error(void);
 uint64_t rlcf_launch_count(void);
 /* 1 = one CTA per tile (UMMA 128x256), 2 = CTA pair per tile (cta_group::2, UMMA 256x256). Returns the value set. */
 int rlcf_set_gemm_cta_group(int cta_group);
+/* Forward attention kernel: 0 = tcgen05/TMEM kernel (default), 1 = warp-level mma.sync kernel. Returns the value set. */
+int rlcf_set_attention_impl(int impl);
 
 /* D[M,N] = A[M,K] * B[N,K]^T, fp16 operands (K contiguous), fp32 accumulate on tcgen05 tensor cores.
  * Replaces: nn.Conv2d patch embedding (TPT/clip/model.py:224), nn.MultiheadAttention in_proj / out_proj

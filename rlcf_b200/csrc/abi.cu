@@ -12,6 +12,7 @@ namespace rlcf {
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_cta_group{0};
+static std::atomic<int> g_attn_impl{-1};
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -39,6 +40,16 @@ int gemm_cta_group() {
     const char* e = getenv("RLCF_GEMM_CTA_GROUP");
     v = (e != nullptr && atoi(e) == 1) ? 1 : 2;
     g_cta_group.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+int attention_impl() {
+  int v = g_attn_impl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("RLCF_ATTN_IMPL");
+    v = (e != nullptr && atoi(e) == 1) ? 1 : 0;
+    g_attn_impl.store(v, std::memory_order_relaxed);
   }
   return v;
 }
@@ -93,6 +104,11 @@ uint64_t rlcf_launch_count(void) { return g_launches.load(std::memory_order_rela
 int rlcf_set_gemm_cta_group(int cta_group) {
   if (cta_group == 1 || cta_group == 2) g_cta_group.store(cta_group, std::memory_order_relaxed);
   return gemm_cta_group();
+}
+
+int rlcf_set_attention_impl(int impl) {
+  if (impl == 0 || impl == 1) g_attn_impl.store(impl, std::memory_order_relaxed);
+  return attention_impl();
 }
 
 int rlcf_gemm_f16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epilogue, float alpha,

@@ -330,9 +330,16 @@ attn_bwd_kernel(const __half* __restrict__ qkv, const __half* __restrict__ out, 
   }
 }
 
+int attention_fwd_tc(const __half* qkv, int n_seq, int L, int heads, int causal, __half* out, float* lse,
+                     cudaStream_t stream);
+
 int attention_fwd(const __half* qkv, int n_seq, int L, int heads, int causal, __half* out, float* lse,
                   cudaStream_t stream) {
   if (n_seq <= 0 || L <= 0 || heads <= 0) return set_error(RLCF_ERR_ARG, "attention_fwd: bad shape");
+  if (attention_impl() == 0) {  // tcgen05 kernel (attention_tc.cu); -1 = shape not covered -> warp-MMA kernel below
+    const int rc = attention_fwd_tc(qkv, n_seq, L, heads, causal, out, lse, stream);
+    if (rc != -1) return rc;
+  }
   const int Lp = (L + 15) / 16 * 16;
   const size_t smem = static_cast<size_t>(2 * Lp + kFwdWarps * 16) * kRowBytes;
   if (smem > 227 * 1024) return set_error(RLCF_ERR_ARG, "attention_fwd: sequence %d too long for one CTA", L);

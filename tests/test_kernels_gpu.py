@@ -151,10 +151,12 @@ def _ref_attention(qkv, n_seq, L, heads, causal):
     return o, torch.logsumexp(s, -1)
 
 
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "mma_sync"])
 @pytest.mark.parametrize("L,heads,causal", [(197, 12, False), (257, 16, False), (77, 8, True), (50, 2, False),
-                                            (16, 1, True), (5, 2, False)])
-def test_attention_fwd_bwd(L, heads, causal):
+                                            (16, 1, True), (5, 2, False), (256, 1, False), (130, 3, True)])
+def test_attention_fwd_bwd(L, heads, causal, impl):
     torch.manual_seed(L)
+    assert _lib.set_attention_impl(impl) == impl
     n_seq, d = 3, heads * 64
     qkv = torch.randn(n_seq * L, 3 * d, device=_dev()).half()
     out = torch.empty(n_seq * L, d, device=_dev(), dtype=torch.float16)
@@ -170,6 +172,7 @@ def test_attention_fwd_bwd(L, heads, causal):
     ops.attention_bwd(qkv, out, dout, lse, n_seq, L, heads, dqkv, causal=causal)
     assert torch.isfinite(dqkv).all()
     assert _rel(dqkv, qf.grad) < 5e-3
+    _lib.set_attention_impl(0)
 
 
 @pytest.mark.parametrize("patch,res,k_pad", [(16, 224, 768), (14, 224, 640), (32, 224, 3072), (8, 32, 192)])
