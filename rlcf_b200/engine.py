@@ -390,6 +390,20 @@ class RlcfEngine:
         """images: fp32 [n_img * n_views, 3, H, W] (view 0 of each image is the clean view).
         Runs reset -> tta_steps x (select, sample, reward, weighted-CE backward, AdamW) -> adapted 1-view logits.
         Returns logits_final [n_img, C] (a workspace tensor that the next call overwrites)."""
+        self.tune(images)
+        return self.predict(images)
+
+    def predict(self, images: torch.Tensor) -> torch.Tensor:
+        """Adapted prediction on the clean view of every image (tune_cls_rl.py:218-222) with its own parameters."""
+        B, P = self.n_img, self.policy.P
+        xf = self.run.forward(B, self.params, pstride=P, seqs_per_set=1, images=images, view_idx=self.first_view)
+        self.run.head(xf, B, self.params, pstride=P, seqs_per_set=1, class_feat=self.class_feat,
+                      logit_scale=self.logit_scale, logits=self.logits_final)
+        return self.logits_final
+
+    def tune(self, images: torch.Tensor) -> torch.Tensor:
+        """test_time_tuning (tpt_cls_rl.py:47-79) for n_img images at once, starting from init_params and an empty
+        Adam state.  Leaves the adapted LayerNorm slices in self.params [n_img, P] and returns them."""
         cfg, B = self.cfg, self.n_img
         V, S, K, C = cfg.n_views, cfg.n_selected, cfg.sample_k, self.class_feat.shape[0]
         pol, P = self.policy, self.policy.P
@@ -433,11 +447,7 @@ class RlcfEngine:
             ops.adamw_step(self.params, self.m, self.v, self.partials, B, N_SLOTS, P, cfg.lr, step,
                            beta1=cfg.betas[0], beta2=cfg.betas[1], eps=cfg.eps, weight_decay=cfg.weight_decay,
                            loss_scale=cfg.loss_scale, grad_out=self.grad)
-        # adapted prediction on the clean view                        (tune_cls_rl.py:218-222)
-        xf = self.run.forward(B, self.params, pstride=P, seqs_per_set=1, images=images, view_idx=self.first_view)
-        self.run.head(xf, B, self.params, pstride=P, seqs_per_set=1, class_feat=self.class_feat,
-                      logit_scale=self.logit_scale, logits=self.logits_final)
-        return self.logits_final
+        return self.params
 
     # ------------------------------------------------------------------ CUDA-graph replay of the whole step
     def capture(self, images_like: torch.Tensor):
@@ -499,9 +509,10 @@ class RlcfEngine:
         return float(total)
 
 
-def text_features(w: TowerWeights, tokens: torch.Tensor, chunk: int = 256) -> torch.Tensor:
+def text_features(w: TowerWeights, tokens: torch.Tensor, chunk: int = 256, normalized: bool = True) -> torch.Tensor:
     """L2-normalised text features [n, E] of tokenised prompts [n, ctx] (CLIP.encode_text, TPT/clip/model.py:342-356,
-    followed by the normalisation of custom_clip.py:404-408 / clip_reward.py:139-150)."""
+    followed by the normalisation of custom_clip.py:404-408 / clip_reward.py:139-150).  normalized=False returns the
+    raw encode_text output."""
     if w.kind != "text":
         raise RlcfError("text_features needs a text tower")
     n, L = tokens.shape
@@ -510,14 +521,15 @@ def text_features(w: TowerWeights, tokens: torch.Tensor, chunk: int = 256) -> to
     tokens = tokens.to(device=w.ln_flat.device, dtype=torch.int64).contiguous()
     run = TowerRunner(w, min(chunk, n))
     out = torch.empty(n, w.E, dtype=torch.float32, device=w.ln_flat.device)
+    inv = torch.empty(n, dtype=torch.float32, device=w.ln_flat.device)
     eot = tokens.argmax(dim=-1).to(torch.int32)   # eot_token is the highest id in each sequence (model.py:352-354)
     for s in range(0, n, chunk):
         e = min(n, s + chunk)
         tk = tokens[s:e].contiguous()
         x = run.forward(e - s, w.ln_flat, tokens=tk)
         rows = (torch.arange(e - s, device=tk.device, dtype=torch.int32) * L + eot[s:e]).contiguous()
-        run.head(x, e - s, w.ln_flat, row_idx=rows, feat=out[s:e])
-    return out
+        run.head(x, e - s, w.ln_flat, row_idx=rows, feat=out[s:e], inv_norm=inv[s:e])
+    return out if normalized else out / inv[:, None]
 
 
 def image_features(w: TowerWeights, images: torch.Tensor, chunk: int = 256) -> torch.Tensor:

@@ -1,0 +1,177 @@
+"""RLCF evaluation driver for image-encoder (LayerNorm) tuning -- the loop of TPT/tune_cls_rl.py:183-256, batched.
+
+The reference adapts one test image per iteration.  Every image restarts from the same weights and an empty Adam
+state (tune_cls_rl.py:210-213), so images are independent: this driver gathers `images_per_step` samples from the
+loader, adapts them in ONE batched launch sequence (CUDA graph) and scores each adapted prediction.  With
+--momentum_update 1 the reset state depends on sample order (custom_clip.py:460-475) and the driver falls back to
+the reference's one-at-a-time order.
+
+Multi-GPU: one process per GPU (torchrun); rank r evaluates samples r, r+R, ...; the only collective is one
+all-reduce of (top-1 hits, top-5 hits, count) per dataset.
+
+    python -m rlcf_b200.tune_cls_rl --synthetic -a ViT-B/16 --reward_arch ViT-L/14 --tpt --tune_norm 1 \
+        --batch_size 64 --selection_p 0.1 --tta_steps 1 --sample_k 3 --n_images 64
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+from copy import deepcopy
+
+import torch
+
+from . import synthetic
+from .clip.custom_clip import CLIPCLS_TTA
+from .clip_reward import get_reward_model
+from .params import get_args
+from .tpt_cls_rl import engine_config, test_time_tuning
+from .utils.tools import AverageMeter, ProgressMeter, Summary, accuracy, set_random_seed
+
+
+def _stack_views(images, device):
+    """One loader sample -> [V,3,H,W] on the device (tune_cls_rl.py:194-207: list of [1,3,H,W] views or a tensor)."""
+    if isinstance(images, (list, tuple)):
+        return torch.cat([im.to(device, non_blocking=True) for im in images], dim=0)
+    if images.dim() > 4:
+        images = images.squeeze(0)
+    return images.to(device, non_blocking=True)
+
+
+def test_time_adapt_eval(val_loader, model, optimizer, optim_state, scaler, args, device=None, reward_model=None):
+    """Returns [top1, top5] (percent, 3 decimals) over this rank's share of the loader, summed over ranks."""
+    device = device if device is not None else torch.device("cuda", args.gpu)
+    batch_time = AverageMeter("Time", ":6.3f", Summary.NONE)
+    top1 = AverageMeter("Acc@1", ":6.2f", Summary.AVERAGE)
+    top5 = AverageMeter("Acc@5", ":6.2f", Summary.AVERAGE)
+    progress = ProgressMeter(len(val_loader), [batch_time, top1, top5], prefix="Test: ")
+    B = 1 if getattr(args, "momentum_update", 0) else max(1, getattr(args, "images_per_step", 8))
+    hits = torch.zeros(3, dtype=torch.int64, device=device)
+    pend_views, pend_targets = [], []
+    end = time.time()
+
+    def flush():
+        nonlocal end
+        n = len(pend_views)
+        if n == 0:
+            return
+        optimizer.load_state_dict(optim_state)                   # tune_cls_rl.py:213
+        views = torch.cat(pend_views, dim=0)
+        target = torch.cat(pend_targets, dim=0)
+        model.train()
+        if n == 1:
+            model.reset()                                        # tune_cls_rl.py:210
+            test_time_tuning(model, views, optimizer, scaler, args, reward_model=reward_model)
+            model.eval()
+            output = model(views[:1])                            # tune_cls_rl.py:220-222
+            model.momentum_update_model()                        # tune_cls_rl.py:240
+        else:
+            cfg = engine_config(args, optimizer, reward_model)
+            cfg.n_views = views.shape[0] // n
+            eng = model.engine(cfg, n, reward_model)
+            model.reset()
+            eng.init_params.copy_(model.clip_model.visual.ln_flat())
+            output = eng.adapt_graph(views.float().contiguous())
+            model.eval()
+        acc1, acc5 = accuracy(output, target, topk=(1, 5))       # tune_cls_rl.py:243-245
+        hits[0] += torch.round(acc1[0] * n / 100).long()
+        hits[1] += torch.round(acc5[0] * n / 100).long()
+        hits[2] += n
+        top1.update(acc1[0], n)
+        top5.update(acc5[0], n)
+        batch_time.update(time.time() - end)
+        end = time.time()
+        pend_views.clear()
+        pend_targets.clear()
+
+    for i, (images, target) in enumerate(val_loader):
+        pend_views.append(_stack_views(images, device))
+        pend_targets.append(target.to(device, non_blocking=True).view(-1)[:1])
+        if len(pend_views) == B:
+            flush()
+        if (i + 1) % args.print_freq == 0:
+            progress.display(i)
+    while pend_views:       # ragged tail: adapt the leftovers one image at a time
+        tail_v, tail_t = pend_views[1:], pend_targets[1:]
+        del pend_views[1:], pend_targets[1:]
+        flush()
+        pend_views.extend(tail_v)
+        pend_targets.extend(tail_t)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.all_reduce(hits, op=torch.distributed.ReduceOp.SUM)
+    progress.display_summary()
+    n = max(1, int(hits[2]))
+    return [round(100.0 * int(hits[0]) / n, 3), round(100.0 * int(hits[1]) / n, 3)]
+
+
+class SyntheticViews(torch.utils.data.Dataset):
+    """Seeded synthetic samples: ([V,3,res,res] views, label); rank r of R sees indices r, r+R, ..."""
+
+    def __init__(self, n_images, n_views, res, n_classes, seed, rank=0, world=1):
+        self.idx = list(range(rank, n_images, world))
+        self.n_views, self.res, self.n_classes, self.seed = n_views, res, n_classes, seed
+
+    def __len__(self):
+        return len(self.idx)
+
+    def __getitem__(self, i):
+        j = self.idx[i]
+        views = synthetic.make_views(1, self.n_views, self.res, self.seed + j)
+        label = torch.tensor(j % self.n_classes)
+        return views, label
+
+
+def main_worker(gpu, args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        gpu = int(os.environ.get("LOCAL_RANK", gpu))
+        torch.cuda.set_device(gpu)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", gpu))
+    args.gpu = gpu
+    set_random_seed(args.seed)
+    if not torch.cuda.is_available():
+        raise SystemExit("rlcf_b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(gpu)
+    device = torch.device("cuda", gpu)
+    if not args.synthetic:
+        raise SystemExit("real datasets are not wired in this build (no data offline); run with --synthetic")
+    arch, reward_arch = "synthetic:" + args.arch + ":0", "synthetic:" + args.reward_arch + ":1"
+    classnames = [f"class {i}" for i in range(args.n_classes)]
+    vocab = synthetic.ARCHS[args.arch][6]
+    tokens = synthetic.make_tokens(args.n_classes, vocab)
+    model = CLIPCLS_TTA(device, classnames, arch=arch, prompt_prefix=args.ctx_init or "a photo of a",
+                        only_visual=True, momentum_update=args.momentum_update, update_freq=args.update_freq,
+                        update_w=args.update_w, momentum=args.tta_momentum, only_norm=args.tune_norm,
+                        tokenized_prompts=tokens)
+    optimizer = torch.optim.AdamW(model.parameters(), args.lr, weight_decay=args.weight_decay)
+    optim_state = deepcopy(optimizer.state_dict())
+    args.reward_arch = reward_arch
+    reward_model = get_reward_model(device, args)
+    reward_model.set_class_features(tokenized_classes=synthetic.make_tokens(
+        args.n_classes, synthetic.ARCHS[reward_arch.split(":")[1]][6]).to(device))
+    scaler = torch.cuda.amp.GradScaler(init_scale=1000)
+    results = {}
+    for set_id in args.test_sets.split("/"):
+        t0 = time.time()
+        ds = SyntheticViews(args.n_images, args.batch_size, args.resolution, args.n_classes, args.seed + 1000,
+                            rank, world)
+        loader = torch.utils.data.DataLoader(ds, batch_size=1, shuffle=False, num_workers=0,
+                                             collate_fn=lambda b: (b[0][0], b[0][1].view(1)))
+        results[set_id] = test_time_adapt_eval(loader, model, optimizer, optim_state, scaler, args, device=device,
+                                               reward_model=reward_model)
+        if rank == 0:
+            dt = time.time() - t0
+            print(f"=> Acc. on testset [{set_id}]: @1 {results[set_id][0]} / @5 {results[set_id][1]}  "
+                  f"({args.n_images / dt:.1f} images/s incl. synthetic view generation)")
+    if rank == 0:
+        with open(os.path.join(args.output, "results.json"), "a+") as fp:
+            json.dump(results, fp, indent=4)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return results
+
+
+if __name__ == "__main__":
+    _args = get_args()
+    main_worker(_args.gpu, _args)

@@ -1,0 +1,137 @@
+"""The reference-facing Python surface (clip.load / CLIPCLS_TTA / get_reward_model / test_time_tuning /
+test_time_adapt_eval) driven exactly like TPT/tune_cls_rl.py drives the reference, checked against the oracle."""
+import argparse
+from copy import deepcopy
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import rlcf_oracle as O  # noqa: E402
+from rlcf_b200 import clip, synthetic  # noqa: E402
+from rlcf_b200.clip.custom_clip import CLIPCLS_TTA  # noqa: E402
+from rlcf_b200.clip_reward import get_clip_reward, get_reward_model  # noqa: E402
+from rlcf_b200.tpt_cls_rl import avg_entropy, select_confident_samples, test_time_tuning  # noqa: E402
+from rlcf_b200.tune_cls_rl import test_time_adapt_eval  # noqa: E402
+
+DEV = torch.device("cuda:0")
+
+
+def make_args(**kw):
+    base = dict(tta_steps=1, selection_p=0.25, batch_size=16, min_entropy_reg=0, multiple_reward_models=0,
+                reward_arch="synthetic:tiny-B:1", reward_amplify=0, sample_k=3, reward_process=1, process_batch=0,
+                momentum_update=0, images_per_step=3, print_freq=1000, gpu=0)
+    base.update(kw)
+    return argparse.Namespace(**base)
+
+
+def test_synthetic_weights_equal_oracle_generator():
+    a, b = synthetic.make_state_dict("tiny-A", 3), O.make_clip_state_dict("tiny-A", 3)
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_load_and_encode():
+    model, embed_dim, preprocess = clip.load("synthetic:tiny-A:0", device=DEV)
+    assert embed_dim == 128 and callable(preprocess)
+    sd = O.make_clip_state_dict("tiny-A", 0)
+    assert set(model.state_dict().keys()) == set(sd.keys())
+    img = O.make_views(1, 4, 64, 2)
+    tok = O.make_tokens(5, 512)
+    with torch.no_grad():
+        ref_i, ref_t = O.encode_image(sd, img), O.encode_text(sd, tok)
+    got_i, got_t = model.encode_image(img.to(DEV)).cpu(), model.encode_text(tok.to(DEV)).cpu()
+    assert (got_i - ref_i).abs().max() < 2e-3 * ref_i.abs().max()
+    assert (got_t - ref_t).abs().max() < 3e-3 * ref_t.abs().max()
+    with pytest.raises(RuntimeError):
+        clip.load("ViT-Z/99", device=DEV)
+    with pytest.raises(RuntimeError):
+        clip.tokenize("word " * 100)
+    assert clip.tokenize("word " * 100, truncate=True).shape == (1, 77)
+
+
+def test_selection_and_entropy_helpers():
+    torch.manual_seed(0)
+    logits = torch.randn(16, 10, device=DEV) * 3
+    out, idx = select_confident_samples(logits, 0.25)
+    ref_out, ref_idx, _ = O.select_confident_samples(logits.cpu(), 0.25)
+    assert torch.equal(idx.cpu(), ref_idx) and torch.equal(out.cpu(), ref_out)
+    assert abs(avg_entropy(out).item() - O.avg_entropy(ref_out).item()) < 1e-5
+
+
+def _setup(args, n_cls=10):
+    tok_p, tok_r = O.make_tokens(n_cls, 512), O.make_tokens(n_cls, 512)
+    model = CLIPCLS_TTA(DEV, [f"class {i}" for i in range(n_cls)], arch="synthetic:tiny-A:0",
+                        prompt_prefix="a photo of a", only_norm=True, tokenized_prompts=tok_p)
+    model = model.cuda(0)
+    optimizer = torch.optim.AdamW(model.parameters(), 5e-3, weight_decay=5e-4)
+    optim_state = deepcopy(optimizer.state_dict())
+    reward_model = get_reward_model(DEV, args)
+    reward_model.set_class_features(tokenized_classes=tok_r.to(DEV))
+    scaler = torch.cuda.amp.GradScaler(init_scale=1000)
+    sd_p, sd_r = O.make_clip_state_dict("tiny-A", 0), O.make_clip_state_dict("tiny-B", 1)
+    return model, optimizer, optim_state, reward_model, scaler, sd_p, sd_r, tok_p, tok_r
+
+
+def test_reference_style_loop_matches_oracle():
+    assert get_clip_reward is get_reward_model
+    args = make_args()
+    model, optimizer, optim_state, reward_model, scaler, sd_p, sd_r, tok_p, tok_r = _setup(args)
+    assert len(list(model.parameters())) == 2 * (2 * 2 + 2)       # LayerNorm weights and biases only
+    cf, rc = O.class_features(sd_p, tok_p), O.class_features(sd_r, tok_r)
+    assert (model.class_features.cpu() - cf).abs().max() < 3e-3
+    views = O.make_views(2, 16, 64, 9)
+    ocfg = O.OracleConfig(n_views=16, selection_p=0.25, tta_steps=1, sample_k=3, lr=5e-3)
+    base = O.flat_ln_params(sd_p)
+    for i in range(2):
+        images = views[i * 16:(i + 1) * 16].to(DEV)
+        model.reset()                                         # tune_cls_rl.py:210
+        optimizer.load_state_dict(optim_state)                # tune_cls_rl.py:213
+        assert torch.equal(model.clip_model.visual.ln_flat().cpu(), base)
+        model.train()
+        test_time_tuning(model, images, optimizer, scaler, args, reward_model=reward_model)
+        model.eval()
+        out = model(images[:1]).cpu()
+        # the oracle sees the class features the CUDA text tower produced (inputs of the per-image loop)
+        ref = O.adapt_one_image(sd_p, model.class_features.cpu(), views[i * 16:(i + 1) * 16], ocfg, sd_r,
+                                reward_model.class_features.cpu())
+        scale = ref["logits_all"].abs().max()
+        delta = (ref["logits_final"] - ref["logits_all"][:1]).abs().max()
+        assert (out - ref["logits_final"]).abs().max() <= 1e-3 * scale + 0.3 * delta
+        moved = (model.clip_model.visual.ln_flat().cpu() - base).abs()
+        assert moved.max() > 1e-3                              # parameters really changed in place ...
+        named = dict(model.clip_model.visual.named_parameters())
+        assert (named["ln_post.weight"].detach().cpu() - sd_p["visual.ln_post.weight"]).abs().max() > 1e-4
+        d = (model.clip_model.visual.ln_flat().cpu() - ref["params"]).abs()
+        assert (d <= 0.02 * 5e-3).float().mean() > 0.9 and d.max() <= 2.02 * 5e-3
+    model.reset()
+    assert torch.equal(model.clip_model.visual.ln_flat().cpu(), base)   # ... and reset() restores them
+
+
+def test_batched_eval_driver_equals_one_at_a_time():
+    args = make_args()
+    model, optimizer, optim_state, reward_model, scaler, *_ = _setup(args)
+    views = O.make_views(7, 16, 64, 13)
+    labels = torch.arange(7) % 10
+    loader = [(views[i * 16:(i + 1) * 16], labels[i:i + 1]) for i in range(7)]   # ragged: 7 = 3 + 3 + 1
+    res_batched = test_time_adapt_eval(loader, model, optimizer, optim_state, scaler, args, device=DEV,
+                                       reward_model=reward_model)
+    args1 = make_args(images_per_step=1)
+    res_single = test_time_adapt_eval(loader, model, optimizer, optim_state, scaler, args1, device=DEV,
+                                      reward_model=reward_model)
+    assert res_batched == res_single
+    assert 0.0 <= res_batched[0] <= res_batched[1] <= 100.0
+
+
+def test_unsupported_modes_fail_loudly():
+    args = make_args()
+    with pytest.raises(NotImplementedError):
+        get_reward_model(DEV, make_args(multiple_reward_models=1))
+    model = CLIPCLS_TTA(DEV, ["a", "b"], arch="synthetic:tiny-A:0", prompt_prefix="a photo of a", only_norm=False,
+                        tokenized_prompts=O.make_tokens(2, 512)).cuda(0)
+    opt = torch.optim.AdamW(model.parameters(), 1e-5)
+    with pytest.raises(NotImplementedError):
+        test_time_tuning(model, O.make_views(1, 16, 64, 1).to(DEV), opt, None, args, reward_model=None)
+    with pytest.raises(Exception):
+        clip.load("synthetic:tiny-A:0", device="cpu")[0].encode_image(torch.zeros(1, 3, 64, 64))  # no CPU fallback

@@ -1,0 +1,136 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol of include/rlcf_b200.h, the host
+logic that needs no device (tokenizer, flags, flat LayerNorm layout, sharding, FLOP accounting) behaves, and a
+world_size-2 gloo run of the accuracy-counter reduction matches the single-process result."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    from rlcf_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "run `python -c 'import __graft_entry__ as g; g.build()'` first"
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _lib.header_symbols()
+    assert len(syms) >= 20
+    missing = [s for s in syms if not hasattr(handle, s)]
+    assert not missing, missing
+    assert set(_lib._PROTOS) == set(syms), set(_lib._PROTOS) ^ set(syms)
+    handle.rlcf_abi_version.restype = ctypes.c_int
+    assert handle.rlcf_abi_version() == 1
+
+
+def test_ops_refuse_cpu_tensors():
+    from rlcf_b200 import _lib, ops
+    a = torch.zeros(8, 64, dtype=torch.float16)
+    with pytest.raises(_lib.RlcfError):
+        ops.gemm(a, a, torch.zeros(8, 8, dtype=torch.float16))
+
+
+def test_flag_names_and_defaults_match_reference():
+    from rlcf_b200.params import build_parser
+    a = build_parser().parse_args([])
+    # TPT/params.py:23-73
+    assert (a.arch, a.batch_size, a.selection_p, a.tta_steps, a.lr, a.weight_decay) == ("RN50", 64, 0.1, 1, 5e-3, 5e-4)
+    assert (a.sample_k, a.reward_arch, a.reward_process, a.process_batch, a.reward_amplify) == (5, "ViT-L/14", 1, 0, 0)
+    assert (a.multiple_reward_models, a.tune_norm, a.momentum_update, a.ctx_init, a.n_ctx, a.seed) == (0, 0, 0, None, 4, 0)
+
+
+def test_flat_layernorm_layout_and_flops():
+    from rlcf_b200 import engine as E
+    w = E.TowerWeights(kind="visual", d=768, heads=12, n_layers=12, L=197, E=512, patch=16)
+    w.ln_flat = torch.zeros((4 * 12 + 4) * 768)
+    assert w.P == 39936
+    assert w.ln_off("ln_pre") == 0 and w.ln_off("ln_1", 0) == 1536 and w.ln_off("ln_2", 11) == 1536 + 11 * 3072 + 1536
+    assert w.ln_off("ln_post") == 39936 - 1536
+    names = [k for k, _ in w.ln_names("visual.")]
+    assert names[0] == "visual.ln_pre.weight" and names[-1] == "visual.ln_post.bias" and len(names) == 52 * 2 // 2
+    offs = [o for _, o in w.ln_names("visual.")]
+    assert offs == sorted(offs) and len(set(offs)) == len(offs)
+    assert abs(E.RlcfEngine.tower_fwd_flops(w) / 1e9 - 35.127) < 0.01
+    assert abs(E.RlcfEngine.tower_dgrad_flops(w) / 1e9 - 36.33) < 0.01
+    r = E.TowerWeights(kind="visual", d=1024, heads=16, n_layers=24, L=257, E=768, patch=14)
+    assert abs(E.RlcfEngine.tower_fwd_flops(r) / 1e9 - 162.026) < 0.01
+    cfg = E.RlcfConfig()
+    assert cfg.n_selected == 6 and E.RlcfConfig(n_views=8).n_selected == 0
+
+
+def test_tokenizer_matches_reference_vectors():
+    vocab = "/root/reference/TPT/clip/bpe_simple_vocab_16e6.txt.gz"
+    if not os.path.exists(vocab):
+        pytest.skip("OpenAI BPE vocabulary not available on this machine")
+    from rlcf_b200.clip.simple_tokenizer import SimpleTokenizer
+    tok = SimpleTokenizer(vocab)
+    # ids produced by the reference tokenizer (TPT/clip/simple_tokenizer.py) for the same strings
+    assert tok.encode("a photo of a great white shark.") == [320, 1125, 539, 320, 830, 1579, 7980, 269]
+    assert tok.encoder["<|startoftext|>"] == 49406 and tok.encoder["<|endoftext|>"] == 49407
+    assert tok.decode(tok.encode("a photo of a tench.")).strip() == "a photo of a tench ."
+
+
+def test_fallback_tokenizer_is_well_formed():
+    from rlcf_b200.clip.simple_tokenizer import SimpleTokenizer
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        os.environ.pop("RLCF_BPE_VOCAB", None)
+        tok = SimpleTokenizer(bpe_path=None) if not os.path.exists(
+            os.path.expanduser("~/.cache/clip/bpe_simple_vocab_16e6.txt.gz")) else None
+    if tok is None:
+        pytest.skip("a real vocabulary is installed")
+    ids = tok.encode("a photo of a dog.")
+    assert ids and max(ids) < 49406
+
+
+def test_synthetic_dataset_sharding():
+    from rlcf_b200.tune_cls_rl import SyntheticViews
+    full = SyntheticViews(10, 4, 32, 5, 0)
+    shards = [SyntheticViews(10, 4, 32, 5, 0, r, 3) for r in range(3)]
+    assert sorted(i for s in shards for i in s.idx) == full.idx
+    v, y = shards[1][0]
+    v0, y0 = full[1]
+    assert torch.equal(v, v0) and int(y) == int(y0) == 1 and v.shape == (4, 3, 32, 32)
+
+
+GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from rlcf_b200.tune_cls_rl import SyntheticViews
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+ds = SyntheticViews(11, 2, 8, 4, 5, r, w)
+# stand-in for the adapted prediction: a deterministic function of the sample, so shards can be compared
+hits = torch.zeros(3, dtype=torch.int64)
+for i in range(len(ds)):
+    v, y = ds[i]
+    pred = int(v.sum().item() * 1000) % 4
+    hits += torch.tensor([int(pred == int(y)), 1, 1])
+dist.all_reduce(hits, op=dist.ReduceOp.SUM)
+if r == 0:
+    print("HITS", hits.tolist())
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_counter_reduction(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script), ROOT],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("HITS")][0]
+    from rlcf_b200.tune_cls_rl import SyntheticViews
+    ds = SyntheticViews(11, 2, 8, 4, 5)
+    exp = [0, 0, 0]
+    for i in range(len(ds)):
+        v, y = ds[i]
+        exp[0] += int(int(v.sum().item() * 1000) % 4 == int(y))
+        exp[1] += 1
+        exp[2] += 1
+    assert line == f"HITS {exp}"
