@@ -13,8 +13,8 @@ from oracle import rlcf_oracle as O  # noqa: E402
 from rlcf_b200 import clip, synthetic  # noqa: E402
 from rlcf_b200.clip.custom_clip import CLIPCLS_TTA  # noqa: E402
 from rlcf_b200.clip_reward import get_clip_reward, get_reward_model  # noqa: E402
-from rlcf_b200.tpt_cls_rl import avg_entropy, select_confident_samples, test_time_tuning  # noqa: E402
-from rlcf_b200.tune_cls_rl import test_time_adapt_eval  # noqa: E402
+from rlcf_b200 import tpt_cls_rl, tune_cls_rl  # noqa: E402  (not `from ... import test_*`: pytest would collect them)
+from rlcf_b200.tpt_cls_rl import avg_entropy, select_confident_samples  # noqa: E402
 
 DEV = torch.device("cuda:0")
 
@@ -90,7 +90,7 @@ def test_reference_style_loop_matches_oracle():
         optimizer.load_state_dict(optim_state)                # tune_cls_rl.py:213
         assert torch.equal(model.clip_model.visual.ln_flat().cpu(), base)
         model.train()
-        test_time_tuning(model, images, optimizer, scaler, args, reward_model=reward_model)
+        tpt_cls_rl.test_time_tuning(model, images, optimizer, scaler, args, reward_model=reward_model)
         model.eval()
         out = model(images[:1]).cpu()
         # the oracle sees the class features the CUDA text tower produced (inputs of the per-image loop)
@@ -115,10 +115,10 @@ def test_batched_eval_driver_equals_one_at_a_time():
     views = O.make_views(7, 16, 64, 13)
     labels = torch.arange(7) % 10
     loader = [(views[i * 16:(i + 1) * 16], labels[i:i + 1]) for i in range(7)]   # ragged: 7 = 3 + 3 + 1
-    res_batched = test_time_adapt_eval(loader, model, optimizer, optim_state, scaler, args, device=DEV,
+    res_batched = tune_cls_rl.test_time_adapt_eval(loader, model, optimizer, optim_state, scaler, args, device=DEV,
                                        reward_model=reward_model)
     args1 = make_args(images_per_step=1)
-    res_single = test_time_adapt_eval(loader, model, optimizer, optim_state, scaler, args1, device=DEV,
+    res_single = tune_cls_rl.test_time_adapt_eval(loader, model, optimizer, optim_state, scaler, args1, device=DEV,
                                       reward_model=reward_model)
     assert res_batched == res_single
     assert 0.0 <= res_batched[0] <= res_batched[1] <= 100.0
@@ -132,6 +132,6 @@ def test_unsupported_modes_fail_loudly():
                         tokenized_prompts=O.make_tokens(2, 512)).cuda(0)
     opt = torch.optim.AdamW(model.parameters(), 1e-5)
     with pytest.raises(NotImplementedError):
-        test_time_tuning(model, O.make_views(1, 16, 64, 1).to(DEV), opt, None, args, reward_model=None)
+        tpt_cls_rl.test_time_tuning(model, O.make_views(1, 16, 64, 1).to(DEV), opt, None, args, reward_model=None)
     with pytest.raises(Exception):
         clip.load("synthetic:tiny-A:0", device="cpu")[0].encode_image(torch.zeros(1, 3, 64, 64))  # no CPU fallback
