@@ -1,11 +1,11 @@
-// tcgen05 fused attention forward for CLIP towers (head_dim 64, L <= 496 tokens).
+// tcgen05 fused attention forward for CLIP towers (head_dim 64, L <= 320 tokens).
 //
 // One CTA = 128 query rows of one (sequence, head).  The whole key/value range of the sequence is resident in
 // shared memory (L <= 257 for every configured tower), so there is no KV loop and no online-softmax rescaling:
 //   TMA     : Q tile [128 x 64], K and V tiles [Lk x 64] (Lk = L rounded up to 16), 128-byte swizzle
 //   UMMA #1 : S[128 x Lk] = Q K^T            (SS, both K-major; fp32 accumulator in TMEM columns [0, Lk))
-//   softmax : one thread per query row reads its S row from TMEM (tcgen05.ld), max / exp2 / sum in fp32,
-//             writes P as packed fp16 back into TMEM columns [0, Lk/2) (tcgen05.st)
+//   softmax : two threads per query row each read half of the S row from TMEM (tcgen05.ld), max / exp2 / sum in
+//             fp32, and write P as packed fp16 back into TMEM columns [0, Lk/2) (tcgen05.st)
 //   UMMA #2 : O[128 x 64] = P V              (TS: A = P from TMEM, B = V from smem, MN-major)
 //   epilogue: O / rowsum -> fp16 -> global, 128 contiguous bytes per row; optional log-sum-exp for the backward
 // Two CTAs are co-resident per SM (<= 84 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the
@@ -47,7 +47,10 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__global__ void __launch_bounds__(128)
+constexpr int kMaxChunksPerGroup = 5;  // 32-column S chunks per thread: Lk <= 320
+constexpr int kAttnThreads = 256;  // two threads per query row: warps 0-3 and 4-7 split the key columns / O columns
+
+__global__ void __launch_bounds__(kAttnThreads)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKV, AttnTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -56,8 +59,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   uint8_t* sV = sK + p.Lk * 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + p.Lk * 128);  // [0] loads, [1] S ready, [2] O ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* xchg = reinterpret_cast<float*>(bars + 4);               // [2][128] partial row max, [2][128] partial row sum
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int grp = warp >> 2;            // 0: first half of the key chunks / O columns [0,32); 1: the rest
+  const int r = tid & 127;              // query row inside the tile (= TMEM lane)
   const int q0 = blockIdx.x * 128, h = blockIdx.y, seq = blockIdx.z;
   const int d = p.heads * 64;
   const int row_base = seq * p.L;
@@ -101,44 +107,72 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   }
   __syncwarp();
 
-  // ------------------------------------------------------------ softmax: thread = query row
+  // ------------------------------------------------------------ softmax: two threads per query row
   mbar_wait(&bars[1], 0);
   tc_fence_after();
-  const int qrow = q0 + tid;  // query index inside the sequence
-  const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const int qrow = q0 + r;  // query index inside the sequence
+  const uint32_t trow = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
   const int n_chunks = (p.Lk + 31) >> 5;
+  const int split = (n_chunks + 1) >> 1;
+  const int ch_begin = grp == 0 ? 0 : split, ch_end = grp == 0 ? split : n_chunks;
   const int key_end = p.causal ? min(p.L, qrow + 1) : p.L;  // keys [0, key_end) are visible to this row
+  // a warp whose 32 rows all lie beyond the sequence does no softmax work (its rows are never stored)
+  const bool warp_live = q0 + (warp & 3) * 32 < p.L;
   float m = -INFINITY;
-  for (int ch = 0; ch < n_chunks; ++ch) {
-    uint32_t r[32];
-    tmem_ld_32x32(trow + ch * 32, r);
-    tmem_ld_wait();
+  if (warp_live) {
+    for (int ch = ch_begin; ch < ch_end; ++ch) {
+      uint32_t v[32];
+      tmem_ld_32x32(trow + ch * 32, v);
+      tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) m = fmaxf(m, (ch * 32 + j < key_end) ? __uint_as_float(r[j]) : -INFINITY);
+      for (int j = 0; j < 32; ++j) m = fmaxf(m, (ch * 32 + j < key_end) ? __uint_as_float(v[j]) : -INFINITY);
+    }
   }
+  xchg[grp * 128 + r] = m;
+  __syncthreads();
+  m = fmaxf(m, xchg[(grp ^ 1) * 128 + r]);
   const float mc = m * c;
   float l = 0.f;
-  for (int ch = 0; ch < n_chunks; ++ch) {
-    uint32_t r[32];
-    tmem_ld_32x32(trow + ch * 32, r);
-    tmem_ld_wait();
-    uint32_t pk[16];
+  // P chunk ch (packed fp16) goes to TMEM columns [16 ch, 16 ch + 16).  For group 0 these are S columns the same
+  // thread has already consumed.  Group 1's P columns overlap S chunks that group 0 may still be reading, so
+  // group 1 keeps its packed chunks in registers until group 0 has finished its second pass (barrier A).
+  uint32_t pkbuf[kMaxChunksPerGroup][16];
+  if (warp_live) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float a = (ch * 32 + 2 * j < key_end) ? exp2f(fmaf(__uint_as_float(r[2 * j]), c, -mc)) : 0.f;
-      const float b = (ch * 32 + 2 * j + 1 < key_end) ? exp2f(fmaf(__uint_as_float(r[2 * j + 1]), c, -mc)) : 0.f;
-      // the row sum uses the fp16-rounded probabilities that the P V product actually sees
-      const __half2 hp = __floats2half2_rn(a, b);
-      const float2 back = __half22float2(hp);
-      l += back.x + back.y;
-      pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
+    for (int i = 0; i < kMaxChunksPerGroup; ++i) {
+      const int ch = ch_begin + i;
+      if (ch < ch_end) {  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(trow + ch * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = (ch * 32 + 2 * j < key_end) ? exp2f(fmaf(__uint_as_float(v[2 * j]), c, -mc)) : 0.f;
+          const float b = (ch * 32 + 2 * j + 1 < key_end) ? exp2f(fmaf(__uint_as_float(v[2 * j + 1]), c, -mc)) : 0.f;
+          // the row sum uses the fp16-rounded probabilities that the P V product actually sees
+          const __half2 hp = __floats2half2_rn(a, b);
+          const float2 back = __half22float2(hp);
+          l += back.x + back.y;
+          pkbuf[i][j] = *reinterpret_cast<const uint32_t*>(&hp);
+        }
+        if (grp == 0) tmem_st_32x16(trow + ch * 16, pkbuf[i]);
+      }
     }
-    tmem_st_32x16(trow + ch * 16, pk);  // overwrites S columns that this row has already consumed
+    if (grp == 0) tmem_st_wait();
   }
-  tmem_st_wait();
+  xchg[256 + grp * 128 + r] = l;
+  __syncthreads();  // barrier A: group 0 has consumed all of its S columns
+  if (grp == 1 && warp_live) {
+#pragma unroll
+    for (int i = 0; i < kMaxChunksPerGroup; ++i) {
+      const int ch = ch_begin + i;
+      if (ch < ch_end) tmem_st_32x16(trow + ch * 16, pkbuf[i]);
+    }
+    tmem_st_wait();
+  }
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();  // barrier B: P complete in TMEM
 
   if (tid == 0) {
     tc_fence_after();
@@ -150,20 +184,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     umma_commit(&bars[2]);
   }
   __syncwarp();
+  l += xchg[256 + (grp ^ 1) * 128 + r];
 
-  // ------------------------------------------------------------ epilogue
+  // ------------------------------------------------------------ epilogue: each thread stores 32 of the 64 columns
   mbar_wait(&bars[2], 0);
   tc_fence_after();
-  {
-    uint32_t o[64];
-    tmem_ld_32x32(trow + p.o_off, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
-    tmem_ld_32x32(trow + p.o_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+  if (warp_live) {
+    uint32_t o[32];
+    tmem_ld_32x32(trow + p.o_off + grp * 32, o);
     tmem_ld_wait();
     if (qrow < p.L) {
       const float inv = 1.f / l;
-      uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(row_base + qrow)) * d + h * 64);
+      uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(row_base + qrow)) * d + h * 64 + grp * 32);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 4; ++j) {
         __half2 h0 = __floats2half2_rn(__uint_as_float(o[8 * j + 0]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
         __half2 h1 = __floats2half2_rn(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
         __half2 h2 = __floats2half2_rn(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
@@ -171,7 +205,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         dst[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
                             *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
       }
-      if (p.lse != nullptr)
+      if (p.lse != nullptr && grp == 0)
         p.lse[(static_cast<size_t>(seq) * p.heads + h) * p.L + qrow] = m * 0.125f + logf(l);
     }
   }
@@ -198,7 +232,7 @@ static int make_tmap_rows64(CUtensorMap* map, const void* base, long long rows, 
 int attention_fwd_tc(const __half* qkv, int n_seq, int L, int heads, int causal, __half* out, float* lse,
                      cudaStream_t stream) {
   const int Lk = (L + 15) / 16 * 16;
-  if (Lk > 496 || (reinterpret_cast<uintptr_t>(qkv) & 15) != 0) return -1;
+  if (Lk > 32 * 2 * kMaxChunksPerGroup || (reinterpret_cast<uintptr_t>(qkv) & 15) != 0) return -1;
   AttnTcArgs a{};
   a.L = L; a.Lk = Lk; a.heads = heads; a.causal = causal; a.out = out; a.lse = lse;
   if (Lk <= 256) {
@@ -210,7 +244,7 @@ int attention_fwd_tc(const __half* qkv, int n_seq, int L, int heads, int causal,
   a.o_off = ((Lk / 2) + 31) / 32 * 32;
   const int need = max(Lk, a.o_off + 64);
   a.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
-  const size_t smem = 1024 + 128 * 128 + 2 * static_cast<size_t>(Lk) * 128 + 64;
+  const size_t smem = 1024 + 128 * 128 + 2 * static_cast<size_t>(Lk) * 128 + 64 + 4 * 128 * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -223,7 +257,7 @@ int attention_fwd_tc(const __half* qkv, int n_seq, int L, int heads, int causal,
   if (int rc = make_tmap_rows64(&mq, qkv, rows, 3 * heads * 64, 128)) return rc;
   if (int rc = make_tmap_rows64(&mkv, qkv, rows, 3 * heads * 64, a.kv_box_rows)) return rc;
   dim3 grid((L + 127) / 128, heads, n_seq);
-  attn_fwd_tc_kernel<<<grid, 128, smem, stream>>>(mq, mkv, a);
+  attn_fwd_tc_kernel<<<grid, kAttnThreads, smem, stream>>>(mq, mkv, a);
   RLCF_CHECK_LAUNCH("attention_fwd_tc");
   return 0;
 }

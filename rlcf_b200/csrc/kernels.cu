@@ -362,50 +362,83 @@ int layernorm_bwd(const void* dy, int dy_is_f32, long long lddy, const float* x,
 
 // ------------------------------------------------------------------------------------------------ head fwd
 // ln_post(x[:,0]) @ proj (model.py:235-238) -> f/|f| -> logit_scale * f @ class_feat^T (custom_clip.py:423-432).
-// One block per sequence. Dynamic smem: y[d] + f[E] + scratch[16].
+// One block handles VPC sequences so that every proj / class_feat element fetched from L2 is used VPC times.
+// Everything stays fp32 (the final features are never rounded to fp16).  Dynamic smem: yT[d][VPC] + f[VPC][E].
 constexpr int kHeadThreads = 256;
+template <int VPC>
 __global__ void __launch_bounds__(kHeadThreads)
 head_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_idx, long long row_stride,
                 const float* __restrict__ gamma, const float* __restrict__ beta, long long pstride, int seqs_per_set,
-                const float* __restrict__ proj, const float* __restrict__ cls_feat, float logit_scale, int d, int E,
-                int C, float eps, float* __restrict__ feat, float* __restrict__ inv_norm, float* __restrict__ logits) {
+                const float* __restrict__ proj, const float* __restrict__ cls_feat, float logit_scale, int n, int d,
+                int E, int C, float eps, float* __restrict__ feat, float* __restrict__ inv_norm,
+                float* __restrict__ logits) {
   extern __shared__ float sm[];
-  float* y = sm;
-  float* f = sm + d;
-  float* scratch = f + E;
-  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long row = row_idx ? row_idx[n] : n * row_stride;
-  const float* xr = x + row * d;
-  float s = 0.f;
-  for (int i = tid; i < d; i += kHeadThreads) { y[i] = xr[i]; s += y[i]; }
-  const float mean = block_sum<kHeadThreads>(s, scratch) / d;
-  float q = 0.f;
-  for (int i = tid; i < d; i += kHeadThreads) { const float a = y[i] - mean; q += a * a; }
-  const float rstd = 1.0f / sqrtf(block_sum<kHeadThreads>(q, scratch) / d + eps);
-  const long long po = static_cast<long long>(n / seqs_per_set) * pstride;
-  for (int i = tid; i < d; i += kHeadThreads) y[i] = (y[i] - mean) * rstd * gamma[po + i] + beta[po + i];
+  float* yT = sm;            // [d][VPC]
+  float* f = sm + d * VPC;   // [VPC][E]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n0 = blockIdx.x * VPC;
+  const int nv = min(VPC, n - n0);
+  // LayerNorm of each sequence's row by one warp (two-pass statistics)
+  for (int v = warp; v < VPC; v += kHeadThreads / 32) {
+    if (v < nv) {
+      const int s = n0 + v;
+      const long long row = row_idx ? row_idx[s] : s * row_stride;
+      const float* xr = x + row * d;
+      float sum = 0.f;
+      for (int i = lane; i < d; i += 32) sum += xr[i];
+      const float mean = warp_sum(sum) / d;
+      float q = 0.f;
+      for (int i = lane; i < d; i += 32) { const float a = xr[i] - mean; q += a * a; }
+      const float rstd = 1.0f / sqrtf(warp_sum(q) / d + eps);
+      const long long po = static_cast<long long>(s / seqs_per_set) * pstride;
+      for (int i = lane; i < d; i += 32) yT[i * VPC + v] = (xr[i] - mean) * rstd * gamma[po + i] + beta[po + i];
+    } else {
+      for (int i = lane; i < d; i += 32) yT[i * VPC + v] = 0.f;
+    }
+  }
   __syncthreads();
-  float ss = 0.f;
   for (int j = tid; j < E; j += kHeadThreads) {
-    float acc = 0.f;
-    for (int i = 0; i < d; ++i) acc = fmaf(y[i], __ldg(proj + static_cast<size_t>(i) * E + j), acc);
-    f[j] = acc;
-    ss += acc * acc;
+    float acc[VPC];
+#pragma unroll
+    for (int v = 0; v < VPC; ++v) acc[v] = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < d; ++i) {
+      const float pj = __ldg(proj + static_cast<size_t>(i) * E + j);
+#pragma unroll
+      for (int v = 0; v < VPC; ++v) acc[v] = fmaf(yT[i * VPC + v], pj, acc[v]);
+    }
+#pragma unroll
+    for (int v = 0; v < VPC; ++v) f[v * E + j] = acc[v];
   }
-  const float inv = 1.0f / sqrtf(block_sum<kHeadThreads>(ss, scratch));
-  for (int j = tid; j < E; j += kHeadThreads) {
-    f[j] *= inv;
-    if (feat) feat[static_cast<size_t>(n) * E + j] = f[j];
+  __syncthreads();
+  for (int v = warp; v < nv; v += kHeadThreads / 32) {
+    float ss = 0.f;
+    for (int j = lane; j < E; j += 32) ss += f[v * E + j] * f[v * E + j];
+    const float inv = 1.0f / sqrtf(warp_sum(ss));
+    for (int j = lane; j < E; j += 32) {
+      const float val = f[v * E + j] * inv;
+      f[v * E + j] = val;
+      if (feat) feat[static_cast<size_t>(n0 + v) * E + j] = val;
+    }
+    if (inv_norm && lane == 0) inv_norm[n0 + v] = inv;
   }
-  if (inv_norm && tid == 0) inv_norm[n] = inv;
   __syncthreads();
   if (logits) {
     for (int c = warp; c < C; c += kHeadThreads / 32) {
       const float* t = cls_feat + static_cast<size_t>(c) * E;
-      float acc = 0.f;
-      for (int j = lane; j < E; j += 32) acc = fmaf(f[j], __ldg(t + j), acc);
-      acc = warp_sum(acc);
-      if (lane == 0) logits[static_cast<size_t>(n) * C + c] = logit_scale * acc;
+      float acc[VPC];
+#pragma unroll
+      for (int v = 0; v < VPC; ++v) acc[v] = 0.f;
+      for (int j = lane; j < E; j += 32) {
+        const float tj = __ldg(t + j);
+#pragma unroll
+        for (int v = 0; v < VPC; ++v) acc[v] = fmaf(f[v * E + j], tj, acc[v]);
+      }
+#pragma unroll
+      for (int v = 0; v < VPC; ++v) {
+        const float r = warp_sum(acc[v]);
+        if (lane == 0 && v < nv) logits[static_cast<size_t>(n0 + v) * C + c] = logit_scale * r;
+      }
     }
   }
 }
@@ -415,9 +448,24 @@ int head_fwd(const float* x, const int32_t* row_idx, long long row_stride, const
              int d, int E, int C, float eps, float* feat, float* inv_norm, float* logits, cudaStream_t stream) {
   if (n <= 0 || d <= 0 || E <= 0 || seqs_per_set <= 0) return set_error(RLCF_ERR_ARG, "head_fwd: bad shape");
   if (logits && (cls_feat == nullptr || C <= 0)) return set_error(RLCF_ERR_ARG, "head_fwd: logits need class_feat");
-  const size_t smem = (d + E + 16) * sizeof(float);
-  head_fwd_kernel<<<n, kHeadThreads, smem, stream>>>(x, row_idx, row_stride, gamma, beta, pstride, seqs_per_set, proj,
-                                                     cls_feat, logit_scale, d, E, C, eps, feat, inv_norm, logits);
+  const int vpc = n >= 8 * 148 / 2 ? 8 : (n >= 64 ? 4 : 1);
+  const size_t smem = static_cast<size_t>(vpc) * (d + E) * sizeof(float);
+  if (smem > 227 * 1024) return set_error(RLCF_ERR_ARG, "head_fwd: width too large");
+#define RLCF_HEAD_LAUNCH(V)                                                                                       \
+  {                                                                                                               \
+    static size_t configured = 0;                                                                                 \
+    if (smem > 48 * 1024 && smem > configured) {                                                                  \
+      cudaError_t e = cudaFuncSetAttribute(head_fwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                           static_cast<int>(smem));                                               \
+      if (e != cudaSuccess) return set_error(RLCF_ERR_CUDA, "head_fwd attr: %s", cudaGetErrorString(e));          \
+      configured = smem;                                                                                          \
+    }                                                                                                             \
+    head_fwd_kernel<V><<<(n + V - 1) / V, kHeadThreads, smem, stream>>>(                                          \
+        x, row_idx, row_stride, gamma, beta, pstride, seqs_per_set, proj, cls_feat, logit_scale, n, d, E, C, eps, \
+        feat, inv_norm, logits);                                                                                  \
+  }
+  if (vpc == 8) RLCF_HEAD_LAUNCH(8) else if (vpc == 4) RLCF_HEAD_LAUNCH(4) else RLCF_HEAD_LAUNCH(1)
+#undef RLCF_HEAD_LAUNCH
   RLCF_CHECK_LAUNCH("head_fwd");
   return 0;
 }

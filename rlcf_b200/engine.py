@@ -20,7 +20,7 @@ import torch
 from . import ops
 from ._lib import EPI_F16, EPI_F32, EPI_GELU_BWD_F16, EPI_GELU_F16, EPI_RESID_F32, RlcfError
 
-N_SLOTS = 8  # gradient partial slots per parameter set (deterministic two-stage reduction)
+N_SLOTS = 32  # gradient partial slots per parameter set = LN-backward blocks per image (deterministic reduction)
 
 
 def _round_up(x, m):
