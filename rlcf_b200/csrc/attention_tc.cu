@@ -1,15 +1,23 @@
-// tcgen05 fused attention forward for CLIP towers (head_dim 64, L <= 320 tokens).
+// Persistent tcgen05 fused attention forward for CLIP towers (head_dim 64, L <= 272 tokens).
 //
-// One CTA = 128 query rows of one (sequence, head).  The whole key/value range of the sequence is resident in
+// Work unit ("tile") = 128 query rows of one (sequence, head).  The whole key/value range of the sequence fits in
 // shared memory (L <= 257 for every configured tower), so there is no KV loop and no online-softmax rescaling:
 //   TMA     : Q tile [128 x 64], K and V tiles [Lk x 64] (Lk = L rounded up to 16), 128-byte swizzle
-//   UMMA #1 : S[128 x Lk] = Q K^T            (SS, both K-major; fp32 accumulator in TMEM columns [0, Lk))
-//   softmax : two threads per query row each read half of the S row from TMEM (tcgen05.ld), max / exp2 / sum in
-//             fp32, and write P as packed fp16 back into TMEM columns [0, Lk/2) (tcgen05.st)
-//   UMMA #2 : O[128 x 64] = P V              (TS: A = P from TMEM, B = V from smem, MN-major)
-//   epilogue: O / rowsum -> fp16 -> global, 128 contiguous bytes per row; optional log-sum-exp for the backward
-// Two CTAs are co-resident per SM (<= 84 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the
-// other's loads and MMAs.  Replaces the bmm-softmax-bmm of nn.MultiheadAttention (TPT/clip/model.py:185-187).
+//   UMMA #1 : S[128 x min(Lk,256)] = Q K^T   (SS, both K-major; fp32 accumulator in TMEM)
+//   softmax : one thread per query row reads its S row from TMEM (tcgen05.ld), max / exp2 / sum in fp32, and writes
+//             P as packed fp16 back into the TMEM columns it has already consumed (tcgen05.st); the at most 16 keys
+//             beyond column 256 (key 256 of ViT-L/14's 257 tokens) are scored on CUDA cores so that a tile never
+//             needs more than 256 TMEM columns
+//   UMMA #2 : O[128 x 64] = P V              (TS: A = P from TMEM, B = V from smem as an MN-major operand)
+//   epilogue: O / rowsum -> fp16 -> global (128 contiguous bytes per row); optional log-sum-exp for the backward
+//
+// One CTA per SM runs two independent "teams"; each team owns one shared-memory stage, 256 TMEM columns, a TMA
+// thread, an MMA-issuing thread and four softmax warps, and walks every second tile of the CTA's tile list.  While one
+// team is in its softmax, the other team's loads and MMAs proceed, so launch, allocation and load latencies are paid
+// once per CTA instead of once per tile.  Replaces the bmm-softmax-bmm of nn.MultiheadAttention
+// (TPT/clip/model.py:185-187).
+#include <cstdlib>
+
 #include "ptx.cuh"
 #include "rlcf_internal.h"
 
@@ -18,9 +26,11 @@ namespace rlcf {
 struct AttnTcArgs {
   int L, Lk, heads, causal;
   int kv_box_rows, n_kv_boxes;  // TMA boxes covering the Lk key rows
-  int n0, n1;                   // UMMA N of the one or two key chunks of S (n0 + n1 == Lk)
-  int o_off;                    // TMEM column of the O accumulator (behind P, inside the dead S region)
-  int tmem_cols;
+  int n_mma;                    // UMMA N of S = min(Lk, 256); keys [n_mma, L) are scored on CUDA cores
+  int o_off;                    // TMEM column (inside the team's 256) of the O accumulator
+  int n_qt, n_units;            // query tiles per (sequence, head); number of (sequence, head) units
+  int stage_bytes;
+  int debug;                    // RLCF_ATTN_DEBUG bit mask (timing probes only): 1 skip max pass, 2 skip exp pass, 4 skip stores
   __half* out;
   float* lse;
 };
@@ -45,173 +55,296 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-constexpr int kMaxChunksPerGroup = 5;  // 32-column S chunks per thread: Lk <= 320
-constexpr int kAttnThreads = 256;  // two threads per query row: warps 0-3 and 4-7 split the key columns / O columns
+constexpr int kAttnThreads = 384;  // warps 0/3: TMA (team 0/1), warps 1/2: MMA (team 0/1), warps 4-7 / 8-11: softmax
+constexpr int kMaxExtraKeys = 16;
 
-__global__ void __launch_bounds__(kAttnThreads)
+// barrier indices inside a team's block of 10
+enum { B_KVFULL = 0, B_KVFREE = 1, B_QFULL = 2 /*+buf*/, B_QFREE = 4 /*+buf*/, B_SREADY = 6, B_PREADY = 7, B_OREADY = 8,
+       B_TMEMFREE = 9, B_PER_TEAM = 10 };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// max over the visible keys of one 32-column S chunk
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], float m, int ch, bool full, int key_end) {
+  if (full) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) m = fmaxf(m, (ch * 32 + j < key_end) ? __uint_as_float(v[j]) : -INFINITY);
+  }
+  return m;
+}
+
+// p = 2^(s c - m c) for one chunk; writes the packed fp16 P chunk to TMEM columns [16 ch, 16 ch + 16) -- S columns
+// this row has already consumed -- and returns the chunk's row-sum contribution
+__device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t trow, int ch, bool full, int key_end,
+                                           float c, float mc) {
+  uint32_t pk[16];
+  float l = 0.f;
+  if (full) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float a = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -mc));
+      const float b = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c, -mc));
+      l += a + b;
+      const __half2 hp = __floats2half2_rn(a, b);
+      pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float a = (ch * 32 + 2 * j < key_end) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -mc)) : 0.f;
+      const float b = (ch * 32 + 2 * j + 1 < key_end) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c, -mc)) : 0.f;
+      l += a + b;
+      const __half2 hp = __floats2half2_rn(a, b);
+      pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
+    }
+  }
+  tmem_st_32x16(trow + ch * 16, pk);
+  return l;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKV, AttnTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + 128 * 128;
-  uint8_t* sV = sK + p.Lk * 128;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + p.Lk * 128);  // [0] loads, [1] S ready, [2] O ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-  float* xchg = reinterpret_cast<float*>(bars + 4);               // [2][128] partial row max, [2][128] partial row sum
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * p.stage_bytes);  // [2 teams][B_PER_TEAM]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * B_PER_TEAM);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int grp = warp >> 2;            // 0: first half of the key chunks / O columns [0,32); 1: the rest
-  const int r = tid & 127;              // query row inside the tile (= TMEM lane)
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, seq = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = p.heads * 64;
-  const int row_base = seq * p.L;
 
   if (tid == 0) {
     tma_prefetch_desc(&mapQ);
     tma_prefetch_desc(&mapKV);
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_init(&bars[2], 1);
+    for (int t = 0; t < 2; ++t) {
+      uint64_t* b = bars + t * B_PER_TEAM;
+      for (int i = 0; i < B_PER_TEAM; ++i) mbar_init(&b[i], 1);
+      mbar_init(&b[B_PREADY], 4);    // one arrive per softmax warp
+      mbar_init(&b[B_TMEMFREE], 4);
+    }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<1>(tmem_slot, p.tmem_cols);
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
 
-  if (tid == 0) {
-    mbar_expect_tx(&bars[0], 128 * 128 + 2 * p.Lk * 128);
-    tma_load_2d(sQ, &mapQ, &bars[0], h * 64, row_base + q0);
-    for (int b = 0; b < p.n_kv_boxes; ++b) {
-      tma_load_2d(sK + b * p.kv_box_rows * 128, &mapKV, &bars[0], d + h * 64, row_base + b * p.kv_box_rows);
-      tma_load_2d(sV + b * p.kv_box_rows * 128, &mapKV, &bars[0], 2 * d + h * 64, row_base + b * p.kv_box_rows);
-    }
-    mbar_wait(&bars[0], 0);
-    tc_fence_after();
-    // S = Q K^T, one UMMA chain per key chunk (N <= 256 per instruction)
-    const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ));
-    int n_off = 0;
-    for (int ch = 0; ch < 2; ++ch) {
-      const int n = ch == 0 ? p.n0 : p.n1;
-      if (n == 0) break;
-      const uint64_t dk = umma_desc_k_sw128(smem_u32(sK) + n_off * 128);
-      const uint32_t idesc = umma_idesc_f16(128, n);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) umma_f16_ss<1>(tmem + n_off, dq + 2 * k, dk + 2 * k, idesc, k != 0);
-      n_off += n;
-    }
-    umma_commit(&bars[1]);
-  }
-  __syncwarp();
+  // role of this warp: team and kind
+  const int team = warp >= 4 ? (warp - 4) >> 2 : (warp == 0 || warp == 1 ? 0 : 1);
+  uint64_t* tb = bars + team * B_PER_TEAM;
+  uint8_t* sQ = smem + team * p.stage_bytes;     // two Q buffers of 16 KB
+  uint8_t* sK = sQ + 2 * 128 * 128;
+  uint8_t* sV = sK + p.Lk * 128;
+  const uint32_t tmem = tmem_base + team * 256;
+  // units (sequence, head) of this CTA: u = blockIdx.x + i * gridDim.x; team t takes i = t, t + 2, ...
+  // K and V of a unit stay in shared memory while the team walks the unit's n_qt query tiles.
+  const int first = blockIdx.x + team * gridDim.x, stride = 2 * gridDim.x;
 
-  // ------------------------------------------------------------ softmax: two threads per query row
-  mbar_wait(&bars[1], 0);
-  tc_fence_after();
-  const int qrow = q0 + r;  // query index inside the sequence
-  const uint32_t trow = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-  const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-  const int n_chunks = (p.Lk + 31) >> 5;
-  const int split = (n_chunks + 1) >> 1;
-  const int ch_begin = grp == 0 ? 0 : split, ch_end = grp == 0 ? split : n_chunks;
-  const int key_end = p.causal ? min(p.L, qrow + 1) : p.L;  // keys [0, key_end) are visible to this row
-  // a warp whose 32 rows all lie beyond the sequence does no softmax work (its rows are never stored)
-  const bool warp_live = q0 + (warp & 3) * 32 < p.L;
-  float m = -INFINITY;
-  if (warp_live) {
-    for (int ch = ch_begin; ch < ch_end; ++ch) {
-      uint32_t v[32];
-      tmem_ld_32x32(trow + ch * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) m = fmaxf(m, (ch * 32 + j < key_end) ? __uint_as_float(v[j]) : -INFINITY);
-    }
-  }
-  xchg[grp * 128 + r] = m;
-  __syncthreads();
-  m = fmaxf(m, xchg[(grp ^ 1) * 128 + r]);
-  const float mc = m * c;
-  float l = 0.f;
-  // P chunk ch (packed fp16) goes to TMEM columns [16 ch, 16 ch + 16).  For group 0 these are S columns the same
-  // thread has already consumed.  Group 1's P columns overlap S chunks that group 0 may still be reading, so
-  // group 1 keeps its packed chunks in registers until group 0 has finished its second pass (barrier A).
-  uint32_t pkbuf[kMaxChunksPerGroup][16];
-  if (warp_live) {
-#pragma unroll
-    for (int i = 0; i < kMaxChunksPerGroup; ++i) {
-      const int ch = ch_begin + i;
-      if (ch < ch_end) {  // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32(trow + ch * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a = (ch * 32 + 2 * j < key_end) ? exp2f(fmaf(__uint_as_float(v[2 * j]), c, -mc)) : 0.f;
-          const float b = (ch * 32 + 2 * j + 1 < key_end) ? exp2f(fmaf(__uint_as_float(v[2 * j + 1]), c, -mc)) : 0.f;
-          // the row sum uses the fp16-rounded probabilities that the P V product actually sees
-          const __half2 hp = __floats2half2_rn(a, b);
-          const float2 back = __half22float2(hp);
-          l += back.x + back.y;
-          pkbuf[i][j] = *reinterpret_cast<const uint32_t*>(&hp);
+  if (warp == 0 || warp == 3) {
+    // ------------------------------------------------------------ TMA producer of this team
+    if (lane == 0) {
+      uint32_t uc = 0, tc = 0;
+      for (int u = first; u < p.n_units; u += stride, ++uc) {
+        const int h = u % p.heads, seq = u / p.heads;
+        const int row_base = seq * p.L;
+        mbar_wait(&tb[B_KVFREE], (uc & 1) ^ 1);
+        mbar_expect_tx(&tb[B_KVFULL], 2 * p.Lk * 128);
+        for (int b = 0; b < p.n_kv_boxes; ++b) {
+          tma_load_2d(sK + b * p.kv_box_rows * 128, &mapKV, &tb[B_KVFULL], d + h * 64, row_base + b * p.kv_box_rows);
+          tma_load_2d(sV + b * p.kv_box_rows * 128, &mapKV, &tb[B_KVFULL], 2 * d + h * 64, row_base + b * p.kv_box_rows);
         }
-        if (grp == 0) tmem_st_32x16(trow + ch * 16, pkbuf[i]);
+        for (int qt = 0; qt < p.n_qt; ++qt, ++tc) {
+          const int buf = tc & 1;
+          mbar_wait(&tb[B_QFREE + buf], ((tc >> 1) & 1) ^ 1);
+          mbar_expect_tx(&tb[B_QFULL + buf], 128 * 128);
+          tma_load_2d(sQ + buf * 128 * 128, &mapQ, &tb[B_QFULL + buf], h * 64, row_base + qt * 128);
+        }
       }
     }
-    if (grp == 0) tmem_st_wait();
-  }
-  xchg[256 + grp * 128 + r] = l;
-  __syncthreads();  // barrier A: group 0 has consumed all of its S columns
-  if (grp == 1 && warp_live) {
+  } else if (warp == 1 || warp == 2) {
+    // ------------------------------------------------------------ MMA issuer of this team
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_f16(128, p.n_mma);
+      const uint32_t idesc_o = umma_idesc_f16(128, 64) | (1u << 16);  // B (= V) is MN-major
+      const uint64_t dk = umma_desc_k_sw128(smem_u32(sK));
+      const uint64_t dv = umma_desc_k_sw128(smem_u32(sV));
+      const int ksteps = p.Lk >> 4;
+      uint32_t uc = 0, tc = 0;
+      for (int u = first; u < p.n_units; u += stride, ++uc) {
+        mbar_wait(&tb[B_KVFULL], uc & 1);
+        for (int qt = 0; qt < p.n_qt; ++qt, ++tc) {
+          const int buf = tc & 1;
+          const uint32_t ph = tc & 1;
+          const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ + buf * 128 * 128));
+          mbar_wait(&tb[B_QFULL + buf], (tc >> 1) & 1);
+          mbar_wait(&tb[B_TMEMFREE], ph ^ 1);  // the previous tile's O has been read out of TMEM
+          tc_fence_after();
 #pragma unroll
-    for (int i = 0; i < kMaxChunksPerGroup; ++i) {
-      const int ch = ch_begin + i;
-      if (ch < ch_end) tmem_st_32x16(trow + ch * 16, pkbuf[i]);
+          for (int k = 0; k < 4; ++k) umma_f16_ss<1>(tmem, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+          umma_commit(&tb[B_SREADY]);
+          mbar_wait(&tb[B_PREADY], ph);        // softmax has written P (and is done with sQ / sK)
+          tc_fence_after();
+          for (int j = 0; j < ksteps; ++j) umma_f16_ts(tmem + p.o_off, tmem + 8 * j, dv + 128 * j, idesc_o, j != 0);
+          umma_commit(&tb[B_OREADY]);
+          umma_commit(&tb[B_QFREE + buf]);
+          if (qt == p.n_qt - 1) umma_commit(&tb[B_KVFREE]);  // all readers of this unit's K/V have retired
+        }
+      }
     }
-    tmem_st_wait();
+  } else {
+    // ------------------------------------------------------------ softmax + epilogue: thread = query row
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t trow = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    const int n_chunks = (p.n_mma + 31) >> 5;
+    const int n_extra = p.L - p.n_mma;              // keys scored on CUDA cores (<= kMaxExtraKeys), usually <= 0
+    uint32_t tc = 0;
+    for (int u = first; u < p.n_units; u += stride) {
+      const int h = u % p.heads, seq = u / p.heads;
+      for (int qt = 0; qt < p.n_qt; ++qt, ++tc) {
+        const uint32_t ph = tc & 1;
+        const uint8_t* sQb = sQ + (tc & 1) * 128 * 128;
+        const int q0 = qt * 128, qrow = q0 + r;
+        const int key_end = p.causal ? min(p.L, qrow + 1) : p.L;  // keys [0, key_end) are visible to this row
+        const bool warp_live = q0 + (warp & 3) * 32 < p.L;         // rows of a dead warp are never stored
+        // chunks below `full_chunks` are visible to every row of this warp: no masking needed there
+        const int warp_min_end = p.causal ? min(p.L, q0 + (warp & 3) * 32 + 1) : p.L;
+        const int full_chunks = min(n_chunks, warp_min_end >> 5);
+        mbar_wait(&tb[B_SREADY], ph);
+        tc_fence_after();
+        float m = -INFINITY, l = 0.f;
+        float sx[kMaxExtraKeys];
+        if (warp_live) {
+          if (n_extra > 0) {
+            // scores of keys >= 256 from shared memory: q row r and key rows n_mma.. (both 128-byte swizzled rows)
+            const uint4* qr = reinterpret_cast<const uint4*>(sQb + r * 128);
+#pragma unroll
+            for (int e = 0; e < kMaxExtraKeys; ++e) {
+              float acc = 0.f;
+              if (e < n_extra) {
+                const int kr = p.n_mma + e;
+                const uint4* kk = reinterpret_cast<const uint4*>(sK + kr * 128);
+#pragma unroll
+                for (int ck = 0; ck < 8; ++ck) {
+                  const uint4 a = qr[ck ^ (r & 7)], b = kk[ck ^ (kr & 7)];
+                  const __half2* ha = reinterpret_cast<const __half2*>(&a);
+                  const __half2* hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+                  for (int x = 0; x < 4; ++x) {
+                    const float2 fa = __half22float2(ha[x]), fb = __half22float2(hb[x]);
+                    acc = fmaf(fa.x, fb.x, fmaf(fa.y, fb.y, acc));
+                  }
+                }
+                if (kr < key_end) m = fmaxf(m, acc);
+              }
+              sx[e] = acc;
+            }
+          }
+          // ---- pass 1: row maximum (the TMEM load of the next chunk is in flight while a chunk is reduced)
+          if (!(p.debug & 1)) {
+            uint32_t va[32], vb[32];
+            tmem_ld_32x32(trow, va);
+            for (int ch = 0; ch < n_chunks; ch += 2) {
+              tmem_ld_wait();
+              if (ch + 1 < n_chunks) tmem_ld_32x32(trow + (ch + 1) * 32, vb);
+              m = chunk_max(va, m, ch, ch < full_chunks, key_end);
+              if (ch + 1 < n_chunks) {
+                tmem_ld_wait();
+                if (ch + 2 < n_chunks) tmem_ld_32x32(trow + (ch + 2) * 32, va);
+                m = chunk_max(vb, m, ch + 1, ch + 1 < full_chunks, key_end);
+              }
+            }
+          } else {
+            m = 0.f;
+          }
+          // ---- pass 2: p = 2^(s*c - m*c), row sum, packed fp16 P back into consumed S columns
+          const float mc = m * c;
+          if (!(p.debug & 2)) {
+            uint32_t va[32], vb[32];
+            tmem_ld_32x32(trow, va);
+            for (int ch = 0; ch < n_chunks; ch += 2) {
+              tmem_ld_wait();
+              if (ch + 1 < n_chunks) tmem_ld_32x32(trow + (ch + 1) * 32, vb);
+              l += chunk_exp(va, trow, ch, ch < full_chunks, key_end, c, mc);
+              if (ch + 1 < n_chunks) {
+                tmem_ld_wait();
+                if (ch + 2 < n_chunks) tmem_ld_32x32(trow + (ch + 2) * 32, va);
+                l += chunk_exp(vb, trow, ch + 1, ch + 1 < full_chunks, key_end, c, mc);
+              }
+            }
+          }
+          if (p.Lk > p.n_mma) {  // P of the keys beyond column 256: 16 keys = 8 packed columns at [n_mma/2, n_mma/2 + 8)
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int k0 = p.n_mma + 2 * j;
+              const float a = (k0 < key_end) ? ex2_approx(fmaf(sx[2 * j], c, -mc)) : 0.f;
+              const float b = (k0 + 1 < key_end) ? ex2_approx(fmaf(sx[2 * j + 1], c, -mc)) : 0.f;
+              l += a + b;
+              const __half2 hp = __floats2half2_rn(a, b);
+              pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
+            }
+            tmem_st_32x8(trow + (p.n_mma >> 1), pk);
+          }
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tb[B_PREADY]);
+        // ---- epilogue
+        mbar_wait(&tb[B_OREADY], ph);
+        tc_fence_after();
+        if (warp_live) {
+          uint32_t o[64];
+          tmem_ld_32x32(trow + p.o_off, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+          tmem_ld_32x32(trow + p.o_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tb[B_TMEMFREE]);
+          if (qrow < p.L && !(p.debug & 4)) {
+            const float inv = 1.f / l;
+            uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(seq) * p.L + qrow) * d + h * 64);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              __half2 h0 = __floats2half2_rn(__uint_as_float(o[8 * j + 0]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
+              __half2 h1 = __floats2half2_rn(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
+              __half2 h2 = __floats2half2_rn(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
+              __half2 h3 = __floats2half2_rn(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
+              dst[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                  *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+            }
+            if (p.lse != nullptr)
+              p.lse[(static_cast<size_t>(seq) * p.heads + h) * p.L + qrow] = m * 0.125f + logf(l);
+          }
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tb[B_TMEMFREE]);
+        }
+      }
+    }
   }
-  tc_fence_before();
-  __syncthreads();  // barrier B: P complete in TMEM
 
-  if (tid == 0) {
-    tc_fence_after();
-    // O = P V : A = P (TMEM, 8 columns per 16 keys), B = V rows [16 j, 16 j + 16) as an MN-major operand
-    const uint32_t idesc = umma_idesc_f16(128, 64) | (1u << 16);
-    const uint64_t dv = umma_desc_k_sw128(smem_u32(sV));
-    const int ksteps = p.Lk >> 4;
-    for (int j = 0; j < ksteps; ++j) umma_f16_ts(tmem + p.o_off, tmem + 8 * j, dv + 128 * j, idesc, j != 0);
-    umma_commit(&bars[2]);
-  }
   __syncwarp();
-  l += xchg[256 + (grp ^ 1) * 128 + r];
-
-  // ------------------------------------------------------------ epilogue: each thread stores 32 of the 64 columns
-  mbar_wait(&bars[2], 0);
-  tc_fence_after();
-  if (warp_live) {
-    uint32_t o[32];
-    tmem_ld_32x32(trow + p.o_off + grp * 32, o);
-    tmem_ld_wait();
-    if (qrow < p.L) {
-      const float inv = 1.f / l;
-      uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(row_base + qrow)) * d + h * 64 + grp * 32);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        __half2 h0 = __floats2half2_rn(__uint_as_float(o[8 * j + 0]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
-        __half2 h1 = __floats2half2_rn(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
-        __half2 h2 = __floats2half2_rn(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
-        __half2 h3 = __floats2half2_rn(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
-        dst[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                            *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
-      }
-      if (p.lse != nullptr && grp == 0)
-        p.lse[(static_cast<size_t>(seq) * p.heads + h) * p.L + qrow] = m * 0.125f + logf(l);
-    }
-  }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<1>(tmem, p.tmem_cols);
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc<1>(tmem_base, 512);
 }
 
 static int make_tmap_rows64(CUtensorMap* map, const void* base, long long rows, int cols, int box_rows) {
@@ -232,19 +365,19 @@ static int make_tmap_rows64(CUtensorMap* map, const void* base, long long rows, 
 int attention_fwd_tc(const __half* qkv, int n_seq, int L, int heads, int causal, __half* out, float* lse,
                      cudaStream_t stream) {
   const int Lk = (L + 15) / 16 * 16;
-  if (Lk > 32 * 2 * kMaxChunksPerGroup || (reinterpret_cast<uintptr_t>(qkv) & 15) != 0) return -1;
+  if (Lk > 256 + kMaxExtraKeys || (reinterpret_cast<uintptr_t>(qkv) & 15) != 0) return -1;
   AttnTcArgs a{};
   a.L = L; a.Lk = Lk; a.heads = heads; a.causal = causal; a.out = out; a.lse = lse;
-  if (Lk <= 256) {
-    a.kv_box_rows = Lk; a.n_kv_boxes = 1; a.n0 = Lk; a.n1 = 0;
-  } else {
-    a.kv_box_rows = Lk / 2; a.n_kv_boxes = 2;
-    a.n0 = ((Lk / 2) + 15) / 16 * 16; a.n1 = Lk - a.n0;
-  }
-  a.o_off = ((Lk / 2) + 31) / 32 * 32;
-  const int need = max(Lk, a.o_off + 64);
-  a.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
-  const size_t smem = 1024 + 128 * 128 + 2 * static_cast<size_t>(Lk) * 128 + 64 + 4 * 128 * sizeof(float);
+  a.n_mma = Lk < 256 ? Lk : 256;
+  if (Lk <= 256) { a.kv_box_rows = Lk; a.n_kv_boxes = 1; }
+  else { a.kv_box_rows = Lk / 2; a.n_kv_boxes = 2; }
+  a.o_off = ((Lk / 2) + 31) / 32 * 32;   // behind P (Lk/2 packed columns), <= 160, so O ends at <= 224 < 256
+  a.n_qt = (L + 127) / 128;
+  a.n_units = heads * n_seq;
+  a.stage_bytes = 2 * 128 * 128 + 2 * Lk * 128;
+  static const int debug = getenv("RLCF_ATTN_DEBUG") ? atoi(getenv("RLCF_ATTN_DEBUG")) : 0;
+  a.debug = debug;
+  const size_t smem = 1024 + 2 * static_cast<size_t>(a.stage_bytes) + 2 * B_PER_TEAM * 8 + 16;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -256,7 +389,7 @@ int attention_fwd_tc(const __half* qkv, int n_seq, int L, int heads, int causal,
   const long long rows = static_cast<long long>(n_seq) * L;
   if (int rc = make_tmap_rows64(&mq, qkv, rows, 3 * heads * 64, 128)) return rc;
   if (int rc = make_tmap_rows64(&mkv, qkv, rows, 3 * heads * 64, a.kv_box_rows)) return rc;
-  dim3 grid((L + 127) / 128, heads, n_seq);
+  const int grid = a.n_units < sm_count() ? a.n_units : sm_count();
   attn_fwd_tc_kernel<<<grid, kAttnThreads, smem, stream>>>(mq, mkv, a);
   RLCF_CHECK_LAUNCH("attention_fwd_tc");
   return 0;
