@@ -185,7 +185,7 @@ attn_fwd_kernel(const __half* __restrict__ qkv, int L, int Lp, int heads, int ca
 // ------------------------------------------------------------------------------------------------ backward
 // One CTA per (sequence, head).  Phase A: each warp owns 16 queries and produces dQ.  Phase B: each warp owns
 // 16 keys and produces dK, dV.  Both recompute P from Q, K and the saved log-sum-exp.
-constexpr int kBwdWarps = 8;
+constexpr int kBwdWarps = 13;  // 197 tokens = 13 blocks of 16 rows: one block per warp in each phase
 __global__ void __launch_bounds__(kBwdWarps * 32)
 attn_bwd_kernel(const __half* __restrict__ qkv, const __half* __restrict__ out, const __half* __restrict__ dout,
                 const float* __restrict__ lse_in, int L, int Lp, int heads, int causal, __half* __restrict__ dqkv) {

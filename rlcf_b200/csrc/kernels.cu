@@ -363,7 +363,7 @@ int layernorm_bwd(const void* dy, int dy_is_f32, long long lddy, const float* x,
 // ------------------------------------------------------------------------------------------------ head fwd
 // ln_post(x[:,0]) @ proj (model.py:235-238) -> f/|f| -> logit_scale * f @ class_feat^T (custom_clip.py:423-432).
 // One block handles VPC sequences so that every proj / class_feat element fetched from L2 is used VPC times.
-// Everything stays fp32 (the final features are never rounded to fp16).  Dynamic smem: yT[d][VPC] + f[VPC][E].
+// Everything stays fp32 (the final features are never rounded to fp16).  Dynamic smem: yT[d][VPC] + 2 f[VPC][E].
 constexpr int kHeadThreads = 256;
 template <int VPC>
 __global__ void __launch_bounds__(kHeadThreads)
@@ -397,18 +397,34 @@ head_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_idx
     }
   }
   __syncthreads();
-  for (int j = tid; j < E; j += kHeadThreads) {
-    float acc[VPC];
+  // f = y @ proj: thread (jq, half) accumulates 4 adjacent columns over half of the rows of proj with 16-byte loads
+  // (8 independent loads in flight per thread), the two halves are summed through shared memory.
+  {
+    const int E4 = E >> 2;
+    float* fpart = f + VPC * E;   // [VPC][E] partial sums of the upper half
+    for (int jq = tid & 127; jq < E4; jq += 128) {
+      const int half = tid >> 7;
+      const int i0 = half * (d >> 1), i1 = i0 + (d >> 1);
+      float acc[VPC][4];
 #pragma unroll
-    for (int v = 0; v < VPC; ++v) acc[v] = 0.f;
-#pragma unroll 4
-    for (int i = 0; i < d; ++i) {
-      const float pj = __ldg(proj + static_cast<size_t>(i) * E + j);
+      for (int v = 0; v < VPC; ++v) acc[v][0] = acc[v][1] = acc[v][2] = acc[v][3] = 0.f;
+#pragma unroll 8
+      for (int i = i0; i < i1; ++i) {
+        const float4 pj = __ldg(reinterpret_cast<const float4*>(proj + static_cast<size_t>(i) * E) + jq);
 #pragma unroll
-      for (int v = 0; v < VPC; ++v) acc[v] = fmaf(yT[i * VPC + v], pj, acc[v]);
+        for (int v = 0; v < VPC; ++v) {
+          const float yv = yT[i * VPC + v];
+          acc[v][0] = fmaf(yv, pj.x, acc[v][0]); acc[v][1] = fmaf(yv, pj.y, acc[v][1]);
+          acc[v][2] = fmaf(yv, pj.z, acc[v][2]); acc[v][3] = fmaf(yv, pj.w, acc[v][3]);
+        }
+      }
+      float* dst = half == 0 ? f : fpart;
+#pragma unroll
+      for (int v = 0; v < VPC; ++v)
+        *reinterpret_cast<float4*>(dst + v * E + jq * 4) = make_float4(acc[v][0], acc[v][1], acc[v][2], acc[v][3]);
     }
-#pragma unroll
-    for (int v = 0; v < VPC; ++v) f[v * E + j] = acc[v];
+    __syncthreads();
+    for (int j = tid; j < VPC * E; j += kHeadThreads) f[j] += fpart[j];
   }
   __syncthreads();
   for (int v = warp; v < nv; v += kHeadThreads / 32) {
@@ -449,7 +465,8 @@ int head_fwd(const float* x, const int32_t* row_idx, long long row_stride, const
   if (n <= 0 || d <= 0 || E <= 0 || seqs_per_set <= 0) return set_error(RLCF_ERR_ARG, "head_fwd: bad shape");
   if (logits && (cls_feat == nullptr || C <= 0)) return set_error(RLCF_ERR_ARG, "head_fwd: logits need class_feat");
   const int vpc = n >= 8 * 148 / 2 ? 8 : (n >= 64 ? 4 : 1);
-  const size_t smem = static_cast<size_t>(vpc) * (d + E) * sizeof(float);
+  if (E % 4 != 0 || d % 2 != 0) return set_error(RLCF_ERR_ARG, "head_fwd: E must be a multiple of 4 and d even");
+  const size_t smem = static_cast<size_t>(vpc) * (d + 2 * E) * sizeof(float);
   if (smem > 227 * 1024) return set_error(RLCF_ERR_ARG, "head_fwd: width too large");
 #define RLCF_HEAD_LAUNCH(V)                                                                                       \
   {                                                                                                               \
