@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--images-per-step", type=int, default=8)
+    ap.add_argument("--images-per-step", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded CPU-baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     return ap.parse_args()
@@ -209,6 +209,12 @@ def run_b200(args):
     for i in range(W):
         step(batches[i % 2])
     torch.cuda.synchronize()
+    # extra untimed warm-up until ~2 s of work have run, so that clocks / power state are in their steady regime
+    t_warm = time.perf_counter()
+    while time.perf_counter() - t_warm < 2.0:
+        step(batches[0])
+        step(batches[1])
+        torch.cuda.synchronize()
 
     def barrier():
         if dist is not None:
@@ -242,15 +248,23 @@ def run_b200(args):
     # ---------------- end-to-end with host buffers (`e2e`): pinned H2D of every step's views + D2H of the logits
     host_in = [b.cpu().pin_memory() for b in batches]
     host_out = torch.empty(B, wl["n_classes"], dtype=torch.float32).pin_memory()
-    for i in range(2):
-        eng.adapt_host(host_in[i % 2], host_out) if not args.no_graph else None
+    pipe = None if args.no_graph else eng.host_pipeline()
+    if pipe is not None:   # warm the copy path
+        pipe.submit(host_in[0], 0)
+        pipe.run(0, host_out)
     barrier()
     e0.record()
-    for i in range(K):
-        if args.no_graph:
+    if pipe is not None:
+        # software pipeline: the H2D copy of step i+1 (side stream) overlaps the adaptation of step i;
+        # every step's views are copied from pinned host memory inside this timed region
+        pipe.submit(host_in[0], 0)
+        for i in range(K):
+            if i + 1 < K:
+                pipe.submit(host_in[(i + 1) % 2], (i + 1) % 2)
+            pipe.run(i % 2, host_out)
+    else:
+        for i in range(K):
             host_out.copy_(eng.adapt(host_in[i % 2].to(dev, non_blocking=True)), non_blocking=True)
-        else:
-            eng.adapt_host(host_in[i % 2], host_out)
     e1.record()
     barrier()
     ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)

@@ -121,9 +121,9 @@ int rlcf_reward_loss(const float* logits, const int32_t* row_idx, const float* r
 int rlcf_avg_entropy_loss(const float* logits, const int32_t* row_idx, int n_img, int S, int C, float loss_scale,
                           float* dlogits, float* loss, void* stream);
 
-/* Backward of rlcf_head_fwd for the selected views of each image (one block per image, S views each):
+/* Backward of rlcf_head_fwd for the S selected views of each image (one block per view):
  * dlogits -> d feat -> d(LN out) -> ln_post backward.  Writes dx into dres rows (row_idx as in head_fwd) and
- * the ln_post d(gamma), d(beta) into partials[g][0][p_off..p_off+2d). */
+ * view s's ln_post d(gamma), d(beta) into partials[g][s][p_off..p_off+2d)  (requires S <= n_slots). */
 int rlcf_head_bwd(const float* dlogits, const float* x, const int32_t* row_idx, int64_t row_stride,
                   const float* gamma, int64_t param_stride, const float* proj, const float* class_feat,
                   float logit_scale, const float* feat, const float* inv_norm, int n_img, int S, int d, int E, int C,

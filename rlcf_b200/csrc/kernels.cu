@@ -735,8 +735,8 @@ int avg_entropy_loss(const float* logits, const int32_t* row_idx, int n_img, int
 }
 
 // ------------------------------------------------------------------------------------------------ head bwd
-// Reverse of head_fwd for the S selected views of one image (one block per image; views in sequence so the
-// ln_post parameter gradient is reduced in a fixed order).
+// Reverse of head_fwd for one selected view per block (grid = (S, n_img)); view s of image g writes its ln_post
+// d(gamma), d(beta) into gradient slot s of set g, so the reduction over views stays deterministic.
 __global__ void __launch_bounds__(kHeadThreads)
 head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ x, const int32_t* __restrict__ row_idx,
                 long long row_stride, const float* __restrict__ gamma, long long pstride,
@@ -745,73 +745,74 @@ head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ x, 
                 float eps, float* __restrict__ dres, float* __restrict__ partials, int n_slots, long long p_total,
                 long long p_off) {
   extern __shared__ float sm[];
-  float* dl = sm;            // [C]
-  float* df = dl + C;        // [E]
+  float* df = sm;            // [E]   (first: read with 16-byte loads, E % 4 == 0)
   float* dy = df + E;        // [d]
   float* xh = dy + d;        // [d]
   float* scratch = xh + d;   // [16]
-  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* dl = scratch + 16;  // [C]
+  const int img = blockIdx.y, s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* gam = gamma + img * pstride;
-  float dg[4] = {0.f, 0.f, 0.f, 0.f}, db[4] = {0.f, 0.f, 0.f, 0.f};  // d <= 1024 -> <= 4 columns per thread
-  for (int s = 0; s < S; ++s) {
-    const int n = img * S + s;
-    __syncthreads();
-    for (int c = tid; c < C; c += kHeadThreads) dl[c] = dlogits[static_cast<size_t>(n) * C + c];
-    __syncthreads();
-    // d fhat = logit_scale * dlogits @ class_feat
-    float dot = 0.f;
-    for (int j = tid; j < E; j += kHeadThreads) {
-      float acc = 0.f;
-      for (int c = 0; c < C; ++c) acc = fmaf(dl[c], __ldg(cls_feat + static_cast<size_t>(c) * E + j), acc);
-      acc *= logit_scale;
-      df[j] = acc;
-      dot += acc * feat[static_cast<size_t>(n) * E + j];
+  const int n = img * S + s;
+  for (int c = tid; c < C; c += kHeadThreads) dl[c] = dlogits[static_cast<size_t>(n) * C + c];
+  __syncthreads();
+  // d fhat = logit_scale * dlogits @ class_feat   (8 independent loads in flight per thread)
+  float dot = 0.f;
+  for (int j = tid; j < E; j += kHeadThreads) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int c = 0;
+    for (; c + 4 <= C; c += 4) {
+      a0 = fmaf(dl[c + 0], __ldg(cls_feat + static_cast<size_t>(c + 0) * E + j), a0);
+      a1 = fmaf(dl[c + 1], __ldg(cls_feat + static_cast<size_t>(c + 1) * E + j), a1);
+      a2 = fmaf(dl[c + 2], __ldg(cls_feat + static_cast<size_t>(c + 2) * E + j), a2);
+      a3 = fmaf(dl[c + 3], __ldg(cls_feat + static_cast<size_t>(c + 3) * E + j), a3);
     }
-    dot = block_sum<kHeadThreads>(dot, scratch);
-    const float inv = inv_norm[n];
-    // d f = (d fhat - fhat * <fhat, d fhat>) / |f|
-    for (int j = tid; j < E; j += kHeadThreads) df[j] = (df[j] - feat[static_cast<size_t>(n) * E + j] * dot) * inv;
-    __syncthreads();
-    // d y = d f @ proj^T
-    for (int i = warp; i < d; i += kHeadThreads / 32) {
-      const float* pr = proj + static_cast<size_t>(i) * E;
-      float acc = 0.f;
-      for (int j = lane; j < E; j += 32) acc = fmaf(df[j], __ldg(pr + j), acc);
-      acc = warp_sum(acc);
-      if (lane == 0) dy[i] = acc;
-    }
-    // ln_post backward on the class-token row
-    const long long row = row_idx ? row_idx[n] : n * row_stride;
-    const float* xr = x + row * d;
-    float sx = 0.f;
-    for (int i = tid; i < d; i += kHeadThreads) { xh[i] = xr[i]; sx += xh[i]; }
-    const float mean = block_sum<kHeadThreads>(sx, scratch) / d;
-    float sq = 0.f;
-    for (int i = tid; i < d; i += kHeadThreads) { const float a = xh[i] - mean; sq += a * a; }
-    const float rstd = 1.0f / sqrtf(block_sum<kHeadThreads>(sq, scratch) / d + eps);
-    float s1 = 0.f, s2 = 0.f;
-    for (int i = tid; i < d; i += kHeadThreads) {
-      xh[i] = (xh[i] - mean) * rstd;
-      const float g = dy[i] * gam[i];
-      s1 += g;
-      s2 += g * xh[i];
-    }
-    s1 = block_sum<kHeadThreads>(s1, scratch) / d;
-    s2 = block_sum<kHeadThreads>(s2, scratch) / d;
-    float* o = dres + row * d;
-    int q = 0;
-    for (int i = tid; i < d; i += kHeadThreads, ++q) {
-      const float g = dy[i] * gam[i];
-      o[i] = rstd * (g - s1 - xh[i] * s2);
-      dg[q] += dy[i] * xh[i];
-      db[q] += dy[i];
-    }
+    for (; c < C; ++c) a0 = fmaf(dl[c], __ldg(cls_feat + static_cast<size_t>(c) * E + j), a0);
+    const float acc = ((a0 + a1) + (a2 + a3)) * logit_scale;
+    df[j] = acc;
+    dot += acc * feat[static_cast<size_t>(n) * E + j];
   }
-  float* part = partials + (static_cast<long long>(img) * n_slots) * p_total + p_off;
-  int q = 0;
-  for (int i = tid; i < d; i += kHeadThreads, ++q) {
-    part[i] = dg[q];
-    part[d + i] = db[q];
+  dot = block_sum<kHeadThreads>(dot, scratch);
+  const float inv = inv_norm[n];
+  // d f = (d fhat - fhat * <fhat, d fhat>) / |f|
+  for (int j = tid; j < E; j += kHeadThreads) df[j] = (df[j] - feat[static_cast<size_t>(n) * E + j] * dot) * inv;
+  __syncthreads();
+  // d y = d f @ proj^T  (warp per output row, 16-byte loads along E)
+  for (int i = warp; i < d; i += kHeadThreads / 32) {
+    const float4* pr = reinterpret_cast<const float4*>(proj + static_cast<size_t>(i) * E);
+    float acc = 0.f;
+    for (int j4 = lane; j4 < (E >> 2); j4 += 32) {
+      const float4 w = __ldg(pr + j4);
+      const float4 g = reinterpret_cast<const float4*>(df)[j4];
+      acc = fmaf(g.x, w.x, fmaf(g.y, w.y, fmaf(g.z, w.z, fmaf(g.w, w.w, acc))));
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) dy[i] = acc;
+  }
+  // ln_post backward on the class-token row
+  const long long row = row_idx ? row_idx[n] : n * row_stride;
+  const float* xr = x + row * d;
+  float sx = 0.f;
+  for (int i = tid; i < d; i += kHeadThreads) { xh[i] = xr[i]; sx += xh[i]; }
+  const float mean = block_sum<kHeadThreads>(sx, scratch) / d;
+  float sq = 0.f;
+  for (int i = tid; i < d; i += kHeadThreads) { const float a = xh[i] - mean; sq += a * a; }
+  const float rstd = 1.0f / sqrtf(block_sum<kHeadThreads>(sq, scratch) / d + eps);
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = tid; i < d; i += kHeadThreads) {
+    xh[i] = (xh[i] - mean) * rstd;
+    const float g = dy[i] * gam[i];
+    s1 += g;
+    s2 += g * xh[i];
+  }
+  s1 = block_sum<kHeadThreads>(s1, scratch) / d;
+  s2 = block_sum<kHeadThreads>(s2, scratch) / d;
+  float* o = dres + row * d;
+  float* part = partials + (static_cast<long long>(img) * n_slots + s) * p_total + p_off;
+  for (int i = tid; i < d; i += kHeadThreads) {
+    const float g = dy[i] * gam[i];
+    o[i] = rstd * (g - s1 - xh[i] * s2);
+    part[i] = dy[i] * xh[i];
+    part[d + i] = dy[i];
   }
 }
 
@@ -819,13 +820,15 @@ int head_bwd(const float* dlogits, const float* x, const int32_t* row_idx, long 
              long long pstride, const float* proj, const float* cls_feat, float logit_scale, const float* feat,
              const float* inv_norm, int n_img, int S, int d, int E, int C, float eps, float* dres, float* partials,
              int n_slots, long long p_total, long long p_off, cudaStream_t stream) {
-  if (n_img <= 0 || S <= 0 || d <= 0 || d > 1024 || E <= 0 || C <= 0)
+  if (n_img <= 0 || S <= 0 || d <= 0 || d > 1024 || E <= 0 || E % 4 != 0 || C <= 0)
     return set_error(RLCF_ERR_ARG, "head_bwd: bad shape");
+  if (S > n_slots) return set_error(RLCF_ERR_ARG, "head_bwd: %d views per image need at least %d gradient slots", S, S);
   const size_t smem = (static_cast<size_t>(C) + E + 2 * d + 16) * sizeof(float);
   if (smem > 48 * 1024) return set_error(RLCF_ERR_ARG, "head_bwd: C too large for shared memory");
-  head_bwd_kernel<<<n_img, kHeadThreads, smem, stream>>>(dlogits, x, row_idx, row_stride, gamma, pstride, proj,
-                                                         cls_feat, logit_scale, feat, inv_norm, S, d, E, C, eps, dres,
-                                                         partials, n_slots, p_total, p_off);
+  dim3 grid(S, n_img);
+  head_bwd_kernel<<<grid, kHeadThreads, smem, stream>>>(dlogits, x, row_idx, row_stride, gamma, pstride, proj,
+                                                        cls_feat, logit_scale, feat, inv_norm, S, d, E, C, eps, dres,
+                                                        partials, n_slots, p_total, p_off);
   RLCF_CHECK_LAUNCH("head_bwd");
   return 0;
 }

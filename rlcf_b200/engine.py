@@ -275,7 +275,7 @@ class TowerRunner:
                      param_stride=pstride, seqs_per_set=seqs_per_set)
 
     # ------------------------------------------------------------------ backward (LayerNorm parameters only)
-    def backward(self, store: ActStore, n_sets, seqs_per_set, ln, pstride, partials):
+    def backward(self, store: ActStore, n_sets, seqs_per_set, ln, pstride, partials, n_slots=N_SLOTS):
         """Propagates self.dres (gradient w.r.t. the tower output rows, fp32, already filled by head_bwd) down to
         ln_pre, writing every LayerNorm's d(gamma), d(beta) partials.  GEMM weights are frozen: dgrad only."""
         w = self.w
@@ -293,7 +293,7 @@ class TowerRunner:
             ops.gemm(dres16, lw.wproj_t, self.gh, epilogue=EPI_GELU_BWD_F16, aux_in=store.u[l], M=rows)
             ops.gemm(self.gh, lw.wfc_t, self.g16, epilogue=EPI_F16, M=rows)
             off = w.ln_off("ln_2", l)
-            ops.layernorm_bwd(self.g16, store.x_mid[l], lnv[off:], rows_per_set, n_sets, d, partials, N_SLOTS, P, off,
+            ops.layernorm_bwd(self.g16, store.x_mid[l], lnv[off:], rows_per_set, n_sets, d, partials, n_slots, P, off,
                               dx=dres, accumulate=True, param_stride=pstride, dx16=dres16)
             # attention branch
             ops.gemm(dres16, lw.wo_t, self.g16, epilogue=EPI_F16, M=rows)
@@ -301,10 +301,10 @@ class TowerRunner:
                               causal=(w.kind == "text"))
             ops.gemm(self.gqkv, lw.wqkv_t, self.g16, epilogue=EPI_F16, M=rows)
             off = w.ln_off("ln_1", l)
-            ops.layernorm_bwd(self.g16, store.x_in[l], lnv[off:], rows_per_set, n_sets, d, partials, N_SLOTS, P, off,
+            ops.layernorm_bwd(self.g16, store.x_in[l], lnv[off:], rows_per_set, n_sets, d, partials, n_slots, P, off,
                               dx=dres, accumulate=True, param_stride=pstride, dx16=dres16)
         if w.has_ln_pre:
-            ops.layernorm_bwd(dres, store.x_pre, lnv, rows_per_set, n_sets, d, partials, N_SLOTS, P, 0, dx=None,
+            ops.layernorm_bwd(dres, store.x_pre, lnv, rows_per_set, n_sets, d, partials, n_slots, P, 0, dx=None,
                               param_stride=pstride)
 
 
@@ -365,7 +365,8 @@ class RlcfEngine:
         self.params = torch.empty(B, P, **f32)
         self.m = torch.empty(B, P, **f32)
         self.v = torch.empty(B, P, **f32)
-        self.partials = torch.empty(B, N_SLOTS, P, **f32)
+        self.n_slots = max(N_SLOTS, S)   # head_bwd writes one slot per selected view
+        self.partials = torch.empty(B, self.n_slots, P, **f32)
         self.grad = torch.empty(B, P, **f32)
         self.logits_all = torch.empty(B * V, C, **f32)
         self.entropy = torch.empty(B, V, **f32)
@@ -442,9 +443,9 @@ class RlcfEngine:
             off = pol.ln_off("ln_post")
             ops.head_bwd(self.dlogits, xs, self.params.view(-1)[off:], pol.proj, self.class_feat, self.logit_scale,
                          self.feat_sel, self.inv_norm_sel, B, S, pol.d, pol.E, C, self.run.dres, self.partials,
-                         N_SLOTS, P, off, row_stride=pol.L, param_stride=P)
-            self.run.backward(self.store, B, S, self.params, P, self.partials)
-            ops.adamw_step(self.params, self.m, self.v, self.partials, B, N_SLOTS, P, cfg.lr, step,
+                         self.n_slots, P, off, row_stride=pol.L, param_stride=P)
+            self.run.backward(self.store, B, S, self.params, P, self.partials, self.n_slots)
+            ops.adamw_step(self.params, self.m, self.v, self.partials, B, self.n_slots, P, cfg.lr, step,
                            beta1=cfg.betas[0], beta2=cfg.betas[1], eps=cfg.eps, weight_decay=cfg.weight_decay,
                            loss_scale=cfg.loss_scale, grad_out=self.grad)
         return self.params
@@ -486,6 +487,12 @@ class RlcfEngine:
         out_pinned.copy_(self.logits_final, non_blocking=True)
         return out_pinned
 
+    def host_pipeline(self) -> "HostPipeline":
+        """Double-buffered host->device feeding for back-to-back adapt calls (see HostPipeline)."""
+        if self._graph is None:
+            raise RlcfError("capture() the step first")
+        return HostPipeline(self)
+
     # FLOP accounting (2*MACs), SURVEY.md 8(d)
     @staticmethod
     def tower_fwd_flops(w: TowerWeights) -> float:
@@ -507,6 +514,41 @@ class RlcfEngine:
         if self.reward is not None and cfg.loss == "rlcf":
             total += S * self.tower_fwd_flops(self.reward)
         return float(total)
+
+
+class HostPipeline:
+    """Overlaps the pinned-host -> device copy of batch i+1 with the adaptation of batch i.
+
+    submit(images_pinned, slot) enqueues the H2D copy into staging buffer `slot` on a side stream;
+    run(slot, out_pinned) makes the compute stream wait for that copy, moves the batch into the graph's static
+    input (a device-to-device copy, ~0.1 ms per 300 MB), replays the captured step and copies the adapted logits
+    back to pinned host memory.  Every byte of every batch still crosses PCIe inside the caller's timed region."""
+
+    def __init__(self, eng: "RlcfEngine"):
+        self.eng = eng
+        self.copy_stream = torch.cuda.Stream()
+        self.stage = [torch.empty_like(eng._static_images) for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.free = [torch.cuda.Event() for _ in range(2)]
+        cur = torch.cuda.current_stream()
+        for e in self.free:
+            e.record(cur)
+
+    def submit(self, images_pinned: torch.Tensor, slot: int):
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[slot])
+            self.stage[slot].copy_(images_pinned, non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+
+    def run(self, slot: int, out_pinned: torch.Tensor) -> torch.Tensor:
+        eng = self.eng
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.ready[slot])
+        eng._static_images.copy_(self.stage[slot], non_blocking=True)
+        self.free[slot].record(cur)
+        eng._graph.replay()
+        out_pinned.copy_(eng.logits_final, non_blocking=True)
+        return out_pinned
 
 
 def text_features(w: TowerWeights, tokens: torch.Tensor, chunk: int = 256, normalized: bool = True) -> torch.Tensor:

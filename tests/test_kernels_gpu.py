@@ -240,7 +240,7 @@ def test_head_fwd_bwd():
     assert _rel(feat, fh) < 1e-5 and _rel(logits, lg) < 1e-5
     dlog = torch.randn(n, C, device=_dev()) * 0.01
     lg.backward(dlog)
-    p_total, n_slots, p_off = 4 * d, 3, 2 * d
+    p_total, n_slots, p_off = 4 * d, 5, 2 * d
     partials = torch.zeros(n_img, n_slots, p_total, device=_dev())
     dres = torch.zeros(n * L, d, device=_dev())
     ops.head_bwd(dlog, x, params, proj, T, 100.0, feat, inv, n_img, S, d, E, C, dres, partials, n_slots, p_total,
