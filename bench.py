@@ -283,10 +283,17 @@ def run_b200(args):
     achieved = g_flops / (g_ms / 1e3) / 1e12
     flops_img = eng.algorithmic_flops_per_image()
     step_tflops = flops_img * value / world / 1e12
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+    if os.path.exists(tpath) and B == 16:   # DRAM bytes per GEMM launch from the committed ncu capture of this workload
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["dram_bytes_per_launch_avg"], tj["source"]
     roofline = {
         "bound": "tensor", "kernel": "gemm_f16_kernel (tcgen05/TMA, all %d launches of one step)" % len(recs),
         "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
-        "traffic": None, "peak_source": pk["source"] + " (sustained bf16 dense, of measured)",
+        "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": pk["source"] + " (sustained bf16 dense, of measured)",
         "avg_launch_us": 1e3 * g_ms / len(recs), "gemm_share_of_step": g_ms / (ms_total / K),
         "flops_per_launch": g_flops / len(recs),
         "whole_step": {"algorithmic_gflop_per_image": flops_img / 1e9, "achieved_tflops": step_tflops,
