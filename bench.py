@@ -42,6 +42,9 @@ def parse_args():
     ap.add_argument("--images-per-step", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded CPU-baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--torch-gpu-baseline", action="store_true",
+                    help="also time the reference algorithm in plain PyTorch on the GPU (fp16 autocast + GradScaler, "
+                         "one image at a time, 64-view backward) -- the denominator of north_star's 10x target")
     return ap.parse_args()
 
 
@@ -158,6 +161,35 @@ def cpu_baseline_leg():
     dt = time.perf_counter() - t0
     return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "1 image at full config-2 sizes (64 views, 6 selected, B/16 policy + L/14 reward), no warm-up"}
+
+
+def torch_gpu_baseline_leg(dev, n_images=10):
+    """The reference algorithm as the reference runs it on a GPU: eager PyTorch, torch.cuda.amp.autocast fp16 +
+    GradScaler(1000), one image per iteration, backward through all 64 views (TPT/tune_cls_rl.py:87,192-222) --
+    via the oracle port moved to the device.  Reported baseline only; none of this repo's kernels are involved."""
+    from oracle import rlcf_oracle as O
+    wl = WORKLOAD
+    sd_p = O.make_clip_state_dict(wl["policy"], 0)
+    sd_r = O.make_clip_state_dict(wl["reward"], 1)
+    cf = O.class_features(sd_p, O.make_tokens(wl["n_classes"], 49408)).to(dev)
+    rc = O.class_features(sd_r, O.make_tokens(wl["n_classes"], 49408)).to(dev)
+    sd_p = {k: v.to(dev) for k, v in sd_p.items() if k.startswith("visual.") or k == "logit_scale"}
+    sd_r = {k: v.to(dev) for k, v in sd_r.items() if k.startswith("visual.") or k == "logit_scale"}
+    cfg = O.OracleConfig(n_views=wl["n_views"], selection_p=wl["selection_p"], tta_steps=wl["tta_steps"],
+                         sample_k=wl["sample_k"], lr=wl["lr"])
+    views = O.make_views(2, wl["n_views"], 224, 11).to(dev)
+    scaler = torch.amp.GradScaler("cuda", init_scale=1000)
+    V = wl["n_views"]
+    for i in range(3):
+        O.adapt_one_image(sd_p, cf, views[(i % 2) * V:(i % 2 + 1) * V], cfg, sd_r, rc, amp=True, scaler=scaler)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(n_images):
+        O.adapt_one_image(sd_p, cf, views[(i % 2) * V:(i % 2 + 1) * V], cfg, sd_r, rc, amp=True, scaler=scaler)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": n_images / dt, "unit": UNIT, "kind": "oracle port on cuda, eager PyTorch, fp16 autocast + GradScaler",
+            "sample": f"{n_images} images, one per iteration, after 3 warm-up images"}
 
 
 # ------------------------------------------------------------------------------------------------ CUDA arm
@@ -318,6 +350,10 @@ def run_b200(args):
         "accuracy_counters": {"top1_hits": int(hits[0]), "top5_hits": int(hits[1]), "count": int(hits[2]),
                               "note": "random labels on synthetic data; summed over ranks with one NCCL all-reduce"},
     }
+    if world == 1 and args.torch_gpu_baseline:
+        del eng
+        torch.cuda.empty_cache()
+        line["torch_gpu_baseline"] = torch_gpu_baseline_leg(dev)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg()
     print(json.dumps(line), flush=True)

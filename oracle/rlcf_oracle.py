@@ -250,11 +250,16 @@ def ln_param_names(sd: dict) -> list:
 
 
 def adapt_one_image(sd_policy: dict, class_feat: torch.Tensor, views: torch.Tensor, cfg: OracleConfig,
-                    sd_reward: dict | None = None, reward_cls: torch.Tensor | None = None) -> dict:
+                    sd_reward: dict | None = None, reward_cls: torch.Tensor | None = None, amp: bool = False,
+                    scaler=None) -> dict:
     """One iteration of the per-image loop of TPT/tune_cls_rl.py:192-222 in LayerNorm-tuning mode
     (--tune_norm 1): reset -> test_time_tuning (TPT/tpt_cls_rl.py:47-79) -> adapted prediction on views[0].
     fp32 on CPU: torch.cuda.amp.autocast and GradScaler are no-ops without CUDA, so the scaler lines
-    (tpt_cls_rl.py:77-79) reduce to loss.backward(); optimizer.step()."""
+    (tpt_cls_rl.py:77-79) reduce to loss.backward(); optimizer.step().  amp=True (+ a GradScaler) reproduces the
+    reference's GPU execution mode -- fp16 autocast around the forward (tpt_cls_rl.py:52) and scaled backward -- and is
+    used only by bench.py's optional PyTorch-on-GPU baseline leg."""
+    import contextlib
+    autocast = (lambda: torch.autocast(device_type=views.device.type, dtype=torch.float16)) if amp else contextlib.nullcontext
     names = ln_param_names(sd_policy)
     sd = {k: v.clone() for k, v in sd_policy.items()}                    # model.reset(), tune_cls_rl.py:210
     params = [sd[n].requires_grad_(True) for n in names]
@@ -262,6 +267,7 @@ def adapt_one_image(sd_policy: dict, class_feat: torch.Tensor, views: torch.Tens
     out = {"losses": [], "grads": []}
     selected_idx = None
     for _ in range(cfg.tta_steps):
+      with autocast():
         if selected_idx is not None:
             output = policy_logits(sd, class_feat, views[selected_idx])                      # tpt_cls_rl.py:55
         else:
@@ -286,12 +292,17 @@ def adapt_one_image(sd_policy: dict, class_feat: torch.Tensor, views: torch.Tens
             out.setdefault("rewards", []).append(rewards.reshape(bs, -1))
         else:
             loss = avg_entropy(output)                                                       # tpt_cls.py:49-78
-        opt.zero_grad()
-        loss.backward()
-        out["grads"].append(torch.cat([p.grad.flatten() for p in params]).clone())
-        opt.step()
-        out["losses"].append(float(loss))
-    with torch.no_grad():
+      opt.zero_grad()
+      if scaler is not None:                                                                 # tpt_cls_rl.py:77-79
+          scaler.scale(loss).backward()
+          scaler.step(opt)
+          scaler.update()
+      else:
+          loss.backward()
+          out["grads"].append(torch.cat([p.grad.flatten() for p in params]).clone())
+          opt.step()
+      out["losses"].append(float(loss.detach()))
+    with torch.no_grad(), autocast():
         out["logits_final"] = policy_logits(sd, class_feat, views[:1])                       # tune_cls_rl.py:218-222
     out["params"] = torch.cat([p.detach().flatten() for p in params])
     return out
