@@ -77,7 +77,7 @@ int rlcf_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const fl
 /* LayerNorm backward.  dy is fp16 (dy_is_f32 = 0) or fp32 rows lddy apart; x is the saved LN input.
  *   dx_accum != NULL : dx_accum[row] (+)= dLN/dx   (accumulate = 1 adds to the residual-stream gradient)
  *   dx16 != NULL     : fp16 copy [rows, d] of the updated dx_accum rows (A operand of the next dgrad GEMM)
- *   partials         : [n_sets, n_slots, p_total] fp32; block b of set g writes d(gamma) at
+ *   partials         : (may be NULL when the LayerNorm is frozen) [n_sets, n_slots, p_total] fp32; block b of set g writes d(gamma) at
  *                      partials[g][b][p_off .. p_off+d) and d(beta) at [p_off+d .. p_off+2d).
  * n_slots blocks are launched per set. */
 int rlcf_layernorm_bwd(const void* dy, int dy_is_f32, int64_t lddy, const float* x, int64_t ldx, const float* gamma,
@@ -128,6 +128,30 @@ int rlcf_head_bwd(const float* dlogits, const float* x, const int32_t* row_idx, 
                   const float* gamma, int64_t param_stride, const float* proj, const float* class_feat,
                   float logit_scale, const float* feat, const float* inv_norm, int n_img, int S, int d, int E, int C,
                   float eps, float* dres, float* partials, int n_slots, int64_t p_total, int64_t p_off, void* stream);
+
+/* Generalised head backward: sequence q of set g has dlogits[g*dl_set_stride + q*dl_seq_stride + k*dl_k_stride],
+ * k < K, taken against other_feat + g*other_set_stride ([K,E]).  With the roles of image and text swapped this is the
+ * backward of the TEXT head in prompt tuning (custom_clip.py:62-73,315-335): sequences = class prompts, K = selected
+ * views, other_feat = that image's view features.  partials may be NULL (frozen LayerNorm). */
+int rlcf_head_bwd_ex(const float* dlogits, int64_t dl_set_stride, int64_t dl_seq_stride, int64_t dl_k_stride,
+                     const float* x, const int32_t* row_idx, int64_t row_stride, const float* gamma,
+                     int64_t param_stride, const float* proj, const float* other_feat, int64_t other_set_stride,
+                     float logit_scale, const float* feat, const float* inv_norm, int n_sets, int seqs_per_set, int d,
+                     int E, int K, float eps, float* dres, float* partials, int n_slots, int64_t p_total, int64_t p_off,
+                     void* stream);
+
+/* Prompt assembly (PromptLearner.forward, class token at the end, custom_clip.py:198-232) + positional embedding:
+ * x[(g,c,t)] = (1 <= t <= n_ctx ? ctx[g*ctx_stride + (t-1)*d ..] : tok_emb[tokens[c,t]]) + pos[t]. */
+int rlcf_embed_prompts(const int64_t* tokens, const float* tok_emb, const float* pos, const float* ctx,
+                       int64_t ctx_stride, int n_ctx, int n_sets, int n_cls, int L, int d, float* x, void* stream);
+
+/* logits[g,s,c] = logit_scale * <img_feat[g,s,:], txt_feat[g*txt_set_stride + c*E ..]>  (custom_clip.py:325-335). */
+int rlcf_pair_logits(const float* img_feat, const float* txt_feat, int64_t txt_set_stride, int n_sets, int S, int C,
+                     int E, float logit_scale, float* logits, void* stream);
+
+/* dctx[g,i,:] = sum over the n_cls prompts of set g of dx[(g*n_cls + c)*L + 1 + i, :]  (gradient of the learnable
+ * context vectors, tpt_cls_rl.py:103-105,119-120). */
+int rlcf_ctx_grad(const float* dx, int n_sets, int n_cls, int L, int n_ctx, int d, float* dctx, void* stream);
 
 /* Fused gradient reduction + AdamW (torch.optim.AdamW semantics, tune_cls_rl.py:79-81, tpt_cls_rl.py:76-79):
  * g = sum over slots of partials / loss_scale; decoupled weight decay; bias-corrected moments.

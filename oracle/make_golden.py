@@ -38,7 +38,14 @@ CASES = {
                            reward_seed=3),   # seed 1 gives all-negative cosines -> all CLIPScores clipped to 0
     "b16_l14_cfg2": dict(policy="ViT-B/16", reward="ViT-L/14", V=64, rho=0.1, K=3, C=200, steps=1, lr=5e-3, n_img=1),
 }
+PROMPT_CASES = {
+    # prompt tuning (TPT/tpt_cls_rl.py + ClipTestTimeTuning): real BPE tokenizer, ctx_init "a_photo_of_a" (4 tokens)
+    "tiny_prompt_rlcf_2step": dict(policy="tiny-P", reward="tiny-Q", V=16, rho=0.25, K=3, C=12, steps=2, lr=5e-3,
+                                   n_img=2, ctx_init="a_photo_of_a", loss="rlcf"),
+}
 POLICY_SEED, REWARD_SEED, VIEW_SEED, TOKEN_SEED = 0, 1, 11, 7
+CLASSNAMES = ["tench", "goldfish", "great white shark", "tiger shark", "hammerhead", "electric ray", "stingray",
+              "cock", "hen", "ostrich", "brambling", "goldfinch", "house finch", "junco", "indigo bunting", "robin"]
 
 
 def import_reference():
@@ -145,13 +152,95 @@ def run_case(name: str, cfg: dict, mods) -> dict:
     return out
 
 
+def run_prompt_case(name: str, cfg: dict, mods) -> dict:
+    """tpt_cls_rl.py:82-279 with get_coop's model class (ClipTestTimeTuning) on one synthetic 'dataset'."""
+    custom_clip, clip_model, clip_reward, tpt_cls_rl = mods
+    import clip.clip as ref_clip
+    sd_p = O.make_clip_state_dict(cfg["policy"], POLICY_SEED)
+    sd_r = O.make_clip_state_dict(cfg["reward"], cfg.get("reward_seed", REWARD_SEED))
+
+    def fake_load(sd):
+        def load(arch, device="cpu", jit=False, download_root=None):
+            model = clip_model.build_model({k: v.clone() for k, v in sd.items()}).to(device).float()
+            return model, sd["text_projection"].shape[1], None
+        return load
+
+    custom_clip.load = fake_load(sd_p)
+    custom_clip.tokenize = ref_clip.tokenize            # the reference's real BPE tokenizer
+    clip_reward.clip.load = fake_load(sd_r)
+    args = argparse.Namespace(
+        tta_steps=cfg["steps"], selection_p=cfg["rho"], min_entropy_reg=False, min_entropy_w=0.0,
+        multiple_reward_models=0, reward_arch=cfg["reward"], reward_amplify=0, sample_k=cfg["K"], reward_process=1,
+        process_batch=0)
+    classnames = CLASSNAMES[:cfg["C"]]
+    model = custom_clip.ClipTestTimeTuning("cpu", classnames, None, arch=cfg["policy"], n_ctx=4,
+                                           ctx_init=cfg["ctx_init"])
+    for n, prm in model.named_parameters():                                          # tpt_cls_rl.py:103-105
+        if "prompt_learner" not in n:
+            prm.requires_grad_(False)
+    optimizer = torch.optim.AdamW(model.prompt_learner.parameters(), cfg["lr"], weight_decay=5e-4)
+    optim_state = copy.deepcopy(optimizer.state_dict())
+    reward_model = clip_reward.get_reward_model("cpu", args)
+    reward_model.set_class_features(tokenized_classes=model.prompt_learner.tokenized_prompts)   # tpt_cls_rl.py:189-191
+    scaler = torch.cuda.amp.GradScaler(init_scale=1000)
+    rec = {}
+    orig_select = tpt_cls_rl.select_confident_samples
+
+    def select(logits, top):
+        out, idx = orig_select(logits, top)
+        rec["logits_all"], rec["selected_idx"] = logits.detach().clone(), idx.clone()
+        return out, idx
+
+    orig_score, orig_post = reward_model.CLIPScore, reward_model.rewards_post_process
+
+    def score(class_index, **kw):
+        rec.setdefault("topk_idx", []).append(class_index.clone())
+        return orig_score(class_index=class_index, **kw)
+
+    def post(cs):
+        r = orig_post(cs)
+        rec.setdefault("rewards", []).append(r.clone())
+        return r
+
+    tpt_cls_rl.select_confident_samples = select
+    reward_model.CLIPScore, reward_model.rewards_post_process = score, post
+    views = O.make_views(cfg["n_img"], cfg["V"], O.ARCHS[cfg["policy"]][1], VIEW_SEED)
+    out = {}
+    S, K = int(cfg["V"] * cfg["rho"]), cfg["K"]
+    try:
+        model.eval()
+        for i in range(cfg["n_img"]):
+            rec.clear()
+            images = views[i * cfg["V"]:(i + 1) * cfg["V"]]
+            with torch.no_grad():
+                model.reset()                                                        # tpt_cls_rl.py:250-252
+            optimizer.load_state_dict(optim_state)
+            tpt_cls_rl.test_time_tuning(model, images, optimizer, scaler, args, reward_model=reward_model)
+            with torch.no_grad():
+                final = model(images[:1])
+            out[f"img{i}.logits_all"] = rec["logits_all"].numpy()
+            out[f"img{i}.selected_idx"] = rec["selected_idx"].numpy()
+            out[f"img{i}.topk_idx"] = torch.stack([t.reshape(S, K) for t in rec["topk_idx"]]).numpy()
+            out[f"img{i}.rewards"] = torch.stack([t.reshape(S, K) for t in rec["rewards"]]).numpy()
+            out[f"img{i}.logits_final"] = final.numpy()
+            out[f"img{i}.params"] = model.prompt_learner.ctx.detach().flatten().numpy().copy()
+    finally:
+        tpt_cls_rl.select_confident_samples = orig_select
+    out["tokens"] = model.prompt_learner.tokenized_prompts.numpy()
+    out["ctx_init"] = model.prompt_learner.ctx_init_state.numpy()
+    out["reward_cls"] = reward_model.class_features.numpy()
+    out["meta"] = np.array(repr(cfg))
+    return out
+
+
 def main():
-    which = sys.argv[1:] or list(CASES)
+    which = sys.argv[1:] or (list(CASES) + list(PROMPT_CASES))
     torch.manual_seed(0)
     mods = import_reference()
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     for name in which:
-        out = run_case(name, CASES[name], mods)
+        out = run_prompt_case(name, PROMPT_CASES[name], mods) if name in PROMPT_CASES else \
+            run_case(name, CASES[name], mods)
         path = os.path.join(ROOT, "tests", "golden", name + ".npz")
         np.savez_compressed(path, **out)
         print(name, "->", path, {k: v.shape for k, v in out.items() if k.startswith("img0")})

@@ -32,6 +32,9 @@ ARCHS = {
     # small towers for fast CPU tests / golden vectors (same code paths: head_dim 64, odd token counts)
     "tiny-A": (128, 64, 2, 128, 16, 77, 512, 128, 2, 2),     # 17 image tokens
     "tiny-B": (256, 64, 3, 256, 8, 77, 512, 128, 2, 2),      # 65 image tokens (reward model in tests)
+    # same towers with CLIP's full vocabulary, for cases tokenised by the real BPE tokenizer (prompt tuning)
+    "tiny-P": (128, 64, 2, 128, 16, 77, 49408, 128, 2, 2),
+    "tiny-Q": (256, 64, 3, 256, 8, 77, 49408, 128, 2, 2),
 }
 
 
@@ -156,7 +159,12 @@ def encode_image(sd: dict, images: torch.Tensor) -> torch.Tensor:
 
 def encode_text(sd: dict, tokens: torch.Tensor) -> torch.Tensor:
     """CLIP.encode_text (TPT/clip/model.py:342-356): un-normalised text features [N, E]."""
-    x = sd["token_embedding.weight"][tokens] + sd["positional_embedding"]
+    return text_from_embeddings(sd, sd["token_embedding.weight"][tokens], tokens)
+
+
+def text_from_embeddings(sd: dict, prompts: torch.Tensor, tokens: torch.Tensor) -> torch.Tensor:
+    """TextEncoder.forward (TPT/clip/custom_clip.py:62-73) == the tail of CLIP.encode_text (model.py:345-356)."""
+    x = prompts + sd["positional_embedding"]
     L, d = x.shape[1], x.shape[2]
     mask = torch.full((L, L), float("-inf")).triu_(1)                                       # model.py:328-334
     for l in range(_n_layers(sd, "")):
@@ -305,6 +313,67 @@ def adapt_one_image(sd_policy: dict, class_feat: torch.Tensor, views: torch.Tens
     with torch.no_grad(), autocast():
         out["logits_final"] = policy_logits(sd, class_feat, views[:1])                       # tune_cls_rl.py:218-222
     out["params"] = torch.cat([p.detach().flatten() for p in params])
+    return out
+
+
+def prompt_text_features(sd: dict, tokens: torch.Tensor, ctx: torch.Tensor) -> torch.Tensor:
+    """PromptLearner.forward with the class token at the end (TPT/clip/custom_clip.py:198-232) followed by
+    ClipTestTimeTuning.get_text_features (315-323): L2-normalised text features [C, E], differentiable in ctx."""
+    emb = sd["token_embedding.weight"][tokens]                         # frozen prefix (SOS) and suffix (class, EOS)
+    n_ctx = ctx.shape[0]
+    prompts = torch.cat([emb[:, :1, :], ctx.unsqueeze(0).expand(tokens.shape[0], -1, -1), emb[:, 1 + n_ctx:, :]], dim=1)
+    t = text_from_embeddings(sd, prompts, tokens)
+    return t / t.norm(dim=-1, keepdim=True)
+
+
+def adapt_one_image_prompt(sd_policy: dict, tokens: torch.Tensor, ctx_init: torch.Tensor, views: torch.Tensor,
+                           cfg: OracleConfig, sd_reward: dict | None = None,
+                           reward_cls: torch.Tensor | None = None) -> dict:
+    """One iteration of the per-image loop of TPT/tpt_cls_rl.py:219-279 (prompt tuning): reset the context vectors,
+    test_time_tuning (47-79) with ClipTestTimeTuning.inference (custom_clip.py:325-335: image tower under no_grad,
+    text tower differentiable), AdamW on ctx only (tpt_cls_rl.py:103-120), adapted prediction on views[0]."""
+    ctx = ctx_init.clone().requires_grad_(True)                                              # prompt_learner.reset()
+    opt = torch.optim.AdamW([ctx], cfg.lr, weight_decay=cfg.weight_decay)
+    scale = sd_policy["logit_scale"].exp()
+
+    def model(images):
+        with torch.no_grad():
+            f = encode_image(sd_policy, images)
+        f = f / f.norm(dim=-1, keepdim=True)
+        return scale * f @ prompt_text_features(sd_policy, tokens, ctx).t()
+
+    out = {"losses": [], "grads": []}
+    selected_idx = None
+    for _ in range(cfg.tta_steps):
+        if selected_idx is not None:
+            output = model(views[selected_idx])
+        else:
+            logits_all = model(views)
+            output, selected_idx, ent = select_confident_samples(logits_all, cfg.selection_p)
+            out["logits_all"], out["entropy"], out["selected_idx"] = logits_all.detach(), ent.detach(), selected_idx
+            if cfg.loss == "rlcf":
+                reward_img = reward_image_features(sd_reward, views[selected_idx])
+        bs = output.shape[0]
+        if cfg.loss == "rlcf":
+            _, index = torch.topk(output, cfg.sample_k, dim=-1)
+            flat = index.flatten()
+            score = clip_score(reward_cls, reward_img, flat, cfg.sample_k)
+            rewards = rewards_post_process(score if cfg.process_batch else score.reshape(bs, -1),
+                                           cfg.reward_process, cfg.reward_amplify)
+            all_loss = F.cross_entropy(torch.repeat_interleave(output, cfg.sample_k, dim=0), flat, reduction="none")
+            loss = torch.mean(rewards * all_loss)
+            out.setdefault("topk_idx", []).append(index)
+            out.setdefault("rewards", []).append(rewards.reshape(bs, -1))
+        else:
+            loss = avg_entropy(output)
+        opt.zero_grad()
+        loss.backward()
+        out["grads"].append(ctx.grad.flatten().clone())
+        opt.step()
+        out["losses"].append(float(loss.detach()))
+    with torch.no_grad():
+        out["logits_final"] = model(views[:1])
+    out["params"] = ctx.detach().flatten().clone()
     return out
 
 

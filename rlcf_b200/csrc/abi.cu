@@ -82,7 +82,11 @@ int reward_loss(const float*, const int32_t*, const float*, const float*, int, i
 int avg_entropy_loss(const float*, const int32_t*, int, int, int, float, float*, float*, cudaStream_t);
 int head_bwd(const float*, const float*, const int32_t*, long long, const float*, long long, const float*,
              const float*, float, const float*, const float*, int, int, int, int, int, float, float*, float*, int,
-             long long, long long, cudaStream_t);
+             long long, long long, long long, long long, long long, long long, cudaStream_t);
+int embed_prompts(const long long*, const float*, const float*, const float*, long long, int, int, int, int, int,
+                  float*, cudaStream_t);
+int pair_logits(const float*, const float*, long long, int, int, int, int, float, float*, cudaStream_t);
+int ctx_grad(const float*, int, int, int, int, int, float*, cudaStream_t);
 int adamw_step(float*, float*, float*, const float*, int, int, long long, float, float, float, float, float, int,
                float, float*, cudaStream_t);
 int reset_params(const float*, float*, float*, float*, int, long long, cudaStream_t);
@@ -202,7 +206,39 @@ int rlcf_head_bwd(const float* dlogits, const float* x, const int32_t* row_idx, 
   if (!dlogits || !x || !gamma || !proj || !class_feat || !feat || !inv_norm || !dres || !partials)
     return set_error(RLCF_ERR_ARG, "head_bwd: null pointer");
   return head_bwd(dlogits, x, row_idx, row_stride, gamma, param_stride, proj, class_feat, logit_scale, feat, inv_norm,
-                  n_img, S_, d, E, C, eps, dres, partials, n_slots, p_total, p_off, S(stream));
+                  n_img, S_, d, E, C, eps, dres, partials, n_slots, p_total, p_off, static_cast<long long>(S_) * C, C, 1,
+                  0, S(stream));
+}
+
+int rlcf_head_bwd_ex(const float* dlogits, int64_t dl_set_stride, int64_t dl_seq_stride, int64_t dl_k_stride,
+                     const float* x, const int32_t* row_idx, int64_t row_stride, const float* gamma,
+                     int64_t param_stride, const float* proj, const float* other_feat, int64_t other_set_stride,
+                     float logit_scale, const float* feat, const float* inv_norm, int n_sets, int seqs_per_set, int d,
+                     int E, int K, float eps, float* dres, float* partials, int n_slots, int64_t p_total, int64_t p_off,
+                     void* stream) {
+  if (!dlogits || !x || !gamma || !proj || !other_feat || !feat || !inv_norm || !dres)
+    return set_error(RLCF_ERR_ARG, "head_bwd_ex: null pointer");
+  return head_bwd(dlogits, x, row_idx, row_stride, gamma, param_stride, proj, other_feat, logit_scale, feat, inv_norm,
+                  n_sets, seqs_per_set, d, E, K, eps, dres, partials, n_slots, p_total, p_off, dl_set_stride,
+                  dl_seq_stride, dl_k_stride, other_set_stride, S(stream));
+}
+
+int rlcf_embed_prompts(const int64_t* tokens, const float* tok_emb, const float* pos, const float* ctx,
+                       int64_t ctx_stride, int n_ctx, int n_sets, int n_cls, int L, int d, float* x, void* stream) {
+  if (!tokens || !tok_emb || !pos || !ctx || !x) return set_error(RLCF_ERR_ARG, "embed_prompts: null pointer");
+  return embed_prompts(reinterpret_cast<const long long*>(tokens), tok_emb, pos, ctx, ctx_stride, n_ctx, n_sets, n_cls,
+                       L, d, x, S(stream));
+}
+
+int rlcf_pair_logits(const float* img_feat, const float* txt_feat, int64_t txt_set_stride, int n_sets, int S_, int C,
+                     int E, float logit_scale, float* logits, void* stream) {
+  if (!img_feat || !txt_feat || !logits) return set_error(RLCF_ERR_ARG, "pair_logits: null pointer");
+  return pair_logits(img_feat, txt_feat, txt_set_stride, n_sets, S_, C, E, logit_scale, logits, S(stream));
+}
+
+int rlcf_ctx_grad(const float* dx, int n_sets, int n_cls, int L, int n_ctx, int d, float* dctx, void* stream) {
+  if (!dx || !dctx) return set_error(RLCF_ERR_ARG, "ctx_grad: null pointer");
+  return ctx_grad(dx, n_sets, n_cls, L, n_ctx, d, dctx, S(stream));
 }
 
 int rlcf_adamw_step(float* params, float* m, float* v, const float* partials, int n_sets, int n_slots,

@@ -321,6 +321,7 @@ ln_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* __restr
       }
     }
   }
+  if (partials == nullptr) return;  // parameters frozen (text tower in prompt tuning): only dx was needed
   float* part = partials + (static_cast<long long>(set) * n_slots + slot) * p_total + p_off;
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
@@ -343,8 +344,8 @@ int layernorm_bwd(const void* dy, int dy_is_f32, long long lddy, const float* x,
                   int accumulate, __half* dx16, float* partials, int n_slots, long long p_total, long long p_off,
                   cudaStream_t stream) {
   if (int rc = check_width(d, "layernorm_bwd")) return rc;
-  if (rows_per_set <= 0 || n_sets <= 0 || n_slots <= 0 || partials == nullptr)
-    return set_error(RLCF_ERR_ARG, "layernorm_bwd: bad shape");
+  if (rows_per_set <= 0 || n_sets <= 0 || n_slots <= 0) return set_error(RLCF_ERR_ARG, "layernorm_bwd: bad shape");
+  if (partials == nullptr && dx == nullptr) return set_error(RLCF_ERR_ARG, "layernorm_bwd: nothing to compute");
   if (dx16 != nullptr && dx == nullptr) return set_error(RLCF_ERR_ARG, "layernorm_bwd: dx16 needs dx_accum");
   dim3 grid(n_slots, n_sets);
   if (dy_is_f32) {
@@ -743,7 +744,7 @@ head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ x, 
                 const float* __restrict__ proj, const float* __restrict__ cls_feat, float logit_scale,
                 const float* __restrict__ feat, const float* __restrict__ inv_norm, int S, int d, int E, int C,
                 float eps, float* __restrict__ dres, float* __restrict__ partials, int n_slots, long long p_total,
-                long long p_off) {
+                long long p_off, long long dl_set, long long dl_s, long long dl_k, long long cls_stride) {
   extern __shared__ float sm[];
   float* df = sm;            // [E]   (first: read with 16-byte loads, E % 4 == 0)
   float* dy = df + E;        // [d]
@@ -753,7 +754,8 @@ head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ x, 
   const int img = blockIdx.y, s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* gam = gamma + img * pstride;
   const int n = img * S + s;
-  for (int c = tid; c < C; c += kHeadThreads) dl[c] = dlogits[static_cast<size_t>(n) * C + c];
+  cls_feat += img * cls_stride;
+  for (int c = tid; c < C; c += kHeadThreads) dl[c] = dlogits[img * dl_set + s * dl_s + c * dl_k];
   __syncthreads();
   // d fhat = logit_scale * dlogits @ class_feat   (8 independent loads in flight per thread)
   float dot = 0.f;
@@ -807,28 +809,33 @@ head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ x, 
   s1 = block_sum<kHeadThreads>(s1, scratch) / d;
   s2 = block_sum<kHeadThreads>(s2, scratch) / d;
   float* o = dres + row * d;
-  float* part = partials + (static_cast<long long>(img) * n_slots + s) * p_total + p_off;
+  float* part = partials ? partials + (static_cast<long long>(img) * n_slots + s) * p_total + p_off : nullptr;
   for (int i = tid; i < d; i += kHeadThreads) {
     const float g = dy[i] * gam[i];
     o[i] = rstd * (g - s1 - xh[i] * s2);
-    part[i] = dy[i] * xh[i];
-    part[d + i] = dy[i];
+    if (part) {
+      part[i] = dy[i] * xh[i];
+      part[d + i] = dy[i];
+    }
   }
 }
 
 int head_bwd(const float* dlogits, const float* x, const int32_t* row_idx, long long row_stride, const float* gamma,
              long long pstride, const float* proj, const float* cls_feat, float logit_scale, const float* feat,
              const float* inv_norm, int n_img, int S, int d, int E, int C, float eps, float* dres, float* partials,
-             int n_slots, long long p_total, long long p_off, cudaStream_t stream) {
+             int n_slots, long long p_total, long long p_off, long long dl_set, long long dl_s, long long dl_k,
+             long long cls_stride, cudaStream_t stream) {
   if (n_img <= 0 || S <= 0 || d <= 0 || d > 1024 || E <= 0 || E % 4 != 0 || C <= 0)
     return set_error(RLCF_ERR_ARG, "head_bwd: bad shape");
-  if (S > n_slots) return set_error(RLCF_ERR_ARG, "head_bwd: %d views per image need at least %d gradient slots", S, S);
+  if (partials != nullptr && S > n_slots)
+    return set_error(RLCF_ERR_ARG, "head_bwd: %d views per image need at least %d gradient slots", S, S);
   const size_t smem = (static_cast<size_t>(C) + E + 2 * d + 16) * sizeof(float);
   if (smem > 48 * 1024) return set_error(RLCF_ERR_ARG, "head_bwd: C too large for shared memory");
   dim3 grid(S, n_img);
   head_bwd_kernel<<<grid, kHeadThreads, smem, stream>>>(dlogits, x, row_idx, row_stride, gamma, pstride, proj,
                                                         cls_feat, logit_scale, feat, inv_norm, S, d, E, C, eps, dres,
-                                                        partials, n_slots, p_total, p_off);
+                                                        partials, n_slots, p_total, p_off, dl_set, dl_s, dl_k,
+                                                        cls_stride);
   RLCF_CHECK_LAUNCH("head_bwd");
   return 0;
 }

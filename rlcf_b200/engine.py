@@ -222,7 +222,7 @@ class TowerRunner:
         return x
 
     def forward(self, n_seq, ln, pstride=0, seqs_per_set=None, images=None, view_idx=None, tokens=None, store=None,
-                causal=None):
+                causal=None, prompt=None):
         """Returns the fp32 residual stream after the last block ([n_seq*L, d]).
 
         ln: flat LayerNorm parameters, [P] (pstride 0) or [n_sets, P] (pstride P, seqs_per_set sequences per set).
@@ -244,7 +244,11 @@ class TowerRunner:
             x = self._embed_visual(images, view_idx, n_seq, lnv, pstride, rows_per_set, store)
         else:
             x = store.x_in[0] if store is not None else self.x
-            ops.embed_text(tokens, w.tok_emb, w.pos, x)
+            if prompt is not None:   # learnable context vectors spliced into the class prompts (PromptLearner)
+                ctx, ctx_stride, n_ctx, n_sets = prompt
+                ops.embed_prompts(tokens, w.tok_emb, w.pos, ctx, ctx_stride, n_ctx, n_sets, x)
+            else:
+                ops.embed_text(tokens, w.tok_emb, w.pos, x)
         for l, lw in enumerate(w.layers):
             qkv = store.qkv[l] if store is not None else self.qkv
             attn = store.attn[l] if store is not None else self.a
@@ -513,6 +517,149 @@ class RlcfEngine:
         total += (cfg.tta_steps - 1) * S * (f + self.tower_dgrad_flops(self.policy))
         if self.reward is not None and cfg.loss == "rlcf":
             total += S * self.tower_fwd_flops(self.reward)
+        return float(total)
+
+
+class PromptEngine:
+    """Batched RLCF / TPT prompt tuning (TPT/tpt_cls_rl.py with ClipTestTimeTuning, custom_clip.py:292-344):
+    `n_img` independent test images per call.  The image tower runs without gradient (custom_clip.py:326-327); the
+    text tower is re-run over all C class prompts with each image's own context vectors, and the backward goes
+    through the text tower down to those n_ctx x d vectors -- the only trainable parameters (tpt_cls_rl.py:103-120)."""
+
+    def __init__(self, visual: TowerWeights, text: TowerWeights, tokens: torch.Tensor, ctx_init: torch.Tensor,
+                 logit_scale: float, cfg: RlcfConfig, n_img: int, reward: TowerWeights | None = None,
+                 reward_class_feat: torch.Tensor | None = None):
+        if text.layers[0].wqkv_t is None:
+            raise RlcfError("text tower must be prepared with need_grad=True")
+        dev = text.ln_flat.device
+        self.cfg, self.n_img, self.visual, self.text, self.reward = cfg, n_img, visual, text, reward
+        self.logit_scale = float(logit_scale)
+        self.tokens = tokens.to(device=dev, dtype=torch.int64).contiguous()
+        C, L = self.tokens.shape
+        self.n_ctx, d = ctx_init.shape
+        B, V, S = n_img, cfg.n_views, cfg.n_selected
+        if S < 1:
+            raise RlcfError(f"int(n_views * selection_p) = {S}: no view would be selected (tpt_cls_rl.py:34)")
+        if cfg.loss == "rlcf" and (reward is None or reward_class_feat is None):
+            raise RlcfError("RLCF loss needs a reward tower and reward class features")
+        self.reward_class_feat = None if reward_class_feat is None else reward_class_feat.float().contiguous()
+        self.P = self.n_ctx * d
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.irun = TowerRunner(visual, B * V)
+        self.trun = TowerRunner(text, B * C)
+        self.trun.reserve_backward(B * C)
+        self.tstore = ActStore(text, B * C, dev)
+        self.rrun = TowerRunner(reward, B * S) if reward is not None else None
+        self.init_ctx = ctx_init.detach().float().reshape(-1).contiguous().clone()
+        self.ctx = torch.empty(B, self.P, **f32)
+        self.m = torch.empty(B, self.P, **f32)
+        self.v = torch.empty(B, self.P, **f32)
+        self.dctx = torch.empty(B, 1, self.P, **f32)
+        self.grad = torch.empty(B, self.P, **f32)
+        eot = self.tokens.argmax(dim=-1).to(torch.int32)
+        self.eot_rows = ((torch.arange(B * C, device=dev, dtype=torch.int32) * L)
+                         + eot.repeat(B)).contiguous()
+        self.img_feat_all = torch.empty(B * V, visual.E, **f32)
+        self.img_feat_sel = torch.empty(B * S, visual.E, **f32)
+        self.img_feat_final = torch.empty(B, visual.E, **f32)
+        self.txt_feat0 = torch.empty(C, text.E, **f32)
+        self.txt_feat = torch.empty(B * C, text.E, **f32)
+        self.txt_inv = torch.empty(B * C, **f32)
+        self.logits_all = torch.empty(B * V, C, **f32)
+        self.entropy = torch.empty(B, V, **f32)
+        self.sel = torch.empty(B, S, **i32)
+        self.sel_global = torch.empty(B * S, **i32)
+        self.sel_rows = torch.empty(B * S, **i32)
+        self.first_view = (torch.arange(B, device=dev, dtype=torch.int32) * V).contiguous()
+        self.logits_sel = torch.empty(B * S, C, **f32)
+        self.dlogits = torch.empty(B * S, C, **f32)
+        self.topk_idx = torch.empty(B * S, cfg.sample_k, **i32)
+        self.scores = torch.empty(B * S, cfg.sample_k, **f32)
+        self.rewards = torch.empty(B * S, cfg.sample_k, **f32)
+        self.loss = torch.empty(cfg.tta_steps, B, **f32)
+        self.logits_final = torch.empty(B, C, **f32)
+        self.reward_feat = torch.empty(B * S, reward.E, **f32) if reward is not None else None
+        self._graph = None
+        self._static_images = None
+        self.refresh_initial_text_features()
+
+    def refresh_initial_text_features(self):
+        """Text features of the un-adapted prompts (shared by every image for the step-0 logits of all views)."""
+        C = self.tokens.shape[0]
+        x = self.trun.forward(C, self.text.ln_flat, tokens=self.tokens, prompt=(self.init_ctx, 0, self.n_ctx, 1))
+        self.trun.head(x, C, self.text.ln_flat, row_idx=self.eot_rows[:C].contiguous(), feat=self.txt_feat0)
+
+    def _text_features(self, store):
+        B, C = self.n_img, self.tokens.shape[0]
+        x = self.trun.forward(B * C, self.text.ln_flat, tokens=self.tokens, store=store,
+                              prompt=(self.ctx, self.P, self.n_ctx, B))
+        self.trun.head(x, B * C, self.text.ln_flat, row_idx=self.eot_rows, feat=self.txt_feat, inv_norm=self.txt_inv)
+        return x
+
+    def tune(self, images: torch.Tensor) -> torch.Tensor:
+        cfg, B = self.cfg, self.n_img
+        V, S, K = cfg.n_views, cfg.n_selected, cfg.sample_k
+        C, L = self.tokens.shape
+        txt, E = self.text, self.text.E
+        if images.shape[0] != B * V:
+            raise RlcfError(f"expected {B * V} views, got {images.shape[0]}")
+        ops.reset_params(self.init_ctx, self.ctx, self.m, self.v, B, self.P)     # model.reset() + empty Adam state
+        x = self.irun.forward(B * V, self.visual.ln_flat, images=images)          # image tower, no gradient
+        self.irun.head(x, B * V, self.visual.ln_flat, feat=self.img_feat_all)
+        ops.pair_logits(self.img_feat_all, self.txt_feat0, 0, 1, B * V, C, E, self.logit_scale, self.logits_all)
+        ops.entropy_select(self.logits_all, B, V, C, S, self.sel, self.sel_global, self.entropy)
+        torch.mul(self.sel_global, self.visual.L, out=self.sel_rows)
+        self.irun.head(x, B * S, self.visual.ln_flat, row_idx=self.sel_rows, feat=self.img_feat_sel)
+        if cfg.loss == "rlcf":
+            xr = self.rrun.forward(B * S, self.reward.ln_flat, images=images, view_idx=self.sel_global)
+            self.rrun.head(xr, B * S, self.reward.ln_flat, feat=self.reward_feat)
+        for step in range(1, cfg.tta_steps + 1):
+            xs = self._text_features(self.tstore)
+            ops.pair_logits(self.img_feat_sel, self.txt_feat, C * E, B, S, C, E, self.logit_scale, self.logits_sel)
+            if cfg.loss == "rlcf":
+                ops.reward_loss(self.logits_sel, None, self.reward_feat, self.reward_class_feat, B, S, K, C,
+                                self.dlogits, clipscore_weight=cfg.clipscore_weight,
+                                reward_process=cfg.reward_process, process_batch=cfg.process_batch,
+                                amplify=cfg.reward_amplify, loss_scale=cfg.loss_scale, topk_idx=self.topk_idx,
+                                scores=self.scores, rewards=self.rewards, loss=self.loss[step - 1])
+            else:
+                ops.avg_entropy_loss(self.logits_sel, None, B, S, C, self.dlogits, loss=self.loss[step - 1],
+                                     loss_scale=cfg.loss_scale)
+            self.trun.dres[:B * C * L].zero_()
+            off = txt.ln_off("ln_final")
+            # text-side head backward: sequences = class prompts, "classes" = this image's S selected views
+            ops.head_bwd_ex(self.dlogits, (S * C, 1, C), xs, txt.ln_flat[off:], txt.proj, self.img_feat_sel, S * E,
+                            self.logit_scale, self.txt_feat, self.txt_inv, B, C, txt.d, E, S, self.trun.dres,
+                            row_idx=self.eot_rows)
+            self.trun.backward(self.tstore, B, C, txt.ln_flat, 0, None)
+            ops.ctx_grad(self.trun.dres, B, C, L, self.n_ctx, txt.d, self.dctx)
+            ops.adamw_step(self.ctx, self.m, self.v, self.dctx, B, 1, self.P, cfg.lr, step, beta1=cfg.betas[0],
+                           beta2=cfg.betas[1], eps=cfg.eps, weight_decay=cfg.weight_decay,
+                           loss_scale=cfg.loss_scale, grad_out=self.grad)
+        return self.ctx
+
+    def predict(self, images: torch.Tensor) -> torch.Tensor:
+        B, C, E = self.n_img, self.tokens.shape[0], self.text.E
+        xf = self.irun.forward(B, self.visual.ln_flat, images=images, view_idx=self.first_view)
+        self.irun.head(xf, B, self.visual.ln_flat, feat=self.img_feat_final)
+        self._text_features(None)
+        ops.pair_logits(self.img_feat_final, self.txt_feat, C * E, B, 1, C, E, self.logit_scale, self.logits_final)
+        return self.logits_final
+
+    def adapt(self, images: torch.Tensor) -> torch.Tensor:
+        self.tune(images)
+        return self.predict(images)
+
+    capture = RlcfEngine.capture
+    adapt_graph = RlcfEngine.adapt_graph
+
+    def algorithmic_flops_per_image(self) -> float:
+        cfg, C = self.cfg, self.tokens.shape[0]
+        fi, ft = RlcfEngine.tower_fwd_flops(self.visual), RlcfEngine.tower_fwd_flops(self.text)
+        total = cfg.n_views * fi + fi + C * ft + cfg.tta_steps * C * (ft + RlcfEngine.tower_dgrad_flops(self.text))
+        if self.reward is not None and cfg.loss == "rlcf":
+            total += cfg.n_selected * RlcfEngine.tower_fwd_flops(self.reward)
         return float(total)
 
 

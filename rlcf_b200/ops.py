@@ -145,6 +145,39 @@ def head_bwd(dlogits, x, gamma, proj, class_feat, logit_scale, feat, inv_norm, n
          ptr(partials), n_slots, p_total, p_off, stream())
 
 
+def head_bwd_ex(dlogits, dl_strides, x, gamma, proj, other_feat, other_set_stride, logit_scale, feat, inv_norm, n_sets,
+                seqs_per_set, d, E, K, dres, row_idx=None, row_stride=1, param_stride=0, partials=None, n_slots=1,
+                p_total=0, p_off=0, eps=1e-5):
+    _chk(dlogits, torch.float32, "dlogits"); _chk(x, torch.float32, "x"); _chk(dres, torch.float32, "dres")
+    _chk(other_feat, torch.float32, "other_feat"); _chk(row_idx, torch.int32, "row_idx")
+    call("rlcf_head_bwd_ex", ptr(dlogits), dl_strides[0], dl_strides[1], dl_strides[2], ptr(x), ptr(row_idx), row_stride,
+         ptr(gamma), param_stride, ptr(proj), ptr(other_feat), other_set_stride, float(logit_scale), ptr(feat),
+         ptr(inv_norm), n_sets, seqs_per_set, d, E, K, eps, ptr(dres), ptr(partials), n_slots, p_total, p_off, stream())
+
+
+def embed_prompts(tokens, tok_emb, pos, ctx, ctx_stride, n_ctx, n_sets, x):
+    _chk(tokens, torch.int64, "tokens"); _chk(tok_emb, torch.float32, "tok_emb"); _chk(ctx, torch.float32, "ctx")
+    _chk(x, torch.float32, "x")
+    n_cls, L = tokens.shape
+    call("rlcf_embed_prompts", ptr(tokens), ptr(tok_emb), ptr(pos), ptr(ctx), ctx_stride, n_ctx, n_sets, n_cls, L,
+         tok_emb.shape[1], ptr(x), stream())
+    return x
+
+
+def pair_logits(img_feat, txt_feat, txt_set_stride, n_sets, S, C, E, logit_scale, logits):
+    _chk(img_feat, torch.float32, "img_feat"); _chk(txt_feat, torch.float32, "txt_feat")
+    _chk(logits, torch.float32, "logits")
+    call("rlcf_pair_logits", ptr(img_feat), ptr(txt_feat), txt_set_stride, n_sets, S, C, E, float(logit_scale),
+         ptr(logits), stream())
+    return logits
+
+
+def ctx_grad(dx, n_sets, n_cls, L, n_ctx, d, dctx):
+    _chk(dx, torch.float32, "dx"); _chk(dctx, torch.float32, "dctx")
+    call("rlcf_ctx_grad", ptr(dx), n_sets, n_cls, L, n_ctx, d, ptr(dctx), stream())
+    return dctx
+
+
 def adamw_step(params, m, v, partials, n_sets, n_slots, p_total, lr, step, beta1=0.9, beta2=0.999, eps=1e-8,
                weight_decay=1e-2, loss_scale=1.0, grad_out=None):
     for t, nm in ((params, "params"), (m, "m"), (v, "v"), (partials, "partials"), (grad_out, "grad_out")):

@@ -87,3 +87,29 @@ def test_selection_edge_cases():
     # a single sampled class is returned unprocessed (clip_reward.py:157)
     s = torch.tensor([[0.3], [0.7]])
     assert torch.equal(O.rewards_post_process(s), s.flatten())
+
+
+def test_prompt_oracle_matches_reference():
+    """Prompt tuning (tpt_cls_rl.py + ClipTestTimeTuning) -- oracle vs the reference's own outputs."""
+    z, cfg = load_case("tiny_prompt_rlcf_2step")
+    sd_p = O.make_clip_state_dict(cfg["policy"], POLICY_SEED)
+    sd_r = O.make_clip_state_dict(cfg["reward"], REWARD_SEED)
+    tokens = torch.tensor(z["tokens"])
+    ctx_init = torch.tensor(z["ctx_init"])
+    assert torch.equal(ctx_init, sd_p["token_embedding.weight"][tokens[0, 1:1 + ctx_init.shape[0]]])
+    rc = O.class_features(sd_r, tokens)
+    assert np.abs(rc.numpy() - z["reward_cls"]).max() < 1e-5
+    views = O.make_views(cfg["n_img"], cfg["V"], O.ARCHS[cfg["policy"]][1], VIEW_SEED)
+    ocfg = O.OracleConfig(n_views=cfg["V"], selection_p=cfg["rho"], tta_steps=cfg["steps"], sample_k=cfg["K"],
+                          lr=cfg["lr"])
+    V = cfg["V"]
+    for i in range(cfg["n_img"]):
+        out = O.adapt_one_image_prompt(sd_p, tokens, ctx_init, views[i * V:(i + 1) * V], ocfg, sd_r, rc)
+        scale = np.abs(z[f"img{i}.logits_all"]).max()
+        assert np.abs(out["logits_all"].numpy() - z[f"img{i}.logits_all"]).max() < 1e-4 * scale
+        assert np.array_equal(out["selected_idx"].numpy(), z[f"img{i}.selected_idx"])
+        assert np.array_equal(torch.stack(out["topk_idx"]).numpy(), z[f"img{i}.topk_idx"])
+        assert np.abs(torch.stack(out["rewards"]).numpy() - z[f"img{i}.rewards"]).max() < 1e-5
+        assert np.abs(out["logits_final"].numpy() - z[f"img{i}.logits_final"]).max() < 1e-4 * scale
+        d = np.abs(out["params"].numpy() - z[f"img{i}.params"])
+        assert d.max() <= 2.02 * cfg["lr"] * cfg["steps"] and (d < 0.02 * cfg["lr"]).mean() > 0.99

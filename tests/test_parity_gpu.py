@@ -250,3 +250,66 @@ def test_engine_rejects_empty_selection():
     cfg = dict(policy="tiny-A", reward="tiny-B", V=8, rho=0.1, K=3, C=10, steps=1, lr=5e-3, n_img=1)
     with pytest.raises(Exception):
         build_engine(cfg, 1)
+
+
+def _prompt_engine(cfg, tokens, ctx_init, n_img, loss="rlcf"):
+    sd_p = O.make_clip_state_dict(cfg["policy"], POLICY_SEED)
+    sd_r = O.make_clip_state_dict(cfg["reward"], REWARD_SEED)
+    sdp_d, sdr_d = to_dev(sd_p), to_dev(sd_r)
+    rc = O.class_features(sd_r, tokens)
+    rcfg = E.RlcfConfig(n_views=cfg["V"], selection_p=cfg["rho"], tta_steps=cfg["steps"], sample_k=cfg["K"],
+                        lr=cfg["lr"], loss=loss)
+    eng = E.PromptEngine(E.prepare_visual(sdp_d), E.prepare_text(sdp_d, need_grad=True), tokens, ctx_init.to(DEV),
+                         float(sd_p["logit_scale"].exp()), rcfg, n_img, reward=E.prepare_visual(sdr_d),
+                         reward_class_feat=rc.to(DEV))
+    return eng, sd_p, sd_r, rc
+
+
+def test_prompt_tuning_matches_reference_golden_and_oracle():
+    """Prompt tuning: backward through the TEXT tower to the context vectors, n images batched."""
+    z = np.load(os.path.join(GOLDEN, "tiny_prompt_rlcf_2step.npz"))
+    cfg = ast.literal_eval(str(z["meta"]))
+    tokens, ctx_init = torch.tensor(z["tokens"]), torch.tensor(z["ctx_init"])
+    eng, sd_p, sd_r, rc = _prompt_engine(cfg, tokens, ctx_init, cfg["n_img"])
+    V, S = cfg["V"], int(cfg["V"] * cfg["rho"])
+    views = O.make_views(cfg["n_img"], V, O.ARCHS[cfg["policy"]][1], VIEW_SEED)
+    out = eng.adapt(views.to(DEV)).cpu()
+    eager = out.clone()
+    ocfg = O.OracleConfig(n_views=V, selection_p=cfg["rho"], tta_steps=1, sample_k=cfg["K"], lr=cfg["lr"])
+    for i in range(cfg["n_img"]):
+        scale = np.abs(z[f"img{i}.logits_all"]).max()
+        # the text tower is ~3x more sensitive to fp16 operand rounding than the image tower (DESIGN.md section 5)
+        assert np.abs(eng.logits_all[i * V:(i + 1) * V].cpu().numpy() - z[f"img{i}.logits_all"]).max() <= 2.5e-3 * scale
+        assert np.array_equal(eng.sel[i].cpu().numpy(), z[f"img{i}.selected_idx"])
+        assert np.array_equal(eng.topk_idx[i * S:(i + 1) * S].cpu().numpy(), z[f"img{i}.topk_idx"][-1])
+        rw = z[f"img{i}.rewards"][-1]
+        assert np.abs(eng.rewards[i * S:(i + 1) * S].cpu().numpy() - rw).max() <= 2e-3 * max(1.0, np.abs(rw).max())
+        delta = np.abs(z[f"img{i}.logits_final"][0] - z[f"img{i}.logits_all"][0]).max()
+        assert np.abs(out[i].numpy() - z[f"img{i}.logits_final"][0]).max() <= 2.5e-3 * scale + 0.3 * delta
+        check_params(eng.ctx[i].cpu().numpy(), z[f"img{i}.params"], None, cfg["lr"], cfg["steps"], f"prompt/img{i}")
+    # one-step gradient of the context vectors against autograd
+    eng1, *_ = _prompt_engine(dict(cfg, steps=1), tokens, ctx_init, cfg["n_img"])
+    eng1.adapt(views.to(DEV))
+    for i in range(cfg["n_img"]):
+        o = O.adapt_one_image_prompt(sd_p, tokens, ctx_init, views[i * V:(i + 1) * V], ocfg, sd_r, rc)
+        g, gr = eng1.grad[i].cpu(), o["grads"][0]
+        assert (g - gr).abs().max() <= 3e-2 * gr.abs().max(), f"ctx grad err {(g - gr).abs().max():.3e} vs {gr.abs().max():.3e}"
+    assert torch.equal(eng.adapt_graph(views.to(DEV)).cpu(), eager)
+
+
+def test_prompt_tuning_tpt_entropy_config1_shape():
+    """BASELINE.json configs[0] plumbing: TPT (entropy) prompt tuning, 8 views, selection_p 0.5, 4 images."""
+    cfg = dict(policy="tiny-P", reward="tiny-Q", V=8, rho=0.5, K=3, C=12, steps=1, lr=5e-3)
+    z = np.load(os.path.join(GOLDEN, "tiny_prompt_rlcf_2step.npz"))
+    tokens, ctx_init = torch.tensor(z["tokens"]), torch.tensor(z["ctx_init"])
+    eng, sd_p, _, _ = _prompt_engine(cfg, tokens, ctx_init, 4, loss="tpt")
+    views = O.make_views(4, 8, 64, 31)
+    out = eng.adapt(views.to(DEV)).cpu()
+    ocfg = O.OracleConfig(n_views=8, selection_p=0.5, tta_steps=1, lr=5e-3, loss="tpt")
+    for i in range(4):
+        o = O.adapt_one_image_prompt(sd_p, tokens, ctx_init, views[i * 8:(i + 1) * 8], ocfg)
+        assert abs(eng.loss[0, i].item() - o["losses"][0]) < 3e-3 * max(1.0, abs(o["losses"][0]))
+        scale = o["logits_all"].abs().max()
+        delta = (o["logits_final"][0] - o["logits_all"][0]).abs().max()
+        assert (out[i] - o["logits_final"][0]).abs().max() <= 2.5e-3 * scale + 0.3 * delta
+        check_params(eng.ctx[i].cpu().numpy(), o["params"].numpy(), o["grads"], 5e-3, 1, f"tpt-prompt/img{i}")
