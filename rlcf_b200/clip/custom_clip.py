@@ -21,6 +21,168 @@ from .clip import load, tokenize
 DOWNLOAD_ROOT = None  # the reference hard-codes a checkpoint directory (custom_clip.py:19-30); here it is optional
 
 
+class TextEncoder(nn.Module):
+    """Text tower on ready-made prompt embeddings (custom_clip.py:53-73): [C, 77, d] -> un-normalised features [C, E]."""
+
+    def __init__(self, clip_model):
+        super().__init__()
+        object.__setattr__(self, "_clip", clip_model)
+        self.transformer = clip_model.transformer
+        self.positional_embedding = clip_model.positional_embedding
+        self.ln_final = clip_model.ln_final
+        self.text_projection = clip_model.text_projection
+        self.dtype = clip_model.dtype
+
+    @torch.no_grad()
+    def forward(self, prompts, tokenized_prompts):
+        t = self._clip._text.tower()
+        n, L = tokenized_prompts.shape
+        run = E.TowerRunner(t, n)
+        x = run.forward(n, t.ln_flat, prompt=prompts.contiguous())
+        eot = tokenized_prompts.argmax(dim=-1).to(device=x.device, dtype=torch.int32)
+        rows = (torch.arange(n, device=x.device, dtype=torch.int32) * L + eot).contiguous()
+        feat = torch.empty(n, t.E, dtype=torch.float32, device=x.device)
+        inv = torch.empty(n, dtype=torch.float32, device=x.device)
+        run.head(x, n, t.ln_flat, row_idx=rows, feat=feat, inv_norm=inv)
+        return feat / inv[:, None]
+
+
+class PromptLearner(nn.Module):
+    """CoOp-style learnable context (custom_clip.py:76-289): prompts = [SOS | ctx (n_ctx x d) | class tokens, EOS].
+    Supported: class token at the end, shared context (`batch_size=None`), fixed class tokens (`learned_cls=False`)
+    -- the configuration of every RLCF / TPT script.  `tokenized_prompts` / `ctx_tokens` bypass the BPE tokenizer."""
+
+    def __init__(self, clip_model, classnames, batch_size=None, n_ctx=16, ctx_init=None, ctx_position="end",
+                 learned_cls=False, tokenized_prompts=None, ctx_tokens=None):
+        super().__init__()
+        if learned_cls or batch_size is not None or ctx_position != "end" or (ctx_init and "[CLS]" in ctx_init):
+            raise NotImplementedError("only ctx_position='end', batch_size=None, learned_cls=False are supported")
+        self.learned_cls, self.batch_size = learned_cls, batch_size
+        self.dtype = clip_model.dtype
+        self.device = clip_model.visual.conv1.weight.device
+        self.ctx_dim = clip_model.ln_final.weight.shape[0]
+        object.__setattr__(self, "_clip", clip_model)
+        if ctx_init or ctx_tokens is not None:
+            if ctx_tokens is None:
+                ctx_init = ctx_init.replace("_", " ")
+                n_ctx = len(ctx_init.split(" "))
+                ctx_tokens = tokenize(ctx_init)[0, 1:1 + n_ctx]
+            n_ctx = len(ctx_tokens)
+            with torch.no_grad():
+                ctx_vectors = clip_model.token_embedding(ctx_tokens.to(self.device)).type(self.dtype)
+            prompt_prefix = ctx_init if ctx_init else " ".join(["X"] * n_ctx)
+        else:
+            ctx_vectors = torch.empty(n_ctx, self.ctx_dim, dtype=self.dtype, device=self.device)
+            nn.init.normal_(ctx_vectors, std=0.02)
+            prompt_prefix = " ".join(["X"] * n_ctx)
+        self.prompt_prefix, self.split_idx = prompt_prefix, None
+        self.ctx_init_state = ctx_vectors.detach().clone()
+        self.ctx = nn.Parameter(ctx_vectors.detach().clone())
+        self.ctx_init, self.class_token_position, self.n_ctx = ctx_init, ctx_position, n_ctx
+        self._set_classes(classnames, tokenized_prompts)
+
+    def _set_classes(self, classnames, tokenized_prompts):
+        self.n_cls = len(classnames)
+        self.classnames = [name.replace("_", " ") for name in classnames]
+        if tokenized_prompts is None:
+            prompts = [self.prompt_prefix + " " + name + "." for name in self.classnames]
+            tokenized_prompts = torch.cat([tokenize(p) for p in prompts])
+        self.tokenized_prompts = tokenized_prompts.to(self.device)
+        self.name_lens = [int(t.argmax()) - 1 - self.n_ctx - 1 for t in self.tokenized_prompts]
+        with torch.no_grad():
+            embedding = self._clip.token_embedding(self.tokenized_prompts).type(self.dtype)
+        self.token_prefix = embedding[:, :1, :]                  # SOS
+        self.token_suffix = embedding[:, 1 + self.n_ctx:, :]     # class tokens, EOS, padding
+
+    @torch.no_grad()
+    def reset(self):
+        self.ctx.copy_(self.ctx_init_state)
+
+    def reset_classnames(self, classnames, arch, tokenized_prompts=None):
+        self._set_classes(classnames, tokenized_prompts)
+
+    def forward(self, init=None):
+        ctx = self.ctx if init is None else init
+        ctx = ctx.unsqueeze(0).expand(self.n_cls, -1, -1)
+        return torch.cat([self.token_prefix, ctx, self.token_suffix], dim=-2)
+
+
+class ClipTestTimeTuning(nn.Module):
+    """Prompt-tuning policy (custom_clip.py:292-344): frozen CLIP + PromptLearner; forward(image) -> logits [N, C]."""
+
+    def __init__(self, device, classnames, batch_size, criterion="cosine", arch="ViT-L/14", n_ctx=16, ctx_init=None,
+                 ctx_position="end", learned_cls=False, tokenized_prompts=None, ctx_tokens=None):
+        super().__init__()
+        clip_model, _, _ = load(arch, device=device, download_root=DOWNLOAD_ROOT)
+        object.__setattr__(self, "_clip", clip_model)
+        self.image_encoder = clip_model.visual
+        self.text_encoder = TextEncoder(clip_model)
+        self.logit_scale = clip_model.logit_scale.data
+        self.prompt_learner = PromptLearner(clip_model, classnames, batch_size, n_ctx, ctx_init, ctx_position,
+                                            learned_cls, tokenized_prompts, ctx_tokens)
+        self.criterion = criterion
+        self._engines = {}
+
+    @property
+    def dtype(self):
+        return self.image_encoder.conv1.weight.dtype
+
+    def reset(self):
+        self.prompt_learner.reset()
+
+    def reset_classnames(self, classnames, arch, tokenized_prompts=None):
+        self.prompt_learner.reset_classnames(classnames, arch, tokenized_prompts)
+        self._engines = {}
+
+    @torch.no_grad()
+    def get_text_features(self):
+        t = self.text_encoder(self.prompt_learner(), self.prompt_learner.tokenized_prompts)
+        return t / t.norm(dim=-1, keepdim=True)
+
+    @torch.no_grad()
+    def inference(self, image):
+        image_features = self.image_encoder(image.type(self.dtype))
+        text_features = self.get_text_features()
+        image_features = image_features / image_features.norm(dim=-1, keepdim=True)
+        return self.logit_scale.exp() * image_features @ text_features.t()
+
+    def forward(self, input):
+        if isinstance(input, tuple) or input.dim() == 2:
+            raise NotImplementedError("contrastive / directional prompt tuning are not part of the RLCF path")
+        return self.inference(input)
+
+    def engine(self, cfg: E.RlcfConfig, n_img: int, reward_model=None) -> E.PromptEngine:
+        """PromptEngine (batched GPU adaptation of the context vectors) for this model, cached."""
+        vis = self._clip.visual.tower()
+        txt = self._clip._text.tower(need_grad=True)
+        rew = rcls = None
+        if reward_model is not None:
+            rew = reward_model.clip_model.visual.tower()
+            rcls = reward_model.class_features
+            if rcls is None:
+                raise RlcfError("reward_model.set_class_features(...) must be called before adaptation")
+        pl = self.prompt_learner
+        key = (id(vis), id(txt), id(rew), n_img, tuple(sorted(vars(cfg).items())), pl.tokenized_prompts.data_ptr(),
+               None if rcls is None else rcls.data_ptr())
+        eng = self._engines.get(key)
+        if eng is None:
+            self._engines.clear()
+            eng = E.PromptEngine(vis, txt, pl.tokenized_prompts, pl.ctx.detach(), float(self.logit_scale.exp()), cfg,
+                                 n_img, reward=rew, reward_class_feat=rcls)
+            self._engines[key] = eng
+        return eng
+
+
+def get_coop(clip_arch, test_set, device, n_ctx, ctx_init, learned_cls=False, classnames=None, tokenized_prompts=None):
+    """Factory with the reference's signature (custom_clip.py:347-361).  The reference looks the class names up in its
+    dataset tables (TPT/data/, not shipped here); pass `classnames` (and optionally `tokenized_prompts`) instead."""
+    if classnames is None:
+        raise RlcfError(f"class-name table for test set {test_set!r} is reference data that is not shipped: "
+                        "pass classnames=[...]")
+    return ClipTestTimeTuning(device, classnames, None, arch=clip_arch, n_ctx=n_ctx, ctx_init=ctx_init,
+                              learned_cls=learned_cls, tokenized_prompts=tokenized_prompts)
+
+
 class CLIPCLS_TTA(nn.Module):
     def __init__(self, device, classnames, arch="ViT-L/14", prompt_prefix=None, only_visual=True,
                  momentum_update=False, update_freq=256, update_w=1.0, momentum=0.9999, only_norm=False,

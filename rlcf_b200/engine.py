@@ -244,7 +244,9 @@ class TowerRunner:
             x = self._embed_visual(images, view_idx, n_seq, lnv, pstride, rows_per_set, store)
         else:
             x = store.x_in[0] if store is not None else self.x
-            if prompt is not None:   # learnable context vectors spliced into the class prompts (PromptLearner)
+            if isinstance(prompt, torch.Tensor):   # ready-made prompt embeddings [n_seq, L, d] (TextEncoder.forward)
+                x[:n_seq * w.L].copy_((prompt.float() + w.pos).reshape(n_seq * w.L, w.d))
+            elif prompt is not None:   # learnable context vectors spliced into the class prompts (PromptLearner)
                 ctx, ctx_stride, n_ctx, n_sets = prompt
                 ops.embed_prompts(tokens, w.tok_emb, w.pos, ctx, ctx_stride, n_ctx, n_sets, x)
             else:

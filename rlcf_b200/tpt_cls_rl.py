@@ -56,7 +56,7 @@ def engine_config(args, optimizer, reward_model, loss="rlcf") -> E.RlcfConfig:
 def test_time_tuning(model, inputs, optimizer, scaler, args, reward_model=None, n_img: int = 1):
     """Updates the LayerNorm parameters of `model` in place (n_img == 1) and returns the adapted slices [n_img, P]."""
     if not hasattr(model, "engine"):
-        raise NotImplementedError("prompt tuning (ClipTestTimeTuning) is the next scope row; pass a CLIPCLS_TTA")
+        raise NotImplementedError("test_time_tuning needs a CLIPCLS_TTA or ClipTestTimeTuning model")
     if optimizer.state:
         raise RlcfError("optimizer state must be empty (call optimizer.load_state_dict(optim_state) first, as "
                         "tune_cls_rl.py:213 does): the fused AdamW restarts from step 0 for every image")
@@ -64,11 +64,20 @@ def test_time_tuning(model, inputs, optimizer, scaler, args, reward_model=None, 
     cfg = engine_config(args, optimizer, reward_model, loss="rlcf" if reward_model is not None else "tpt")
     cfg.n_views = n_views
     eng = model.engine(cfg, n_img, reward_model)
-    vis = model.clip_model.visual
-    eng.init_params.copy_(vis.ln_flat())           # adapt from the model's current (reset) state
-    params = eng.tune(inputs.float().contiguous())
+    if hasattr(model, "prompt_learner"):           # prompt tuning: the trainable slice is prompt_learner.ctx
+        pl = model.prompt_learner
+        eng.init_ctx.copy_(pl.ctx.detach().reshape(-1))
+        eng.refresh_initial_text_features()
+        params = eng.tune(inputs.float().contiguous())
+        if n_img == 1:
+            with torch.no_grad():
+                pl.ctx.copy_(params[0].view_as(pl.ctx))
+    else:                                          # image-encoder (LayerNorm) tuning
+        vis = model.clip_model.visual
+        eng.init_params.copy_(vis.ln_flat())       # adapt from the model's current (reset) state
+        params = eng.tune(inputs.float().contiguous())
+        if n_img == 1:
+            vis.ln_flat().copy_(params[0])         # model(image) now sees the adapted parameters
     if reward_model is not None:                   # mirror the reference's side effect (tpt_cls_rl.py:59)
         reward_model.image_features = eng.reward_feat
-    if n_img == 1:
-        vis.ln_flat().copy_(params[0])             # model(image) now sees the adapted parameters
     return params

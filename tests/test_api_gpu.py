@@ -135,3 +135,44 @@ def test_unsupported_modes_fail_loudly():
         tpt_cls_rl.test_time_tuning(model, O.make_views(1, 16, 64, 1).to(DEV), opt, None, args, reward_model=None)
     with pytest.raises(Exception):
         clip.load("synthetic:tiny-A:0", device="cpu")[0].encode_image(torch.zeros(1, 3, 64, 64))  # no CPU fallback
+
+
+def test_prompt_tuning_api_matches_oracle():
+    """get_coop / ClipTestTimeTuning / PromptLearner driven like TPT/tpt_cls_rl.py:219-279."""
+    from rlcf_b200.clip.custom_clip import get_coop
+    args = make_args(reward_arch="synthetic:tiny-Q:1", tta_steps=1)
+    tokens = O.make_tokens(9, 49408)
+    tokens[:, 1:5] = torch.tensor([320, 1125, 539, 320])     # every prompt starts with the 4 context tokens
+    model = get_coop("synthetic:tiny-P:0", "synthetic", DEV, 4, None, classnames=[f"c{i}" for i in range(9)],
+                     tokenized_prompts=tokens)
+    sd_p, sd_r = O.make_clip_state_dict("tiny-P", 0), O.make_clip_state_dict("tiny-Q", 1)
+    with torch.no_grad():   # random ctx init in the model -> use it as the oracle's starting point
+        ctx_init = model.prompt_learner.ctx.detach().cpu().clone()
+    for n, p in model.named_parameters():
+        if "prompt_learner" not in n:
+            p.requires_grad_(False)
+    optimizer = torch.optim.AdamW(model.prompt_learner.parameters(), 5e-3, weight_decay=5e-4)
+    optim_state = deepcopy(optimizer.state_dict())
+    reward_model = get_reward_model(DEV, args)
+    reward_model.set_class_features(tokenized_classes=model.prompt_learner.tokenized_prompts)
+    views = O.make_views(1, 16, 64, 17)
+    # plain inference through the API == oracle forward with the same context
+    with torch.no_grad():
+        ref0 = O.policy_logits.__globals__["encode_image"](sd_p, views[:2])
+        ref0 = ref0 / ref0.norm(dim=-1, keepdim=True)
+        ref_logits = 100.0 * ref0 @ O.prompt_text_features(sd_p, tokens, ctx_init).t()
+    got = model(views[:2].to(DEV)).cpu()
+    assert (got - ref_logits).abs().max() <= 2.5e-3 * ref_logits.abs().max()
+    model.reset()
+    optimizer.load_state_dict(optim_state)
+    tpt_cls_rl.test_time_tuning(model, views.to(DEV), optimizer, None, args, reward_model=reward_model)
+    out = model(views[:1].to(DEV)).cpu()
+    ocfg = O.OracleConfig(n_views=16, selection_p=0.25, tta_steps=1, sample_k=3, lr=5e-3)
+    ref = O.adapt_one_image_prompt(sd_p, tokens, ctx_init, views, ocfg, sd_r, reward_model.class_features.cpu())
+    scale = ref["logits_all"].abs().max()
+    delta = (ref["logits_final"][0] - ref["logits_all"][0]).abs().max()
+    assert (out[0] - ref["logits_final"][0]).abs().max() <= 2.5e-3 * scale + 0.3 * delta
+    d = (model.prompt_learner.ctx.detach().cpu().flatten() - ref["params"]).abs()
+    assert d.max() <= 2.02 * 5e-3 and (d <= 0.02 * 5e-3).float().mean() > 0.9
+    model.reset()
+    assert torch.equal(model.prompt_learner.ctx.detach().cpu(), ctx_init)
