@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--images-per-step", type=int, default=16)
+    ap.add_argument("--mode", default="ln", choices=["ln", "prompt"],
+                    help="ln = LayerNorm tuning (the BASELINE.json metric); prompt = prompt tuning (informational)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded CPU-baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--torch-gpu-baseline", action="store_true",
@@ -213,16 +215,22 @@ def run_b200(args):
     wl = WORKLOAD
     sd_p = S.make_state_dict(wl["policy"], 0, dev)
     sd_r = S.make_state_dict(wl["reward"], 1, dev)
-    pol = E.prepare_visual(sd_p, need_grad=True)
     rew = E.prepare_visual(sd_r)
     tok = S.make_tokens(wl["n_classes"], 49408)
-    cf = E.text_features(E.prepare_text(sd_p), tok)
     rc = E.text_features(E.prepare_text(sd_r), tok)
     logit_scale = float(sd_p["logit_scale"].exp())
-    del sd_p, sd_r
     cfg = E.RlcfConfig(n_views=wl["n_views"], selection_p=wl["selection_p"], tta_steps=wl["tta_steps"],
                        sample_k=wl["sample_k"], lr=wl["lr"])
-    eng = E.RlcfEngine(pol, cf, logit_scale, cfg, B, reward=rew, reward_class_feat=rc)
+    if args.mode == "prompt":
+        tok[:, 1:5] = torch.tensor([320, 1125, 539, 320])   # "a photo of a": the 4 context positions
+        ctx_init = sd_p["token_embedding.weight"][tok[0, 1:5].to(dev)]
+        eng = E.PromptEngine(E.prepare_visual(sd_p), E.prepare_text(sd_p, need_grad=True), tok, ctx_init, logit_scale,
+                             cfg, B, reward=rew, reward_class_feat=rc)
+    else:
+        pol = E.prepare_visual(sd_p, need_grad=True)
+        cf = E.text_features(E.prepare_text(sd_p), tok)
+        eng = E.RlcfEngine(pol, cf, logit_scale, cfg, B, reward=rew, reward_class_feat=rc)
+    del sd_p, sd_r
     V = wl["n_views"]
     # two different resident input batches, alternated: 2 x B x 38.5 MB (> 126 MB L2 for B >= 2)
     batches = [S.make_views(B, V, 224, 1000 + 17 * rank + i, device=dev) for i in range(2)]
@@ -339,7 +347,9 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
-        "config": {"workload": "ViT-B/16 RLCF cls, 64 views, 1 step, reward ViT-L/14 (config 2), LN-only", **wl,
+        "config": {"workload": "ViT-B/16 RLCF cls, 64 views, 1 step, reward ViT-L/14 (config 2), "
+                               + ("LN-only" if args.mode == "ln" else "prompt tuning (ctx 4x512)"), **wl,
+                   "mode": wl["mode"] if args.mode == "ln" else "prompt tuning (tpt_cls_rl.py, ctx_init a_photo_of_a)",
                    "images_per_step": B, "parallelism": f"dp{world} (independent images, no data-path collective)",
                    "l2": "inputs larger than L2: two alternating resident batches of %.0f MB" % (in_bytes / 1e6),
                    "cuda_graph": not args.no_graph, "gemm_cta_group": _lib.set_gemm_cta_group(0)},
