@@ -60,6 +60,64 @@ def peaks():
     return dict(tflops_burst=1590.0, tflops_sustained=1400.0, hbm_gbs=6650.0, source="B200_PROFILING.md fallback")
 
 
+class NvmlSampler:
+    """SM clock / power / throttle reasons sampled every 200 ms through NVML from a background thread (the same
+    counters `nvidia-smi --query-gpu=clocks.sm,...,clocks_event_reasons.*` prints, without a second process)."""
+
+    def __init__(self, gpu_index: int):
+        import threading
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        uuid = torch.cuda.get_device_properties(gpu_index).uuid
+        try:
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+        except Exception:
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        self.stop_flag = threading.Event()
+        self.sm, self.power, self.reasons = [], [], set()
+        self.t = threading.Thread(target=self._loop, daemon=True)
+
+    def _loop(self):
+        nv = self.nv
+        masks = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, m in masks.items():
+                    if r & m:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def start(self):
+        self.t.start()
+
+    def stop(self) -> dict:
+        self.stop_flag.set()
+        self.t.join()
+        mx = float(self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
+                "power_w_max": max(self.power) if self.power else None, "samples": len(sm),
+                "reasons": sorted(self.reasons), "source": "nvml"}
+
+
+def make_sampler(gpu_index: int):
+    if os.environ.get("RLCF_BENCH_SAMPLER", "nvml") == "nvml":
+        try:
+            return NvmlSampler(gpu_index)
+        except Exception:
+            pass
+    return ClockSampler(gpu_index)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -262,7 +320,7 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput (`value`)
-    sampler = ClockSampler(local)
+    sampler = make_sampler(local)
     hits = torch.zeros(3, device=dev, dtype=torch.int64)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

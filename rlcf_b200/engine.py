@@ -655,6 +655,8 @@ class PromptEngine:
 
     capture = RlcfEngine.capture
     adapt_graph = RlcfEngine.adapt_graph
+    adapt_host = RlcfEngine.adapt_host
+    host_pipeline = RlcfEngine.host_pipeline
 
     def algorithmic_flops_per_image(self) -> float:
         cfg, C = self.cfg, self.tokens.shape[0]
