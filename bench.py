@@ -40,6 +40,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--images-per-step", type=int, default=16)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5],
+                    help="BASELINE.json configs index: 2 = the metric's workload (default); 3 = same with 3 TTA steps; "
+                         "5 = ViT-L/14 policy LN-tuning (informational)")
     ap.add_argument("--mode", default="ln", choices=["ln", "prompt"],
                     help="ln = LayerNorm tuning (the BASELINE.json metric); prompt = prompt tuning (informational)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded CPU-baseline leg")
@@ -270,9 +273,13 @@ def run_b200(args):
     K = args.steps if args.steps is not None else 10
     W = max(3, args.warmup if args.warmup is not None else 3)
     B = args.images_per_step
-    wl = WORKLOAD
+    wl = dict(WORKLOAD)
+    if args.config == 3:
+        wl["tta_steps"] = 3
+    elif args.config == 5:
+        wl["policy"] = "ViT-L/14"
     sd_p = S.make_state_dict(wl["policy"], 0, dev)
-    sd_r = S.make_state_dict(wl["reward"], 1, dev)
+    sd_r = S.make_state_dict(wl["reward"], 1 if args.config != 5 else 3, dev)
     rew = E.prepare_visual(sd_r)
     tok = S.make_tokens(wl["n_classes"], 49408)
     rc = E.text_features(E.prepare_text(sd_r), tok)
@@ -405,7 +412,8 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
-        "config": {"workload": "ViT-B/16 RLCF cls, 64 views, 1 step, reward ViT-L/14 (config 2), "
+        "config": {"workload": "%s RLCF cls, 64 views, %d step(s), reward ViT-L/14 (config %d), " % (
+                        wl["policy"], wl["tta_steps"], args.config)
                                + ("LN-only" if args.mode == "ln" else "prompt tuning (ctx 4x512)"), **wl,
                    "mode": wl["mode"] if args.mode == "ln" else "prompt tuning (tpt_cls_rl.py, ctx_init a_photo_of_a)",
                    "images_per_step": B, "parallelism": f"dp{world} (independent images, no data-path collective)",

@@ -313,3 +313,23 @@ def test_prompt_tuning_tpt_entropy_config1_shape():
         delta = (o["logits_final"][0] - o["logits_all"][0]).abs().max()
         assert (out[i] - o["logits_final"][0]).abs().max() <= 2.5e-3 * scale + 0.3 * delta
         check_params(eng.ctx[i].cpu().numpy(), o["params"].numpy(), o["grads"], 5e-3, 1, f"tpt-prompt/img{i}")
+
+
+def test_vit_l14_policy_config5_shape():
+    """BASELINE.json configs[4] shape: ViT-L/14 policy (width 1024, 24 layers, 257 tokens, 102 400 LN parameters) with
+    a ViT-L/14 reward model, reduced to 8 views / 4 selected so the CPU oracle finishes in seconds."""
+    cfg = dict(policy="ViT-L/14", reward="ViT-L/14", V=8, rho=0.5, K=3, C=200, steps=1, lr=5e-3, n_img=1,
+               reward_seed=3)
+    eng, (sd_p, sd_r, tok_p, tok_r, cf, rc) = build_engine(cfg, 1)
+    assert eng.policy.P == 102400                                   # SURVEY.md 8(d) config 5
+    views = O.make_views(1, 8, 224, VIEW_SEED + 2)
+    ocfg = O.OracleConfig(n_views=8, selection_p=0.5, tta_steps=1, sample_k=3, lr=5e-3)
+    torch.set_num_threads(os.cpu_count() or 1)
+    o = O.adapt_one_image(sd_p, cf.cpu(), views, ocfg, sd_r, rc.cpu())
+    eng.adapt(views.to(DEV))
+    ref = dict(logits_all=o["logits_all"].numpy(), selected_idx=o["selected_idx"].numpy(),
+               topk_idx=torch.stack(o["topk_idx"]).numpy(), rewards=torch.stack(o["rewards"]).numpy(),
+               logits_final=o["logits_final"].numpy(), params=o["params"].numpy(), grads=o["grads"])
+    check_image(eng, 0, ref, cfg, "L14", sd_p, cf.cpu(), views[:1])
+    g, gr = eng.grad[0].cpu(), o["grads"][0]
+    assert (g - gr).abs().max() <= 2e-2 * gr.abs().max()
