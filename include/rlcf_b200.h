@@ -138,7 +138,9 @@ int rlcf_head_bwd_ex(const float* dlogits, int64_t dl_set_stride, int64_t dl_seq
                      int64_t param_stride, const float* proj, const float* other_feat, int64_t other_set_stride,
                      float logit_scale, const float* feat, const float* inv_norm, int n_sets, int seqs_per_set, int d,
                      int E, int K, float eps, float* dres, float* partials, int n_slots, int64_t p_total, int64_t p_off,
-                     void* stream);
+                     const float* beta, float* y_out, float* df_out, void* stream);
+/* (beta, y_out [n,d], df_out [n,E] may be NULL; when given, the LayerNorm output y and d(features before
+ * normalisation) are kept for the projection's weight gradient.) */
 
 /* Prompt assembly (PromptLearner.forward, class token at the end, custom_clip.py:198-232) + positional embedding:
  * x[(g,c,t)] = (1 <= t <= n_ctx ? ctx[g*ctx_stride + (t-1)*d ..] : tok_emb[tokens[c,t]]) + pos[t]. */
@@ -159,6 +161,29 @@ int rlcf_ctx_grad(const float* dx, int n_sets, int n_cls, int L, int n_ctx, int 
 int rlcf_adamw_step(float* params, float* m, float* v, const float* partials, int n_sets, int n_slots,
                     int64_t p_total, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                     float loss_scale, float* grad_out, void* stream);
+
+/* AdamW reading the parameters from params_in + g*params_in_stride (0 = one shared initial copy) and writing them to
+ * params[g]; fresh_state != 0 treats the moments as zero without reading them.  This is the first optimiser step
+ * after the per-image reset (tune_cls_rl.py:210-213) for the 86 M-parameter full-tuning case without ever copying
+ * the initial weights per image.  grads: [n_sets, n_slots, p_total]. */
+int rlcf_adamw_step_from(float* params, float* m, float* v, const float* grads, int n_sets, int n_slots,
+                         int64_t p_total, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                         float loss_scale, const float* params_in, int64_t params_in_stride, int fresh_state,
+                         void* stream);
+
+/* Per-set transposed fp16 copies for weight-gradient GEMMs: out[c, g*rows_pad + r] = in[row(g,r), c], zero padded to
+ * rows_pad; skip_first = L drops the first of every L input rows (class token).  dW = dY^T X then runs on
+ * rlcf_gemm_f16 with both operands K-major (autograd wgrad of model.py:175-181,224). */
+int rlcf_transpose_blocks_f16(const void* in, int in_is_f32, int n_sets, int rows_per_set, int rows_pad, int cols,
+                              int skip_first, int64_t in_set_stride_rows, void* out, int64_t ld_out, void* stream);
+/* Bias gradients: out[g*out_stride + c] = sum over the set's rows of in[., c] (fp16 in, fp32 out). */
+int rlcf_colsum_f16(const void* in, int n_sets, int rows_per_set, int cols, float* out, int64_t out_stride,
+                    void* stream);
+/* positional / class embedding gradient: out[g][t][:] = sum over the set's S sequences of dx[(g*S+s)*L + t][:]. */
+int rlcf_seq_sum(const float* dx, int n_sets, int S, int L, int d, float* out, int64_t out_stride, void* stream);
+/* projection gradient: out[g][i][j] = sum_s y[g*S+s][i] * df[g*S+s][j]. */
+int rlcf_outer_sum(const float* y, const float* df, int n_sets, int S, int d, int E, float* out, int64_t out_stride,
+                   void* stream);
 
 /* model.reset() + optimizer.load_state_dict (tune_cls_rl.py:210-213) for the trainable slice only:
  * params[g] = init for every set g; m = v = 0. */

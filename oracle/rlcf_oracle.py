@@ -259,7 +259,7 @@ def ln_param_names(sd: dict) -> list:
 
 def adapt_one_image(sd_policy: dict, class_feat: torch.Tensor, views: torch.Tensor, cfg: OracleConfig,
                     sd_reward: dict | None = None, reward_cls: torch.Tensor | None = None, amp: bool = False,
-                    scaler=None) -> dict:
+                    scaler=None, tune: str = "ln") -> dict:
     """One iteration of the per-image loop of TPT/tune_cls_rl.py:192-222 in LayerNorm-tuning mode
     (--tune_norm 1): reset -> test_time_tuning (TPT/tpt_cls_rl.py:47-79) -> adapted prediction on views[0].
     fp32 on CPU: torch.cuda.amp.autocast and GradScaler are no-ops without CUDA, so the scaler lines
@@ -268,7 +268,8 @@ def adapt_one_image(sd_policy: dict, class_feat: torch.Tensor, views: torch.Tens
     used only by bench.py's optional PyTorch-on-GPU baseline leg."""
     import contextlib
     autocast = (lambda: torch.autocast(device_type=views.device.type, dtype=torch.float16)) if amp else contextlib.nullcontext
-    names = ln_param_names(sd_policy)
+    # tune="ln": --tune_norm 1 (LayerNorm parameters); tune="full": every visual parameter (custom_clip.py:477-479)
+    names = ln_param_names(sd_policy) if tune == "ln" else [k for k in sd_policy if k.startswith("visual.")]
     sd = {k: v.clone() for k, v in sd_policy.items()}                    # model.reset(), tune_cls_rl.py:210
     params = [sd[n].requires_grad_(True) for n in names]
     opt = torch.optim.AdamW(params, cfg.lr, weight_decay=cfg.weight_decay)   # fresh state, tune_cls_rl.py:80,213

@@ -42,7 +42,12 @@ _PROTOS = {
     "rlcf_head_bwd": [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _i,
                       _i64, _i64, _vp],
     "rlcf_head_bwd_ex": [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _f, _vp, _vp, _i, _i, _i, _i,
-                         _i, _f, _vp, _vp, _i, _i64, _i64, _vp],
+                         _i, _f, _vp, _vp, _i, _i64, _i64, _vp, _vp, _vp, _vp],
+    "rlcf_adamw_step_from": [_vp, _vp, _vp, _vp, _i, _i, _i64, _f, _f, _f, _f, _f, _i, _f, _vp, _i64, _i, _vp],
+    "rlcf_transpose_blocks_f16": [_vp, _i, _i, _i, _i, _i, _i, _i64, _vp, _i64, _vp],
+    "rlcf_colsum_f16": [_vp, _i, _i, _i, _vp, _i64, _vp],
+    "rlcf_seq_sum": [_vp, _i, _i, _i, _i, _vp, _i64, _vp],
+    "rlcf_outer_sum": [_vp, _vp, _i, _i, _i, _i, _vp, _i64, _vp],
     "rlcf_embed_prompts": [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp],
     "rlcf_pair_logits": [_vp, _vp, _i64, _i, _i, _i, _i, _f, _vp, _vp],
     "rlcf_ctx_grad": [_vp, _i, _i, _i, _i, _i, _vp, _vp],

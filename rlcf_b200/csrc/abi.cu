@@ -82,13 +82,18 @@ int reward_loss(const float*, const int32_t*, const float*, const float*, int, i
 int avg_entropy_loss(const float*, const int32_t*, int, int, int, float, float*, float*, cudaStream_t);
 int head_bwd(const float*, const float*, const int32_t*, long long, const float*, long long, const float*,
              const float*, float, const float*, const float*, int, int, int, int, int, float, float*, float*, int,
-             long long, long long, long long, long long, long long, long long, cudaStream_t);
+             long long, long long, long long, long long, long long, long long, const float*, float*, float*,
+             cudaStream_t);
+int transpose_blocks(const void*, int, int, int, int, int, int, long long, __half*, long long, cudaStream_t);
+int colsum_f16(const __half*, int, int, int, float*, long long, cudaStream_t);
+int seq_sum(const float*, int, int, int, int, float*, long long, cudaStream_t);
+int outer_sum(const float*, const float*, int, int, int, int, float*, long long, cudaStream_t);
 int embed_prompts(const long long*, const float*, const float*, const float*, long long, int, int, int, int, int,
                   float*, cudaStream_t);
 int pair_logits(const float*, const float*, long long, int, int, int, int, float, float*, cudaStream_t);
 int ctx_grad(const float*, int, int, int, int, int, float*, cudaStream_t);
 int adamw_step(float*, float*, float*, const float*, int, int, long long, float, float, float, float, float, int,
-               float, float*, cudaStream_t);
+               float, float*, const float*, long long, int, cudaStream_t);
 int reset_params(const float*, float*, float*, float*, int, long long, cudaStream_t);
 int cast_f16(const float*, long long, long long, long long, __half*, long long, cudaStream_t);
 int transpose_cast_f16(const float*, int, int, __half*, cudaStream_t);
@@ -207,7 +212,7 @@ int rlcf_head_bwd(const float* dlogits, const float* x, const int32_t* row_idx, 
     return set_error(RLCF_ERR_ARG, "head_bwd: null pointer");
   return head_bwd(dlogits, x, row_idx, row_stride, gamma, param_stride, proj, class_feat, logit_scale, feat, inv_norm,
                   n_img, S_, d, E, C, eps, dres, partials, n_slots, p_total, p_off, static_cast<long long>(S_) * C, C, 1,
-                  0, S(stream));
+                  0, nullptr, nullptr, nullptr, S(stream));
 }
 
 int rlcf_head_bwd_ex(const float* dlogits, int64_t dl_set_stride, int64_t dl_seq_stride, int64_t dl_k_stride,
@@ -215,12 +220,12 @@ int rlcf_head_bwd_ex(const float* dlogits, int64_t dl_set_stride, int64_t dl_seq
                      int64_t param_stride, const float* proj, const float* other_feat, int64_t other_set_stride,
                      float logit_scale, const float* feat, const float* inv_norm, int n_sets, int seqs_per_set, int d,
                      int E, int K, float eps, float* dres, float* partials, int n_slots, int64_t p_total, int64_t p_off,
-                     void* stream) {
+                     const float* beta, float* y_out, float* df_out, void* stream) {
   if (!dlogits || !x || !gamma || !proj || !other_feat || !feat || !inv_norm || !dres)
     return set_error(RLCF_ERR_ARG, "head_bwd_ex: null pointer");
   return head_bwd(dlogits, x, row_idx, row_stride, gamma, param_stride, proj, other_feat, logit_scale, feat, inv_norm,
                   n_sets, seqs_per_set, d, E, K, eps, dres, partials, n_slots, p_total, p_off, dl_set_stride,
-                  dl_seq_stride, dl_k_stride, other_set_stride, S(stream));
+                  dl_seq_stride, dl_k_stride, other_set_stride, beta, y_out, df_out, S(stream));
 }
 
 int rlcf_embed_prompts(const int64_t* tokens, const float* tok_emb, const float* pos, const float* ctx,
@@ -246,7 +251,40 @@ int rlcf_adamw_step(float* params, float* m, float* v, const float* partials, in
                     float loss_scale, float* grad_out, void* stream) {
   if (!params || !m || !v || !partials) return set_error(RLCF_ERR_ARG, "adamw_step: null pointer");
   return adamw_step(params, m, v, partials, n_sets, n_slots, p_total, lr, beta1, beta2, eps, weight_decay, step,
-                    loss_scale, grad_out, S(stream));
+                    loss_scale, grad_out, nullptr, 0, 0, S(stream));
+}
+
+int rlcf_adamw_step_from(float* params, float* m, float* v, const float* grads, int n_sets, int n_slots,
+                         int64_t p_total, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                         float loss_scale, const float* params_in, int64_t params_in_stride, int fresh_state,
+                         void* stream) {
+  if (!params || !m || !v || !grads || !params_in) return set_error(RLCF_ERR_ARG, "adamw_step_from: null pointer");
+  return adamw_step(params, m, v, grads, n_sets, n_slots, p_total, lr, beta1, beta2, eps, weight_decay, step,
+                    loss_scale, nullptr, params_in, params_in_stride, fresh_state, S(stream));
+}
+
+int rlcf_transpose_blocks_f16(const void* in, int in_is_f32, int n_sets, int rows_per_set, int rows_pad, int cols,
+                              int skip_first, int64_t in_set_stride_rows, void* out, int64_t ld_out, void* stream) {
+  if (!in || !out) return set_error(RLCF_ERR_ARG, "transpose_blocks: null pointer");
+  return transpose_blocks(in, in_is_f32, n_sets, rows_per_set, rows_pad, cols, skip_first, in_set_stride_rows, H(out),
+                          ld_out, S(stream));
+}
+
+int rlcf_colsum_f16(const void* in, int n_sets, int rows_per_set, int cols, float* out, int64_t out_stride,
+                    void* stream) {
+  if (!in || !out) return set_error(RLCF_ERR_ARG, "colsum: null pointer");
+  return colsum_f16(CH(in), n_sets, rows_per_set, cols, out, out_stride, S(stream));
+}
+
+int rlcf_seq_sum(const float* dx, int n_sets, int S_, int L, int d, float* out, int64_t out_stride, void* stream) {
+  if (!dx || !out) return set_error(RLCF_ERR_ARG, "seq_sum: null pointer");
+  return seq_sum(dx, n_sets, S_, L, d, out, out_stride, S(stream));
+}
+
+int rlcf_outer_sum(const float* y, const float* df, int n_sets, int S_, int d, int E, float* out, int64_t out_stride,
+                   void* stream) {
+  if (!y || !df || !out) return set_error(RLCF_ERR_ARG, "outer_sum: null pointer");
+  return outer_sum(y, df, n_sets, S_, d, E, out, out_stride, S(stream));
 }
 
 int rlcf_reset_params(const float* init, float* params, float* m, float* v, int n_sets, int64_t p_total,

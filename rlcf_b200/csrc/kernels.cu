@@ -744,7 +744,8 @@ head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ x, 
                 const float* __restrict__ proj, const float* __restrict__ cls_feat, float logit_scale,
                 const float* __restrict__ feat, const float* __restrict__ inv_norm, int S, int d, int E, int C,
                 float eps, float* __restrict__ dres, float* __restrict__ partials, int n_slots, long long p_total,
-                long long p_off, long long dl_set, long long dl_s, long long dl_k, long long cls_stride) {
+                long long p_off, long long dl_set, long long dl_s, long long dl_k, long long cls_stride,
+                const float* __restrict__ beta, float* __restrict__ y_out, float* __restrict__ df_out) {
   extern __shared__ float sm[];
   float* df = sm;            // [E]   (first: read with 16-byte loads, E % 4 == 0)
   float* dy = df + E;        // [d]
@@ -776,7 +777,10 @@ head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ x, 
   dot = block_sum<kHeadThreads>(dot, scratch);
   const float inv = inv_norm[n];
   // d f = (d fhat - fhat * <fhat, d fhat>) / |f|
-  for (int j = tid; j < E; j += kHeadThreads) df[j] = (df[j] - feat[static_cast<size_t>(n) * E + j] * dot) * inv;
+  for (int j = tid; j < E; j += kHeadThreads) {
+    df[j] = (df[j] - feat[static_cast<size_t>(n) * E + j] * dot) * inv;
+    if (df_out) df_out[static_cast<size_t>(n) * E + j] = df[j];   // needed for d proj = y^T d f (full tuning)
+  }
   __syncthreads();
   // d y = d f @ proj^T  (warp per output row, 16-byte loads along E)
   for (int i = warp; i < d; i += kHeadThreads / 32) {
@@ -817,6 +821,7 @@ head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ x, 
       part[i] = dy[i] * xh[i];
       part[d + i] = dy[i];
     }
+    if (y_out) y_out[static_cast<size_t>(n) * d + i] = xh[i] * gam[i] + beta[img * pstride + i];  // ln_post output
   }
 }
 
@@ -824,9 +829,10 @@ int head_bwd(const float* dlogits, const float* x, const int32_t* row_idx, long 
              long long pstride, const float* proj, const float* cls_feat, float logit_scale, const float* feat,
              const float* inv_norm, int n_img, int S, int d, int E, int C, float eps, float* dres, float* partials,
              int n_slots, long long p_total, long long p_off, long long dl_set, long long dl_s, long long dl_k,
-             long long cls_stride, cudaStream_t stream) {
+             long long cls_stride, const float* beta, float* y_out, float* df_out, cudaStream_t stream) {
   if (n_img <= 0 || S <= 0 || d <= 0 || d > 1024 || E <= 0 || E % 4 != 0 || C <= 0)
     return set_error(RLCF_ERR_ARG, "head_bwd: bad shape");
+  if (y_out != nullptr && beta == nullptr) return set_error(RLCF_ERR_ARG, "head_bwd: y_out needs beta");
   if (partials != nullptr && S > n_slots)
     return set_error(RLCF_ERR_ARG, "head_bwd: %d views per image need at least %d gradient slots", S, S);
   const size_t smem = (static_cast<size_t>(C) + E + 2 * d + 16) * sizeof(float);
@@ -835,7 +841,7 @@ int head_bwd(const float* dlogits, const float* x, const int32_t* row_idx, long 
   head_bwd_kernel<<<grid, kHeadThreads, smem, stream>>>(dlogits, x, row_idx, row_stride, gamma, pstride, proj,
                                                         cls_feat, logit_scale, feat, inv_norm, S, d, E, C, eps, dres,
                                                         partials, n_slots, p_total, p_off, dl_set, dl_s, dl_k,
-                                                        cls_stride);
+                                                        cls_stride, beta, y_out, df_out);
   RLCF_CHECK_LAUNCH("head_bwd");
   return 0;
 }
@@ -845,7 +851,8 @@ int head_bwd(const float* dlogits, const float* x, const int32_t* row_idx, long 
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ partials,
              int n_slots, long long p_total, long long total, float lr, float b1, float b2, float eps, float wd,
-             float bc1, float bc2_sqrt, float inv_scale, float* __restrict__ grad_out) {
+             float bc1, float bc2_sqrt, float inv_scale, float* __restrict__ grad_out,
+             const float* __restrict__ p_in, long long p_in_stride, int fresh) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long set = i / p_total, j = i % p_total;
@@ -854,9 +861,12 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v
     for (int s = 0; s < n_slots; ++s) g += pp[s * p_total];
     g *= inv_scale;
     if (grad_out) grad_out[i] = g;
-    float w = p[i] * (1.f - lr * wd);
-    const float mi = m[i] + (g - m[i]) * (1.f - b1);  // exp_avg.lerp_(grad, 1 - beta1)
-    const float vi = v[i] * b2 + (1.f - b2) * g * g;
+    // fresh: first step after reset -- parameters come from the (shared) initial copy, moments start at zero
+    const float p0 = p_in ? p_in[set * p_in_stride + j] : p[i];
+    const float m0 = fresh ? 0.f : m[i], v0 = fresh ? 0.f : v[i];
+    float w = p0 * (1.f - lr * wd);
+    const float mi = m0 + (g - m0) * (1.f - b1);  // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v0 * b2 + (1.f - b2) * g * g;
     m[i] = mi;
     v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
@@ -867,7 +877,7 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v
 
 int adamw_step(float* params, float* m, float* v, const float* partials, int n_sets, int n_slots, long long p_total,
                float lr, float b1, float b2, float eps, float wd, int step, float loss_scale, float* grad_out,
-               cudaStream_t stream) {
+               const float* params_in, long long params_in_stride, int fresh, cudaStream_t stream) {
   if (n_sets <= 0 || n_slots <= 0 || p_total <= 0 || step < 1) return set_error(RLCF_ERR_ARG, "adamw: bad shape");
   const long long total = n_sets * p_total;
   const double bc1 = 1.0 - pow(static_cast<double>(b1), step);
@@ -876,7 +886,8 @@ int adamw_step(float* params, float* m, float* v, const float* partials, int n_s
   if (blocks > 148 * 8) blocks = 148 * 8;
   adamw_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(params, m, v, partials, n_slots, p_total, total, lr, b1,
                                                              b2, eps, wd, static_cast<float>(bc1),
-                                                             static_cast<float>(sqrt(bc2)), 1.f / loss_scale, grad_out);
+                                                             static_cast<float>(sqrt(bc2)), 1.f / loss_scale, grad_out,
+                                                             params_in, params_in_stride, fresh);
   RLCF_CHECK_LAUNCH("adamw");
   return 0;
 }

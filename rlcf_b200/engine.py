@@ -159,7 +159,8 @@ def prepare_text(sd: dict, need_grad: bool = False) -> TowerWeights:
 class ActStore:
     """Activations one training-mode forward keeps for the backward (per layer, for `rows` token rows)."""
 
-    def __init__(self, w: TowerWeights, n_seq: int, device):
+    def __init__(self, w: TowerWeights, n_seq: int, device, full: bool = False):
+        """full=True also keeps the fp16 inputs of the four linear layers (needed for weight gradients)."""
         d, L, nl = w.d, w.L, w.n_layers
         rows = n_seq * L
         f32 = dict(dtype=torch.float32, device=device)
@@ -172,6 +173,9 @@ class ActStore:
         self.attn = torch.empty(nl, rows, d, **f16)
         self.lse = torch.empty(nl, n_seq, w.heads, L, **f32)
         self.u = torch.empty(nl, rows, 4 * d, **f16)      # QuickGELU pre-activation
+        self.a1 = torch.empty(nl, rows, d, **f16) if full else None      # ln_1 output (input of in_proj)
+        self.a2 = torch.empty(nl, rows, d, **f16) if full else None      # ln_2 output (input of c_fc)
+        self.h = torch.empty(nl, rows, 4 * d, **f16) if full else None   # QuickGELU output (input of c_proj)
 
 
 class TowerRunner:
@@ -209,8 +213,8 @@ class TowerRunner:
         self.gqkv = torch.empty(rows, 3 * w.d, **f16)
 
     # ------------------------------------------------------------------ forward
-    def _embed_visual(self, images, view_idx, n_seq, ln, pstride, rows_per_set, store):
-        w = self.w
+    def _embed_visual(self, images, view_idx, n_seq, ln, pstride, rows_per_set, store, w=None):
+        w = self.w if w is None else w
         P = w.L - 1
         if images.shape[-1] != w.resolution or images.shape[-2] != w.resolution:
             raise RlcfError(f"expected {w.resolution}x{w.resolution} input, got {tuple(images.shape)}")
@@ -222,13 +226,14 @@ class TowerRunner:
         return x
 
     def forward(self, n_seq, ln, pstride=0, seqs_per_set=None, images=None, view_idx=None, tokens=None, store=None,
-                causal=None, prompt=None):
+                causal=None, prompt=None, w=None):
         """Returns the fp32 residual stream after the last block ([n_seq*L, d]).
 
         ln: flat LayerNorm parameters, [P] (pstride 0) or [n_sets, P] (pstride P, seqs_per_set sequences per set).
         store: ActStore to keep activations for backward() (training-mode forward), else None.
+        w: weights to use instead of the runner's own (same architecture; per-image weights in full tuning).
         """
-        w = self.w
+        w = self.w if w is None else w
         if n_seq > self.max_seq:
             raise RlcfError(f"n_seq {n_seq} exceeds reserved {self.max_seq}")
         d, L = w.d, w.L
@@ -241,7 +246,7 @@ class TowerRunner:
             return lnv[off:], lnv[off + d:]
 
         if w.kind == "visual":
-            x = self._embed_visual(images, view_idx, n_seq, lnv, pstride, rows_per_set, store)
+            x = self._embed_visual(images, view_idx, n_seq, lnv, pstride, rows_per_set, store, w)
         else:
             x = store.x_in[0] if store is not None else self.x
             if isinstance(prompt, torch.Tensor):   # ready-made prompt embeddings [n_seq, L, d] (TextEncoder.forward)
@@ -254,26 +259,30 @@ class TowerRunner:
         for l, lw in enumerate(w.layers):
             qkv = store.qkv[l] if store is not None else self.qkv
             attn = store.attn[l] if store is not None else self.a
+            full = store is not None and store.a1 is not None
+            a1 = store.a1[l] if full else self.a
             g, b = gb(w.ln_off("ln_1", l))
-            ops.layernorm_fwd(x, g, b, rows, d, out16=self.a, param_stride=pstride, rows_per_set=rows_per_set)
-            ops.gemm(self.a, lw.wqkv, qkv, epilogue=EPI_F16, bias=lw.bqkv, M=rows)
+            ops.layernorm_fwd(x, g, b, rows, d, out16=a1, param_stride=pstride, rows_per_set=rows_per_set)
+            ops.gemm(a1, lw.wqkv, qkv, epilogue=EPI_F16, bias=lw.bqkv, M=rows)
             ops.attention_fwd(qkv, n_seq, L, w.heads, attn, causal=causal,
                               lse=None if store is None else store.lse[l])
             x_mid = store.x_mid[l] if store is not None else x
             ops.gemm(attn, lw.wo, x_mid, epilogue=EPI_RESID_F32, bias=lw.bo, resid=x, M=rows)
+            a2 = store.a2[l] if full else self.a
+            h = store.h[l] if full else self.h
             g, b = gb(w.ln_off("ln_2", l))
-            ops.layernorm_fwd(x_mid, g, b, rows, d, out16=self.a, param_stride=pstride, rows_per_set=rows_per_set)
-            ops.gemm(self.a, lw.wfc, self.h, epilogue=EPI_GELU_F16, bias=lw.bfc, M=rows,
+            ops.layernorm_fwd(x_mid, g, b, rows, d, out16=a2, param_stride=pstride, rows_per_set=rows_per_set)
+            ops.gemm(a2, lw.wfc, h, epilogue=EPI_GELU_F16, bias=lw.bfc, M=rows,
                      aux_out=None if store is None else store.u[l])
             x_next = store.x_in[l + 1] if store is not None else x
-            ops.gemm(self.h, lw.wproj, x_next, epilogue=EPI_RESID_F32, bias=lw.bproj, resid=x_mid, M=rows)
+            ops.gemm(h, lw.wproj, x_next, epilogue=EPI_RESID_F32, bias=lw.bproj, resid=x_mid, M=rows)
             x = x_next
         return x
 
     def head(self, x, n_seq, ln, pstride=0, seqs_per_set=None, row_idx=None, class_feat=None, logit_scale=1.0,
-             feat=None, inv_norm=None, logits=None):
+             feat=None, inv_norm=None, logits=None, w=None):
         """ln_post/ln_final on one row per sequence -> projection -> L2 normalise (-> logits)."""
-        w = self.w
+        w = self.w if w is None else w
         lnv = ln.view(-1)
         off = w.ln_off("ln_post")
         ops.head_fwd(x, lnv[off:], lnv[off + w.d:], w.proj, n_seq, w.d, w.E, feat=feat, inv_norm=inv_norm,
@@ -281,10 +290,13 @@ class TowerRunner:
                      param_stride=pstride, seqs_per_set=seqs_per_set)
 
     # ------------------------------------------------------------------ backward (LayerNorm parameters only)
-    def backward(self, store: ActStore, n_sets, seqs_per_set, ln, pstride, partials, n_slots=N_SLOTS):
+    def backward(self, store: ActStore, n_sets, seqs_per_set, ln, pstride, partials, n_slots=N_SLOTS, w=None,
+                 hook=None):
         """Propagates self.dres (gradient w.r.t. the tower output rows, fp32, already filled by head_bwd) down to
-        ln_pre, writing every LayerNorm's d(gamma), d(beta) partials.  GEMM weights are frozen: dgrad only."""
-        w = self.w
+        ln_pre, writing every LayerNorm's d(gamma), d(beta) partials.  Without `hook` the GEMM weights are frozen
+        (dgrad only); with it, hook.linear(layer, name, dY, X) is called where a weight gradient dY^T X is due and
+        hook.embed(dx_pre) at the end (full image-encoder tuning)."""
+        w = self.w if w is None else w
         d, L = w.d, w.L
         n_seq = n_sets * seqs_per_set
         rows = n_seq * L
@@ -296,22 +308,33 @@ class TowerRunner:
         for l in range(w.n_layers - 1, -1, -1):
             lw = w.layers[l]
             # MLP branch: d u = (d x_out @ Wproj) * gelu'(u);  d a2 = d u @ Wfc
+            if hook is not None:
+                hook.linear(l, "c_proj", dres16, store.h[l])
             ops.gemm(dres16, lw.wproj_t, self.gh, epilogue=EPI_GELU_BWD_F16, aux_in=store.u[l], M=rows)
+            if hook is not None:
+                hook.linear(l, "c_fc", self.gh, store.a2[l])
             ops.gemm(self.gh, lw.wfc_t, self.g16, epilogue=EPI_F16, M=rows)
             off = w.ln_off("ln_2", l)
             ops.layernorm_bwd(self.g16, store.x_mid[l], lnv[off:], rows_per_set, n_sets, d, partials, n_slots, P, off,
                               dx=dres, accumulate=True, param_stride=pstride, dx16=dres16)
             # attention branch
+            if hook is not None:
+                hook.linear(l, "out_proj", dres16, store.attn[l])
             ops.gemm(dres16, lw.wo_t, self.g16, epilogue=EPI_F16, M=rows)
             ops.attention_bwd(store.qkv[l], store.attn[l], self.g16, store.lse[l], n_seq, L, w.heads, self.gqkv,
                               causal=(w.kind == "text"))
+            if hook is not None:
+                hook.linear(l, "in_proj", self.gqkv, store.a1[l])
             ops.gemm(self.gqkv, lw.wqkv_t, self.g16, epilogue=EPI_F16, M=rows)
             off = w.ln_off("ln_1", l)
             ops.layernorm_bwd(self.g16, store.x_in[l], lnv[off:], rows_per_set, n_sets, d, partials, n_slots, P, off,
                               dx=dres, accumulate=True, param_stride=pstride, dx16=dres16)
         if w.has_ln_pre:
-            ops.layernorm_bwd(dres, store.x_pre, lnv, rows_per_set, n_sets, d, partials, n_slots, P, 0, dx=None,
-                              param_stride=pstride)
+            dxp = hook.dx_pre if hook is not None else None
+            ops.layernorm_bwd(dres, store.x_pre, lnv, rows_per_set, n_sets, d, partials, n_slots, P, 0, dx=dxp,
+                              accumulate=False, param_stride=pstride)
+            if hook is not None:
+                hook.embed(dxp)
 
 
 @dataclass

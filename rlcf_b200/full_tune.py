@@ -1,0 +1,347 @@
+"""Full image-encoder tuning (TPT/tune_cls_rl.py with --tune_norm 0, the default recipe of scripts/rlcf-tune.sh):
+every parameter of the visual tower is trainable (custom_clip.py:477-479), so each test image ends up with its own
+86 M weights after the first AdamW step.
+
+Step 1 still runs batched over all images on the shared initial weights (forward of all views, training forward +
+dgrad of the selected views); what is new is
+  * weight gradients: per image, dW[out,in] = dY^T X as a tcgen05 GEMM over transposed fp16 copies of dY and X,
+    bias gradients as column sums, conv1 / class / positional / projection gradients from the ln_pre input gradient,
+  * a per-image fp32 master copy of all non-LayerNorm parameters with Adam moments (the first step reads the shared
+    initial copy, so the reference's 345 MB per-image state-dict restore never happens),
+  * per-image fp16 weight copies, used by the remaining TTA steps and the adapted prediction, which therefore run one
+    image at a time (small-M GEMMs, weight-read bound).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import engine as E
+from . import ops
+from ._lib import EPI_F32, RlcfError
+
+
+class FullLayout:
+    """Offsets of the non-LayerNorm visual parameters inside one flat fp32 vector.
+    [ GEMM block: conv1 [d,k_pad] | per layer in_proj_w, out_proj_w, c_fc_w, c_proj_w ]  (cast to fp16 in one go)
+    [ class_embedding | positional_embedding | proj | per layer in_proj_b, out_proj_b, c_fc_b, c_proj_b ]"""
+
+    def __init__(self, w: E.TowerWeights):
+        d, L, Ed, nl, kp = w.d, w.L, w.E, w.n_layers, w.k_pad
+        self.d, self.L, self.E, self.nl, self.k_pad = d, L, Ed, nl, kp
+        off = 0
+        self.conv = off; off += d * kp
+        self.wq, self.wo, self.wf, self.wp = [], [], [], []
+        for _ in range(nl):
+            self.wq.append(off); off += 3 * d * d
+            self.wo.append(off); off += d * d
+            self.wf.append(off); off += 4 * d * d
+            self.wp.append(off); off += 4 * d * d
+        self.p_gemm = off
+        self.cls = off; off += d
+        self.pos = off; off += L * d
+        self.proj = off; off += d * Ed
+        self.bq, self.bo, self.bf, self.bp = [], [], [], []
+        for _ in range(nl):
+            self.bq.append(off); off += 3 * d
+            self.bo.append(off); off += d
+            self.bf.append(off); off += 4 * d
+            self.bp.append(off); off += d
+        self.total = off
+
+    def entries(self, prefix="visual."):
+        """(state_dict key, offset, shape) of every entry, conv1 in its flattened zero-padded [d, k_pad] form."""
+        d, nl = self.d, self.nl
+        out = [(prefix + "conv1.weight", self.conv, (d, self.k_pad)), (prefix + "class_embedding", self.cls, (d,)),
+               (prefix + "positional_embedding", self.pos, (self.L, d)), (prefix + "proj", self.proj, (d, self.E))]
+        for l in range(nl):
+            rb = f"{prefix}transformer.resblocks.{l}."
+            out += [(rb + "attn.in_proj_weight", self.wq[l], (3 * d, d)), (rb + "attn.out_proj.weight", self.wo[l], (d, d)),
+                    (rb + "mlp.c_fc.weight", self.wf[l], (4 * d, d)), (rb + "mlp.c_proj.weight", self.wp[l], (d, 4 * d)),
+                    (rb + "attn.in_proj_bias", self.bq[l], (3 * d,)), (rb + "attn.out_proj.bias", self.bo[l], (d,)),
+                    (rb + "mlp.c_fc.bias", self.bf[l], (4 * d,)), (rb + "mlp.c_proj.bias", self.bp[l], (d,))]
+        return out
+
+
+def pack_rest(sd: dict, lay: FullLayout, prefix="visual.") -> torch.Tensor:
+    dev = sd[prefix + "proj"].device
+    flat = torch.zeros(lay.total, dtype=torch.float32, device=dev)
+    for key, off, shape in lay.entries(prefix):
+        src = sd[key].detach().float()
+        if key.endswith("conv1.weight"):
+            k_real = src[0].numel()
+            flat[off:off + shape[0] * shape[1]].view(shape)[:, :k_real].copy_(src.reshape(shape[0], k_real))
+        else:
+            flat[off:off + src.numel()].copy_(src.reshape(-1))
+    return flat
+
+
+def tower_view(base: E.TowerWeights, lay: FullLayout, rest: torch.Tensor, w16: torch.Tensor, w16t, ln_flat):
+    """TowerWeights whose tensors are views into one image's parameter vectors (fp32 `rest`, fp16 `w16`/`w16t`)."""
+    d = lay.d
+    t = E.TowerWeights(kind="visual", d=d, heads=base.heads, n_layers=lay.nl, L=lay.L, E=lay.E, patch=base.patch,
+                       resolution=base.resolution, k_pad=lay.k_pad)
+    t.conv_w = w16[lay.conv:lay.conv + d * lay.k_pad].view(d, lay.k_pad)
+    t.cls = rest[lay.cls:lay.cls + d]
+    t.pos = rest[lay.pos:lay.pos + lay.L * d].view(lay.L, d)
+    t.proj = rest[lay.proj:lay.proj + d * lay.E].view(d, lay.E)
+    t.ln_flat = ln_flat
+    for l in range(lay.nl):
+        def m(buf, off, r, c):
+            return None if buf is None else buf[off:off + r * c].view(r, c)
+        t.layers.append(E.LayerWeights(
+            wqkv=m(w16, lay.wq[l], 3 * d, d), bqkv=rest[lay.bq[l]:lay.bq[l] + 3 * d],
+            wo=m(w16, lay.wo[l], d, d), bo=rest[lay.bo[l]:lay.bo[l] + d],
+            wfc=m(w16, lay.wf[l], 4 * d, d), bfc=rest[lay.bf[l]:lay.bf[l] + 4 * d],
+            wproj=m(w16, lay.wp[l], d, 4 * d), bproj=rest[lay.bp[l]:lay.bp[l] + d],
+            wqkv_t=m(w16t, lay.wq[l], d, 3 * d), wo_t=m(w16t, lay.wo[l], d, d),
+            wfc_t=m(w16t, lay.wf[l], d, 4 * d), wproj_t=m(w16t, lay.wp[l], 4 * d, d)))
+    return t
+
+
+class WgradHook:
+    """Weight / bias / embedding gradients of `n_sets` images whose rows are laid out set after set.
+    grads: fp32 [n_sets, lay.total] (written, not accumulated).  dY carries the loss scale; so do the gradients."""
+
+    def __init__(self, lay: FullLayout, w: E.TowerWeights, n_sets_max: int, seqs_per_set: int, device):
+        self.lay, self.w, self.S = lay, w, seqs_per_set
+        d, L = lay.d, lay.L
+        self.rows = seqs_per_set * L
+        self.rows_pad = E._round_up(self.rows, 8)
+        self.prow = seqs_per_set * (L - 1)
+        self.prow_pad = E._round_up(self.prow, 8)
+        f16 = dict(dtype=torch.float16, device=device)
+        self.t_dy = torch.empty(4 * d, n_sets_max * self.rows_pad, **f16)
+        self.t_x = torch.empty(max(4 * d, lay.k_pad), n_sets_max * self.rows_pad, **f16)
+        self.dx_pre = torch.empty(n_sets_max * self.rows, d, dtype=torch.float32, device=device)
+        self.y = torch.empty(n_sets_max * seqs_per_set, d, dtype=torch.float32, device=device)
+        self.df = torch.empty(n_sets_max * seqs_per_set, lay.E, dtype=torch.float32, device=device)
+        self.grads = None
+        self.n_sets = 0
+        self.patches = None
+
+    def bind(self, grads: torch.Tensor, n_sets: int, patches: torch.Tensor):
+        self.grads, self.n_sets, self.patches = grads, n_sets, patches
+
+    def _wgrad(self, dY, X, n_out, n_in, off, rows, rows_pad, skip=0, dy_stride_rows=None, x_rows=None):
+        ns = self.n_sets
+        ld = ns * rows_pad
+        ops.transpose_blocks(dY, ns, rows, rows_pad, n_out, self.t_dy, ld, skip_first=skip,
+                             in_set_stride_rows=dy_stride_rows)
+        ops.transpose_blocks(X, ns, rows, rows_pad, n_in, self.t_x, ld)
+        ty, tx = self.t_dy.view(-1)[:n_out * ld].view(n_out, ld), self.t_x.view(-1)[:n_in * ld].view(n_in, ld)
+        for g in range(ns):
+            out = self.grads[g, off:off + n_out * n_in].view(n_out, n_in)
+            ops.gemm(ty[:, g * rows_pad:(g + 1) * rows_pad], tx[:, g * rows_pad:(g + 1) * rows_pad], out,
+                     epilogue=EPI_F32)
+
+    def linear(self, l: int, name: str, dY: torch.Tensor, X: torch.Tensor):
+        lay, d = self.lay, self.lay.d
+        n_out, n_in, woff, boff = {"in_proj": (3 * d, d, lay.wq[l], lay.bq[l]), "out_proj": (d, d, lay.wo[l], lay.bo[l]),
+                                   "c_fc": (4 * d, d, lay.wf[l], lay.bf[l]),
+                                   "c_proj": (d, 4 * d, lay.wp[l], lay.bp[l])}[name]
+        self._wgrad(dY, X, n_out, n_in, woff, self.rows, self.rows_pad)
+        ops.colsum_f16(dY, self.n_sets, self.rows, n_out, self.grads[:, boff:], self.grads.stride(0))
+
+    def embed(self, dx_pre: torch.Tensor):
+        lay, d, L = self.lay, self.lay.d, self.lay.L
+        ns = self.n_sets
+        # positional embedding (row 0 of it is also the class-embedding gradient: x_pre[v,0] = cls + pos[0])
+        ops.seq_sum(dx_pre, ns, self.S, L, d, self.grads[:, lay.pos:], self.grads.stride(0))
+        self.grads[:ns, lay.cls:lay.cls + d].copy_(self.grads[:ns, lay.pos:lay.pos + d])
+        # conv1: d patch_out = dx_pre without the class-token rows; X = the im2col patches of the same views
+        self._wgrad(dx_pre, self.patches, d, lay.k_pad, lay.conv, self.prow, self.prow_pad, skip=L,
+                    dy_stride_rows=self.rows)
+
+    def proj(self):
+        lay = self.lay
+        ops.outer_sum(self.y, self.df, self.n_sets, self.S, lay.d, lay.E, self.grads[:, lay.proj:], self.grads.stride(0))
+
+
+class FullTuneEngine:
+    """Batched RLCF adaptation of the whole image encoder for `n_img` independent test images."""
+
+    def __init__(self, sd_visual: dict, class_feat: torch.Tensor, logit_scale: float, cfg: E.RlcfConfig, n_img: int,
+                 reward: E.TowerWeights, reward_class_feat: torch.Tensor, prefix: str = "visual."):
+        self.cfg, self.n_img = cfg, n_img
+        self.base = E.prepare_visual(sd_visual, prefix=prefix, need_grad=True)
+        pol = self.base
+        dev = pol.ln_flat.device
+        self.lay = lay = FullLayout(pol)
+        self.class_feat = class_feat.float().contiguous()
+        self.logit_scale = float(logit_scale)
+        self.reward, self.reward_class_feat = reward, reward_class_feat.float().contiguous()
+        B, V, S, C = n_img, cfg.n_views, cfg.n_selected, self.class_feat.shape[0]
+        if S < 1:
+            raise RlcfError(f"int(n_views * selection_p) = {S}: no view would be selected (tpt_cls_rl.py:34)")
+        if cfg.loss != "rlcf":
+            raise NotImplementedError("full tuning implements the RLCF loss")
+        P = pol.P
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.run = E.TowerRunner(pol, B * V)
+        self.run.reserve_backward(B * S)
+        self.store = E.ActStore(pol, B * S, dev, full=True)
+        self.prun = E.TowerRunner(pol, S)            # per-image work (steps >= 2, adapted prediction)
+        self.prun.reserve_backward(S)
+        self.pstore = E.ActStore(pol, S, dev, full=True) if cfg.tta_steps > 1 else None
+        self.rrun = E.TowerRunner(reward, B * S)
+        self.hook = WgradHook(lay, pol, B, S, dev)
+        # parameters: LayerNorm slice as in RlcfEngine, everything else in `rest`
+        self.init_ln = pol.ln_flat.clone()
+        self.init_rest = pack_rest(sd_visual, lay, prefix)
+        self.ln = torch.empty(B, P, **f32); self.ln_m = torch.empty(B, P, **f32); self.ln_v = torch.empty(B, P, **f32)
+        self.n_slots = max(E.N_SLOTS, S)
+        self.partials = torch.empty(B, self.n_slots, P, **f32)
+        self.ln_grad = torch.empty(B, P, **f32)
+        self.rest = torch.empty(B, lay.total, **f32)
+        self.rest_m = torch.empty(B, lay.total, **f32)
+        self.rest_v = torch.empty(B, lay.total, **f32)
+        self.grads = torch.zeros(B, lay.total, **f32)
+        self.w16 = torch.empty(B, lay.p_gemm, dtype=torch.float16, device=dev)
+        self.w16t = torch.empty(B, lay.p_gemm, dtype=torch.float16, device=dev) if cfg.tta_steps > 1 else None
+        self.img_w = [tower_view(pol, lay, self.rest[b], self.w16[b], None if self.w16t is None else self.w16t[b],
+                                 self.ln[b]) for b in range(B)]
+        self.logits_all = torch.empty(B * V, C, **f32)
+        self.entropy = torch.empty(B, V, **f32)
+        self.sel = torch.empty(B, S, **i32)
+        self.sel_global = torch.empty(B * S, **i32)
+        self.first_view = (torch.arange(B, device=dev, dtype=torch.int32) * V).contiguous()
+        self.logits_sel = torch.empty(B * S, C, **f32)
+        self.feat_sel = torch.empty(B * S, pol.E, **f32)
+        self.inv_norm_sel = torch.empty(B * S, **f32)
+        self.dlogits = torch.empty(B * S, C, **f32)
+        self.topk_idx = torch.empty(B * S, cfg.sample_k, **i32)
+        self.scores = torch.empty(B * S, cfg.sample_k, **f32)
+        self.rewards = torch.empty(B * S, cfg.sample_k, **f32)
+        self.loss = torch.empty(cfg.tta_steps, B, **f32)
+        self.logits_final = torch.empty(B, C, **f32)
+        self.reward_feat = torch.empty(B * S, reward.E, **f32)
+        self._graph = None
+        self._static_images = None
+
+    # ------------------------------------------------------------------
+    def _loss_and_head_bwd(self, step, xs, runner, ln, pstride, n_sets, w, rows0=0):
+        """reward loss + head backward for sets [rows0, rows0 + n_sets) whose tower outputs are in xs."""
+        cfg = self.cfg
+        S, K, C = cfg.n_selected, cfg.sample_k, self.class_feat.shape[0]
+        pol = self.base
+        sl = slice(rows0 * S, (rows0 + n_sets) * S)
+        runner.head(xs, n_sets * S, ln, pstride=pstride, seqs_per_set=S, class_feat=self.class_feat,
+                    logit_scale=self.logit_scale, feat=self.feat_sel[sl], inv_norm=self.inv_norm_sel[sl],
+                    logits=self.logits_sel[sl], w=w)
+        ops.reward_loss(self.logits_sel[sl], None, self.reward_feat[sl], self.reward_class_feat, n_sets, S, K, C,
+                        self.dlogits[sl], clipscore_weight=cfg.clipscore_weight, reward_process=cfg.reward_process,
+                        process_batch=cfg.process_batch, amplify=cfg.reward_amplify, loss_scale=cfg.loss_scale,
+                        topk_idx=self.topk_idx[sl], scores=self.scores[sl], rewards=self.rewards[sl],
+                        loss=self.loss[step - 1][rows0:rows0 + n_sets])
+        off = pol.ln_off("ln_post")
+        lnv = ln.view(-1)
+        runner.dres[:n_sets * S * pol.L].zero_()
+        hk = self.hook
+        ops.head_bwd_ex(self.dlogits[sl], (S * C, C, 1), xs, lnv[off:], w.proj, self.class_feat, 0, self.logit_scale,
+                        self.feat_sel[sl], self.inv_norm_sel[sl], n_sets, S, pol.d, pol.E, C, runner.dres,
+                        row_stride=pol.L, param_stride=pstride, partials=self.partials[rows0:rows0 + n_sets],
+                        n_slots=self.n_slots, p_total=pol.P, p_off=off, beta=lnv[off + pol.d:], y_out=hk.y,
+                        df_out=hk.df)
+
+    def _adamw(self, step):
+        cfg, B, P, lay = self.cfg, self.n_img, self.base.P, self.lay
+        kw = dict(beta1=cfg.betas[0], beta2=cfg.betas[1], eps=cfg.eps, weight_decay=cfg.weight_decay,
+                  loss_scale=cfg.loss_scale)
+        ops.adamw_step(self.ln, self.ln_m, self.ln_v, self.partials, B, self.n_slots, P, cfg.lr, step,
+                       grad_out=self.ln_grad, **kw)
+        if step == 1:   # parameters come from the shared initial copy, moments start from zero: no per-image reset
+            ops.adamw_step_from(self.rest, self.rest_m, self.rest_v, self.grads, B, 1, lay.total, cfg.lr, step,
+                                self.init_rest, 0, True, **kw)
+        else:
+            ops.adamw_step_from(self.rest, self.rest_m, self.rest_v, self.grads, B, 1, lay.total, cfg.lr, step,
+                                self.rest, lay.total, False, **kw)
+        # fp16 copies of the updated GEMM weights (and their transposes when another backward follows)
+        ops.call("rlcf_cast_f16", ops.ptr(self.rest), B, lay.p_gemm, lay.total, ops.ptr(self.w16), lay.p_gemm,
+                 ops.stream())
+        if step < cfg.tta_steps:
+            d = lay.d
+            for b in range(B):
+                for l in range(lay.nl):
+                    for off, r, c in ((lay.wq[l], 3 * d, d), (lay.wo[l], d, d), (lay.wf[l], 4 * d, d),
+                                      (lay.wp[l], d, 4 * d)):
+                        ops.call("rlcf_transpose_cast_f16", ops.ptr(self.rest[b, off:]), r, c,
+                                 ops.ptr(self.w16t[b, off:]), ops.stream())
+
+    def tune(self, images: torch.Tensor):
+        cfg, B = self.cfg, self.n_img
+        V, S, C = cfg.n_views, cfg.n_selected, self.class_feat.shape[0]
+        pol, P, hk = self.base, self.base.P, self.hook
+        if images.shape[0] != B * V:
+            raise RlcfError(f"expected {B * V} views, got {images.shape[0]}")
+        ops.reset_params(self.init_ln, self.ln, self.ln_m, self.ln_v, B, P)
+        x = self.run.forward(B * V, self.init_ln, images=images)
+        self.run.head(x, B * V, self.init_ln, class_feat=self.class_feat, logit_scale=self.logit_scale,
+                      logits=self.logits_all)
+        ops.entropy_select(self.logits_all, B, V, C, S, self.sel, self.sel_global, self.entropy)
+        xr = self.rrun.forward(B * S, self.reward.ln_flat, images=images, view_idx=self.sel_global)
+        self.rrun.head(xr, B * S, self.reward.ln_flat, feat=self.reward_feat)
+        # ---- step 1: all images on the shared initial weights
+        xs = self.run.forward(B * S, self.ln, pstride=P, seqs_per_set=S, images=images, view_idx=self.sel_global,
+                              store=self.store)
+        self.partials.zero_()
+        self._loss_and_head_bwd(1, xs, self.run, self.ln, P, B, pol)
+        hk.bind(self.grads, B, self.run.patches)
+        hk.proj()
+        self.run.backward(self.store, B, S, self.ln, P, self.partials, self.n_slots, hook=hk)
+        self._adamw(1)
+        # ---- steps >= 2: every image on its own weights
+        for step in range(2, cfg.tta_steps + 1):
+            self.partials.zero_()
+            for b in range(B):
+                w = self.img_w[b]
+                xs = self.prun.forward(S, self.ln[b], images=images, view_idx=self.sel_global[b * S:(b + 1) * S],
+                                       store=self.pstore, w=w)
+                self._loss_and_head_bwd(step, xs, self.prun, self.ln[b], 0, 1, w, rows0=b)
+                hk.bind(self.grads[b:b + 1], 1, self.prun.patches)
+                hk.proj()   # head_bwd of this one-image call left y / d f in rows [0, S)
+                self.prun.backward(self.pstore, 1, S, self.ln[b], 0, self.partials[b:b + 1], self.n_slots, w=w, hook=hk)
+            self._adamw(step)
+        return self.ln, self.rest
+
+    def predict(self, images: torch.Tensor) -> torch.Tensor:
+        B = self.n_img
+        for b in range(B):
+            w = self.img_w[b]
+            xf = self.prun.forward(1, self.ln[b], images=images, view_idx=self.first_view[b:b + 1], w=w)
+            self.prun.head(xf, 1, self.ln[b], class_feat=self.class_feat, logit_scale=self.logit_scale,
+                           logits=self.logits_final[b:b + 1], w=w)
+        return self.logits_final
+
+    def adapt(self, images: torch.Tensor) -> torch.Tensor:
+        self.tune(images)
+        return self.predict(images)
+
+    capture = E.RlcfEngine.capture
+    adapt_graph = E.RlcfEngine.adapt_graph
+
+    def algorithmic_flops_per_image(self) -> float:
+        """SURVEY.md 8(d), full tuning: backward = dgrad + wgrad over the selected views."""
+        cfg, w = self.cfg, self.base
+        V, S = cfg.n_views, cfg.n_selected
+        f = E.RlcfEngine.tower_fwd_flops(w)
+        wgrad = w.n_layers * 24 * w.L * w.d * w.d + 2 * (w.L - 1) * w.d * 3 * w.patch * w.patch + 2 * w.d * w.E
+        bwd = E.RlcfEngine.tower_dgrad_flops(w) + wgrad
+        total = V * f + S * bwd + f + (cfg.tta_steps - 1) * S * (f + bwd) + S * E.RlcfEngine.tower_fwd_flops(self.reward)
+        return float(total)
+
+    def export_params(self, b: int, prefix: str = "visual.") -> dict:
+        """Adapted parameters of image b under the reference's state-dict names (conv1 in its [d,3,p,p] shape)."""
+        lay, pol = self.lay, self.base
+        out = {}
+        for key, off, shape in lay.entries(prefix):
+            n = 1
+            for s_ in shape:
+                n *= s_
+            t = self.rest[b, off:off + n].view(shape)
+            if key.endswith("conv1.weight"):
+                t = t[:, :3 * pol.patch * pol.patch].reshape(lay.d, 3, pol.patch, pol.patch)
+            out[key] = t
+        for key, off in pol.ln_names(prefix):
+            out[key] = self.ln[b, off:off + pol.d]
+        return out

@@ -28,8 +28,11 @@ GEMM_TIMER = None
 
 
 def gemm(a, b, out, epilogue=EPI_F16, bias=None, resid=None, aux_in=None, aux_out=None, alpha=1.0, M=None):
-    """out[M,N] = epilogue(alpha * a[M,K] @ b[N,K]^T).  a, b fp16 row-major; M may restrict the rows used."""
-    _chk(a, torch.float16, "a"); _chk(b, torch.float16, "b")
+    """out[M,N] = epilogue(alpha * a[M,K] @ b[N,K]^T).  a, b fp16 row-major (row-strided views allowed: the leading
+    dimension is passed to the kernel); M may restrict the rows used."""
+    for t, nm in ((a, "a"), (b, "b")):
+        if not t.is_cuda or t.dtype != torch.float16 or t.dim() != 2 or t.stride(1) != 1:
+            raise _lib.RlcfError(f"gemm: {nm} must be a 2-D CUDA fp16 tensor with unit inner stride")
     _chk(bias, torch.float32, "bias"); _chk(resid, torch.float32, "resid")
     _chk(aux_in, torch.float16, "aux_in"); _chk(aux_out, torch.float16, "aux_out")
     m = a.shape[0] if M is None else M
@@ -147,12 +150,48 @@ def head_bwd(dlogits, x, gamma, proj, class_feat, logit_scale, feat, inv_norm, n
 
 def head_bwd_ex(dlogits, dl_strides, x, gamma, proj, other_feat, other_set_stride, logit_scale, feat, inv_norm, n_sets,
                 seqs_per_set, d, E, K, dres, row_idx=None, row_stride=1, param_stride=0, partials=None, n_slots=1,
-                p_total=0, p_off=0, eps=1e-5):
+                p_total=0, p_off=0, eps=1e-5, beta=None, y_out=None, df_out=None):
     _chk(dlogits, torch.float32, "dlogits"); _chk(x, torch.float32, "x"); _chk(dres, torch.float32, "dres")
     _chk(other_feat, torch.float32, "other_feat"); _chk(row_idx, torch.int32, "row_idx")
     call("rlcf_head_bwd_ex", ptr(dlogits), dl_strides[0], dl_strides[1], dl_strides[2], ptr(x), ptr(row_idx), row_stride,
          ptr(gamma), param_stride, ptr(proj), ptr(other_feat), other_set_stride, float(logit_scale), ptr(feat),
-         ptr(inv_norm), n_sets, seqs_per_set, d, E, K, eps, ptr(dres), ptr(partials), n_slots, p_total, p_off, stream())
+         ptr(inv_norm), n_sets, seqs_per_set, d, E, K, eps, ptr(dres), ptr(partials), n_slots, p_total, p_off,
+         ptr(beta), ptr(y_out), ptr(df_out), stream())
+
+
+def adamw_step_from(params, m, v, grads, n_sets, n_slots, p_total, lr, step, params_in, params_in_stride, fresh,
+                    beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2, loss_scale=1.0):
+    for t, nm in ((params, "params"), (m, "m"), (v, "v"), (grads, "grads"), (params_in, "params_in")):
+        _chk(t, torch.float32, nm)
+    call("rlcf_adamw_step_from", ptr(params), ptr(m), ptr(v), ptr(grads), n_sets, n_slots, p_total, float(lr),
+         float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(loss_scale), ptr(params_in),
+         params_in_stride, int(bool(fresh)), stream())
+
+
+def transpose_blocks(src, n_sets, rows_per_set, rows_pad, cols, out, ld_out, skip_first=0, in_set_stride_rows=None):
+    """out[c, g*rows_pad + r] = src[row(g, r), c] as fp16 (src fp16 or fp32), zero padded rows."""
+    _chk(out, torch.float16, "out")
+    if src.dtype not in (torch.float16, torch.float32) or not src.is_cuda:
+        raise _lib.RlcfError("transpose_blocks: src must be a CUDA fp16/fp32 tensor")
+    stride = rows_per_set if in_set_stride_rows is None else in_set_stride_rows
+    call("rlcf_transpose_blocks_f16", ptr(src), int(src.dtype == torch.float32), n_sets, rows_per_set, rows_pad, cols,
+         skip_first, stride, ptr(out), ld_out, stream())
+    return out
+
+
+def colsum_f16(src, n_sets, rows_per_set, cols, out, out_stride):
+    _chk(src, torch.float16, "src"); _chk(out, torch.float32, "out")
+    call("rlcf_colsum_f16", ptr(src), n_sets, rows_per_set, cols, ptr(out), out_stride, stream())
+
+
+def seq_sum(dx, n_sets, S, L, d, out, out_stride):
+    _chk(dx, torch.float32, "dx"); _chk(out, torch.float32, "out")
+    call("rlcf_seq_sum", ptr(dx), n_sets, S, L, d, ptr(out), out_stride, stream())
+
+
+def outer_sum(y, df, n_sets, S, d, E, out, out_stride):
+    _chk(y, torch.float32, "y"); _chk(df, torch.float32, "df"); _chk(out, torch.float32, "out")
+    call("rlcf_outer_sum", ptr(y), ptr(df), n_sets, S, d, E, ptr(out), out_stride, stream())
 
 
 def embed_prompts(tokens, tok_emb, pos, ctx, ctx_stride, n_ctx, n_sets, x):

@@ -333,3 +333,49 @@ def test_vit_l14_policy_config5_shape():
     check_image(eng, 0, ref, cfg, "L14", sd_p, cf.cpu(), views[:1])
     g, gr = eng.grad[0].cpu(), o["grads"][0]
     assert (g - gr).abs().max() <= 2e-2 * gr.abs().max()
+
+
+@pytest.mark.parametrize("steps", [1, 2])
+def test_full_encoder_tuning_matches_oracle(steps):
+    """Full image-encoder tuning (tune_cls_rl.py --tune_norm 0): weight gradients for every visual
+    parameter, per-image AdamW state and per-image weights for the later steps and the adapted prediction."""
+    from rlcf_b200 import full_tune as FT
+    cfg = dict(policy="tiny-A", reward="tiny-B", V=16, rho=0.25, K=3, C=10, steps=steps, lr=1e-4, n_img=2)
+    sd_p = O.make_clip_state_dict(cfg["policy"], POLICY_SEED)
+    sd_r = O.make_clip_state_dict(cfg["reward"], REWARD_SEED)
+    tok = O.make_tokens(cfg["C"], 512, seed=TOKEN_SEED)
+    cf, rc = O.class_features(sd_p, tok), O.class_features(sd_r, tok)
+    rcfg = E.RlcfConfig(n_views=16, selection_p=0.25, tta_steps=steps, sample_k=3, lr=cfg["lr"])
+    eng = FT.FullTuneEngine(to_dev(sd_p), cf.to(DEV), float(sd_p["logit_scale"].exp()), rcfg, 2,
+                            E.prepare_visual(to_dev(sd_r)), rc.to(DEV))
+    views = O.make_views(2, 16, 64, VIEW_SEED + 3)
+    out = eng.adapt(views.to(DEV)).cpu()
+    ocfg = O.OracleConfig(n_views=16, selection_p=0.25, tta_steps=steps, sample_k=3, lr=cfg["lr"])
+    for i in range(2):
+        o = O.adapt_one_image(sd_p, cf, views[i * 16:(i + 1) * 16], ocfg, sd_r, rc, tune="full")
+        assert torch.equal(eng.sel[i].cpu().long(), o["selected_idx"])
+        scale = o["logits_all"].abs().max()
+        delta = (o["logits_final"][0] - o["logits_all"][0]).abs().max()
+        err = (out[i] - o["logits_final"][0]).abs().max()
+        print(f"full/{steps} img{i}: final logits err {err / scale:.2e} (adaptation delta {delta / scale:.2e})")
+        assert err <= LOGIT_TOL * scale + 0.3 * delta
+        got = eng.export_params(i)
+        if steps == 1:
+            # one-step gradients of every parameter tensor against autograd (relative to the tensor's largest entry)
+            gd = o["grad_dicts"][0]
+            g_rest = eng.grads[i] / rcfg.loss_scale
+            for key, off, shape in eng.lay.entries():
+                n = int(np.prod(shape))
+                g = g_rest[off:off + n].view(shape).cpu()
+                ref = gd[key]
+                if key.endswith("conv1.weight"):
+                    g = g[:, :ref[0].numel()].reshape(ref.shape)
+                e = (g - ref).abs().max() / ref.abs().max().clamp_min(1e-20)
+                assert e <= 3e-2, f"{key}: grad rel err {e:.3e}"
+        # updated parameters: sign-like AdamW steps -> flip-aware bounds per tensor
+        worst = 0.0
+        for key, ref in o["param_dict"].items():
+            dlt = (got[key].cpu() - ref).abs()
+            assert dlt.max() <= 2.02 * cfg["lr"] * steps + 1e-7, key
+            worst = max(worst, 1.0 - float((dlt <= 0.05 * cfg["lr"] * steps).float().mean()))
+        assert worst <= 0.1, f"up to {100 * worst:.1f}% of a tensor's entries off by more than 5% of a step"
