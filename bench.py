@@ -43,8 +43,9 @@ def parse_args():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5],
                     help="BASELINE.json configs index: 2 = the metric's workload (default); 3 = same with 3 TTA steps; "
                          "5 = ViT-L/14 policy LN-tuning (informational)")
-    ap.add_argument("--mode", default="ln", choices=["ln", "prompt"],
-                    help="ln = LayerNorm tuning (the BASELINE.json metric); prompt = prompt tuning (informational)")
+    ap.add_argument("--mode", default="ln", choices=["ln", "prompt", "full"],
+                    help="ln = LayerNorm tuning (the BASELINE.json metric); prompt = prompt tuning; full = the whole "
+                         "image encoder is trainable (both informational)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded CPU-baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--torch-gpu-baseline", action="store_true",
@@ -291,6 +292,11 @@ def run_b200(args):
         ctx_init = sd_p["token_embedding.weight"][tok[0, 1:5].to(dev)]
         eng = E.PromptEngine(E.prepare_visual(sd_p), E.prepare_text(sd_p, need_grad=True), tok, ctx_init, logit_scale,
                              cfg, B, reward=rew, reward_class_feat=rc)
+    elif args.mode == "full":
+        from rlcf_b200 import full_tune as FT
+        cf = E.text_features(E.prepare_text(sd_p), tok)
+        cfg.lr = 1e-5                                        # scripts/rlcf-tune.sh
+        eng = FT.FullTuneEngine(sd_p, cf, logit_scale, cfg, B, rew, rc)
     else:
         pol = E.prepare_visual(sd_p, need_grad=True)
         cf = E.text_features(E.prepare_text(sd_p), tok)
@@ -353,7 +359,7 @@ def run_b200(args):
     # ---------------- end-to-end with host buffers (`e2e`): pinned H2D of every step's views + D2H of the logits
     host_in = [b.cpu().pin_memory() for b in batches]
     host_out = torch.empty(B, wl["n_classes"], dtype=torch.float32).pin_memory()
-    pipe = None if args.no_graph else eng.host_pipeline()
+    pipe = None if (args.no_graph or not hasattr(eng, "host_pipeline")) else eng.host_pipeline()
     if pipe is not None:   # warm the copy path
         pipe.submit(host_in[0], 0)
         pipe.run(0, host_out)
@@ -414,8 +420,10 @@ def run_b200(args):
         "dtype": "f16", "data": "synthetic",
         "config": {"workload": "%s RLCF cls, 64 views, %d step(s), reward ViT-L/14 (config %d), " % (
                         wl["policy"], wl["tta_steps"], args.config)
-                               + ("LN-only" if args.mode == "ln" else "prompt tuning (ctx 4x512)"), **wl,
-                   "mode": wl["mode"] if args.mode == "ln" else "prompt tuning (tpt_cls_rl.py, ctx_init a_photo_of_a)",
+                               + {"ln": "LN-only", "prompt": "prompt tuning (ctx 4x512)",
+                                  "full": "full image-encoder tuning"}[args.mode], **wl,
+                   "mode": {"ln": wl["mode"], "prompt": "prompt tuning (tpt_cls_rl.py, ctx_init a_photo_of_a)",
+                            "full": "full image-encoder tuning (--tune_norm 0, lr 1e-5)"}[args.mode],
                    "images_per_step": B, "parallelism": f"dp{world} (independent images, no data-path collective)",
                    "l2": "inputs larger than L2: two alternating resident batches of %.0f MB" % (in_bytes / 1e6),
                    "cuda_graph": not args.no_graph, "gemm_cta_group": _lib.set_gemm_cta_group(0)},

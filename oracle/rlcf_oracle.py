@@ -314,6 +314,10 @@ def adapt_one_image(sd_policy: dict, class_feat: torch.Tensor, views: torch.Tens
     with torch.no_grad(), autocast():
         out["logits_final"] = policy_logits(sd, class_feat, views[:1])                       # tune_cls_rl.py:218-222
     out["params"] = torch.cat([p.detach().flatten() for p in params])
+    out["param_names"] = names
+    out["param_dict"] = {n: p.detach() for n, p in zip(names, params)}
+    out["grad_dicts"] = [dict(zip(names, [t.view_as(p) for t, p in zip(torch.split(g, [p.numel() for p in params]),
+                                                                      params)])) for g in out["grads"]]
     return out
 
 

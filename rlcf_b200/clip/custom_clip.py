@@ -291,13 +291,29 @@ class CLIPCLS_TTA(nn.Module):
         self.clip_model.ln_final.eval()
         return self
 
+    def _full_engine(self, cfg, n_img, reward_model):
+        from .. import full_tune as FT
+        if reward_model is None or reward_model.class_features is None:
+            raise RlcfError("full image-encoder tuning needs a reward model with class features set")
+        vis = self.clip_model.visual
+        rew = reward_model.clip_model.visual.tower()
+        key = ("full", vis._frozen_key(), id(rew), n_img, tuple(sorted(vars(cfg).items())),
+               self.class_features.data_ptr(), reward_model.class_features.data_ptr())
+        eng = self._engines.get(key)
+        if eng is None:
+            self._engines.clear()
+            eng = FT.FullTuneEngine(vis.state_dict(), self.class_features, float(self.clip_model.logit_scale.exp()), cfg,
+                                    n_img, rew, reward_model.class_features, prefix="")
+            self._engines[key] = eng
+        return eng
+
     # ------------------------------------------------------------------ bridge to the batched CUDA engine
     def engine(self, cfg: E.RlcfConfig, n_img: int, reward_model=None) -> E.RlcfEngine:
-        """RlcfEngine for this policy (+ reward model) and configuration, cached."""
-        if not self.only_norm:
-            raise NotImplementedError("GPU adaptation currently covers LayerNorm tuning (--tune_norm 1); full "
-                                      "image-encoder tuning is the next scope row (DESIGN.md, SURVEY.md 8(f2))")
+        """Engine for this policy (+ reward model) and configuration, cached: RlcfEngine for LayerNorm tuning
+        (only_norm=True), FullTuneEngine when the whole image encoder is trainable (only_norm=False)."""
         vis = self.clip_model.visual
+        if not self.only_norm:
+            return self._full_engine(cfg, n_img, reward_model)
         pol = vis.tower(need_grad=True)
         rew = rcls = None
         if reward_model is not None:

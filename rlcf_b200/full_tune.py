@@ -319,6 +319,8 @@ class FullTuneEngine:
 
     capture = E.RlcfEngine.capture
     adapt_graph = E.RlcfEngine.adapt_graph
+    adapt_host = E.RlcfEngine.adapt_host
+    host_pipeline = E.RlcfEngine.host_pipeline
 
     def algorithmic_flops_per_image(self) -> float:
         """SURVEY.md 8(d), full tuning: backward = dgrad + wgrad over the selected views."""

@@ -11,14 +11,15 @@ from . import _lib
 from ._lib import EPI_F16, EPI_F32, EPI_GELU_BWD_F16, EPI_GELU_F16, EPI_RESID_F32, call, ptr, stream  # noqa: F401
 
 
-def _chk(t, dtype, name):
+def _chk(t, dtype, name, strided=False):
+    """strided=True: the tensor is only a base pointer for a kernel that takes its own stride argument."""
     if t is None:
         return
     if not t.is_cuda:
         raise _lib.RlcfError(f"{name} must be a CUDA tensor (rlcf_b200 has no CPU path)")
     if t.dtype != dtype:
         raise _lib.RlcfError(f"{name} must be {dtype}, got {t.dtype}")
-    if not t.is_contiguous():
+    if not strided and not t.is_contiguous():
         raise _lib.RlcfError(f"{name} must be contiguous")
 
 
@@ -180,17 +181,17 @@ def transpose_blocks(src, n_sets, rows_per_set, rows_pad, cols, out, ld_out, ski
 
 
 def colsum_f16(src, n_sets, rows_per_set, cols, out, out_stride):
-    _chk(src, torch.float16, "src"); _chk(out, torch.float32, "out")
+    _chk(src, torch.float16, "src"); _chk(out, torch.float32, "out", strided=True)
     call("rlcf_colsum_f16", ptr(src), n_sets, rows_per_set, cols, ptr(out), out_stride, stream())
 
 
 def seq_sum(dx, n_sets, S, L, d, out, out_stride):
-    _chk(dx, torch.float32, "dx"); _chk(out, torch.float32, "out")
+    _chk(dx, torch.float32, "dx"); _chk(out, torch.float32, "out", strided=True)
     call("rlcf_seq_sum", ptr(dx), n_sets, S, L, d, ptr(out), out_stride, stream())
 
 
 def outer_sum(y, df, n_sets, S, d, E, out, out_stride):
-    _chk(y, torch.float32, "y"); _chk(df, torch.float32, "df"); _chk(out, torch.float32, "out")
+    _chk(y, torch.float32, "y"); _chk(df, torch.float32, "df"); _chk(out, torch.float32, "out", strided=True)
     call("rlcf_outer_sum", ptr(y), ptr(df), n_sets, S, d, E, ptr(out), out_stride, stream())
 
 

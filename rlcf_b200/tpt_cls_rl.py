@@ -72,6 +72,13 @@ def test_time_tuning(model, inputs, optimizer, scaler, args, reward_model=None, 
         if n_img == 1:
             with torch.no_grad():
                 pl.ctx.copy_(params[0].view_as(pl.ctx))
+    elif hasattr(eng, "init_rest"):                # full image-encoder tuning (engine built from the current weights)
+        params = eng.tune(inputs.float().contiguous())
+        if n_img == 1:
+            named = dict(model.clip_model.visual.named_parameters())
+            with torch.no_grad():
+                for key, val in eng.export_params(0, prefix="").items():
+                    named[key].copy_(val.view_as(named[key]))
     else:                                          # image-encoder (LayerNorm) tuning
         vis = model.clip_model.visual
         eng.init_params.copy_(vis.ln_flat())       # adapt from the model's current (reset) state

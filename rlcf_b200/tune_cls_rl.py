@@ -68,9 +68,10 @@ def test_time_adapt_eval(val_loader, model, optimizer, optim_state, scaler, args
         else:
             cfg = engine_config(args, optimizer, reward_model)
             cfg.n_views = views.shape[0] // n
-            eng = model.engine(cfg, n, reward_model)
             model.reset()
-            eng.init_params.copy_(model.clip_model.visual.ln_flat())
+            eng = model.engine(cfg, n, reward_model)
+            if hasattr(eng, "init_params"):      # LayerNorm tuning: adapt from the model's current LN parameters
+                eng.init_params.copy_(model.clip_model.visual.ln_flat())
             output = eng.adapt_graph(views.float().contiguous())
             model.eval()
         acc1, acc5 = accuracy(output, target, topk=(1, 5))       # tune_cls_rl.py:243-245

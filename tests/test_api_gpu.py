@@ -124,15 +124,42 @@ def test_batched_eval_driver_equals_one_at_a_time():
     assert 0.0 <= res_batched[0] <= res_batched[1] <= 100.0
 
 
+def test_full_tuning_through_the_api():
+    """rlcf-tune.sh's default mode (--tune_norm 0): every visual parameter adapts; reset() restores them."""
+    args = make_args()
+    tok = O.make_tokens(10, 512)
+    model = CLIPCLS_TTA(DEV, [f"class {i}" for i in range(10)], arch="synthetic:tiny-A:0",
+                        prompt_prefix="a photo of a", only_norm=False, tokenized_prompts=tok).cuda(0)
+    optimizer = torch.optim.AdamW(model.parameters(), 1e-4, weight_decay=5e-4)
+    optim_state = deepcopy(optimizer.state_dict())
+    assert len(list(model.parameters())) == len(list(model.clip_model.visual.parameters())) > 12
+    reward_model = get_reward_model(DEV, args)
+    reward_model.set_class_features(tokenized_classes=tok.to(DEV))
+    sd_p, sd_r = O.make_clip_state_dict("tiny-A", 0), O.make_clip_state_dict("tiny-B", 1)
+    views = O.make_views(1, 16, 64, 23)
+    model.reset()
+    optimizer.load_state_dict(optim_state)
+    model.train()
+    tpt_cls_rl.test_time_tuning(model, views.to(DEV), optimizer, None, args, reward_model=reward_model)
+    model.eval()
+    out = model(views[:1].to(DEV)).cpu()
+    ocfg = O.OracleConfig(n_views=16, selection_p=0.25, tta_steps=1, sample_k=3, lr=1e-4)
+    ref = O.adapt_one_image(sd_p, model.class_features.cpu(), views, ocfg, sd_r, reward_model.class_features.cpu(),
+                            tune="full")
+    scale = ref["logits_all"].abs().max()
+    delta = (ref["logits_final"] - ref["logits_all"][:1]).abs().max()
+    assert (out - ref["logits_final"]).abs().max() <= 1e-3 * scale + 0.3 * delta
+    w = dict(model.clip_model.visual.named_parameters())["transformer.resblocks.0.mlp.c_fc.weight"].detach().cpu()
+    assert (w - sd_p["visual.transformer.resblocks.0.mlp.c_fc.weight"]).abs().max() > 5e-5     # weights really moved
+    model.reset()
+    w = dict(model.clip_model.visual.named_parameters())["transformer.resblocks.0.mlp.c_fc.weight"].detach().cpu()
+    assert torch.equal(w, sd_p["visual.transformer.resblocks.0.mlp.c_fc.weight"])
+
+
 def test_unsupported_modes_fail_loudly():
     args = make_args()
     with pytest.raises(NotImplementedError):
         get_reward_model(DEV, make_args(multiple_reward_models=1))
-    model = CLIPCLS_TTA(DEV, ["a", "b"], arch="synthetic:tiny-A:0", prompt_prefix="a photo of a", only_norm=False,
-                        tokenized_prompts=O.make_tokens(2, 512)).cuda(0)
-    opt = torch.optim.AdamW(model.parameters(), 1e-5)
-    with pytest.raises(NotImplementedError):
-        tpt_cls_rl.test_time_tuning(model, O.make_views(1, 16, 64, 1).to(DEV), opt, None, args, reward_model=None)
     with pytest.raises(Exception):
         clip.load("synthetic:tiny-A:0", device="cpu")[0].encode_image(torch.zeros(1, 3, 64, 64))  # no CPU fallback
 

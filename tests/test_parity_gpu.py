@@ -372,10 +372,15 @@ def test_full_encoder_tuning_matches_oracle(steps):
                     g = g[:, :ref[0].numel()].reshape(ref.shape)
                 e = (g - ref).abs().max() / ref.abs().max().clamp_min(1e-20)
                 assert e <= 3e-2, f"{key}: grad rel err {e:.3e}"
-        # updated parameters: sign-like AdamW steps -> flip-aware bounds per tensor
-        worst = 0.0
+        # updated parameters: AdamW's first steps are sign-like, so entries whose gradient is numerically zero (e.g.
+        # the key third of in_proj_bias: softmax is invariant to a shift of all keys) move by +-lr at random in ANY
+        # implementation.  Entries whose oracle gradient is clearly signed in every step must agree within 10% of a step.
         for key, ref in o["param_dict"].items():
             dlt = (got[key].cpu() - ref).abs()
             assert dlt.max() <= 2.02 * cfg["lr"] * steps + 1e-7, key
-            worst = max(worst, 1.0 - float((dlt <= 0.05 * cfg["lr"] * steps).float().mean()))
-        assert worst <= 0.1, f"up to {100 * worst:.1f}% of a tensor's entries off by more than 5% of a step"
+            strong = torch.ones_like(ref, dtype=torch.bool)
+            for gd in o["grad_dicts"]:
+                strong &= gd[key].abs() >= 0.05 * gd[key].abs().max()
+            if strong.any():
+                bad = float((dlt[strong] > 0.1 * cfg["lr"] * steps).float().mean())
+                assert bad <= 0.02, f"{key}: {100 * bad:.1f}% of the clearly-signed entries off by > 10% of a step"
