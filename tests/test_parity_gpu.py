@@ -384,3 +384,39 @@ def test_full_encoder_tuning_matches_oracle(steps):
             if strong.any():
                 bad = float((dlt[strong] > 0.1 * cfg["lr"] * steps).float().mean())
                 assert bad <= 0.02, f"{key}: {100 * bad:.1f}% of the clearly-signed entries off by > 10% of a step"
+
+
+@pytest.mark.parametrize("kw", [
+    dict(K=1),                                  # a single sampled class: rewards are returned unprocessed (clip_reward.py:157)
+    dict(K=4, reward_process=0),                # raw CLIPScores as rewards (no baseline): dlogits keeps its softmax term
+    dict(V=5, rho=0.4, C=1000, K=5),            # odd view count, 2 selected views, ImageNet-sized label space, default K
+    dict(V=3, rho=1.0, K=2, steps=3),           # every view selected, several steps
+], ids=["K1", "raw-rewards", "odd-views-C1000", "all-selected-3step"])
+def test_edge_configurations_match_oracle(kw):
+    cfg = dict(policy="tiny-A", reward="tiny-B", V=16, rho=0.25, K=3, C=10, steps=1, lr=5e-3, n_img=2)
+    cfg.update(kw)
+    eng, (sd_p, sd_r, tok_p, tok_r, cf, rc) = build_engine(cfg, cfg["n_img"])
+    V = cfg["V"]
+    views = O.make_views(cfg["n_img"], V, 64, VIEW_SEED + 7)
+    ocfg = O.OracleConfig(n_views=V, selection_p=cfg["rho"], tta_steps=cfg["steps"], sample_k=cfg["K"], lr=cfg["lr"],
+                          reward_process=bool(cfg.get("reward_process", 1)))
+    eng.adapt(views.to(DEV))
+    for i in range(cfg["n_img"]):
+        o = O.adapt_one_image(sd_p, cf.cpu(), views[i * V:(i + 1) * V], ocfg, sd_r, rc.cpu())
+        ref = dict(logits_all=o["logits_all"].numpy(), selected_idx=o["selected_idx"].numpy(),
+                   topk_idx=torch.stack(o["topk_idx"]).numpy(), rewards=torch.stack(o["rewards"]).numpy(),
+                   logits_final=o["logits_final"].numpy(), params=o["params"].numpy(), grads=o["grads"])
+        check_image(eng, i, ref, cfg, f"edge/img{i}", sd_p, cf.cpu(), views[i * V:i * V + 1])
+
+
+def test_bad_inputs_are_rejected():
+    cfg = dict(policy="tiny-A", reward="tiny-B", V=16, rho=0.25, K=3, C=10, steps=1, lr=5e-3, n_img=1)
+    eng, _ = build_engine(cfg, 1)
+    with pytest.raises(Exception):
+        eng.adapt(torch.zeros(16, 3, 32, 32, device=DEV))            # wrong resolution
+    with pytest.raises(Exception):
+        eng.adapt(torch.zeros(15, 3, 64, 64, device=DEV))            # wrong number of views
+    with pytest.raises(Exception):
+        eng.adapt(torch.zeros(16, 3, 64, 64))                        # host tensor: no CPU path
+    with pytest.raises(Exception):
+        build_engine(dict(cfg, K=9), 1)[0].adapt(torch.zeros(16, 3, 64, 64, device=DEV))   # sample_k > 8
