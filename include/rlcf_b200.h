@@ -42,6 +42,8 @@ const char* rlcf_last_error(void);
 uint64_t rlcf_launch_count(void);
 /* 1 = one CTA per tile (UMMA 128x256), 2 = CTA pair per tile (cta_group::2, UMMA 256x256). Returns the value set. */
 int rlcf_set_gemm_cta_group(int cta_group);
+/* 1 = 4-CTA clusters: two CTA pairs share one weight tile through TMA multicast (512 x 256 cluster tile). */
+int rlcf_set_gemm_multicast(int on);
 /* Forward attention kernel: 0 = tcgen05/TMEM kernel (default), 1 = warp-level mma.sync kernel. Returns the value set. */
 int rlcf_set_attention_impl(int impl);
 

@@ -26,6 +26,7 @@ _PROTOS = {
     "rlcf_launch_count": [],
     "rlcf_set_gemm_cta_group": [_i],
     "rlcf_set_attention_impl": [_i],
+    "rlcf_set_gemm_multicast": [_i],
     "rlcf_gemm_f16": [_vp, _i, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "rlcf_im2col_f16": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "rlcf_embed_lnpre": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _f, _vp, _vp, _vp],
@@ -117,6 +118,10 @@ def launch_count() -> int:
 
 def set_attention_impl(impl: int) -> int:
     return int(load().rlcf_set_attention_impl(int(impl)))
+
+
+def set_gemm_multicast(on: int) -> int:
+    return int(load().rlcf_set_gemm_multicast(int(on)))
 
 
 def set_gemm_cta_group(g: int) -> int:

@@ -13,6 +13,7 @@ static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_cta_group{0};
 static std::atomic<int> g_attn_impl{-1};
+static std::atomic<int> g_gemm_mc{-1};
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -40,6 +41,16 @@ int gemm_cta_group() {
     const char* e = getenv("RLCF_GEMM_CTA_GROUP");
     v = (e != nullptr && atoi(e) == 1) ? 1 : 2;
     g_cta_group.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+int gemm_multicast() {
+  int v = g_gemm_mc.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("RLCF_GEMM_MULTICAST");
+    v = (e != nullptr) ? (atoi(e) != 0) : 0;
+    g_gemm_mc.store(v, std::memory_order_relaxed);
   }
   return v;
 }
@@ -113,6 +124,11 @@ uint64_t rlcf_launch_count(void) { return g_launches.load(std::memory_order_rela
 int rlcf_set_gemm_cta_group(int cta_group) {
   if (cta_group == 1 || cta_group == 2) g_cta_group.store(cta_group, std::memory_order_relaxed);
   return gemm_cta_group();
+}
+
+int rlcf_set_gemm_multicast(int on) {
+  if (on == 0 || on == 1) g_gemm_mc.store(on, std::memory_order_relaxed);
+  return gemm_multicast();
 }
 
 int rlcf_set_attention_impl(int impl) {

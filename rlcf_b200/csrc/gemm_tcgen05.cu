@@ -15,6 +15,7 @@
 // The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.  kCtaGroup == 2 pairs two SMs (cta_group::2): each CTA stages its own 128 rows of A
 // and half (128 rows) of B, halving the shared-memory and L2 traffic per FLOP.
+#include <cstdio>
 #include <cstdlib>
 
 #include "ptx.cuh"
@@ -53,10 +54,14 @@ struct GemmArgs {
   int debug_nostore;     // RLCF_GEMM_DEBUG_NOSTORE=1: skip the epilogue's global traffic (timing probe only)
 };
 
-template <int kCtaGroup, int kEpi>
+// kMc = CTA pairs per cluster (cta_group::2 only).  With kMc == 2 a 4-CTA cluster computes a 512 x 256 super tile:
+// the two pairs share the B (weight) tile, which pair 0 loads once and TMA-multicasts into both pairs' shared
+// memory -- 25 % fewer L2->SM operand bytes per FLOP, which is what bounds the K = 768 shapes.
+template <int kCtaGroup, int kEpi, int kMc>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs p) {
   using Cfg = GemmCfg<kCtaGroup>;
+  static_assert(kMc == 1 || kCtaGroup == 2, "multicast needs CTA pairs");
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled UMMA/TMA tiles need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -69,16 +74,18 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = kCtaGroup == 2 ? cluster_ctarank() : 0;
+  const uint32_t cluster_rank = kCtaGroup == 2 ? cluster_ctarank() : 0;
+  const uint32_t pair = cluster_rank >> 1;      // CTA pair inside the cluster
+  const uint32_t cta_rank = cluster_rank & 1;   // rank inside the pair
   const bool leader = cta_rank == 0;
 
-  const int tile_m = kBM * kCtaGroup;
+  const int tile_m = kBM * kCtaGroup * kMc;     // rows per cluster tile
   const int m_tiles = (p.M + tile_m - 1) / tile_m;
   const int n_tiles = (p.N + kBN - 1) / kBN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (p.K + kBK - 1) / kBK;
-  const int worker = blockIdx.x / kCtaGroup;
-  const int num_workers = gridDim.x / kCtaGroup;
+  const int worker = blockIdx.x / (kCtaGroup * kMc);
+  const int num_workers = gridDim.x / (kCtaGroup * kMc);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -87,7 +94,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], kMc);   // one tcgen05.commit arrive per pair that reads this stage
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -110,7 +117,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t peer_mask = 0xFEFFFFFFu;
       for (int t = worker; t < num_tiles; t += num_workers) {
         const int m_blk = t / n_tiles, n_blk = t % n_tiles;
-        const int m0 = m_blk * tile_m + static_cast<int>(cta_rank) * kBM;
+        const int m0 = m_blk * tile_m + static_cast<int>(pair) * kBM * kCtaGroup + static_cast<int>(cta_rank) * kBM;
         const int n0 = n_blk * kBN + static_cast<int>(cta_rank) * Cfg::kBRows;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -124,7 +131,12 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
             const uint32_t bar = smem_u32(&full_bar[stage]) & peer_mask;
             tma_load_2d_cg2(sa, &tmA, bar, kb * kBK, m0);
-            tma_load_2d_cg2(sb, &tmB, bar, kb * kBK, n0);
+            if constexpr (kMc == 1) {
+              tma_load_2d_cg2(sb, &tmB, bar, kb * kBK, n0);
+            } else if (pair == 0) {
+              // this CTA's half of the B tile goes to the CTAs of the same in-pair rank in both pairs
+              tma_load_2d_cg2_mc(sb, &tmB, bar, kb * kBK, n0, static_cast<uint16_t>(0b0101u << cta_rank));
+            }
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -154,12 +166,14 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // advance 32 bytes (16 fp16) along K inside the swizzle atom: +2 in the >>4 address field
             umma_f16_ss<kCtaGroup>(tacc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
+          // the smem slot is released to every producer that writes into it (all CTAs of the cluster when the
+          // B tile is multicast); the accumulator-ready signal goes to this pair's two CTAs only
           if constexpr (kCtaGroup == 1) umma_commit(&empty_bar[stage]);
-          else umma_commit_cg2(&empty_bar[stage], 0b11);
+          else umma_commit_cg2(&empty_bar[stage], static_cast<uint16_t>((1u << (2 * kMc)) - 1));
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
         if constexpr (kCtaGroup == 1) umma_commit(&tfull_bar[as]);
-        else umma_commit_cg2(&tfull_bar[as], 0b11);
+        else umma_commit_cg2(&tfull_bar[as], static_cast<uint16_t>(0b11u << (2 * pair)));
       }
     }
   } else if (warp >= 4) {
@@ -178,7 +192,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int m_blk = t / n_tiles, n_blk = t % n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int row0 = m_blk * tile_m + static_cast<int>(cta_rank) * kBM + ew * 32;
+      const int row0 = m_blk * tile_m + static_cast<int>(pair) * kBM * kCtaGroup + static_cast<int>(cta_rank) * kBM + ew * 32;
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * kBN + half_id * 128;
       const int col_base = n_blk * kBN + half_id * 128;
       const int n_chunks = max(0, min(4, (p.N - col_base + 31) / 32));  // warp-uniform
@@ -194,7 +208,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
         if (lane == 0) {
           if constexpr (kCtaGroup == 1) mbar_arrive(&tempty_bar[as]);
-          else mbar_arrive_cluster(&tempty_bar[as], 0);
+          else mbar_arrive_cluster(&tempty_bar[as], 2 * pair);
         }
       }
       // per-lane global offsets of the coalesced phase: row (row0 + tr + 4 i), columns col_base + 32 c + 4 tj .. +3
@@ -227,7 +241,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
           if (lane == 0) {
             if constexpr (kCtaGroup == 1) mbar_arrive(&tempty_bar[as]);
-            else mbar_arrive_cluster(&tempty_bar[as], 0);
+            else mbar_arrive_cluster(&tempty_bar[as], 2 * pair);
           }
         }
         if (p.debug_nostore) { __syncwarp(); continue; }  // bring-up probe: main loop + TMEM drain only
@@ -304,33 +318,54 @@ static int make_tmap_2d_f16(CUtensorMap* map, const void* base, int rows, int co
   return 0;
 }
 
-template <int kCtaGroup, int kEpi>
+template <int kCtaGroup, int kEpi, int kMc>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
   using Cfg = GemmCfg<kCtaGroup>;
+  constexpr int kClusterCtas = kCtaGroup * kMc;
   static bool configured = false;
+  static int max_clusters = 0;   // co-resident clusters: the kernel is persistent, so the grid must not exceed it
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<kCtaGroup, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<kCtaGroup, kEpi, kMc>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return set_error(RLCF_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
+    max_clusters = sm_count() / kClusterCtas;
+    if (kClusterCtas > 2) {
+      // GPCs do not all hold a multiple of 4 SMs; ask the driver how many 4-CTA clusters fit at once
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3(max_clusters * kClusterCtas);
+      q.blockDim = dim3(kGemmThreads);
+      q.dynamicSmemBytes = Cfg::kSmemBytes;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = kClusterCtas;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      int n = 0;
+      e = cudaOccupancyMaxActiveClusters(&n, gemm_f16_kernel<kCtaGroup, kEpi, kMc>, &q);
+      if (e != cudaSuccess) return set_error(RLCF_ERR_CUDA, "cudaOccupancyMaxActiveClusters: %s", cudaGetErrorString(e));
+      if (n > 0 && n < max_clusters) max_clusters = n;
+      if (getenv("RLCF_GEMM_VERBOSE")) fprintf(stderr, "rlcf gemm: %d-CTA clusters, %d co-resident\n", kClusterCtas, n);
+    }
     configured = true;
   }
-  const int tile_m = kBM * kCtaGroup;
+  const int tile_m = kBM * kClusterCtas;
   const int tiles = ((args.M + tile_m - 1) / tile_m) * ((args.N + kBN - 1) / kBN);
-  const int sms = sm_count();
-  int workers = tiles < sms / kCtaGroup ? tiles : sms / kCtaGroup;
+  int workers = tiles < max_clusters ? tiles : max_clusters;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(workers * kCtaGroup);
+  cfg.gridDim = dim3(workers * kClusterCtas);
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCtaGroup;
+  attr[0].val.clusterDim.x = kClusterCtas;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_f16_kernel<kCtaGroup, kEpi>, ta, tb, args);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_f16_kernel<kCtaGroup, kEpi, kMc>, ta, tb, args);
   if (e != cudaSuccess) return set_error(RLCF_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   count_launch();
   return 0;
@@ -352,9 +387,13 @@ int gemm_f16(const __half* A, int lda, const __half* B, int ldb, int M, int N, i
   if (int rc = make_tmap_2d_f16(&tb, B, N, K, ldb, kBN / cg)) return rc;
   static const int debug_nostore = getenv("RLCF_GEMM_DEBUG_NOSTORE") != nullptr;
   GemmArgs args{M, N, K, epi, bias, resid, aux_in, aux_out, out, ldo, alpha, debug_nostore};
+  // multicast pays once there are at least two 256-row tiles per cluster slot; tiny problems keep 2-CTA clusters
+  const bool mc = cg == 2 && gemm_multicast() && M > 2 * kBM * 2;
   switch (epi) {
-#define RLCF_GEMM_CASE(E) \
-  case E: return cg == 2 ? launch_gemm<2, E>(ta, tb, args, stream) : launch_gemm<1, E>(ta, tb, args, stream);
+#define RLCF_GEMM_CASE(E)                                              \
+  case E:                                                              \
+    if (mc) return launch_gemm<2, E, 2>(ta, tb, args, stream);         \
+    return cg == 2 ? launch_gemm<2, E, 1>(ta, tb, args, stream) : launch_gemm<1, E, 1>(ta, tb, args, stream);
     RLCF_GEMM_CASE(EPI_F16)
     RLCF_GEMM_CASE(EPI_GELU_F16)
     RLCF_GEMM_CASE(EPI_RESID_F32)

@@ -24,6 +24,7 @@ int set_error(int code, const char* fmt, ...);
 void count_launch();
 int sm_count();
 int gemm_cta_group();
+int gemm_multicast();  // 1 = 4-CTA clusters with the B tile TMA-multicast across two CTA pairs
 int attention_impl();  // 0 = tcgen05 forward kernel, 1 = warp-level mma.sync kernel
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
