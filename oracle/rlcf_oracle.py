@@ -392,3 +392,153 @@ def accuracy(output, target, topk=(1,)):
     _, pred = output.topk(maxk, 1, True, True)
     correct = pred.t().eq(target.view(1, -1).expand_as(pred.t()))
     return [correct[:k].reshape(-1).float().sum(0, keepdim=True).mul_(100.0 / target.size(0)) for k in topk]
+
+
+# --------------------------------------------------------------------------------------------------------------
+# retrieval TTA (retrieval/clip_ret_policy.py, retrieval/custom_models.py, retrieval/clip_reward.py)
+# The retrieval CLIP (retrieval/lavis/models/clip_models/model.py:262-376,538-569) is the same ViT / text transformer
+# under the same state-dict keys as TPT/clip/model.py, so the towers above are reused.
+# --------------------------------------------------------------------------------------------------------------
+def openai_load_rounding(sd: dict) -> dict:
+    """load_openai_model -> build_model_from_openai_state_dict (lavis/models/clip_models/model.py:763-791,869-871):
+    the model is converted to fp16 BEFORE load_state_dict, so Conv/Linear/MultiheadAttention weights and biases,
+    `visual.proj` and `text_projection` take fp16-representable values; CLIPRet_TTA / CLIPRewards then call .float()
+    (custom_models.py:41, clip_reward.py:124).  A no-op for OpenAI archives (already fp16), visible for synthetic
+    fp32 weights."""
+    out = {}
+    for k, v in sd.items():
+        rounded = (k.endswith(("conv1.weight", "in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias",
+                               "c_fc.weight", "c_fc.bias", "c_proj.weight", "c_proj.bias"))
+                   or k in ("visual.proj", "text_projection"))
+        out[k] = v.half().float() if rounded else v.clone()
+    return out
+
+
+def retrieval_features(sd: dict, images=None, tokens=None) -> torch.Tensor:
+    """CLIPRet_TTA.get_image_features / get_text_features (retrieval/custom_models.py:78-90) and the reward model's
+    extract_*_features (retrieval/clip_reward.py:170-189): L2-normalised features."""
+    f = encode_image(sd, images) if images is not None else encode_text(sd, tokens)
+    return F.normalize(f, dim=-1)
+
+
+def retrieval_clip_score(reward_text, reward_image, sample_k, text_index=None, images_index=None, weight=2.5):
+    """CLIPRewards.CLIPScore with pairwise=False (retrieval/clip_reward.py:143-168)."""
+    t = reward_text[text_index] if text_index is not None else torch.repeat_interleave(reward_text, sample_k, dim=0)
+    i = reward_image[images_index] if images_index is not None else torch.repeat_interleave(reward_image, sample_k, dim=0)
+    similarity = weight * torch.sum(t * i, dim=-1)
+    return torch.maximum(similarity, torch.zeros_like(similarity)).squeeze()
+
+
+@dataclass
+class RetrievalConfig:
+    tta_steps: int = 8            # scripts/tta_coco_ret.sh:33
+    sample_k: int = 20            # 20 for image->text, 12 for text->image (tta_coco_ret.sh:19-20)
+    lr: float = 1e-6
+    weight_decay: float = 5e-4
+    eps: float = 1e-6             # clip_ret_policy.py:235
+    reward_process: bool = True
+    process_batch: bool = False
+    reward_amplify: bool = False
+    momentum_update: bool = False
+    update_freq: int = 256
+    update_w: float = 1.0
+    momentum: float = 0.9999
+
+
+def retrieval_trainable(sd: dict, task: str) -> list:
+    """CLIPRet_TTA.parameters (retrieval/custom_models.py:144-152): image->text tunes every `visual.*` parameter,
+    text->image every other parameter -- including token_embedding and logit_scale.  Sorted by name so that a
+    concatenation of them does not depend on the state dict's insertion order."""
+    vis = task == "image2text"
+    return sorted(k for k in sd if k.startswith("visual.") == vis)
+
+
+def retrieval_tune_query(sd_init: dict, cfg: RetrievalConfig, task: str, query: torch.Tensor, gallery: torch.Tensor,
+                         reward_query: torch.Tensor, reward_gallery: torch.Tensor) -> dict:
+    """tune_image / tune_text (retrieval/clip_ret_policy.py:76-137) followed by the evaluation forward of
+    test_time_tune (161-168 / 178-184), for ONE query on the weights `sd_init`.
+
+    task "image2text": query = image [1,3,H,W]; gallery = policy text features [Nt,E]; reward_query = reward-model
+    feature of the image [1,Er]; reward_gallery = reward text features [Nt,Er].
+    task "text2image": query = token ids [1,77]; gallery = policy image features [Ni,E]; reward_query = reward text
+    feature [1,Er]; reward_gallery = reward image features [Ni,Er]."""
+    i2t = task == "image2text"
+    sd = {k: v.clone() for k, v in sd_init.items()}                      # reset_initial(), custom_models.py:122-124
+    names = retrieval_trainable(sd, task)
+    params = [sd[n].requires_grad_(True) for n in names]
+    opt = torch.optim.AdamW(params, lr=cfg.lr, eps=cfg.eps, weight_decay=cfg.weight_decay)   # clip_ret_policy.py:235
+    K = cfg.sample_k
+
+    def model():                                                         # CLIPRet_TTA.forward, custom_models.py:66-76
+        f = retrieval_features(sd, images=query) if i2t else retrieval_features(sd, tokens=query)
+        return sd["logit_scale"].exp() * f @ gallery.t()
+
+    out = {"losses": [], "topk_idx": [], "scores": [], "rewards": [], "grads": []}
+    for _ in range(cfg.tta_steps):
+        opt.zero_grad()
+        logits = model()
+        _, index = torch.topk(logits, K, dim=-1)                         # clip_ret_policy.py:90 / 123
+        flat = index.flatten()
+        if i2t:
+            score = retrieval_clip_score(reward_gallery, reward_query, K, text_index=flat)
+        else:
+            score = retrieval_clip_score(reward_query, reward_gallery, K, images_index=flat)
+        rewards = rewards_post_process(score if cfg.process_batch else score.reshape(logits.shape[0], -1),
+                                       cfg.reward_process, cfg.reward_amplify)
+        rep = torch.repeat_interleave(logits, K, dim=0)
+        loss = torch.mean(rewards * F.cross_entropy(rep, flat, reduction="none"))   # clip_ret_policy.py:97-98
+        loss.backward()
+        out["grads"].append({n: (torch.zeros_like(p) if p.grad is None else p.grad.clone()) for n, p in zip(names, params)})
+        opt.step()
+        out["losses"].append(float(loss.detach()))
+        out["topk_idx"].append(index.detach()[0])
+        out["scores"].append(score.detach().reshape(-1))
+        out["rewards"].append(rewards.detach().reshape(-1))
+    with torch.no_grad():
+        out["score_row"] = model()[0]                                    # clip_ret_policy.py:166-167 / 183-184
+    out["state"] = {k: v.detach() for k, v in sd.items()}
+    out["param_names"] = names
+    return out
+
+
+class RetrievalMomentum:
+    """CLIPRet_TTA's cross-query state (retrieval/custom_models.py:55-60,114-142): `initial` is what every query
+    starts from; with momentum_update an EMA of the adapted weights replaces it every `update_freq` queries."""
+
+    def __init__(self, sd: dict, cfg: RetrievalConfig):
+        self.cfg = cfg
+        self.clip = {k: v.clone() for k, v in sd.items()}
+        self.initial = {k: v.clone() for k, v in sd.items()}
+        self.ema = {k: v.clone() for k, v in sd.items()} if cfg.momentum_update else None
+        self.counter = 0
+
+    def update(self, adapted: dict):
+        """momentum_update_model (custom_models.py:126-142), called after each query with the adapted weights."""
+        c = self.cfg
+        if not c.momentum_update:
+            return
+        self.counter += 1
+        for k, v in adapted.items():
+            self.ema[k] = c.momentum * self.ema[k] + (1.0 - c.momentum) * v
+        if self.counter >= c.update_freq:
+            self.counter = 0
+            for k in adapted:
+                self.initial[k] = (1 - c.update_w) * self.clip[k] + c.update_w * self.ema[k]
+
+
+def retrieval_report_metrics(scores_i2t: np.ndarray, scores_t2i: np.ndarray, txt2img, img2txt) -> dict:
+    """RetrievalTask._report_metrics (retrieval/lavis/tasks/retrieval.py:52-107) without the log-file write:
+    recall@1/5/10 both ways.  Ranks follow np.argsort(score)[::-1] exactly (ties broken as numpy does)."""
+    ranks = np.zeros(scores_i2t.shape[0])
+    for index, score in enumerate(scores_i2t):
+        inds = np.argsort(score)[::-1]
+        ranks[index] = min(int(np.where(inds == i)[0][0]) for i in img2txt[index])
+    tr = [100.0 * float(np.sum(ranks < k)) / len(ranks) for k in (1, 5, 10)]
+    ranks = np.zeros(scores_t2i.shape[0])
+    for index, score in enumerate(scores_t2i):
+        inds = np.argsort(score)[::-1]
+        ranks[index] = np.where(inds == txt2img[index])[0][0]
+    ir = [100.0 * float(np.sum(ranks < k)) / len(ranks) for k in (1, 5, 10)]
+    tr_mean, ir_mean = sum(tr) / 3, sum(ir) / 3
+    return {"txt_r1": tr[0], "txt_r5": tr[1], "txt_r10": tr[2], "txt_r_mean": tr_mean, "img_r1": ir[0], "img_r5": ir[1],
+            "img_r10": ir[2], "img_r_mean": ir_mean, "r_mean": (tr_mean + ir_mean) / 2, "agg_metrics": sum(tr) / 3}
