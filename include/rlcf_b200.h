@@ -55,6 +55,17 @@ int rlcf_gemm_f16(const void* A, int lda, const void* B, int ldb, int M, int N, 
                   const float* bias, const float* resid, const void* aux_in, void* aux_out, void* out, int ldo,
                   void* stream);
 
+/* `groups` independent GEMMs of one shape in a single persistent launch (rank-3 TMA maps: k, row, group): group g
+ * reads A + g*a_group_stride and B + g*b_group_stride, adds bias + g*bias_group_stride and writes
+ * out / resid / aux + g*out_group_stride (strides in elements; A/B/out strides % 8 == 0, bias stride % 4 == 0).
+ * Replaces the per-sample Linear / autograd calls once every test sample owns its weights: TTA steps >= 2 of full
+ * encoder tuning (TPT/tpt_cls_rl.py:52-79 with custom_clip.py:477-479; retrieval/clip_ret_policy.py:84-103) and the
+ * per-sample wgrad dW = dY^T X. */
+int rlcf_gemm_f16_grouped(const void* A, int lda, int64_t a_group_stride, const void* B, int ldb, int64_t b_group_stride,
+                          int groups, int M, int N, int K, int epilogue, float alpha, const float* bias,
+                          int64_t bias_group_stride, const float* resid, const void* aux_in, void* aux_out, void* out,
+                          int ldo, int64_t out_group_stride, void* stream);
+
 /* images fp32 [*,C,H,W] -> patch rows fp16 [n_views*(H/p)*(W/p), k_pad] (column = c*p*p + ky*p + kx, zero padded
  * to k_pad); view_idx (device int32 [n_views], may be NULL = identity) picks the source views.
  * Together with rlcf_gemm_f16 replaces conv1 (model.py:224) and the inputs[selected_idx] gather (tpt_cls_rl.py:55,59). */

@@ -28,6 +28,8 @@ _PROTOS = {
     "rlcf_set_attention_impl": [_i],
     "rlcf_set_gemm_multicast": [_i],
     "rlcf_gemm_f16": [_vp, _i, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "rlcf_gemm_f16_grouped": [_vp, _i, _i64, _vp, _i, _i64, _i, _i, _i, _i, _i, _f, _vp, _i64, _vp, _vp, _vp, _vp, _i,
+                              _i64, _vp],
     "rlcf_im2col_f16": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "rlcf_embed_lnpre": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _f, _vp, _vp, _vp],
     "rlcf_embed_text": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp],

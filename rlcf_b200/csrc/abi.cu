@@ -144,6 +144,15 @@ int rlcf_gemm_f16(const void* A, int lda, const void* B, int ldb, int M, int N, 
                   S(stream));
 }
 
+int rlcf_gemm_f16_grouped(const void* A, int lda, int64_t a_group_stride, const void* B, int ldb, int64_t b_group_stride,
+                          int groups, int M, int N, int K, int epilogue, float alpha, const float* bias,
+                          int64_t bias_group_stride, const float* resid, const void* aux_in, void* aux_out, void* out,
+                          int ldo, int64_t out_group_stride, void* stream) {
+  if (A == nullptr || B == nullptr || out == nullptr) return set_error(RLCF_ERR_ARG, "gemm: null pointer");
+  return gemm_f16_grouped(CH(A), lda, a_group_stride, CH(B), ldb, b_group_stride, groups, M, N, K, epilogue, alpha, bias,
+                          bias_group_stride, resid, CH(aux_in), H(aux_out), out, ldo, out_group_stride, S(stream));
+}
+
 int rlcf_im2col_f16(const float* images, const int32_t* view_idx, int n_views, int C, int H_, int W, int patch,
                     int k_pad, void* out, void* stream) {
   if (images == nullptr || out == nullptr) return set_error(RLCF_ERR_ARG, "im2col: null pointer");

@@ -42,7 +42,10 @@ struct GemmCfg {
 };
 
 struct GemmArgs {
-  int M, N, K;
+  int M, N, K;           // per group
+  int G;                 // independent problems (groups); group g uses A/B/out/bias advanced by g group strides
+  long long out_gs;      // elements between consecutive groups of out / resid / aux
+  long long bias_gs;     // elements between consecutive groups of bias
   int epi;
   const float* bias;     // [N] or null
   const float* resid;    // EPI_RESID_F32: [M, ldo] fp32 (may alias out)
@@ -82,7 +85,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int tile_m = kBM * kCtaGroup * kMc;     // rows per cluster tile
   const int m_tiles = (p.M + tile_m - 1) / tile_m;
   const int n_tiles = (p.N + kBN - 1) / kBN;
-  const int num_tiles = m_tiles * n_tiles;
+  const int tiles_per_group = m_tiles * n_tiles;
+  const int num_tiles = p.G * tiles_per_group;
   const int num_kb = (p.K + kBK - 1) / kBK;
   const int worker = blockIdx.x / (kCtaGroup * kMc);
   const int num_workers = gridDim.x / (kCtaGroup * kMc);
@@ -116,7 +120,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // In a CTA pair every load signals the leader's barrier (same smem offset, peer bit cleared).
       const uint32_t peer_mask = 0xFEFFFFFFu;
       for (int t = worker; t < num_tiles; t += num_workers) {
-        const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+        const int g = t / tiles_per_group, tg = t - g * tiles_per_group;
+        const int m_blk = tg / n_tiles, n_blk = tg % n_tiles;
         const int m0 = m_blk * tile_m + static_cast<int>(pair) * kBM * kCtaGroup + static_cast<int>(cta_rank) * kBM;
         const int n0 = n_blk * kBN + static_cast<int>(cta_rank) * Cfg::kBRows;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -125,17 +130,17 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           uint8_t* sb = sa + Cfg::kABytes;
           if constexpr (kCtaGroup == 1) {
             mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBK, m0);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBK, n0);
+            tma_load_3d(sa, &tmA, &full_bar[stage], kb * kBK, m0, g);
+            tma_load_3d(sb, &tmB, &full_bar[stage], kb * kBK, n0, g);
           } else {
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
             const uint32_t bar = smem_u32(&full_bar[stage]) & peer_mask;
-            tma_load_2d_cg2(sa, &tmA, bar, kb * kBK, m0);
+            tma_load_3d_cg2(sa, &tmA, bar, kb * kBK, m0, g);
             if constexpr (kMc == 1) {
-              tma_load_2d_cg2(sb, &tmB, bar, kb * kBK, n0);
+              tma_load_3d_cg2(sb, &tmB, bar, kb * kBK, n0, g);
             } else if (pair == 0) {
               // this CTA's half of the B tile goes to the CTAs of the same in-pair rank in both pairs
-              tma_load_2d_cg2_mc(sb, &tmB, bar, kb * kBK, n0, static_cast<uint16_t>(0b0101u << cta_rank));
+              tma_load_3d_cg2_mc(sb, &tmB, bar, kb * kBK, n0, g, static_cast<uint16_t>(0b0101u << cta_rank));
             }
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -189,7 +194,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int tj = lane & 7;   // float4 column chunk (transposed phase)
     int it = 0;
     for (int t = worker; t < num_tiles; t += num_workers, ++it) {
-      const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+      const int g = t / tiles_per_group, tg = t - g * tiles_per_group;
+      const int m_blk = tg / n_tiles, n_blk = tg % n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int row0 = m_blk * tile_m + static_cast<int>(pair) * kBM * kCtaGroup + static_cast<int>(cta_rank) * kBM + ew * 32;
@@ -200,7 +206,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // shared memory per CTA there is no L1 left, so per-chunk bias loads would each pay an L2 round trip.
       float4 breg = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.bias != nullptr && col_base + 4 * lane < p.N)
-        breg = __ldg(reinterpret_cast<const float4*>(p.bias + col_base) + lane);
+        breg = __ldg(reinterpret_cast<const float4*>(p.bias + g * p.bias_gs + col_base) + lane);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       if (n_chunks == 0) {  // this warp's column half lies entirely beyond N: nothing to read, release at once
@@ -212,7 +218,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
       // per-lane global offsets of the coalesced phase: row (row0 + tr + 4 i), columns col_base + 32 c + 4 tj .. +3
-      const size_t goff0 = static_cast<size_t>(row0 + tr) * p.ldo + col_base + tj * 4;
+      const size_t goff0 = static_cast<size_t>(g * p.out_gs) + static_cast<size_t>(row0 + tr) * p.ldo + col_base + tj * 4;
       const size_t gstep = static_cast<size_t>(4) * p.ldo;
       const int rows_left = p.M - (row0 + tr);  // row i of this lane is valid iff 4 i < rows_left
 #pragma unroll 1
@@ -302,16 +308,21 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-static int make_tmap_2d_f16(CUtensorMap* map, const void* base, int rows, int cols, int ld_elems, int box_rows) {
+// Rank-3 map (k, row, group): rows beyond `rows` inside a group read as zeros, so tiles never cross a group boundary.
+static int make_tmap_f16(CUtensorMap* map, const void* base, int rows, int cols, int ld_elems, int groups,
+                         long long gs_elems, int box_rows) {
   static PFN_encodeTiled encode = get_encode_tiled();
   if (encode == nullptr) return set_error(RLCF_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not found");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld_elems % 8) != 0)
     return set_error(RLCF_ERR_ARG, "gemm operand must be 16-byte aligned with a leading dimension multiple of 8");
-  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  if (groups == 1) gs_elems = static_cast<long long>(rows) * ld_elems;
+  if (gs_elems <= 0 || (gs_elems % 8) != 0)
+    return set_error(RLCF_ERR_ARG, "gemm group stride must be a positive multiple of 8 elements");
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(groups)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld_elems) * 2, static_cast<cuuint64_t>(gs_elems) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(RLCF_ERR_DRIVER, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
@@ -351,7 +362,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
     configured = true;
   }
   const int tile_m = kBM * kClusterCtas;
-  const int tiles = ((args.M + tile_m - 1) / tile_m) * ((args.N + kBN - 1) / kBN);
+  const int tiles = args.G * ((args.M + tile_m - 1) / tile_m) * ((args.N + kBN - 1) / kBN);
   int workers = tiles < max_clusters ? tiles : max_clusters;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(workers * kClusterCtas);
@@ -374,7 +385,19 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
 int gemm_f16(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, int epi, float alpha,
              const float* bias, const float* resid, const __half* aux_in, __half* aux_out, void* out, int ldo,
              cudaStream_t stream) {
+  return gemm_f16_grouped(A, lda, 0, B, ldb, 0, 1, M, N, K, epi, alpha, bias, 0, resid, aux_in, aux_out, out, ldo, 0,
+                          stream);
+}
+
+int gemm_f16_grouped(const __half* A, int lda, long long a_gs, const __half* B, int ldb, long long b_gs, int G, int M,
+                     int N, int K, int epi, float alpha, const float* bias, long long bias_gs, const float* resid,
+                     const __half* aux_in, __half* aux_out, void* out, int ldo, long long out_gs,
+                     cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(RLCF_ERR_ARG, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  if (G <= 0) return set_error(RLCF_ERR_ARG, "gemm: G=%d groups", G);
+  if (G > 1 && (out_gs % 8 != 0 || bias_gs % 4 != 0 || out_gs < 0 || bias_gs < 0))
+    return set_error(RLCF_ERR_ARG, "gemm: group strides of out (%lld) / bias (%lld) must be multiples of 8 / 4", out_gs,
+                     bias_gs);
   if (N % 32 != 0) return set_error(RLCF_ERR_ARG, "gemm: N=%d must be a multiple of 32", N);
   if (K % 8 != 0) return set_error(RLCF_ERR_ARG, "gemm: K=%d must be a multiple of 8", K);
   if (ldo % 8 != 0) return set_error(RLCF_ERR_ARG, "gemm: ldo=%d must be a multiple of 8", ldo);
@@ -383,10 +406,11 @@ int gemm_f16(const __half* A, int lda, const __half* B, int ldb, int M, int N, i
   if (epi == EPI_GELU_BWD_F16 && aux_in == nullptr) return set_error(RLCF_ERR_ARG, "gemm: gelu-bwd needs aux_in");
   const int cg = gemm_cta_group();
   CUtensorMap ta, tb;
-  if (int rc = make_tmap_2d_f16(&ta, A, M, K, lda, kBM)) return rc;
-  if (int rc = make_tmap_2d_f16(&tb, B, N, K, ldb, kBN / cg)) return rc;
+  if (int rc = make_tmap_f16(&ta, A, M, K, lda, G, a_gs, kBM)) return rc;
+  if (int rc = make_tmap_f16(&tb, B, N, K, ldb, G, b_gs, kBN / cg)) return rc;
   static const int debug_nostore = getenv("RLCF_GEMM_DEBUG_NOSTORE") != nullptr;
-  GemmArgs args{M, N, K, epi, bias, resid, aux_in, aux_out, out, ldo, alpha, debug_nostore};
+  GemmArgs args{M, N, K, G, G > 1 ? out_gs : 0, G > 1 ? bias_gs : 0, epi, bias, resid, aux_in, aux_out, out, ldo,
+                alpha, debug_nostore};
   // multicast pays once there are at least two 256-row tiles per cluster slot; tiny problems keep 2-CTA clusters
   const bool mc = cg == 2 && gemm_multicast() && M > 2 * kBM * 2;
   switch (epi) {

@@ -35,6 +35,12 @@ PFN_encodeTiled get_encode_tiled();
 int gemm_f16(const __half* A, int lda, const __half* B, int ldb, int M, int N, int K, int epi, float alpha,
              const float* bias, const float* resid, const __half* aux_in, __half* aux_out, void* out, int ldo,
              cudaStream_t stream);
+// G independent problems of the same shape in one launch: group g reads A + g*a_gs, B + g*b_gs, bias + g*bias_gs and
+// writes out/resid/aux + g*out_gs (strides in elements).
+int gemm_f16_grouped(const __half* A, int lda, long long a_gs, const __half* B, int ldb, long long b_gs, int G, int M,
+                     int N, int K, int epi, float alpha, const float* bias, long long bias_gs, const float* resid,
+                     const __half* aux_in, __half* aux_out, void* out, int ldo, long long out_gs,
+                     cudaStream_t stream);
 
 // Checks the launch of the kernel that was just enqueued.
 #define RLCF_CHECK_LAUNCH(name)                                                                 \

@@ -56,6 +56,36 @@ def gemm(a, b, out, epilogue=EPI_F16, bias=None, resid=None, aux_in=None, aux_ou
     return out
 
 
+def gemm_grouped(a, b, out, epilogue=EPI_F16, bias=None, resid=None, aux_in=None, aux_out=None, alpha=1.0):
+    """G independent GEMMs in one launch: out[g] = epilogue(alpha * a[g] @ b[g]^T).  a [G,M,K], b [G,N,K] fp16 and
+    out [G,M,N] are 3-D views with unit inner stride (any row / group strides that are multiples of 8 elements);
+    bias [G,N] fp32; resid / aux share out's layout."""
+    for t, nm in ((a, "a"), (b, "b"), (out, "out")):
+        if not t.is_cuda or t.dim() != 3 or t.stride(2) != 1:
+            raise _lib.RlcfError(f"gemm_grouped: {nm} must be a 3-D CUDA tensor with unit inner stride")
+    if a.dtype != torch.float16 or b.dtype != torch.float16:
+        raise _lib.RlcfError("gemm_grouped: a and b must be fp16")
+    G, m, k = a.shape
+    n = b.shape[1]
+    if b.shape[0] != G or b.shape[2] != k or tuple(out.shape) != (G, m, n):
+        raise _lib.RlcfError(f"gemm_grouped: shapes {tuple(a.shape)} x {tuple(b.shape)} -> {tuple(out.shape)}")
+    want = torch.float32 if epilogue in (EPI_RESID_F32, EPI_F32) else torch.float16
+    if out.dtype != want:
+        raise _lib.RlcfError(f"gemm_grouped: out must be {want}")
+    bias_gs = 0
+    if bias is not None:
+        if bias.dtype != torch.float32 or bias.dim() != 2 or bias.shape != (G, n) or bias.stride(1) != 1:
+            raise _lib.RlcfError("gemm_grouped: bias must be fp32 [G, N]")
+        bias_gs = bias.stride(0)
+    for t, dt, nm in ((resid, torch.float32, "resid"), (aux_in, torch.float16, "aux_in"), (aux_out, torch.float16, "aux_out")):
+        if t is not None and (t.dtype != dt or t.dim() != 3 or t.stride() != out.stride()):
+            raise _lib.RlcfError(f"gemm_grouped: {nm} must be {dt} with out's layout")
+    call("rlcf_gemm_f16_grouped", ptr(a), a.stride(1), a.stride(0), ptr(b), b.stride(1), b.stride(0), G, m, n, k,
+         epilogue, float(alpha), ptr(bias), bias_gs, ptr(resid), ptr(aux_in), ptr(aux_out), ptr(out), out.stride(1),
+         out.stride(0), stream())
+    return out
+
+
 def im2col(images, view_idx, n_views, patch, k_pad, out):
     _chk(images, torch.float32, "images"); _chk(view_idx, torch.int32, "view_idx"); _chk(out, torch.float16, "out")
     _, c, h, w = images.shape

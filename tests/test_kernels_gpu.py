@@ -89,6 +89,44 @@ def test_gemm_epilogues(cg):
     assert _rel(big[:M], acc) < 2e-5 and big[M:].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("cg", _CGS)
+@pytest.mark.parametrize("G,M,N,K", [(5, 197, 768, 768), (3, 17, 96, 128), (16, 300, 256, 64), (2, 640, 512, 200)])
+def test_gemm_grouped(cg, G, M, N, K):
+    """Per-group operands, bias and outputs; rows of one group never leak into the next (M is not a tile multiple)."""
+    torch.manual_seed(G * M + N)
+    _lib.set_gemm_cta_group(cg)
+    m_pad = (M + 7) // 8 * 8
+    a_buf = (torch.randn(G, m_pad, K, device=_dev()) * 0.5).half()       # padded rows between groups
+    b_buf = (torch.randn(G, N + 8, K, device=_dev()) * 0.1).half()
+    bias = torch.randn(G, N, device=_dev())
+    a, b = a_buf[:, :M], b_buf[:, :N]
+    ref = torch.einsum("gmk,gnk->gmn", a.float(), b.float())
+    out_buf = torch.full((G, m_pad, N), 7.0, device=_dev())
+    out = out_buf[:, :M]
+    ops.gemm_grouped(a, b, out, epilogue=ops.EPI_F32, bias=bias)
+    assert _rel(out, ref + bias[:, None, :]) < 2e-5
+    assert (out_buf[:, M:] == 7.0).all()                                  # padding rows untouched
+    # residual epilogue in place + fp16 epilogue with pre-activation save
+    x = torch.randn(G, M, N, device=_dev())
+    x0 = x.clone()
+    ops.gemm_grouped(a, b, x, epilogue=ops.EPI_RESID_F32, bias=bias, resid=x)
+    assert _rel(x, ref + bias[:, None, :] + x0) < 1e-5
+    o16 = torch.empty(G, M, N, device=_dev(), dtype=torch.float16)
+    pre = torch.empty_like(o16)
+    ops.gemm_grouped(a, b, o16, epilogue=ops.EPI_GELU_F16, bias=bias, aux_out=pre)
+    assert _rel(pre, ref + bias[:, None, :]) < 1e-3
+    assert _rel(o16, quick_gelu(ref + bias[:, None, :])) < 1e-3
+    # K-sliced operands (the wgrad layout: one [n, G * k] buffer, group g owns columns g*k .. (g+1)*k)
+    if K % 8 == 0:
+        ta = (torch.randn(N, G * K, device=_dev()) * 0.3).half()
+        tb = (torch.randn(M if M % 32 == 0 else 64, G * K, device=_dev()) * 0.3).half()
+        a3 = ta.view(N, G, K).permute(1, 0, 2)
+        b3 = tb.view(tb.shape[0], G, K).permute(1, 0, 2)
+        w = torch.empty(G, N, tb.shape[0], device=_dev())
+        ops.gemm_grouped(a3, b3, w, epilogue=ops.EPI_F32)
+        assert _rel(w, torch.einsum("gnk,gmk->gnm", a3.float(), b3.float())) < 2e-5
+
+
 def test_gemm_rejects_bad_shapes():
     a = torch.zeros(8, 64, device=_dev(), dtype=torch.float16)
     b = torch.zeros(24, 64, device=_dev(), dtype=torch.float16)
