@@ -136,7 +136,8 @@ def check_params(p, p_ref, grads, lr, steps, tag):
 
 
 def golden_cases():
-    return [f[:-4] for f in sorted(os.listdir(GOLDEN)) if f.endswith(".npz") and "prompt" not in f]
+    return [f[:-4] for f in sorted(os.listdir(GOLDEN)) if f.endswith(".npz") and "prompt" not in f
+            and not f.startswith("ret_")]   # ret_*: retrieval fixtures (tests/test_retrieval_gpu.py)
 
 
 @pytest.mark.parametrize("name", golden_cases())
