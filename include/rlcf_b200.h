@@ -209,6 +209,64 @@ int rlcf_cast_f16(const float* in, int64_t rows, int64_t cols, int64_t ld_in, vo
 /* out16[c, r] = in32[r, c]  (W^T copies used as the B operand of dgrad GEMMs). */
 int rlcf_transpose_cast_f16(const float* in, int rows, int cols, void* out, void* stream);
 
+/* ---- per-sample weights (every test sample / query owns ALL parameters of the tuned tower) --------------------
+ * Retrieval TTA tunes the whole image (or text) encoder for 8 steps per query (retrieval/clip_ret_policy.py:76-137,
+ * custom_models.py:144-152) and full-encoder classification tuning does the same per image (custom_clip.py:477-479),
+ * so after the first AdamW step the class/positional embeddings and the output projection differ per sample too.
+ * These variants take the per-set stride of those tensors (in floats; 0 = shared). */
+int rlcf_embed_lnpre_sets(const float* patch_out, const float* cls, const float* pos, int64_t embed_stride,
+                          const float* gamma, const float* beta, int64_t param_stride, int rows_per_set, int n_views,
+                          int L, int d, float eps, float* x_pre, float* x, void* stream);
+int rlcf_head_fwd_sets(const float* x, const int32_t* row_idx, int64_t row_stride, const float* gamma,
+                       const float* beta, int64_t param_stride, int seqs_per_set, const float* proj,
+                       int64_t proj_stride, const float* class_feat, float logit_scale, int n, int d, int E, int C,
+                       float eps, float* feat, float* inv_norm, float* logits, void* stream);
+int rlcf_head_bwd_sets(const float* dlogits, int64_t dl_set_stride, int64_t dl_seq_stride, int64_t dl_k_stride,
+                       const float* x, const int32_t* row_idx, int64_t row_stride, const float* gamma,
+                       int64_t param_stride, const float* proj, int64_t proj_stride, const float* other_feat,
+                       int64_t other_set_stride, float logit_scale, const float* feat, const float* inv_norm,
+                       int n_sets, int seqs_per_set, int d, int E, int K, float eps, float* dres, float* partials,
+                       int n_slots, int64_t p_total, int64_t p_off, const float* beta, float* y_out, float* df_out,
+                       void* stream);
+/* n_sets transposing casts in one launch: out16[g*out_stride + c*rows + r] = in32[g*in_stride + r*cols + c]. */
+int rlcf_transpose_cast_f16_sets(const float* in, int rows, int cols, int n_sets, int64_t in_stride, void* out,
+                                 int64_t out_stride, void* stream);
+
+/* ---- retrieval TTA (retrieval/clip_ret_policy.py:76-137) ------------------------------------------------------
+ * One query per row of `logits` [n_query, C] (row stride ld) against a gallery of C candidates.  Per query:
+ * top-K candidates (torch.topk, clip_ret_policy.py:90/123), CLIPScore = max(0, w*<reward_gallery[idx],
+ * reward_query>) (retrieval/clip_reward.py:143-168), rewards_post_process over the K samples, loss =
+ * mean_k(r_k * CE(logits, idx_k)) (clip_ret_policy.py:97-98) and dlogits [n_query, C] = loss_scale * dL/dlogits.
+ * K <= 32.  topk_idx [n_query,K] int32, scores / rewards [n_query,K], loss [n_query] may be NULL. */
+int rlcf_retrieval_loss(const float* logits, int64_t ld, const float* reward_query, const float* reward_gallery,
+                        int n_query, int K, int C, int Er, float clipscore_weight, int reward_process, int amplify,
+                        float loss_scale, float* dlogits, int32_t* topk_idx, float* scores, float* rewards,
+                        float* loss, void* stream);
+/* partial[q, chunk, :] = sum over the chunk's candidates c of dlogits[q,c] * gallery[c,:]  (gallery [C,E] fp32).
+ * The chunks are summed, in order, by rlcf_head_bwd_sets called with K = n_chunks and other_feat = partial, which
+ * makes d(query feature) = dlogits @ gallery deterministic for any gallery size. */
+int rlcf_dfeat_partial(const float* dlogits, const float* gallery, int n_query, int C, int E, int n_chunks,
+                       float* partial, void* stream);
+/* out[q*out_stride] = scale * sum_c a[q,c]*b[q,c]: the gradient of logit_scale (tuned in text->image retrieval,
+ * custom_models.py:144-152) is sum_c dlogits[c]*logits[c]. */
+int rlcf_rowdot(const float* a, const float* b, int n_rows, int C, float scale, float* out, int64_t out_stride,
+                void* stream);
+
+/* ---- text->image retrieval: the text tower is tuned, including the caption's token-embedding rows, the positional
+ * embedding and logit_scale (custom_models.py:144-152; tune_text, clip_ret_policy.py:106-137) ----
+ * x[g*n + i] = a[g*a_stride + i] + b[g*b_stride + i]: per-query token rows + positional embedding (CLIP.encode_text,
+ * open_clip model: x = token_embedding(text) + positional_embedding). */
+int rlcf_add_rows(const float* a, int64_t a_stride, const float* b, int64_t b_stride, int n_sets, int64_t n, float* x,
+                  void* stream);
+/* out[q,c] = in[q,c] * exp(ls[q*ls_stride]): logits = logit_scale.exp() * cos with a per-query, trainable
+ * logit_scale (forward), and d cos = exp(ls) * dlogits (backward). in == out allowed. */
+int rlcf_scale_rows_exp(const float* in, const float* ls, int64_t ls_stride, int n_rows, int C, float* out,
+                        void* stream);
+/* Gradient of the per-query embedding rows from dx [n_sets*L, d]: g_pos[g][t] = dx[g,t]; g_tok[g][t] = sum of dx over
+ * the positions of query g that hold the same token id as position t (weight tying of nn.Embedding rows). */
+int rlcf_tied_rows_grad(const float* dx, const int64_t* tokens, int n_sets, int L, int d, float* g_tok, float* g_pos,
+                        int64_t out_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,18 @@ _PROTOS = {
     "rlcf_reset_params": [_vp, _vp, _vp, _vp, _i, _i64, _vp],
     "rlcf_cast_f16": [_vp, _i64, _i64, _i64, _vp, _i64, _vp],
     "rlcf_transpose_cast_f16": [_vp, _i, _i, _vp, _vp],
+    "rlcf_embed_lnpre_sets": [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _f, _vp, _vp, _vp],
+    "rlcf_head_fwd_sets": [_vp, _vp, _i64, _vp, _vp, _i64, _i, _vp, _i64, _vp, _f, _i, _i, _i, _i, _f, _vp, _vp, _vp,
+                           _vp],
+    "rlcf_head_bwd_sets": [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _f, _vp, _vp, _i, _i,
+                           _i, _i, _i, _f, _vp, _vp, _i, _i64, _i64, _vp, _vp, _vp, _vp],
+    "rlcf_transpose_cast_f16_sets": [_vp, _i, _i, _i, _i64, _vp, _i64, _vp],
+    "rlcf_retrieval_loss": [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp],
+    "rlcf_dfeat_partial": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "rlcf_rowdot": [_vp, _vp, _i, _i, _f, _vp, _i64, _vp],
+    "rlcf_add_rows": [_vp, _i64, _vp, _i64, _i, _i64, _vp, _vp],
+    "rlcf_scale_rows_exp": [_vp, _vp, _i64, _i, _i, _vp, _vp],
+    "rlcf_tied_rows_grad": [_vp, _vp, _i, _i, _i, _vp, _vp, _i64, _vp],
 }
 _RESTYPES = {"rlcf_last_error": C.c_char_p, "rlcf_launch_count": C.c_uint64}
 

@@ -76,7 +76,7 @@ PFN_encodeTiled get_encode_tiled() {
 // implemented in kernels.cu / attention.cu
 int im2col_f16(const float*, const int32_t*, int, int, int, int, int, int, __half*, cudaStream_t);
 int embed_lnpre(const float*, const float*, const float*, const float*, const float*, long long, int, int, int, int,
-                float, float*, float*, cudaStream_t);
+                float, float*, float*, long long, cudaStream_t);
 int embed_text(const long long*, const float*, const float*, int, int, int, float*, cudaStream_t);
 int layernorm_fwd(const float*, long long, const float*, const float*, long long, int, int, int, float, __half*,
                   float*, cudaStream_t);
@@ -86,7 +86,7 @@ int attention_fwd(const __half*, int, int, int, int, __half*, float*, cudaStream
 int attention_bwd(const __half*, const __half*, const __half*, const float*, int, int, int, int, __half*,
                   cudaStream_t);
 int head_fwd(const float*, const int32_t*, long long, const float*, const float*, long long, int, const float*,
-             const float*, float, int, int, int, int, float, float*, float*, float*, cudaStream_t);
+             const float*, float, int, int, int, int, float, float*, float*, float*, long long, cudaStream_t);
 int entropy_select(const float*, int, int, int, int, int32_t*, int32_t*, float*, cudaStream_t);
 int reward_loss(const float*, const int32_t*, const float*, const float*, int, int, int, int, int, float, int, int,
                 int, float, float*, int32_t*, float*, float*, float*, cudaStream_t);
@@ -94,7 +94,7 @@ int avg_entropy_loss(const float*, const int32_t*, int, int, int, float, float*,
 int head_bwd(const float*, const float*, const int32_t*, long long, const float*, long long, const float*,
              const float*, float, const float*, const float*, int, int, int, int, int, float, float*, float*, int,
              long long, long long, long long, long long, long long, long long, const float*, float*, float*,
-             cudaStream_t);
+             long long, cudaStream_t);
 int transpose_blocks(const void*, int, int, int, int, int, int, long long, __half*, long long, cudaStream_t);
 int colsum_f16(const __half*, int, int, int, float*, long long, cudaStream_t);
 int seq_sum(const float*, int, int, int, int, float*, long long, cudaStream_t);
@@ -107,7 +107,14 @@ int adamw_step(float*, float*, float*, const float*, int, int, long long, float,
                float, float*, const float*, long long, int, cudaStream_t);
 int reset_params(const float*, float*, float*, float*, int, long long, cudaStream_t);
 int cast_f16(const float*, long long, long long, long long, __half*, long long, cudaStream_t);
-int transpose_cast_f16(const float*, int, int, __half*, cudaStream_t);
+int transpose_cast_f16(const float*, int, int, __half*, int, long long, long long, cudaStream_t);
+int retrieval_loss(const float*, long long, const float*, const float*, int, int, int, int, float, int, int, float,
+                   float*, int32_t*, float*, float*, float*, cudaStream_t);
+int dfeat_partial(const float*, const float*, int, int, int, int, float*, cudaStream_t);
+int rowdot(const float*, const float*, int, int, float, float*, long long, cudaStream_t);
+int add_rows(const float*, long long, const float*, long long, int, long long, float*, cudaStream_t);
+int scale_rows_exp(const float*, const float*, long long, int, int, float*, cudaStream_t);
+int tied_rows_grad(const float*, const long long*, int, int, int, float*, float*, long long, cudaStream_t);
 
 }  // namespace rlcf
 
@@ -163,8 +170,17 @@ int rlcf_embed_lnpre(const float* patch_out, const float* cls, const float* pos,
                      const float* beta, int64_t param_stride, int rows_per_set, int n_views, int L, int d, float eps,
                      float* x_pre, float* x, void* stream) {
   if (!patch_out || !cls || !pos || !gamma || !beta || !x) return set_error(RLCF_ERR_ARG, "embed_lnpre: null pointer");
-  return embed_lnpre(patch_out, cls, pos, gamma, beta, param_stride, rows_per_set, n_views, L, d, eps, x_pre, x,
+  return embed_lnpre(patch_out, cls, pos, gamma, beta, param_stride, rows_per_set, n_views, L, d, eps, x_pre, x, 0,
                      S(stream));
+}
+
+int rlcf_embed_lnpre_sets(const float* patch_out, const float* cls, const float* pos, int64_t embed_stride,
+                          const float* gamma, const float* beta, int64_t param_stride, int rows_per_set, int n_views,
+                          int L, int d, float eps, float* x_pre, float* x, void* stream) {
+  if (!patch_out || !cls || !pos || !gamma || !beta || !x)
+    return set_error(RLCF_ERR_ARG, "embed_lnpre_sets: null pointer");
+  return embed_lnpre(patch_out, cls, pos, gamma, beta, param_stride, rows_per_set, n_views, L, d, eps, x_pre, x,
+                     embed_stride, S(stream));
 }
 
 int rlcf_embed_text(const int64_t* tokens, const float* tok_emb, const float* pos, int n_seq, int L, int d, float* x,
@@ -205,7 +221,16 @@ int rlcf_head_fwd(const float* x, const int32_t* row_idx, int64_t row_stride, co
                   int n, int d, int E, int C, float eps, float* feat, float* inv_norm, float* logits, void* stream) {
   if (!x || !gamma || !beta || !proj) return set_error(RLCF_ERR_ARG, "head_fwd: null pointer");
   return head_fwd(x, row_idx, row_stride, gamma, beta, param_stride, seqs_per_set, proj, class_feat, logit_scale, n, d,
-                  E, C, eps, feat, inv_norm, logits, S(stream));
+                  E, C, eps, feat, inv_norm, logits, 0, S(stream));
+}
+
+int rlcf_head_fwd_sets(const float* x, const int32_t* row_idx, int64_t row_stride, const float* gamma,
+                       const float* beta, int64_t param_stride, int seqs_per_set, const float* proj,
+                       int64_t proj_stride, const float* class_feat, float logit_scale, int n, int d, int E, int C,
+                       float eps, float* feat, float* inv_norm, float* logits, void* stream) {
+  if (!x || !gamma || !beta || !proj) return set_error(RLCF_ERR_ARG, "head_fwd_sets: null pointer");
+  return head_fwd(x, row_idx, row_stride, gamma, beta, param_stride, seqs_per_set, proj, class_feat, logit_scale, n, d,
+                  E, C, eps, feat, inv_norm, logits, proj_stride, S(stream));
 }
 
 int rlcf_entropy_select(const float* logits, int n_img, int V, int C, int S_, int32_t* sel, int32_t* sel_global,
@@ -237,7 +262,7 @@ int rlcf_head_bwd(const float* dlogits, const float* x, const int32_t* row_idx, 
     return set_error(RLCF_ERR_ARG, "head_bwd: null pointer");
   return head_bwd(dlogits, x, row_idx, row_stride, gamma, param_stride, proj, class_feat, logit_scale, feat, inv_norm,
                   n_img, S_, d, E, C, eps, dres, partials, n_slots, p_total, p_off, static_cast<long long>(S_) * C, C, 1,
-                  0, nullptr, nullptr, nullptr, S(stream));
+                  0, nullptr, nullptr, nullptr, 0, S(stream));
 }
 
 int rlcf_head_bwd_ex(const float* dlogits, int64_t dl_set_stride, int64_t dl_seq_stride, int64_t dl_k_stride,
@@ -250,7 +275,21 @@ int rlcf_head_bwd_ex(const float* dlogits, int64_t dl_set_stride, int64_t dl_seq
     return set_error(RLCF_ERR_ARG, "head_bwd_ex: null pointer");
   return head_bwd(dlogits, x, row_idx, row_stride, gamma, param_stride, proj, other_feat, logit_scale, feat, inv_norm,
                   n_sets, seqs_per_set, d, E, K, eps, dres, partials, n_slots, p_total, p_off, dl_set_stride,
-                  dl_seq_stride, dl_k_stride, other_set_stride, beta, y_out, df_out, S(stream));
+                  dl_seq_stride, dl_k_stride, other_set_stride, beta, y_out, df_out, 0, S(stream));
+}
+
+int rlcf_head_bwd_sets(const float* dlogits, int64_t dl_set_stride, int64_t dl_seq_stride, int64_t dl_k_stride,
+                       const float* x, const int32_t* row_idx, int64_t row_stride, const float* gamma,
+                       int64_t param_stride, const float* proj, int64_t proj_stride, const float* other_feat,
+                       int64_t other_set_stride, float logit_scale, const float* feat, const float* inv_norm,
+                       int n_sets, int seqs_per_set, int d, int E, int K, float eps, float* dres, float* partials,
+                       int n_slots, int64_t p_total, int64_t p_off, const float* beta, float* y_out, float* df_out,
+                       void* stream) {
+  if (!dlogits || !x || !gamma || !proj || !other_feat || !feat || !inv_norm || !dres)
+    return set_error(RLCF_ERR_ARG, "head_bwd_sets: null pointer");
+  return head_bwd(dlogits, x, row_idx, row_stride, gamma, param_stride, proj, other_feat, logit_scale, feat, inv_norm,
+                  n_sets, seqs_per_set, d, E, K, eps, dres, partials, n_slots, p_total, p_off, dl_set_stride,
+                  dl_seq_stride, dl_k_stride, other_set_stride, beta, y_out, df_out, proj_stride, S(stream));
 }
 
 int rlcf_embed_prompts(const int64_t* tokens, const float* tok_emb, const float* pos, const float* ctx,
@@ -326,7 +365,54 @@ int rlcf_cast_f16(const float* in, int64_t rows, int64_t cols, int64_t ld_in, vo
 
 int rlcf_transpose_cast_f16(const float* in, int rows, int cols, void* out, void* stream) {
   if (!in || !out) return set_error(RLCF_ERR_ARG, "transpose_cast_f16: null pointer");
-  return transpose_cast_f16(in, rows, cols, H(out), S(stream));
+  return transpose_cast_f16(in, rows, cols, H(out), 1, 0, 0, S(stream));
+}
+
+int rlcf_transpose_cast_f16_sets(const float* in, int rows, int cols, int n_sets, int64_t in_stride, void* out,
+                                 int64_t out_stride, void* stream) {
+  if (!in || !out) return set_error(RLCF_ERR_ARG, "transpose_cast_f16_sets: null pointer");
+  return transpose_cast_f16(in, rows, cols, H(out), n_sets, in_stride, out_stride, S(stream));
+}
+
+int rlcf_retrieval_loss(const float* logits, int64_t ld, const float* reward_query, const float* reward_gallery,
+                        int n_query, int K, int C, int Er, float clipscore_weight, int reward_process, int amplify,
+                        float loss_scale, float* dlogits, int32_t* topk_idx, float* scores, float* rewards,
+                        float* loss, void* stream) {
+  if (!logits || !reward_query || !reward_gallery || !dlogits)
+    return set_error(RLCF_ERR_ARG, "retrieval_loss: null pointer");
+  return retrieval_loss(logits, ld, reward_query, reward_gallery, n_query, K, C, Er, clipscore_weight, reward_process,
+                        amplify, loss_scale, dlogits, topk_idx, scores, rewards, loss, S(stream));
+}
+
+int rlcf_dfeat_partial(const float* dlogits, const float* gallery, int n_query, int C, int E, int n_chunks,
+                       float* partial, void* stream) {
+  if (!dlogits || !gallery || !partial) return set_error(RLCF_ERR_ARG, "dfeat_partial: null pointer");
+  return dfeat_partial(dlogits, gallery, n_query, C, E, n_chunks, partial, S(stream));
+}
+
+int rlcf_rowdot(const float* a, const float* b, int n_rows, int C, float scale, float* out, int64_t out_stride,
+                void* stream) {
+  if (!a || !b || !out) return set_error(RLCF_ERR_ARG, "rowdot: null pointer");
+  return rowdot(a, b, n_rows, C, scale, out, out_stride, S(stream));
+}
+
+int rlcf_add_rows(const float* a, int64_t a_stride, const float* b, int64_t b_stride, int n_sets, int64_t n, float* x,
+                  void* stream) {
+  if (!a || !b || !x) return set_error(RLCF_ERR_ARG, "add_rows: null pointer");
+  return add_rows(a, a_stride, b, b_stride, n_sets, n, x, S(stream));
+}
+
+int rlcf_scale_rows_exp(const float* in, const float* ls, int64_t ls_stride, int n_rows, int C, float* out,
+                        void* stream) {
+  if (!in || !ls || !out) return set_error(RLCF_ERR_ARG, "scale_rows_exp: null pointer");
+  return scale_rows_exp(in, ls, ls_stride, n_rows, C, out, S(stream));
+}
+
+int rlcf_tied_rows_grad(const float* dx, const int64_t* tokens, int n_sets, int L, int d, float* g_tok, float* g_pos,
+                        int64_t out_stride, void* stream) {
+  if (!dx || !tokens || !g_tok || !g_pos) return set_error(RLCF_ERR_ARG, "tied_rows_grad: null pointer");
+  return tied_rows_grad(dx, reinterpret_cast<const long long*>(tokens), n_sets, L, d, g_tok, g_pos, out_stride,
+                        S(stream));
 }
 
 }  // extern "C"

@@ -167,15 +167,17 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 embed_lnpre_kernel(const float* __restrict__ patch_out, const float* __restrict__ cls, const float* __restrict__ pos,
                    const float* __restrict__ gamma, const float* __restrict__ beta, long long pstride,
-                   int rows_per_set, int M, int L, float eps, float* __restrict__ x_pre, float* __restrict__ x) {
+                   int rows_per_set, int M, int L, float eps, float* __restrict__ x_pre, float* __restrict__ x,
+                   long long embed_stride) {
   constexpr int d = NV * 128;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int v = row / L, t = row % L;
-  const float4* src = t == 0 ? reinterpret_cast<const float4*>(cls)
+  const long long eo = static_cast<long long>(row / rows_per_set) * embed_stride;   // per-set class / positional rows
+  const float4* src = t == 0 ? reinterpret_cast<const float4*>(cls + eo)
                              : reinterpret_cast<const float4*>(patch_out + (static_cast<size_t>(v) * (L - 1) + t - 1) * d);
-  const float4* p4 = reinterpret_cast<const float4*>(pos + static_cast<size_t>(t) * d);
+  const float4* p4 = reinterpret_cast<const float4*>(pos + eo + static_cast<size_t>(t) * d);
   float4 val[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -203,13 +205,15 @@ embed_lnpre_kernel(const float* __restrict__ patch_out, const float* __restrict_
 
 int embed_lnpre(const float* patch_out, const float* cls, const float* pos, const float* gamma, const float* beta,
                 long long pstride, int rows_per_set, int n_views, int L, int d, float eps, float* x_pre, float* x,
-                cudaStream_t stream) {
+                long long embed_stride, cudaStream_t stream) {
   if (int rc = check_width(d, "embed_lnpre")) return rc;
+  if (embed_stride % 4) return set_error(RLCF_ERR_ARG, "embed_lnpre: embed_stride must be a multiple of 4 floats");
   if (n_views <= 0 || L < 2 || rows_per_set <= 0) return set_error(RLCF_ERR_ARG, "embed_lnpre: bad shape");
   const int M = n_views * L;
   const int blocks = (M + 7) / 8;
   RLCF_DISPATCH_NV(d, (embed_lnpre_kernel<NV><<<blocks, 256, 0, stream>>>(patch_out, cls, pos, gamma, beta, pstride,
-                                                                           rows_per_set, M, L, eps, x_pre, x)));
+                                                                           rows_per_set, M, L, eps, x_pre, x,
+                                                                           embed_stride)));
   RLCF_CHECK_LAUNCH("embed_lnpre");
   return 0;
 }
@@ -372,12 +376,13 @@ head_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_idx
                 const float* __restrict__ gamma, const float* __restrict__ beta, long long pstride, int seqs_per_set,
                 const float* __restrict__ proj, const float* __restrict__ cls_feat, float logit_scale, int n, int d,
                 int E, int C, float eps, float* __restrict__ feat, float* __restrict__ inv_norm,
-                float* __restrict__ logits) {
+                float* __restrict__ logits, long long proj_stride) {
   extern __shared__ float sm[];
   float* yT = sm;            // [d][VPC]
   float* f = sm + d * VPC;   // [VPC][E]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n0 = blockIdx.x * VPC;
+  proj += static_cast<long long>(n0 / seqs_per_set) * proj_stride;   // per-set projection (host: VPC | seqs_per_set)
   const int nv = min(VPC, n - n0);
   // LayerNorm of each sequence's row by one warp (two-pass statistics)
   for (int v = warp; v < VPC; v += kHeadThreads / 32) {
@@ -462,10 +467,14 @@ head_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_idx
 
 int head_fwd(const float* x, const int32_t* row_idx, long long row_stride, const float* gamma, const float* beta,
              long long pstride, int seqs_per_set, const float* proj, const float* cls_feat, float logit_scale, int n,
-             int d, int E, int C, float eps, float* feat, float* inv_norm, float* logits, cudaStream_t stream) {
+             int d, int E, int C, float eps, float* feat, float* inv_norm, float* logits, long long proj_stride,
+             cudaStream_t stream) {
   if (n <= 0 || d <= 0 || E <= 0 || seqs_per_set <= 0) return set_error(RLCF_ERR_ARG, "head_fwd: bad shape");
   if (logits && (cls_feat == nullptr || C <= 0)) return set_error(RLCF_ERR_ARG, "head_fwd: logits need class_feat");
-  const int vpc = n >= 8 * 148 / 2 ? 8 : (n >= 64 ? 4 : 1);
+  if (proj_stride % 4) return set_error(RLCF_ERR_ARG, "head_fwd: proj_stride must be a multiple of 4 floats");
+  int vpc = n >= 8 * 148 / 2 ? 8 : (n >= 64 ? 4 : 1);
+  while (proj_stride != 0 && seqs_per_set % vpc != 0) vpc >>= 1;   // a block must not straddle two projections
+  if (vpc == 2) vpc = 1;
   if (E % 4 != 0 || d % 2 != 0) return set_error(RLCF_ERR_ARG, "head_fwd: E must be a multiple of 4 and d even");
   const size_t smem = static_cast<size_t>(vpc) * (d + 2 * E) * sizeof(float);
   if (smem > 227 * 1024) return set_error(RLCF_ERR_ARG, "head_fwd: width too large");
@@ -480,7 +489,7 @@ int head_fwd(const float* x, const int32_t* row_idx, long long row_stride, const
     }                                                                                                             \
     head_fwd_kernel<V><<<(n + V - 1) / V, kHeadThreads, smem, stream>>>(                                          \
         x, row_idx, row_stride, gamma, beta, pstride, seqs_per_set, proj, cls_feat, logit_scale, n, d, E, C, eps, \
-        feat, inv_norm, logits);                                                                                  \
+        feat, inv_norm, logits, proj_stride);                                                                     \
   }
   if (vpc == 8) RLCF_HEAD_LAUNCH(8) else if (vpc == 4) RLCF_HEAD_LAUNCH(4) else RLCF_HEAD_LAUNCH(1)
 #undef RLCF_HEAD_LAUNCH
@@ -745,7 +754,8 @@ head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ x, 
                 const float* __restrict__ feat, const float* __restrict__ inv_norm, int S, int d, int E, int C,
                 float eps, float* __restrict__ dres, float* __restrict__ partials, int n_slots, long long p_total,
                 long long p_off, long long dl_set, long long dl_s, long long dl_k, long long cls_stride,
-                const float* __restrict__ beta, float* __restrict__ y_out, float* __restrict__ df_out) {
+                const float* __restrict__ beta, float* __restrict__ y_out, float* __restrict__ df_out,
+                long long proj_stride) {
   extern __shared__ float sm[];
   float* df = sm;            // [E]   (first: read with 16-byte loads, E % 4 == 0)
   float* dy = df + E;        // [d]
@@ -756,6 +766,7 @@ head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ x, 
   const float* gam = gamma + img * pstride;
   const int n = img * S + s;
   cls_feat += img * cls_stride;
+  proj += img * proj_stride;
   for (int c = tid; c < C; c += kHeadThreads) dl[c] = dlogits[img * dl_set + s * dl_s + c * dl_k];
   __syncthreads();
   // d fhat = logit_scale * dlogits @ class_feat   (8 independent loads in flight per thread)
@@ -829,7 +840,9 @@ int head_bwd(const float* dlogits, const float* x, const int32_t* row_idx, long 
              long long pstride, const float* proj, const float* cls_feat, float logit_scale, const float* feat,
              const float* inv_norm, int n_img, int S, int d, int E, int C, float eps, float* dres, float* partials,
              int n_slots, long long p_total, long long p_off, long long dl_set, long long dl_s, long long dl_k,
-             long long cls_stride, const float* beta, float* y_out, float* df_out, cudaStream_t stream) {
+             long long cls_stride, const float* beta, float* y_out, float* df_out, long long proj_stride,
+             cudaStream_t stream) {
+  if (proj_stride % 4) return set_error(RLCF_ERR_ARG, "head_bwd: proj_stride must be a multiple of 4 floats");
   if (n_img <= 0 || S <= 0 || d <= 0 || d > 1024 || E <= 0 || E % 4 != 0 || C <= 0)
     return set_error(RLCF_ERR_ARG, "head_bwd: bad shape");
   if (y_out != nullptr && beta == nullptr) return set_error(RLCF_ERR_ARG, "head_bwd: y_out needs beta");
@@ -841,7 +854,7 @@ int head_bwd(const float* dlogits, const float* x, const int32_t* row_idx, long 
   head_bwd_kernel<<<grid, kHeadThreads, smem, stream>>>(dlogits, x, row_idx, row_stride, gamma, pstride, proj,
                                                         cls_feat, logit_scale, feat, inv_norm, S, d, E, C, eps, dres,
                                                         partials, n_slots, p_total, p_off, dl_set, dl_s, dl_k,
-                                                        cls_stride, beta, y_out, df_out);
+                                                        cls_stride, beta, y_out, df_out, proj_stride);
   RLCF_CHECK_LAUNCH("head_bwd");
   return 0;
 }
@@ -934,9 +947,12 @@ int cast_f16(const float* in, long long rows, long long cols, long long ld_in, _
   return 0;
 }
 
-__global__ void transpose_cast_kernel(const float* __restrict__ in, int rows, int cols, __half* __restrict__ out) {
+__global__ void transpose_cast_kernel(const float* __restrict__ in, int rows, int cols, __half* __restrict__ out,
+                                      long long in_stride, long long out_stride) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  in += blockIdx.z * in_stride;     // one parameter set per grid.z
+  out += blockIdx.z * out_stride;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int r = r0 + j, c = c0 + threadIdx.x;
     tile[j][threadIdx.x] = (r < rows && c < cols) ? in[static_cast<size_t>(r) * cols + c] : 0.f;
@@ -948,10 +964,12 @@ __global__ void transpose_cast_kernel(const float* __restrict__ in, int rows, in
   }
 }
 
-int transpose_cast_f16(const float* in, int rows, int cols, __half* out, cudaStream_t stream) {
-  if (rows <= 0 || cols <= 0) return set_error(RLCF_ERR_ARG, "transpose_cast_f16: bad shape");
-  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-  transpose_cast_kernel<<<grid, block, 0, stream>>>(in, rows, cols, out);
+int transpose_cast_f16(const float* in, int rows, int cols, __half* out, int n_sets, long long in_stride,
+                       long long out_stride, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0 || n_sets <= 0 || n_sets > 65535)
+    return set_error(RLCF_ERR_ARG, "transpose_cast_f16: bad shape");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, n_sets), block(32, 8);
+  transpose_cast_kernel<<<grid, block, 0, stream>>>(in, rows, cols, out, in_stride, out_stride);
   RLCF_CHECK_LAUNCH("transpose_cast_f16");
   return 0;
 }

@@ -66,6 +66,11 @@ class TowerWeights:
     pos: torch.Tensor | None = None       # fp32 [L, d]
     # text only
     tok_emb: torch.Tensor | None = None   # fp32 [vocab, d]
+    # per-sample weights (every test sample owns the whole tower: full tuning after its first step, retrieval TTA):
+    # the GEMM weights are then 3-D [G, out, in] views, biases [G, n], and cls/pos (embed_stride) and proj
+    # (proj_stride) are the first sample's tensors with the stride, in floats, to the next sample's.
+    embed_stride: int = 0
+    proj_stride: int = 0
 
     @property
     def P(self):
@@ -156,6 +161,32 @@ def prepare_text(sd: dict, need_grad: bool = False) -> TowerWeights:
     return w
 
 
+def linear(a, wt, out, M, epilogue=EPI_F16, bias=None, resid=None, aux_in=None, aux_out=None):
+    """out[:M] = epilogue(a[:M] @ wt^T).  wt [N,K]: one weight for all rows.  wt [G,N,K]: per-sample weights, the M
+    rows being G equal runs (one grouped launch)."""
+    if wt.dim() == 2:
+        return ops.gemm(a, wt, out, epilogue=epilogue, bias=bias, resid=resid, aux_in=aux_in, aux_out=aux_out, M=M)
+    G = wt.shape[0]
+    if M % G:
+        raise RlcfError(f"{M} rows do not split into {G} weight groups")
+    m = M // G
+
+    def v(t):
+        return None if t is None else t[:M].view(G, m, t.shape[-1])
+    return ops.gemm_grouped(v(a), wt, v(out), epilogue=epilogue, bias=bias, resid=v(resid), aux_in=v(aux_in),
+                            aux_out=v(aux_out))
+
+
+@dataclass
+class EmbedRows:
+    """Text-tower input when every sample owns its embedding rows (text->image retrieval tunes token_embedding and
+    positional_embedding, retrieval/custom_models.py:144-152): sample g's L token rows start at tok + g*stride, its
+    positional embedding at pos + g*stride (floats)."""
+    tok: torch.Tensor
+    pos: torch.Tensor
+    stride: int
+
+
 class ActStore:
     """Activations one training-mode forward keeps for the backward (per layer, for `rows` token rows)."""
 
@@ -219,10 +250,10 @@ class TowerRunner:
         if images.shape[-1] != w.resolution or images.shape[-2] != w.resolution:
             raise RlcfError(f"expected {w.resolution}x{w.resolution} input, got {tuple(images.shape)}")
         ops.im2col(images, view_idx, n_seq, w.patch, w.k_pad, self.patches)
-        ops.gemm(self.patches, w.conv_w, self.patch_out, epilogue=EPI_F32, M=n_seq * P)
+        linear(self.patches, w.conv_w, self.patch_out, n_seq * P, epilogue=EPI_F32)
         x = store.x_in[0] if store is not None else self.x
         ops.embed_lnpre(self.patch_out, w.cls, w.pos, ln, ln[w.d:], pstride, rows_per_set, n_seq, w.L, w.d, x,
-                        x_pre=None if store is None else store.x_pre)
+                        x_pre=None if store is None else store.x_pre, embed_stride=w.embed_stride)
         return x
 
     def forward(self, n_seq, ln, pstride=0, seqs_per_set=None, images=None, view_idx=None, tokens=None, store=None,
@@ -249,7 +280,9 @@ class TowerRunner:
             x = self._embed_visual(images, view_idx, n_seq, lnv, pstride, rows_per_set, store, w)
         else:
             x = store.x_in[0] if store is not None else self.x
-            if isinstance(prompt, torch.Tensor):   # ready-made prompt embeddings [n_seq, L, d] (TextEncoder.forward)
+            if isinstance(prompt, EmbedRows):   # per-sample token rows + per-sample positional embedding
+                ops.add_rows(prompt.tok, prompt.stride, prompt.pos, prompt.stride, n_seq, w.L * w.d, x)
+            elif isinstance(prompt, torch.Tensor):   # ready-made prompt embeddings [n_seq, L, d] (TextEncoder.forward)
                 x[:n_seq * w.L].copy_((prompt.float() + w.pos).reshape(n_seq * w.L, w.d))
             elif prompt is not None:   # learnable context vectors spliced into the class prompts (PromptLearner)
                 ctx, ctx_stride, n_ctx, n_sets = prompt
@@ -263,19 +296,19 @@ class TowerRunner:
             a1 = store.a1[l] if full else self.a
             g, b = gb(w.ln_off("ln_1", l))
             ops.layernorm_fwd(x, g, b, rows, d, out16=a1, param_stride=pstride, rows_per_set=rows_per_set)
-            ops.gemm(a1, lw.wqkv, qkv, epilogue=EPI_F16, bias=lw.bqkv, M=rows)
+            linear(a1, lw.wqkv, qkv, rows, epilogue=EPI_F16, bias=lw.bqkv)
             ops.attention_fwd(qkv, n_seq, L, w.heads, attn, causal=causal,
                               lse=None if store is None else store.lse[l])
             x_mid = store.x_mid[l] if store is not None else x
-            ops.gemm(attn, lw.wo, x_mid, epilogue=EPI_RESID_F32, bias=lw.bo, resid=x, M=rows)
+            linear(attn, lw.wo, x_mid, rows, epilogue=EPI_RESID_F32, bias=lw.bo, resid=x)
             a2 = store.a2[l] if full else self.a
             h = store.h[l] if full else self.h
             g, b = gb(w.ln_off("ln_2", l))
             ops.layernorm_fwd(x_mid, g, b, rows, d, out16=a2, param_stride=pstride, rows_per_set=rows_per_set)
-            ops.gemm(a2, lw.wfc, h, epilogue=EPI_GELU_F16, bias=lw.bfc, M=rows,
-                     aux_out=None if store is None else store.u[l])
+            linear(a2, lw.wfc, h, rows, epilogue=EPI_GELU_F16, bias=lw.bfc,
+                   aux_out=None if store is None else store.u[l])
             x_next = store.x_in[l + 1] if store is not None else x
-            ops.gemm(h, lw.wproj, x_next, epilogue=EPI_RESID_F32, bias=lw.bproj, resid=x_mid, M=rows)
+            linear(h, lw.wproj, x_next, rows, epilogue=EPI_RESID_F32, bias=lw.bproj, resid=x_mid)
             x = x_next
         return x
 
@@ -287,7 +320,7 @@ class TowerRunner:
         off = w.ln_off("ln_post")
         ops.head_fwd(x, lnv[off:], lnv[off + w.d:], w.proj, n_seq, w.d, w.E, feat=feat, inv_norm=inv_norm,
                      logits=logits, class_feat=class_feat, logit_scale=logit_scale, row_idx=row_idx, row_stride=w.L,
-                     param_stride=pstride, seqs_per_set=seqs_per_set)
+                     param_stride=pstride, seqs_per_set=seqs_per_set, proj_stride=w.proj_stride)
 
     # ------------------------------------------------------------------ backward (LayerNorm parameters only)
     def backward(self, store: ActStore, n_sets, seqs_per_set, ln, pstride, partials, n_slots=N_SLOTS, w=None,
@@ -310,22 +343,22 @@ class TowerRunner:
             # MLP branch: d u = (d x_out @ Wproj) * gelu'(u);  d a2 = d u @ Wfc
             if hook is not None:
                 hook.linear(l, "c_proj", dres16, store.h[l])
-            ops.gemm(dres16, lw.wproj_t, self.gh, epilogue=EPI_GELU_BWD_F16, aux_in=store.u[l], M=rows)
+            linear(dres16, lw.wproj_t, self.gh, rows, epilogue=EPI_GELU_BWD_F16, aux_in=store.u[l])
             if hook is not None:
                 hook.linear(l, "c_fc", self.gh, store.a2[l])
-            ops.gemm(self.gh, lw.wfc_t, self.g16, epilogue=EPI_F16, M=rows)
+            linear(self.gh, lw.wfc_t, self.g16, rows, epilogue=EPI_F16)
             off = w.ln_off("ln_2", l)
             ops.layernorm_bwd(self.g16, store.x_mid[l], lnv[off:], rows_per_set, n_sets, d, partials, n_slots, P, off,
                               dx=dres, accumulate=True, param_stride=pstride, dx16=dres16)
             # attention branch
             if hook is not None:
                 hook.linear(l, "out_proj", dres16, store.attn[l])
-            ops.gemm(dres16, lw.wo_t, self.g16, epilogue=EPI_F16, M=rows)
+            linear(dres16, lw.wo_t, self.g16, rows, epilogue=EPI_F16)
             ops.attention_bwd(store.qkv[l], store.attn[l], self.g16, store.lse[l], n_seq, L, w.heads, self.gqkv,
                               causal=(w.kind == "text"))
             if hook is not None:
                 hook.linear(l, "in_proj", self.gqkv, store.a1[l])
-            ops.gemm(self.gqkv, lw.wqkv_t, self.g16, epilogue=EPI_F16, M=rows)
+            linear(self.gqkv, lw.wqkv_t, self.g16, rows, epilogue=EPI_F16)
             off = w.ln_off("ln_1", l)
             ops.layernorm_bwd(self.g16, store.x_in[l], lnv[off:], rows_per_set, n_sets, d, partials, n_slots, P, off,
                               dx=dres, accumulate=True, param_stride=pstride, dx16=dres16)

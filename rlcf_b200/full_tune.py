@@ -98,6 +98,48 @@ def tower_view(base: E.TowerWeights, lay: FullLayout, rest: torch.Tensor, w16: t
     return t
 
 
+def tower_view_grouped(base: E.TowerWeights, lay: FullLayout, rest: torch.Tensor, w16: torch.Tensor, w16t, ln):
+    """TowerWeights over ALL samples' parameter vectors at once (rest [G,total] fp32, w16 / w16t [G,p_gemm] fp16,
+    ln [G,P]): GEMM weights become [G,out,in] views for the grouped tcgen05 launch, biases [G,n] views, and the
+    embedding / projection tensors carry the per-sample stride."""
+    d, G = lay.d, rest.shape[0]
+    t = E.TowerWeights(kind="visual", d=d, heads=base.heads, n_layers=lay.nl, L=lay.L, E=lay.E, patch=base.patch,
+                       resolution=base.resolution, k_pad=lay.k_pad)
+
+    def m(buf, off, r, c):
+        return None if buf is None else buf.as_strided((G, r, c), (buf.stride(0), c, 1), buf.storage_offset() + off)
+
+    def b(off, n):
+        return rest.as_strided((G, n), (rest.stride(0), 1), rest.storage_offset() + off)
+
+    t.conv_w = m(w16, lay.conv, d, lay.k_pad)
+    t.cls = rest[0, lay.cls:lay.cls + d]
+    t.pos = rest[0, lay.pos:lay.pos + lay.L * d].view(lay.L, d)
+    t.proj = rest[0, lay.proj:lay.proj + d * lay.E].view(d, lay.E)
+    t.embed_stride = t.proj_stride = rest.stride(0)
+    t.ln_flat = ln[0]   # P = one sample's LayerNorm slice; callers pass the [G, P] tensor and its stride explicitly
+    for l in range(lay.nl):
+        t.layers.append(E.LayerWeights(
+            wqkv=m(w16, lay.wq[l], 3 * d, d), bqkv=b(lay.bq[l], 3 * d),
+            wo=m(w16, lay.wo[l], d, d), bo=b(lay.bo[l], d),
+            wfc=m(w16, lay.wf[l], 4 * d, d), bfc=b(lay.bf[l], 4 * d),
+            wproj=m(w16, lay.wp[l], d, 4 * d), bproj=b(lay.bp[l], d),
+            wqkv_t=m(w16t, lay.wq[l], d, 3 * d), wo_t=m(w16t, lay.wo[l], d, d),
+            wfc_t=m(w16t, lay.wf[l], d, 4 * d), wproj_t=m(w16t, lay.wp[l], 4 * d, d)))
+    return t
+
+
+def cast_weights(lay: FullLayout, rest: torch.Tensor, w16: torch.Tensor, w16t=None):
+    """fp16 copies of every sample's GEMM weights (and their transposes, the dgrad B operands) from the fp32 masters."""
+    G, d = rest.shape[0], lay.d
+    ops.call("rlcf_cast_f16", ops.ptr(rest), G, lay.p_gemm, rest.stride(0), ops.ptr(w16), w16.stride(0), ops.stream())
+    if w16t is None:
+        return
+    for l in range(lay.nl):
+        for off, r, c in ((lay.wq[l], 3 * d, d), (lay.wo[l], d, d), (lay.wf[l], 4 * d, d), (lay.wp[l], d, 4 * d)):
+            ops.transpose_cast_f16_sets(rest.view(-1)[off:], r, c, G, rest.stride(0), w16t.view(-1)[off:], w16t.stride(0))
+
+
 class WgradHook:
     """Weight / bias / embedding gradients of `n_sets` images whose rows are laid out set after set.
     grads: fp32 [n_sets, lay.total] (written, not accumulated).  dY carries the loss scale; so do the gradients."""
@@ -128,11 +170,12 @@ class WgradHook:
         ops.transpose_blocks(dY, ns, rows, rows_pad, n_out, self.t_dy, ld, skip_first=skip,
                              in_set_stride_rows=dy_stride_rows)
         ops.transpose_blocks(X, ns, rows, rows_pad, n_in, self.t_x, ld)
-        ty, tx = self.t_dy.view(-1)[:n_out * ld].view(n_out, ld), self.t_x.view(-1)[:n_in * ld].view(n_in, ld)
-        for g in range(ns):
-            out = self.grads[g, off:off + n_out * n_in].view(n_out, n_in)
-            ops.gemm(ty[:, g * rows_pad:(g + 1) * rows_pad], tx[:, g * rows_pad:(g + 1) * rows_pad], out,
-                     epilogue=EPI_F32)
+        # one grouped launch: group g = columns [g*rows_pad, (g+1)*rows_pad) of the transposed operands
+        ty = self.t_dy.as_strided((ns, n_out, rows_pad), (rows_pad, ld, 1))
+        tx = self.t_x.as_strided((ns, n_in, rows_pad), (rows_pad, ld, 1))
+        g = self.grads
+        out = g.as_strided((ns, n_out, n_in), (g.stride(0), n_in, 1), g.storage_offset() + off)
+        ops.gemm_grouped(ty, tx, out, epilogue=EPI_F32)
 
     def linear(self, l: int, name: str, dY: torch.Tensor, X: torch.Tensor):
         lay, d = self.lay, self.lay.d
@@ -181,9 +224,6 @@ class FullTuneEngine:
         self.run = E.TowerRunner(pol, B * V)
         self.run.reserve_backward(B * S)
         self.store = E.ActStore(pol, B * S, dev, full=True)
-        self.prun = E.TowerRunner(pol, S)            # per-image work (steps >= 2, adapted prediction)
-        self.prun.reserve_backward(S)
-        self.pstore = E.ActStore(pol, S, dev, full=True) if cfg.tta_steps > 1 else None
         self.rrun = E.TowerRunner(reward, B * S)
         self.hook = WgradHook(lay, pol, B, S, dev)
         # parameters: LayerNorm slice as in RlcfEngine, everything else in `rest`
@@ -199,8 +239,8 @@ class FullTuneEngine:
         self.grads = torch.zeros(B, lay.total, **f32)
         self.w16 = torch.empty(B, lay.p_gemm, dtype=torch.float16, device=dev)
         self.w16t = torch.empty(B, lay.p_gemm, dtype=torch.float16, device=dev) if cfg.tta_steps > 1 else None
-        self.img_w = [tower_view(pol, lay, self.rest[b], self.w16[b], None if self.w16t is None else self.w16t[b],
-                                 self.ln[b]) for b in range(B)]
+        # all images' weights as one set of [B, out, in] views: steps >= 2 and the adapted prediction are grouped launches
+        self.gw = tower_view_grouped(pol, lay, self.rest, self.w16, self.w16t, self.ln)
         self.logits_all = torch.empty(B * V, C, **f32)
         self.entropy = torch.empty(B, V, **f32)
         self.sel = torch.empty(B, S, **i32)
@@ -242,7 +282,7 @@ class FullTuneEngine:
                         self.feat_sel[sl], self.inv_norm_sel[sl], n_sets, S, pol.d, pol.E, C, runner.dres,
                         row_stride=pol.L, param_stride=pstride, partials=self.partials[rows0:rows0 + n_sets],
                         n_slots=self.n_slots, p_total=pol.P, p_off=off, beta=lnv[off + pol.d:], y_out=hk.y,
-                        df_out=hk.df)
+                        df_out=hk.df, proj_stride=w.proj_stride)
 
     def _adamw(self, step):
         cfg, B, P, lay = self.cfg, self.n_img, self.base.P, self.lay
@@ -257,16 +297,7 @@ class FullTuneEngine:
             ops.adamw_step_from(self.rest, self.rest_m, self.rest_v, self.grads, B, 1, lay.total, cfg.lr, step,
                                 self.rest, lay.total, False, **kw)
         # fp16 copies of the updated GEMM weights (and their transposes when another backward follows)
-        ops.call("rlcf_cast_f16", ops.ptr(self.rest), B, lay.p_gemm, lay.total, ops.ptr(self.w16), lay.p_gemm,
-                 ops.stream())
-        if step < cfg.tta_steps:
-            d = lay.d
-            for b in range(B):
-                for l in range(lay.nl):
-                    for off, r, c in ((lay.wq[l], 3 * d, d), (lay.wo[l], d, d), (lay.wf[l], 4 * d, d),
-                                      (lay.wp[l], d, 4 * d)):
-                        ops.call("rlcf_transpose_cast_f16", ops.ptr(self.rest[b, off:]), r, c,
-                                 ops.ptr(self.w16t[b, off:]), ops.stream())
+        cast_weights(lay, self.rest, self.w16, self.w16t if step < cfg.tta_steps else None)
 
     def tune(self, images: torch.Tensor):
         cfg, B = self.cfg, self.n_img
@@ -290,27 +321,23 @@ class FullTuneEngine:
         hk.proj()
         self.run.backward(self.store, B, S, self.ln, P, self.partials, self.n_slots, hook=hk)
         self._adamw(1)
-        # ---- steps >= 2: every image on its own weights
+        # ---- steps >= 2: every image on its own weights (grouped GEMMs, one group per image)
         for step in range(2, cfg.tta_steps + 1):
             self.partials.zero_()
-            for b in range(B):
-                w = self.img_w[b]
-                xs = self.prun.forward(S, self.ln[b], images=images, view_idx=self.sel_global[b * S:(b + 1) * S],
-                                       store=self.pstore, w=w)
-                self._loss_and_head_bwd(step, xs, self.prun, self.ln[b], 0, 1, w, rows0=b)
-                hk.bind(self.grads[b:b + 1], 1, self.prun.patches)
-                hk.proj()   # head_bwd of this one-image call left y / d f in rows [0, S)
-                self.prun.backward(self.pstore, 1, S, self.ln[b], 0, self.partials[b:b + 1], self.n_slots, w=w, hook=hk)
+            xs = self.run.forward(B * S, self.ln, pstride=P, seqs_per_set=S, images=images, view_idx=self.sel_global,
+                                  store=self.store, w=self.gw)
+            self._loss_and_head_bwd(step, xs, self.run, self.ln, P, B, self.gw)
+            hk.bind(self.grads, B, self.run.patches)
+            hk.proj()
+            self.run.backward(self.store, B, S, self.ln, P, self.partials, self.n_slots, w=self.gw, hook=hk)
             self._adamw(step)
         return self.ln, self.rest
 
     def predict(self, images: torch.Tensor) -> torch.Tensor:
-        B = self.n_img
-        for b in range(B):
-            w = self.img_w[b]
-            xf = self.prun.forward(1, self.ln[b], images=images, view_idx=self.first_view[b:b + 1], w=w)
-            self.prun.head(xf, 1, self.ln[b], class_feat=self.class_feat, logit_scale=self.logit_scale,
-                           logits=self.logits_final[b:b + 1], w=w)
+        B, P = self.n_img, self.base.P
+        xf = self.run.forward(B, self.ln, pstride=P, seqs_per_set=1, images=images, view_idx=self.first_view, w=self.gw)
+        self.run.head(xf, B, self.ln, pstride=P, seqs_per_set=1, class_feat=self.class_feat,
+                      logit_scale=self.logit_scale, logits=self.logits_final, w=self.gw)
         return self.logits_final
 
     def adapt(self, images: torch.Tensor) -> torch.Tensor:

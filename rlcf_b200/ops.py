@@ -93,10 +93,16 @@ def im2col(images, view_idx, n_views, patch, k_pad, out):
     return out
 
 
-def embed_lnpre(patch_out, cls, pos, gamma, beta, param_stride, rows_per_set, n_views, L, d, x, x_pre=None, eps=1e-5):
+def embed_lnpre(patch_out, cls, pos, gamma, beta, param_stride, rows_per_set, n_views, L, d, x, x_pre=None, eps=1e-5,
+                embed_stride=0):
+    """embed_stride != 0: set g reads its own class / positional embedding at cls + g*embed_stride, pos + g*embed_stride."""
     _chk(patch_out, torch.float32, "patch_out"); _chk(x, torch.float32, "x"); _chk(x_pre, torch.float32, "x_pre")
-    call("rlcf_embed_lnpre", ptr(patch_out), ptr(cls), ptr(pos), ptr(gamma), ptr(beta), param_stride, rows_per_set,
-         n_views, L, d, eps, ptr(x_pre), ptr(x), stream())
+    if embed_stride:
+        call("rlcf_embed_lnpre_sets", ptr(patch_out), ptr(cls), ptr(pos), embed_stride, ptr(gamma), ptr(beta),
+             param_stride, rows_per_set, n_views, L, d, eps, ptr(x_pre), ptr(x), stream())
+    else:
+        call("rlcf_embed_lnpre", ptr(patch_out), ptr(cls), ptr(pos), ptr(gamma), ptr(beta), param_stride, rows_per_set,
+             n_views, L, d, eps, ptr(x_pre), ptr(x), stream())
     return x
 
 
@@ -139,13 +145,19 @@ def attention_bwd(qkv, out, dout, lse, n_seq, L, heads, dqkv, causal=False):
 
 
 def head_fwd(x, gamma, beta, proj, n, d, E, feat=None, inv_norm=None, logits=None, class_feat=None, logit_scale=1.0,
-             row_idx=None, row_stride=1, param_stride=0, seqs_per_set=None, eps=1e-5):
-    _chk(x, torch.float32, "x"); _chk(proj, torch.float32, "proj"); _chk(class_feat, torch.float32, "class_feat")
+             row_idx=None, row_stride=1, param_stride=0, seqs_per_set=None, eps=1e-5, proj_stride=0):
+    _chk(x, torch.float32, "x"); _chk(proj, torch.float32, "proj", strided=bool(proj_stride))
+    _chk(class_feat, torch.float32, "class_feat")
     _chk(row_idx, torch.int32, "row_idx"); _chk(feat, torch.float32, "feat"); _chk(logits, torch.float32, "logits")
     C = 0 if class_feat is None else class_feat.shape[0]
-    call("rlcf_head_fwd", ptr(x), ptr(row_idx), row_stride, ptr(gamma), ptr(beta), param_stride,
-         n if seqs_per_set is None else seqs_per_set, ptr(proj), ptr(class_feat), float(logit_scale), n, d, E, C, eps,
-         ptr(feat), ptr(inv_norm), ptr(logits), stream())
+    sps = n if seqs_per_set is None else seqs_per_set
+    if proj_stride:
+        call("rlcf_head_fwd_sets", ptr(x), ptr(row_idx), row_stride, ptr(gamma), ptr(beta), param_stride, sps,
+             ptr(proj), proj_stride, ptr(class_feat), float(logit_scale), n, d, E, C, eps, ptr(feat), ptr(inv_norm),
+             ptr(logits), stream())
+    else:
+        call("rlcf_head_fwd", ptr(x), ptr(row_idx), row_stride, ptr(gamma), ptr(beta), param_stride, sps, ptr(proj),
+             ptr(class_feat), float(logit_scale), n, d, E, C, eps, ptr(feat), ptr(inv_norm), ptr(logits), stream())
 
 
 def entropy_select(logits, n_img, V, C, S, sel, sel_global=None, entropy=None):
@@ -181,9 +193,15 @@ def head_bwd(dlogits, x, gamma, proj, class_feat, logit_scale, feat, inv_norm, n
 
 def head_bwd_ex(dlogits, dl_strides, x, gamma, proj, other_feat, other_set_stride, logit_scale, feat, inv_norm, n_sets,
                 seqs_per_set, d, E, K, dres, row_idx=None, row_stride=1, param_stride=0, partials=None, n_slots=1,
-                p_total=0, p_off=0, eps=1e-5, beta=None, y_out=None, df_out=None):
+                p_total=0, p_off=0, eps=1e-5, beta=None, y_out=None, df_out=None, proj_stride=0):
     _chk(dlogits, torch.float32, "dlogits"); _chk(x, torch.float32, "x"); _chk(dres, torch.float32, "dres")
     _chk(other_feat, torch.float32, "other_feat"); _chk(row_idx, torch.int32, "row_idx")
+    if proj_stride:
+        call("rlcf_head_bwd_sets", ptr(dlogits), dl_strides[0], dl_strides[1], dl_strides[2], ptr(x), ptr(row_idx),
+             row_stride, ptr(gamma), param_stride, ptr(proj), proj_stride, ptr(other_feat), other_set_stride,
+             float(logit_scale), ptr(feat), ptr(inv_norm), n_sets, seqs_per_set, d, E, K, eps, ptr(dres), ptr(partials),
+             n_slots, p_total, p_off, ptr(beta), ptr(y_out), ptr(df_out), stream())
+        return
     call("rlcf_head_bwd_ex", ptr(dlogits), dl_strides[0], dl_strides[1], dl_strides[2], ptr(x), ptr(row_idx), row_stride,
          ptr(gamma), param_stride, ptr(proj), ptr(other_feat), other_set_stride, float(logit_scale), ptr(feat),
          ptr(inv_norm), n_sets, seqs_per_set, d, E, K, eps, ptr(dres), ptr(partials), n_slots, p_total, p_off,
@@ -281,3 +299,62 @@ def transpose_cast_f16(src):
     out = torch.empty(cols, rows, dtype=torch.float16, device=src.device)
     call("rlcf_transpose_cast_f16", ptr(src), rows, cols, ptr(out), stream())
     return out
+
+
+def transpose_cast_f16_sets(src, rows, cols, n_sets, in_stride, out, out_stride):
+    """n_sets transposing casts in one launch: out[g] ([cols, rows] fp16 at g*out_stride) = src[g] ([rows, cols] fp32 at
+    g*in_stride)^T.  src / out are base pointers (strided views)."""
+    _chk(src, torch.float32, "src", strided=True); _chk(out, torch.float16, "out", strided=True)
+    call("rlcf_transpose_cast_f16_sets", ptr(src), rows, cols, n_sets, in_stride, ptr(out), out_stride, stream())
+    return out
+
+
+def retrieval_loss(logits, reward_query, reward_gallery, K, dlogits, clipscore_weight=2.5, reward_process=True,
+                   amplify=False, loss_scale=1.0, topk_idx=None, scores=None, rewards=None, loss=None):
+    """One retrieval query per row of logits [Q, C]: top-K sampling, CLIPScore, rewards, loss and dlogits
+    (retrieval/clip_ret_policy.py:88-98 / 121-131)."""
+    _chk(logits, torch.float32, "logits"); _chk(reward_query, torch.float32, "reward_query")
+    _chk(reward_gallery, torch.float32, "reward_gallery"); _chk(dlogits, torch.float32, "dlogits")
+    _chk(topk_idx, torch.int32, "topk_idx"); _chk(scores, torch.float32, "scores")
+    _chk(rewards, torch.float32, "rewards"); _chk(loss, torch.float32, "loss")
+    Q, C = logits.shape
+    if reward_gallery.shape[0] != C or reward_query.shape[0] != Q or reward_query.shape[1] != reward_gallery.shape[1]:
+        raise _lib.RlcfError("retrieval_loss: reward feature shapes do not match the score rows")
+    call("rlcf_retrieval_loss", ptr(logits), C, ptr(reward_query), ptr(reward_gallery), Q, K, C,
+         reward_gallery.shape[1], float(clipscore_weight), int(bool(reward_process)), int(bool(amplify)),
+         float(loss_scale), ptr(dlogits), ptr(topk_idx), ptr(scores), ptr(rewards), ptr(loss), stream())
+
+
+def dfeat_partial(dlogits, gallery, partial):
+    """partial [Q, n_chunks, E] = per-chunk pieces of dlogits [Q, C] @ gallery [C, E]."""
+    _chk(dlogits, torch.float32, "dlogits"); _chk(gallery, torch.float32, "gallery"); _chk(partial, torch.float32, "partial")
+    Q, C = dlogits.shape
+    call("rlcf_dfeat_partial", ptr(dlogits), ptr(gallery), Q, C, gallery.shape[1], partial.shape[1], ptr(partial),
+         stream())
+    return partial
+
+
+def rowdot(a, b, out, out_stride=1, scale=1.0):
+    _chk(a, torch.float32, "a"); _chk(b, torch.float32, "b"); _chk(out, torch.float32, "out", strided=True)
+    call("rlcf_rowdot", ptr(a), ptr(b), a.shape[0], a.shape[1], float(scale), ptr(out), out_stride, stream())
+    return out
+
+
+def add_rows(a, a_stride, b, b_stride, n_sets, n, x):
+    """x[g, :n] = a[g*a_stride : +n] + b[g*b_stride : +n]  (a, b base pointers of strided per-query vectors)."""
+    _chk(a, torch.float32, "a", strided=True); _chk(b, torch.float32, "b", strided=True); _chk(x, torch.float32, "x")
+    call("rlcf_add_rows", ptr(a), a_stride, ptr(b), b_stride, n_sets, n, ptr(x), stream())
+    return x
+
+
+def scale_rows_exp(src, ls, ls_stride, out):
+    """out[q, :] = src[q, :] * exp(ls[q*ls_stride])."""
+    _chk(src, torch.float32, "src"); _chk(ls, torch.float32, "ls", strided=True); _chk(out, torch.float32, "out")
+    call("rlcf_scale_rows_exp", ptr(src), ptr(ls), ls_stride, src.shape[0], src.shape[1], ptr(out), stream())
+    return out
+
+
+def tied_rows_grad(dx, tokens, n_sets, L, d, g_tok, g_pos, out_stride):
+    _chk(dx, torch.float32, "dx"); _chk(tokens, torch.int64, "tokens")
+    _chk(g_tok, torch.float32, "g_tok", strided=True); _chk(g_pos, torch.float32, "g_pos", strided=True)
+    call("rlcf_tied_rows_grad", ptr(dx), ptr(tokens), n_sets, L, d, ptr(g_tok), ptr(g_pos), out_stride, stream())

@@ -1,0 +1,206 @@
+"""Retrieval TTA on the GPU (rlcf_b200/retrieval.py through the C ABI) against (i) the committed outputs of the
+reference's own retrieval code (tests/golden/ret_*.npz, oracle/make_golden_retrieval.py) and (ii) the CPU oracle run
+on the same seeded inputs (per-tensor gradients, adapted parameters)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rlcf_oracle as O
+from test_oracle_retrieval import CASES, load_case, retrieval_setup
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+ROW_TOL = 1e-3          # score rows: <= 1e-3 of the row's largest |score| (north-star tolerance on final logits)
+
+
+def to_dev(sd):
+    return {k: v.to(DEV) for k, v in sd.items()}
+
+
+def build(cfg, rcfg_o, sd_p, sd_r, gal_p, gal_r, n_query):
+    from rlcf_b200 import engine as E, retrieval as R
+    rc = R.RetrievalConfig(tta_steps=rcfg_o.tta_steps, sample_k=rcfg_o.sample_k, lr=rcfg_o.lr,
+                           weight_decay=rcfg_o.weight_decay, eps=rcfg_o.eps, momentum_update=rcfg_o.momentum_update,
+                           update_freq=rcfg_o.update_freq, update_w=rcfg_o.update_w, momentum=rcfg_o.momentum)
+    if cfg["task"] == "image2text":
+        return R.ImageQueryEngine(to_dev(sd_p), gal_p.to(DEV), float(sd_p["logit_scale"].exp()), rc, n_query,
+                                  E.prepare_visual(to_dev(sd_r)), gal_r.to(DEV))
+    return R.TextQueryEngine(to_dev(sd_p), gal_p.to(DEV), rc, n_query, E.prepare_text(to_dev(sd_r)), gal_r.to(DEV))
+
+
+def check_query(eng, q, out, z_row, cfg, tag, row0):
+    """Engine slot q against the oracle's result `out` for the same query (and the reference's score row).
+    row0: the oracle's score row BEFORE adaptation.  Tolerance as in tests/test_parity_gpu.py: 1e-3 of the largest
+    |score| plus 30% of what adaptation changed (AdamW's sign-like first steps amplify rounding-level gradient noise)."""
+    steps, lr = cfg["steps"], cfg["lr"]
+    row = eng.score_rows[q].cpu().numpy()
+    ref_row = out["score_row"].numpy()
+    scale = np.abs(ref_row).max()
+    delta = np.abs(ref_row - row0).max()
+    err = np.abs(row - ref_row).max()
+    print(f"{tag}: score row err {err / scale:.2e} of max |score| {scale:.2f} (adaptation delta {delta / scale:.2e})")
+    assert err <= ROW_TOL * scale + 0.3 * delta, f"{tag}: score row differs from the oracle by {err:.3e}"
+    if z_row is not None:
+        assert np.abs(row - z_row).max() <= ROW_TOL * np.abs(z_row).max() + 0.3 * delta, \
+            f"{tag}: score row differs from the reference"
+    # sampled candidates: identical sets per step unless the K-th / (K+1)-th scores are closer than the score error
+    for s in range(steps):
+        got = eng.topk_idx[s, q].cpu().numpy()
+        want = out["topk_idx"][s].numpy()
+        if not np.array_equal(got, want):
+            assert set(got.tolist()) == set(want.tolist()) or s > 0, f"{tag}: step-{s} samples differ: {got} vs {want}"
+            if set(got.tolist()) != set(want.tolist()):
+                pytest.skip(f"{tag}: sampled set diverged at step {s} (near-tie after adaptation)")
+            continue
+        sc = out["scores"][s].numpy()
+        assert np.abs(eng.scores[s, q].cpu().numpy() - sc).max() <= 2e-3 * max(1.0, np.abs(sc).max()), tag
+        rw = out["rewards"][s].numpy()
+        assert np.abs(eng.rewards[s, q].cpu().numpy() - rw).max() <= 2e-3 * max(1.0, np.abs(rw).max()), tag
+
+
+def check_grads_and_params(eng, q, out, cfg, tag, named, grads=True):
+    """named: list of (oracle parameter name, engine gradient tensor (loss-scaled), engine parameter tensor).
+    eng.grads holds the LAST step's gradient: it is compared with the oracle's last-step gradient, which is taken at
+    (slightly) different weights once steps > 1 -- only meaningful while lr*steps is tiny (the recipe cases)."""
+    steps, lr = cfg["steps"], cfg["lr"]
+    g_last = out["grads"][-1]
+    for name, g, p in named:
+        ref = g_last[name]
+        if grads and name == "logit_scale":
+            # d logit_scale = sum_c dlogits[c] * logits[c] = -(1/K) sum_k r_k * logit[idx_k] with sum_k r_k = 0: only the
+            # DIFFERENCES between the sampled scores survive, so the 1e-3 relative error of fp16-operand logits is
+            # amplified by |logit| / |logit differences|.  Bound: 2e-3 * (1/K) sum_k |r_k| |logit_k|.
+            r, idx = out["rewards"][-1], out["topk_idx"][-1]
+            row = eng.logits[q].cpu()[idx.long()]
+            bound = 2e-3 * float((r.abs() * row.abs()).mean())
+            e = abs(float(g) / eng.cfg.loss_scale - float(ref))
+            print(f"{tag} logit_scale: grad {float(g) / eng.cfg.loss_scale:.4e} vs {float(ref):.4e} (bound {bound:.2e})")
+            assert e <= bound, f"{tag} logit_scale grad off by {e:.3e} > {bound:.3e}"
+        elif grads:
+            g = (g / eng.cfg.loss_scale).cpu().reshape(ref.shape)
+            e = (g - ref).abs().max() / ref.abs().max().clamp_min(1e-20)
+            print(f"{tag} {name}: last-step grad rel err {e:.2e}")
+            assert e <= 3e-2, f"{tag} {name}: grad rel err {e:.3e}"
+        pref = out["state"][name]
+        dlt = (p.cpu().reshape(pref.shape) - pref).abs()
+        assert dlt.max() <= 2.02 * lr * steps + 1e-7, f"{tag} {name}: moved {dlt.max():.3e}"
+        strong = torch.ones_like(pref, dtype=torch.bool)
+        for gd in out["grads"]:
+            strong &= gd[name].abs() >= 0.05 * gd[name].abs().max()
+        if strong.any():
+            bad = float((dlt[strong] > 0.1 * lr * steps).float().mean())
+            assert bad <= 0.02, f"{tag} {name}: {100 * bad:.1f}% of the clearly-signed entries off by > 10% of a step"
+
+
+def named_tensors(eng, q, task, tokens_q=None, out=None):
+    lay = eng.lay
+    params = eng.export_params(q)
+    named = []
+    prefix = "visual." if task == "image2text" else ""
+    entries = lay.entries(prefix) if task == "image2text" else lay.entries()
+    for key, off, shape in entries:
+        n = int(np.prod(shape))
+        g = eng.grads[q, off:off + n].view(shape)
+        p = params[key]
+        if key.endswith("conv1.weight"):
+            k_real = int(np.prod(p.shape[1:]))
+            g = g[:, :k_real]
+        named.append((key, g, p))
+    if task == "text2image":
+        named.append(("logit_scale", eng.grads[q, lay.ls], params["logit_scale"]))
+    return named
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_retrieval_cuda_matches_reference_and_oracle(name):
+    z, cfg = load_case(name)
+    torch.set_num_threads(os.cpu_count() or 1)
+    i2t = cfg["task"] == "image2text"
+    sd_p, sd_r, images, tokens, rcfg, gal_p, gal_r = retrieval_setup(cfg)
+    nq = cfg["n_query"]
+    sequential = rcfg.momentum_update
+    eng = build(cfg, rcfg, sd_p, sd_r, gal_p, gal_r, 1 if sequential else nq)
+    state = O.RetrievalMomentum(sd_p, rcfg)
+    queries = images if i2t else tokens
+
+    def oracle(qi):
+        query = queries[qi:qi + 1]
+        with torch.no_grad():
+            rq = O.retrieval_features(sd_r, images=query) if i2t else O.retrieval_features(sd_r, tokens=query)
+            f0 = (O.retrieval_features(state.initial, images=query) if i2t
+                  else O.retrieval_features(state.initial, tokens=query))
+            row0 = (state.initial["logit_scale"].exp() * f0 @ gal_p.t())[0].numpy()
+        return O.retrieval_tune_query(state.initial, rcfg, cfg["task"], query, gal_p, rq, gal_r), row0
+
+    if sequential:
+        for qi in range(nq):
+            eng.adapt(queries[qi:qi + 1].to(DEV))
+            out, row0 = oracle(qi)
+            check_query(eng, 0, out, z[f"q{qi}.score_row"], cfg, f"{name} q{qi}", row0)
+            if qi == 0:   # first query: same initial weights on both sides -> gradients and parameters comparable
+                check_grads_and_params(eng, 0, out, cfg, f"{name} q{qi}", named_tensors(eng, 0, cfg["task"]),
+                                       grads=False)   # lr = 1e-4 x 3 steps: the last-step weights differ visibly
+            eng.momentum_update(0)
+            state.update(out["state"])
+    else:
+        eng.adapt(queries[:nq].to(DEV))
+        for qi in range(nq):
+            out, row0 = oracle(qi)
+            check_query(eng, qi, out, z[f"q{qi}.score_row"], cfg, f"{name} q{qi}", row0)
+            check_grads_and_params(eng, qi, out, cfg, f"{name} q{qi}", named_tensors(eng, qi, cfg["task"]))
+            if not i2t:   # the caption's token-embedding rows: gradient of row tokens[t] (tied positions summed)
+                lay, L, d = eng.lay, eng.base.L, eng.base.d
+                g_tok = (eng.grads[qi, lay.tok:lay.tok + L * d].view(L, d) / eng.cfg.loss_scale).cpu()
+                ref = out["grads"][-1]["token_embedding.weight"][tokens[qi]]
+                assert (g_tok - ref).abs().max() <= 3e-2 * ref.abs().max().clamp_min(1e-20)
+                g_pos = (eng.grads[qi, lay.pos:lay.pos + L * d].view(L, d) / eng.cfg.loss_scale).cpu()
+                refp = out["grads"][-1]["positional_embedding"]
+                assert (g_pos - refp).abs().max() <= 3e-2 * refp.abs().max().clamp_min(1e-20)
+    assert np.isfinite(eng.loss.cpu().numpy()).all()
+
+
+def test_retrieval_batched_equals_one_at_a_time():
+    """Independent queries (momentum_update off): a batch of Q queries gives the rows of Q single-query runs."""
+    z, cfg = load_case("ret_i2t_tiny_recipe")
+    sd_p, sd_r, images, tokens, rcfg, gal_p, gal_r = retrieval_setup(cfg)
+    nq = cfg["n_query"]
+    eng = build(cfg, rcfg, sd_p, sd_r, gal_p, gal_r, nq)
+    rows = eng.adapt(images[:nq].to(DEV)).clone()
+    one = build(cfg, rcfg, sd_p, sd_r, gal_p, gal_r, 1)
+    for qi in range(nq):
+        r = one.adapt(images[qi:qi + 1].to(DEV))
+        assert torch.equal(r[0], rows[qi]), f"query {qi}: batched and single-query score rows differ"
+
+
+def test_retrieval_loss_kernel_large_gallery():
+    """rlcf_retrieval_loss / rlcf_dfeat_partial at COCO gallery width (25 000 candidates, K = 20) against PyTorch."""
+    from rlcf_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    Q, C, K, E, Er = 3, 25000, 20, 512, 768
+    logits = (torch.randn(Q, C, generator=g) * 4).to(DEV)
+    rq = torch.nn.functional.normalize(torch.randn(Q, Er, generator=g), dim=-1).to(DEV)
+    rg = torch.nn.functional.normalize(torch.randn(C, Er, generator=g) + 0.05, dim=-1).to(DEV)
+    gal = torch.nn.functional.normalize(torch.randn(C, E, generator=g), dim=-1).to(DEV)
+    dl = torch.empty(Q, C, device=DEV)
+    idx = torch.empty(Q, K, dtype=torch.int32, device=DEV)
+    sc, rw, loss = torch.empty(Q, K, device=DEV), torch.empty(Q, K, device=DEV), torch.empty(Q, device=DEV)
+    ops.retrieval_loss(logits, rq, rg, K, dl, topk_idx=idx, scores=sc, rewards=rw, loss=loss, loss_scale=8.0)
+    lg = logits.clone().requires_grad_(True)
+    _, ti = torch.topk(lg, K, dim=-1)
+    assert torch.equal(ti.int(), idx)
+    for q in range(Q):
+        score = torch.clamp(2.5 * (rg[ti[q]] * rq[q]).sum(-1), min=0)
+        assert torch.allclose(score, sc[q], atol=1e-5)
+        r = score - score.mean()
+        assert torch.allclose(r, rw[q], atol=1e-5)
+        l = (r * torch.nn.functional.cross_entropy(lg[q:q + 1].expand(K, C), ti[q], reduction="none")).mean()
+        assert abs(float(l) - float(loss[q])) <= 1e-4 * max(1.0, abs(float(l)))
+        (gq,) = torch.autograd.grad(l, lg, retain_graph=True)
+        assert (gq[q] * 8.0 - dl[q]).abs().max() <= 1e-5 * max(1.0, float(gq[q].abs().max()) * 8.0)
+    n_chunks = 128
+    part = torch.empty(Q, n_chunks, E, device=DEV)
+    ops.dfeat_partial(dl, gal, part)
+    want = dl.double() @ gal.double()
+    assert (part.double().sum(1) - want).abs().max() <= 1e-4 * want.abs().max()
