@@ -43,9 +43,11 @@ def parse_args():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5],
                     help="BASELINE.json configs index: 2 = the metric's workload (default); 3 = same with 3 TTA steps; "
                          "5 = ViT-L/14 policy LN-tuning (informational)")
-    ap.add_argument("--mode", default="ln", choices=["ln", "prompt", "full"],
+    ap.add_argument("--mode", default="ln", choices=["ln", "prompt", "full", "ret_i2t", "ret_t2i"],
                     help="ln = LayerNorm tuning (the BASELINE.json metric); prompt = prompt tuning; full = the whole "
-                         "image encoder is trainable (both informational)")
+                         "image encoder is trainable; ret_i2t / ret_t2i = retrieval TTA, BASELINE.json configs[3] "
+                         "(all informational)")
+    ap.add_argument("--queries-per-step", type=int, default=32, help="retrieval modes: queries adapted per launch sequence")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded CPU-baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--torch-gpu-baseline", action="store_true",
@@ -445,10 +447,118 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ retrieval (config 4)
+def run_retrieval(args):
+    """BASELINE.json configs[3]: retrieval/clip_ret_policy.py, ViT-B/16 policy + ViT-L/14 reward, COCO shape
+    (5 000 images x 25 000 captions), 8 TTA steps per query, every parameter of the query's encoder tuned.
+    Informational line (the headline metric is the classification loop): queries/s and the achieved fraction of
+    the HBM roofline -- with M = 197 (or 77) rows per weight group the path is weight-bandwidth bound."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the rlcf_b200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from rlcf_b200 import _lib, engine as E, retrieval as R, synthetic as S
+    i2t = args.mode == "ret_i2t"
+    K = args.steps if args.steps is not None else 5
+    W = max(3, args.warmup if args.warmup is not None else 3)
+    Q = args.queries_per_step
+    n_gallery = 25000 if i2t else 5000
+    sd_p = S.make_state_dict("ViT-B/16", 0, dev)
+    sd_r = S.make_state_dict("ViT-L/14", 1, dev)
+    g = torch.Generator(device=dev).manual_seed(5 + rank)
+    gal_p = torch.nn.functional.normalize(torch.randn(n_gallery, 512, generator=g, device=dev), dim=-1)
+    gal_r = torch.nn.functional.normalize(torch.randn(n_gallery, 768, generator=g, device=dev), dim=-1)
+    rcfg = R.RetrievalConfig(tta_steps=8, sample_k=20 if i2t else 12, lr=1e-6)
+    if i2t:
+        eng = R.ImageQueryEngine(sd_p, gal_p, float(sd_p["logit_scale"].exp()), rcfg, Q, E.prepare_visual(sd_r), gal_r)
+        batches = [S.make_views(Q, 1, 224, 2000 + 17 * rank + i, device=dev) for i in range(2)]
+    else:
+        eng = R.TextQueryEngine(sd_p, gal_p, rcfg, Q, E.prepare_text(sd_r), gal_r)
+        batches = [S.make_tokens(Q, 49408, seed=31 + 17 * rank + i).to(dev) for i in range(2)]
+    del sd_p, sd_r
+    l0 = _lib.launch_count()
+    eng.adapt(batches[0])
+    launches_per_step = _lib.launch_count() - l0
+    step = eng.adapt
+    if not args.no_graph and i2t:
+        eng.capture(batches[0])
+        step = eng.adapt_graph
+    for i in range(W):
+        step(batches[i % 2])
+    torch.cuda.synchronize()
+    sampler = make_sampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    e0.record()
+    for i in range(K):
+        step(batches[i % 2])
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * Q * K / (ms_total / 1e3)
+    # end to end: queries from pinned host memory, score rows back to pinned host memory
+    host_in = [b.cpu().pin_memory() for b in batches]
+    host_out = torch.empty(Q, n_gallery, dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(K):
+        host_out.copy_(step(host_in[i % 2].to(dev, non_blocking=True)), non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = world * Q * K / (float(ms2.item()) / 1e3)
+    pk = peaks()
+    gbs = eng.bytes_per_query() * (value / world) / 1e9
+    if rank == 0:
+        line = {
+            "metric": "adapted retrieval queries/sec (ViT-B/16 policy, ViT-L/14 reward, 8 TTA steps, all encoder "
+                      "parameters tuned)", "value": value, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "retrieval %s, COCO shape (config 4): %d gallery candidates, K=%d, 8 steps, lr 1e-6"
+                                   % ("image->text" if i2t else "text->image", n_gallery, rcfg.sample_k),
+                       "queries_per_step": Q, "parallelism": f"dp{world} (independent queries)",
+                       "cuda_graph": bool(not args.no_graph and i2t),
+                       "l2": "per-query weights + Adam state: %.1f GB per step, far beyond L2" % (
+                           Q * eng.lay.total * 16 / 1e9)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": host_in[0].numel() * host_in[0].element_size(),
+                    "d2h_bytes_per_step": host_out.numel() * 4},
+            "gpu_launches": int(launches_per_step * K),
+            "roofline": {"bound": "hbm", "kernel": "whole step (per-query weight streaming: grouped GEMMs, wgrad, AdamW, casts)",
+                         "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                         "traffic": None, "algorithmic_bytes_per_query": eng.bytes_per_query(),
+                         "peak_source": pk["source"]},
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode in ("ret_i2t", "ret_t2i"):
+        run_retrieval(args)
     else:
         run_b200(args)
 

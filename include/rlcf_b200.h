@@ -267,6 +267,18 @@ int rlcf_scale_rows_exp(const float* in, const float* ls, int64_t ls_stride, int
 int rlcf_tied_rows_grad(const float* dx, const int64_t* tokens, int n_sets, int L, int d, float* g_tok, float* g_pos,
                         int64_t out_stride, void* stream);
 
+/* torch.optim.AdamW over EVERY parameter of a tuned encoder, one parameter vector of p_total floats per sample
+ * (TPT/tune_cls_rl.py:79-81 with custom_clip.py:477-479; retrieval/clip_ret_policy.py:235): streaming 16-byte pass,
+ * params_in / fresh_state as in rlcf_adamw_step_from, and the fp16 copy of the first n16 parameters (the GEMM weights)
+ * is written to w16 + g*w16_stride in the same pass (w16 may be NULL).  Sizes and strides are multiples of 4. */
+int rlcf_adamw_full(float* params, float* m, float* v, const float* grads, int n_sets, int64_t p_total, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int step, float loss_scale,
+                    const float* params_in, int64_t params_in_stride, int fresh_state, void* w16, int64_t w16_stride,
+                    int64_t n16, void* stream);
+/* out16[g][c][r] = in16[g][r][c] for n_sets matrices laid out set_stride elements apart (in and out share it). */
+int rlcf_transpose_f16_sets(const void* in, int rows, int cols, void* out, int n_sets, int64_t set_stride,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

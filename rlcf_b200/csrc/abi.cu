@@ -112,6 +112,9 @@ int retrieval_loss(const float*, long long, const float*, const float*, int, int
                    float*, int32_t*, float*, float*, float*, cudaStream_t);
 int dfeat_partial(const float*, const float*, int, int, int, int, float*, cudaStream_t);
 int rowdot(const float*, const float*, int, int, float, float*, long long, cudaStream_t);
+int adamw_full(float*, float*, float*, const float*, int, long long, float, float, float, float, float, int, float,
+               const float*, long long, int, __half*, long long, long long, cudaStream_t);
+int transpose_f16(const __half*, int, int, __half*, int, long long, cudaStream_t);
 int add_rows(const float*, long long, const float*, long long, int, long long, float*, cudaStream_t);
 int scale_rows_exp(const float*, const float*, long long, int, int, float*, cudaStream_t);
 int tied_rows_grad(const float*, const long long*, int, int, int, float*, float*, long long, cudaStream_t);
@@ -413,6 +416,21 @@ int rlcf_tied_rows_grad(const float* dx, const int64_t* tokens, int n_sets, int 
   if (!dx || !tokens || !g_tok || !g_pos) return set_error(RLCF_ERR_ARG, "tied_rows_grad: null pointer");
   return tied_rows_grad(dx, reinterpret_cast<const long long*>(tokens), n_sets, L, d, g_tok, g_pos, out_stride,
                         S(stream));
+}
+
+int rlcf_adamw_full(float* params, float* m, float* v, const float* grads, int n_sets, int64_t p_total, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int step, float loss_scale,
+                    const float* params_in, int64_t params_in_stride, int fresh_state, void* w16, int64_t w16_stride,
+                    int64_t n16, void* stream) {
+  if (!params || !m || !v || !grads || !params_in) return set_error(RLCF_ERR_ARG, "adamw_full: null pointer");
+  return adamw_full(params, m, v, grads, n_sets, p_total, lr, beta1, beta2, eps, weight_decay, step, loss_scale,
+                    params_in, params_in_stride, fresh_state, H(w16), w16_stride, n16, S(stream));
+}
+
+int rlcf_transpose_f16_sets(const void* in, int rows, int cols, void* out, int n_sets, int64_t set_stride,
+                            void* stream) {
+  if (!in || !out) return set_error(RLCF_ERR_ARG, "transpose_f16_sets: null pointer");
+  return transpose_f16(CH(in), rows, cols, H(out), n_sets, set_stride, S(stream));
 }
 
 }  // extern "C"

@@ -905,6 +905,122 @@ int adamw_step(float* params, float* m, float* v, const float* partials, int n_s
   return 0;
 }
 
+// Streaming AdamW for a whole encoder per sample (full tuning / retrieval TTA: 86 M parameters x n_sets): 16-byte
+// accesses, 4 independent float4 groups in flight per thread, and the fp16 GEMM copy of the first n16 parameters is
+// written in the same pass (saves re-reading the fp32 masters for the cast).  HBM-bound: 16 B read (g, p, m, v) +
+// 12 B written (p, m, v) + 2 B (fp16 copy) per parameter.
+__device__ __forceinline__ float adamw_one(float p0, float g, float& m, float& v, float lr, float b1, float b2,
+                                           float eps, float wd, float bc1, float bc2_sqrt) {
+  float w = p0 * (1.f - lr * wd);
+  m = m + (g - m) * (1.f - b1);
+  v = v * b2 + (1.f - b2) * g * g;
+  const float denom = sqrtf(v) / bc2_sqrt + eps;
+  return w - (lr / bc1) * (m / denom);
+}
+
+__global__ void __launch_bounds__(256)
+adamw_full_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ grads,
+                  long long p4, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                  float inv_scale, const float* __restrict__ p_in, long long p_in_stride, int fresh,
+                  __half* __restrict__ w16, long long w16_stride, long long n16_4) {
+  const long long set = blockIdx.y;
+  const long long base = set * p4;   // in float4 units
+  float4* P = reinterpret_cast<float4*>(p) + base;
+  float4* M = reinterpret_cast<float4*>(m) + base;
+  float4* V = reinterpret_cast<float4*>(v) + base;
+  const float4* G = reinterpret_cast<const float4*>(grads) + base;
+  const float4* PI = reinterpret_cast<const float4*>(p_in + set * p_in_stride);
+  uint2* W = w16 ? reinterpret_cast<uint2*>(w16 + set * w16_stride) : nullptr;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  constexpr int U = 4;
+  for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < p4; i0 += U * stride) {
+    float4 g[U], q[U], mm[U], vv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < p4) {
+        g[u] = __ldcs(G + i);
+        q[u] = fresh ? __ldg(PI + i) : __ldcs(PI + i);
+        if (!fresh) { mm[u] = __ldcs(M + i); vv[u] = __ldcs(V + i); }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= p4) continue;
+      if (fresh) { mm[u] = make_float4(0.f, 0.f, 0.f, 0.f); vv[u] = mm[u]; }
+      float4 w;
+      w.x = adamw_one(q[u].x, g[u].x * inv_scale, mm[u].x, vv[u].x, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+      w.y = adamw_one(q[u].y, g[u].y * inv_scale, mm[u].y, vv[u].y, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+      w.z = adamw_one(q[u].z, g[u].z * inv_scale, mm[u].z, vv[u].z, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+      w.w = adamw_one(q[u].w, g[u].w * inv_scale, mm[u].w, vv[u].w, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+      __stcs(P + i, w);
+      __stcs(M + i, mm[u]);
+      __stcs(V + i, vv[u]);
+      if (W != nullptr && i < n16_4) {
+        const __half2 h0 = __floats2half2_rn(w.x, w.y), h1 = __floats2half2_rn(w.z, w.w);
+        W[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      }
+    }
+  }
+}
+
+int adamw_full(float* params, float* m, float* v, const float* grads, int n_sets, long long p_total, float lr,
+               float b1, float b2, float eps, float wd, int step, float loss_scale, const float* params_in,
+               long long params_in_stride, int fresh, __half* w16, long long w16_stride, long long n16,
+               cudaStream_t stream) {
+  if (n_sets <= 0 || n_sets > 65535 || p_total <= 0 || step < 1) return set_error(RLCF_ERR_ARG, "adamw_full: bad shape");
+  if (p_total % 4 || params_in_stride % 4 || n16 % 4 || w16_stride % 4 || n16 > p_total)
+    return set_error(RLCF_ERR_ARG, "adamw_full: sizes and strides must be multiples of 4 elements");
+  const double bc1 = 1.0 - pow(static_cast<double>(b1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(b2), step);
+  const long long p4 = p_total / 4;
+  long long bx = (p4 + 256 * 4 - 1) / (256 * 4);
+  const long long cap = (148 * 8 + n_sets - 1) / n_sets;   // ~8 resident blocks per SM over all sets
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid(static_cast<unsigned>(bx), n_sets);
+  adamw_full_kernel<<<grid, 256, 0, stream>>>(params, m, v, grads, p4, lr, b1, b2, eps, wd, static_cast<float>(bc1),
+                                              static_cast<float>(sqrt(bc2)), 1.f / loss_scale, params_in,
+                                              params_in_stride, fresh, w16, w16_stride, n16 / 4);
+  RLCF_CHECK_LAUNCH("adamw_full");
+  return 0;
+}
+
+// out16[g][c][r] = in16[g][r][c]: transposed fp16 weight copies (dgrad B operands) from the fp16 copies the AdamW pass
+// has just written -- 2 B read + 2 B written per weight instead of 4 + 2 from the fp32 masters.
+__global__ void transpose_f16_kernel(const __half* __restrict__ in, int rows, int cols, __half* __restrict__ out,
+                                     long long set_stride) {
+  __shared__ __half tile[64][66];
+  in += blockIdx.z * set_stride;
+  out += blockIdx.z * set_stride;
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 256 threads: 32 x 8
+  for (int j = ty; j < 64; j += 8) {
+    const int r = r0 + j, c = c0 + 2 * tx;
+    __half2 val = __floats2half2_rn(0.f, 0.f);
+    if (r < rows && c < cols) val = *reinterpret_cast<const __half2*>(in + static_cast<size_t>(r) * cols + c);
+    tile[j][2 * tx] = __low2half(val);
+    tile[j][2 * tx + 1] = __high2half(val);
+  }
+  __syncthreads();
+  for (int j = ty; j < 64; j += 8) {
+    const int c = c0 + j, r = r0 + 2 * tx;
+    if (c < cols && r < rows)
+      *reinterpret_cast<__half2*>(out + static_cast<size_t>(c) * rows + r) = __halves2half2(tile[2 * tx][j], tile[2 * tx + 1][j]);
+  }
+}
+
+int transpose_f16(const __half* in, int rows, int cols, __half* out, int n_sets, long long set_stride,
+                  cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0 || rows % 2 || cols % 2 || n_sets <= 0 || n_sets > 65535)
+    return set_error(RLCF_ERR_ARG, "transpose_f16: bad shape (rows, cols even)");
+  dim3 grid((cols + 63) / 64, (rows + 63) / 64, n_sets);
+  transpose_f16_kernel<<<grid, 256, 0, stream>>>(in, rows, cols, out, set_stride);
+  RLCF_CHECK_LAUNCH("transpose_f16");
+  return 0;
+}
+
 __global__ void reset_params_kernel(const float* __restrict__ init, float* __restrict__ p, float* __restrict__ m,
                                     float* __restrict__ v, long long p_total, long long total) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;

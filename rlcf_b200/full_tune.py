@@ -140,6 +140,24 @@ def cast_weights(lay: FullLayout, rest: torch.Tensor, w16: torch.Tensor, w16t=No
             ops.transpose_cast_f16_sets(rest.view(-1)[off:], r, c, G, rest.stride(0), w16t.view(-1)[off:], w16t.stride(0))
 
 
+def transpose_weights(lay, w16: torch.Tensor, w16t: torch.Tensor):
+    """w16t[g] = per-matrix transposes of the fp16 weights w16[g] (dgrad B operands), for all samples at once."""
+    G, d = w16.shape[0], lay.d
+    for l in range(lay.nl):
+        for off, r, c in ((lay.wq[l], 3 * d, d), (lay.wo[l], d, d), (lay.wf[l], 4 * d, d), (lay.wp[l], d, 4 * d)):
+            ops.transpose_f16_sets(w16.view(-1)[off:], r, c, w16t.view(-1)[off:], G, w16.stride(0))
+
+
+def adamw_weights(lay, rest, rest_m, rest_v, grads, w16, w16t, cfg, step, params_in, params_in_stride, fresh):
+    """AdamW over every sample's non-LayerNorm parameters + refreshed fp16 GEMM copies in the same pass; the transposed
+    copies follow only when another backward will use them (w16t not None)."""
+    ops.adamw_full(rest, rest_m, rest_v, grads, rest.shape[0], rest.shape[1], cfg.lr, step, params_in, params_in_stride,
+                   fresh, w16=w16, n16=lay.p_gemm, beta1=cfg.betas[0], beta2=cfg.betas[1], eps=cfg.eps,
+                   weight_decay=cfg.weight_decay, loss_scale=cfg.loss_scale)
+    if w16t is not None:
+        transpose_weights(lay, w16, w16t)
+
+
 class WgradHook:
     """Weight / bias / embedding gradients of `n_sets` images whose rows are laid out set after set.
     grads: fp32 [n_sets, lay.total] (written, not accumulated).  dY carries the loss scale; so do the gradients."""
@@ -290,14 +308,15 @@ class FullTuneEngine:
                   loss_scale=cfg.loss_scale)
         ops.adamw_step(self.ln, self.ln_m, self.ln_v, self.partials, B, self.n_slots, P, cfg.lr, step,
                        grad_out=self.ln_grad, **kw)
-        if step == 1:   # parameters come from the shared initial copy, moments start from zero: no per-image reset
-            ops.adamw_step_from(self.rest, self.rest_m, self.rest_v, self.grads, B, 1, lay.total, cfg.lr, step,
-                                self.init_rest, 0, True, **kw)
+        # step 1: parameters come from the shared initial copy, moments start from zero -- no per-image reset.
+        # The same pass writes the fp16 copies of the updated GEMM weights; transposes only if another backward follows.
+        w16t = self.w16t if step < cfg.tta_steps else None
+        if step == 1:
+            adamw_weights(lay, self.rest, self.rest_m, self.rest_v, self.grads, self.w16, w16t, cfg, step,
+                          self.init_rest, 0, True)
         else:
-            ops.adamw_step_from(self.rest, self.rest_m, self.rest_v, self.grads, B, 1, lay.total, cfg.lr, step,
-                                self.rest, lay.total, False, **kw)
-        # fp16 copies of the updated GEMM weights (and their transposes when another backward follows)
-        cast_weights(lay, self.rest, self.w16, self.w16t if step < cfg.tta_steps else None)
+            adamw_weights(lay, self.rest, self.rest_m, self.rest_v, self.grads, self.w16, w16t, cfg, step,
+                          self.rest, lay.total, False)
 
     def tune(self, images: torch.Tensor):
         cfg, B = self.cfg, self.n_img

@@ -358,3 +358,20 @@ def tied_rows_grad(dx, tokens, n_sets, L, d, g_tok, g_pos, out_stride):
     _chk(dx, torch.float32, "dx"); _chk(tokens, torch.int64, "tokens")
     _chk(g_tok, torch.float32, "g_tok", strided=True); _chk(g_pos, torch.float32, "g_pos", strided=True)
     call("rlcf_tied_rows_grad", ptr(dx), ptr(tokens), n_sets, L, d, ptr(g_tok), ptr(g_pos), out_stride, stream())
+
+
+def adamw_full(params, m, v, grads, n_sets, p_total, lr, step, params_in, params_in_stride, fresh, w16=None, n16=0,
+               beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2, loss_scale=1.0):
+    """Streaming AdamW over whole per-sample parameter vectors [n_sets, p_total]; also writes the fp16 copy of the first
+    n16 parameters of every sample into w16 [n_sets, >= n16]."""
+    for t, nm in ((params, "params"), (m, "m"), (v, "v"), (grads, "grads")):
+        _chk(t, torch.float32, nm)
+    _chk(params_in, torch.float32, "params_in", strided=True); _chk(w16, torch.float16, "w16")
+    call("rlcf_adamw_full", ptr(params), ptr(m), ptr(v), ptr(grads), n_sets, p_total, float(lr), float(beta1),
+         float(beta2), float(eps), float(weight_decay), int(step), float(loss_scale), ptr(params_in), params_in_stride,
+         int(bool(fresh)), ptr(w16), 0 if w16 is None else w16.stride(0), n16, stream())
+
+
+def transpose_f16_sets(src, rows, cols, out, n_sets, set_stride):
+    _chk(src, torch.float16, "src", strided=True); _chk(out, torch.float16, "out", strided=True)
+    call("rlcf_transpose_f16_sets", ptr(src), rows, cols, ptr(out), n_sets, set_stride, stream())

@@ -170,13 +170,13 @@ class ImageQueryEngine:
                   loss_scale=cfg.loss_scale)
         ops.adamw_step(self.ln, self.ln_m, self.ln_v, self.partials, Q, self.n_slots, P, cfg.lr, step,
                        grad_out=self.ln_grad, **kw)
+        w16t = self.w16t if step < cfg.tta_steps else None
         if step == 1:   # masters come from the shared initial copy, moments start at zero: no per-query restore
-            ops.adamw_step_from(self.rest, self.rest_m, self.rest_v, self.grads, Q, 1, lay.total, cfg.lr, step,
-                                self.init_rest, 0, True, **kw)
+            FT.adamw_weights(lay, self.rest, self.rest_m, self.rest_v, self.grads, self.w16, w16t, cfg, step,
+                             self.init_rest, 0, True)
         else:
-            ops.adamw_step_from(self.rest, self.rest_m, self.rest_v, self.grads, Q, 1, lay.total, cfg.lr, step,
-                                self.rest, lay.total, False, **kw)
-        FT.cast_weights(lay, self.rest, self.w16, self.w16t if step < cfg.tta_steps else None)
+            FT.adamw_weights(lay, self.rest, self.rest_m, self.rest_v, self.grads, self.w16, w16t, cfg, step,
+                             self.rest, lay.total, False)
 
     def tune(self, images: torch.Tensor):
         """tune_image for n_query images [Q,3,H,W] at once.  Leaves the adapted parameters in self.ln / self.rest."""
@@ -453,9 +453,8 @@ class TextQueryEngine:
                   loss_scale=cfg.loss_scale)
         ops.adamw_step(self.ln, self.ln_m, self.ln_v, self.partials, Q, self.n_slots, P, cfg.lr, step,
                        grad_out=self.ln_grad, **kw)
-        ops.adamw_step_from(self.rest, self.rest_m, self.rest_v, self.grads, Q, 1, lay.total, cfg.lr, step, self.rest,
-                            lay.total, step == 1, **kw)
-        FT.cast_weights(lay, self.rest, self.w16, self.w16t if step < cfg.tta_steps else None)
+        FT.adamw_weights(lay, self.rest, self.rest_m, self.rest_v, self.grads, self.w16,
+                         self.w16t if step < cfg.tta_steps else None, cfg, step, self.rest, lay.total, step == 1)
 
     def tune(self, tokens: torch.Tensor):
         """tune_text for n_query tokenised captions [Q, 77] (int64) at once."""

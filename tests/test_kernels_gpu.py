@@ -375,6 +375,39 @@ def test_adamw_matches_torch():
             assert (params[s] - refs[s].data).abs().max().item() < 2e-6
 
 
+def test_adamw_full_matches_torch_and_writes_fp16_copies():
+    """Streaming whole-encoder AdamW (rlcf_adamw_full): torch.optim.AdamW per sample, first step from a shared initial
+    vector with empty moments, later steps in place; the fp16 copy of the first n16 parameters comes with it."""
+    torch.manual_seed(15)
+    n_sets, P, n16 = 3, 4 * 1031, 4 * 500
+    init = torch.randn(P, device=_dev())
+    params = torch.full((n_sets, P), 7.0, device=_dev()); m = torch.full_like(params, 3.0); v = torch.full_like(params, 3.0)
+    w16 = torch.zeros(n_sets, n16 + 8, dtype=torch.float16, device=_dev())
+    refs = [torch.nn.Parameter(init.clone()) for _ in range(n_sets)]
+    opts = [torch.optim.AdamW([r], lr=1e-3, eps=1e-6, weight_decay=5e-4) for r in refs]
+    for step in (1, 2, 3):
+        grads = torch.randn(n_sets, P, device=_dev()) * 8.0
+        if step == 1:
+            ops.adamw_full(params, m, v, grads, n_sets, P, 1e-3, step, init, 0, True, w16=w16, n16=n16, eps=1e-6,
+                           weight_decay=5e-4, loss_scale=8.0)
+        else:
+            ops.adamw_full(params, m, v, grads, n_sets, P, 1e-3, step, params, P, False, w16=w16, n16=n16, eps=1e-6,
+                           weight_decay=5e-4, loss_scale=8.0)
+        for s_ in range(n_sets):
+            refs[s_].grad = grads[s_] / 8.0
+            opts[s_].step()
+            assert (params[s_] - refs[s_].data).abs().max().item() < 2e-6
+        assert torch.equal(w16[:, :n16], params[:, :n16].half()) and w16[:, n16:].abs().max().item() == 0
+    # transposed fp16 copies of several per-sample matrices in one launch
+    rows, cols = 70, 50
+    src = torch.randn(n_sets, 5000, device=_dev()).half()
+    out = torch.zeros_like(src)
+    ops.transpose_f16_sets(src.view(-1)[100:], rows, cols, out.view(-1)[100:], n_sets, src.stride(0))
+    for s_ in range(n_sets):
+        assert torch.equal(out[s_, 100:100 + rows * cols].view(cols, rows), src[s_, 100:100 + rows * cols].view(rows, cols).t())
+    assert out[:, :100].abs().max().item() == 0 and out[:, 100 + rows * cols:].abs().max().item() == 0
+
+
 def test_cast_helpers():
     torch.manual_seed(6)
     w = torch.randn(70, 50, device=_dev())
