@@ -207,3 +207,57 @@ def test_retrieval_loss_kernel_large_gallery():
     ops.dfeat_partial(dl, gal, part)
     want = dl.double() @ gal.double()
     assert (part.double().sum(1) - want).abs().max() <= 1e-4 * want.abs().max()
+
+
+class _Args:
+    multiple_reward_models = 0
+    reward_amplify = 0
+    reward_process = 1
+    process_batch = 0
+    weight_decay = 5e-4
+
+
+class _Dataset:
+    pass
+
+
+@pytest.mark.parametrize("name", ["ret_i2t_tiny_recipe", "ret_t2i_tiny_recipe", "ret_i2t_tiny_3step"])
+def test_driver_reproduces_reference_score_matrix(name):
+    """CLIPRet_TTA / CLIPRewards / test_time_tune / report_metrics (the reference-facing surface) against the score
+    matrix and the recall metrics the reference produced for the same synthetic dataset."""
+    from rlcf_b200 import clip_ret_policy as C
+    z, cfg = load_case(name)
+    i2t = cfg["task"] == "image2text"
+    sd_p, sd_r, images, tokens, rcfg, gal_p, gal_r = retrieval_setup(cfg)
+    args = _Args()
+    args.tta_steps, args.lr, args.sample_k = cfg["steps"], cfg["lr"], cfg["K"]
+    model = C.CLIPRet_TTA(DEV, only_visual=i2t, momentum_update=rcfg.momentum_update, update_freq=rcfg.update_freq,
+                          update_w=rcfg.update_w, momentum=rcfg.momentum, state_dict=sd_p)
+    reward = C.CLIPRewards(DEV, sample_k=cfg["K"], state_dict=sd_r)
+    ds = _Dataset()
+    ds.text, ds.image_tensor = tokens, images
+    s_i2t, s_t2i = C.test_time_tune(ds, DEV, model, reward, args=args, queries_per_step=3)
+    got = s_i2t if i2t else s_t2i
+    ref = z["score_matrix"]
+    assert got.shape == ref.shape
+    other = s_t2i if i2t else s_i2t
+    assert (other == -100.0).all()                       # the direction that was not run (clip_ret_policy.py:147-148)
+    # gallery features through the CUDA towers equal the reference's
+    feat = (model.text_features if i2t else model.image_features).cpu().numpy()
+    assert np.abs(feat - z["gallery_policy"]).max() < 2e-3
+    # un-adapted rows give the size of what adaptation changes; tolerance as in check_query
+    with torch.no_grad():
+        q_feat = O.retrieval_features(sd_p, images=images[:ref.shape[0]]) if i2t else \
+            O.retrieval_features(sd_p, tokens=tokens[:ref.shape[0]])
+        row0 = (sd_p["logit_scale"].exp() * q_feat @ gal_p.t()).numpy()
+    delta = np.abs(ref - row0).max()
+    err = np.abs(got - ref).max()
+    print(f"{name}: driver score matrix err {err / np.abs(ref).max():.2e} (adaptation delta {delta / np.abs(ref).max():.2e})")
+    assert err <= ROW_TOL * np.abs(ref).max() + 0.3 * delta
+    n_img, n_txt = images.shape[0], tokens.shape[0]
+    if n_txt >= n_img:   # every image owns at least one caption: the recall metrics are defined
+        txt2img = [t % n_img for t in range(n_txt)]
+        img2txt = [[t for t in range(n_txt) if t % n_img == i] for i in range(n_img)]
+        m = C.report_metrics(s_i2t, s_t2i, txt2img, img2txt)
+        assert set(m) == set(z["metrics_keys"].tolist())
+        assert m["img_r1"] == 0.0 or not i2t     # the t2i matrix is all -100 in an image->text run: rank by index only
