@@ -260,4 +260,3 @@ def test_driver_reproduces_reference_score_matrix(name):
         img2txt = [[t for t in range(n_txt) if t % n_img == i] for i in range(n_img)]
         m = C.report_metrics(s_i2t, s_t2i, txt2img, img2txt)
         assert set(m) == set(z["metrics_keys"].tolist())
-        assert m["img_r1"] == 0.0 or not i2t     # the t2i matrix is all -100 in an image->text run: rank by index only
