@@ -124,6 +124,8 @@ def layernorm_bwd(dy, x, gamma, rows_per_set, n_sets, d, partials, n_slots, p_to
                   param_stride=0, lddy=None, ldx=None, lddx=None, eps=1e-5, dx16=None):
     _chk(x, torch.float32, "x"); _chk(partials, torch.float32, "partials"); _chk(dx, torch.float32, "dx")
     _chk(dx16, torch.float16, "dx16")
+    if partials is not None and partials.numel() < n_sets * n_slots * p_total:
+        raise _lib.RlcfError(f"layernorm_bwd: partials holds {partials.numel()} floats, {n_sets}x{n_slots}x{p_total} needed")
     is32 = dy.dtype == torch.float32
     call("rlcf_layernorm_bwd", ptr(dy), int(is32), d if lddy is None else lddy, ptr(x), d if ldx is None else ldx,
          ptr(gamma), param_stride, rows_per_set, n_sets, d, eps, ptr(dx), d if lddx is None else lddx,
@@ -196,6 +198,8 @@ def head_bwd_ex(dlogits, dl_strides, x, gamma, proj, other_feat, other_set_strid
                 p_total=0, p_off=0, eps=1e-5, beta=None, y_out=None, df_out=None, proj_stride=0):
     _chk(dlogits, torch.float32, "dlogits"); _chk(x, torch.float32, "x"); _chk(dres, torch.float32, "dres")
     _chk(other_feat, torch.float32, "other_feat"); _chk(row_idx, torch.int32, "row_idx")
+    if partials is not None and partials.numel() < n_sets * n_slots * p_total:
+        raise _lib.RlcfError(f"head_bwd: partials holds {partials.numel()} floats, {n_sets}x{n_slots}x{p_total} needed")
     if proj_stride:
         call("rlcf_head_bwd_sets", ptr(dlogits), dl_strides[0], dl_strides[1], dl_strides[2], ptr(x), ptr(row_idx),
              row_stride, ptr(gamma), param_stride, ptr(proj), proj_stride, ptr(other_feat), other_set_stride,
@@ -270,6 +274,8 @@ def adamw_step(params, m, v, partials, n_sets, n_slots, p_total, lr, step, beta1
                weight_decay=1e-2, loss_scale=1.0, grad_out=None):
     for t, nm in ((params, "params"), (m, "m"), (v, "v"), (partials, "partials"), (grad_out, "grad_out")):
         _chk(t, torch.float32, nm)
+    if partials.numel() < n_sets * n_slots * p_total or params.numel() < n_sets * p_total:
+        raise _lib.RlcfError(f"adamw_step: buffers too small for {n_sets} sets x {n_slots} slots x {p_total} parameters")
     call("rlcf_adamw_step", ptr(params), ptr(m), ptr(v), ptr(partials), n_sets, n_slots, p_total, float(lr),
          float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(loss_scale), ptr(grad_out),
          stream())
