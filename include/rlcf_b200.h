@@ -279,6 +279,26 @@ int rlcf_adamw_full(float* params, float* m, float* v, const float* grads, int n
 int rlcf_transpose_f16_sets(const void* in, int rows, int cols, void* out, int n_sets, int64_t set_stride,
                             void* stream);
 
+/* ---- on-device view generation (TPT/data/datautils.py:76-128, TPT/data/augmix_ops.py) --------------------------
+ * rlcf_resample_u8: n_views crops of ONE decoded uint8 image src [H,W,3], each resized to [out_h,out_w,3] exactly as
+ * PIL's Image.resize does (libImaging/Resample.c: separable, 22-bit fixed-point taps, uint8 rounding after each pass).
+ * Replaces transforms.Resize + CenterCrop (view 0) and RandomResizedCrop + RandomHorizontalFlip (datautils.py:89-92).
+ * The host supplies what Pillow precomputes per call: hdr [n_views,8] int32 = {x0, y0, row_first, n_rows, flip,0,0,0}
+ * (crop origin, first source row below y0 that is needed and how many), hb / vb [n_views,out,2] = (first tap, tap
+ * count) and hk / vk [n_views,out,ks] = taps.  tmp: uint8 scratch [n_views,tmp_rows,out_w,3], tmp_rows >= max n_rows. */
+int rlcf_resample_u8(const uint8_t* src, int H, int W, int n_views, const int32_t* hdr, const int32_t* hb,
+                     const int32_t* hk, int ks_h, const int32_t* vb, const int32_t* vk, int ks_v, int out_h, int out_w,
+                     uint8_t* tmp, int tmp_rows, uint8_t* out, void* stream);
+/* AugMix (datautils.py:95-111) on n_views 224x224 uint8 crops x_orig [n_views,224,224,3]: per view up to 3 chains of
+ * up to 3 operations -- type 0 autocontrast, 1 equalize, 2 posterize(param = bits), 3 solarize(param = threshold),
+ * 4 affine with BILINEAR resampling (rotate / shear / translate; coefficients in mats) -- ToTensor + Normalize and
+ * the blend m*x + (1-m)*sum_i w_i*aug_i, all with PIL's / torch's arithmetic.  vflag[v] = 0 emits the plain
+ * normalised view.  wts [n_views,4] = (w0,w1,w2,m), omm [n_views] = float32(1-m), n_ops [n_views,3],
+ * ops [n_views,3,3,2] int32, mats [n_views,3,3,6] double, out fp32 [n_views,3,224,224]. */
+int rlcf_augmix_views(const uint8_t* x_orig, int n_views, const int32_t* vflag, const float* wts, const float* omm,
+                      const int32_t* n_ops, const int32_t* ops, const double* mats, float mean0, float mean1,
+                      float mean2, float std0, float std1, float std2, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

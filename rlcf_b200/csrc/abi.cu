@@ -115,6 +115,10 @@ int rowdot(const float*, const float*, int, int, float, float*, long long, cudaS
 int adamw_full(float*, float*, float*, const float*, int, long long, float, float, float, float, float, int, float,
                const float*, long long, int, __half*, long long, long long, cudaStream_t);
 int transpose_f16(const __half*, int, int, __half*, int, long long, cudaStream_t);
+int resample_u8(const uint8_t*, int, int, int, const int*, const int*, const int*, int, const int*, const int*, int, int,
+                int, uint8_t*, int, uint8_t*, cudaStream_t);
+int augmix_views(const uint8_t*, int, const int*, const float*, const float*, const int*, const int*, const double*,
+                 const float*, const float*, float*, cudaStream_t);
 int add_rows(const float*, long long, const float*, long long, int, long long, float*, cudaStream_t);
 int scale_rows_exp(const float*, const float*, long long, int, int, float*, cudaStream_t);
 int tied_rows_grad(const float*, const long long*, int, int, int, float*, float*, long long, cudaStream_t);
@@ -431,6 +435,22 @@ int rlcf_transpose_f16_sets(const void* in, int rows, int cols, void* out, int n
                             void* stream) {
   if (!in || !out) return set_error(RLCF_ERR_ARG, "transpose_f16_sets: null pointer");
   return transpose_f16(CH(in), rows, cols, H(out), n_sets, set_stride, S(stream));
+}
+
+int rlcf_resample_u8(const uint8_t* src, int H_, int W, int n_views, const int32_t* hdr, const int32_t* hb,
+                     const int32_t* hk, int ks_h, const int32_t* vb, const int32_t* vk, int ks_v, int out_h, int out_w,
+                     uint8_t* tmp, int tmp_rows, uint8_t* out, void* stream) {
+  if (!src || !hdr || !hb || !hk || !vb || !vk || !tmp || !out) return set_error(RLCF_ERR_ARG, "resample_u8: null pointer");
+  return resample_u8(src, H_, W, n_views, hdr, hb, hk, ks_h, vb, vk, ks_v, out_h, out_w, tmp, tmp_rows, out, S(stream));
+}
+
+int rlcf_augmix_views(const uint8_t* x_orig, int n_views, const int32_t* vflag, const float* wts, const float* omm,
+                      const int32_t* n_ops, const int32_t* ops, const double* mats, float mean0, float mean1,
+                      float mean2, float std0, float std1, float std2, float* out, void* stream) {
+  if (!x_orig || !vflag || !wts || !omm || !n_ops || !ops || !mats || !out)
+    return set_error(RLCF_ERR_ARG, "augmix_views: null pointer");
+  const float mean[3] = {mean0, mean1, mean2}, stdv[3] = {std0, std1, std2};
+  return augmix_views(x_orig, n_views, vflag, wts, omm, n_ops, ops, mats, mean, stdv, out, S(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,273 @@
+"""View generation with the reference's surface (TPT/data/datautils.py:76-128) executed on the GPU.
+
+The reference builds, per test image, the un-augmented view (Resize(224, BICUBIC) + CenterCrop) and `n_views`
+augmented ones (RandomResizedCrop(224) + RandomHorizontalFlip, then AugMix chains for the fine-grained datasets,
+tune_cls_rl.py:102-110) with PIL on the host.  Here the host only draws the random decisions -- from the same global
+torch / numpy generators, in the same order, so a seeded run produces the reference's views -- and precomputes what
+Pillow precomputes per call (resampling taps, affine coefficients); the pixels are produced by
+librlcf_b200.so (csrc/augment_kernels.cu) from ONE upload of the decoded uint8 image.
+
+    aug = AugMixAugmenter(None, None, n_views=63, augmix=False)     # same constructor as the reference
+    views = aug(pil_image)            # list of 64 device tensors [3,224,224] (views of one [64,3,224,224] tensor)
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import RlcfError
+
+MEAN = (0.48145466, 0.4578275, 0.40821073)      # tune_cls_rl.py:92-93
+STD = (0.26862954, 0.26130258, 0.27577711)
+OUT = 224
+PRECISION_BITS = 32 - 8 - 2                      # Pillow, libImaging/Resample.c
+
+OP_AUTOCONTRAST, OP_EQUALIZE, OP_POSTERIZE, OP_SOLARIZE, OP_AFFINE = range(5)
+# order of augmix_ops.augmentations (augmix_ops.py:141-144)
+AUG_NAMES = ("autocontrast", "equalize", "posterize", "rotate", "solarize", "shear_x", "shear_y", "translate_x",
+             "translate_y")
+
+
+# ------------------------------------------------------------------------------------------------ Pillow's resampling taps
+def _bilinear(x):
+    x = np.abs(x)
+    return np.where(x < 1.0, 1.0 - x, 0.0)
+
+
+def _bicubic(x):
+    a = -0.5
+    x = np.abs(x)
+    return np.where(x < 1.0, ((a + 2.0) * x - (a + 3.0)) * x * x + 1,
+                    np.where(x < 2.0, (((x - 5) * x + 8) * x - 4) * a, 0.0))
+
+
+FILTERS = {"bilinear": (_bilinear, 1.0), "bicubic": (_bicubic, 2.0)}
+
+
+def resample_taps(in_size: int, out_size: int, filt: str, out_lo: int = 0, out_n: int | None = None):
+    """precompute_coeffs + normalize_coeffs_8bpc (libImaging/Resample.c) for resizing `in_size` samples to `out_size`,
+    restricted to outputs [out_lo, out_lo + out_n).  Returns (bounds int32 [out_n,2] = (first tap, count),
+    taps int32 [out_n, ksize]).  Same double-precision operation order as the C source; the taps of one output are
+    accumulated sequentially."""
+    fn, support0 = FILTERS[filt]
+    out_n = out_size if out_n is None else out_n
+    scale = filterscale = float(np.float32(in_size) - np.float32(0)) / out_size
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = support0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    xx = np.arange(out_lo, out_lo + out_n, dtype=np.float64)
+    center = 0.0 + (xx + 0.5) * scale
+    ss = 1.0 / filterscale
+    xmin = np.maximum((center - support + 0.5).astype(np.int64), 0)       # (int) truncates toward zero, then clamp
+    xmax = np.minimum((center + support + 0.5).astype(np.int64), in_size) - xmin
+    k = np.zeros((out_n, ksize), dtype=np.float64)
+    ww = np.zeros(out_n, dtype=np.float64)
+    for x in range(ksize):
+        w = np.where(x < xmax, fn((x + xmin - center + 0.5) * ss), 0.0)
+        k[:, x] = w
+        ww = ww + w
+    nz = ww != 0.0
+    k[nz] = k[nz] / ww[nz, None]
+    k[np.arange(ksize)[None, :] >= xmax[:, None]] = 0.0
+    fixed = np.where(k < 0, -0.5 + k * (1 << PRECISION_BITS), 0.5 + k * (1 << PRECISION_BITS)).astype(np.int64)
+    bounds = np.stack([xmin, xmax], axis=1).astype(np.int32)
+    return bounds, fixed.astype(np.int32)
+
+
+# ------------------------------------------------------------------------------------------------ the random plan
+@dataclass
+class ViewPlan:
+    """Everything the kernels need for the views of one image (host numpy arrays)."""
+    hdr: np.ndarray      # int32 [V,8]   x0, y0, row_first, n_rows, flip
+    hb: np.ndarray       # int32 [V,224,2]
+    hk: np.ndarray       # int32 [V,224,ks_h]
+    vb: np.ndarray       # int32 [V,224,2]
+    vk: np.ndarray       # int32 [V,224,ks_v]
+    vflag: np.ndarray    # int32 [V]     1 = AugMix blend, 0 = plain normalised view
+    wts: np.ndarray      # float32 [V,4] w0, w1, w2, m
+    omm: np.ndarray      # float32 [V]   float32(1 - m)
+    n_ops: np.ndarray    # int32 [V,3]
+    ops: np.ndarray      # int32 [V,3,3,2]
+    mats: np.ndarray     # float64 [V,3,3,6]
+    tmp_rows: int
+
+
+def _pad_taps(taps, ks):
+    out = np.zeros((len(taps), OUT, ks), dtype=np.int32)
+    for i, t in enumerate(taps):
+        out[i, :, :t.shape[1]] = t
+    return out
+
+
+def _crop_tables(in_w, in_h, filt, x_lo=0, y_lo=0, out_w=OUT, out_h=OUT, res_w=OUT, res_h=OUT):
+    """Taps of one view: the source region (in_w x in_h) is resized to (res_w x res_h) and the window of OUT x OUT
+    outputs starting at (x_lo, y_lo) is kept."""
+    hb, hk = resample_taps(in_w, res_w, filt, x_lo, out_w)
+    vb, vk = resample_taps(in_h, res_h, filt, y_lo, out_h)
+    row_first = int(vb[0, 0])
+    row_last = int(vb[-1, 0] + vb[-1, 1])
+    vb = vb.copy()
+    vb[:, 0] -= row_first
+    return hb, hk, vb, vk, row_first, row_last - row_first
+
+
+def _rotate_matrix(degrees: int):
+    """Image.rotate(angle, BILINEAR) on a 224 x 224 image (PIL/Image.py): the AFFINE coefficients it hands to
+    Image.transform, or None when the fast path returns a copy."""
+    angle = degrees % 360.0
+    if angle == 0:
+        return None
+    w = h = OUT
+    cx, cy = w / 2, h / 2
+    a = -math.radians(angle)
+    m = [round(math.cos(a), 15), round(math.sin(a), 15), 0.0, round(-math.sin(a), 15), round(math.cos(a), 15), 0.0]
+    m[2] = m[0] * (-cx) + m[1] * (-cy) + m[2]
+    m[5] = m[3] * (-cx) + m[4] * (-cy) + m[5]
+    m[2] += cx
+    m[5] += cy
+    return m
+
+
+def _sample_op(name: str, severity):
+    """Draws one operation's parameters exactly as augmix_ops.py:44-107 does and returns (type, int param, matrix)."""
+    if name == "autocontrast":
+        return OP_AUTOCONTRAST, 0, None
+    if name == "equalize":
+        return OP_EQUALIZE, 0, None
+    level = np.random.uniform(low=0.1, high=severity)                    # sample_level
+    if name == "posterize":
+        return OP_POSTERIZE, 4 - int(level * 4 / 10), None
+    if name == "solarize":
+        return OP_SOLARIZE, 256 - int(level * 256 / 10), None
+    if name == "rotate":
+        degrees = int(level * 30 / 10)
+        if np.random.uniform() > 0.5:
+            degrees = -degrees
+        m = _rotate_matrix(degrees)
+        return (OP_AFFINE, 0, m) if m is not None else (-1, 0, None)
+    if name in ("shear_x", "shear_y"):
+        lv = float(level) * 0.3 / 10.
+        if np.random.uniform() > 0.5:
+            lv = -lv
+        return OP_AFFINE, 0, ([1, lv, 0, 0, 1, 0] if name == "shear_x" else [1, 0, 0, lv, 1, 0])
+    if name in ("translate_x", "translate_y"):
+        lv = int(level * (OUT / 3) / 10)
+        if np.random.random() > 0.5:
+            lv = -lv
+        return OP_AFFINE, 0, ([1, 0, lv, 0, 1, 0] if name == "translate_x" else [1, 0, 0, 0, 1, lv])
+    raise KeyError(name)
+
+
+def sample_plan(img_w: int, img_h: int, n_views: int, augmix: bool, severity: int = 1) -> ViewPlan:
+    """The random decisions of AugMixAugmenter.__call__ (datautils.py:123-126) for one image of img_w x img_h pixels,
+    drawn from the global torch / numpy generators in the reference's order, plus the derived tables."""
+    from torchvision.transforms import RandomResizedCrop
+    V = n_views + 1
+    hdr = np.zeros((V, 8), dtype=np.int32)
+    hbs, hks, vbs, vks = [], [], [], []
+    vflag = np.zeros(V, dtype=np.int32)
+    wts = np.zeros((V, 4), dtype=np.float32)
+    omm = np.zeros(V, dtype=np.float32)
+    n_ops = np.zeros((V, 3), dtype=np.int32)
+    op_codes = np.zeros((V, 3, 3, 2), dtype=np.int32)
+    mats = np.zeros((V, 3, 3, 6), dtype=np.float64)
+    tmp_rows = 1
+    # view 0: transforms.Resize(224, BICUBIC) + CenterCrop(224)            (tune_cls_rl.py:103-105)
+    if img_w <= img_h:
+        new_w, new_h = OUT, int(OUT * img_h / img_w)
+    else:
+        new_w, new_h = int(OUT * img_w / img_h), OUT
+    top, left = int(round((new_h - OUT) / 2.0)), int(round((new_w - OUT) / 2.0))
+    hb, hk, vb, vk, rf, nr = _crop_tables(img_w, img_h, "bicubic", left, top, res_w=new_w, res_h=new_h)
+    hdr[0, :5] = (0, 0, rf, nr, 0)
+    hbs.append(hb); hks.append(hk); vbs.append(vb); vks.append(vk)
+    tmp_rows = max(tmp_rows, nr)
+    dummy = torch.empty(3, img_h, img_w, dtype=torch.uint8)
+    for v in range(1, V):
+        # preaugment: RandomResizedCrop(224) + RandomHorizontalFlip           (datautils.py:89-92)
+        i, j, h, w = RandomResizedCrop.get_params(dummy, scale=(0.08, 1.0), ratio=(3.0 / 4.0, 4.0 / 3.0))
+        flip = bool(torch.rand(1) < 0.5)
+        hb, hk, vb, vk, rf, nr = _crop_tables(w, h, "bilinear")
+        hdr[v, :5] = (j, i, rf, nr, int(flip))
+        hbs.append(hb); hks.append(hk); vbs.append(vb); vks.append(vk)
+        tmp_rows = max(tmp_rows, nr)
+        if not augmix:
+            continue
+        # augmix()                                                            (datautils.py:95-111)
+        vflag[v] = 1
+        ws = np.float32(np.random.dirichlet([1.0, 1.0, 1.0]))
+        m = np.float32(np.random.beta(1.0, 1.0))
+        wts[v, :3], wts[v, 3] = ws, m
+        omm[v] = 1 - m
+        for c in range(3):
+            depth = np.random.randint(1, 4)
+            k = 0
+            for _ in range(depth):
+                name = AUG_NAMES[np.random.choice(len(AUG_NAMES))]
+                t, p, mat = _sample_op(name, severity)
+                if t < 0:          # rotate by 0 degrees: Image.rotate returns a copy
+                    continue
+                op_codes[v, c, k] = (t, p)
+                if mat is not None:
+                    mats[v, c, k] = mat
+                k += 1
+            n_ops[v, c] = k
+    ks_h, ks_v = max(t.shape[1] for t in hks), max(t.shape[1] for t in vks)
+    return ViewPlan(hdr=hdr, hb=np.stack(hbs), hk=_pad_taps(hks, ks_h), vb=np.stack(vbs), vk=_pad_taps(vks, ks_v),
+                    vflag=vflag, wts=wts, omm=omm, n_ops=n_ops, ops=op_codes, mats=mats, tmp_rows=tmp_rows)
+
+
+# ------------------------------------------------------------------------------------------------ device execution
+def _to_u8_hwc(x) -> torch.Tensor:
+    """PIL image / numpy array / tensor -> contiguous uint8 [H,W,3] (host)."""
+    if isinstance(x, torch.Tensor):
+        t = x
+    elif isinstance(x, np.ndarray):
+        t = torch.from_numpy(x)
+    else:   # PIL
+        t = torch.from_numpy(np.asarray(x.convert("RGB")).copy())
+    if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] != 3:
+        raise RlcfError(f"expected a uint8 [H,W,3] image, got {t.dtype} {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def run_plan(image_u8: torch.Tensor, plan: ViewPlan, device) -> torch.Tensor:
+    """Executes a ViewPlan on `device`: uint8 [H,W,3] image -> fp32 views [V,3,224,224]."""
+    dev = torch.device(device)
+    src = image_u8.to(dev, non_blocking=True)
+    V = plan.hdr.shape[0]
+
+    def d(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+    tmp = torch.empty(V, plan.tmp_rows, OUT, 3, dtype=torch.uint8, device=dev)
+    x_orig = torch.empty(V, OUT, OUT, 3, dtype=torch.uint8, device=dev)
+    ops.resample_u8(src, d(plan.hdr), d(plan.hb), d(plan.hk), d(plan.vb), d(plan.vk), OUT, OUT, tmp, x_orig)
+    out = torch.empty(V, 3, OUT, OUT, dtype=torch.float32, device=dev)
+    ops.augmix_views(x_orig, d(plan.vflag), d(plan.wts), d(plan.omm), d(plan.n_ops), d(plan.ops), d(plan.mats), MEAN, STD,
+                     out)
+    return out
+
+
+class AugMixAugmenter:
+    """datautils.AugMixAugmenter (datautils.py:114-128) on the GPU.  `base_transform` / `preprocess` are accepted for
+    signature compatibility; the fixed pipeline of tune_cls_rl.py:102-108 (Resize 224 bicubic + CenterCrop, ToTensor +
+    CLIP normalisation) is what the kernels implement.  hard_aug (BYOL-style colour jitter) is not supported."""
+
+    def __init__(self, base_transform=None, preprocess=None, n_views=2, augmix=False, severity=1, hard_aug=False,
+                 device="cuda"):
+        if hard_aug:
+            raise NotImplementedError("hard_aug=True (ColorJitter / GaussianBlur pre-augmentation) is out of scope")
+        self.n_views, self.augmix, self.severity, self.device = n_views, bool(augmix), severity, device
+
+    def views(self, x) -> torch.Tensor:
+        img = _to_u8_hwc(x)
+        plan = sample_plan(img.shape[1], img.shape[0], self.n_views, self.augmix, self.severity)
+        return run_plan(img, plan, self.device)
+
+    def __call__(self, x):
+        return list(self.views(x))

@@ -381,3 +381,29 @@ def adamw_full(params, m, v, grads, n_sets, p_total, lr, step, params_in, params
 def transpose_f16_sets(src, rows, cols, out, n_sets, set_stride):
     _chk(src, torch.float16, "src", strided=True); _chk(out, torch.float16, "out", strided=True)
     call("rlcf_transpose_f16_sets", ptr(src), rows, cols, ptr(out), n_sets, set_stride, stream())
+
+
+def resample_u8(src, hdr, hb, hk, vb, vk, out_h, out_w, tmp, out):
+    """PIL-exact crops + resizes of one uint8 HWC image (see rlcf_resample_u8); all plan tensors int32 on the device."""
+    _chk(src, torch.uint8, "src"); _chk(tmp, torch.uint8, "tmp"); _chk(out, torch.uint8, "out")
+    for t, nm in ((hdr, "hdr"), (hb, "hb"), (hk, "hk"), (vb, "vb"), (vk, "vk")):
+        _chk(t, torch.int32, nm)
+    H, W, _ = src.shape
+    V = hdr.shape[0]
+    if tuple(out.shape) != (V, out_h, out_w, 3) or tmp.shape[0] < V or tuple(tmp.shape[2:]) != (out_w, 3):
+        raise _lib.RlcfError("resample_u8: out must be [V, out_h, out_w, 3] and tmp [V, rows, out_w, 3]")
+    call("rlcf_resample_u8", ptr(src), H, W, V, ptr(hdr), ptr(hb), ptr(hk), hk.shape[-1], ptr(vb), ptr(vk), vk.shape[-1],
+         out_h, out_w, ptr(tmp), tmp.shape[1], ptr(out), stream())
+    return out
+
+
+def augmix_views(x_orig, vflag, wts, omm, n_ops, op_codes, mats, mean, std, out):
+    _chk(x_orig, torch.uint8, "x_orig"); _chk(vflag, torch.int32, "vflag"); _chk(wts, torch.float32, "wts")
+    _chk(omm, torch.float32, "omm"); _chk(n_ops, torch.int32, "n_ops"); _chk(op_codes, torch.int32, "ops")
+    _chk(mats, torch.float64, "mats"); _chk(out, torch.float32, "out")
+    V = x_orig.shape[0]
+    if tuple(x_orig.shape[1:]) != (224, 224, 3) or tuple(out.shape) != (V, 3, 224, 224):
+        raise _lib.RlcfError("augmix_views: x_orig must be [V,224,224,3] uint8 and out [V,3,224,224] fp32")
+    call("rlcf_augmix_views", ptr(x_orig), V, ptr(vflag), ptr(wts), ptr(omm), ptr(n_ops), ptr(op_codes), ptr(mats),
+         float(mean[0]), float(mean[1]), float(mean[2]), float(std[0]), float(std[1]), float(std[2]), ptr(out), stream())
+    return out

@@ -1,0 +1,55 @@
+"""On-device view generation (rlcf_b200/datautils.py + csrc/augment_kernels.cu through the C ABI) against the PIL
+oracle: integer / byte work, so the bar is bit-exact -- both the uint8 crops and the final fp32 views."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import augmix_oracle as A
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "augmix_ref.json")
+with open(GOLDEN) as f:
+    CASES = json.load(f)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_views_are_bit_exact_with_the_reference_pipeline(name):
+    from rlcf_b200 import datautils as D
+    c = CASES[name]
+    img = A.synthetic_image(c["h"], c["w"], c["seed"])
+    torch.manual_seed(c["seed"]); np.random.seed(c["seed"])
+    ref = A.augmix_views(img, c["n_views"], bool(c["augmix"]))
+    torch.manual_seed(c["seed"]); np.random.seed(c["seed"])
+    aug = D.AugMixAugmenter(None, None, n_views=c["n_views"], augmix=bool(c["augmix"]), device=DEV)
+    views = aug(img)
+    assert isinstance(views, list) and len(views) == c["n_views"] + 1 and views[0].is_cuda
+    got = torch.stack(views).cpu()
+    bad = [i for i in range(got.shape[0]) if not torch.equal(got[i], ref[i])]
+    assert not bad, f"views {bad} differ from the reference pipeline; max |diff| {(got - ref).abs().max():.3e}"
+    import hashlib
+    assert hashlib.sha256(got.contiguous().numpy().tobytes()).hexdigest() == c["sha256"]   # the reference's own digest
+
+
+def test_sixty_four_views_feed_the_engine_shape():
+    """The shape the hot path consumes: 1 + 63 views of one ImageNet-sized image, one small upload."""
+    from rlcf_b200 import datautils as D
+    img = A.synthetic_image(375, 500, 21)
+    torch.manual_seed(1); np.random.seed(1)
+    ref = A.augmix_views(img, 63, False)
+    torch.manual_seed(1); np.random.seed(1)
+    v = D.AugMixAugmenter(n_views=63, augmix=False, device=DEV).views(img)
+    assert tuple(v.shape) == (64, 3, 224, 224) and v.dtype == torch.float32
+    assert torch.equal(v.cpu(), ref)
+
+
+def test_bad_inputs_are_rejected():
+    from rlcf_b200 import datautils as D
+    from rlcf_b200._lib import RlcfError
+    with pytest.raises(NotImplementedError):
+        D.AugMixAugmenter(n_views=3, hard_aug=True)
+    with pytest.raises(RlcfError):
+        D.AugMixAugmenter(n_views=3, device=DEV).views(torch.zeros(10, 10, 3))   # not uint8
