@@ -48,35 +48,40 @@ def _bicubic(x):
 FILTERS = {"bilinear": (_bilinear, 1.0), "bicubic": (_bicubic, 2.0)}
 
 
-def resample_taps(in_size: int, out_size: int, filt: str, out_lo: int = 0, out_n: int | None = None):
-    """precompute_coeffs + normalize_coeffs_8bpc (libImaging/Resample.c) for resizing `in_size` samples to `out_size`,
-    restricted to outputs [out_lo, out_lo + out_n).  Returns (bounds int32 [out_n,2] = (first tap, count),
-    taps int32 [out_n, ksize]).  Same double-precision operation order as the C source; the taps of one output are
-    accumulated sequentially."""
+def resample_taps_batch(in_sizes, out_size: int, filt: str, out_lo: int = 0, out_n: int | None = None):
+    """precompute_coeffs + normalize_coeffs_8bpc (libImaging/Resample.c) for resizing in_sizes[v] samples to `out_size`
+    (all views at once), restricted to outputs [out_lo, out_lo + out_n).  Returns (bounds int32 [V,out_n,2] = (first tap,
+    count), taps int32 [V,out_n,ks_max]).  Same double-precision operation order as the C source; the taps of one
+    output are accumulated sequentially."""
     fn, support0 = FILTERS[filt]
     out_n = out_size if out_n is None else out_n
-    scale = filterscale = float(np.float32(in_size) - np.float32(0)) / out_size
-    if filterscale < 1.0:
-        filterscale = 1.0
+    in_sizes = np.asarray(in_sizes, dtype=np.int64).reshape(-1)
+    scale = ((in_sizes.astype(np.float32) - np.float32(0)).astype(np.float64) / out_size)[:, None]     # [V,1]
+    filterscale = np.maximum(scale, 1.0)
     support = support0 * filterscale
-    ksize = int(math.ceil(support)) * 2 + 1
-    xx = np.arange(out_lo, out_lo + out_n, dtype=np.float64)
-    center = 0.0 + (xx + 0.5) * scale
+    ksize = int(np.ceil(support).max()) * 2 + 1
+    xx = np.arange(out_lo, out_lo + out_n, dtype=np.float64)[None, :]
+    center = 0.0 + (xx + 0.5) * scale                                       # [V,out_n]
     ss = 1.0 / filterscale
-    xmin = np.maximum((center - support + 0.5).astype(np.int64), 0)       # (int) truncates toward zero, then clamp
-    xmax = np.minimum((center + support + 0.5).astype(np.int64), in_size) - xmin
-    k = np.zeros((out_n, ksize), dtype=np.float64)
-    ww = np.zeros(out_n, dtype=np.float64)
+    xmin = np.maximum((center - support + 0.5).astype(np.int64), 0)         # (int) truncates toward zero, then clamp
+    xmax = np.minimum((center + support + 0.5).astype(np.int64), in_sizes[:, None]) - xmin
+    k = np.zeros(center.shape + (ksize,), dtype=np.float64)
+    ww = np.zeros_like(center)
     for x in range(ksize):
         w = np.where(x < xmax, fn((x + xmin - center + 0.5) * ss), 0.0)
-        k[:, x] = w
+        k[..., x] = w
         ww = ww + w
     nz = ww != 0.0
-    k[nz] = k[nz] / ww[nz, None]
-    k[np.arange(ksize)[None, :] >= xmax[:, None]] = 0.0
+    k[nz] = k[nz] / ww[nz][:, None]
     fixed = np.where(k < 0, -0.5 + k * (1 << PRECISION_BITS), 0.5 + k * (1 << PRECISION_BITS)).astype(np.int64)
-    bounds = np.stack([xmin, xmax], axis=1).astype(np.int32)
+    bounds = np.stack([xmin, xmax], axis=-1).astype(np.int32)
     return bounds, fixed.astype(np.int32)
+
+
+def resample_taps(in_size: int, out_size: int, filt: str, out_lo: int = 0, out_n: int | None = None):
+    """Single-view form of resample_taps_batch: (bounds [out_n,2], taps [out_n,ksize])."""
+    b, t = resample_taps_batch([in_size], out_size, filt, out_lo, out_n)
+    return b[0], t[0]
 
 
 # ------------------------------------------------------------------------------------------------ the random plan
@@ -97,23 +102,14 @@ class ViewPlan:
     tmp_rows: int
 
 
-def _pad_taps(taps, ks):
-    out = np.zeros((len(taps), OUT, ks), dtype=np.int32)
-    for i, t in enumerate(taps):
-        out[i, :, :t.shape[1]] = t
-    return out
-
-
-def _crop_tables(in_w, in_h, filt, x_lo=0, y_lo=0, out_w=OUT, out_h=OUT, res_w=OUT, res_h=OUT):
-    """Taps of one view: the source region (in_w x in_h) is resized to (res_w x res_h) and the window of OUT x OUT
-    outputs starting at (x_lo, y_lo) is kept."""
-    hb, hk = resample_taps(in_w, res_w, filt, x_lo, out_w)
-    vb, vk = resample_taps(in_h, res_h, filt, y_lo, out_h)
-    row_first = int(vb[0, 0])
-    row_last = int(vb[-1, 0] + vb[-1, 1])
+def _window(vb):
+    """Rows of the source the vertical pass touches (ImagingResample: ybox_first / ybox_last) and the row taps
+    re-based to the first of them.  vb [..., out, 2]."""
+    first = vb[..., 0, 0].copy()
+    n_rows = vb[..., -1, 0] + vb[..., -1, 1] - first
     vb = vb.copy()
-    vb[:, 0] -= row_first
-    return hb, hk, vb, vk, row_first, row_last - row_first
+    vb[..., 0] -= first[..., None]
+    return vb, first, n_rows
 
 
 def _rotate_matrix(degrees: int):
@@ -169,33 +165,31 @@ def sample_plan(img_w: int, img_h: int, n_views: int, augmix: bool, severity: in
     from torchvision.transforms import RandomResizedCrop
     V = n_views + 1
     hdr = np.zeros((V, 8), dtype=np.int32)
-    hbs, hks, vbs, vks = [], [], [], []
     vflag = np.zeros(V, dtype=np.int32)
     wts = np.zeros((V, 4), dtype=np.float32)
     omm = np.zeros(V, dtype=np.float32)
     n_ops = np.zeros((V, 3), dtype=np.int32)
     op_codes = np.zeros((V, 3, 3, 2), dtype=np.int32)
     mats = np.zeros((V, 3, 3, 6), dtype=np.float64)
-    tmp_rows = 1
-    # view 0: transforms.Resize(224, BICUBIC) + CenterCrop(224)            (tune_cls_rl.py:103-105)
+    # view 0: transforms.Resize(224, BICUBIC) + CenterCrop(224)            (tune_cls_rl.py:103-105): the window of
+    # OUT x OUT outputs at (left, top) of the image resized to new_w x new_h
     if img_w <= img_h:
         new_w, new_h = OUT, int(OUT * img_h / img_w)
     else:
         new_w, new_h = int(OUT * img_w / img_h), OUT
     top, left = int(round((new_h - OUT) / 2.0)), int(round((new_w - OUT) / 2.0))
-    hb, hk, vb, vk, rf, nr = _crop_tables(img_w, img_h, "bicubic", left, top, res_w=new_w, res_h=new_h)
-    hdr[0, :5] = (0, 0, rf, nr, 0)
-    hbs.append(hb); hks.append(hk); vbs.append(vb); vks.append(vk)
-    tmp_rows = max(tmp_rows, nr)
+    hb0, hk0 = resample_taps(img_w, new_w, "bicubic", left, OUT)
+    vb0, vk0 = resample_taps(img_h, new_h, "bicubic", top, OUT)
+    vb0, rf0, nr0 = _window(vb0)
+    hdr[0, :5] = (0, 0, rf0, nr0, 0)
     dummy = torch.empty(3, img_h, img_w, dtype=torch.uint8)
+    crop_w, crop_h = np.zeros(n_views, dtype=np.int64), np.zeros(n_views, dtype=np.int64)
     for v in range(1, V):
         # preaugment: RandomResizedCrop(224) + RandomHorizontalFlip           (datautils.py:89-92)
         i, j, h, w = RandomResizedCrop.get_params(dummy, scale=(0.08, 1.0), ratio=(3.0 / 4.0, 4.0 / 3.0))
         flip = bool(torch.rand(1) < 0.5)
-        hb, hk, vb, vk, rf, nr = _crop_tables(w, h, "bilinear")
-        hdr[v, :5] = (j, i, rf, nr, int(flip))
-        hbs.append(hb); hks.append(hk); vbs.append(vb); vks.append(vk)
-        tmp_rows = max(tmp_rows, nr)
+        hdr[v, :5] = (j, i, 0, 0, int(flip))
+        crop_w[v - 1], crop_h[v - 1] = w, h
         if not augmix:
             continue
         # augmix()                                                            (datautils.py:95-111)
@@ -217,9 +211,25 @@ def sample_plan(img_w: int, img_h: int, n_views: int, augmix: bool, severity: in
                     mats[v, c, k] = mat
                 k += 1
             n_ops[v, c] = k
-    ks_h, ks_v = max(t.shape[1] for t in hks), max(t.shape[1] for t in vks)
-    return ViewPlan(hdr=hdr, hb=np.stack(hbs), hk=_pad_taps(hks, ks_h), vb=np.stack(vbs), vk=_pad_taps(vks, ks_v),
-                    vflag=vflag, wts=wts, omm=omm, n_ops=n_ops, ops=op_codes, mats=mats, tmp_rows=tmp_rows)
+    # taps of all random crops at once (the crop is resized as an image of its own: F.resized_crop)
+    hb = np.zeros((V, OUT, 2), dtype=np.int32)
+    vb = np.zeros((V, OUT, 2), dtype=np.int32)
+    hb[0], vb[0] = hb0, vb0
+    ks_h, ks_v = hk0.shape[1], vk0.shape[1]
+    if n_views > 0:
+        hbn, hkn = resample_taps_batch(crop_w, OUT, "bilinear")
+        vbn, vkn = resample_taps_batch(crop_h, OUT, "bilinear")
+        vbn, rfn, nrn = _window(vbn)
+        hb[1:], vb[1:] = hbn, vbn
+        hdr[1:, 2], hdr[1:, 3] = rfn, nrn
+        ks_h, ks_v = max(ks_h, hkn.shape[2]), max(ks_v, vkn.shape[2])
+    hk = np.zeros((V, OUT, ks_h), dtype=np.int32)
+    vk = np.zeros((V, OUT, ks_v), dtype=np.int32)
+    hk[0, :, :hk0.shape[1]], vk[0, :, :vk0.shape[1]] = hk0, vk0
+    if n_views > 0:
+        hk[1:, :, :hkn.shape[2]], vk[1:, :, :vkn.shape[2]] = hkn, vkn
+    return ViewPlan(hdr=hdr, hb=hb, hk=hk, vb=vb, vk=vk, vflag=vflag, wts=wts, omm=omm, n_ops=n_ops, ops=op_codes,
+                    mats=mats, tmp_rows=int(hdr[:, 3].max()))
 
 
 # ------------------------------------------------------------------------------------------------ device execution

@@ -1,0 +1,39 @@
+"""Throughput of the on-device view generation (64 views of one 500x375 image) next to the reference's PIL pipeline on
+one host thread.  Reported per image: host plan (random decisions + Pillow tap tables), upload + kernels."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from oracle import augmix_oracle as A          # the PIL pipeline, as the timed CPU baseline only
+from rlcf_b200 import datautils as D
+
+dev = torch.device("cuda:0")
+img = A.synthetic_image(375, 500, 3)
+u8 = D._to_u8_hwc(img)
+for augmix in (False, True):
+    torch.manual_seed(0); np.random.seed(0)
+    aug = D.AugMixAugmenter(n_views=63, augmix=augmix, device=dev)
+    for _ in range(3):
+        aug.views(img)
+    torch.cuda.synchronize()
+    n = 30
+    t0 = time.perf_counter()
+    plans = [D.sample_plan(500, 375, 63, augmix) for _ in range(n)]
+    t_plan = (time.perf_counter() - t0) / n
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for p in plans:
+        D.run_plan(u8, p, dev)
+    e1.record()
+    torch.cuda.synchronize()
+    t_run = (time.perf_counter() - t0) / n
+    t0 = time.perf_counter()
+    for _ in range(3):
+        A.augmix_views(img, 63, augmix)
+    t_pil = (time.perf_counter() - t0) / 3
+    print(f"augmix={augmix}: host plan {t_plan*1e3:.2f} ms/img, upload+kernels {t_run*1e3:.2f} ms/img (wall) "
+          f"{e0.elapsed_time(e1)/n:.2f} ms/img (device) -> {1/(t_plan+t_run):.0f} img/s single-threaded; "
+          f"PIL pipeline (1 thread) {t_pil*1e3:.1f} ms/img = {1/t_pil:.1f} img/s; "
+          f"bytes uploaded per image {u8.numel() + sum(a.nbytes for a in (p.hdr,p.hb,p.hk,p.vb,p.vk,p.vflag,p.wts,p.omm,p.n_ops,p.ops,p.mats))} "
+          f"vs {64*3*224*224*4} of fp32 views", flush=True)
