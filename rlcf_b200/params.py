@@ -59,6 +59,8 @@ def build_parser():
     # additions of this implementation
     parser.add_argument("--images_per_step", type=int, default=8, help="independent test images adapted per launch")
     parser.add_argument("--synthetic", action="store_true", help="synthetic weights / views / labels (offline)")
+    parser.add_argument("--synthetic_weights", action="store_true",
+                        help="real images from DIR (views generated on the GPU) with seeded random-init CLIP weights")
     parser.add_argument("--n_images", type=int, default=64, help="synthetic: test images per dataset")
     parser.add_argument("--n_classes", type=int, default=200, help="synthetic: classes per dataset")
     return parser

@@ -21,7 +21,7 @@ from copy import deepcopy
 
 import torch
 
-from . import synthetic
+from . import datautils, synthetic
 from .clip.custom_clip import CLIPCLS_TTA
 from .clip_reward import get_reward_model
 from .params import get_args
@@ -30,7 +30,10 @@ from .utils.tools import AverageMeter, ProgressMeter, Summary, accuracy, set_ran
 
 
 def _stack_views(images, device):
-    """One loader sample -> [V,3,H,W] on the device (tune_cls_rl.py:194-207: list of [1,3,H,W] views or a tensor)."""
+    """One loader sample -> [V,3,H,W] on the device (tune_cls_rl.py:194-207: list of [1,3,H,W] views or a tensor), or
+    (uint8 image, ViewPlan) from ImageFolderViews: the views are then generated on the device."""
+    if isinstance(images, tuple) and len(images) == 2 and isinstance(images[1], datautils.ViewPlan):
+        return datautils.run_plan(images[0], images[1], device)
     if isinstance(images, (list, tuple)):
         return torch.cat([im.to(device, non_blocking=True) for im in images], dim=0)
     if images.dim() > 4:
@@ -122,6 +125,42 @@ class SyntheticViews(torch.utils.data.Dataset):
         return views, label
 
 
+# TPT/data/datautils.py:22-39
+ID_to_DIRNAME = {"I": "ImageNet", "A": "imagenet-a", "K": "ImageNet-Sketch", "R": "imagenet-r",
+                 "V": "imagenetv2-matched-frequency-format-val", "flower102": "oxford_flowers", "dtd": "dtd",
+                 "pets": "oxford_pets", "cars": "stanford_cars", "ucf101": "ucf101", "caltech101": "caltech-101",
+                 "food101": "food-101", "sun397": "sun397", "aircraft": "fgvc_aircraft", "eurosat": "eurosat",
+                 "C": "imagenet-c"}
+
+
+class ImageFolderViews(torch.utils.data.Dataset):
+    """datasets.ImageFolder + AugMixAugmenter (tune_cls_rl.py:102-150) with the pixels left to the GPU: a sample is
+    ((decoded uint8 image [H,W,3], ViewPlan), label).  The plan (random crops / flips / AugMix decisions and Pillow tap
+    tables) is host work and parallelises over DataLoader workers; rank r of R sees indices r, r+R, ..."""
+
+    def __init__(self, root, n_views, augmix, rank=0, world=1, severity=1):
+        from torchvision.datasets import ImageFolder
+        self.folder = ImageFolder(root)
+        self.classes = self.folder.classes
+        self.idx = list(range(rank, len(self.folder), world))
+        self.n_views, self.augmix, self.severity = n_views, bool(augmix), severity
+
+    def __len__(self):
+        return len(self.idx)
+
+    def __getitem__(self, i):
+        img, label = self.folder[self.idx[i]]
+        u8 = datautils._to_u8_hwc(img)
+        plan = datautils.sample_plan(u8.shape[1], u8.shape[0], self.n_views, self.augmix, self.severity)
+        return (u8, plan), torch.tensor(label)
+
+
+def _real_dataset_root(args, set_id):
+    if set_id == "I":
+        return os.path.join(args.data, ID_to_DIRNAME[set_id], "val")
+    return os.path.join(args.data, ID_to_DIRNAME.get(set_id.lower() if len(set_id) > 1 else set_id, set_id))
+
+
 def main_worker(gpu, args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -135,12 +174,25 @@ def main_worker(gpu, args):
         raise SystemExit("rlcf_b200 needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(gpu)
     device = torch.device("cuda", gpu)
-    if not args.synthetic:
-        raise SystemExit("real datasets are not wired in this build (no data offline); run with --synthetic")
-    arch, reward_arch = "synthetic:" + args.arch + ":0", "synthetic:" + args.reward_arch + ":1"
-    classnames = [f"class {i}" for i in range(args.n_classes)]
-    vocab = synthetic.ARCHS[args.arch][6]
-    tokens = synthetic.make_tokens(args.n_classes, vocab)
+    real_data = args.data is not None and not args.synthetic
+    if not real_data and not args.synthetic:
+        raise SystemExit("give a dataset root (DIR, ImageFolder layout as in TPT/data/datautils.py) or --synthetic")
+    synth_w = args.synthetic or getattr(args, "synthetic_weights", False)
+    arch = "synthetic:" + args.arch + ":0" if synth_w else args.arch
+    reward_arch = "synthetic:" + args.reward_arch + ":1" if synth_w else args.reward_arch
+    datasets_ = {}
+    if real_data:   # the class names come from the first dataset's folders (one model per run, as in the reference loop)
+        for set_id in args.test_sets.split("/"):
+            datasets_[set_id] = ImageFolderViews(_real_dataset_root(args, set_id), args.batch_size - 1,
+                                                 augmix=len(set_id) > 1, rank=rank, world=world)   # tune_cls_rl.py:109-110
+        first = datasets_[args.test_sets.split("/")[0]]
+        classnames = [c.replace("_", " ") for c in first.classes]
+        args.n_classes = len(classnames)
+    else:
+        classnames = [f"class {i}" for i in range(args.n_classes)]
+    key = arch.split(":")[1] if synth_w else args.arch
+    vocab = synthetic.ARCHS[key][6] if key in synthetic.ARCHS else 49408
+    tokens = synthetic.make_tokens(args.n_classes, vocab) if args.synthetic else None
     model = CLIPCLS_TTA(device, classnames, arch=arch, prompt_prefix=args.ctx_init or "a photo of a",
                         only_visual=True, momentum_update=args.momentum_update, update_freq=args.update_freq,
                         update_w=args.update_w, momentum=args.tta_momentum, only_norm=args.tune_norm,
@@ -149,22 +201,31 @@ def main_worker(gpu, args):
     optim_state = deepcopy(optimizer.state_dict())
     args.reward_arch = reward_arch
     reward_model = get_reward_model(device, args)
-    reward_model.set_class_features(tokenized_classes=synthetic.make_tokens(
-        args.n_classes, synthetic.ARCHS[reward_arch.split(":")[1]][6]).to(device))
+    if args.synthetic:
+        reward_model.set_class_features(tokenized_classes=synthetic.make_tokens(
+            args.n_classes, synthetic.ARCHS[reward_arch.split(":")[1]][6]).to(device))
+    else:
+        reward_model.set_class_features(classnames=[f"{args.ctx_init or 'a photo of a'} {c}." for c in classnames])
     scaler = torch.cuda.amp.GradScaler(init_scale=1000)
     results = {}
     for set_id in args.test_sets.split("/"):
         t0 = time.time()
-        ds = SyntheticViews(args.n_images, args.batch_size, args.resolution, args.n_classes, args.seed + 1000,
-                            rank, world)
-        loader = torch.utils.data.DataLoader(ds, batch_size=1, shuffle=False, num_workers=0,
-                                             collate_fn=lambda b: (b[0][0], b[0][1].view(1)))
+        if real_data:
+            ds = datasets_[set_id]
+            args.n_images = len(ds.folder)
+            loader = torch.utils.data.DataLoader(ds, batch_size=1, shuffle=False, num_workers=args.workers,
+                                                 collate_fn=lambda b: (b[0][0], b[0][1].view(1)))
+        else:
+            ds = SyntheticViews(args.n_images, args.batch_size, args.resolution, args.n_classes, args.seed + 1000,
+                                rank, world)
+            loader = torch.utils.data.DataLoader(ds, batch_size=1, shuffle=False, num_workers=0,
+                                                 collate_fn=lambda b: (b[0][0], b[0][1].view(1)))
         results[set_id] = test_time_adapt_eval(loader, model, optimizer, optim_state, scaler, args, device=device,
                                                reward_model=reward_model)
         if rank == 0:
             dt = time.time() - t0
             print(f"=> Acc. on testset [{set_id}]: @1 {results[set_id][0]} / @5 {results[set_id][1]}  "
-                  f"({args.n_images / dt:.1f} images/s incl. synthetic view generation)")
+                  f"({args.n_images / dt:.1f} images/s incl. view generation)")
     if rank == 0:
         with open(os.path.join(args.output, "results.json"), "a+") as fp:
             json.dump(results, fp, indent=4)
