@@ -60,10 +60,10 @@ def test_driver_on_an_image_folder_with_gpu_views(tmp_path):
     LayerNorm-tuning RLCF) with seeded random-init ViT-B/32 weights: the whole reference flow minus the checkpoints."""
     from rlcf_b200 import params, tune_cls_rl
     root = tmp_path / "data" / "imagenet-a"
-    for ci, cname in enumerate(["n01_goldfish", "n02_tabby_cat"]):
+    names = ["n01_goldfish", "n02_tabby_cat", "n03_fire_truck", "n04_volcano", "n05_accordion", "n06_snail"]
+    for ci, cname in enumerate(names):     # top-5 accuracy needs at least 5 classes (tools.accuracy, as the reference)
         (root / cname).mkdir(parents=True)
-        for k in range(3):
-            A.synthetic_image(120 + 10 * k, 160 - 7 * k, 100 * ci + k).save(root / cname / f"img{k}.png")
+        A.synthetic_image(120 + 10 * ci, 160 - 7 * ci, 100 + ci).save(root / cname / "img0.png")
     args = params.build_parser().parse_args([
         str(tmp_path / "data"), "--test_sets", "A", "-a", "ViT-B/32", "--reward_arch", "ViT-B/32", "--tpt",
         "--tune_norm", "1", "--batch_size", "8", "--selection_p", "0.5", "--tta_steps", "1", "--sample_k", "2",
@@ -71,5 +71,5 @@ def test_driver_on_an_image_folder_with_gpu_views(tmp_path):
     os.makedirs(args.output, exist_ok=True)
     res = tune_cls_rl.main_worker(0, args)
     top1, top5 = res["A"]
-    assert 0.0 <= top1 <= 100.0 and top5 == 100.0        # 2 classes: top-5 always contains the label
-    assert args.n_images == 6 and args.n_classes == 2
+    assert 0.0 <= top1 <= top5 <= 100.0
+    assert args.n_images == 6 and args.n_classes == 6
