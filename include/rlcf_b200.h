@@ -299,6 +299,13 @@ int rlcf_augmix_views(const uint8_t* x_orig, int n_views, const int32_t* vflag, 
                       const int32_t* n_ops, const int32_t* ops, const double* mats, float mean0, float mean1,
                       float mean2, float std0, float std1, float std2, float* out, void* stream);
 
+/* rlcf_transpose_blocks_f16 for fp16 input with the per-set column sums in the same pass: colsum[g*colsum_stride + c] =
+ * sum_r in[row(g,r), c] (the bias gradient of the Linear whose output gradient is being laid out for the wgrad GEMM;
+ * colsum may be NULL).  rows_pad, cols, ld_out even. */
+int rlcf_transpose_blocks_colsum(const void* in, int n_sets, int rows_per_set, int rows_pad, int cols, int skip_first,
+                                 int64_t in_set_stride_rows, void* out, int64_t ld_out, float* colsum,
+                                 int64_t colsum_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

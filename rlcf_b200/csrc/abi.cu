@@ -97,6 +97,8 @@ int head_bwd(const float*, const float*, const int32_t*, long long, const float*
              long long, cudaStream_t);
 int transpose_blocks(const void*, int, int, int, int, int, int, long long, __half*, long long, cudaStream_t);
 int colsum_f16(const __half*, int, int, int, float*, long long, cudaStream_t);
+int transpose_blocks_colsum(const __half*, int, int, int, int, int, long long, __half*, long long, float*, long long,
+                            cudaStream_t);
 int seq_sum(const float*, int, int, int, int, float*, long long, cudaStream_t);
 int outer_sum(const float*, const float*, int, int, int, int, float*, long long, cudaStream_t);
 int embed_prompts(const long long*, const float*, const float*, const float*, long long, int, int, int, int, int,
@@ -451,6 +453,14 @@ int rlcf_augmix_views(const uint8_t* x_orig, int n_views, const int32_t* vflag, 
     return set_error(RLCF_ERR_ARG, "augmix_views: null pointer");
   const float mean[3] = {mean0, mean1, mean2}, stdv[3] = {std0, std1, std2};
   return augmix_views(x_orig, n_views, vflag, wts, omm, n_ops, ops, mats, mean, stdv, out, S(stream));
+}
+
+int rlcf_transpose_blocks_colsum(const void* in, int n_sets, int rows_per_set, int rows_pad, int cols, int skip_first,
+                                 int64_t in_set_stride_rows, void* out, int64_t ld_out, float* colsum,
+                                 int64_t colsum_stride, void* stream) {
+  if (!in || !out) return set_error(RLCF_ERR_ARG, "transpose_blocks_colsum: null pointer");
+  return transpose_blocks_colsum(CH(in), n_sets, rows_per_set, rows_pad, cols, skip_first, in_set_stride_rows, H(out),
+                                 ld_out, colsum, colsum_stride, S(stream));
 }
 
 }  // extern "C"

@@ -35,6 +35,66 @@ __global__ void transpose_blocks_kernel(const Tin* __restrict__ in, int rows_per
   }
 }
 
+// fp16 fast path: 64 x 64 tiles, 4-byte accesses on both sides, one block per (column tile, set) walking down the set's
+// rows, which also yields the column sums of the set (the bias gradient of the Linear whose dY is being transposed).
+__global__ void __launch_bounds__(256)
+transpose_blocks_f16_kernel(const __half* __restrict__ in, int rows_per_set, int rows_pad, int cols, int skip_first,
+                            long long in_set_stride_rows, __half* __restrict__ out, long long ld_out,
+                            float* __restrict__ colsum, long long colsum_stride) {
+  __shared__ __half tile[64][66];
+  __shared__ float part[8][64];
+  const int g = blockIdx.y, c0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = c0 + 2 * tx;
+  float s0 = 0.f, s1 = 0.f;
+  for (int r0 = 0; r0 < rows_pad; r0 += 64) {
+    for (int j = ty; j < 64; j += 8) {
+      const int r = r0 + j;
+      __half2 val = __floats2half2_rn(0.f, 0.f);
+      if (r < rows_per_set && c < cols) {
+        long long src = r;
+        if (skip_first > 0) src = static_cast<long long>(r / (skip_first - 1)) * skip_first + 1 + r % (skip_first - 1);
+        val = *reinterpret_cast<const __half2*>(in + (g * in_set_stride_rows + src) * cols + c);
+        const float2 f = __half22float2(val);
+        s0 += f.x; s1 += f.y;
+      }
+      tile[j][2 * tx] = __low2half(val);
+      tile[j][2 * tx + 1] = __high2half(val);
+    }
+    __syncthreads();
+    for (int j = ty; j < 64; j += 8) {
+      const int cc = c0 + j, r = r0 + 2 * tx;
+      if (cc < cols && r < rows_pad)
+        *reinterpret_cast<__half2*>(out + static_cast<long long>(cc) * ld_out + static_cast<long long>(g) * rows_pad + r) =
+            __halves2half2(tile[2 * tx][j], tile[2 * tx + 1][j]);
+    }
+    __syncthreads();
+  }
+  if (colsum == nullptr) return;
+  part[ty][2 * tx] = s0;
+  part[ty][2 * tx + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64 && c0 + threadIdx.x < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += part[k][threadIdx.x];
+    colsum[g * colsum_stride + c0 + threadIdx.x] = s;
+  }
+}
+
+int transpose_blocks_colsum(const __half* in, int n_sets, int rows_per_set, int rows_pad, int cols, int skip_first,
+                            long long in_set_stride_rows, __half* out, long long ld_out, float* colsum,
+                            long long colsum_stride, cudaStream_t stream) {
+  if (n_sets <= 0 || n_sets > 65535 || rows_per_set <= 0 || rows_pad < rows_per_set || rows_pad % 2 || cols <= 0 ||
+      cols % 2 || skip_first == 1 || ld_out % 2)
+    return set_error(RLCF_ERR_ARG, "transpose_blocks_colsum: bad shape");
+  dim3 grid((cols + 63) / 64, n_sets);
+  transpose_blocks_f16_kernel<<<grid, 256, 0, stream>>>(in, rows_per_set, rows_pad, cols, skip_first,
+                                                        in_set_stride_rows, out, ld_out, colsum, colsum_stride);
+  RLCF_CHECK_LAUNCH("transpose_blocks_colsum");
+  return 0;
+}
+
 int transpose_blocks(const void* in, int in_is_f32, int n_sets, int rows_per_set, int rows_pad, int cols,
                      int skip_first, long long in_set_stride_rows, __half* out, long long ld_out,
                      cudaStream_t stream) {

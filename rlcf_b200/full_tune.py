@@ -182,16 +182,24 @@ class WgradHook:
     def bind(self, grads: torch.Tensor, n_sets: int, patches: torch.Tensor):
         self.grads, self.n_sets, self.patches = grads, n_sets, patches
 
-    def _wgrad(self, dY, X, n_out, n_in, off, rows, rows_pad, skip=0, dy_stride_rows=None, x_rows=None):
+    def _wgrad(self, dY, X, n_out, n_in, off, rows, rows_pad, skip=0, dy_stride_rows=None, bias_off=None):
+        """grads[g, off:...] = dY_g^T X_g for every set g (one grouped GEMM over transposed fp16 operands); with
+        bias_off the column sums of dY (the bias gradient) come out of the same transposing pass."""
         ns = self.n_sets
         ld = ns * rows_pad
-        ops.transpose_blocks(dY, ns, rows, rows_pad, n_out, self.t_dy, ld, skip_first=skip,
-                             in_set_stride_rows=dy_stride_rows)
-        ops.transpose_blocks(X, ns, rows, rows_pad, n_in, self.t_x, ld)
+        g = self.grads
+        if dY.dtype == torch.float16:
+            ops.transpose_blocks_colsum(dY, ns, rows, rows_pad, n_out, self.t_dy, ld, skip_first=skip,
+                                        in_set_stride_rows=dy_stride_rows,
+                                        colsum=None if bias_off is None else g.view(-1)[bias_off:],
+                                        colsum_stride=g.stride(0))
+        else:
+            ops.transpose_blocks(dY, ns, rows, rows_pad, n_out, self.t_dy, ld, skip_first=skip,
+                                 in_set_stride_rows=dy_stride_rows)
+        ops.transpose_blocks_colsum(X, ns, rows, rows_pad, n_in, self.t_x, ld)
         # one grouped launch: group g = columns [g*rows_pad, (g+1)*rows_pad) of the transposed operands
         ty = self.t_dy.as_strided((ns, n_out, rows_pad), (rows_pad, ld, 1))
         tx = self.t_x.as_strided((ns, n_in, rows_pad), (rows_pad, ld, 1))
-        g = self.grads
         out = g.as_strided((ns, n_out, n_in), (g.stride(0), n_in, 1), g.storage_offset() + off)
         ops.gemm_grouped(ty, tx, out, epilogue=EPI_F32)
 
@@ -200,8 +208,7 @@ class WgradHook:
         n_out, n_in, woff, boff = {"in_proj": (3 * d, d, lay.wq[l], lay.bq[l]), "out_proj": (d, d, lay.wo[l], lay.bo[l]),
                                    "c_fc": (4 * d, d, lay.wf[l], lay.bf[l]),
                                    "c_proj": (d, 4 * d, lay.wp[l], lay.bp[l])}[name]
-        self._wgrad(dY, X, n_out, n_in, woff, self.rows, self.rows_pad)
-        ops.colsum_f16(dY, self.n_sets, self.rows, n_out, self.grads[:, boff:], self.grads.stride(0))
+        self._wgrad(dY, X, n_out, n_in, woff, self.rows, self.rows_pad, bias_off=boff)
 
     def embed(self, dx_pre: torch.Tensor):
         lay, d, L = self.lay, self.lay.d, self.lay.L

@@ -232,6 +232,17 @@ def transpose_blocks(src, n_sets, rows_per_set, rows_pad, cols, out, ld_out, ski
     return out
 
 
+def transpose_blocks_colsum(src, n_sets, rows_per_set, rows_pad, cols, out, ld_out, colsum=None, colsum_stride=0,
+                            skip_first=0, in_set_stride_rows=None):
+    """transpose_blocks for fp16 input; colsum (fp32 base pointer, set stride colsum_stride) also receives the per-set
+    column sums."""
+    _chk(src, torch.float16, "src"); _chk(out, torch.float16, "out"); _chk(colsum, torch.float32, "colsum", strided=True)
+    stride = rows_per_set if in_set_stride_rows is None else in_set_stride_rows
+    call("rlcf_transpose_blocks_colsum", ptr(src), n_sets, rows_per_set, rows_pad, cols, skip_first, stride, ptr(out),
+         ld_out, ptr(colsum), colsum_stride, stream())
+    return out
+
+
 def colsum_f16(src, n_sets, rows_per_set, cols, out, out_stride):
     _chk(src, torch.float16, "src"); _chk(out, torch.float32, "out", strided=True)
     call("rlcf_colsum_f16", ptr(src), n_sets, rows_per_set, cols, ptr(out), out_stride, stream())
