@@ -453,8 +453,18 @@ def retrieval_trainable(sd: dict, task: str) -> list:
     return sorted(k for k in sd if k.startswith("visual.") == vis)
 
 
+_AUTOCAST_KEYS = ("conv1.weight", "in_proj_weight", "out_proj.weight", "c_fc.weight", "c_proj.weight")
+
+
+def autocast_weights(sd: dict) -> dict:
+    """What torch.cuda.amp.autocast does to the parameters on the reference's GPU path (clip_ret_policy.py:87,120): every
+    Conv / Linear / MultiheadAttention weight is cast to fp16 for the matmul at each forward, the fp32 master stays the
+    optimizer's.  The cast is differentiable (identity gradient), so the masters still receive gradient."""
+    return {k: (v.half().float() if k.endswith(_AUTOCAST_KEYS) else v) for k, v in sd.items()}
+
+
 def retrieval_tune_query(sd_init: dict, cfg: RetrievalConfig, task: str, query: torch.Tensor, gallery: torch.Tensor,
-                         reward_query: torch.Tensor, reward_gallery: torch.Tensor) -> dict:
+                         reward_query: torch.Tensor, reward_gallery: torch.Tensor, fp16_weights: bool = False) -> dict:
     """tune_image / tune_text (retrieval/clip_ret_policy.py:76-137) followed by the evaluation forward of
     test_time_tune (161-168 / 178-184), for ONE query on the weights `sd_init`.
 
@@ -470,7 +480,8 @@ def retrieval_tune_query(sd_init: dict, cfg: RetrievalConfig, task: str, query: 
     K = cfg.sample_k
 
     def model():                                                         # CLIPRet_TTA.forward, custom_models.py:66-76
-        f = retrieval_features(sd, images=query) if i2t else retrieval_features(sd, tokens=query)
+        w = autocast_weights(sd) if fp16_weights else sd                 # fp16_weights: the reference's GPU numerics
+        f = retrieval_features(w, images=query) if i2t else retrieval_features(w, tokens=query)
         return sd["logit_scale"].exp() * f @ gallery.t()
 
     out = {"losses": [], "topk_idx": [], "scores": [], "rewards": [], "grads": []}
