@@ -306,6 +306,15 @@ int rlcf_transpose_blocks_colsum(const void* in, int n_sets, int rows_per_set, i
                                  int64_t in_set_stride_rows, void* out, int64_t ld_out, float* colsum,
                                  int64_t colsum_stride, void* stream);
 
+/* The tap tables rlcf_resample_u8 consumes, computed on the device exactly as Pillow's precompute_coeffs +
+ * normalize_coeffs_8bpc do (double precision, same operation order).  geom [n_views,8] int32 = {in_w, in_h, res_w,
+ * res_h, lo_x, lo_y, filter (0 = BILINEAR, 1 = BICUBIC), 0}: a source region of in_w x in_h pixels is resized to
+ * res_w x res_h, of which the window of out x out outputs at (lo_x, lo_y) is kept.  ks_h / ks_v >= the largest tap
+ * count (ceil(support * max(scale, 1)) * 2 + 1).  Fills hb/hk/vb/vk and hdr[:,2:4] (hdr[:,0:2] and [:,4], the crop
+ * origin and the flip flag, are the caller's). */
+int rlcf_resample_taps(const int32_t* geom, int n_views, int out, int ks_h, int ks_v, int32_t* hdr, int32_t* hb,
+                       int32_t* hk, int32_t* vb, int32_t* vk, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

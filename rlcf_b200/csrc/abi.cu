@@ -119,6 +119,7 @@ int adamw_full(float*, float*, float*, const float*, int, long long, float, floa
 int transpose_f16(const __half*, int, int, __half*, int, long long, cudaStream_t);
 int resample_u8(const uint8_t*, int, int, int, const int*, const int*, const int*, int, const int*, const int*, int, int,
                 int, uint8_t*, int, uint8_t*, cudaStream_t);
+int resample_taps(const int*, int, int, int, int, int*, int*, int*, int*, int*, cudaStream_t);
 int augmix_views(const uint8_t*, int, const int*, const float*, const float*, const int*, const int*, const double*,
                  const float*, const float*, float*, cudaStream_t);
 int add_rows(const float*, long long, const float*, long long, int, long long, float*, cudaStream_t);
@@ -461,6 +462,12 @@ int rlcf_transpose_blocks_colsum(const void* in, int n_sets, int rows_per_set, i
   if (!in || !out) return set_error(RLCF_ERR_ARG, "transpose_blocks_colsum: null pointer");
   return transpose_blocks_colsum(CH(in), n_sets, rows_per_set, rows_pad, cols, skip_first, in_set_stride_rows, H(out),
                                  ld_out, colsum, colsum_stride, S(stream));
+}
+
+int rlcf_resample_taps(const int32_t* geom, int n_views, int out, int ks_h, int ks_v, int32_t* hdr, int32_t* hb,
+                       int32_t* hk, int32_t* vb, int32_t* vk, void* stream) {
+  if (!geom || !hdr || !hb || !hk || !vb || !vk) return set_error(RLCF_ERR_ARG, "resample_taps: null pointer");
+  return resample_taps(geom, n_views, out, ks_h, ks_v, hdr, hb, hk, vb, vk, S(stream));
 }
 
 }  // extern "C"

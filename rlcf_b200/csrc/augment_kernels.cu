@@ -73,6 +73,77 @@ resample_v_kernel(const uint8_t* __restrict__ tmp, int tmp_rows, const int* __re
   }
 }
 
+// precompute_coeffs + normalize_coeffs_8bpc (libImaging/Resample.c) on the device, in double with the C source's
+// operation order (explicit _rn intrinsics: no FMA contraction), so the host only draws the crop boxes.
+// geom [V][8] int32 = {in_w, in_h, res_w, res_h, lo_x, lo_y, filter (0 bilinear, 1 bicubic), 0}: the source region of
+// in_w x in_h pixels is resized to res_w x res_h and the window of `out` outputs starting at (lo_x, lo_y) is kept.
+// grid (2 axes, V), one thread per output index.  The vertical block also fills hdr[v][2..3] = (first source row the
+// window needs, number of rows) and re-bases its first-tap indices to that row (ImagingResample: ybox_first).
+__device__ __forceinline__ double pil_filter(int filt, double x) {
+  if (x < 0.0) x = -x;
+  if (filt == 0) return x < 1.0 ? __dsub_rn(1.0, x) : 0.0;
+  if (x < 1.0) return __dadd_rn(__dmul_rn(__dmul_rn(__dsub_rn(__dmul_rn(1.5, x), 2.5), x), x), 1.0);
+  if (x < 2.0) return __dmul_rn(__dsub_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dsub_rn(x, 5.0), x), 8.0), x), 4.0), -0.5);
+  return 0.0;
+}
+
+__global__ void resample_taps_kernel(const int* __restrict__ geom, int out, int ks_h, int ks_v, int* __restrict__ hdr,
+                                     int* __restrict__ hb, int* __restrict__ hk, int* __restrict__ vb,
+                                     int* __restrict__ vk) {
+  __shared__ int s_first, s_last;
+  const int axis = blockIdx.x, v = blockIdx.y, t = threadIdx.x;
+  const int* g = geom + v * 8;
+  const int in_size = g[axis], res = g[2 + axis], lo = g[4 + axis], filt = g[6];
+  const int ks = axis == 0 ? ks_h : ks_v;
+  int* bounds = (axis == 0 ? hb : vb) + (static_cast<size_t>(v) * out) * 2;
+  int* taps = (axis == 0 ? hk : vk) + (static_cast<size_t>(v) * out) * ks;
+  int xmin = 0, cnt = 0;
+  if (t < out) {
+    const double scale = __ddiv_rn(static_cast<double>(static_cast<float>(in_size)), static_cast<double>(res));
+    const double filterscale = scale < 1.0 ? 1.0 : scale;
+    const double support = __dmul_rn(filt == 0 ? 1.0 : 2.0, filterscale);
+    const double center = __dadd_rn(0.0, __dmul_rn(__dadd_rn(static_cast<double>(lo + t), 0.5), scale));
+    const double ss = __ddiv_rn(1.0, filterscale);
+    xmin = static_cast<int>(__dadd_rn(__dsub_rn(center, support), 0.5));
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(__dadd_rn(__dadd_rn(center, support), 0.5));
+    if (xmax > in_size) xmax = in_size;
+    cnt = xmax - xmin;
+    double ww = 0.0;
+    for (int x = 0; x < cnt; ++x)
+      ww = __dadd_rn(ww, pil_filter(filt, __dmul_rn(__dadd_rn(__dsub_rn(static_cast<double>(x + xmin), center), 0.5), ss)));
+    int* k = taps + static_cast<size_t>(t) * ks;
+    for (int x = 0; x < ks; ++x) {
+      int fixed = 0;
+      if (x < cnt) {
+        double w = pil_filter(filt, __dmul_rn(__dadd_rn(__dsub_rn(static_cast<double>(x + xmin), center), 0.5), ss));
+        if (ww != 0.0) w = __ddiv_rn(w, ww);
+        fixed = w < 0 ? static_cast<int>(__dadd_rn(-0.5, __dmul_rn(w, 4194304.0)))
+                      : static_cast<int>(__dadd_rn(0.5, __dmul_rn(w, 4194304.0)));
+      }
+      k[x] = fixed;
+    }
+  }
+  if (axis == 1) {
+    if (t == 0) s_first = xmin;
+    if (t == out - 1) s_last = xmin + cnt;
+    __syncthreads();
+    if (t < out) xmin -= s_first;
+    if (t == 0) { hdr[v * 8 + 2] = s_first; hdr[v * 8 + 3] = s_last - s_first; }
+  }
+  if (t < out) { bounds[t * 2] = xmin; bounds[t * 2 + 1] = cnt; }
+}
+
+int resample_taps(const int* geom, int n_views, int out, int ks_h, int ks_v, int* hdr, int* hb, int* hk, int* vb,
+                  int* vk, cudaStream_t stream) {
+  if (n_views <= 0 || n_views > 65535 || out <= 0 || out > 1024 || ks_h <= 0 || ks_v <= 0)
+    return set_error(RLCF_ERR_ARG, "resample_taps: bad shape");
+  dim3 grid(2, n_views);
+  resample_taps_kernel<<<grid, (out + 31) / 32 * 32, 0, stream>>>(geom, out, ks_h, ks_v, hdr, hb, hk, vb, vk);
+  RLCF_CHECK_LAUNCH("resample_taps");
+  return 0;
+}
+
 int resample_u8(const uint8_t* src, int H, int W, int n_views, const int* hdr, const int* hb, const int* hk, int ks_h,
                 const int* vb, const int* vk, int ks_v, int out_h, int out_w, uint8_t* tmp, int tmp_rows, uint8_t* out,
                 cudaStream_t stream) {

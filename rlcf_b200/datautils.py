@@ -100,6 +100,9 @@ class ViewPlan:
     ops: np.ndarray      # int32 [V,3,3,2]
     mats: np.ndarray     # float64 [V,3,3,6]
     tmp_rows: int
+    geom: np.ndarray | None = None   # int32 [V,8] in_w, in_h, res_w, res_h, lo_x, lo_y, filter: taps are then computed
+    ks_h: int = 0                    # on the device (hb/hk/vb/vk are None) with these tap-count bounds
+    ks_v: int = 0
 
 
 def _window(vb):
@@ -159,9 +162,16 @@ def _sample_op(name: str, severity):
     raise KeyError(name)
 
 
-def sample_plan(img_w: int, img_h: int, n_views: int, augmix: bool, severity: int = 1) -> ViewPlan:
+def _ksize(in_sizes, res_sizes, support0):
+    """Largest tap count of a set of resizes: ceil(support * max(scale, 1)) * 2 + 1 (precompute_coeffs)."""
+    scale = np.asarray(in_sizes, dtype=np.float64) / np.asarray(res_sizes, dtype=np.float64)
+    return int(np.ceil(support0 * np.maximum(scale, 1.0)).max()) * 2 + 1
+
+
+def sample_plan(img_w: int, img_h: int, n_views: int, augmix: bool, severity: int = 1, host_taps: bool = True) -> ViewPlan:
     """The random decisions of AugMixAugmenter.__call__ (datautils.py:123-126) for one image of img_w x img_h pixels,
-    drawn from the global torch / numpy generators in the reference's order, plus the derived tables."""
+    drawn from the global torch / numpy generators in the reference's order, plus the derived tables.
+    host_taps=False leaves Pillow's tap tables to the device (rlcf_resample_taps) and only records the geometry."""
     from torchvision.transforms import RandomResizedCrop
     V = n_views + 1
     hdr = np.zeros((V, 8), dtype=np.int32)
@@ -211,6 +221,15 @@ def sample_plan(img_w: int, img_h: int, n_views: int, augmix: bool, severity: in
                     mats[v, c, k] = mat
                 k += 1
             n_ops[v, c] = k
+    if not host_taps:
+        geom = np.zeros((V, 8), dtype=np.int32)
+        geom[0, :7] = (img_w, img_h, new_w, new_h, left, top, 1)
+        geom[1:, 0], geom[1:, 1], geom[1:, 2], geom[1:, 3] = crop_w, crop_h, OUT, OUT
+        ks_h = max(_ksize([img_w], [new_w], 2.0), _ksize(crop_w, OUT, 1.0) if n_views else 0)
+        ks_v = max(_ksize([img_h], [new_h], 2.0), _ksize(crop_h, OUT, 1.0) if n_views else 0)
+        hdr[0, 2:4] = 0
+        return ViewPlan(hdr=hdr, hb=None, hk=None, vb=None, vk=None, vflag=vflag, wts=wts, omm=omm, n_ops=n_ops,
+                        ops=op_codes, mats=mats, tmp_rows=img_h, geom=geom, ks_h=ks_h, ks_v=ks_v)
     # taps of all random crops at once (the crop is resized as an image of its own: F.resized_crop)
     hb = np.zeros((V, OUT, 2), dtype=np.int32)
     vb = np.zeros((V, OUT, 2), dtype=np.int32)
@@ -256,7 +275,12 @@ def run_plan(image_u8: torch.Tensor, plan: ViewPlan, device) -> torch.Tensor:
         return torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
     tmp = torch.empty(V, plan.tmp_rows, OUT, 3, dtype=torch.uint8, device=dev)
     x_orig = torch.empty(V, OUT, OUT, 3, dtype=torch.uint8, device=dev)
-    ops.resample_u8(src, d(plan.hdr), d(plan.hb), d(plan.hk), d(plan.vb), d(plan.vk), OUT, OUT, tmp, x_orig)
+    hdr = d(plan.hdr)
+    if plan.geom is not None:
+        hb, hk, vb, vk = ops.resample_taps(d(plan.geom), OUT, plan.ks_h, plan.ks_v, hdr)
+    else:
+        hb, hk, vb, vk = d(plan.hb), d(plan.hk), d(plan.vb), d(plan.vk)
+    ops.resample_u8(src, hdr, hb, hk, vb, vk, OUT, OUT, tmp, x_orig)
     out = torch.empty(V, 3, OUT, OUT, dtype=torch.float32, device=dev)
     ops.augmix_views(x_orig, d(plan.vflag), d(plan.wts), d(plan.omm), d(plan.n_ops), d(plan.ops), d(plan.mats), MEAN, STD,
                      out)
@@ -276,7 +300,7 @@ class AugMixAugmenter:
 
     def views(self, x) -> torch.Tensor:
         img = _to_u8_hwc(x)
-        plan = sample_plan(img.shape[1], img.shape[0], self.n_views, self.augmix, self.severity)
+        plan = sample_plan(img.shape[1], img.shape[0], self.n_views, self.augmix, self.severity, host_taps=False)
         return run_plan(img, plan, self.device)
 
     def __call__(self, x):

@@ -418,3 +418,14 @@ def augmix_views(x_orig, vflag, wts, omm, n_ops, op_codes, mats, mean, std, out)
     call("rlcf_augmix_views", ptr(x_orig), V, ptr(vflag), ptr(wts), ptr(omm), ptr(n_ops), ptr(op_codes), ptr(mats),
          float(mean[0]), float(mean[1]), float(mean[2]), float(std[0]), float(std[1]), float(std[2]), ptr(out), stream())
     return out
+
+
+def resample_taps(geom, out, ks_h, ks_v, hdr):
+    """Pillow's tap tables on the device (see rlcf_resample_taps): returns (hb, hk, vb, vk) and fills hdr[:, 2:4]."""
+    _chk(geom, torch.int32, "geom"); _chk(hdr, torch.int32, "hdr")
+    V, dev = geom.shape[0], geom.device
+    hb = torch.empty(V, out, 2, dtype=torch.int32, device=dev); vb = torch.empty_like(hb)
+    hk = torch.empty(V, out, ks_h, dtype=torch.int32, device=dev)
+    vk = torch.empty(V, out, ks_v, dtype=torch.int32, device=dev)
+    call("rlcf_resample_taps", ptr(geom), V, out, ks_h, ks_v, ptr(hdr), ptr(hb), ptr(hk), ptr(vb), ptr(vk), stream())
+    return hb, hk, vb, vk

@@ -151,7 +151,7 @@ class ImageFolderViews(torch.utils.data.Dataset):
     def __getitem__(self, i):
         img, label = self.folder[self.idx[i]]
         u8 = datautils._to_u8_hwc(img)
-        plan = datautils.sample_plan(u8.shape[1], u8.shape[0], self.n_views, self.augmix, self.severity)
+        plan = datautils.sample_plan(u8.shape[1], u8.shape[0], self.n_views, self.augmix, self.severity, host_taps=False)
         return (u8, plan), torch.tensor(label)
 
 

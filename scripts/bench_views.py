@@ -17,7 +17,7 @@ for augmix in (False, True):
     torch.cuda.synchronize()
     n = 30
     t0 = time.perf_counter()
-    plans = [D.sample_plan(500, 375, 63, augmix) for _ in range(n)]
+    plans = [D.sample_plan(500, 375, 63, augmix, host_taps=False) for _ in range(n)]
     t_plan = (time.perf_counter() - t0) / n
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -35,5 +35,5 @@ for augmix in (False, True):
     print(f"augmix={augmix}: host plan {t_plan*1e3:.2f} ms/img, upload+kernels {t_run*1e3:.2f} ms/img (wall) "
           f"{e0.elapsed_time(e1)/n:.2f} ms/img (device) -> {1/(t_plan+t_run):.0f} img/s single-threaded; "
           f"PIL pipeline (1 thread) {t_pil*1e3:.1f} ms/img = {1/t_pil:.1f} img/s; "
-          f"bytes uploaded per image {u8.numel() + sum(a.nbytes for a in (p.hdr,p.hb,p.hk,p.vb,p.vk,p.vflag,p.wts,p.omm,p.n_ops,p.ops,p.mats))} "
+          f"bytes uploaded per image {u8.numel() + sum(a.nbytes for a in (p.hdr,p.geom,p.vflag,p.wts,p.omm,p.n_ops,p.ops,p.mats))} "
           f"vs {64*3*224*224*4} of fp32 views", flush=True)

@@ -73,3 +73,22 @@ def test_driver_on_an_image_folder_with_gpu_views(tmp_path):
     top1, top5 = res["A"]
     assert 0.0 <= top1 <= top5 <= 100.0
     assert args.n_images == 6 and args.n_classes == 6
+
+
+def test_device_tap_tables_equal_the_host_restatement_of_pillow():
+    """rlcf_resample_taps (device, double precision) against datautils.resample_taps_batch (numpy restatement of
+    Pillow's precompute_coeffs, itself pinned to PIL in tests/test_datautils_host_cpu.py): bit-identical tables."""
+    from rlcf_b200 import datautils as D, ops
+    for (w, h, seed) in ((500, 375, 1), (427, 640, 2), (200, 150, 3), (3000, 2000, 4), (224, 224, 5)):
+        torch.manual_seed(seed); np.random.seed(seed)
+        host = D.sample_plan(w, h, 15, False, host_taps=True)
+        torch.manual_seed(seed); np.random.seed(seed)
+        dev = D.sample_plan(w, h, 15, False, host_taps=False)
+        hdr = torch.from_numpy(dev.hdr).to(DEV)
+        hb, hk, vb, vk = ops.resample_taps(torch.from_numpy(dev.geom).to(DEV), 224, dev.ks_h, dev.ks_v, hdr)
+        assert np.array_equal(hdr.cpu().numpy(), host.hdr)
+        assert np.array_equal(hb.cpu().numpy(), host.hb) and np.array_equal(vb.cpu().numpy(), host.vb)
+        for got, want in ((hk.cpu().numpy(), host.hk), (vk.cpu().numpy(), host.vk)):
+            k = min(got.shape[2], want.shape[2])
+            assert np.array_equal(got[:, :, :k], want[:, :, :k])
+            assert not got[:, :, k:].any() and not want[:, :, k:].any()
