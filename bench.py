@@ -115,7 +115,19 @@ class NvmlSampler:
                 "reasons": sorted(self.reasons), "source": "nvml"}
 
 
+class NullSampler:
+    """RLCF_BENCH_SAMPLER=off: no sampling (only to measure what the sampling itself costs)."""
+
+    def start(self):
+        pass
+
+    def stop(self):
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampling disabled"]}
+
+
 def make_sampler(gpu_index: int):
+    if os.environ.get("RLCF_BENCH_SAMPLER", "nvml") == "off":
+        return NullSampler()
     if os.environ.get("RLCF_BENCH_SAMPLER", "nvml") == "nvml":
         try:
             return NvmlSampler(gpu_index)
@@ -362,9 +374,16 @@ def run_b200(args):
     host_in = [b.cpu().pin_memory() for b in batches]
     host_out = torch.empty(B, wl["n_classes"], dtype=torch.float32).pin_memory()
     pipe = None if (args.no_graph or not hasattr(eng, "host_pipeline")) else eng.host_pipeline()
-    if pipe is not None:   # warm the copy path
-        pipe.submit(host_in[0], 0)
-        pipe.run(0, host_out)
+    if pipe is not None:
+        # warm the copy path and bring clocks / power back to their steady regime (pinning the host buffers above
+        # left the GPU idle for seconds; timing right after would measure a boost transient, not throughput)
+        t_warm = time.perf_counter()
+        while time.perf_counter() - t_warm < 2.0:
+            pipe.submit(host_in[0], 0)
+            pipe.submit(host_in[1], 1)
+            pipe.run(0, host_out)
+            pipe.run(1, host_out)
+            torch.cuda.synchronize()
     barrier()
     e0.record()
     if pipe is not None:
