@@ -7,7 +7,7 @@
 Workload (BASELINE.json configs[1]): policy ViT-B/16, reward ViT-L/14, 64 views per image,
 rho = 0.1 -> 6 selected views, K = 3 sampled classes, C = 200 classes, 1 TTA step, LayerNorm-only tuning,
 synthetic 224x224 views and random-init CLIP weights (no datasets / checkpoints offline).
-One "step" adapts `--images-per-step` independent test images in one batched launch sequence (CUDA graph):
+One "step" adapts `--images-per-step` (default 32) independent test images in one batched launch sequence (CUDA graph):
 reset -> 64-view policy forward -> entropy selection -> reward forward on the selected views -> top-K/CLIPScore/
 reward-weighted CE -> backward to the LayerNorm parameters -> AdamW -> adapted 1-view prediction.
 Prints ONE JSON line on rank 0 (see the task contract for the keys).
@@ -39,7 +39,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--images-per-step", type=int, default=16)
+    ap.add_argument("--images-per-step", type=int, default=None,
+                    help="independent test images adapted per launch sequence (default 32 for --mode ln, 8 otherwise)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5],
                     help="BASELINE.json configs index: 2 = the metric's workload (default); 3 = same with 3 TTA steps; "
                          "5 = ViT-L/14 policy LN-tuning (informational)")
@@ -287,7 +288,7 @@ def run_b200(args):
 
     K = args.steps if args.steps is not None else 10
     W = max(3, args.warmup if args.warmup is not None else 3)
-    B = args.images_per_step
+    B = args.images_per_step if args.images_per_step is not None else (32 if args.mode == "ln" else 8)
     wl = dict(WORKLOAD)
     if args.config == 3:
         wl["tta_steps"] = 3
@@ -416,8 +417,8 @@ def run_b200(args):
     flops_img = eng.algorithmic_flops_per_image()
     step_tflops = flops_img * value / world / 1e12
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
-    if os.path.exists(tpath) and B == 16:   # DRAM bytes per GEMM launch from the committed ncu capture of this workload
+    tpath = os.path.join(ROOT, "profiles", {16: "r1_gemm_traffic.json", 32: "r1_gemm_traffic_b32.json"}.get(B, "none"))
+    if os.path.exists(tpath) and args.mode == "ln" and args.config == 2:   # DRAM bytes per GEMM launch from the committed ncu capture of this workload
         with open(tpath) as f:
             tj = json.load(f)
         traffic, traffic_src = tj["dram_bytes_per_launch_avg"], tj["source"]
