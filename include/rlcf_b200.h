@@ -33,7 +33,8 @@ enum {
   RLCF_EPI_GELU_F16 = 1,     /* u = alpha*acc + bias; aux_out16 = u; out16 = u*sigmoid(1.702u)  (model.py:166-168) */
   RLCF_EPI_RESID_F32 = 2,    /* out32 = alpha*acc + bias + resid32                         (model.py:190-191) */
   RLCF_EPI_GELU_BWD_F16 = 3, /* out16 = alpha*acc * quickgelu'(aux_in16)                   */
-  RLCF_EPI_F32 = 4           /* out32 = alpha*acc + bias                                   */
+  RLCF_EPI_F32 = 4,          /* out32 = alpha*acc + bias                                   */
+  RLCF_EPI_ADAMW = 5         /* out32 (= the parameter) <- AdamW(param, m, v, alpha*acc): rlcf_gemm_wgrad_adamw only */
 };
 
 int rlcf_abi_version(void);
@@ -274,7 +275,9 @@ int rlcf_tied_rows_grad(const float* dx, const int64_t* tokens, int n_sets, int 
 int rlcf_adamw_full(float* params, float* m, float* v, const float* grads, int n_sets, int64_t p_total, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int step, float loss_scale,
                     const float* params_in, int64_t params_in_stride, int fresh_state, void* w16, int64_t w16_stride,
-                    int64_t n16, void* stream);
+                    int64_t n16, int64_t set_stride, void* stream);
+/* (set_stride: floats between consecutive samples' vectors in params / m / v / grads; 0 = p_total.  A larger stride
+ * updates a sub-range of every sample's vector, e.g. everything after the GEMM weights that rlcf_gemm_wgrad_adamw owns.) */
 /* out16[g][c][r] = in16[g][r][c] for n_sets matrices laid out set_stride elements apart (in and out share it). */
 int rlcf_transpose_f16_sets(const void* in, int rows, int cols, void* out, int n_sets, int64_t set_stride,
                             void* stream);
@@ -314,6 +317,20 @@ int rlcf_transpose_blocks_colsum(const void* in, int n_sets, int rows_per_set, i
  * origin and the flip flag, are the caller's). */
 int rlcf_resample_taps(const int32_t* geom, int n_views, int out, int ks_h, int ks_v, int32_t* hdr, int32_t* hb,
                        int32_t* hk, int32_t* vb, int32_t* vk, void* stream);
+
+/* Weight gradient + optimizer in ONE kernel: for every group g (test sample), dW_g = A_g @ B_g^T (A = dY^T [N_out, K =
+ * rows], B = X^T [N_in, K]) is accumulated in TMEM and the epilogue applies torch.optim.AdamW to the sample's fp32 master
+ * weight tile right there: it reads the parameter (from params_in + g*params_in_gs; pass the shared initial copy with
+ * stride 0 for the first step) and the moments (skipped when fresh_state), writes parameter / moments back and the
+ * fp16 copy the next forward reads -- the gradient never goes to HBM (8 B per weight per step less traffic than a
+ * wgrad GEMM followed by rlcf_adamw_full).  The accumulator carries loss_scale; bias correction uses `step`.
+ * Replaces autograd's wgrad + torch.optim.AdamW.step + autocast's cast for one Linear weight
+ * (TPT/tpt_cls_rl.py:76-79, retrieval/clip_ret_policy.py:100-103,134-137). */
+int rlcf_gemm_wgrad_adamw(const void* A, int lda, int64_t a_group_stride, const void* B, int ldb, int64_t b_group_stride,
+                          int groups, int n_out, int n_in, int K, float* params, float* m, float* v, int ldp,
+                          int64_t param_group_stride, const float* params_in, int64_t params_in_gs, int fresh_state,
+                          void* w16, int64_t w16_group_stride, float lr, float beta1, float beta2, float eps,
+                          float weight_decay, int step, float loss_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librlcf_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "rlcf_b200.h")
 
-EPI_F16, EPI_GELU_F16, EPI_RESID_F32, EPI_GELU_BWD_F16, EPI_F32 = range(5)
+EPI_F16, EPI_GELU_F16, EPI_RESID_F32, EPI_GELU_BWD_F16, EPI_F32, EPI_ADAMW = range(6)
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
@@ -67,12 +67,15 @@ _PROTOS = {
     "rlcf_retrieval_loss": [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp],
     "rlcf_dfeat_partial": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "rlcf_rowdot": [_vp, _vp, _i, _i, _f, _vp, _i64, _vp],
-    "rlcf_adamw_full": [_vp, _vp, _vp, _vp, _i, _i64, _f, _f, _f, _f, _f, _i, _f, _vp, _i64, _i, _vp, _i64, _i64, _vp],
+    "rlcf_adamw_full": [_vp, _vp, _vp, _vp, _i, _i64, _f, _f, _f, _f, _f, _i, _f, _vp, _i64, _i, _vp, _i64, _i64, _i64,
+                        _vp],
     "rlcf_transpose_f16_sets": [_vp, _i, _i, _vp, _i, _i64, _vp],
     "rlcf_resample_u8": [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp],
     "rlcf_resample_taps": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "rlcf_augmix_views": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _vp, _vp],
     "rlcf_transpose_blocks_colsum": [_vp, _i, _i, _i, _i, _i, _i64, _vp, _i64, _vp, _i64, _vp],
+    "rlcf_gemm_wgrad_adamw": [_vp, _i, _i64, _vp, _i, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i64, _vp, _i64, _i, _vp,
+                              _i64, _f, _f, _f, _f, _f, _i, _f, _vp],
     "rlcf_add_rows": [_vp, _i64, _vp, _i64, _i, _i64, _vp, _vp],
     "rlcf_scale_rows_exp": [_vp, _vp, _i64, _i, _i, _vp, _vp],
     "rlcf_tied_rows_grad": [_vp, _vp, _i, _i, _i, _vp, _vp, _i64, _vp],

@@ -1,6 +1,7 @@
 // extern "C" surface of librlcf_b200.so (declared in include/rlcf_b200.h) plus the small amount of
 // process-wide state the library keeps: last-error text, launch counter, GEMM CTA-group mode.
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -115,7 +116,7 @@ int retrieval_loss(const float*, long long, const float*, const float*, int, int
 int dfeat_partial(const float*, const float*, int, int, int, int, float*, cudaStream_t);
 int rowdot(const float*, const float*, int, int, float, float*, long long, cudaStream_t);
 int adamw_full(float*, float*, float*, const float*, int, long long, float, float, float, float, float, int, float,
-               const float*, long long, int, __half*, long long, long long, cudaStream_t);
+               const float*, long long, int, __half*, long long, long long, long long, cudaStream_t);
 int transpose_f16(const __half*, int, int, __half*, int, long long, cudaStream_t);
 int resample_u8(const uint8_t*, int, int, int, const int*, const int*, const int*, int, const int*, const int*, int, int,
                 int, uint8_t*, int, uint8_t*, cudaStream_t);
@@ -428,10 +429,10 @@ int rlcf_tied_rows_grad(const float* dx, const int64_t* tokens, int n_sets, int 
 int rlcf_adamw_full(float* params, float* m, float* v, const float* grads, int n_sets, int64_t p_total, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int step, float loss_scale,
                     const float* params_in, int64_t params_in_stride, int fresh_state, void* w16, int64_t w16_stride,
-                    int64_t n16, void* stream) {
+                    int64_t n16, int64_t set_stride, void* stream) {
   if (!params || !m || !v || !grads || !params_in) return set_error(RLCF_ERR_ARG, "adamw_full: null pointer");
   return adamw_full(params, m, v, grads, n_sets, p_total, lr, beta1, beta2, eps, weight_decay, step, loss_scale,
-                    params_in, params_in_stride, fresh_state, H(w16), w16_stride, n16, S(stream));
+                    params_in, params_in_stride, fresh_state, H(w16), w16_stride, n16, set_stride, S(stream));
 }
 
 int rlcf_transpose_f16_sets(const void* in, int rows, int cols, void* out, int n_sets, int64_t set_stride,
@@ -468,6 +469,25 @@ int rlcf_resample_taps(const int32_t* geom, int n_views, int out, int ks_h, int 
                        int32_t* hk, int32_t* vb, int32_t* vk, void* stream) {
   if (!geom || !hdr || !hb || !hk || !vb || !vk) return set_error(RLCF_ERR_ARG, "resample_taps: null pointer");
   return resample_taps(geom, n_views, out, ks_h, ks_v, hdr, hb, hk, vb, vk, S(stream));
+}
+
+int rlcf_gemm_wgrad_adamw(const void* A, int lda, int64_t a_group_stride, const void* B, int ldb, int64_t b_group_stride,
+                          int groups, int n_out, int n_in, int K, float* params, float* m, float* v, int ldp,
+                          int64_t param_group_stride, const float* params_in, int64_t params_in_gs, int fresh_state,
+                          void* w16, int64_t w16_group_stride, float lr, float beta1, float beta2, float eps,
+                          float weight_decay, int step, float loss_scale, void* stream) {
+  if (!A || !B || !params || !m || !v || !params_in) return set_error(RLCF_ERR_ARG, "gemm_wgrad_adamw: null pointer");
+  if (step < 1 || loss_scale <= 0.f) return set_error(RLCF_ERR_ARG, "gemm_wgrad_adamw: bad step / loss_scale");
+  if (groups > 1 && (params_in_gs % 4 != 0 || w16_group_stride % 4 != 0))
+    return set_error(RLCF_ERR_ARG, "gemm_wgrad_adamw: group strides must be multiples of 4 elements");
+  AdamwEpi o;
+  o.m = m; o.v = v; o.p_in = params_in; o.p_in_gs = params_in_gs; o.w16 = H(w16); o.w16_gs = w16_group_stride;
+  o.fresh = fresh_state; o.lr = lr; o.b1 = beta1; o.b2 = beta2; o.eps = eps; o.wd = weight_decay;
+  o.bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), step));
+  o.bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), step)));
+  return gemm_f16_grouped(CH(A), lda, a_group_stride, CH(B), ldb, b_group_stride, groups, n_out, n_in, K, EPI_ADAMW,
+                          1.0f / loss_scale, nullptr, 0, nullptr, nullptr, nullptr, params, ldp, param_group_stride,
+                          S(stream), &o);
 }
 
 }  // extern "C"

@@ -55,7 +55,17 @@ struct GemmArgs {
   int ldo;               // leading dimension of out / resid / aux (elements)
   float alpha;           // scale applied to the accumulator before the epilogue
   int debug_nostore;     // RLCF_GEMM_DEBUG_NOSTORE=1: skip the epilogue's global traffic (timing probe only)
+  AdamwEpi opt;          // EPI_ADAMW only
 };
+
+// torch.optim.AdamW, single-tensor order: decoupled decay, moment updates, bias-corrected step (as adamw_full_kernel)
+__device__ __forceinline__ float adamw_elem(float p0, float g, float& m, float& v, const AdamwEpi& o) {
+  const float w = p0 * (1.f - o.lr * o.wd);
+  m = m + (g - m) * (1.f - o.b1);
+  v = v * o.b2 + (1.f - o.b2) * g * g;
+  const float denom = sqrtf(v) / o.bc2_sqrt + o.eps;
+  return w - (o.lr / o.bc1) * (m / denom);
+}
 
 // kMc = CTA pairs per cluster (cta_group::2 only).  With kMc == 2 a 4-CTA cluster computes a 512 x 256 super tile:
 // the two pairs share the B (weight) tile, which pair 0 loads once and TMA-multicasts into both pairs' shared
@@ -272,7 +282,29 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           q.x = fmaf(q.x, p.alpha, b4.x); q.y = fmaf(q.y, p.alpha, b4.y);
           q.z = fmaf(q.z, p.alpha, b4.z); q.w = fmaf(q.w, p.alpha, b4.w);
           if (4 * i < rows_left) {
-            if constexpr (kEpi == EPI_RESID_F32 || kEpi == EPI_F32) {
+            if constexpr (kEpi == EPI_ADAMW) {
+              // q = unscaled weight gradient of 4 adjacent weights: optimizer step on the fp32 master tile in place
+              const size_t e = goff + i * gstep;
+              const size_t e_in = e - static_cast<size_t>(g * p.out_gs) + static_cast<size_t>(g * p.opt.p_in_gs);
+              const float4 pw = *reinterpret_cast<const float4*>(p.opt.p_in + e_in);
+              float4 mm = make_float4(0.f, 0.f, 0.f, 0.f), vv = mm;
+              if (!p.opt.fresh) {
+                mm = *reinterpret_cast<const float4*>(p.opt.m + e);
+                vv = *reinterpret_cast<const float4*>(p.opt.v + e);
+              }
+              float4 w;
+              w.x = adamw_elem(pw.x, q.x, mm.x, vv.x, p.opt); w.y = adamw_elem(pw.y, q.y, mm.y, vv.y, p.opt);
+              w.z = adamw_elem(pw.z, q.z, mm.z, vv.z, p.opt); w.w = adamw_elem(pw.w, q.w, mm.w, vv.w, p.opt);
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + e) = w;
+              *reinterpret_cast<float4*>(p.opt.m + e) = mm;
+              *reinterpret_cast<float4*>(p.opt.v + e) = vv;
+              if (p.opt.w16 != nullptr) {
+                const size_t e16 = e - static_cast<size_t>(g * p.out_gs) + static_cast<size_t>(g * p.opt.w16_gs);
+                __half2 h0 = __floats2half2_rn(w.x, w.y), h1 = __floats2half2_rn(w.z, w.w);
+                *reinterpret_cast<uint2*>(p.opt.w16 + e16) =
+                    make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+              }
+            } else if constexpr (kEpi == EPI_RESID_F32 || kEpi == EPI_F32) {
               if constexpr (kEpi == EPI_RESID_F32) { q.x += z[i].x; q.y += z[i].y; q.z += z[i].z; q.w += z[i].w; }
               *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + goff + i * gstep) = q;
             } else {
@@ -392,8 +424,9 @@ int gemm_f16(const __half* A, int lda, const __half* B, int ldb, int M, int N, i
 int gemm_f16_grouped(const __half* A, int lda, long long a_gs, const __half* B, int ldb, long long b_gs, int G, int M,
                      int N, int K, int epi, float alpha, const float* bias, long long bias_gs, const float* resid,
                      const __half* aux_in, __half* aux_out, void* out, int ldo, long long out_gs,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, const AdamwEpi* adamw) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(RLCF_ERR_ARG, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  if ((epi == EPI_ADAMW) != (adamw != nullptr)) return set_error(RLCF_ERR_ARG, "gemm: EPI_ADAMW needs optimizer state");
   if (G <= 0) return set_error(RLCF_ERR_ARG, "gemm: G=%d groups", G);
   if (G > 1 && (out_gs % 8 != 0 || bias_gs % 4 != 0 || out_gs < 0 || bias_gs < 0))
     return set_error(RLCF_ERR_ARG, "gemm: group strides of out (%lld) / bias (%lld) must be multiples of 8 / 4", out_gs,
@@ -410,7 +443,8 @@ int gemm_f16_grouped(const __half* A, int lda, long long a_gs, const __half* B, 
   if (int rc = make_tmap_f16(&tb, B, N, K, ldb, G, b_gs, kBN / cg)) return rc;
   static const int debug_nostore = getenv("RLCF_GEMM_DEBUG_NOSTORE") != nullptr;
   GemmArgs args{M, N, K, G, G > 1 ? out_gs : 0, G > 1 ? bias_gs : 0, epi, bias, resid, aux_in, aux_out, out, ldo,
-                alpha, debug_nostore};
+                alpha, debug_nostore, adamw != nullptr ? *adamw : AdamwEpi{}};
+  if (G == 1) { args.opt.p_in_gs = 0; args.opt.w16_gs = 0; }
   // multicast pays once there are at least two 256-row tiles per cluster slot; tiny problems keep 2-CTA clusters
   const bool mc = cg == 2 && gemm_multicast() && M > 2 * kBM * 2;
   switch (epi) {
@@ -423,6 +457,7 @@ int gemm_f16_grouped(const __half* A, int lda, long long a_gs, const __half* B, 
     RLCF_GEMM_CASE(EPI_RESID_F32)
     RLCF_GEMM_CASE(EPI_GELU_BWD_F16)
     RLCF_GEMM_CASE(EPI_F32)
+    RLCF_GEMM_CASE(EPI_ADAMW)
 #undef RLCF_GEMM_CASE
   }
   return set_error(RLCF_ERR_ARG, "gemm: unknown epilogue %d", epi);

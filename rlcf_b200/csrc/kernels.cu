@@ -922,9 +922,9 @@ __global__ void __launch_bounds__(256)
 adamw_full_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ grads,
                   long long p4, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
                   float inv_scale, const float* __restrict__ p_in, long long p_in_stride, int fresh,
-                  __half* __restrict__ w16, long long w16_stride, long long n16_4) {
+                  __half* __restrict__ w16, long long w16_stride, long long n16_4, long long set_stride4) {
   const long long set = blockIdx.y;
-  const long long base = set * p4;   // in float4 units
+  const long long base = set * set_stride4;   // in float4 units
   float4* P = reinterpret_cast<float4*>(p) + base;
   float4* M = reinterpret_cast<float4*>(m) + base;
   float4* V = reinterpret_cast<float4*>(v) + base;
@@ -968,9 +968,11 @@ adamw_full_kernel(float* __restrict__ p, float* __restrict__ m, float* __restric
 int adamw_full(float* params, float* m, float* v, const float* grads, int n_sets, long long p_total, float lr,
                float b1, float b2, float eps, float wd, int step, float loss_scale, const float* params_in,
                long long params_in_stride, int fresh, __half* w16, long long w16_stride, long long n16,
-               cudaStream_t stream) {
+               long long set_stride, cudaStream_t stream) {
   if (n_sets <= 0 || n_sets > 65535 || p_total <= 0 || step < 1) return set_error(RLCF_ERR_ARG, "adamw_full: bad shape");
-  if (p_total % 4 || params_in_stride % 4 || n16 % 4 || w16_stride % 4 || n16 > p_total)
+  if (set_stride == 0) set_stride = p_total;
+  if (p_total % 4 || params_in_stride % 4 || n16 % 4 || w16_stride % 4 || n16 > p_total || set_stride % 4 ||
+      set_stride < p_total)
     return set_error(RLCF_ERR_ARG, "adamw_full: sizes and strides must be multiples of 4 elements");
   const double bc1 = 1.0 - pow(static_cast<double>(b1), step);
   const double bc2 = 1.0 - pow(static_cast<double>(b2), step);
@@ -982,7 +984,7 @@ int adamw_full(float* params, float* m, float* v, const float* grads, int n_sets
   dim3 grid(static_cast<unsigned>(bx), n_sets);
   adamw_full_kernel<<<grid, 256, 0, stream>>>(params, m, v, grads, p4, lr, b1, b2, eps, wd, static_cast<float>(bc1),
                                               static_cast<float>(sqrt(bc2)), 1.f / loss_scale, params_in,
-                                              params_in_stride, fresh, w16, w16_stride, n16 / 4);
+                                              params_in_stride, fresh, w16, w16_stride, n16 / 4, set_stride / 4);
   RLCF_CHECK_LAUNCH("adamw_full");
   return 0;
 }

@@ -17,7 +17,21 @@ enum : int {
   EPI_RESID_F32 = RLCF_EPI_RESID_F32,
   EPI_GELU_BWD_F16 = RLCF_EPI_GELU_BWD_F16,
   EPI_F32 = RLCF_EPI_F32,
-  EPI_COUNT = 5,
+  EPI_ADAMW = RLCF_EPI_ADAMW,
+  EPI_COUNT = 6,
+};
+
+// Optimizer state of the fused wgrad + AdamW epilogue (EPI_ADAMW); all pointers address the weight's [n_out, n_in] tile
+// of group 0, group g is `*_gs` elements further.
+struct AdamwEpi {
+  float* m = nullptr;
+  float* v = nullptr;
+  const float* p_in = nullptr;   // parameters are read here (written to GemmArgs::out)
+  long long p_in_gs = 0;
+  __half* w16 = nullptr;
+  long long w16_gs = 0;
+  int fresh = 0;                 // 1: moments start from zero (first step after reset)
+  float lr = 0, b1 = 0, b2 = 0, eps = 0, wd = 0, bc1 = 1, bc2_sqrt = 1;
 };
 
 int set_error(int code, const char* fmt, ...);
@@ -40,7 +54,7 @@ int gemm_f16(const __half* A, int lda, const __half* B, int ldb, int M, int N, i
 int gemm_f16_grouped(const __half* A, int lda, long long a_gs, const __half* B, int ldb, long long b_gs, int G, int M,
                      int N, int K, int epi, float alpha, const float* bias, long long bias_gs, const float* resid,
                      const __half* aux_in, __half* aux_out, void* out, int ldo, long long out_gs,
-                     cudaStream_t stream);
+                     cudaStream_t stream, const AdamwEpi* adamw = nullptr);
 
 // Checks the launch of the kernel that was just enqueued.
 #define RLCF_CHECK_LAUNCH(name)                                                                 \

@@ -13,6 +13,8 @@ dgrad of the selected views); what is new is
 """
 from __future__ import annotations
 
+from dataclasses import dataclass
+
 import torch
 
 from . import engine as E
@@ -148,12 +150,39 @@ def transpose_weights(lay, w16: torch.Tensor, w16t: torch.Tensor):
             ops.transpose_f16_sets(w16.view(-1)[off:], r, c, w16t.view(-1)[off:], G, w16.stride(0))
 
 
-def adamw_weights(lay, rest, rest_m, rest_v, grads, w16, w16t, cfg, step, params_in, params_in_stride, fresh):
+# Default for the engines' `fused_adamw`: the weight-gradient GEMMs apply AdamW in their epilogue (the gradient of a GEMM
+# weight never reaches HBM).  False keeps the gradients in `grads` (what the gradient-parity tests read).
+FUSED_ADAMW = True
+
+
+@dataclass
+class FusedAdamw:
+    """What the fused wgrad + AdamW epilogue needs besides the GEMM operands (one optimizer step of all samples)."""
+    rest: torch.Tensor          # fp32 masters [G, total] (written)
+    m: torch.Tensor
+    v: torch.Tensor
+    w16: torch.Tensor           # fp16 GEMM copies [G, p_gemm] (written)
+    p_in: torch.Tensor          # where the parameters are read: the shared initial vector (stride 0) or `rest`
+    p_in_gs: int
+    fresh: bool
+    cfg: object
+    step: int
+
+
+def adamw_weights(lay, rest, rest_m, rest_v, grads, w16, w16t, cfg, step, params_in, params_in_stride, fresh,
+                  fused: bool = False):
     """AdamW over every sample's non-LayerNorm parameters + refreshed fp16 GEMM copies in the same pass; the transposed
-    copies follow only when another backward will use them (w16t not None)."""
-    ops.adamw_full(rest, rest_m, rest_v, grads, rest.shape[0], rest.shape[1], cfg.lr, step, params_in, params_in_stride,
-                   fresh, w16=w16, n16=lay.p_gemm, beta1=cfg.betas[0], beta2=cfg.betas[1], eps=cfg.eps,
-                   weight_decay=cfg.weight_decay, loss_scale=cfg.loss_scale)
+    copies follow only when another backward will use them (w16t not None).  fused=True: the GEMM weights were already
+    updated by the wgrad epilogues (FusedAdamw), only the rest of the vector (embeddings, projection, biases) is left."""
+    kw = dict(beta1=cfg.betas[0], beta2=cfg.betas[1], eps=cfg.eps, weight_decay=cfg.weight_decay,
+              loss_scale=cfg.loss_scale)
+    if fused:
+        g, tot = lay.p_gemm, rest.shape[1]
+        ops.adamw_full(rest.view(-1)[g:], rest_m.view(-1)[g:], rest_v.view(-1)[g:], grads.view(-1)[g:], rest.shape[0],
+                       tot - g, cfg.lr, step, params_in.view(-1)[g:], params_in_stride, fresh, set_stride=tot, **kw)
+    else:
+        ops.adamw_full(rest, rest_m, rest_v, grads, rest.shape[0], rest.shape[1], cfg.lr, step, params_in,
+                       params_in_stride, fresh, w16=w16, n16=lay.p_gemm, **kw)
     if w16t is not None:
         transpose_weights(lay, w16, w16t)
 
@@ -178,9 +207,10 @@ class WgradHook:
         self.grads = None
         self.n_sets = 0
         self.patches = None
+        self.fused = None
 
-    def bind(self, grads: torch.Tensor, n_sets: int, patches: torch.Tensor):
-        self.grads, self.n_sets, self.patches = grads, n_sets, patches
+    def bind(self, grads: torch.Tensor, n_sets: int, patches: torch.Tensor, fused: "FusedAdamw | None" = None):
+        self.grads, self.n_sets, self.patches, self.fused = grads, n_sets, patches, fused
 
     def _wgrad(self, dY, X, n_out, n_in, off, rows, rows_pad, skip=0, dy_stride_rows=None, bias_off=None):
         """grads[g, off:...] = dY_g^T X_g for every set g (one grouped GEMM over transposed fp16 operands); with
@@ -200,8 +230,18 @@ class WgradHook:
         # one grouped launch: group g = columns [g*rows_pad, (g+1)*rows_pad) of the transposed operands
         ty = self.t_dy.as_strided((ns, n_out, rows_pad), (rows_pad, ld, 1))
         tx = self.t_x.as_strided((ns, n_in, rows_pad), (rows_pad, ld, 1))
-        out = g.as_strided((ns, n_out, n_in), (g.stride(0), n_in, 1), g.storage_offset() + off)
-        ops.gemm_grouped(ty, tx, out, epilogue=EPI_F32)
+        fz = self.fused
+        if fz is None:
+            out = g.as_strided((ns, n_out, n_in), (g.stride(0), n_in, 1), g.storage_offset() + off)
+            ops.gemm_grouped(ty, tx, out, epilogue=EPI_F32)
+            return
+
+        def view(t):   # this weight's [n_out, n_in] tile of every sample's flat vector
+            return t.as_strided((ns, n_out, n_in), (t.stride(0), n_in, 1), t.storage_offset() + off)
+        c = fz.cfg
+        ops.gemm_wgrad_adamw(ty, tx, view(fz.rest), view(fz.m), view(fz.v), fz.p_in.view(-1)[off:], fz.p_in_gs, fz.fresh,
+                             view(fz.w16), c.lr, fz.step, beta1=c.betas[0], beta2=c.betas[1], eps=c.eps,
+                             weight_decay=c.weight_decay, loss_scale=c.loss_scale)
 
     def linear(self, l: int, name: str, dY: torch.Tensor, X: torch.Tensor):
         lay, d = self.lay, self.lay.d
@@ -283,6 +323,14 @@ class FullTuneEngine:
         self.reward_feat = torch.empty(B * S, reward.E, **f32)
         self._graph = None
         self._static_images = None
+        self.fused_adamw = FUSED_ADAMW
+
+    def _fused(self, step):
+        if not self.fused_adamw:
+            return None
+        first = step == 1
+        return FusedAdamw(self.rest, self.rest_m, self.rest_v, self.w16, self.init_rest if first else self.rest,
+                          0 if first else self.lay.total, first, self.cfg, step)
 
     # ------------------------------------------------------------------
     def _loss_and_head_bwd(self, step, xs, runner, ln, pstride, n_sets, w, rows0=0):
@@ -320,10 +368,10 @@ class FullTuneEngine:
         w16t = self.w16t if step < cfg.tta_steps else None
         if step == 1:
             adamw_weights(lay, self.rest, self.rest_m, self.rest_v, self.grads, self.w16, w16t, cfg, step,
-                          self.init_rest, 0, True)
+                          self.init_rest, 0, True, fused=self.fused_adamw)
         else:
             adamw_weights(lay, self.rest, self.rest_m, self.rest_v, self.grads, self.w16, w16t, cfg, step,
-                          self.rest, lay.total, False)
+                          self.rest, lay.total, False, fused=self.fused_adamw)
 
     def tune(self, images: torch.Tensor):
         cfg, B = self.cfg, self.n_img
@@ -343,7 +391,7 @@ class FullTuneEngine:
                               store=self.store)
         self.partials.zero_()
         self._loss_and_head_bwd(1, xs, self.run, self.ln, P, B, pol)
-        hk.bind(self.grads, B, self.run.patches)
+        hk.bind(self.grads, B, self.run.patches, fused=self._fused(1))
         hk.proj()
         self.run.backward(self.store, B, S, self.ln, P, self.partials, self.n_slots, hook=hk)
         self._adamw(1)
@@ -353,7 +401,7 @@ class FullTuneEngine:
             xs = self.run.forward(B * S, self.ln, pstride=P, seqs_per_set=S, images=images, view_idx=self.sel_global,
                                   store=self.store, w=self.gw)
             self._loss_and_head_bwd(step, xs, self.run, self.ln, P, B, self.gw)
-            hk.bind(self.grads, B, self.run.patches)
+            hk.bind(self.grads, B, self.run.patches, fused=self._fused(step))
             hk.proj()
             self.run.backward(self.store, B, S, self.ln, P, self.partials, self.n_slots, w=self.gw, hook=hk)
             self._adamw(step)

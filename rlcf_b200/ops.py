@@ -378,15 +378,16 @@ def tied_rows_grad(dx, tokens, n_sets, L, d, g_tok, g_pos, out_stride):
 
 
 def adamw_full(params, m, v, grads, n_sets, p_total, lr, step, params_in, params_in_stride, fresh, w16=None, n16=0,
-               beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2, loss_scale=1.0):
+               beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2, loss_scale=1.0, set_stride=0):
     """Streaming AdamW over whole per-sample parameter vectors [n_sets, p_total]; also writes the fp16 copy of the first
-    n16 parameters of every sample into w16 [n_sets, >= n16]."""
+    n16 parameters of every sample into w16 [n_sets, >= n16].  set_stride > p_total: params / m / v / grads are base
+    pointers into larger per-sample vectors and only p_total entries of each are updated."""
     for t, nm in ((params, "params"), (m, "m"), (v, "v"), (grads, "grads")):
-        _chk(t, torch.float32, nm)
+        _chk(t, torch.float32, nm, strided=bool(set_stride))
     _chk(params_in, torch.float32, "params_in", strided=True); _chk(w16, torch.float16, "w16")
     call("rlcf_adamw_full", ptr(params), ptr(m), ptr(v), ptr(grads), n_sets, p_total, float(lr), float(beta1),
          float(beta2), float(eps), float(weight_decay), int(step), float(loss_scale), ptr(params_in), params_in_stride,
-         int(bool(fresh)), ptr(w16), 0 if w16 is None else w16.stride(0), n16, stream())
+         int(bool(fresh)), ptr(w16), 0 if w16 is None else w16.stride(0), n16, set_stride, stream())
 
 
 def transpose_f16_sets(src, rows, cols, out, n_sets, set_stride):
@@ -429,3 +430,26 @@ def resample_taps(geom, out, ks_h, ks_v, hdr):
     vk = torch.empty(V, out, ks_v, dtype=torch.int32, device=dev)
     call("rlcf_resample_taps", ptr(geom), V, out, ks_h, ks_v, ptr(hdr), ptr(hb), ptr(hk), ptr(vb), ptr(vk), stream())
     return hb, hk, vb, vk
+
+
+def gemm_wgrad_adamw(a, b, params, m, v, params_in, params_in_gs, fresh, w16, lr, step, beta1=0.9, beta2=0.999, eps=1e-8,
+                     weight_decay=1e-2, loss_scale=1.0):
+    """Fused weight gradient + AdamW (rlcf_gemm_wgrad_adamw): a [G, n_out, K], b [G, n_in, K] fp16 views; params / m / v
+    fp32 [G, n_out, n_in] views of one layout (params is written, params_in -- a base pointer, group stride params_in_gs
+    floats -- is read); w16 fp16 [G, n_out, n_in] view receiving the updated weights (or None)."""
+    for t, nm in ((a, "a"), (b, "b")):
+        if not t.is_cuda or t.dtype != torch.float16 or t.dim() != 3 or t.stride(2) != 1:
+            raise _lib.RlcfError(f"gemm_wgrad_adamw: {nm} must be a 3-D CUDA fp16 tensor with unit inner stride")
+    G, n_out, k = a.shape
+    n_in = b.shape[1]
+    for t, nm in ((params, "params"), (m, "m"), (v, "v")):
+        if t.dtype != torch.float32 or tuple(t.shape) != (G, n_out, n_in) or t.stride() != params.stride() or t.stride(2) != 1:
+            raise _lib.RlcfError(f"gemm_wgrad_adamw: {nm} must be fp32 [G, n_out, n_in] with params' strides")
+    if w16 is not None and (w16.dtype != torch.float16 or tuple(w16.shape) != (G, n_out, n_in)
+                            or w16.stride(1) != params.stride(1) or w16.stride(2) != 1):
+        raise _lib.RlcfError("gemm_wgrad_adamw: w16 must be fp16 [G, n_out, n_in] with params' row stride")
+    _chk(params_in, torch.float32, "params_in", strided=True)
+    call("rlcf_gemm_wgrad_adamw", ptr(a), a.stride(1), a.stride(0), ptr(b), b.stride(1), b.stride(0), G, n_out, n_in, k,
+         ptr(params), ptr(m), ptr(v), params.stride(1), params.stride(0), ptr(params_in), params_in_gs, int(bool(fresh)),
+         ptr(w16), 0 if w16 is None else w16.stride(0), float(lr), float(beta1), float(beta2), float(eps),
+         float(weight_decay), int(step), float(loss_scale), stream())

@@ -120,6 +120,7 @@ class ImageQueryEngine:
         self.seq_idx = torch.arange(Q, device=dev, dtype=torch.int32)
         self._graph = None
         self._static_images = None
+        self.fused_adamw = FT.FUSED_ADAMW
 
     # ------------------------------------------------------------------ initial weights / momentum
     def _cast_initial(self):
@@ -163,7 +164,12 @@ class ImageQueryEngine:
                         self.logit_scale, self.feat, self.inv_norm, Q, 1, base.d, base.E, self.n_chunks, self.run.dres,
                         row_stride=base.L, param_stride=P, partials=self.partials, n_slots=self.n_slots, p_total=P,
                         p_off=off, beta=lnv[off + base.d:], y_out=hk.y, df_out=hk.df, proj_stride=w.proj_stride)
-        hk.bind(self.grads, Q, self.run.patches)
+        fz = None
+        if self.fused_adamw:   # the wgrad GEMMs apply AdamW to the GEMM weights in their epilogue
+            first = step == 1
+            fz = FT.FusedAdamw(self.rest, self.rest_m, self.rest_v, self.w16, self.init_rest if first else self.rest,
+                               0 if first else lay.total, first, cfg, step)
+        hk.bind(self.grads, Q, self.run.patches, fused=fz)
         hk.proj()
         self.run.backward(self.store, Q, 1, self.ln, P, self.partials, self.n_slots, w=w, hook=hk)
         kw = dict(beta1=cfg.betas[0], beta2=cfg.betas[1], eps=cfg.eps, weight_decay=cfg.weight_decay,
@@ -173,10 +179,10 @@ class ImageQueryEngine:
         w16t = self.w16t if step < cfg.tta_steps else None
         if step == 1:   # masters come from the shared initial copy, moments start at zero: no per-query restore
             FT.adamw_weights(lay, self.rest, self.rest_m, self.rest_v, self.grads, self.w16, w16t, cfg, step,
-                             self.init_rest, 0, True)
+                             self.init_rest, 0, True, fused=self.fused_adamw)
         else:
             FT.adamw_weights(lay, self.rest, self.rest_m, self.rest_v, self.grads, self.w16, w16t, cfg, step,
-                             self.rest, lay.total, False)
+                             self.rest, lay.total, False, fused=self.fused_adamw)
 
     def tune(self, images: torch.Tensor):
         """tune_image for n_query images [Q,3,H,W] at once.  Leaves the adapted parameters in self.ln / self.rest."""
@@ -390,6 +396,7 @@ class TextQueryEngine:
         self.reot_rows = torch.empty(Q, **i32)
         self._graph = None
         self._static_images = None
+        self.fused_adamw = FT.FUSED_ADAMW
 
     # ------------------------------------------------------------------
     def momentum_update(self, q: int = 0):
@@ -445,7 +452,9 @@ class TextQueryEngine:
                         row_idx=self.eot_rows, param_stride=P, partials=self.partials, n_slots=self.n_slots,
                         p_total=P, p_off=off, beta=lnv[off + base.d:], y_out=hk.y, df_out=hk.df,
                         proj_stride=w.proj_stride)
-        hk.bind(self.grads, Q, None)
+        fz = FT.FusedAdamw(self.rest, self.rest_m, self.rest_v, self.w16, self.rest, lay.total, step == 1, cfg,
+                           step) if self.fused_adamw else None
+        hk.bind(self.grads, Q, None, fused=fz)
         hk.proj()
         self.run.backward(self.store, Q, 1, self.ln, P, self.partials, self.n_slots, w=w, hook=hk)
         ops.tied_rows_grad(self.run.dres, self.tokens, Q, base.L, base.d, flat_g[lay.tok:], flat_g[lay.pos:], lay.total)
@@ -454,7 +463,8 @@ class TextQueryEngine:
         ops.adamw_step(self.ln, self.ln_m, self.ln_v, self.partials, Q, self.n_slots, P, cfg.lr, step,
                        grad_out=self.ln_grad, **kw)
         FT.adamw_weights(lay, self.rest, self.rest_m, self.rest_v, self.grads, self.w16,
-                         self.w16t if step < cfg.tta_steps else None, cfg, step, self.rest, lay.total, step == 1)
+                         self.w16t if step < cfg.tta_steps else None, cfg, step, self.rest, lay.total, step == 1,
+                         fused=self.fused_adamw)
 
     def tune(self, tokens: torch.Tensor):
         """tune_text for n_query tokenised captions [Q, 77] (int64) at once."""

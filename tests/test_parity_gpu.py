@@ -350,7 +350,14 @@ def test_full_encoder_tuning_matches_oracle(steps):
     eng = FT.FullTuneEngine(to_dev(sd_p), cf.to(DEV), float(sd_p["logit_scale"].exp()), rcfg, 2,
                             E.prepare_visual(to_dev(sd_r)), rc.to(DEV))
     views = O.make_views(2, 16, 64, VIEW_SEED + 3)
+    # default: AdamW fused into the wgrad GEMM epilogues; the unfused sequence (gradients kept in eng.grads, read by the
+    # per-tensor gradient checks below) must give bit-identical parameters and logits
+    assert eng.fused_adamw
+    out_fused = eng.adapt(views.to(DEV)).clone()
+    rest_fused = eng.rest.clone()
+    eng.fused_adamw = False
     out = eng.adapt(views.to(DEV)).cpu()
+    assert torch.equal(out_fused.cpu(), out) and torch.equal(rest_fused, eng.rest)
     ocfg = O.OracleConfig(n_views=16, selection_p=0.25, tta_steps=steps, sample_k=3, lr=cfg["lr"])
     for i in range(2):
         o = O.adapt_one_image(sd_p, cf, views[i * 16:(i + 1) * 16], ocfg, sd_r, rc, tune="full")

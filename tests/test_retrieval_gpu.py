@@ -19,7 +19,15 @@ def to_dev(sd):
     return {k: v.to(DEV) for k, v in sd.items()}
 
 
-def build(cfg, rcfg_o, sd_p, sd_r, gal_p, gal_r, n_query):
+def build(cfg, rcfg_o, sd_p, sd_r, gal_p, gal_r, n_query, fused=False):
+    """fused=False keeps the weight gradients in eng.grads (what the gradient checks read); the fused wgrad + AdamW
+    epilogue is held to bit-identical results in test_fused_adamw_epilogue_is_bit_identical."""
+    eng = _build(cfg, rcfg_o, sd_p, sd_r, gal_p, gal_r, n_query)
+    eng.fused_adamw = fused
+    return eng
+
+
+def _build(cfg, rcfg_o, sd_p, sd_r, gal_p, gal_r, n_query):
     from rlcf_b200 import engine as E, retrieval as R
     rc = R.RetrievalConfig(tta_steps=rcfg_o.tta_steps, sample_k=rcfg_o.sample_k, lr=rcfg_o.lr,
                            weight_decay=rcfg_o.weight_decay, eps=rcfg_o.eps, momentum_update=rcfg_o.momentum_update,
@@ -319,6 +327,7 @@ def test_retrieval_edge_configurations_match_oracle(task, kw):
                                  E.prepare_visual(to_dev(sd_r)), gal_r.to(DEV))
     else:
         eng = R.TextQueryEngine(to_dev(sd_p), gal_p.to(DEV), rc, 2, E.prepare_text(to_dev(sd_r)), gal_r.to(DEV))
+    eng.fused_adamw = False                             # the gradient checks below read eng.grads
     queries = images if i2t else tokens
     assert eng.n_chunks > 1                             # 300 candidates: several gallery chunks
     eng.adapt(queries[:2].to(DEV))
@@ -333,3 +342,23 @@ def test_retrieval_edge_configurations_match_oracle(task, kw):
         tag = f"{task} {kw} q{qi}"
         check_query(eng, qi, out, None, cfg, tag, row0, slack=0.05)
         check_grads_and_params(eng, qi, out, cfg, tag, named_tensors(eng, qi, task))
+
+
+@pytest.mark.parametrize("name", ["ret_i2t_tiny_recipe", "ret_t2i_tiny_recipe", "ret_i2t_tiny_3step"])
+def test_fused_adamw_epilogue_is_bit_identical(name):
+    """rlcf_gemm_wgrad_adamw (AdamW applied in the wgrad GEMM's epilogue, the engines' default) against the unfused
+    sequence wgrad GEMM -> rlcf_adamw_full: same accumulators, same arithmetic -> identical parameters, moments, fp16
+    copies and score rows, bit for bit, over all TTA steps."""
+    z, cfg = load_case(name)
+    i2t = cfg["task"] == "image2text"
+    sd_p, sd_r, images, tokens, rcfg, gal_p, gal_r = retrieval_setup(cfg)
+    rcfg.momentum_update = False
+    nq = cfg["n_query"]
+    queries = (images if i2t else tokens)[:nq].to(DEV)
+    res = {}
+    for fused in (False, True):
+        eng = build(cfg, rcfg, sd_p, sd_r, gal_p, gal_r, nq, fused=fused)
+        rows = eng.adapt(queries).clone()
+        res[fused] = (rows, eng.rest.clone(), eng.rest_m.clone(), eng.rest_v.clone(), eng.w16.clone(), eng.ln.clone())
+    for a, b, nm in zip(res[False], res[True], ("score rows", "parameters", "exp_avg", "exp_avg_sq", "fp16 weights", "LayerNorm")):
+        assert torch.equal(a, b), f"{nm} differ between the fused and the unfused optimizer step"
