@@ -58,13 +58,8 @@ struct GemmArgs {
   AdamwEpi opt;          // EPI_ADAMW only
 };
 
-// torch.optim.AdamW, single-tensor order: decoupled decay, moment updates, bias-corrected step (as adamw_full_kernel)
 __device__ __forceinline__ float adamw_elem(float p0, float g, float& m, float& v, const AdamwEpi& o) {
-  const float w = p0 * (1.f - o.lr * o.wd);
-  m = m + (g - m) * (1.f - o.b1);
-  v = v * o.b2 + (1.f - o.b2) * g * g;
-  const float denom = sqrtf(v) / o.bc2_sqrt + o.eps;
-  return w - (o.lr / o.bc1) * (m / denom);
+  return adamw_update(p0, g, m, v, o.lr, o.b1, o.b2, o.eps, o.wd, o.bc1, o.bc2_sqrt);   // ptx.cuh: shared with adamw_full
 }
 
 // kMc = CTA pairs per cluster (cta_group::2 only).  With kMc == 2 a 4-CTA cluster computes a 512 x 256 super tile:
@@ -275,6 +270,52 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         b4.w = __shfl_sync(0xffffffffu, breg.w, c * 8 + tj);
         __syncwarp();
         // phase 2 (8 lanes = one 128-byte row segment): epilogue math + coalesced global stores
+        if constexpr (kEpi == EPI_ADAMW) {
+          // The accumulator chunk is the (loss-scaled) gradient of 32 columns x 32 rows of one sample's weight.  Optimizer
+          // step on the fp32 master tile in place, 4 rows at a time so that 12 independent 16-byte loads are in flight
+          // per lane (master, exp_avg, exp_avg_sq) before the first dependent instruction.
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float4 pw[4], mm[4], vv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = 4 * h + j;
+              pw[j] = mm[j] = vv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (4 * i < rows_left) {
+                const size_t e = goff + i * gstep;
+                const size_t e_in = e - static_cast<size_t>(g * p.out_gs) + static_cast<size_t>(g * p.opt.p_in_gs);
+                pw[j] = *reinterpret_cast<const float4*>(p.opt.p_in + e_in);
+                if (!p.opt.fresh) {
+                  mm[j] = *reinterpret_cast<const float4*>(p.opt.m + e);
+                  vv[j] = *reinterpret_cast<const float4*>(p.opt.v + e);
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = 4 * h + j;
+              const int rr = tr + 4 * i;
+              float4 q = stg[rr * 8 + (tj ^ (rr & 7))];
+              q.x = __fmul_rn(q.x, p.alpha); q.y = __fmul_rn(q.y, p.alpha);
+              q.z = __fmul_rn(q.z, p.alpha); q.w = __fmul_rn(q.w, p.alpha);
+              if (4 * i < rows_left) {
+                const size_t e = goff + i * gstep;
+                float4 w;
+                w.x = adamw_elem(pw[j].x, q.x, mm[j].x, vv[j].x, p.opt); w.y = adamw_elem(pw[j].y, q.y, mm[j].y, vv[j].y, p.opt);
+                w.z = adamw_elem(pw[j].z, q.z, mm[j].z, vv[j].z, p.opt); w.w = adamw_elem(pw[j].w, q.w, mm[j].w, vv[j].w, p.opt);
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + e) = w;
+                *reinterpret_cast<float4*>(p.opt.m + e) = mm[j];
+                *reinterpret_cast<float4*>(p.opt.v + e) = vv[j];
+                if (p.opt.w16 != nullptr) {
+                  const size_t e16 = e - static_cast<size_t>(g * p.out_gs) + static_cast<size_t>(g * p.opt.w16_gs);
+                  __half2 h0 = __floats2half2_rn(w.x, w.y), h1 = __floats2half2_rn(w.z, w.w);
+                  *reinterpret_cast<uint2*>(p.opt.w16 + e16) =
+                      make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+                }
+              }
+            }
+          }
+        } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = tr + 4 * i;
@@ -282,29 +323,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           q.x = fmaf(q.x, p.alpha, b4.x); q.y = fmaf(q.y, p.alpha, b4.y);
           q.z = fmaf(q.z, p.alpha, b4.z); q.w = fmaf(q.w, p.alpha, b4.w);
           if (4 * i < rows_left) {
-            if constexpr (kEpi == EPI_ADAMW) {
-              // q = unscaled weight gradient of 4 adjacent weights: optimizer step on the fp32 master tile in place
-              const size_t e = goff + i * gstep;
-              const size_t e_in = e - static_cast<size_t>(g * p.out_gs) + static_cast<size_t>(g * p.opt.p_in_gs);
-              const float4 pw = *reinterpret_cast<const float4*>(p.opt.p_in + e_in);
-              float4 mm = make_float4(0.f, 0.f, 0.f, 0.f), vv = mm;
-              if (!p.opt.fresh) {
-                mm = *reinterpret_cast<const float4*>(p.opt.m + e);
-                vv = *reinterpret_cast<const float4*>(p.opt.v + e);
-              }
-              float4 w;
-              w.x = adamw_elem(pw.x, q.x, mm.x, vv.x, p.opt); w.y = adamw_elem(pw.y, q.y, mm.y, vv.y, p.opt);
-              w.z = adamw_elem(pw.z, q.z, mm.z, vv.z, p.opt); w.w = adamw_elem(pw.w, q.w, mm.w, vv.w, p.opt);
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + e) = w;
-              *reinterpret_cast<float4*>(p.opt.m + e) = mm;
-              *reinterpret_cast<float4*>(p.opt.v + e) = vv;
-              if (p.opt.w16 != nullptr) {
-                const size_t e16 = e - static_cast<size_t>(g * p.out_gs) + static_cast<size_t>(g * p.opt.w16_gs);
-                __half2 h0 = __floats2half2_rn(w.x, w.y), h1 = __floats2half2_rn(w.z, w.w);
-                *reinterpret_cast<uint2*>(p.opt.w16 + e16) =
-                    make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-              }
-            } else if constexpr (kEpi == EPI_RESID_F32 || kEpi == EPI_F32) {
+            if constexpr (kEpi == EPI_RESID_F32 || kEpi == EPI_F32) {
               if constexpr (kEpi == EPI_RESID_F32) { q.x += z[i].x; q.y += z[i].y; q.z += z[i].z; q.w += z[i].w; }
               *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + goff + i * gstep) = q;
             } else {
@@ -326,6 +345,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                   make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
             }
           }
+        }
         }
         __syncwarp();  // staging buffer is reused by the next chunk; also reconverges for the .aligned TMEM load
       }

@@ -911,11 +911,7 @@ int adamw_step(float* params, float* m, float* v, const float* partials, int n_s
 // 12 B written (p, m, v) + 2 B (fp16 copy) per parameter.
 __device__ __forceinline__ float adamw_one(float p0, float g, float& m, float& v, float lr, float b1, float b2,
                                            float eps, float wd, float bc1, float bc2_sqrt) {
-  float w = p0 * (1.f - lr * wd);
-  m = m + (g - m) * (1.f - b1);
-  v = v * b2 + (1.f - b2) * g * g;
-  const float denom = sqrtf(v) / bc2_sqrt + eps;
-  return w - (lr / bc1) * (m / denom);
+  return adamw_update(p0, g, m, v, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
 }
 
 __global__ void __launch_bounds__(256)
@@ -950,10 +946,10 @@ adamw_full_kernel(float* __restrict__ p, float* __restrict__ m, float* __restric
       if (i >= p4) continue;
       if (fresh) { mm[u] = make_float4(0.f, 0.f, 0.f, 0.f); vv[u] = mm[u]; }
       float4 w;
-      w.x = adamw_one(q[u].x, g[u].x * inv_scale, mm[u].x, vv[u].x, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
-      w.y = adamw_one(q[u].y, g[u].y * inv_scale, mm[u].y, vv[u].y, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
-      w.z = adamw_one(q[u].z, g[u].z * inv_scale, mm[u].z, vv[u].z, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
-      w.w = adamw_one(q[u].w, g[u].w * inv_scale, mm[u].w, vv[u].w, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+      w.x = adamw_one(q[u].x, __fmul_rn(g[u].x, inv_scale), mm[u].x, vv[u].x, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+      w.y = adamw_one(q[u].y, __fmul_rn(g[u].y, inv_scale), mm[u].y, vv[u].y, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+      w.z = adamw_one(q[u].z, __fmul_rn(g[u].z, inv_scale), mm[u].z, vv[u].z, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+      w.w = adamw_one(q[u].w, __fmul_rn(g[u].w, inv_scale), mm[u].w, vv[u].w, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
       __stcs(P + i, w);
       __stcs(M + i, mm[u]);
       __stcs(V + i, vv[u]);

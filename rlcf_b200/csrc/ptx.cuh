@@ -255,4 +255,16 @@ __device__ __forceinline__ float quick_gelu_grad(float x) {
   return s * (1.f + 1.702f * x * (1.f - s));
 }
 
+// torch.optim.AdamW, single-tensor order (decoupled decay, lerp of exp_avg, addcmul of exp_avg_sq, bias-corrected
+// addcdiv), with every rounding pinned by an explicit intrinsic so that the streaming kernel (adamw_full_kernel) and the
+// fused wgrad epilogue (gemm_f16_kernel<.., EPI_ADAMW>) produce the same bits.
+__device__ __forceinline__ float adamw_update(float p0, float g, float& m, float& v, float lr, float b1, float b2,
+                                              float eps, float wd, float bc1, float bc2_sqrt) {
+  const float w = __fmul_rn(p0, __fsub_rn(1.f, __fmul_rn(lr, wd)));
+  m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), __fsub_rn(1.f, b1)));
+  v = __fadd_rn(__fmul_rn(v, b2), __fmul_rn(__fmul_rn(__fsub_rn(1.f, b2), g), g));
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), eps);
+  return __fsub_rn(w, __fmul_rn(__fdiv_rn(lr, bc1), __fdiv_rn(m, denom)));
+}
+
 }  // namespace rlcf

@@ -47,6 +47,11 @@ class RetrievalConfig:
     momentum: float = 0.9999
 
 
+def _bytes_per_query(lay, steps: int) -> float:
+    g, n = lay.p_gemm, lay.total
+    return float(steps * (34 * g + 36 * (n - g)) + 2 * g)
+
+
 def _n_chunks(C: int) -> int:
     return max(1, min(128, C // 64))
 
@@ -247,13 +252,12 @@ class ImageQueryEngine:
         return float(E.RlcfEngine.tower_fwd_flops(self.reward) + cfg.tta_steps * step + f + 2 * C * w.E)
 
     def bytes_per_query(self) -> float:
-        """Algorithmic HBM bytes of one query (the path is weight-bandwidth bound, SURVEY.md 8(d) tail-kernel rule):
-        per step the fp16 weights are read twice (forward + dgrad copies), the fp32 gradient is written and read once,
-        AdamW reads p,m,v and writes p,m,v, and the two fp16 copies are rewritten; plus one weight read to score."""
-        n = self.lay.total
-        g = self.lay.p_gemm
-        per_step = 2 * g * 2 + 2 * n * 4 + 6 * n * 4 + 2 * g * 2
-        return float(self.cfg.tta_steps * per_step + g * 2)
+        """Algorithmic HBM bytes of one query (the path is weight-bandwidth bound, SURVEY.md 8(d) tail-kernel rule).
+        Per step and GEMM weight: 2 B + 2 B read by the forward and dgrad GEMMs, 12 B read + 12 B written for the fp32
+        master and the two Adam moments, 2 B for the refreshed fp16 copy, 2 B + 2 B to re-lay the transposed dgrad copy
+        = 34 B (the gradient itself stays in TMEM: fused epilogue); every other parameter: gradient written and read
+        (8 B) + AdamW (28 B).  Plus one fp16 weight read for the scoring forward."""
+        return _bytes_per_query(self.lay, self.cfg.tta_steps)
 
 
 # ====================================================================================================================
@@ -516,6 +520,4 @@ class TextQueryEngine:
         return out
 
     def bytes_per_query(self) -> float:
-        n, g = self.lay.total, self.lay.p_gemm
-        per_step = 2 * g * 2 + 2 * n * 4 + 6 * n * 4 + 2 * g * 2
-        return float(self.cfg.tta_steps * per_step + g * 2)
+        return _bytes_per_query(self.lay, self.cfg.tta_steps)
