@@ -150,9 +150,13 @@ def transpose_weights(lay, w16: torch.Tensor, w16t: torch.Tensor):
             ops.transpose_f16_sets(w16.view(-1)[off:], r, c, w16t.view(-1)[off:], G, w16.stride(0))
 
 
-# Default for the engines' `fused_adamw`: the weight-gradient GEMMs apply AdamW in their epilogue (the gradient of a GEMM
-# weight never reaches HBM).  False keeps the gradients in `grads` (what the gradient-parity tests read).
-FUSED_ADAMW = True
+# Default for the engines' `fused_adamw`.  True: the weight-gradient GEMMs apply AdamW in their epilogue
+# (rlcf_gemm_wgrad_adamw), so the gradient of a GEMM weight never reaches HBM -- 26 B instead of 34 B of traffic per
+# weight and step, bit-identical results.  Measured on a B200 (round 1) the epilogue-driven streaming reaches 3.4 TB/s
+# against 5.5 TB/s for the dedicated streaming pass (only the 8 epilogue warps of a CTA have loads in flight), so the
+# unfused sequence wgrad GEMM -> rlcf_adamw_full is still faster end to end (retrieval image->text 130 vs 110 queries/s)
+# and stays the default until the epilogue prefetches its tiles with TMA.
+FUSED_ADAMW = False
 
 
 @dataclass
