@@ -134,3 +134,18 @@ def test_two_rank_gloo_counter_reduction(tmp_path):
         exp[1] += 1
         exp[2] += 1
     assert line == f"HITS {exp}"
+
+
+def test_ctypes_prototypes_match_the_header_parameter_counts():
+    """Every entry point's ctypes argtypes list has exactly as many entries as the C declaration has parameters
+    (guards against the binding drifting from include/rlcf_b200.h when a signature changes)."""
+    import re
+    from rlcf_b200 import _lib
+    with open(_lib.HEADER_PATH) as f:
+        src = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    decls = re.findall(r"\b(rlcf_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    assert len(decls) >= 40
+    for name, params in decls:
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert len(_lib._PROTOS[name]) == n, f"{name}: header has {n} parameters, _lib._PROTOS {len(_lib._PROTOS[name])}"
