@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import rlcf_oracle as O
-from test_oracle_retrieval import CASES, load_case, retrieval_setup
+from test_oracle_retrieval import CASES, IMAGE_SEED, POLICY_SEED, REWARD_SEED, TOKEN_SEED, load_case, retrieval_setup
 
 pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda:0")
@@ -362,3 +362,44 @@ def test_fused_adamw_epilogue_is_bit_identical(name):
         res[fused] = (rows, eng.rest.clone(), eng.rest_m.clone(), eng.rest_v.clone(), eng.w16.clone(), eng.ln.clone())
     for a, b, nm in zip(res[False], res[True], ("score rows", "parameters", "exp_avg", "exp_avg_sq", "fp16 weights", "LayerNorm")):
         assert torch.equal(a, b), f"{nm} differ between the fused and the unfused optimizer step"
+
+
+@pytest.mark.parametrize("task", ["image2text", "text2image"])
+def test_retrieval_at_vit_b16_size_matches_oracle(task):
+    """The config-4 policy at its real size (ViT-B/16: 197 tokens x 768 / 77 tokens x 512, 12 layers; grouped GEMMs with
+    197 / 77 rows per weight group, K = 20 / 12 over a 1 000-candidate gallery, recipe lr) for two queries and two
+    steps, against the oracle with the reference's GPU numerics (autocast weight cast).  The gallery features are
+    seeded unit vectors (they are inputs of the per-query loop)."""
+    from rlcf_b200 import engine as E, retrieval as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    i2t = task == "image2text"
+    sd_p = O.openai_load_rounding(O.make_clip_state_dict("ViT-B/16", POLICY_SEED))
+    sd_r = O.openai_load_rounding(O.make_clip_state_dict("ViT-B/32", REWARD_SEED))
+    g = torch.Generator().manual_seed(77)
+    C, K, steps, lr = 1000, (20 if i2t else 12), 2, 1e-6
+    gal_p = torch.nn.functional.normalize(torch.randn(C, 512, generator=g), dim=-1)
+    gal_r = torch.nn.functional.normalize(torch.randn(C, 512, generator=g), dim=-1)
+    images = O.make_views(2, 1, 224, IMAGE_SEED)
+    tokens = O.make_tokens(2, 49408, seed=TOKEN_SEED)
+    rcfg = O.RetrievalConfig(tta_steps=steps, sample_k=K, lr=lr)
+    rc = R.RetrievalConfig(tta_steps=steps, sample_k=K, lr=lr)
+    if i2t:
+        sd_pd = {k: v.to(DEV) for k, v in sd_p.items() if k.startswith("visual.") or k == "logit_scale"}
+        sd_rd = {k: v.to(DEV) for k, v in sd_r.items() if k.startswith("visual.")}
+        eng = R.ImageQueryEngine(sd_pd, gal_p.to(DEV), float(sd_p["logit_scale"].exp()), rc, 2,
+                                 E.prepare_visual(sd_rd), gal_r.to(DEV))
+    else:
+        sd_pd = {k: v.to(DEV) for k, v in sd_p.items() if not k.startswith("visual.")}
+        sd_rd = {k: v.to(DEV) for k, v in sd_r.items() if not k.startswith("visual.")}
+        eng = R.TextQueryEngine(sd_pd, gal_p.to(DEV), rc, 2, E.prepare_text(sd_rd), gal_r.to(DEV))
+    queries = images if i2t else tokens
+    rows = eng.adapt(queries.to(DEV)).cpu().numpy()
+    cfg = dict(steps=steps, lr=lr)
+    for qi in range(2):
+        query = queries[qi:qi + 1]
+        with torch.no_grad():
+            rq = O.retrieval_features(sd_r, images=query) if i2t else O.retrieval_features(sd_r, tokens=query)
+            f0 = O.retrieval_features(sd_p, images=query) if i2t else O.retrieval_features(sd_p, tokens=query)
+            row0 = (sd_p["logit_scale"].exp() * f0 @ gal_p.t())[0].numpy()
+        out = O.retrieval_tune_query(sd_p, rcfg, task, query, gal_p, rq, gal_r, fp16_weights=True)
+        check_query(eng, qi, out, None, cfg, f"B/16 {task} q{qi}", row0, slack=0.05)
