@@ -507,7 +507,7 @@ def run_retrieval(args):
     eng.adapt(batches[0])
     launches_per_step = _lib.launch_count() - l0
     step = eng.adapt
-    if not args.no_graph and i2t:
+    if not args.no_graph:
         eng.capture(batches[0])
         step = eng.adapt_graph
     for i in range(W):
@@ -556,7 +556,7 @@ def run_retrieval(args):
             "config": {"workload": "retrieval %s, COCO shape (config 4): %d gallery candidates, K=%d, 8 steps, lr 1e-6"
                                    % ("image->text" if i2t else "text->image", n_gallery, rcfg.sample_k),
                        "queries_per_step": Q, "parallelism": f"dp{world} (independent queries)",
-                       "cuda_graph": bool(not args.no_graph and i2t),
+                       "cuda_graph": bool(not args.no_graph),
                        "l2": "per-query weights + Adam state: %.1f GB per step, far beyond L2" % (
                            Q * eng.lay.total * 16 / 1e9)},
             "clocks": clocks,

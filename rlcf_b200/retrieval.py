@@ -503,6 +503,13 @@ class TextQueryEngine:
         self.tune(tokens)
         return self.predict()
 
+    @property
+    def logits_final(self):   # name shared with the classification engines (graph helpers)
+        return self.score_rows
+
+    capture = E.RlcfEngine.capture            # the whole adaptation of a token batch as one CUDA graph
+    adapt_graph = E.RlcfEngine.adapt_graph
+
     def export_params(self, q: int) -> dict:
         """Adapted parameters of query q under the reference's state-dict names; `token_embedding.rows` holds the
         caption's own L rows (row t belongs to token id tokens[q, t])."""
