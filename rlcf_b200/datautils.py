@@ -265,8 +265,9 @@ def _to_u8_hwc(x) -> torch.Tensor:
     return t.contiguous()
 
 
-def run_plan(image_u8: torch.Tensor, plan: ViewPlan, device) -> torch.Tensor:
-    """Executes a ViewPlan on `device`: uint8 [H,W,3] image -> fp32 views [V,3,224,224]."""
+def run_plan(image_u8: torch.Tensor, plan: ViewPlan, device, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Executes a ViewPlan on `device`: uint8 [H,W,3] image -> fp32 views [V,3,224,224] (written into `out` when given,
+    e.g. this image's slice of an engine's input batch)."""
     dev = torch.device(device)
     src = image_u8.to(dev, non_blocking=True)
     V = plan.hdr.shape[0]
@@ -281,7 +282,10 @@ def run_plan(image_u8: torch.Tensor, plan: ViewPlan, device) -> torch.Tensor:
     else:
         hb, hk, vb, vk = d(plan.hb), d(plan.hk), d(plan.vb), d(plan.vk)
     ops.resample_u8(src, hdr, hb, hk, vb, vk, OUT, OUT, tmp, x_orig)
-    out = torch.empty(V, 3, OUT, OUT, dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty(V, 3, OUT, OUT, dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != (V, 3, OUT, OUT) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise RlcfError(f"run_plan: out must be a contiguous fp32 [{V},3,{OUT},{OUT}] tensor")
     ops.augmix_views(x_orig, d(plan.vflag), d(plan.wts), d(plan.omm), d(plan.n_ops), d(plan.ops), d(plan.mats), MEAN, STD,
                      out)
     return out
