@@ -332,6 +332,17 @@ int rlcf_gemm_wgrad_adamw(const void* A, int lda, int64_t a_group_stride, const 
                           void* w16, int64_t w16_group_stride, float lr, float beta1, float beta2, float eps,
                           float weight_decay, int step, float loss_scale, void* stream);
 
+/* rlcf_reward_loss with an ensemble of up to 4 frozen reward models (CLIPRewardsMultiple, TPT/clip_reward.py:180-307):
+ * model i contributes weight_i * max(0, w * <reward_cls_i[idx], reward_img_i>) to a sample's CLIPScore (weights = the
+ * normalised confidences of clip_reward.py:207, or 1/n for weighted_scores = False).  Unused slots: NULL / 0. */
+int rlcf_reward_loss_multi(const float* logits, const int32_t* row_idx, int n_models, const float* reward_img0,
+                           const float* reward_img1, const float* reward_img2, const float* reward_img3,
+                           const float* reward_cls0, const float* reward_cls1, const float* reward_cls2,
+                           const float* reward_cls3, int er0, int er1, int er2, int er3, float weight0, float weight1,
+                           float weight2, float weight3, int n_img, int S, int K, int C, float clipscore_weight,
+                           int reward_process, int process_batch, int amplify, float loss_scale, float* dlogits,
+                           int32_t* topk_idx, float* scores, float* rewards, float* loss, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,13 @@ CASES = {
     "b32_cfg1_shape": dict(policy="ViT-B/32", reward="ViT-B/32", V=8, rho=0.5, K=3, C=32, steps=1, lr=5e-3, n_img=1,
                            reward_seed=3),   # seed 1 gives all-negative cosines -> all CLIPScores clipped to 0
     "b16_l14_cfg2": dict(policy="ViT-B/16", reward="ViT-L/14", V=64, rho=0.1, K=3, C=200, steps=1, lr=5e-3, n_img=1),
+    # CLIPRewardsMultiple (clip_reward.py:180-307) with two / three ViT members; confidences as CONFIDECES would give
+    # ViT-L/14 (5) and ViT-B/16 (1)
+    "tiny_rlcf_multi_reward": dict(policy="tiny-A", reward=["tiny-B", "tiny-A"], reward_seeds=[1, 5], confidences=[5, 1],
+                                   V=16, rho=0.25, K=3, C=10, steps=2, lr=5e-3, n_img=2),
+    "tiny_rlcf_multi_reward_mean": dict(policy="tiny-A", reward=["tiny-B", "tiny-A", "tiny-B"], reward_seeds=[1, 5, 6],
+                                        confidences=[5, 1, 3], weighted_scores=0, V=16, rho=0.25, K=3, C=10, steps=1,
+                                        lr=5e-3, n_img=1),
 }
 PROMPT_CASES = {
     # prompt tuning (TPT/tpt_cls_rl.py + ClipTestTimeTuning): real BPE tokenizer, ctx_init "a_photo_of_a" (4 tokens)
@@ -68,9 +75,17 @@ def import_reference():
 def run_case(name: str, cfg: dict, mods) -> dict:
     custom_clip, clip_model, clip_reward, tpt_cls_rl = mods
     sds = {cfg["policy"]: O.make_clip_state_dict(cfg["policy"], POLICY_SEED)}
-    sd_reward = O.make_clip_state_dict(cfg["reward"], cfg.get("reward_seed", REWARD_SEED))
+    multi = isinstance(cfg["reward"], list)
+    if multi:
+        member_names = [f"member{i}:{a}" for i, a in enumerate(cfg["reward"])]
+        sd_members = {n: O.make_clip_state_dict(a, sd_seed) for n, a, sd_seed in
+                      zip(member_names, cfg["reward"], cfg["reward_seeds"])}
+        sd_reward = None
+        vocab_r = O.ARCHS[cfg["reward"][0]][6]
+    else:
+        sd_reward = O.make_clip_state_dict(cfg["reward"], cfg.get("reward_seed", REWARD_SEED))
+        vocab_r = O.ARCHS[cfg["reward"]][6]
     vocab_p = O.ARCHS[cfg["policy"]][6]
-    vocab_r = O.ARCHS[cfg["reward"]][6]
     res = O.ARCHS[cfg["policy"]][1]
     tokens_p = O.make_tokens(cfg["C"], vocab_p, seed=TOKEN_SEED)
     tokens_r = O.make_tokens(cfg["C"], vocab_r, seed=TOKEN_SEED)
@@ -83,7 +98,16 @@ def run_case(name: str, cfg: dict, mods) -> dict:
 
     custom_clip.load = fake_load(sds[cfg["policy"]])
     custom_clip.tokenize = lambda prompts: tokens_p.clone()
-    clip_reward.clip.load = fake_load(sd_reward)
+    if multi:
+        def load_member(arch, device="cpu", jit=False, download_root=None):
+            sd = sd_members[arch]
+            model = clip_model.build_model({k: v.clone() for k, v in sd.items()}).to(device).float()
+            return model, sd["text_projection"].shape[1], None
+        clip_reward.clip.load = load_member
+        for n, c in zip(member_names, cfg["confidences"]):     # the table the class reads its weights from (clip_reward.py:22-27,200)
+            clip_reward.CONFIDECES[n] = c
+    else:
+        clip_reward.clip.load = fake_load(sd_reward)
 
     args = argparse.Namespace(
         tta_steps=cfg["steps"], selection_p=cfg["rho"], min_entropy_reg=False, min_entropy_w=0.0,
@@ -94,7 +118,13 @@ def run_case(name: str, cfg: dict, mods) -> dict:
                                     only_norm=True)
     optimizer = torch.optim.AdamW(model.parameters(), cfg["lr"], weight_decay=5e-4)   # tune_cls_rl.py:79-81
     optim_state = copy.deepcopy(optimizer.state_dict())
-    reward_model = clip_reward.get_reward_model("cpu", args)
+    if multi:   # get_reward_model's multiple_reward_models branch (clip_reward.py:30-35) with this case's members
+        reward_model = clip_reward.CLIPRewardsMultiple(
+            "cpu", arch=member_names, classification=True, amplify_rewards=args.reward_amplify, sample_k=args.sample_k,
+            reward_process=args.reward_process, process_batch=args.process_batch,
+            weighted_scores=cfg.get("weighted_scores", 1))
+    else:
+        reward_model = clip_reward.get_reward_model("cpu", args)
     reward_model.set_class_features(tokenized_classes=tokens_r)                        # tune_cls_rl.py:142-143
     scaler = torch.cuda.amp.GradScaler(init_scale=1000)                                # tune_cls_rl.py:87
 
@@ -147,7 +177,12 @@ def run_case(name: str, cfg: dict, mods) -> dict:
     finally:
         tpt_cls_rl.select_confident_samples = orig_select
     out["class_feat"] = model.class_features.numpy()
-    out["reward_cls"] = reward_model.class_features.numpy()
+    if multi:
+        for i, f in enumerate(reward_model.class_features):
+            out[f"reward_cls{i}"] = f.numpy()
+        out["reward_weights"] = np.array(reward_model.weights, dtype=np.float64)
+    else:
+        out["reward_cls"] = reward_model.class_features.numpy()
     out["meta"] = np.array(repr(cfg))
     return out
 

@@ -223,6 +223,24 @@ def clip_score(reward_cls, reward_img, class_index, sample_k, weight=2.5):
     return torch.maximum(similarity, torch.zeros_like(similarity)).squeeze()
 
 
+CONFIDENCES = {"ViT-L/14@336px": 10, "ViT-L/14": 5, "RN50x64": 3, "ViT-B/16": 1}      # TPT/clip_reward.py:22-27
+
+
+def ensemble_weights(confidences) -> list:
+    """CLIPRewardsMultiple.__init__ (TPT/clip_reward.py:207): normalised confidences rounded to 2 decimals."""
+    return [round(x / sum(confidences), 2) for x in confidences]
+
+
+def clip_score_multi(reward_cls_list, reward_img_list, class_index, sample_k, weights, weighted=True, weight=2.5):
+    """CLIPRewardsMultiple.CLIPScore with pairwise=False (TPT/clip_reward.py:226-250)."""
+    scores = torch.stack([clip_score(c, f, class_index, sample_k, weight) for c, f in zip(reward_cls_list, reward_img_list)],
+                         dim=0)
+    if weighted:
+        w = torch.tensor(weights, dtype=scores.dtype).unsqueeze(1)
+        return torch.sum(w * scores, dim=0)
+    return torch.mean(scores, dim=0)
+
+
 def rewards_post_process(clip_score_, reward_process=True, amplify=False):
     """CLIPRewards.rewards_post_process (TPT/clip_reward.py:152-165)."""
     if clip_score_.shape[-1] > 1 and reward_process:
@@ -244,6 +262,8 @@ class OracleConfig:
     process_batch: bool = False
     reward_amplify: bool = False
     loss: str = "rlcf"        # "rlcf" | "tpt"
+    reward_weights: tuple = ()    # ensemble of reward models (sd_reward / reward_cls are then lists): per-model weights
+    weighted_scores: bool = True  # CLIPRewardsMultiple(weighted_scores=...): weighted sum, else plain mean
 
 
 def ln_param_names(sd: dict) -> list:
@@ -284,13 +304,17 @@ def adapt_one_image(sd_policy: dict, class_feat: torch.Tensor, views: torch.Tens
             output, selected_idx, ent = select_confident_samples(logits_all, cfg.selection_p)
             out["logits_all"], out["entropy"], out["selected_idx"] = logits_all.detach(), ent.detach(), selected_idx
             if cfg.loss == "rlcf":
-                reward_img = reward_image_features(sd_reward, views[selected_idx])           # tpt_cls_rl.py:59
+                multi = isinstance(sd_reward, (list, tuple))
+                reward_img = ([reward_image_features(r, views[selected_idx]) for r in sd_reward] if multi
+                              else reward_image_features(sd_reward, views[selected_idx]))   # tpt_cls_rl.py:59
                 out["reward_img"] = reward_img
         bs = output.shape[0]
         if cfg.loss == "rlcf":
             _, index = torch.topk(output, cfg.sample_k, dim=-1)                              # tpt_cls_rl.py:63
             flat = index.flatten()
-            score = clip_score(reward_cls, reward_img, flat, cfg.sample_k)                   # tpt_cls_rl.py:66
+            score = (clip_score_multi(reward_cls, reward_img, flat, cfg.sample_k, cfg.reward_weights,
+                                      cfg.weighted_scores) if isinstance(reward_img, list)
+                     else clip_score(reward_cls, reward_img, flat, cfg.sample_k))           # tpt_cls_rl.py:66
             rewards = rewards_post_process(score if cfg.process_batch else score.reshape(bs, -1),
                                            cfg.reward_process, cfg.reward_amplify)           # tpt_cls_rl.py:67
             rep = torch.repeat_interleave(output, cfg.sample_k, dim=0)

@@ -41,6 +41,8 @@ _PROTOS = {
     "rlcf_head_fwd": [_vp, _vp, _i64, _vp, _vp, _i64, _i, _vp, _vp, _f, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp],
     "rlcf_entropy_select": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "rlcf_reward_loss": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp],
+    "rlcf_reward_loss_multi": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _i, _i,
+                               _i, _i, _f, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp],
     "rlcf_avg_entropy_loss": [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp],
     "rlcf_head_bwd": [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _i,
                       _i64, _i64, _vp],

@@ -21,6 +21,23 @@ from .clip import load, tokenize
 DOWNLOAD_ROOT = None  # the reference hard-codes a checkpoint directory (custom_clip.py:19-30); here it is optional
 
 
+def _reward_inputs(reward_model):
+    """(tower(s), class features, weights) of a CLIPRewards / CLIPRewardsMultiple for the engines."""
+    from ..clip_reward import engine_inputs
+    rew, rcls, weights = engine_inputs(reward_model)
+    if rcls is None:
+        raise RlcfError("reward_model.set_class_features(...) must be called before adaptation")
+    return rew, rcls, weights
+
+
+def _ids(x):
+    return None if x is None else (tuple(id(t) for t in x) if isinstance(x, (list, tuple)) else id(x))
+
+
+def _ptrs(x):
+    return None if x is None else (tuple(t.data_ptr() for t in x) if isinstance(x, (list, tuple)) else x.data_ptr())
+
+
 class TextEncoder(nn.Module):
     """Text tower on ready-made prompt embeddings (custom_clip.py:53-73): [C, 77, d] -> un-normalised features [C, E]."""
 
@@ -157,13 +174,10 @@ class ClipTestTimeTuning(nn.Module):
         txt = self._clip._text.tower(need_grad=True)
         rew = rcls = None
         if reward_model is not None:
-            rew = reward_model.clip_model.visual.tower()
-            rcls = reward_model.class_features
-            if rcls is None:
-                raise RlcfError("reward_model.set_class_features(...) must be called before adaptation")
+            rew, rcls, cfg.reward_weights = _reward_inputs(reward_model)
         pl = self.prompt_learner
-        key = (id(vis), id(txt), id(rew), n_img, tuple(sorted(vars(cfg).items())), pl.tokenized_prompts.data_ptr(),
-               None if rcls is None else rcls.data_ptr())
+        key = (id(vis), id(txt), _ids(rew), n_img, tuple(sorted(vars(cfg).items())), pl.tokenized_prompts.data_ptr(),
+               _ptrs(rcls))
         eng = self._engines.get(key)
         if eng is None:
             self._engines.clear()
@@ -296,14 +310,14 @@ class CLIPCLS_TTA(nn.Module):
         if reward_model is None or reward_model.class_features is None:
             raise RlcfError("full image-encoder tuning needs a reward model with class features set")
         vis = self.clip_model.visual
-        rew = reward_model.clip_model.visual.tower()
-        key = ("full", vis._frozen_key(), id(rew), n_img, tuple(sorted(vars(cfg).items())),
-               self.class_features.data_ptr(), reward_model.class_features.data_ptr())
+        rew, rcls, cfg.reward_weights = _reward_inputs(reward_model)
+        key = ("full", vis._frozen_key(), _ids(rew), n_img, tuple(sorted(vars(cfg).items())),
+               self.class_features.data_ptr(), _ptrs(rcls))
         eng = self._engines.get(key)
         if eng is None:
             self._engines.clear()
             eng = FT.FullTuneEngine(vis.state_dict(), self.class_features, float(self.clip_model.logit_scale.exp()), cfg,
-                                    n_img, rew, reward_model.class_features, prefix="")
+                                    n_img, rew, rcls, prefix="")
             self._engines[key] = eng
         return eng
 
@@ -317,12 +331,8 @@ class CLIPCLS_TTA(nn.Module):
         pol = vis.tower(need_grad=True)
         rew = rcls = None
         if reward_model is not None:
-            rew = reward_model.clip_model.visual.tower()
-            rcls = reward_model.class_features
-            if rcls is None:
-                raise RlcfError("reward_model.set_class_features(...) must be called before adaptation")
-        key = (id(pol), id(rew), n_img, tuple(sorted(vars(cfg).items())), self.class_features.data_ptr(),
-               None if rcls is None else rcls.data_ptr())
+            rew, rcls, cfg.reward_weights = _reward_inputs(reward_model)
+        key = (id(pol), _ids(rew), n_img, tuple(sorted(vars(cfg).items())), self.class_features.data_ptr(), _ptrs(rcls))
         eng = self._engines.get(key)
         if eng is None:
             self._engines.clear()

@@ -1,7 +1,9 @@
 """Reward model with the reference's surface (TPT/clip_reward.py): a frozen CLIP that scores sampled predictions.
 
-get_reward_model(device, args) -> CLIPRewards (clip_reward.py:29-40); the ensemble CLIPRewardsMultiple
-(RN50x64 + ViT-L/14@336, clip_reward.py:180-307) needs a ResNet tower and is out of scope.
+get_reward_model(device, args) -> CLIPRewards (clip_reward.py:29-40) or, with --multiple_reward_models 1, the ensemble
+CLIPRewardsMultiple (clip_reward.py:180-307).  The ensemble works for any list of 224-pixel ViT CLIPs; the reference's
+hard-coded list ["ViT-L/14@336px", "RN50x64", "ViT-L/14"] needs a ModifiedResNet tower and a 336-pixel ViT, which are
+out of scope -- pass the architectures as a comma-separated --reward_arch instead.
 """
 from __future__ import annotations
 
@@ -18,7 +20,15 @@ CONFIDECES = {"ViT-L/14@336px": 10, "ViT-L/14": 5, "RN50x64": 3, "ViT-B/16": 1}
 
 def get_reward_model(device, args):
     if getattr(args, "multiple_reward_models", 0):
-        raise NotImplementedError("CLIPRewardsMultiple (RN50x64 + ViT-L/14@336px ensemble) is out of scope")
+        archs = [a.strip() for a in str(args.reward_arch).split(",") if a.strip()]
+        if len(archs) < 2:
+            raise NotImplementedError(
+                "--multiple_reward_models 1: the reference's ensemble [ViT-L/14@336px, RN50x64, ViT-L/14] "
+                "(clip_reward.py:31) needs a ResNet tower and a 336-pixel ViT; give 2-4 ViT architectures as "
+                "--reward_arch 'ViT-L/14,ViT-B/16'")
+        return CLIPRewardsMultiple(device, arch=archs, classification=True, amplify_rewards=args.reward_amplify,
+                                   sample_k=args.sample_k, reward_process=args.reward_process,
+                                   process_batch=args.process_batch, weighted_scores=getattr(args, "weighted_scores", 1))
     return CLIPRewards(device, arch=args.reward_arch, classification=True, amplify_rewards=args.reward_amplify,
                        sample_k=args.sample_k, reward_process=args.reward_process,
                        process_batch=args.process_batch)
@@ -41,6 +51,16 @@ class BaseRewards(nn.Module):
         value, _ = torch.topk(predictions, 2, dim=-1)
         gap = value[:, 0] - value[:, 1]
         return gap - torch.mean(gap)
+
+
+def engine_inputs(reward_model):
+    """(reward tower(s), class features, weights) in the form the engines take: single objects for CLIPRewards, lists
+    (+ one weight per model) for CLIPRewardsMultiple."""
+    if isinstance(reward_model, CLIPRewardsMultiple):
+        n = reward_model.n_model
+        w = reward_model.weights if reward_model.weighted_scores else [1.0 / n] * n
+        return [m.visual.tower() for m in reward_model.clip_models], reward_model.class_features, tuple(w)
+    return reward_model.clip_model.visual.tower(), reward_model.class_features, ()
 
 
 class CLIPRewards(BaseRewards):
@@ -105,3 +125,82 @@ class CLIPRewards(BaseRewards):
         logit_scale = self.clip_model.logit_scale.exp()
         logits_per_image = logit_scale * self.image_features @ self.class_features.t()
         return logits_per_image, logits_per_image.t()
+
+
+def _confidence(arch: str) -> float:
+    key = arch.split(":")[1] if arch.startswith("synthetic:") else arch
+    return float(CONFIDECES.get(key, 1))
+
+
+class CLIPRewardsMultiple(BaseRewards):
+    """Ensemble of frozen CLIPs (clip_reward.py:180-307): a sample's CLIPScore is the confidence-weighted sum (or the
+    mean) of the members' scores.  Members must be 224-pixel ViT models."""
+
+    def __init__(self, device, arch=("ViT-B/16", "ViT-L/14"), clipscore_weight=2.5, classification=True,
+                 amplify_rewards=False, sample_k=5, reward_process=True, process_batch=True, weighted_scores=True,
+                 default_resolutions=224) -> None:
+        super().__init__()
+        if not 2 <= len(arch) <= 4:
+            raise RlcfError("CLIPRewardsMultiple takes 2..4 reward models")
+        models, weights = [], []
+        self.preprocess, self.resolutions = [], []
+        self.default_resolutions = default_resolutions
+        for ar in arch:
+            clip_model, _, preprocess = clip.load(ar, device=device, download_root=DOWNLOAD_ROOT)
+            if clip_model.visual.input_resolution != default_resolutions:
+                raise NotImplementedError(f"{ar}: reward models at a resolution other than {default_resolutions} need "
+                                          "the bicubic resize of clip_reward.py:262-264, which is not implemented")
+            models.append(clip_model)
+            self.preprocess.append(preprocess)
+            self.resolutions.append(clip_model.visual.input_resolution)
+            weights.append(_confidence(ar))
+        self.clip_models = nn.ModuleList(models)
+        self.n_model = len(models)
+        self.weights = [round(x / sum(weights), 2) for x in weights]       # clip_reward.py:207
+        self.clipscore_weight = clipscore_weight
+        self.device = device
+        self.classification = classification
+        self.class_features = None
+        self.image_features = None
+        self.amplify_rewards, self.sample_k = amplify_rewards, sample_k
+        self.reward_process, self.process_batch, self.weighted_scores = reward_process, process_batch, weighted_scores
+        self.clip_models.eval()
+
+    @torch.no_grad()
+    def CLIPScore(self, class_index, images=None, image_features=None, captions=None, tokenized_cap=None,
+                  text_features=None, pairwise=False):
+        if pairwise:
+            raise NotImplementedError    # as the reference (clip_reward.py:237-238)
+        all_scores = []
+        for i in range(self.n_model):
+            t = self.class_features[i][class_index]
+            f = torch.repeat_interleave(self.image_features[i], self.sample_k, dim=0)
+            sim = self.clipscore_weight * torch.sum(t * f, dim=-1)
+            all_scores.append(torch.maximum(sim, torch.zeros_like(sim)).squeeze())
+        scores = torch.stack(all_scores, dim=0)
+        if self.weighted_scores:
+            w = torch.tensor(self.weights, device=scores.device, dtype=scores.dtype).unsqueeze(1)
+            return torch.sum(w * scores, dim=0)
+        return torch.mean(scores, dim=0)
+
+    @torch.no_grad()
+    def extract_image_features(self, images):
+        feats = []
+        for m in self.clip_models:
+            f = m.encode_image(images).float()
+            feats.append(f / f.norm(dim=1, keepdim=True))
+        return feats
+
+    @torch.no_grad()
+    def extract_text_features(self, captions=None, tokenized_cap=None):
+        if captions is not None:
+            tokenized_cap = clip.tokenize(captions, truncate=True).to(self.device)
+        if tokenized_cap is None:
+            raise RlcfError("extract_text_features needs captions or tokenized_cap")
+        feats = []
+        for m in self.clip_models:
+            f = m.encode_text(tokenized_cap).float()
+            feats.append(f / f.norm(dim=1, keepdim=True))
+        return feats
+
+    rewards_post_process = CLIPRewards.rewards_post_process

@@ -91,6 +91,9 @@ int head_fwd(const float*, const int32_t*, long long, const float*, const float*
 int entropy_select(const float*, int, int, int, int, int32_t*, int32_t*, float*, cudaStream_t);
 int reward_loss(const float*, const int32_t*, const float*, const float*, int, int, int, int, int, float, int, int,
                 int, float, float*, int32_t*, float*, float*, float*, cudaStream_t);
+int reward_loss_multi(const float*, const int32_t*, int, const float* const*, const float* const*, const int*,
+                      const float*, int, int, int, int, float, int, int, int, float, float*, int32_t*, float*, float*,
+                      float*, cudaStream_t);
 int avg_entropy_loss(const float*, const int32_t*, int, int, int, float, float*, float*, cudaStream_t);
 int head_bwd(const float*, const float*, const int32_t*, long long, const float*, long long, const float*,
              const float*, float, const float*, const float*, int, int, int, int, int, float, float*, float*, int,
@@ -488,6 +491,23 @@ int rlcf_gemm_wgrad_adamw(const void* A, int lda, int64_t a_group_stride, const 
   return gemm_f16_grouped(CH(A), lda, a_group_stride, CH(B), ldb, b_group_stride, groups, n_out, n_in, K, EPI_ADAMW,
                           1.0f / loss_scale, nullptr, 0, nullptr, nullptr, nullptr, params, ldp, param_group_stride,
                           S(stream), &o);
+}
+
+int rlcf_reward_loss_multi(const float* logits, const int32_t* row_idx, int n_models, const float* reward_img0,
+                           const float* reward_img1, const float* reward_img2, const float* reward_img3,
+                           const float* reward_cls0, const float* reward_cls1, const float* reward_cls2,
+                           const float* reward_cls3, int er0, int er1, int er2, int er3, float weight0, float weight1,
+                           float weight2, float weight3, int n_img, int S_, int K, int C, float clipscore_weight,
+                           int reward_process, int process_batch, int amplify, float loss_scale, float* dlogits,
+                           int32_t* topk_idx, float* scores, float* rewards, float* loss, void* stream) {
+  if (!logits || !dlogits) return set_error(RLCF_ERR_ARG, "reward_loss_multi: null pointer");
+  const float* img[4] = {reward_img0, reward_img1, reward_img2, reward_img3};
+  const float* cls[4] = {reward_cls0, reward_cls1, reward_cls2, reward_cls3};
+  const int er[4] = {er0, er1, er2, er3};
+  const float wt[4] = {weight0, weight1, weight2, weight3};
+  return reward_loss_multi(logits, row_idx, n_models, img, cls, er, wt, n_img, S_, K, C, clipscore_weight,
+                           reward_process, process_batch, amplify, loss_scale, dlogits, topk_idx, scores, rewards, loss,
+                           S(stream));
 }
 
 }  // extern "C"

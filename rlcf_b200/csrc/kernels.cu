@@ -549,10 +549,21 @@ int entropy_select(const float* logits, int n_img, int V, int C, int S, int32_t*
 // ------------------------------------------------------------------------------------------------ reward + loss
 // tpt_cls_rl.py:63-71 and clip_reward.py:111-128,152-165.  One block per image, one warp per selected view.
 constexpr int kMaxK = 8;
+constexpr int kMaxRewardModels = 4;
+// One or several frozen reward models (CLIPRewards / CLIPRewardsMultiple, clip_reward.py:43-178 / 180-307): model i has
+// image features img[i] [n_views_total, er[i]] and class features cls[i] [C, er[i]]; the sample's score is
+// sum_i wt[i] * max(0, w * <cls_i, img_i>)  (wt = normalised confidences, or 1/n for the plain mean; n = 1: wt = 1).
+struct RewardSet {
+  const float* img[kMaxRewardModels];
+  const float* cls[kMaxRewardModels];
+  int er[kMaxRewardModels];
+  float wt[kMaxRewardModels];
+  int n;
+};
+
 __global__ void __launch_bounds__(256)
-reward_loss_kernel(const float* __restrict__ logits, const int32_t* __restrict__ row_idx,
-                   const float* __restrict__ r_img, const float* __restrict__ r_cls, int S, int K, int C, int Er,
-                   float w, int reward_process, int process_batch, int amplify, float loss_scale,
+reward_loss_kernel(const float* __restrict__ logits, const int32_t* __restrict__ row_idx, const RewardSet rs, int S,
+                   int K, int C, float w, int reward_process, int process_batch, int amplify, float loss_scale,
                    float* __restrict__ dlogits, int32_t* __restrict__ topk_idx, float* __restrict__ scores_out,
                    float* __restrict__ rewards_out, float* __restrict__ loss_out) {
   extern __shared__ float smf[];
@@ -588,14 +599,21 @@ reward_loss_kernel(const float* __restrict__ logits, const int32_t* __restrict__
         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
       }
       chosen[k] = bi;
-      // CLIPScore = max(0, w * <t_cls, f_img>)   (clip_reward.py:119-126)
-      const float* t = r_cls + static_cast<size_t>(bi) * Er;
-      const float* f = r_img + static_cast<size_t>(n) * Er;
-      float acc = 0.f;
-      for (int j = lane; j < Er; j += 32) acc = fmaf(__ldg(t + j), __ldg(f + j), acc);
-      acc = warp_sum(acc);
+      // CLIPScore = max(0, w * <t_cls, f_img>)   (clip_reward.py:119-126); ensembles: weighted sum over the models
+      // (clip_reward.py:226-250)
+      float score = 0.f;
+      for (int mdl = 0; mdl < rs.n; ++mdl) {
+        const int Er = rs.er[mdl];
+        const float* t = rs.cls[mdl] + static_cast<size_t>(bi) * Er;
+        const float* f = rs.img[mdl] + static_cast<size_t>(n) * Er;
+        float acc = 0.f;
+        for (int j = lane; j < Er; j += 32) acc = fmaf(__ldg(t + j), __ldg(f + j), acc);
+        acc = warp_sum(acc);
+        const float sm = fmaxf(w * acc, 0.f);
+        score = rs.n == 1 ? sm : score + rs.wt[mdl] * sm;
+      }
       if (lane == 0) {
-        sc[s * K + k] = fmaxf(w * acc, 0.f);
+        sc[s * K + k] = score;
         ce[s * K + k] = (mx + lse) - bv;
         idx[s * K + k] = bi;
       }
@@ -664,18 +682,34 @@ reward_loss_kernel(const float* __restrict__ logits, const int32_t* __restrict__
   }
 }
 
+int reward_loss_multi(const float* logits, const int32_t* row_idx, int n_models, const float* const* r_img,
+                      const float* const* r_cls, const int* er, const float* wt, int n_img, int S, int K, int C, float w,
+                      int reward_process, int process_batch, int amplify, float loss_scale, float* dlogits,
+                      int32_t* topk_idx, float* scores, float* rewards, float* loss, cudaStream_t stream) {
+  if (n_img <= 0 || S <= 0 || K <= 0 || K > kMaxK || K > C || n_models < 1 || n_models > kMaxRewardModels)
+    return set_error(RLCF_ERR_ARG, "reward_loss: bad shape (K must be 1..%d, 1..%d reward models)", kMaxK,
+                     kMaxRewardModels);
+  RewardSet rs{};
+  rs.n = n_models;
+  for (int i = 0; i < n_models; ++i) {
+    if (r_img[i] == nullptr || r_cls[i] == nullptr || er[i] <= 0)
+      return set_error(RLCF_ERR_ARG, "reward_loss: reward model %d has no features", i);
+    rs.img[i] = r_img[i]; rs.cls[i] = r_cls[i]; rs.er[i] = er[i]; rs.wt[i] = wt[i];
+  }
+  const size_t smem = (static_cast<size_t>(3) * S * K + 2 * S) * sizeof(float);
+  if (smem > 48 * 1024) return set_error(RLCF_ERR_ARG, "reward_loss: S*K too large");
+  reward_loss_kernel<<<n_img, 256, smem, stream>>>(logits, row_idx, rs, S, K, C, w, reward_process, process_batch,
+                                                   amplify, loss_scale, dlogits, topk_idx, scores, rewards, loss);
+  RLCF_CHECK_LAUNCH("reward_loss");
+  return 0;
+}
+
 int reward_loss(const float* logits, const int32_t* row_idx, const float* r_img, const float* r_cls, int n_img, int S,
                 int K, int C, int Er, float w, int reward_process, int process_batch, int amplify, float loss_scale,
                 float* dlogits, int32_t* topk_idx, float* scores, float* rewards, float* loss, cudaStream_t stream) {
-  if (n_img <= 0 || S <= 0 || K <= 0 || K > kMaxK || K > C || Er <= 0)
-    return set_error(RLCF_ERR_ARG, "reward_loss: bad shape (K must be 1..%d)", kMaxK);
-  const size_t smem = (static_cast<size_t>(3) * S * K + 2 * S) * sizeof(float);
-  if (smem > 48 * 1024) return set_error(RLCF_ERR_ARG, "reward_loss: S*K too large");
-  reward_loss_kernel<<<n_img, 256, smem, stream>>>(logits, row_idx, r_img, r_cls, S, K, C, Er, w, reward_process,
-                                                   process_batch, amplify, loss_scale, dlogits, topk_idx, scores,
-                                                   rewards, loss);
-  RLCF_CHECK_LAUNCH("reward_loss");
-  return 0;
+  const float one = 1.f;
+  return reward_loss_multi(logits, row_idx, 1, &r_img, &r_cls, &Er, &one, n_img, S, K, C, w, reward_process,
+                           process_batch, amplify, loss_scale, dlogits, topk_idx, scores, rewards, loss, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ TPT entropy loss

@@ -387,10 +387,51 @@ class RlcfConfig:
     reward_amplify: bool = False  # --reward_amplify
     loss_scale: float = 1024.0   # static gradient scale for the fp16 dgrad operands (the reference's GradScaler(1000))
     loss: str = "rlcf"           # "rlcf" (tpt_cls_rl.py:63-71) | "tpt" (avg_entropy, tpt_cls_rl.py:38-44)
+    reward_weights: tuple = ()   # ensemble of reward models (CLIPRewardsMultiple, clip_reward.py:180-307): one weight
+                                 # per model -- normalised confidences, or 1/n each for weighted_scores = False
 
     @property
     def n_selected(self):
         return int(self.n_views * self.selection_p)  # tpt_cls_rl.py:34
+
+
+class RewardScorer:
+    """The frozen reward model(s) of one engine: image features of the selected views and the reward-weighted loss.
+    One tower (CLIPRewards, clip_reward.py:43-178) or up to four (CLIPRewardsMultiple, clip_reward.py:180-307), each
+    with its class features [C, E_i]; `weights` as RlcfConfig.reward_weights."""
+
+    def __init__(self, reward, class_feat, n_seq_max: int, weights=()):
+        self.towers = list(reward) if isinstance(reward, (list, tuple)) else [reward]
+        cls = list(class_feat) if isinstance(class_feat, (list, tuple)) else [class_feat]
+        if len(cls) != len(self.towers) or not 1 <= len(self.towers) <= 4:
+            raise RlcfError("one set of reward class features per reward tower (1..4 towers)")
+        self.class_feats = [c.float().contiguous() for c in cls]
+        for t, c in zip(self.towers, self.class_feats):
+            if c.shape[1] != t.E:
+                raise RlcfError(f"reward class features have width {c.shape[1]}, the tower embeds to {t.E}")
+        self.weights = [float(x) for x in weights] if len(self.towers) > 1 else [1.0]
+        if len(self.weights) != len(self.towers):
+            raise RlcfError("RlcfConfig.reward_weights must hold one weight per reward model")
+        dev = self.towers[0].ln_flat.device
+        self.runners = [TowerRunner(t, n_seq_max) for t in self.towers]
+        self.feats = [torch.empty(n_seq_max, t.E, dtype=torch.float32, device=dev) for t in self.towers]
+
+    def features(self, images, view_idx, n_seq):
+        """reward_model.set_image_features(inputs[selected_idx])          (tpt_cls_rl.py:59, clip_reward.py:130-137)"""
+        for t, r, f in zip(self.towers, self.runners, self.feats):
+            x = r.forward(n_seq, t.ln_flat, images=images, view_idx=view_idx)
+            r.head(x, n_seq, t.ln_flat, feat=f)
+
+    def loss(self, logits, n_img, S, K, C, dlogits, cfg, **outs):
+        kw = dict(clipscore_weight=cfg.clipscore_weight, reward_process=cfg.reward_process,
+                  process_batch=cfg.process_batch, amplify=cfg.reward_amplify, loss_scale=cfg.loss_scale, **outs)
+        if len(self.towers) == 1:
+            ops.reward_loss(logits, None, self.feats[0], self.class_feats[0], n_img, S, K, C, dlogits, **kw)
+        else:
+            ops.reward_loss_multi(logits, None, self.feats, self.class_feats, self.weights, n_img, S, K, C, dlogits, **kw)
+
+    def fwd_flops(self) -> float:
+        return float(sum(RlcfEngine.tower_fwd_flops(t) for t in self.towers))
 
 
 class RlcfEngine:
@@ -409,18 +450,17 @@ class RlcfEngine:
         self.policy, self.reward = policy, reward
         self.class_feat = class_feat.float().contiguous()
         self.logit_scale = float(logit_scale)
-        self.reward_class_feat = None if reward_class_feat is None else reward_class_feat.float().contiguous()
         dev = policy.ln_flat.device
         V, S, C = cfg.n_views, cfg.n_selected, self.class_feat.shape[0]
         if S < 1:
             raise RlcfError(f"int(n_views * selection_p) = {S}: no view would be selected (tpt_cls_rl.py:34)")
-        if cfg.loss == "rlcf" and (reward is None or self.reward_class_feat is None):
+        if cfg.loss == "rlcf" and (reward is None or reward_class_feat is None):
             raise RlcfError("RLCF loss needs a reward tower and reward class features")
         B, P = n_img, policy.P
         self.run = TowerRunner(policy, B * V)
         self.run.reserve_backward(B * S)
         self.store = ActStore(policy, B * S, dev)
-        self.rrun = TowerRunner(reward, B * S) if reward is not None else None
+        self.scorer = RewardScorer(reward, reward_class_feat, B * S, cfg.reward_weights) if reward is not None else None
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
         self.init_params = policy.ln_flat.clone()
@@ -444,9 +484,15 @@ class RlcfEngine:
         self.rewards = torch.empty(B * S, cfg.sample_k, **f32)
         self.loss = torch.empty(cfg.tta_steps, B, **f32)
         self.logits_final = torch.empty(B, C, **f32)
-        self.reward_feat = torch.empty(B * S, reward.E, **f32) if reward is not None else None
         self._graph = None
         self._static_images = None
+
+    @property
+    def reward_feat(self):
+        """Reward-model image features of the selected views (a list for an ensemble of reward models)."""
+        if self.scorer is None:
+            return None
+        return self.scorer.feats[0] if len(self.scorer.feats) == 1 else self.scorer.feats
 
     # ------------------------------------------------------------------
     def adapt(self, images: torch.Tensor) -> torch.Tensor:
@@ -482,8 +528,7 @@ class RlcfEngine:
         ops.entropy_select(self.logits_all, B, V, C, S, self.sel, self.sel_global, self.entropy)
         # reward_model.set_image_features(inputs[selected_idx])       (tpt_cls_rl.py:59)
         if cfg.loss == "rlcf":
-            xr = self.rrun.forward(B * S, self.reward.ln_flat, images=images, view_idx=self.sel_global)
-            self.rrun.head(xr, B * S, self.reward.ln_flat, feat=self.reward_feat)
+            self.scorer.features(images, self.sel_global, B * S)
         for step in range(1, cfg.tta_steps + 1):
             # training-mode forward of the selected views with each image's own parameters (tpt_cls_rl.py:55)
             xs = self.run.forward(B * S, self.params, pstride=P, seqs_per_set=S, images=images,
@@ -492,11 +537,8 @@ class RlcfEngine:
                           logit_scale=self.logit_scale, feat=self.feat_sel, inv_norm=self.inv_norm_sel,
                           logits=self.logits_sel)
             if cfg.loss == "rlcf":
-                ops.reward_loss(self.logits_sel, None, self.reward_feat, self.reward_class_feat, B, S, K, C,
-                                self.dlogits, clipscore_weight=cfg.clipscore_weight,
-                                reward_process=cfg.reward_process, process_batch=cfg.process_batch,
-                                amplify=cfg.reward_amplify, loss_scale=cfg.loss_scale, topk_idx=self.topk_idx,
-                                scores=self.scores, rewards=self.rewards, loss=self.loss[step - 1])
+                self.scorer.loss(self.logits_sel, B, S, K, C, self.dlogits, cfg, topk_idx=self.topk_idx,
+                                 scores=self.scores, rewards=self.rewards, loss=self.loss[step - 1])
             else:
                 ops.avg_entropy_loss(self.logits_sel, None, B, S, C, self.dlogits, loss=self.loss[step - 1],
                                      loss_scale=cfg.loss_scale)
@@ -573,8 +615,8 @@ class RlcfEngine:
         f = self.tower_fwd_flops(self.policy)
         total = V * f + S * self.tower_dgrad_flops(self.policy) + f
         total += (cfg.tta_steps - 1) * S * (f + self.tower_dgrad_flops(self.policy))
-        if self.reward is not None and cfg.loss == "rlcf":
-            total += S * self.tower_fwd_flops(self.reward)
+        if self.scorer is not None and cfg.loss == "rlcf":
+            total += S * self.scorer.fwd_flops()
         return float(total)
 
 
@@ -600,7 +642,6 @@ class PromptEngine:
             raise RlcfError(f"int(n_views * selection_p) = {S}: no view would be selected (tpt_cls_rl.py:34)")
         if cfg.loss == "rlcf" and (reward is None or reward_class_feat is None):
             raise RlcfError("RLCF loss needs a reward tower and reward class features")
-        self.reward_class_feat = None if reward_class_feat is None else reward_class_feat.float().contiguous()
         self.P = self.n_ctx * d
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
@@ -608,7 +649,7 @@ class PromptEngine:
         self.trun = TowerRunner(text, B * C)
         self.trun.reserve_backward(B * C)
         self.tstore = ActStore(text, B * C, dev)
-        self.rrun = TowerRunner(reward, B * S) if reward is not None else None
+        self.scorer = RewardScorer(reward, reward_class_feat, B * S, cfg.reward_weights) if reward is not None else None
         self.init_ctx = ctx_init.detach().float().reshape(-1).contiguous().clone()
         self.ctx = torch.empty(B, self.P, **f32)
         self.m = torch.empty(B, self.P, **f32)
@@ -637,10 +678,11 @@ class PromptEngine:
         self.rewards = torch.empty(B * S, cfg.sample_k, **f32)
         self.loss = torch.empty(cfg.tta_steps, B, **f32)
         self.logits_final = torch.empty(B, C, **f32)
-        self.reward_feat = torch.empty(B * S, reward.E, **f32) if reward is not None else None
         self._graph = None
         self._static_images = None
         self.refresh_initial_text_features()
+
+    reward_feat = RlcfEngine.reward_feat
 
     def refresh_initial_text_features(self):
         """Text features of the un-adapted prompts (shared by every image for the step-0 logits of all views)."""
@@ -670,17 +712,13 @@ class PromptEngine:
         torch.mul(self.sel_global, self.visual.L, out=self.sel_rows)
         self.irun.head(x, B * S, self.visual.ln_flat, row_idx=self.sel_rows, feat=self.img_feat_sel)
         if cfg.loss == "rlcf":
-            xr = self.rrun.forward(B * S, self.reward.ln_flat, images=images, view_idx=self.sel_global)
-            self.rrun.head(xr, B * S, self.reward.ln_flat, feat=self.reward_feat)
+            self.scorer.features(images, self.sel_global, B * S)
         for step in range(1, cfg.tta_steps + 1):
             xs = self._text_features(self.tstore)
             ops.pair_logits(self.img_feat_sel, self.txt_feat, C * E, B, S, C, E, self.logit_scale, self.logits_sel)
             if cfg.loss == "rlcf":
-                ops.reward_loss(self.logits_sel, None, self.reward_feat, self.reward_class_feat, B, S, K, C,
-                                self.dlogits, clipscore_weight=cfg.clipscore_weight,
-                                reward_process=cfg.reward_process, process_batch=cfg.process_batch,
-                                amplify=cfg.reward_amplify, loss_scale=cfg.loss_scale, topk_idx=self.topk_idx,
-                                scores=self.scores, rewards=self.rewards, loss=self.loss[step - 1])
+                self.scorer.loss(self.logits_sel, B, S, K, C, self.dlogits, cfg, topk_idx=self.topk_idx,
+                                 scores=self.scores, rewards=self.rewards, loss=self.loss[step - 1])
             else:
                 ops.avg_entropy_loss(self.logits_sel, None, B, S, C, self.dlogits, loss=self.loss[step - 1],
                                      loss_scale=cfg.loss_scale)
@@ -718,8 +756,8 @@ class PromptEngine:
         cfg, C = self.cfg, self.tokens.shape[0]
         fi, ft = RlcfEngine.tower_fwd_flops(self.visual), RlcfEngine.tower_fwd_flops(self.text)
         total = cfg.n_views * fi + fi + C * ft + cfg.tta_steps * C * (ft + RlcfEngine.tower_dgrad_flops(self.text))
-        if self.reward is not None and cfg.loss == "rlcf":
-            total += cfg.n_selected * RlcfEngine.tower_fwd_flops(self.reward)
+        if self.scorer is not None and cfg.loss == "rlcf":
+            total += cfg.n_selected * self.scorer.fwd_flops()
         return float(total)
 
 

@@ -281,7 +281,7 @@ class FullTuneEngine:
         self.lay = lay = FullLayout(pol)
         self.class_feat = class_feat.float().contiguous()
         self.logit_scale = float(logit_scale)
-        self.reward, self.reward_class_feat = reward, reward_class_feat.float().contiguous()
+        self.reward = reward
         B, V, S, C = n_img, cfg.n_views, cfg.n_selected, self.class_feat.shape[0]
         if S < 1:
             raise RlcfError(f"int(n_views * selection_p) = {S}: no view would be selected (tpt_cls_rl.py:34)")
@@ -293,7 +293,7 @@ class FullTuneEngine:
         self.run = E.TowerRunner(pol, B * V)
         self.run.reserve_backward(B * S)
         self.store = E.ActStore(pol, B * S, dev, full=True)
-        self.rrun = E.TowerRunner(reward, B * S)
+        self.scorer = E.RewardScorer(reward, reward_class_feat, B * S, cfg.reward_weights)
         self.hook = WgradHook(lay, pol, B, S, dev)
         # parameters: LayerNorm slice as in RlcfEngine, everything else in `rest`
         self.init_ln = pol.ln_flat.clone()
@@ -324,7 +324,6 @@ class FullTuneEngine:
         self.rewards = torch.empty(B * S, cfg.sample_k, **f32)
         self.loss = torch.empty(cfg.tta_steps, B, **f32)
         self.logits_final = torch.empty(B, C, **f32)
-        self.reward_feat = torch.empty(B * S, reward.E, **f32)
         self._graph = None
         self._static_images = None
         self.fused_adamw = FUSED_ADAMW
@@ -346,11 +345,8 @@ class FullTuneEngine:
         runner.head(xs, n_sets * S, ln, pstride=pstride, seqs_per_set=S, class_feat=self.class_feat,
                     logit_scale=self.logit_scale, feat=self.feat_sel[sl], inv_norm=self.inv_norm_sel[sl],
                     logits=self.logits_sel[sl], w=w)
-        ops.reward_loss(self.logits_sel[sl], None, self.reward_feat[sl], self.reward_class_feat, n_sets, S, K, C,
-                        self.dlogits[sl], clipscore_weight=cfg.clipscore_weight, reward_process=cfg.reward_process,
-                        process_batch=cfg.process_batch, amplify=cfg.reward_amplify, loss_scale=cfg.loss_scale,
-                        topk_idx=self.topk_idx[sl], scores=self.scores[sl], rewards=self.rewards[sl],
-                        loss=self.loss[step - 1][rows0:rows0 + n_sets])
+        self.scorer.loss(self.logits_sel[sl], n_sets, S, K, C, self.dlogits[sl], cfg, topk_idx=self.topk_idx[sl],
+                         scores=self.scores[sl], rewards=self.rewards[sl], loss=self.loss[step - 1][rows0:rows0 + n_sets])
         off = pol.ln_off("ln_post")
         lnv = ln.view(-1)
         runner.dres[:n_sets * S * pol.L].zero_()
@@ -388,8 +384,7 @@ class FullTuneEngine:
         self.run.head(x, B * V, self.init_ln, class_feat=self.class_feat, logit_scale=self.logit_scale,
                       logits=self.logits_all)
         ops.entropy_select(self.logits_all, B, V, C, S, self.sel, self.sel_global, self.entropy)
-        xr = self.rrun.forward(B * S, self.reward.ln_flat, images=images, view_idx=self.sel_global)
-        self.rrun.head(xr, B * S, self.reward.ln_flat, feat=self.reward_feat)
+        self.scorer.features(images, self.sel_global, B * S)
         # ---- step 1: all images on the shared initial weights
         xs = self.run.forward(B * S, self.ln, pstride=P, seqs_per_set=S, images=images, view_idx=self.sel_global,
                               store=self.store)
@@ -426,6 +421,7 @@ class FullTuneEngine:
     adapt_graph = E.RlcfEngine.adapt_graph
     adapt_host = E.RlcfEngine.adapt_host
     host_pipeline = E.RlcfEngine.host_pipeline
+    reward_feat = E.RlcfEngine.reward_feat
 
     def algorithmic_flops_per_image(self) -> float:
         """SURVEY.md 8(d), full tuning: backward = dgrad + wgrad over the selected views."""
@@ -434,7 +430,7 @@ class FullTuneEngine:
         f = E.RlcfEngine.tower_fwd_flops(w)
         wgrad = w.n_layers * 24 * w.L * w.d * w.d + 2 * (w.L - 1) * w.d * 3 * w.patch * w.patch + 2 * w.d * w.E
         bwd = E.RlcfEngine.tower_dgrad_flops(w) + wgrad
-        total = V * f + S * bwd + f + (cfg.tta_steps - 1) * S * (f + bwd) + S * E.RlcfEngine.tower_fwd_flops(self.reward)
+        total = V * f + S * bwd + f + (cfg.tta_steps - 1) * S * (f + bwd) + S * self.scorer.fwd_flops()
         return float(total)
 
     def export_params(self, b: int, prefix: str = "visual.") -> dict:

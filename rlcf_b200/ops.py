@@ -179,6 +179,29 @@ def reward_loss(logits, row_idx, reward_img, reward_cls, n_img, S, K, C, dlogits
          stream())
 
 
+def reward_loss_multi(logits, row_idx, reward_imgs, reward_clss, weights, n_img, S, K, C, dlogits, clipscore_weight=2.5,
+                      reward_process=True, process_batch=False, amplify=False, loss_scale=1.0, topk_idx=None,
+                      scores=None, rewards=None, loss=None):
+    """reward_loss with an ensemble of reward models: lists of image features [n, E_i], class features [C, E_i] and
+    per-model weights (CLIPRewardsMultiple, clip_reward.py:180-307)."""
+    n = len(reward_imgs)
+    if not 1 <= n <= 4 or len(reward_clss) != n or len(weights) != n:
+        raise _lib.RlcfError("reward_loss_multi: 1..4 reward models with one weight each")
+    _chk(logits, torch.float32, "logits"); _chk(row_idx, torch.int32, "row_idx"); _chk(dlogits, torch.float32, "dlogits")
+    _chk(topk_idx, torch.int32, "topk_idx")
+    for a, b in zip(reward_imgs, reward_clss):
+        _chk(a, torch.float32, "reward_img"); _chk(b, torch.float32, "reward_cls")
+        if a.shape[1] != b.shape[1] or b.shape[0] != C:
+            raise _lib.RlcfError("reward_loss_multi: feature shapes do not match")
+    pad = [None] * (4 - n)
+    imgs, clss = list(reward_imgs) + pad, list(reward_clss) + pad
+    ers = [t.shape[1] for t in reward_imgs] + [0] * (4 - n)
+    wts = [float(x) for x in weights] + [0.0] * (4 - n)
+    call("rlcf_reward_loss_multi", ptr(logits), ptr(row_idx), n, *[ptr(t) for t in imgs], *[ptr(t) for t in clss], *ers,
+         *wts, n_img, S, K, C, float(clipscore_weight), int(bool(reward_process)), int(bool(process_batch)),
+         int(bool(amplify)), float(loss_scale), ptr(dlogits), ptr(topk_idx), ptr(scores), ptr(rewards), ptr(loss), stream())
+
+
 def avg_entropy_loss(logits, row_idx, n_img, S, C, dlogits, loss=None, loss_scale=1.0):
     _chk(logits, torch.float32, "logits"); _chk(dlogits, torch.float32, "dlogits")
     call("rlcf_avg_entropy_loss", ptr(logits), ptr(row_idx), n_img, S, C, float(loss_scale), ptr(dlogits), ptr(loss),

@@ -203,3 +203,48 @@ def test_prompt_tuning_api_matches_oracle():
     assert d.max() <= 2.02 * 5e-3 and (d <= 0.02 * 5e-3).float().mean() > 0.9
     model.reset()
     assert torch.equal(model.prompt_learner.ctx.detach().cpu(), ctx_init)
+
+
+def test_reward_model_ensemble_through_the_api():
+    """CLIPRewardsMultiple (TPT/clip_reward.py:180-307) with two ViT members behind get_reward_model's
+    --multiple_reward_models switch: CLIPScore as the reference computes it, and the adapted logits of the reference-
+    style loop against the oracle's ensemble restatement (itself pinned to the reference's class by golden vectors)."""
+    from rlcf_b200 import clip_reward as CR
+    args = make_args(multiple_reward_models=1, reward_arch="synthetic:tiny-B:1,synthetic:tiny-A:5")
+    with pytest.raises(NotImplementedError):
+        CR.get_reward_model(DEV, make_args(multiple_reward_models=1))          # the reference's RN50x64 ensemble
+    tok_p, tok_r = O.make_tokens(10, 512), O.make_tokens(10, 512)
+    model = CLIPCLS_TTA(DEV, [f"class {i}" for i in range(10)], arch="synthetic:tiny-A:0", prompt_prefix="a photo of a",
+                        only_norm=True, tokenized_prompts=tok_p).cuda(0)
+    optimizer = torch.optim.AdamW(model.parameters(), 5e-3, weight_decay=5e-4)
+    optim_state = deepcopy(optimizer.state_dict())
+    reward_model = CR.CLIPRewardsMultiple(DEV, arch=["synthetic:tiny-B:1", "synthetic:tiny-A:5"], sample_k=3,
+                                          process_batch=False, default_resolutions=64)
+    assert reward_model.weights == [0.5, 0.5] and reward_model.n_model == 2
+    reward_model.set_class_features(tokenized_classes=tok_r.to(DEV))
+    sd_p = O.make_clip_state_dict("tiny-A", 0)
+    sd_r = [O.make_clip_state_dict("tiny-B", 1), O.make_clip_state_dict("tiny-A", 5)]
+    views = O.make_views(1, 16, 64, 9)
+    images = views.to(DEV)
+    # CLIPScore of the class: weighted sum of the members' clipped cosines
+    reward_model.set_image_features(images[:2])
+    idx = torch.tensor([1, 4, 7, 0, 2, 3], device=DEV)
+    got = reward_model.CLIPScore(class_index=idx, pairwise=False).cpu()
+    want = O.clip_score_multi([f.cpu() for f in reward_model.class_features], [f.cpu() for f in reward_model.image_features],
+                              idx.cpu(), 3, reward_model.weights)
+    assert torch.allclose(got, want, atol=1e-6)
+    # the loop
+    model.reset()
+    optimizer.load_state_dict(optim_state)
+    model.train()
+    tpt_cls_rl.test_time_tuning(model, images, optimizer, torch.cuda.amp.GradScaler(init_scale=1000), args,
+                                reward_model=reward_model)
+    model.eval()
+    out = model(images[:1]).cpu()
+    ocfg = O.OracleConfig(n_views=16, selection_p=0.25, tta_steps=1, sample_k=3, lr=5e-3, reward_weights=(0.5, 0.5))
+    ref = O.adapt_one_image(sd_p, model.class_features.cpu(), views, ocfg, sd_r,
+                            [f.cpu() for f in reward_model.class_features])
+    scale = ref["logits_all"].abs().max()
+    delta = (ref["logits_final"] - ref["logits_all"][:1]).abs().max()
+    assert (out - ref["logits_final"]).abs().max() <= 1e-3 * scale + 0.3 * delta
+    assert isinstance(reward_model.image_features, list) and len(reward_model.image_features) == 2

@@ -11,7 +11,8 @@ from oracle import rlcf_oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 POLICY_SEED, REWARD_SEED, VIEW_SEED, TOKEN_SEED = 0, 1, 11, 7
-FAST = ["tiny_rlcf_1step", "tiny_rlcf_3step_amplify", "tiny_rlcf_process_batch", "b32_cfg1_shape"]
+FAST = ["tiny_rlcf_1step", "tiny_rlcf_3step_amplify", "tiny_rlcf_process_batch", "b32_cfg1_shape",
+        "tiny_rlcf_multi_reward", "tiny_rlcf_multi_reward_mean"]
 SLOW = ["b16_l14_cfg2"]
 
 
@@ -26,14 +27,22 @@ def load_case(name):
 
 def oracle_setup(cfg):
     sd_p = O.make_clip_state_dict(cfg["policy"], POLICY_SEED)
-    sd_r = O.make_clip_state_dict(cfg["reward"], cfg.get("reward_seed", REWARD_SEED))
+    multi = isinstance(cfg["reward"], list)       # CLIPRewardsMultiple: a list of reward models
+    if multi:
+        sd_r = [O.make_clip_state_dict(a, s_) for a, s_ in zip(cfg["reward"], cfg["reward_seeds"])]
+        vocab_r = O.ARCHS[cfg["reward"][0]][6]
+    else:
+        sd_r = O.make_clip_state_dict(cfg["reward"], cfg.get("reward_seed", REWARD_SEED))
+        vocab_r = O.ARCHS[cfg["reward"]][6]
     tok_p = O.make_tokens(cfg["C"], O.ARCHS[cfg["policy"]][6], seed=TOKEN_SEED)
-    tok_r = O.make_tokens(cfg["C"], O.ARCHS[cfg["reward"]][6], seed=TOKEN_SEED)
+    tok_r = O.make_tokens(cfg["C"], vocab_r, seed=TOKEN_SEED)
     views = O.make_views(cfg["n_img"], cfg["V"], O.ARCHS[cfg["policy"]][1], VIEW_SEED)
     ocfg = O.OracleConfig(n_views=cfg["V"], selection_p=cfg["rho"], tta_steps=cfg["steps"], sample_k=cfg["K"],
                           lr=cfg["lr"], reward_process=bool(cfg.get("reward_process", 1)),
                           process_batch=bool(cfg.get("process_batch", 0)),
-                          reward_amplify=bool(cfg.get("reward_amplify", 0)))
+                          reward_amplify=bool(cfg.get("reward_amplify", 0)),
+                          reward_weights=tuple(O.ensemble_weights(cfg["confidences"])) if multi else (),
+                          weighted_scores=bool(cfg.get("weighted_scores", 1)))
     return sd_p, sd_r, tok_p, tok_r, views, ocfg
 
 
@@ -43,9 +52,15 @@ def test_oracle_matches_reference(name):
     torch.set_num_threads(os.cpu_count() or 1)
     sd_p, sd_r, tok_p, tok_r, views, ocfg = oracle_setup(cfg)
     cf = O.class_features(sd_p, tok_p)
-    rc = O.class_features(sd_r, tok_r)
     assert np.abs(cf.numpy() - z["class_feat"]).max() < 1e-5
-    assert np.abs(rc.numpy() - z["reward_cls"]).max() < 1e-5
+    if isinstance(sd_r, list):
+        rc = [O.class_features(r, tok_r) for r in sd_r]
+        for i, f in enumerate(rc):
+            assert np.abs(f.numpy() - z[f"reward_cls{i}"]).max() < 1e-5
+        assert list(ocfg.reward_weights) == z["reward_weights"].tolist()
+    else:
+        rc = O.class_features(sd_r, tok_r)
+        assert np.abs(rc.numpy() - z["reward_cls"]).max() < 1e-5
     V = cfg["V"]
     for i in range(cfg["n_img"]):
         out = O.adapt_one_image(sd_p, cf, views[i * V:(i + 1) * V], ocfg, sd_r, rc)

@@ -36,21 +36,32 @@ def build_engine(cfg, n_img, loss="rlcf", cuda_text=False):
     per-image hot loop (computed once per dataset), so hot-path parity is judged on identical
     inputs; cuda_text=True also computes them with the CUDA text tower (end-to-end drop-in behaviour)."""
     sd_p = O.make_clip_state_dict(cfg["policy"], POLICY_SEED)
-    sd_r = O.make_clip_state_dict(cfg["reward"], cfg.get("reward_seed", REWARD_SEED))
     tok_p = O.make_tokens(cfg["C"], O.ARCHS[cfg["policy"]][6], seed=TOKEN_SEED)
-    tok_r = O.make_tokens(cfg["C"], O.ARCHS[cfg["reward"]][6], seed=TOKEN_SEED)
-    sdp_d, sdr_d = to_dev(sd_p), to_dev(sd_r)
+    sdp_d = to_dev(sd_p)
     pol = E.prepare_visual(sdp_d, need_grad=True)
-    rew = E.prepare_visual(sdr_d)
-    if cuda_text:
-        cf = E.text_features(E.prepare_text(sdp_d), tok_p)
-        rc = E.text_features(E.prepare_text(sdr_d), tok_r)
+    weights = ()
+    if isinstance(cfg["reward"], list):      # CLIPRewardsMultiple: an ensemble of reward models (clip_reward.py:180-307)
+        sd_r = [O.make_clip_state_dict(a, s_) for a, s_ in zip(cfg["reward"], cfg["reward_seeds"])]
+        tok_r = O.make_tokens(cfg["C"], O.ARCHS[cfg["reward"][0]][6], seed=TOKEN_SEED)
+        rew = [E.prepare_visual(to_dev(r)) for r in sd_r]
+        rc = [O.class_features(r, tok_r).to(DEV) for r in sd_r]
+        cf = O.class_features(sd_p, tok_p).to(DEV)
+        w = O.ensemble_weights(cfg["confidences"])
+        weights = tuple(w) if cfg.get("weighted_scores", 1) else tuple(1.0 / len(w) for _ in w)
     else:
-        cf, rc = O.class_features(sd_p, tok_p).to(DEV), O.class_features(sd_r, tok_r).to(DEV)
+        sd_r = O.make_clip_state_dict(cfg["reward"], cfg.get("reward_seed", REWARD_SEED))
+        tok_r = O.make_tokens(cfg["C"], O.ARCHS[cfg["reward"]][6], seed=TOKEN_SEED)
+        sdr_d = to_dev(sd_r)
+        rew = E.prepare_visual(sdr_d)
+        if cuda_text:
+            cf = E.text_features(E.prepare_text(sdp_d), tok_p)
+            rc = E.text_features(E.prepare_text(sdr_d), tok_r)
+        else:
+            cf, rc = O.class_features(sd_p, tok_p).to(DEV), O.class_features(sd_r, tok_r).to(DEV)
     rcfg = E.RlcfConfig(n_views=cfg["V"], selection_p=cfg["rho"], tta_steps=cfg["steps"], sample_k=cfg["K"],
                         lr=cfg["lr"], reward_process=bool(cfg.get("reward_process", 1)),
                         process_batch=bool(cfg.get("process_batch", 0)),
-                        reward_amplify=bool(cfg.get("reward_amplify", 0)), loss=loss)
+                        reward_amplify=bool(cfg.get("reward_amplify", 0)), loss=loss, reward_weights=weights)
     eng = E.RlcfEngine(pol, cf, float(sd_p["logit_scale"].exp()), rcfg, n_img, reward=rew, reward_class_feat=rc)
     return eng, (sd_p, sd_r, tok_p, tok_r, cf, rc)
 
@@ -147,7 +158,11 @@ def test_cuda_matches_reference_golden(name):
     cfg = ast.literal_eval(str(z["meta"]))
     eng, (sd_p, _, _, _, cf, rc) = build_engine(cfg, cfg["n_img"])
     assert np.abs(cf.cpu().numpy() - z["class_feat"]).max() < 1e-5      # oracle text features == reference's
-    assert np.abs(rc.cpu().numpy() - z["reward_cls"]).max() < 1e-5
+    if isinstance(rc, list):
+        for i, f in enumerate(rc):
+            assert np.abs(f.cpu().numpy() - z[f"reward_cls{i}"]).max() < 1e-5
+    else:
+        assert np.abs(rc.cpu().numpy() - z["reward_cls"]).max() < 1e-5
     views = O.make_views(cfg["n_img"], cfg["V"], O.ARCHS[cfg["policy"]][1], VIEW_SEED).to(DEV)
     eng.adapt(views)
     torch.cuda.synchronize()
