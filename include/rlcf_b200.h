@@ -343,6 +343,12 @@ int rlcf_reward_loss_multi(const float* logits, const int32_t* row_idx, int n_mo
                            int reward_process, int process_batch, int amplify, float loss_scale, float* dlogits,
                            int32_t* topk_idx, float* scores, float* rewards, float* loss, void* stream);
 
+/* nn.functional.interpolate(images[view_idx], size=(oh, ow), mode="bicubic", align_corners=True): the resize of the
+ * selected views to a reward model's own input resolution (TPT/clip_reward.py:133-134).  images fp32 [*, C, H, W],
+ * view_idx int32 [n_views] or NULL, out fp32 [n_views, C, oh, ow]. */
+int rlcf_bicubic_resize(const float* images, const int32_t* view_idx, int n_views, int C, int H, int W, int oh, int ow,
+                        float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,8 @@ ARCHS = {
     # small towers for fast CPU tests / golden vectors (same code paths: head_dim 64, odd token counts)
     "tiny-A": (128, 64, 2, 128, 16, 77, 512, 128, 2, 2),     # 17 image tokens
     "tiny-B": (256, 64, 3, 256, 8, 77, 512, 128, 2, 2),      # 65 image tokens (reward model in tests)
+    "tiny-C": (256, 96, 3, 256, 16, 77, 512, 128, 2, 2),     # 37 image tokens at 96 px: a reward model whose
+                                                             # resolution differs from the views' (bicubic resize)
     # same towers with CLIP's full vocabulary, for cases tokenised by the real BPE tokenizer (prompt tuning)
     "tiny-P": (128, 64, 2, 128, 16, 77, 49408, 128, 2, 2),
     "tiny-Q": (256, 64, 3, 256, 8, 77, 49408, 128, 2, 2),
@@ -208,9 +210,13 @@ def avg_entropy(outputs):
 
 
 def reward_image_features(sd_reward: dict, images: torch.Tensor) -> torch.Tensor:
-    """CLIPRewards.extract_image_features (TPT/clip_reward.py:130-137); the bicubic resize branch (133-134) is
-    not taken because every configured reward tower runs at the default 224 resolution."""
+    """CLIPRewards.extract_image_features (TPT/clip_reward.py:130-137), including the bicubic resize to the reward
+    model's own input resolution (133-134; e.g. ViT-L/14@336px scoring 224-pixel views)."""
     with torch.no_grad():
+        conv = sd_reward["visual.conv1.weight"]
+        res = conv.shape[-1] * int(round(math.sqrt(sd_reward["visual.positional_embedding"].shape[0] - 1)))
+        if images.shape[-1] != res:
+            images = F.interpolate(images, size=res, mode="bicubic", align_corners=True)
         f = encode_image(sd_reward, images).float()
         return f / f.norm(dim=1, keepdim=True)
 

@@ -74,6 +74,7 @@ _PROTOS = {
     "rlcf_transpose_f16_sets": [_vp, _i, _i, _vp, _i, _i64, _vp],
     "rlcf_resample_u8": [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp],
     "rlcf_resample_taps": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "rlcf_bicubic_resize": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "rlcf_augmix_views": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _vp, _vp],
     "rlcf_transpose_blocks_colsum": [_vp, _i, _i, _i, _i, _i, _i64, _vp, _i64, _vp, _i64, _vp],
     "rlcf_gemm_wgrad_adamw": [_vp, _i, _i64, _vp, _i, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i64, _vp, _i64, _i, _vp,

@@ -1,9 +1,10 @@
 """Reward model with the reference's surface (TPT/clip_reward.py): a frozen CLIP that scores sampled predictions.
 
 get_reward_model(device, args) -> CLIPRewards (clip_reward.py:29-40) or, with --multiple_reward_models 1, the ensemble
-CLIPRewardsMultiple (clip_reward.py:180-307).  The ensemble works for any list of 224-pixel ViT CLIPs; the reference's
-hard-coded list ["ViT-L/14@336px", "RN50x64", "ViT-L/14"] needs a ModifiedResNet tower and a 336-pixel ViT, which are
-out of scope -- pass the architectures as a comma-separated --reward_arch instead.
+CLIPRewardsMultiple (clip_reward.py:180-307).  The ensemble works for any list of ViT CLIPs (views are resized to a
+member's own resolution, clip_reward.py:133-134 / 262-264); the reference's hard-coded list ["ViT-L/14@336px",
+"RN50x64", "ViT-L/14"] contains a ModifiedResNet, which is out of scope -- pass the
+architectures as a comma-separated --reward_arch instead.
 """
 from __future__ import annotations
 
@@ -24,7 +25,7 @@ def get_reward_model(device, args):
         if len(archs) < 2:
             raise NotImplementedError(
                 "--multiple_reward_models 1: the reference's ensemble [ViT-L/14@336px, RN50x64, ViT-L/14] "
-                "(clip_reward.py:31) needs a ResNet tower and a 336-pixel ViT; give 2-4 ViT architectures as "
+                "(clip_reward.py:31) contains a ResNet tower; give 2-4 ViT architectures as "
                 "--reward_arch 'ViT-L/14,ViT-B/16'")
         return CLIPRewardsMultiple(device, arch=archs, classification=True, amplify_rewards=args.reward_amplify,
                                    sample_k=args.sample_k, reward_process=args.reward_process,
@@ -134,7 +135,7 @@ def _confidence(arch: str) -> float:
 
 class CLIPRewardsMultiple(BaseRewards):
     """Ensemble of frozen CLIPs (clip_reward.py:180-307): a sample's CLIPScore is the confidence-weighted sum (or the
-    mean) of the members' scores.  Members must be 224-pixel ViT models."""
+    mean) of the members' scores.  Members must be ViT models (views are resized to each member's resolution)."""
 
     def __init__(self, device, arch=("ViT-B/16", "ViT-L/14"), clipscore_weight=2.5, classification=True,
                  amplify_rewards=False, sample_k=5, reward_process=True, process_batch=True, weighted_scores=True,
@@ -147,9 +148,6 @@ class CLIPRewardsMultiple(BaseRewards):
         self.default_resolutions = default_resolutions
         for ar in arch:
             clip_model, _, preprocess = clip.load(ar, device=device, download_root=DOWNLOAD_ROOT)
-            if clip_model.visual.input_resolution != default_resolutions:
-                raise NotImplementedError(f"{ar}: reward models at a resolution other than {default_resolutions} need "
-                                          "the bicubic resize of clip_reward.py:262-264, which is not implemented")
             models.append(clip_model)
             self.preprocess.append(preprocess)
             self.resolutions.append(clip_model.visual.input_resolution)
@@ -186,8 +184,11 @@ class CLIPRewardsMultiple(BaseRewards):
     @torch.no_grad()
     def extract_image_features(self, images):
         feats = []
-        for m in self.clip_models:
-            f = m.encode_image(images).float()
+        for m, res in zip(self.clip_models, self.resolutions):
+            x = images
+            if res != images.shape[-1]:   # clip_reward.py:262-264 (the engines use rlcf_bicubic_resize for this)
+                x = nn.functional.interpolate(images, size=res, mode="bicubic", align_corners=True)
+            f = m.encode_image(x).float()
             feats.append(f / f.norm(dim=1, keepdim=True))
         return feats
 

@@ -124,6 +124,7 @@ int transpose_f16(const __half*, int, int, __half*, int, long long, cudaStream_t
 int resample_u8(const uint8_t*, int, int, int, const int*, const int*, const int*, int, const int*, const int*, int, int,
                 int, uint8_t*, int, uint8_t*, cudaStream_t);
 int resample_taps(const int*, int, int, int, int, int*, int*, int*, int*, int*, cudaStream_t);
+int bicubic_resize(const float*, const int32_t*, int, int, int, int, int, int, float*, cudaStream_t);
 int augmix_views(const uint8_t*, int, const int*, const float*, const float*, const int*, const int*, const double*,
                  const float*, const float*, float*, cudaStream_t);
 int add_rows(const float*, long long, const float*, long long, int, long long, float*, cudaStream_t);
@@ -508,6 +509,12 @@ int rlcf_reward_loss_multi(const float* logits, const int32_t* row_idx, int n_mo
   return reward_loss_multi(logits, row_idx, n_models, img, cls, er, wt, n_img, S_, K, C, clipscore_weight,
                            reward_process, process_batch, amplify, loss_scale, dlogits, topk_idx, scores, rewards, loss,
                            S(stream));
+}
+
+int rlcf_bicubic_resize(const float* images, const int32_t* view_idx, int n_views, int C, int H_, int W, int oh, int ow,
+                        float* out, void* stream) {
+  if (!images || !out) return set_error(RLCF_ERR_ARG, "bicubic_resize: null pointer");
+  return bicubic_resize(images, view_idx, n_views, C, H_, W, oh, ow, out, S(stream));
 }
 
 }  // extern "C"

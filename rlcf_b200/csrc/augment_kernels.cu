@@ -158,6 +158,65 @@ int resample_u8(const uint8_t* src, int H, int W, int n_views, const int* hdr, c
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ bicubic resize
+// nn.functional.interpolate(images, size, mode="bicubic", align_corners=True) (TPT/clip_reward.py:133-134): the views
+// are resized to the reward model's own input resolution when it is not 224 (e.g. ViT-L/14@336px).  PyTorch's cubic
+// convolution kernel (A = -0.75), source index = dst * (in - 1) / (out - 1), border indices clamped.  view_idx gathers
+// the selected views.  One thread per output pixel and channel plane.
+__device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {
+  const float A = -0.75f;
+  const float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+  w[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  w[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+  w[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+
+__global__ void __launch_bounds__(256)
+bicubic_resize_kernel(const float* __restrict__ in, const int32_t* __restrict__ view_idx, int C, int H, int W, int oh,
+                      int ow, float sy, float sx, long long total, float* __restrict__ out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % ow);
+    const int y = static_cast<int>((i / ow) % oh);
+    const long long plane = i / (static_cast<long long>(ow) * oh);      // view * C + channel
+    const int c = static_cast<int>(plane % C);
+    const long long v = plane / C;
+    const long long sv = view_idx ? view_idx[v] : v;
+    const float* src = in + (sv * C + c) * static_cast<long long>(H) * W;
+    const float fy = sy * y, fx = sx * x;
+    const int iy = static_cast<int>(floorf(fy)), ix = static_cast<int>(floorf(fx));
+    float wy[4], wx[4];
+    cubic_coeffs(fy - iy, wy);
+    cubic_coeffs(fx - ix, wx);
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = min(max(iy - 1 + a, 0), H - 1);
+      const float* row = src + static_cast<long long>(yy) * W;
+      float r = 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) r += row[min(max(ix - 1 + b, 0), W - 1)] * wx[b];
+      acc += r * wy[a];
+    }
+    out[i] = acc;
+  }
+}
+
+int bicubic_resize(const float* in, const int32_t* view_idx, int n_views, int C, int H, int W, int oh, int ow, float* out,
+                   cudaStream_t stream) {
+  if (n_views <= 0 || C <= 0 || H <= 0 || W <= 0 || oh <= 0 || ow <= 0)
+    return set_error(RLCF_ERR_ARG, "bicubic_resize: bad shape");
+  const float sy = oh > 1 ? static_cast<float>(H - 1) / static_cast<float>(oh - 1) : 0.f;
+  const float sx = ow > 1 ? static_cast<float>(W - 1) / static_cast<float>(ow - 1) : 0.f;
+  const long long total = static_cast<long long>(n_views) * C * oh * ow;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  bicubic_resize_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(in, view_idx, C, H, W, oh, ow, sy, sx, total, out);
+  RLCF_CHECK_LAUNCH("bicubic_resize");
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ AugMix
 enum { OP_AUTOCONTRAST = 0, OP_EQUALIZE = 1, OP_POSTERIZE = 2, OP_SOLARIZE = 3, OP_AFFINE = 4 };
 constexpr int kPlane = 224;

@@ -415,11 +415,20 @@ class RewardScorer:
         dev = self.towers[0].ln_flat.device
         self.runners = [TowerRunner(t, n_seq_max) for t in self.towers]
         self.feats = [torch.empty(n_seq_max, t.E, dtype=torch.float32, device=dev) for t in self.towers]
+        self.resized = [None] * len(self.towers)    # views at the tower's own resolution, allocated on first use
 
     def features(self, images, view_idx, n_seq):
-        """reward_model.set_image_features(inputs[selected_idx])          (tpt_cls_rl.py:59, clip_reward.py:130-137)"""
-        for t, r, f in zip(self.towers, self.runners, self.feats):
-            x = r.forward(n_seq, t.ln_flat, images=images, view_idx=view_idx)
+        """reward_model.set_image_features(inputs[selected_idx])          (tpt_cls_rl.py:59, clip_reward.py:130-137),
+        with the bicubic resize of clip_reward.py:133-134 when a reward model runs at another resolution."""
+        for i, (t, r, f) in enumerate(zip(self.towers, self.runners, self.feats)):
+            if images.shape[-1] != t.resolution or images.shape[-2] != t.resolution:
+                if self.resized[i] is None:
+                    self.resized[i] = torch.empty(r.max_seq, images.shape[1], t.resolution, t.resolution,
+                                                  dtype=torch.float32, device=images.device)
+                ops.bicubic_resize(images, view_idx, n_seq, self.resized[i])
+                x = r.forward(n_seq, t.ln_flat, images=self.resized[i])
+            else:
+                x = r.forward(n_seq, t.ln_flat, images=images, view_idx=view_idx)
             r.head(x, n_seq, t.ln_flat, feat=f)
 
     def loss(self, logits, n_img, S, K, C, dlogits, cfg, **outs):

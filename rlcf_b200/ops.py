@@ -476,3 +476,13 @@ def gemm_wgrad_adamw(a, b, params, m, v, params_in, params_in_gs, fresh, w16, lr
          ptr(params), ptr(m), ptr(v), params.stride(1), params.stride(0), ptr(params_in), params_in_gs, int(bool(fresh)),
          ptr(w16), 0 if w16 is None else w16.stride(0), float(lr), float(beta1), float(beta2), float(eps),
          float(weight_decay), int(step), float(loss_scale), stream())
+
+
+def bicubic_resize(images, view_idx, n_views, out):
+    """out [n_views, C, oh, ow] = interpolate(images[view_idx], size=(oh, ow), mode="bicubic", align_corners=True)."""
+    _chk(images, torch.float32, "images"); _chk(view_idx, torch.int32, "view_idx"); _chk(out, torch.float32, "out")
+    _, c, h, w = images.shape
+    if out.shape[0] < n_views or out.shape[1] != c:
+        raise _lib.RlcfError("bicubic_resize: out must be [>= n_views, C, oh, ow]")
+    call("rlcf_bicubic_resize", ptr(images), ptr(view_idx), n_views, c, h, w, out.shape[2], out.shape[3], ptr(out), stream())
+    return out

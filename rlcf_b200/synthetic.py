@@ -17,6 +17,7 @@ ARCHS = {
     "ViT-L/14": (768, 224, 24, 1024, 14, 77, 49408, 768, 12, 12),
     "tiny-A": (128, 64, 2, 128, 16, 77, 512, 128, 2, 2),
     "tiny-B": (256, 64, 3, 256, 8, 77, 512, 128, 2, 2),
+    "tiny-C": (256, 96, 3, 256, 16, 77, 512, 128, 2, 2),
     "tiny-P": (128, 64, 2, 128, 16, 77, 49408, 128, 2, 2),
     "tiny-Q": (256, 64, 3, 256, 8, 77, 49408, 128, 2, 2),
 }

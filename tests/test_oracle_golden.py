@@ -12,7 +12,7 @@ from oracle import rlcf_oracle as O
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 POLICY_SEED, REWARD_SEED, VIEW_SEED, TOKEN_SEED = 0, 1, 11, 7
 FAST = ["tiny_rlcf_1step", "tiny_rlcf_3step_amplify", "tiny_rlcf_process_batch", "b32_cfg1_shape",
-        "tiny_rlcf_multi_reward", "tiny_rlcf_multi_reward_mean"]
+        "tiny_rlcf_multi_reward", "tiny_rlcf_multi_reward_mean", "tiny_rlcf_reward_resize"]
 SLOW = ["b16_l14_cfg2"]
 
 
