@@ -39,7 +39,7 @@ CASES = {
     "b16_l14_cfg2": dict(policy="ViT-B/16", reward="ViT-L/14", V=64, rho=0.1, K=3, C=200, steps=1, lr=5e-3, n_img=1),
     # reward model at another resolution than the views (clip_reward.py:133-134: bicubic resize, align_corners=True)
     "tiny_rlcf_reward_resize": dict(policy="tiny-A", reward="tiny-C", V=16, rho=0.25, K=3, C=10, steps=1, lr=5e-3,
-                                    n_img=2),
+                                    n_img=2, reward_seed=3),   # seed 1: every CLIPScore of image 0 is clipped to 0
     # CLIPRewardsMultiple (clip_reward.py:180-307) with two / three ViT members; confidences as CONFIDECES would give
     # ViT-L/14 (5) and ViT-B/16 (1)
     "tiny_rlcf_multi_reward": dict(policy="tiny-A", reward=["tiny-B", "tiny-A"], reward_seeds=[1, 5], confidences=[5, 1],
