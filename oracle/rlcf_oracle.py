@@ -29,6 +29,7 @@ ARCHS = {
     "ViT-B/32": (512, 224, 12, 768, 32, 77, 49408, 512, 8, 12),
     "ViT-B/16": (512, 224, 12, 768, 16, 77, 49408, 512, 8, 12),
     "ViT-L/14": (768, 224, 24, 1024, 14, 77, 49408, 768, 12, 12),
+    "ViT-L/14@336px": (768, 336, 24, 1024, 14, 77, 49408, 768, 12, 12),
     # small towers for fast CPU tests / golden vectors (same code paths: head_dim 64, odd token counts)
     "tiny-A": (128, 64, 2, 128, 16, 77, 512, 128, 2, 2),     # 17 image tokens
     "tiny-B": (256, 64, 3, 256, 8, 77, 512, 128, 2, 2),      # 65 image tokens (reward model in tests)

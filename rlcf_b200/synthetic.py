@@ -15,6 +15,7 @@ ARCHS = {
     "ViT-B/32": (512, 224, 12, 768, 32, 77, 49408, 512, 8, 12),
     "ViT-B/16": (512, 224, 12, 768, 16, 77, 49408, 512, 8, 12),
     "ViT-L/14": (768, 224, 24, 1024, 14, 77, 49408, 768, 12, 12),
+    "ViT-L/14@336px": (768, 336, 24, 1024, 14, 77, 49408, 768, 12, 12),
     "tiny-A": (128, 64, 2, 128, 16, 77, 512, 128, 2, 2),
     "tiny-B": (256, 64, 3, 256, 8, 77, 512, 128, 2, 2),
     "tiny-C": (256, 96, 3, 256, 16, 77, 512, 128, 2, 2),

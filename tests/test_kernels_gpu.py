@@ -213,6 +213,19 @@ def test_attention_fwd_bwd(L, heads, causal, impl):
     _lib.set_attention_impl(0)
 
 
+def test_attention_forward_at_336_pixel_sequence_length():
+    """577 tokens (ViT-L/14@336px as a reward model, clip_reward.py:22-27): beyond the single-tile tcgen05 kernel, served
+    by the warp-MMA kernel; forward only (reward models are frozen)."""
+    torch.manual_seed(577)
+    n_seq, L, heads = 2, 577, 16
+    d = heads * 64
+    qkv = torch.randn(n_seq * L, 3 * d, device=_dev()).half()
+    out = torch.empty(n_seq * L, d, device=_dev(), dtype=torch.float16)
+    ops.attention_fwd(qkv, n_seq, L, heads, out)
+    ref, _ = _ref_attention(qkv.float(), n_seq, L, heads, False)
+    assert _rel(out, ref) < 2e-3
+
+
 @pytest.mark.parametrize("patch,res,k_pad", [(16, 224, 768), (14, 224, 640), (32, 224, 3072), (8, 32, 192)])
 def test_im2col(patch, res, k_pad):
     torch.manual_seed(patch)
