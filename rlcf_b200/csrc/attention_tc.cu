@@ -30,7 +30,7 @@ struct AttnTcArgs {
   int o_off;                    // TMEM column (inside the team's 256) of the O accumulator
   int n_qt, n_units;            // query tiles per (sequence, head); number of (sequence, head) units
   int stage_bytes;
-  int debug;                    // RLCF_ATTN_DEBUG bit mask (timing probes only): 1 skip max pass, 2 skip exp pass, 4 skip stores
+  int debug;                    // RLCF_ATTN_DEBUG bit mask (timing probes only): 1 skip max pass, 2 skip exp pass, 4 skip stores, 8 timeline, 16 no exp token, 32 per-thread O stores
   __half* out;
   float* lse;
 };
@@ -69,59 +69,57 @@ constexpr int kMaxExtraKeys = 16;
 enum { B_KVFULL = 0, B_KVFREE = 1, B_QFULL = 2 /*+buf*/, B_QFREE = 4 /*+buf*/, B_SREADY = 6, B_PREADY = 7, B_OREADY = 8,
        B_TMEMFREE = 9, B_PER_TEAM = 10 };
 
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// max over the visible keys of one 32-column S chunk
+// max over the visible keys of one 32-column S chunk (two independent chains of 3-input maxima)
 __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], float m, int ch, bool full, int key_end) {
+  float m2 = -INFINITY;
   if (full) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+    for (int j = 0; j < 16; ++j) {
+      m = fmaxf(m, __uint_as_float(v[j]));
+      m2 = fmaxf(m2, __uint_as_float(v[16 + j]));
+    }
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) m = fmaxf(m, (ch * 32 + j < key_end) ? __uint_as_float(v[j]) : -INFINITY);
+    for (int j = 0; j < 16; ++j) {
+      m = fmaxf(m, (ch * 32 + j < key_end) ? __uint_as_float(v[j]) : -INFINITY);
+      m2 = fmaxf(m2, (ch * 32 + 16 + j < key_end) ? __uint_as_float(v[16 + j]) : -INFINITY);
+    }
   }
-  return m;
+  return fmaxf(m, m2);
 }
 
 // p = 2^(s c - m c) for one chunk; writes the packed fp16 P chunk to TMEM columns [16 ch, 16 ch + 16) -- S columns
-// this row has already consumed -- and returns the chunk's row-sum contribution
+// this row has already consumed -- and returns the chunk's row-sum contribution.  (Evaluating a fraction of the
+// exponentials with a polynomial on the FMA pipe, as FlashAttention-4 does, was measured 8-14 % SLOWER here: the pass
+// is paced by TMEM reads and per-warp issue latency, not by the MUFU lanes -- profiles/r1_attention_probes.txt.)
 __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t trow, int ch, bool full, int key_end,
                                            float c, float mc) {
   uint32_t pk[16];
-  float l = 0.f;
-  if (full) {
+  float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float a = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -mc));
-      const float b = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c, -mc));
-      l += a + b;
-      const __half2 hp = __floats2half2_rn(a, b);
-      pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
+  for (int j = 0; j < 16; ++j) {
+    const float ta = fmaf(__uint_as_float(v[2 * j]), c, -mc), tb = fmaf(__uint_as_float(v[2 * j + 1]), c, -mc);
+    float a = ex2_approx(ta), b = ex2_approx(tb);
+    if (!full) {
+      a = (ch * 32 + 2 * j < key_end) ? a : 0.f;
+      b = (ch * 32 + 2 * j + 1 < key_end) ? b : 0.f;
     }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float a = (ch * 32 + 2 * j < key_end) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -mc)) : 0.f;
-      const float b = (ch * 32 + 2 * j + 1 < key_end) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c, -mc)) : 0.f;
-      l += a + b;
-      const __half2 hp = __floats2half2_rn(a, b);
-      pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
-    }
+    if (j & 1) l1 += a + b; else l0 += a + b;
+    const __half2 hp = __floats2half2_rn(a, b);
+    pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
   }
   tmem_st_32x16(trow + ch * 16, pk);
-  return l;
+  return l0 + l1;
 }
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKV, AttnTcArgs p) {
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKV,
+                   const __grid_constant__ CUtensorMap mapO, AttnTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * p.stage_bytes);  // [2 teams][B_PER_TEAM]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * B_PER_TEAM);
+  uint64_t* tok = bars + 2 * B_PER_TEAM;                                   // [4 lane quarters][2 teams]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = p.heads * 64;
@@ -129,12 +127,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   if (tid == 0) {
     tma_prefetch_desc(&mapQ);
     tma_prefetch_desc(&mapKV);
+    tma_prefetch_desc(&mapO);
     for (int t = 0; t < 2; ++t) {
       uint64_t* b = bars + t * B_PER_TEAM;
       for (int i = 0; i < B_PER_TEAM; ++i) mbar_init(&b[i], 1);
       mbar_init(&b[B_PREADY], 4);    // one arrive per softmax warp
       mbar_init(&b[B_TMEMFREE], 4);
+      if (!(p.debug & 32)) {         // the O tile is staged in the Q buffer: its TMA store must have read it too
+        mbar_init(&b[B_QFREE], 5);
+        mbar_init(&b[B_QFREE + 1], 5);
+      }
     }
+    for (int i = 0; i < 8; ++i) mbar_init(&tok[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
@@ -212,6 +216,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
     const int n_chunks = (p.n_mma + 31) >> 5;
     const int n_extra = p.L - p.n_mma;              // keys scored on CUDA cores (<= kMaxExtraKeys), usually <= 0
+    // The exponential pass is bound by the MUFU / conversion lanes of the SM sub-partition that this warp shares with
+    // the other team's warp of the same lane quarter.  Left alone the two teams fall into lockstep (both in the exp
+    // pass, then both waiting for the tensor core).  A token per lane quarter lets one of the two warps through at a
+    // time, strictly alternating, which shifts the teams by one exp pass: one team's exponentials overlap the other
+    // team's MMAs, epilogue and loads.  Every warp takes the token once per tile (dead warps pass it on) and the team
+    // with fewer tiles keeps passing it until the other one is done.
+    const bool use_tok = !(p.debug & 16);
+    const bool tma_out = !(p.debug & 32);
+    uint64_t* tok_mine = &tok[(warp & 3) * 2 + team];
+    uint64_t* tok_other = &tok[(warp & 3) * 2 + (team ^ 1)];
+    auto units_of = [&](int t) {
+      const int f = static_cast<int>(blockIdx.x) + t * static_cast<int>(gridDim.x);
+      return f < p.n_units ? (p.n_units - f + stride - 1) / stride : 0;
+    };
+    const uint32_t n_tok = static_cast<uint32_t>(max(units_of(0), units_of(1)) * p.n_qt);
     uint32_t tc = 0;
     for (int u = first; u < p.n_units; u += stride) {
       const int h = u % p.heads, seq = u / p.heads;
@@ -224,9 +243,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         // chunks below `full_chunks` are visible to every row of this warp: no masking needed there
         const int warp_min_end = p.causal ? min(p.L, q0 + (warp & 3) * 32 + 1) : p.L;
         const int full_chunks = min(n_chunks, warp_min_end >> 5);
+        // RLCF_ATTN_DEBUG & 8: timeline probe -- the first softmax warp of each team of CTA 0 writes clock64 stamps of
+        // its first 64 tiles into the (oversized) lse buffer: [team][tile][8] = {start, S ready, max done, P written,
+        // O ready, stored}
+        const bool probe = (p.debug & 8) && blockIdx.x == 0 && (warp & 3) == 0 && lane == 0 && tc < 64 && p.lse != nullptr;
+        long long* stamp = reinterpret_cast<long long*>(p.lse) + (team * 64 + (tc & 63)) * 8;
+        if (probe) stamp[0] = clock64();
         mbar_wait(&tb[B_SREADY], ph);
         tc_fence_after();
+        if (probe) stamp[1] = clock64();
+        if (tma_out && tc > 0 && lane == 0) {   // the previous tile's O store has left its Q buffer
+          bulk_wait_read_all();
+          mbar_arrive(&tb[B_QFREE + ((tc - 1) & 1)]);
+        }
         float m = -INFINITY, l = 0.f;
+        bool tok_held = false;
         float sx[kMaxExtraKeys];
         if (warp_live) {
           if (n_extra > 0) {
@@ -273,6 +304,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
           }
           // ---- pass 2: p = 2^(s*c - m*c), row sum, packed fp16 P back into consumed S columns
           const float mc = m * c;
+          if (probe) stamp[2] = clock64();
+          if (use_tok) {
+            mbar_wait(tok_mine, team == 0 ? ((tc & 1) ^ 1) : (tc & 1));
+            tok_held = true;
+          }
           if (!(p.debug & 2)) {
             uint32_t va[32], vb[32];
             tmem_ld_32x32(trow, va);
@@ -302,12 +338,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
           }
           tmem_st_wait();
         }
+        if (use_tok && !tok_held) mbar_wait(tok_mine, team == 0 ? ((tc & 1) ^ 1) : (tc & 1));  // dead warp: pass it on
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tb[B_PREADY]);
+        if (lane == 0) {
+          if (use_tok) mbar_arrive(tok_other);
+          mbar_arrive(&tb[B_PREADY]);
+        }
+        if (probe) stamp[3] = clock64();
         // ---- epilogue
         mbar_wait(&tb[B_OREADY], ph);
         tc_fence_after();
+        if (probe) stamp[4] = clock64();
         if (warp_live) {
           uint32_t o[64];
           tmem_ld_32x32(trow + p.o_off, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
@@ -316,26 +358,55 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tb[B_TMEMFREE]);
-          if (qrow < p.L && !(p.debug & 4)) {
-            const float inv = 1.f / l;
+          const float inv = 1.f / l;
+          uint4 ov[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __half2 h0 = __floats2half2_rn(__uint_as_float(o[8 * j + 0]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
+            __half2 h1 = __floats2half2_rn(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
+            __half2 h2 = __floats2half2_rn(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
+            __half2 h3 = __floats2half2_rn(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
+            ov[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                               *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+          }
+          if (tma_out) {
+            // Stage this warp's 32 x 64 O block in its rows of the tile's Q buffer (S = Q K^T has retired; the buffer
+            // is handed back to the producer only after this store, see B_QFREE), 128-byte swizzled like a TMA box,
+            // and let one TMA store write it: full 128-byte rows, rows >= L clipped by the tensor map.  One thread
+            // per row storing its own 128 bytes cost 8 fully scattered store instructions per warp, which backed the
+            // LSU up for ~2000 cycles per tile.
+            if (!(p.debug & 4)) {
+              uint4* srow = reinterpret_cast<uint4*>(const_cast<uint8_t*>(sQb) + r * 128);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) srow[j ^ (r & 7)] = ov[j];
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(&mapO, sQb + (warp & 3) * 32 * 128, h * 64, q0 + (warp & 3) * 32, seq);
+                bulk_commit_group();
+              }
+            }
+          } else if (qrow < p.L && !(p.debug & 4)) {
             uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(seq) * p.L + qrow) * d + h * 64);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __half2 h0 = __floats2half2_rn(__uint_as_float(o[8 * j + 0]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
-              __half2 h1 = __floats2half2_rn(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
-              __half2 h2 = __floats2half2_rn(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
-              __half2 h3 = __floats2half2_rn(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
-              dst[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                                  *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
-            }
-            if (p.lse != nullptr)
-              p.lse[(static_cast<size_t>(seq) * p.heads + h) * p.L + qrow] = m * 0.125f + logf(l);
+            for (int j = 0; j < 8; ++j) dst[j] = ov[j];
           }
+          if (qrow < p.L && !(p.debug & 4) && p.lse != nullptr && !(p.debug & 8))
+            p.lse[(static_cast<size_t>(seq) * p.heads + h) * p.L + qrow] = m * 0.125f + logf(l);
         } else {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tb[B_TMEMFREE]);
         }
+        if (probe) stamp[5] = clock64();
+      }
+    }
+    if (tma_out && lane == 0) bulk_wait_read_all();  // shared memory must outlive the last O store's read
+    if (use_tok) {
+      for (; tc < n_tok; ++tc) {                     // keep the other team's token moving
+        mbar_wait(tok_mine, team == 0 ? ((tc & 1) ^ 1) : (tc & 1));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tok_other);
       }
     }
   }
@@ -377,11 +448,11 @@ int attention_fwd_tc(const __half* qkv, int n_seq, int L, int heads, int causal,
   a.stage_bytes = 2 * 128 * 128 + 2 * Lk * 128;
   static const int debug = getenv("RLCF_ATTN_DEBUG") ? atoi(getenv("RLCF_ATTN_DEBUG")) : 0;
   a.debug = debug;
-  const size_t smem = 1024 + 2 * static_cast<size_t>(a.stage_bytes) + 2 * B_PER_TEAM * 8 + 16;
+  const size_t smem = 1024 + 2 * static_cast<size_t>(a.stage_bytes) + (2 * B_PER_TEAM + 8) * 8 + 16;
+  auto kernel = attn_fwd_tc_kernel;
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return set_error(RLCF_ERR_CUDA, "attention_fwd_tc attr: %s", cudaGetErrorString(e));
     configured = smem;
   }
@@ -389,8 +460,24 @@ int attention_fwd_tc(const __half* qkv, int n_seq, int L, int heads, int causal,
   const long long rows = static_cast<long long>(n_seq) * L;
   if (int rc = make_tmap_rows64(&mq, qkv, rows, 3 * heads * 64, 128)) return rc;
   if (int rc = make_tmap_rows64(&mkv, qkv, rows, 3 * heads * 64, a.kv_box_rows)) return rc;
+  // out as (column, token, sequence): a 64 x 32 box per softmax warp, tokens >= L clipped
+  CUtensorMap mo;
+  if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return -1;
+  {
+    static PFN_encodeTiled encode = get_encode_tiled();
+    if (encode == nullptr) return set_error(RLCF_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not found");
+    const cuuint64_t dm = static_cast<cuuint64_t>(heads) * 64;
+    cuuint64_t gdim[3] = {dm, static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(n_seq)};
+    cuuint64_t gstride[2] = {dm * 2, dm * 2 * static_cast<cuuint64_t>(L)};
+    cuuint32_t box[3] = {64u, 32u, 1u};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, out, gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(RLCF_ERR_DRIVER, "cuTensorMapEncodeTiled(attention out) failed (%d)", static_cast<int>(r));
+  }
   const int grid = a.n_units < sm_count() ? a.n_units : sm_count();
-  attn_fwd_tc_kernel<<<grid, kAttnThreads, smem, stream>>>(mq, mkv, a);
+  kernel<<<grid, kAttnThreads, smem, stream>>>(mq, mkv, mo, a);
   RLCF_CHECK_LAUNCH("attention_fwd_tc");
   return 0;
 }

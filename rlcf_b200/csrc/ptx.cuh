@@ -85,6 +85,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 // Tile load global -> shared (this CTA) from a rank-3 tensor map (k, row, group), completion on this CTA's mbarrier.
+// TMA store of one box (shared -> global, rows / columns outside the tensor are clipped) + bulk-group bookkeeping
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk stores of this thread have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
                                             int c2) {
   asm volatile(
@@ -249,7 +259,21 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ float quick_gelu(float x) { return __fdividef(x, 1.f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// x * sigmoid(1.702 x) = x / (1 + 2^(-1.702 log2(e) x)) with the two bare MUFU operations (flush-to-zero forms, no range
+// fix-up code): 5 instructions per value.  x -> -inf gives x * rcp(inf) = -0.
+__device__ __forceinline__ float quick_gelu(float x) {
+  return x * rcp_approx(1.f + ex2_approx(x * (-1.702f * 1.4426950408889634f)));
+}
 __device__ __forceinline__ float quick_gelu_grad(float x) {
   float s = __fdividef(1.f, 1.f + __expf(-1.702f * x));
   return s * (1.f + 1.702f * x * (1.f - s));
