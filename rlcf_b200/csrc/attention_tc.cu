@@ -96,17 +96,24 @@ __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t tro
                                            float c, float mc) {
   uint32_t pk[16];
   float l0 = 0.f, l1 = 0.f;
+  if (full) {   // separate straight-line path: predicated-off masking instructions would still take issue slots
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float ta = fmaf(__uint_as_float(v[2 * j]), c, -mc), tb = fmaf(__uint_as_float(v[2 * j + 1]), c, -mc);
-    float a = ex2_approx(ta), b = ex2_approx(tb);
-    if (!full) {
-      a = (ch * 32 + 2 * j < key_end) ? a : 0.f;
-      b = (ch * 32 + 2 * j + 1 < key_end) ? b : 0.f;
+    for (int j = 0; j < 16; ++j) {
+      const float a = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -mc));
+      const float b = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c, -mc));
+      if (j & 1) l1 += a + b; else l0 += a + b;
+      const __half2 hp = __floats2half2_rn(a, b);
+      pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
     }
-    if (j & 1) l1 += a + b; else l0 += a + b;
-    const __half2 hp = __floats2half2_rn(a, b);
-    pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float a = (ch * 32 + 2 * j < key_end) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -mc)) : 0.f;
+      const float b = (ch * 32 + 2 * j + 1 < key_end) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c, -mc)) : 0.f;
+      if (j & 1) l1 += a + b; else l0 += a + b;
+      const __half2 hp = __floats2half2_rn(a, b);
+      pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
+    }
   }
   tmem_st_32x16(trow + ch * 16, pk);
   return l0 + l1;
