@@ -2,6 +2,8 @@
 // head (ln_post + proj + L2-norm + logits) fwd/bwd, entropy selection, top-K/CLIPScore/reward/CE-gradient,
 // fused gradient-reduce + AdamW.  Warp-shuffle reductions, 128-bit global accesses where the layout allows.
 // Reference lines are cited per kernel; see include/rlcf_b200.h for the ABI contract.
+#include <cstdlib>
+
 #include "ptx.cuh"
 #include "rlcf_internal.h"
 
@@ -343,6 +345,125 @@ ln_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* __restr
   }
 }
 
+// Opt-in variant (RLCF_LN_BWD_SMEM=1; measured 197.7 -> 130.0 us per launch at the 32-image policy geometry and
+// bit-identical there for widths 768 / 1024, fp16 and fp32 dy -- scripts/dump_ln_bwd.py; it becomes the default once the
+// whole GPU suite has run with it, this round's GPU budget ended first): the per-warp dgamma / dbeta
+// accumulators live in shared memory instead of 48 registers per lane.  ln_bwd_kernel needs 168 registers, so only ONE
+// 256-thread block fits an SM (8 warps, each with two dependent memory round trips per row) and a 32-image launch runs
+// 7 waves; this form is bounded to 128 registers -> two blocks per SM.  Same additions in the same order per warp and
+// the same slot reduction, so the partials are bit-identical (tests/test_kernels_gpu.py, RLCF_EXPERIMENTAL=1).
+template <int NV, bool kDyF32>
+__global__ void __launch_bounds__(256, 2)
+ln_bwd_smem_kernel(const void* __restrict__ dy_, long long lddy, const float* __restrict__ x, long long ldx,
+                   const float* __restrict__ gamma, long long pstride, int rows_per_set, float eps,
+                   float* __restrict__ dx, long long lddx, int accumulate, __half* __restrict__ dx16,
+                   float* __restrict__ partials, long long p_total, long long p_off) {
+  constexpr int d = NV * 128;
+  extern __shared__ float4 ln_acc[];   // [8 warps][2: dgamma, dbeta][d / 4]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int set = blockIdx.y, slot = blockIdx.x, n_slots = gridDim.x;
+  const int rpb = (rows_per_set + n_slots - 1) / n_slots;
+  const int r_begin = slot * rpb;
+  const int r_end = min(rows_per_set, r_begin + rpb);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma + set * pstride);
+  float4* acc_g = ln_acc + (warp * 2) * (d / 4);
+  float4* acc_b = acc_g + d / 4;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    acc_g[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc_b[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int r = r_begin + warp; r < r_end; r += 8) {
+    const long long row = static_cast<long long>(set) * rows_per_set + r;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+    float4 v[NV], g[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+    if constexpr (kDyF32) {
+      const float4* dr = reinterpret_cast<const float4*>(static_cast<const float*>(dy_) + row * lddy);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) g[i] = dr[lane + 32 * i];
+    } else {
+      const uint2* dr = reinterpret_cast<const uint2*>(static_cast<const __half*>(dy_) + row * lddy);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const uint2 q = dr[lane + 32 * i];
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+        g[i] = make_float4(a.x, a.y, b.x, b.y);
+      }
+    }
+    float mean, rstd;
+    ln_row_stats<NV>(v, d, eps, mean, rstd);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i].x = (v[i].x - mean) * rstd; v[i].y = (v[i].y - mean) * rstd;
+      v[i].z = (v[i].z - mean) * rstd; v[i].w = (v[i].w - mean) * rstd;
+      float4 dg = acc_g[lane + 32 * i], db = acc_b[lane + 32 * i];
+      dg.x += g[i].x * v[i].x; dg.y += g[i].y * v[i].y; dg.z += g[i].z * v[i].z; dg.w += g[i].w * v[i].w;
+      db.x += g[i].x; db.y += g[i].y; db.z += g[i].z; db.w += g[i].w;
+      acc_g[lane + 32 * i] = dg;
+      acc_b[lane + 32 * i] = db;
+      const float4 gm = __ldg(g4 + lane + 32 * i);
+      g[i].x *= gm.x; g[i].y *= gm.y; g[i].z *= gm.z; g[i].w *= gm.w;
+      s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      s2 += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+    if (dx) {
+      float4* o = reinterpret_cast<float4*>(dx + row * lddx);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float4 t;
+        t.x = rstd * (g[i].x - s1 - v[i].x * s2); t.y = rstd * (g[i].y - s1 - v[i].y * s2);
+        t.z = rstd * (g[i].z - s1 - v[i].z * s2); t.w = rstd * (g[i].w - s1 - v[i].w * s2);
+        if (accumulate) {
+          const float4 old = o[lane + 32 * i];
+          t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
+        }
+        o[lane + 32 * i] = t;
+        if (dx16) {
+          __half2 h0 = __floats2half2_rn(t.x, t.y), h1 = __floats2half2_rn(t.z, t.w);
+          *reinterpret_cast<uint2*>(dx16 + row * static_cast<long long>(d) + (lane + 32 * i) * 4) =
+              make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        }
+      }
+    }
+  }
+  if (partials == nullptr) return;
+  float* part = partials + (static_cast<long long>(set) * n_slots + slot) * p_total + p_off;
+  __syncthreads();
+  const float* accf = reinterpret_cast<const float*>(ln_acc);
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int c = threadIdx.x; c < d; c += 256) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += accf[(w * 2 + pass) * d + c];
+      part[pass * d + c] = s;
+    }
+  }
+}
+
+template <int NV, bool kDyF32>
+static cudaError_t launch_ln_bwd_smem(dim3 grid, cudaStream_t stream, const void* dy, long long lddy, const float* x,
+                                      long long ldx, const float* gamma, long long pstride, int rows_per_set, float eps,
+                                      float* dx, long long lddx, int accumulate, __half* dx16, float* partials,
+                                      long long p_total, long long p_off) {
+  constexpr int smem = 8 * 2 * NV * 128 * static_cast<int>(sizeof(float));
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ln_bwd_smem_kernel<NV, kDyF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  ln_bwd_smem_kernel<NV, kDyF32><<<grid, 256, smem, stream>>>(dy, lddy, x, ldx, gamma, pstride, rows_per_set, eps, dx,
+                                                                lddx, accumulate, dx16, partials, p_total, p_off);
+  return cudaSuccess;
+}
+
 int layernorm_bwd(const void* dy, int dy_is_f32, long long lddy, const float* x, long long ldx, const float* gamma,
                   long long pstride, int rows_per_set, int n_sets, int d, float eps, float* dx, long long lddx,
                   int accumulate, __half* dx16, float* partials, int n_slots, long long p_total, long long p_off,
@@ -352,6 +473,20 @@ int layernorm_bwd(const void* dy, int dy_is_f32, long long lddy, const float* x,
   if (partials == nullptr && dx == nullptr) return set_error(RLCF_ERR_ARG, "layernorm_bwd: nothing to compute");
   if (dx16 != nullptr && dx == nullptr) return set_error(RLCF_ERR_ARG, "layernorm_bwd: dx16 needs dx_accum");
   dim3 grid(n_slots, n_sets);
+  static const bool smem_acc = getenv("RLCF_LN_BWD_SMEM") != nullptr && atoi(getenv("RLCF_LN_BWD_SMEM")) != 0;
+  if (smem_acc) {
+    cudaError_t e = cudaSuccess;
+    if (dy_is_f32) {
+      RLCF_DISPATCH_NV(d, (e = launch_ln_bwd_smem<NV, true>(grid, stream, dy, lddy, x, ldx, gamma, pstride, rows_per_set,
+                                                             eps, dx, lddx, accumulate, dx16, partials, p_total, p_off)));
+    } else {
+      RLCF_DISPATCH_NV(d, (e = launch_ln_bwd_smem<NV, false>(grid, stream, dy, lddy, x, ldx, gamma, pstride, rows_per_set,
+                                                              eps, dx, lddx, accumulate, dx16, partials, p_total, p_off)));
+    }
+    if (e != cudaSuccess) return set_error(RLCF_ERR_CUDA, "layernorm_bwd attr: %s", cudaGetErrorString(e));
+    RLCF_CHECK_LAUNCH("layernorm_bwd");
+    return 0;
+  }
   if (dy_is_f32) {
     RLCF_DISPATCH_NV(d, (ln_bwd_kernel<NV, true><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, gamma, pstride,
                                                                             rows_per_set, eps, dx, lddx, accumulate,

@@ -178,6 +178,24 @@ def test_layernorm_fwd_bwd(d):
     assert _rel(dx, xr.grad.view(M, d)) < 2e-5
 
 
+@pytest.mark.skipif(os.environ.get("RLCF_EXPERIMENTAL") != "1", reason="opt-in kernel variants (RLCF_EXPERIMENTAL=1)")
+def test_layernorm_bwd_smem_variant_is_bit_identical(tmp_path):
+    """RLCF_LN_BWD_SMEM=1 (accumulators in shared memory, two blocks per SM) must reproduce the default kernel bit for
+    bit: same additions in the same order.  The switch is read once per process, hence two subprocesses."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("0", "1"):
+        out = tmp_path / f"ln_bwd_{flag}.pt"
+        env = dict(os.environ, RLCF_LN_BWD_SMEM=flag)
+        subprocess.run([sys.executable, os.path.join(root, "scripts", "dump_ln_bwd.py"), str(out)], check=True, env=env,
+                       timeout=300)
+        outs.append(torch.load(out))
+    for key in outs[0]:
+        for a, b in zip(outs[0][key], outs[1][key]):
+            assert torch.equal(a, b), key
+
+
 def _ref_attention(qkv, n_seq, L, heads, causal):
     d = heads * 64
     q, k, v = qkv.float().view(n_seq, L, 3, heads, 64).permute(2, 0, 3, 1, 4)
