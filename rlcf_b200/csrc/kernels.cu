@@ -251,26 +251,40 @@ int embed_text(const long long* tokens, const float* tok_emb, const float* pos, 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma = sum dy * xhat;  dbeta = sum dy.
 // grid (n_slots, n_sets): block b of set s reduces its contiguous chunk of the set's rows and writes one
 // deterministic partial; the AdamW kernel sums the slots.
-template <int NV, bool kDyF32>
-__global__ void __launch_bounds__(256)
-ln_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* __restrict__ x, long long ldx,
-              const float* __restrict__ gamma, long long pstride, int rows_per_set, float eps,
-              float* __restrict__ dx, long long lddx, int accumulate, __half* __restrict__ dx16,
-              float* __restrict__ partials, long long p_total, long long p_off) {
+// kSmemAcc: the per-warp dgamma / dbeta accumulators live in shared memory (`acc`, [8 warps][2][d] floats) instead of 48
+// registers per lane.  ln_bwd_kernel needs 168 registers, so only ONE 256-thread block fits an SM (8 warps, each with two
+// dependent memory round trips per row) and a 32-image launch runs 7 waves; ln_bwd_smem_kernel is bounded to 128
+// registers -> two blocks per SM.  Same additions in the same order per warp and the same slot reduction, so the
+// results are bit-identical.  Opt-in (RLCF_LN_BWD_SMEM=1; measured 197.7 -> 130.0 us per launch at the 32-image policy
+// geometry and bit-identical there for widths 768 / 1024, fp16 and fp32 dy -- scripts/dump_ln_bwd.py,
+// tests/test_kernels_gpu.py with RLCF_EXPERIMENTAL=1; it becomes the default once the whole GPU suite has run with it,
+// this round's GPU budget ended first).
+template <int NV, bool kDyF32, bool kSmemAcc>
+__device__ __forceinline__ void ln_bwd_body(const void* __restrict__ dy_, long long lddy, const float* __restrict__ x,
+                                            long long ldx, const float* __restrict__ gamma, long long pstride,
+                                            int rows_per_set, float eps, float* __restrict__ dx, long long lddx,
+                                            int accumulate, __half* __restrict__ dx16, float* __restrict__ partials,
+                                            long long p_total, long long p_off, float* acc) {
   constexpr int d = NV * 128;
-  __shared__ float red[8][d];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int set = blockIdx.y, slot = blockIdx.x, n_slots = gridDim.x;
   const int rpb = (rows_per_set + n_slots - 1) / n_slots;
   const int r_begin = slot * rpb;
   const int r_end = min(rows_per_set, r_begin + rpb);
   const float4* g4 = reinterpret_cast<const float4*>(gamma + set * pstride);
-  float4 gam[NV], dg[NV], db[NV];
+  float4* acc_g = reinterpret_cast<float4*>(acc) + (warp * 2) * (d / 4);   // kSmemAcc only
+  float4* acc_b = acc_g + d / 4;
+  float4 gam[kSmemAcc ? 1 : NV], dg[kSmemAcc ? 1 : NV], db[kSmemAcc ? 1 : NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    gam[i] = __ldg(g4 + lane + 32 * i);
-    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (kSmemAcc) {
+      acc_g[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      acc_b[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      gam[i] = __ldg(g4 + lane + 32 * i);
+      dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   for (int r = r_begin + warp; r < r_end; r += 8) {
     const long long row = static_cast<long long>(set) * rows_per_set + r;
@@ -299,9 +313,19 @@ ln_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* __restr
     for (int i = 0; i < NV; ++i) {
       v[i].x = (v[i].x - mean) * rstd; v[i].y = (v[i].y - mean) * rstd;
       v[i].z = (v[i].z - mean) * rstd; v[i].w = (v[i].w - mean) * rstd;
-      dg[i].x += g[i].x * v[i].x; dg[i].y += g[i].y * v[i].y; dg[i].z += g[i].z * v[i].z; dg[i].w += g[i].w * v[i].w;
-      db[i].x += g[i].x; db[i].y += g[i].y; db[i].z += g[i].z; db[i].w += g[i].w;
-      g[i].x *= gam[i].x; g[i].y *= gam[i].y; g[i].z *= gam[i].z; g[i].w *= gam[i].w;
+      if constexpr (kSmemAcc) {
+        float4 ag = acc_g[lane + 32 * i], ab = acc_b[lane + 32 * i];
+        ag.x += g[i].x * v[i].x; ag.y += g[i].y * v[i].y; ag.z += g[i].z * v[i].z; ag.w += g[i].w * v[i].w;
+        ab.x += g[i].x; ab.y += g[i].y; ab.z += g[i].z; ab.w += g[i].w;
+        acc_g[lane + 32 * i] = ag;
+        acc_b[lane + 32 * i] = ab;
+        const float4 gm = __ldg(g4 + lane + 32 * i);
+        g[i].x *= gm.x; g[i].y *= gm.y; g[i].z *= gm.z; g[i].w *= gm.w;
+      } else {
+        dg[i].x += g[i].x * v[i].x; dg[i].y += g[i].y * v[i].y; dg[i].z += g[i].z * v[i].z; dg[i].w += g[i].w * v[i].w;
+        db[i].x += g[i].x; db[i].y += g[i].y; db[i].z += g[i].z; db[i].w += g[i].w;
+        g[i].x *= gam[i].x; g[i].y *= gam[i].y; g[i].z *= gam[i].z; g[i].w *= gam[i].w;
+      }
       s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
       s2 += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
     }
@@ -329,122 +353,56 @@ ln_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* __restr
   }
   if (partials == nullptr) return;  // parameters frozen (text tower in prompt tuning): only dx was needed
   float* part = partials + (static_cast<long long>(set) * n_slots + slot) * p_total + p_off;
+  if constexpr (kSmemAcc) {
+    __syncthreads();
 #pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    __syncthreads();
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int c = threadIdx.x; c < d; c += 256) {
+        float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
-      reinterpret_cast<float4*>(red[warp])[lane + 32 * i] = pass == 0 ? dg[i] : db[i];
-    __syncthreads();
-    for (int c = threadIdx.x; c < d; c += 256) {
-      float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += acc[(w * 2 + pass) * d + c];
+        part[pass * d + c] = s;
+      }
+    }
+  } else {
+    float(*red)[d] = reinterpret_cast<float(*)[d]>(acc);   // [8][d]
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      __syncthreads();
 #pragma unroll
-      for (int w = 0; w < 8; ++w) s += red[w][c];
-      part[pass * d + c] = s;
+      for (int i = 0; i < NV; ++i)
+        reinterpret_cast<float4*>(red[warp])[lane + 32 * i] = pass == 0 ? dg[i] : db[i];
+      __syncthreads();
+      for (int c = threadIdx.x; c < d; c += 256) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][c];
+        part[pass * d + c] = s;
+      }
     }
   }
 }
 
-// Opt-in variant (RLCF_LN_BWD_SMEM=1; measured 197.7 -> 130.0 us per launch at the 32-image policy geometry and
-// bit-identical there for widths 768 / 1024, fp16 and fp32 dy -- scripts/dump_ln_bwd.py; it becomes the default once the
-// whole GPU suite has run with it, this round's GPU budget ended first): the per-warp dgamma / dbeta
-// accumulators live in shared memory instead of 48 registers per lane.  ln_bwd_kernel needs 168 registers, so only ONE
-// 256-thread block fits an SM (8 warps, each with two dependent memory round trips per row) and a 32-image launch runs
-// 7 waves; this form is bounded to 128 registers -> two blocks per SM.  Same additions in the same order per warp and
-// the same slot reduction, so the partials are bit-identical (tests/test_kernels_gpu.py, RLCF_EXPERIMENTAL=1).
+template <int NV, bool kDyF32>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* __restrict__ x, long long ldx,
+              const float* __restrict__ gamma, long long pstride, int rows_per_set, float eps,
+              float* __restrict__ dx, long long lddx, int accumulate, __half* __restrict__ dx16,
+              float* __restrict__ partials, long long p_total, long long p_off) {
+  __shared__ float red[8 * NV * 128];
+  ln_bwd_body<NV, kDyF32, false>(dy_, lddy, x, ldx, gamma, pstride, rows_per_set, eps, dx, lddx, accumulate, dx16,
+                                 partials, p_total, p_off, red);
+}
+
 template <int NV, bool kDyF32>
 __global__ void __launch_bounds__(256, 2)
 ln_bwd_smem_kernel(const void* __restrict__ dy_, long long lddy, const float* __restrict__ x, long long ldx,
                    const float* __restrict__ gamma, long long pstride, int rows_per_set, float eps,
                    float* __restrict__ dx, long long lddx, int accumulate, __half* __restrict__ dx16,
                    float* __restrict__ partials, long long p_total, long long p_off) {
-  constexpr int d = NV * 128;
   extern __shared__ float4 ln_acc[];   // [8 warps][2: dgamma, dbeta][d / 4]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int set = blockIdx.y, slot = blockIdx.x, n_slots = gridDim.x;
-  const int rpb = (rows_per_set + n_slots - 1) / n_slots;
-  const int r_begin = slot * rpb;
-  const int r_end = min(rows_per_set, r_begin + rpb);
-  const float4* g4 = reinterpret_cast<const float4*>(gamma + set * pstride);
-  float4* acc_g = ln_acc + (warp * 2) * (d / 4);
-  float4* acc_b = acc_g + d / 4;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    acc_g[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    acc_b[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  for (int r = r_begin + warp; r < r_end; r += 8) {
-    const long long row = static_cast<long long>(set) * rows_per_set + r;
-    const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
-    float4 v[NV], g[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
-    if constexpr (kDyF32) {
-      const float4* dr = reinterpret_cast<const float4*>(static_cast<const float*>(dy_) + row * lddy);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) g[i] = dr[lane + 32 * i];
-    } else {
-      const uint2* dr = reinterpret_cast<const uint2*>(static_cast<const __half*>(dy_) + row * lddy);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const uint2 q = dr[lane + 32 * i];
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
-        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
-        g[i] = make_float4(a.x, a.y, b.x, b.y);
-      }
-    }
-    float mean, rstd;
-    ln_row_stats<NV>(v, d, eps, mean, rstd);
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      v[i].x = (v[i].x - mean) * rstd; v[i].y = (v[i].y - mean) * rstd;
-      v[i].z = (v[i].z - mean) * rstd; v[i].w = (v[i].w - mean) * rstd;
-      float4 dg = acc_g[lane + 32 * i], db = acc_b[lane + 32 * i];
-      dg.x += g[i].x * v[i].x; dg.y += g[i].y * v[i].y; dg.z += g[i].z * v[i].z; dg.w += g[i].w * v[i].w;
-      db.x += g[i].x; db.y += g[i].y; db.z += g[i].z; db.w += g[i].w;
-      acc_g[lane + 32 * i] = dg;
-      acc_b[lane + 32 * i] = db;
-      const float4 gm = __ldg(g4 + lane + 32 * i);
-      g[i].x *= gm.x; g[i].y *= gm.y; g[i].z *= gm.z; g[i].w *= gm.w;
-      s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
-      s2 += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
-    }
-    s1 = warp_sum(s1) / d;
-    s2 = warp_sum(s2) / d;
-    if (dx) {
-      float4* o = reinterpret_cast<float4*>(dx + row * lddx);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        float4 t;
-        t.x = rstd * (g[i].x - s1 - v[i].x * s2); t.y = rstd * (g[i].y - s1 - v[i].y * s2);
-        t.z = rstd * (g[i].z - s1 - v[i].z * s2); t.w = rstd * (g[i].w - s1 - v[i].w * s2);
-        if (accumulate) {
-          const float4 old = o[lane + 32 * i];
-          t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
-        }
-        o[lane + 32 * i] = t;
-        if (dx16) {
-          __half2 h0 = __floats2half2_rn(t.x, t.y), h1 = __floats2half2_rn(t.z, t.w);
-          *reinterpret_cast<uint2*>(dx16 + row * static_cast<long long>(d) + (lane + 32 * i) * 4) =
-              make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-        }
-      }
-    }
-  }
-  if (partials == nullptr) return;
-  float* part = partials + (static_cast<long long>(set) * n_slots + slot) * p_total + p_off;
-  __syncthreads();
-  const float* accf = reinterpret_cast<const float*>(ln_acc);
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    for (int c = threadIdx.x; c < d; c += 256) {
-      float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) s += accf[(w * 2 + pass) * d + c];
-      part[pass * d + c] = s;
-    }
-  }
+  ln_bwd_body<NV, kDyF32, true>(dy_, lddy, x, ldx, gamma, pstride, rows_per_set, eps, dx, lddx, accumulate, dx16,
+                                partials, p_total, p_off, reinterpret_cast<float*>(ln_acc));
 }
 
 template <int NV, bool kDyF32>
