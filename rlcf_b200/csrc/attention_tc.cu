@@ -223,12 +223,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
     const int n_chunks = (p.n_mma + 31) >> 5;
     const int n_extra = p.L - p.n_mma;              // keys scored on CUDA cores (<= kMaxExtraKeys), usually <= 0
-    // The exponential pass is bound by the MUFU / conversion lanes of the SM sub-partition that this warp shares with
-    // the other team's warp of the same lane quarter.  Left alone the two teams fall into lockstep (both in the exp
-    // pass, then both waiting for the tensor core).  A token per lane quarter lets one of the two warps through at a
-    // time, strictly alternating, which shifts the teams by one exp pass: one team's exponentials overlap the other
-    // team's MMAs, epilogue and loads.  Every warp takes the token once per tile (dead warps pass it on) and the team
-    // with fewer tiles keeps passing it until the other one is done.
+    // Left alone the two teams fall into lockstep (same phase within 200 cycles: both in the exp pass on the same SM
+    // sub-partitions, then both waiting for the tensor core).  A token per lane quarter lets only one of the two warps
+    // that share a sub-partition into its exp pass at a time, strictly alternating, which shifts the teams by one exp
+    // pass: one team's exponentials overlap the other team's MMAs, O read-out and loads (-10 % kernel time; one token
+    // per team instead of per quarter measures the same).  Every warp takes the token once per tile (dead warps pass
+    // it on) and the team with fewer tiles keeps passing it until the other one is done.
     const bool use_tok = !(p.debug & 16);
     const bool tma_out = !(p.debug & 32);
     uint64_t* tok_mine = &tok[(warp & 3) * 2 + team];
