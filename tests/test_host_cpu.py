@@ -149,3 +149,70 @@ def test_ctypes_prototypes_match_the_header_parameter_counts():
         params = params.strip()
         n = 0 if params in ("", "void") else params.count(",") + 1
         assert len(_lib._PROTOS[name]) == n, f"{name}: header has {n} parameters, _lib._PROTOS {len(_lib._PROTOS[name])}"
+
+
+def _stub_cls_tta(only_norm, momentum_update, update_freq=2, update_w=0.5, momentum=0.9):
+    """CLIPCLS_TTA without its constructor (which loads a CLIP onto the GPU): only the weight-snapshot logic."""
+    import copy
+    import types
+
+    from rlcf_b200.clip.custom_clip import CLIPCLS_TTA
+
+    class Visual(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ln_pre = torch.nn.LayerNorm(8)
+            self.fc = torch.nn.Linear(8, 8)
+
+    m = object.__new__(CLIPCLS_TTA)
+    torch.nn.Module.__init__(m)
+    torch.manual_seed(0)
+    m.clip_model = types.SimpleNamespace(visual=Visual())
+    m.only_norm, m.momentum_update = only_norm, momentum_update
+    m.update_freq, m.update_w, m.momentum, m.update_counter = update_freq, update_w, momentum, 0
+    sd = m.clip_model.visual.state_dict()
+    m.clip_state_dict, m.initial_state_dict = copy.deepcopy(sd), copy.deepcopy(sd)
+    m.momentum_state_dict = copy.deepcopy(sd)
+    return m
+
+
+def test_reset_restores_what_the_mode_can_change():
+    """reset() (TPT/clip/custom_clip.py:456-458): whole tower in full-tuning mode, LayerNorm entries in LN mode."""
+    for only_norm in (False, True):
+        m = _stub_cls_tta(only_norm, False)
+        vis = m.clip_model.visual
+        w0, g0 = vis.fc.weight.detach().clone(), vis.ln_pre.weight.detach().clone()
+        with torch.no_grad():
+            vis.ln_pre.weight.add_(1.0)
+            if not only_norm:
+                vis.fc.weight.add_(1.0)
+        m.reset()
+        assert torch.equal(vis.ln_pre.weight, g0) and torch.equal(vis.fc.weight, w0)
+        assert len(list(m.parameters())) == (2 if only_norm else 4)
+
+
+def test_momentum_update_model_follows_the_reference_formula():
+    """custom_clip.py:460-475: EMA after every sample; every update_freq samples the reset state becomes
+    (1 - update_w) * pretrained + update_w * EMA."""
+    m = _stub_cls_tta(False, True, update_freq=2, update_w=0.5, momentum=0.9)
+    vis = m.clip_model.visual
+    w_pre = vis.fc.weight.detach().clone()
+    ema = w_pre.clone()
+    for step in range(1, 4):
+        with torch.no_grad():
+            vis.fc.weight.add_(0.1 * step)                 # "adapted" weights of this sample
+        ema = 0.9 * ema + (1.0 - 0.9) * vis.fc.weight.detach()
+        m.momentum_update_model()
+        assert torch.allclose(m.momentum_state_dict["fc.weight"], ema, atol=0, rtol=0)
+        if step == 2:                                      # counter reached update_freq
+            assert m.update_counter == 0
+            assert torch.equal(m.initial_state_dict["fc.weight"], (1 - 0.5) * w_pre + 0.5 * ema)
+            init2 = m.initial_state_dict["fc.weight"].clone()
+        elif step == 1:
+            assert torch.equal(m.initial_state_dict["fc.weight"], w_pre)
+        m.reset()                                          # next sample starts from the (possibly moved) reset state
+        assert torch.equal(vis.fc.weight, m.initial_state_dict["fc.weight"])
+    assert torch.equal(m.initial_state_dict["fc.weight"], init2) and m.update_counter == 1
+    off = _stub_cls_tta(False, False)
+    off.momentum_update_model()
+    assert off.update_counter == 0
