@@ -2,7 +2,7 @@
 """bench.py -- adapted images/sec of the RLCF test-time-adaptation hot path (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # the UNMODIFIED reference (baseline/_ref) on the host CPU
 
 Workload (BASELINE.json configs[1]): policy ViT-B/16, reward ViT-L/14, 64 views per image,
 rho = 0.1 -> 6 selected views, K = 3 sampled classes, C = 200 classes, 1 TTA step, LayerNorm-only tuning,
@@ -51,10 +51,41 @@ def parse_args():
     ap.add_argument("--queries-per-step", type=int, default=32, help="retrieval modes: queries adapted per launch sequence")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded CPU-baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
-    ap.add_argument("--torch-gpu-baseline", action="store_true",
-                    help="also time the reference algorithm in plain PyTorch on the GPU (fp16 autocast + GradScaler, "
-                         "one image at a time, 64-view backward) -- the denominator of north_star's 10x target")
+    ap.add_argument("--no-torch-gpu-baseline", action="store_true",
+                    help="skip the leg that times the UNMODIFIED reference (baseline/_ref: CLIPCLS_TTA + "
+                         "test_time_tuning, fp16 autocast + GradScaler, nn.MultiheadAttention, one image at a time) on "
+                         "the same GPU -- the denominator of north_star's 10x target")
+    ap.add_argument("--no-other-modes", action="store_true",
+                    help="skip the short informational runs of the other modes (prompt, full, config 3, config 5)")
     return ap.parse_args()
+
+
+def workload_of(args) -> dict:
+    wl = dict(WORKLOAD)
+    if args.config == 3:
+        wl["tta_steps"] = 3
+    elif args.config == 5:
+        wl["policy"] = "ViT-L/14"
+    return wl
+
+
+MODE_TEXT = {"ln": "LN-only", "prompt": "prompt tuning (ctx 4x512)", "full": "full image-encoder tuning"}
+MODE_LONG = {"ln": WORKLOAD["mode"], "prompt": "prompt tuning (tpt_cls_rl.py, ctx_init a_photo_of_a)",
+             "full": "full image-encoder tuning (--tune_norm 0, lr 1e-5)"}
+
+
+def make_config(wl: dict, mode: str, config: int, images_per_step: int, world: int) -> dict:
+    """The `config` object of the JSON line.  Both arms (--impl b200 / reference) build it here, so the two dicts are
+    identical except for `images_per_step` (the CUDA path adapts a batch of independent images per launch sequence,
+    the reference one image per call)."""
+    return {"workload": "%s RLCF cls, %d views, %d step%s, reward %s (config %d), %s" % (
+                wl["policy"], wl["n_views"], wl["tta_steps"], "" if wl["tta_steps"] == 1 else "s", wl["reward"], config,
+                MODE_TEXT[mode]),
+            **{k: v for k, v in wl.items() if k != "mode"}, "mode": MODE_LONG[mode],
+            "images_per_step": images_per_step,
+            "parallelism": f"dp{world} (independent images, no data-path collective)",
+            "l2": "inputs larger than L2: every step reads a different batch of 64-view images (38.5 MB per image) "
+                  "than the step before"}
 
 
 def peaks():
@@ -183,97 +214,303 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def run_reference(args):
-    """The reference algorithm (CPU, fp32, all host threads) through the oracle port: one image per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    from oracle import rlcf_oracle as O
-    K = args.steps if args.steps is not None else 2
-    W = args.warmup if args.warmup is not None else 1
+def _ref_harness():
+    """baseline/ref_harness.py when the verbatim reference copy (baseline/_ref/TPT, made by baseline/make_ref.py in the
+    build container; git-ignored, travels with the gpurun snapshot) is present, else None."""
+    try:
+        from baseline import ref_harness as H
+    except Exception:
+        return None
+    return H if H.available() else None
+
+
+def reference_cpu_images_per_s(wl, n_timed: int, n_warm: int):
+    """(images/s, kind, cores, note): the reference's own per-image loop on all host cores, fp32.  kind "reference" =
+    the unmodified reference code (tune_cls_rl.test_time_adapt_eval -> tpt_cls_rl.test_time_tuning -> CLIPCLS_TTA /
+    CLIPRewards); kind "port" = the oracle restatement, used only when baseline/_ref is absent."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    wl = WORKLOAD
-    sd_p = O.make_clip_state_dict(wl["policy"], 0)
-    sd_r = O.make_clip_state_dict(wl["reward"], 1)
+    H = _ref_harness()
+    from rlcf_b200 import synthetic as S
+    views = S.make_views(2, wl["n_views"], 224, 11)
+    if H is not None:
+        run = H.ReferenceRun("cpu", wl, S.make_state_dict)
+        try:
+            if n_warm:
+                run.run(views, n_warm)
+            dt = run.run(views, n_timed)
+        finally:
+            run.close()
+        return n_timed / dt, "reference", cores, "unmodified reference code from baseline/_ref/TPT"
+    from oracle import rlcf_oracle as O
+    sd_p, sd_r = O.make_clip_state_dict(wl["policy"], 0), O.make_clip_state_dict(wl["reward"], 1)
     cf = O.class_features(sd_p, O.make_tokens(wl["n_classes"], 49408))
     rc = O.class_features(sd_r, O.make_tokens(wl["n_classes"], 49408))
     cfg = O.OracleConfig(n_views=wl["n_views"], selection_p=wl["selection_p"], tta_steps=wl["tta_steps"],
                          sample_k=wl["sample_k"], lr=wl["lr"])
-    views = O.make_views(1, wl["n_views"], 224, 11)
-    for _ in range(W):
-        O.adapt_one_image(sd_p, cf, views, cfg, sd_r, rc)
+    V = wl["n_views"]
+    for i in range(n_warm):
+        O.adapt_one_image(sd_p, cf, views[(i % 2) * V:(i % 2 + 1) * V], cfg, sd_r, rc)
     t0 = time.perf_counter()
-    for _ in range(K):
-        O.adapt_one_image(sd_p, cf, views, cfg, sd_r, rc)
+    for i in range(n_timed):
+        O.adapt_one_image(sd_p, cf, views[(i % 2) * V:(i % 2 + 1) * V], cfg, sd_r, rc)
     dt = time.perf_counter() - t0
-    value = K / dt
-    sample = f"{K} images x full config-2 sizes (64 views, B/16 policy + L/14 reward), one image per step"
+    return n_timed / dt, "port", cores, "oracle port (baseline/_ref absent)"
+
+
+def run_reference(args):
+    """The reference on the host CPU (fp32, all host threads), one image per step, through its own per-image loop."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    K = args.steps if args.steps is not None else 2
+    W = args.warmup if args.warmup is not None else 1
+    wl = workload_of(args)
+    value, kind, cores, note = reference_cpu_images_per_s(wl, K, W)
+    sample = (f"{K} images x full config-{args.config} sizes ({wl['n_views']} views, {wl['policy']} policy + "
+              f"{wl['reward']} reward), one image per step, {W} warm-up image(s); {note}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
-        "warmup": W, "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": W, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ViT-B/16 RLCF cls, 64 views, 1 step, reward ViT-L/14 (config 2), LN-only", **wl,
-                   "images_per_step": 1},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": make_config(wl, args.mode if args.mode in MODE_TEXT else "ln", args.config, 1, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_leg():
-    """Bounded CPU baseline on rank 0: the oracle port on two full-size images (about 15 s of host work on 16 cores)."""
-    from oracle import rlcf_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    wl = WORKLOAD
-    sd_p = O.make_clip_state_dict(wl["policy"], 0)
-    sd_r = O.make_clip_state_dict(wl["reward"], 1)
-    cf = O.class_features(sd_p, O.make_tokens(wl["n_classes"], 49408))
-    rc = O.class_features(sd_r, O.make_tokens(wl["n_classes"], 49408))
-    cfg = O.OracleConfig(n_views=wl["n_views"], selection_p=wl["selection_p"], tta_steps=wl["tta_steps"],
-                         sample_k=wl["sample_k"], lr=wl["lr"])
-    n_img, V = 2, wl["n_views"]
-    views = O.make_views(n_img, V, 224, 11)
-    t0 = time.perf_counter()
-    for i in range(n_img):
-        O.adapt_one_image(sd_p, cf, views[i * V:(i + 1) * V], cfg, sd_r, rc)
-    dt = time.perf_counter() - t0
-    return {"value": n_img / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n_img} images at full config-2 sizes (64 views, 6 selected, B/16 policy + L/14 reward), no warm-up"}
+def cpu_baseline_leg(wl):
+    """Bounded CPU baseline on rank 0: two full-size images through the reference's own loop (10-15 s of host work)."""
+    value, kind, cores, note = reference_cpu_images_per_s(wl, 2, 0)
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"2 images at full sizes ({wl['n_views']} views, {wl['policy']} policy + {wl['reward']} reward), "
+                      f"no warm-up; {note}"}
 
 
-def torch_gpu_baseline_leg(dev, n_images=10):
-    """The reference algorithm as the reference runs it on a GPU: eager PyTorch, torch.cuda.amp.autocast fp16 +
-    GradScaler(1000), one image per iteration, backward through all 64 views (TPT/tune_cls_rl.py:87,192-222) --
-    via the oracle port moved to the device.  Reported baseline only; none of this repo's kernels are involved."""
-    from oracle import rlcf_oracle as O
-    wl = WORKLOAD
-    sd_p = O.make_clip_state_dict(wl["policy"], 0)
-    sd_r = O.make_clip_state_dict(wl["reward"], 1)
-    cf = O.class_features(sd_p, O.make_tokens(wl["n_classes"], 49408)).to(dev)
-    rc = O.class_features(sd_r, O.make_tokens(wl["n_classes"], 49408)).to(dev)
-    sd_p = {k: v.to(dev) for k, v in sd_p.items() if k.startswith("visual.") or k == "logit_scale"}
-    sd_r = {k: v.to(dev) for k, v in sd_r.items() if k.startswith("visual.") or k == "logit_scale"}
-    cfg = O.OracleConfig(n_views=wl["n_views"], selection_p=wl["selection_p"], tta_steps=wl["tta_steps"],
-                         sample_k=wl["sample_k"], lr=wl["lr"])
-    views = O.make_views(2, wl["n_views"], 224, 11).to(dev)
-    scaler = torch.amp.GradScaler("cuda", init_scale=1000)
-    V = wl["n_views"]
-    for i in range(3):
-        O.adapt_one_image(sd_p, cf, views[(i % 2) * V:(i % 2 + 1) * V], cfg, sd_r, rc, amp=True, scaler=scaler)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(n_images):
-        O.adapt_one_image(sd_p, cf, views[(i % 2) * V:(i % 2 + 1) * V], cfg, sd_r, rc, amp=True, scaler=scaler)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    return {"value": n_images / dt, "unit": UNIT, "kind": "oracle port on cuda, eager PyTorch, fp16 autocast + GradScaler",
-            "sample": f"{n_images} images, one per iteration, after 3 warm-up images"}
+def torch_gpu_baseline_leg(dev, wl, n_images=20, n_warm=3):
+    """North_star's 10x denominator: the UNMODIFIED reference on the same GPU, as it runs there -- eager PyTorch,
+    torch.cuda.amp.autocast fp16 + GradScaler(1000), nn.MultiheadAttention, one image per iteration, backward through
+    all 64 views (TPT/tune_cls_rl.py:87,183-256, tpt_cls_rl.py:47-79).  None of this repo's kernels is involved."""
+    H = _ref_harness()
+    if H is None:
+        return {"unavailable": "baseline/_ref/TPT missing (run python baseline/make_ref.py in the build container)"}
+    from rlcf_b200 import synthetic as S
+    run = H.ReferenceRun(str(dev), wl, S.make_state_dict)
+    try:
+        views = S.make_views(2, wl["n_views"], 224, 11)
+        run.run(views, n_warm)
+        dt = run.run(views, n_images)
+    finally:
+        run.close()
+    return {"value": n_images / dt, "unit": UNIT, "kind": "reference",
+            "what": "unmodified reference (baseline/_ref/TPT: tune_cls_rl.test_time_adapt_eval, CLIPCLS_TTA, CLIPRewards, "
+                    "tpt_cls_rl.test_time_tuning) on cuda, eager PyTorch, fp16 autocast + GradScaler(1000)",
+            "sample": f"{n_images} images, one per iteration (H2D of the 64 views included, as in the reference loop), "
+                      f"after {n_warm} warm-up images"}
 
 
 # ------------------------------------------------------------------------------------------------ CUDA arm
+def build_engine(mode: str, wl: dict, B: int, dev, reward_seed: int = 1):
+    """Policy + reward towers with synthetic weights and the batched engine of the requested mode."""
+    from rlcf_b200 import engine as E, synthetic as S
+    sd_p = S.make_state_dict(wl["policy"], 0, dev)
+    sd_r = S.make_state_dict(wl["reward"], reward_seed, dev)
+    rew = E.prepare_visual(sd_r)
+    tok = S.make_tokens(wl["n_classes"], 49408)
+    rc = E.text_features(E.prepare_text(sd_r), tok)
+    logit_scale = float(sd_p["logit_scale"].exp())
+    cfg = E.RlcfConfig(n_views=wl["n_views"], selection_p=wl["selection_p"], tta_steps=wl["tta_steps"],
+                       sample_k=wl["sample_k"], lr=wl["lr"])
+    if mode == "prompt":
+        tok[:, 1:5] = torch.tensor([320, 1125, 539, 320])   # "a photo of a": the 4 context positions
+        ctx_init = sd_p["token_embedding.weight"][tok[0, 1:5].to(dev)]
+        return E.PromptEngine(E.prepare_visual(sd_p), E.prepare_text(sd_p, need_grad=True), tok, ctx_init, logit_scale,
+                              cfg, B, reward=rew, reward_class_feat=rc)
+    if mode == "full":
+        from rlcf_b200 import full_tune as FT
+        cf = E.text_features(E.prepare_text(sd_p), tok)
+        cfg.lr = 1e-5                                        # scripts/rlcf-tune.sh
+        return FT.FullTuneEngine(sd_p, cf, logit_scale, cfg, B, rew, rc)
+    pol = E.prepare_visual(sd_p, need_grad=True)
+    cf = E.text_features(E.prepare_text(sd_p), tok)
+    return E.RlcfEngine(pol, cf, logit_scale, cfg, B, reward=rew, reward_class_feat=rc)
+
+
+def measure(eng, wl, B, K, W, dev, rank, world, dist, use_graph=True, warm_seconds=2.0):
+    """Times K steps of the device-resident path (`value`) and K steps of the host-buffer path (`e2e`).  A step =
+    adapt B images (reset -> ... -> adapted prediction) + the top-1/top-5 counters of tools.accuracy, all of it this
+    library's kernels (no eager torch op inside either timed region)."""
+    from rlcf_b200 import _lib, ops, synthetic as S
+    V, C = wl["n_views"], wl["n_classes"]
+    # two different resident input batches, alternated: 2 x B x 38.5 MB (> 126 MB L2 for B >= 2)
+    batches = [S.make_views(B, V, 224, 1000 + 17 * rank + i, device=dev) for i in range(2)]
+    labels = [torch.randint(0, C, (B,), device=dev, dtype=torch.int64) for _ in range(2)]
+    hits = torch.zeros(3, device=dev, dtype=torch.int64)
+    in_bytes = batches[0].numel() * 4
+
+    l0 = _lib.launch_count()
+    if use_graph:
+        eng.capture(batches[0])
+        launches_per_step = (_lib.launch_count() - l0) // 3 + 1   # 2 eager warm-ups + 1 capture; + accuracy_count
+        adapt = eng.adapt_graph
+    else:
+        eng.adapt(batches[0])
+        launches_per_step = _lib.launch_count() - l0 + 1
+        adapt = eng.adapt
+
+    def step(i):
+        ops.accuracy_count(adapt(batches[i % 2]), labels[i % 2], hits)
+
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    # extra untimed warm-up until ~2 s of work have run, so that clocks / power state are in their steady regime
+    t_warm = time.perf_counter()
+    while time.perf_counter() - t_warm < warm_seconds:
+        step(0)
+        step(1)
+        torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`)
+    local = dev.index or 0
+    sampler = make_sampler(local)
+    hits.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    e0.record()
+    for i in range(K):
+        step(i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    counters = hits.clone()
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)   # the only collective: final accuracy counters
+    ms_total = float(ms.item())
+    value = world * B * K / (ms_total / 1e3)
+
+    # ---------------- end-to-end with host buffers (`e2e`): pinned H2D of every step's views and labels, D2H of the
+    # adapted logits and of the counters
+    host_in = [b.cpu().pin_memory() for b in batches]
+    host_lab = [l.cpu().pin_memory() for l in labels]
+    lab_dev = torch.empty_like(labels[0])
+    host_out = torch.empty(B, C, dtype=torch.float32).pin_memory()
+    host_hits = torch.zeros(3, dtype=torch.int64).pin_memory()
+    pipe = eng.host_pipeline() if (use_graph and hasattr(eng, "host_pipeline")) else None
+
+    def e2e_step(i):
+        if pipe is not None:
+            if i + 1 < K:
+                pipe.submit(host_in[(i + 1) % 2], (i + 1) % 2)
+            lab_dev.copy_(host_lab[i % 2], non_blocking=True)
+            pipe.run(i % 2, host_out)
+        else:
+            lab_dev.copy_(host_lab[i % 2], non_blocking=True)
+            host_out.copy_(eng.adapt(host_in[i % 2].to(dev, non_blocking=True)), non_blocking=True)
+        ops.accuracy_count(eng.logits_final, lab_dev, hits)
+        host_hits.copy_(hits, non_blocking=True)
+
+    if pipe is not None:
+        # warm the copy path and bring clocks / power back to their steady regime (pinning the host buffers above
+        # left the GPU idle for seconds; timing right after would measure a boost transient, not throughput)
+        t_warm = time.perf_counter()
+        while time.perf_counter() - t_warm < warm_seconds:
+            pipe.submit(host_in[0], 0)
+            pipe.submit(host_in[1], 1)
+            pipe.run(0, host_out)
+            pipe.run(1, host_out)
+            torch.cuda.synchronize()
+    barrier()
+    e0.record()
+    if pipe is not None:
+        # software pipeline: the H2D copy of step i+1 (side stream) overlaps the adaptation of step i;
+        # every step's views are copied from pinned host memory inside this timed region
+        pipe.submit(host_in[0], 0)
+    for i in range(K):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / (float(ms2.item()) / 1e3)
+    return dict(value=value, ms_total=ms_total, e2e_value=e2e_value, clocks=clocks, counters=counters,
+                launches_per_step=launches_per_step, in_bytes=in_bytes + B * 8, out_bytes=host_out.numel() * 4 + 24,
+                batches=batches)
+
+
+def gemm_roofline(eng, batch, ms_per_step, B, value, world, args):
+    """Roofline of the dominant kernel (the tcgen05 GEMM), every launch of one step timed live with CUDA events."""
+    from rlcf_b200 import ops
+    pk = peaks()
+    ops.GEMM_TIMER = []
+    eng.adapt(batch)
+    torch.cuda.synchronize()
+    recs, ops.GEMM_TIMER = ops.GEMM_TIMER, None
+    g_ms = sum(a.elapsed_time(b) for (_, _, _, a, b) in recs)
+    g_flops = sum(2.0 * m * n * k for (m, n, k, _, _) in recs)
+    achieved = g_flops / (g_ms / 1e3) / 1e12
+    flops_img = eng.algorithmic_flops_per_image()
+    step_tflops = flops_img * value / world / 1e12
+    traffic, traffic_src = None, None
+    for name in ("r2_gemm_traffic_b%d.json" % B, {16: "r1_gemm_traffic.json", 32: "r1_gemm_traffic_b32.json"}.get(B, "none")):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath) and args.mode == "ln" and args.config == 2:   # DRAM bytes per GEMM launch, committed ncu capture of this workload
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic, traffic_src = tj["dram_bytes_per_launch_avg"], tj["source"]
+            break
+    return {
+        "bound": "tensor", "kernel": "gemm_f16_kernel (tcgen05/TMA, all %d launches of one step)" % len(recs),
+        "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
+        "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": pk["source"] + " (sustained bf16 dense, of measured)",
+        "avg_launch_us": 1e3 * g_ms / len(recs), "gemm_share_of_step": g_ms / ms_per_step,
+        "flops_per_launch": g_flops / len(recs),
+        "whole_step": {"algorithmic_gflop_per_image": flops_img / 1e9, "achieved_tflops": step_tflops,
+                       "frac": step_tflops / pk["tflops_sustained"]},
+    }
+
+
+def other_modes_leg(dev, rank):
+    """Short informational runs of the other supported modes at the same shapes, so that the driver (not only the
+    builder) records them with clocks: prompt tuning, full image-encoder tuning, config 3 (3 TTA steps), config 5
+    (ViT-L/14 policy).  3 timed steps each after 3 warm-up steps + 1 s of steady-state warm-up."""
+    import gc
+    pk = peaks()
+    out = {}
+    for name, mode, config in (("prompt", "prompt", 2), ("full", "full", 2), ("config3_ln", "ln", 3),
+                               ("config5_ln", "ln", 5)):
+        try:
+            wl = workload_of(argparse.Namespace(config=config))
+            B = 8
+            eng = build_engine(mode, wl, B, dev, reward_seed=3 if config == 5 else 1)
+            m = measure(eng, wl, B, 3, 3, dev, rank, 1, None, warm_seconds=1.0)
+            fl = eng.algorithmic_flops_per_image()
+            out[name] = {"value": m["value"], "e2e": m["e2e_value"], "unit": UNIT, "images_per_step": B, "steps": 3,
+                         "ms_per_step": m["ms_total"] / 3, "algorithmic_gflop_per_image": fl / 1e9,
+                         "frac_of_sustained_tensor_peak": fl * m["value"] / 1e12 / pk["tflops_sustained"],
+                         "workload": make_config(wl, mode, config, B, 1)["workload"],
+                         "clocks": {k: m["clocks"].get(k) for k in ("sm_mhz", "reasons")}}
+            del eng, m
+        except Exception as e:   # informational leg: never take the headline line down with it
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        gc.collect()
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -286,184 +523,54 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    from rlcf_b200 import _lib, engine as E, ops, synthetic as S
+    from rlcf_b200 import _lib
 
     K = args.steps if args.steps is not None else 10
     W = max(3, args.warmup if args.warmup is not None else 3)
     B = args.images_per_step if args.images_per_step is not None else (32 if args.mode == "ln" else 8)
-    wl = dict(WORKLOAD)
-    if args.config == 3:
-        wl["tta_steps"] = 3
-    elif args.config == 5:
-        wl["policy"] = "ViT-L/14"
-    sd_p = S.make_state_dict(wl["policy"], 0, dev)
-    sd_r = S.make_state_dict(wl["reward"], 1 if args.config != 5 else 3, dev)
-    rew = E.prepare_visual(sd_r)
-    tok = S.make_tokens(wl["n_classes"], 49408)
-    rc = E.text_features(E.prepare_text(sd_r), tok)
-    logit_scale = float(sd_p["logit_scale"].exp())
-    cfg = E.RlcfConfig(n_views=wl["n_views"], selection_p=wl["selection_p"], tta_steps=wl["tta_steps"],
-                       sample_k=wl["sample_k"], lr=wl["lr"])
-    if args.mode == "prompt":
-        tok[:, 1:5] = torch.tensor([320, 1125, 539, 320])   # "a photo of a": the 4 context positions
-        ctx_init = sd_p["token_embedding.weight"][tok[0, 1:5].to(dev)]
-        eng = E.PromptEngine(E.prepare_visual(sd_p), E.prepare_text(sd_p, need_grad=True), tok, ctx_init, logit_scale,
-                             cfg, B, reward=rew, reward_class_feat=rc)
-    elif args.mode == "full":
-        from rlcf_b200 import full_tune as FT
-        cf = E.text_features(E.prepare_text(sd_p), tok)
-        cfg.lr = 1e-5                                        # scripts/rlcf-tune.sh
-        eng = FT.FullTuneEngine(sd_p, cf, logit_scale, cfg, B, rew, rc)
-    else:
-        pol = E.prepare_visual(sd_p, need_grad=True)
-        cf = E.text_features(E.prepare_text(sd_p), tok)
-        eng = E.RlcfEngine(pol, cf, logit_scale, cfg, B, reward=rew, reward_class_feat=rc)
-    del sd_p, sd_r
-    V = wl["n_views"]
-    # two different resident input batches, alternated: 2 x B x 38.5 MB (> 126 MB L2 for B >= 2)
-    batches = [S.make_views(B, V, 224, 1000 + 17 * rank + i, device=dev) for i in range(2)]
-    labels = torch.randint(0, wl["n_classes"], (B,), device=dev)
-    in_bytes = batches[0].numel() * 4
-
-    l0 = _lib.launch_count()
-    if args.no_graph:
-        step = eng.adapt
-        eng.adapt(batches[0])
-        launches_per_step = _lib.launch_count() - l0
-    else:
-        eng.capture(batches[0])
-        launches_per_step = (_lib.launch_count() - l0) // 3   # 2 eager warm-ups + 1 capture
-        step = eng.adapt_graph
-    for i in range(W):
-        step(batches[i % 2])
-    torch.cuda.synchronize()
-    # extra untimed warm-up until ~2 s of work have run, so that clocks / power state are in their steady regime
-    t_warm = time.perf_counter()
-    while time.perf_counter() - t_warm < 2.0:
-        step(batches[0])
-        step(batches[1])
-        torch.cuda.synchronize()
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------- device-resident throughput (`value`)
-    sampler = make_sampler(local)
-    hits = torch.zeros(3, device=dev, dtype=torch.int64)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    sampler.start()
-    e0.record()
-    for i in range(K):
-        logits = step(batches[i % 2])
-        # accuracy counters as tools.accuracy (TPT/utils/tools.py:84-98): top-1 / top-5 hits, count
-        top5 = logits.topk(5, dim=1).indices
-        hits[0] += (top5[:, 0] == labels).sum()
-        hits[1] += (top5 == labels[:, None]).any(1).sum()
-        hits[2] += B
-    e1.record()
-    barrier()
-    clocks = sampler.stop()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(hits, op=dist.ReduceOp.SUM)   # the only collective: final accuracy counters
-    ms_total = float(ms.item())
-    value = world * B * K / (ms_total / 1e3)
-
-    # ---------------- end-to-end with host buffers (`e2e`): pinned H2D of every step's views + D2H of the logits
-    host_in = [b.cpu().pin_memory() for b in batches]
-    host_out = torch.empty(B, wl["n_classes"], dtype=torch.float32).pin_memory()
-    pipe = None if (args.no_graph or not hasattr(eng, "host_pipeline")) else eng.host_pipeline()
-    if pipe is not None:
-        # warm the copy path and bring clocks / power back to their steady regime (pinning the host buffers above
-        # left the GPU idle for seconds; timing right after would measure a boost transient, not throughput)
-        t_warm = time.perf_counter()
-        while time.perf_counter() - t_warm < 2.0:
-            pipe.submit(host_in[0], 0)
-            pipe.submit(host_in[1], 1)
-            pipe.run(0, host_out)
-            pipe.run(1, host_out)
-            torch.cuda.synchronize()
-    barrier()
-    e0.record()
-    if pipe is not None:
-        # software pipeline: the H2D copy of step i+1 (side stream) overlaps the adaptation of step i;
-        # every step's views are copied from pinned host memory inside this timed region
-        pipe.submit(host_in[0], 0)
-        for i in range(K):
-            if i + 1 < K:
-                pipe.submit(host_in[(i + 1) % 2], (i + 1) % 2)
-            pipe.run(i % 2, host_out)
-    else:
-        for i in range(K):
-            host_out.copy_(eng.adapt(host_in[i % 2].to(dev, non_blocking=True)), non_blocking=True)
-    e1.record()
-    barrier()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * K / (float(ms2.item()) / 1e3)
-
-    # ---------------- roofline of the dominant kernel (the tcgen05 GEMM), timed live per launch with CUDA events
-    pk = peaks()
-    ops.GEMM_TIMER = []
-    eng.adapt(batches[0])
-    torch.cuda.synchronize()
-    recs, ops.GEMM_TIMER = ops.GEMM_TIMER, None
-    g_ms = sum(a.elapsed_time(b) for (_, _, _, a, b) in recs)
-    g_flops = sum(2.0 * m * n * k for (m, n, k, _, _) in recs)
-    achieved = g_flops / (g_ms / 1e3) / 1e12
-    flops_img = eng.algorithmic_flops_per_image()
-    step_tflops = flops_img * value / world / 1e12
-    traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", {16: "r1_gemm_traffic.json", 32: "r1_gemm_traffic_b32.json"}.get(B, "none"))
-    if os.path.exists(tpath) and args.mode == "ln" and args.config == 2:   # DRAM bytes per GEMM launch from the committed ncu capture of this workload
-        with open(tpath) as f:
-            tj = json.load(f)
-        traffic, traffic_src = tj["dram_bytes_per_launch_avg"], tj["source"]
-    roofline = {
-        "bound": "tensor", "kernel": "gemm_f16_kernel (tcgen05/TMA, all %d launches of one step)" % len(recs),
-        "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
-        "traffic": traffic, "traffic_source": traffic_src,
-        "peak_source": pk["source"] + " (sustained bf16 dense, of measured)",
-        "avg_launch_us": 1e3 * g_ms / len(recs), "gemm_share_of_step": g_ms / (ms_total / K),
-        "flops_per_launch": g_flops / len(recs),
-        "whole_step": {"algorithmic_gflop_per_image": flops_img / 1e9, "achieved_tflops": step_tflops,
-                       "frac": step_tflops / pk["tflops_sustained"]},
-    }
+    wl = workload_of(args)
+    eng = build_engine(args.mode, wl, B, dev, reward_seed=1 if args.config != 5 else 3)
+    m = measure(eng, wl, B, K, W, dev, rank, world, dist, use_graph=not args.no_graph)
+    value, ms_total = m["value"], m["ms_total"]
+    roofline = gemm_roofline(eng, m["batches"][0], ms_total / K, B, value, world, args)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
+    hits = m["counters"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
-        "config": {"workload": "%s RLCF cls, 64 views, %d step(s), reward ViT-L/14 (config %d), " % (
-                        wl["policy"], wl["tta_steps"], args.config)
-                               + {"ln": "LN-only", "prompt": "prompt tuning (ctx 4x512)",
-                                  "full": "full image-encoder tuning"}[args.mode], **wl,
-                   "mode": {"ln": wl["mode"], "prompt": "prompt tuning (tpt_cls_rl.py, ctx_init a_photo_of_a)",
-                            "full": "full image-encoder tuning (--tune_norm 0, lr 1e-5)"}[args.mode],
-                   "images_per_step": B, "parallelism": f"dp{world} (independent images, no data-path collective)",
-                   "l2": "inputs larger than L2: two alternating resident batches of %.0f MB" % (in_bytes / 1e6),
-                   "cuda_graph": not args.no_graph, "gemm_cta_group": _lib.set_gemm_cta_group(0)},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": host_out.numel() * 4},
-        "gpu_launches": int(launches_per_step * K),
+        "config": make_config(wl, args.mode, args.config, B, world),
+        "impl_details": {"cuda_graph": not args.no_graph, "gemm_cta_group": _lib.set_gemm_cta_group(0),
+                         "resident_input_bytes": 2 * (m["in_bytes"] - B * 8)},
+        "clocks": m["clocks"],
+        "e2e": {"value": m["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": m["in_bytes"],
+                "d2h_bytes_per_step": m["out_bytes"]},
+        "gpu_launches": int(m["launches_per_step"] * K),
         "roofline": roofline,
         "accuracy_counters": {"top1_hits": int(hits[0]), "top5_hits": int(hits[1]), "count": int(hits[2]),
-                              "note": "random labels on synthetic data; summed over ranks with one NCCL all-reduce"},
+                              "note": "random labels on synthetic data; rlcf_accuracy_count on the device, summed "
+                                      "over ranks with one NCCL all-reduce"},
     }
-    if world == 1 and args.torch_gpu_baseline:
-        del eng
+    del eng, m
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_torch_gpu_baseline and args.mode == "ln":
+        try:
+            line["torch_gpu_baseline"] = torch_gpu_baseline_leg(dev, wl)
+            if "value" in line["torch_gpu_baseline"]:
+                line["torch_gpu_baseline"]["e2e_speedup_vs_it"] = line["e2e"]["value"] / line["torch_gpu_baseline"]["value"]
+        except Exception as e:
+            line["torch_gpu_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        gc.collect()
         torch.cuda.empty_cache()
-        line["torch_gpu_baseline"] = torch_gpu_baseline_leg(dev)
+    if world == 1 and not args.no_other_modes and args.mode == "ln" and args.config == 2:
+        line["other_modes"] = other_modes_leg(dev, rank)
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_leg()
+        line["cpu_baseline"] = cpu_baseline_leg(wl)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

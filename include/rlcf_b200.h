@@ -253,6 +253,11 @@ int rlcf_dfeat_partial(const float* dlogits, const float* gallery, int n_query, 
 int rlcf_rowdot(const float* a, const float* b, int n_rows, int C, float scale, float* out, int64_t out_stride,
                 void* stream);
 
+/* Top-1 / top-5 hit counters of `accuracy` (TPT/utils/tools.py:84-98) as tune_cls_rl.py:243-247 accumulates them:
+ * hits[0] += #rows whose target is the arg-max, hits[1] += #rows whose target is among the 5 largest logits,
+ * hits[2] += n (device int64 [3], accumulated with integer atomics; ties go to the lower class index). */
+int rlcf_accuracy_count(const float* logits, const int64_t* target, int n, int C, int64_t* hits, void* stream);
+
 /* ---- text->image retrieval: the text tower is tuned, including the caption's token-embedding rows, the positional
  * embedding and logit_scale (custom_models.py:144-152; tune_text, clip_ret_policy.py:106-137) ----
  * x[g*n + i] = a[g*a_stride + i] + b[g*b_stride + i]: per-query token rows + positional embedding (CLIP.encode_text,

@@ -47,11 +47,35 @@ CASES = {
     "tiny_rlcf_multi_reward_mean": dict(policy="tiny-A", reward=["tiny-B", "tiny-A", "tiny-B"], reward_seeds=[1, 5, 6],
                                         confidences=[5, 1, 3], weighted_scores=0, V=16, rho=0.25, K=3, C=10, steps=1,
                                         lr=5e-3, n_img=1),
+    # round 2: full config-2 sizes with two DIFFERENT images (adapted in one launch sequence by the
+    # CUDA path), config 3 (three steps: steps >= 1 reuse selected_idx, tpt_cls_rl.py:52-58) at ViT-B/16 + ViT-L/14
+    "b16_l14_cfg2_2img": dict(policy="ViT-B/16", reward="ViT-L/14", V=64, rho=0.1, K=3, C=200, steps=1, lr=5e-3,
+                              n_img=2, view_seed=12),
+    "b16_l14_cfg3_3step": dict(policy="ViT-B/16", reward="ViT-L/14", V=64, rho=0.1, K=3, C=200, steps=3, lr=5e-3,
+                               n_img=1, view_seed=13),
+    # full image-encoder tuning (only_norm=False, custom_clip.py:477-479; scripts/rlcf-tune.sh: 3 steps, lr 1e-5)
+    "tiny_full_tune_2step": dict(policy="tiny-A", reward="tiny-B", V=16, rho=0.25, K=3, C=10, steps=2, lr=1e-4,
+                                 n_img=2, only_norm=False, view_seed=14),
+    "b32_full_tune_3step": dict(policy="ViT-B/32", reward="ViT-B/32", V=8, rho=0.5, K=3, C=32, steps=3, lr=1e-5,
+                                n_img=1, only_norm=False, reward_seed=3, view_seed=15, params="ln+bias"),
+}
+# top-1 agreement fixture: final logits of N images at config 2 from the reference, one seed per
+# image (views of image i = make_views(1, V, 224, view_seed + i)); only what the agreement test needs is stored
+AGREE_CASES = {
+    "agree_cfg2": dict(policy="ViT-B/16", reward="ViT-L/14", V=64, rho=0.1, K=3, C=200, steps=1, lr=5e-3, n_img=64,
+                       view_seed=1000, per_image_seeds=True, compact=True),
 }
 PROMPT_CASES = {
     # prompt tuning (TPT/tpt_cls_rl.py + ClipTestTimeTuning): real BPE tokenizer, ctx_init "a_photo_of_a" (4 tokens)
     "tiny_prompt_rlcf_2step": dict(policy="tiny-P", reward="tiny-Q", V=16, rho=0.25, K=3, C=12, steps=2, lr=5e-3,
                                    n_img=2, ctx_init="a_photo_of_a", loss="rlcf"),
+    # BASELINE.json configs[0] exactly: ViT-B/32, get_coop's model, TPT entropy loss of
+    # TPT/tpt_cls.py:49-78, 8 views, selection_p 0.5, 4 images, C = 32 synthetic class names "class i", lr 5e-3, 1 step
+    "b32_cfg1_exact": dict(policy="ViT-B/32", reward=None, V=8, rho=0.5, K=3, C=32, steps=1, lr=5e-3, n_img=4,
+                           ctx_init="a_photo_of_a", loss="tpt", classnames="class_i", policy_seed=2, view_seed=1),
+    # prompt-mode RLCF at the real text-tower size (width 512, 12 layers, 8 heads): VERDICT r1 item 6
+    "b32_prompt_rlcf": dict(policy="ViT-B/32", reward="ViT-B/32", V=8, rho=0.5, K=3, C=16, steps=1, lr=5e-3, n_img=2,
+                            ctx_init="a_photo_of_a", loss="rlcf", reward_seed=3, view_seed=16),
 }
 POLICY_SEED, REWARD_SEED, VIEW_SEED, TOKEN_SEED = 0, 1, 11, 7
 CLASSNAMES = ["tench", "goldfish", "great white shark", "tiger shark", "hammerhead", "electric ray", "stingray",
@@ -117,8 +141,9 @@ def run_case(name: str, cfg: dict, mods) -> dict:
         multiple_reward_models=0, reward_arch=cfg["reward"], reward_amplify=cfg.get("reward_amplify", 0),
         sample_k=cfg["K"], reward_process=cfg.get("reward_process", 1), process_batch=cfg.get("process_batch", 0))
     classnames = [f"class {i}" for i in range(cfg["C"])]
+    only_norm = cfg.get("only_norm", True)
     model = custom_clip.CLIPCLS_TTA("cpu", classnames, arch=cfg["policy"], prompt_prefix="a photo of a",
-                                    only_norm=True)
+                                    only_norm=only_norm)
     optimizer = torch.optim.AdamW(model.parameters(), cfg["lr"], weight_decay=5e-4)   # tune_cls_rl.py:79-81
     optim_state = copy.deepcopy(optimizer.state_dict())
     if multi:   # get_reward_model's multiple_reward_models branch (clip_reward.py:30-35) with this case's members
@@ -154,14 +179,17 @@ def run_case(name: str, cfg: dict, mods) -> dict:
     tpt_cls_rl.select_confident_samples = select
     reward_model.CLIPScore, reward_model.rewards_post_process = score, post
 
-    views = O.make_views(cfg["n_img"], cfg["V"], res, VIEW_SEED)
+    view_seed = cfg.get("view_seed", VIEW_SEED)
+    per_image = cfg.get("per_image_seeds", False)
+    views = None if per_image else O.make_views(cfg["n_img"], cfg["V"], res, view_seed)
     names = O.ln_param_names(sds[cfg["policy"]])
     named = dict(model.clip_model.named_parameters())
     out = {}
     try:
         for i in range(cfg["n_img"]):
             rec.clear()
-            images = views[i * cfg["V"]:(i + 1) * cfg["V"]]
+            images = (O.make_views(1, cfg["V"], res, view_seed + i) if per_image
+                      else views[i * cfg["V"]:(i + 1) * cfg["V"]])
             model.reset()                                                              # tune_cls_rl.py:210
             optimizer.load_state_dict(optim_state)                                     # tune_cls_rl.py:213
             model.train()
@@ -170,6 +198,16 @@ def run_case(name: str, cfg: dict, mods) -> dict:
             with torch.no_grad():
                 final = model(images[:1])                                              # tune_cls_rl.py:220-222
             S, K = int(cfg["V"] * cfg["rho"]), cfg["K"]
+            if cfg.get("compact"):
+                # agreement fixture: clean-view logits before / after adaptation, the discrete decisions, the entropies
+                out[f"img{i}.logits_view0"] = rec["logits_all"][:1].numpy()
+                lg = rec["logits_all"]
+                out[f"img{i}.entropy"] = (-(lg.softmax(1) * lg.log_softmax(1)).sum(1)).numpy()
+                out[f"img{i}.selected_idx"] = rec["selected_idx"].numpy()
+                out[f"img{i}.topk_idx"] = torch.stack([t.reshape(S, K) for t in rec["topk_idx"]]).numpy()
+                out[f"img{i}.logits_final"] = final.numpy()
+                print(f"  {name}: image {i} done", flush=True)
+                continue
             out[f"img{i}.logits_all"] = rec["logits_all"].numpy()
             out[f"img{i}.selected_idx"] = rec["selected_idx"].numpy()
             out[f"img{i}.topk_idx"] = torch.stack([t.reshape(S, K) for t in rec["topk_idx"]]).numpy()
@@ -177,6 +215,12 @@ def run_case(name: str, cfg: dict, mods) -> dict:
             out[f"img{i}.rewards"] = torch.stack([t.reshape(S, K) for t in rec["rewards"]]).numpy()
             out[f"img{i}.logits_final"] = final.numpy()
             out[f"img{i}.params"] = torch.cat([named[n].detach().flatten() for n in names]).numpy()
+            if not only_norm:
+                # every trainable tensor (visual.*), or -- for towers too big to commit -- the 1-D tensors only
+                for n, prm in model.clip_model.visual.named_parameters():
+                    if cfg.get("params") == "ln+bias" and prm.dim() > 1:
+                        continue
+                    out[f"img{i}.param.visual.{n}"] = prm.detach().numpy().copy()
     finally:
         tpt_cls_rl.select_confident_samples = orig_select
     out["class_feat"] = model.class_features.numpy()
@@ -194,8 +238,9 @@ def run_prompt_case(name: str, cfg: dict, mods) -> dict:
     """tpt_cls_rl.py:82-279 with get_coop's model class (ClipTestTimeTuning) on one synthetic 'dataset'."""
     custom_clip, clip_model, clip_reward, tpt_cls_rl = mods
     import clip.clip as ref_clip
-    sd_p = O.make_clip_state_dict(cfg["policy"], POLICY_SEED)
-    sd_r = O.make_clip_state_dict(cfg["reward"], cfg.get("reward_seed", REWARD_SEED))
+    tpt = cfg.get("loss") == "tpt"
+    sd_p = O.make_clip_state_dict(cfg["policy"], cfg.get("policy_seed", POLICY_SEED))
+    sd_r = None if tpt else O.make_clip_state_dict(cfg["reward"], cfg.get("reward_seed", REWARD_SEED))
 
     def fake_load(sd):
         def load(arch, device="cpu", jit=False, download_root=None):
@@ -205,12 +250,14 @@ def run_prompt_case(name: str, cfg: dict, mods) -> dict:
 
     custom_clip.load = fake_load(sd_p)
     custom_clip.tokenize = ref_clip.tokenize            # the reference's real BPE tokenizer
-    clip_reward.clip.load = fake_load(sd_r)
+    if not tpt:
+        clip_reward.clip.load = fake_load(sd_r)
     args = argparse.Namespace(
         tta_steps=cfg["steps"], selection_p=cfg["rho"], min_entropy_reg=False, min_entropy_w=0.0,
         multiple_reward_models=0, reward_arch=cfg["reward"], reward_amplify=0, sample_k=cfg["K"], reward_process=1,
-        process_batch=0)
-    classnames = CLASSNAMES[:cfg["C"]]
+        process_batch=0, cocoop=False)
+    classnames = ([f"class {i}" for i in range(cfg["C"])] if cfg.get("classnames") == "class_i"
+                  else CLASSNAMES[:cfg["C"]])
     model = custom_clip.ClipTestTimeTuning("cpu", classnames, None, arch=cfg["policy"], n_ctx=4,
                                            ctx_init=cfg["ctx_init"])
     for n, prm in model.named_parameters():                                          # tpt_cls_rl.py:103-105
@@ -218,9 +265,11 @@ def run_prompt_case(name: str, cfg: dict, mods) -> dict:
             prm.requires_grad_(False)
     optimizer = torch.optim.AdamW(model.prompt_learner.parameters(), cfg["lr"], weight_decay=5e-4)
     optim_state = copy.deepcopy(optimizer.state_dict())
+    scaler = torch.cuda.amp.GradScaler(init_scale=1000)
+    if tpt:
+        return run_tpt_prompt_loop(name, cfg, model, optimizer, optim_state, scaler, args)
     reward_model = clip_reward.get_reward_model("cpu", args)
     reward_model.set_class_features(tokenized_classes=model.prompt_learner.tokenized_prompts)   # tpt_cls_rl.py:189-191
-    scaler = torch.cuda.amp.GradScaler(init_scale=1000)
     rec = {}
     orig_select = tpt_cls_rl.select_confident_samples
 
@@ -242,7 +291,7 @@ def run_prompt_case(name: str, cfg: dict, mods) -> dict:
 
     tpt_cls_rl.select_confident_samples = select
     reward_model.CLIPScore, reward_model.rewards_post_process = score, post
-    views = O.make_views(cfg["n_img"], cfg["V"], O.ARCHS[cfg["policy"]][1], VIEW_SEED)
+    views = O.make_views(cfg["n_img"], cfg["V"], O.ARCHS[cfg["policy"]][1], cfg.get("view_seed", VIEW_SEED))
     out = {}
     S, K = int(cfg["V"] * cfg["rho"]), cfg["K"]
     try:
@@ -271,17 +320,55 @@ def run_prompt_case(name: str, cfg: dict, mods) -> dict:
     return out
 
 
+def run_tpt_prompt_loop(name, cfg, model, optimizer, optim_state, scaler, args) -> dict:
+    """The per-image loop of TPT/tpt_cls.py:219-262 with ITS test_time_tuning (tpt_cls.py:49-78: marginal-entropy
+    loss, no reward model) -- BASELINE.json configs[0]."""
+    import tpt_cls
+    rec = {}
+    orig_select = tpt_cls.select_confident_samples
+
+    def select(logits, top):
+        out, idx = orig_select(logits, top)
+        rec["logits_all"], rec["selected_idx"] = logits.detach().clone(), idx.clone()
+        return out, idx
+
+    tpt_cls.select_confident_samples = select
+    views = O.make_views(cfg["n_img"], cfg["V"], O.ARCHS[cfg["policy"]][1], cfg.get("view_seed", VIEW_SEED))
+    out = {}
+    try:
+        model.eval()
+        for i in range(cfg["n_img"]):
+            rec.clear()
+            images = views[i * cfg["V"]:(i + 1) * cfg["V"]]
+            with torch.no_grad():
+                model.reset()                                                        # tpt_cls.py:233-235
+            optimizer.load_state_dict(optim_state)
+            tpt_cls.test_time_tuning(model, images, optimizer, scaler, args)
+            with torch.no_grad():
+                final = model(images[:1])
+            out[f"img{i}.logits_all"] = rec["logits_all"].numpy()
+            out[f"img{i}.selected_idx"] = rec["selected_idx"].numpy()
+            out[f"img{i}.logits_final"] = final.numpy()
+            out[f"img{i}.params"] = model.prompt_learner.ctx.detach().flatten().numpy().copy()
+    finally:
+        tpt_cls.select_confident_samples = orig_select
+    out["tokens"] = model.prompt_learner.tokenized_prompts.numpy()
+    out["ctx_init"] = model.prompt_learner.ctx_init_state.numpy()
+    out["meta"] = np.array(repr(cfg))
+    return out
+
+
 def main():
-    which = sys.argv[1:] or (list(CASES) + list(PROMPT_CASES))
+    which = sys.argv[1:] or (list(CASES) + list(PROMPT_CASES) + list(AGREE_CASES))
     torch.manual_seed(0)
     mods = import_reference()
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     for name in which:
         out = run_prompt_case(name, PROMPT_CASES[name], mods) if name in PROMPT_CASES else \
-            run_case(name, CASES[name], mods)
+            run_case(name, {**CASES, **AGREE_CASES}[name], mods)
         path = os.path.join(ROOT, "tests", "golden", name + ".npz")
         np.savez_compressed(path, **out)
-        print(name, "->", path, {k: v.shape for k, v in out.items() if k.startswith("img0")})
+        print(name, "->", path, f"({len(out)} arrays, {os.path.getsize(path) / 1e6:.2f} MB)")
 
 
 if __name__ == "__main__":

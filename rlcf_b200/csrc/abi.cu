@@ -130,6 +130,7 @@ int augmix_views(const uint8_t*, int, const int*, const float*, const float*, co
 int add_rows(const float*, long long, const float*, long long, int, long long, float*, cudaStream_t);
 int scale_rows_exp(const float*, const float*, long long, int, int, float*, cudaStream_t);
 int tied_rows_grad(const float*, const long long*, int, int, int, float*, float*, long long, cudaStream_t);
+int accuracy_count(const float*, const long long*, int, int, long long*, cudaStream_t);
 
 }  // namespace rlcf
 
@@ -409,6 +410,12 @@ int rlcf_rowdot(const float* a, const float* b, int n_rows, int C, float scale, 
                 void* stream) {
   if (!a || !b || !out) return set_error(RLCF_ERR_ARG, "rowdot: null pointer");
   return rowdot(a, b, n_rows, C, scale, out, out_stride, S(stream));
+}
+
+int rlcf_accuracy_count(const float* logits, const int64_t* target, int n, int C, int64_t* hits, void* stream) {
+  if (!logits || !target || !hits) return set_error(RLCF_ERR_ARG, "accuracy_count: null pointer");
+  return accuracy_count(logits, reinterpret_cast<const long long*>(target), n, C, reinterpret_cast<long long*>(hits),
+                        S(stream));
 }
 
 int rlcf_add_rows(const float* a, int64_t a_stride, const float* b, int64_t b_stride, int n_sets, int64_t n, float* x,

@@ -380,6 +380,15 @@ def rowdot(a, b, out, out_stride=1, scale=1.0):
     return out
 
 
+def accuracy_count(logits, target, hits):
+    """hits[0] += top-1 hits, hits[1] += top-5 hits, hits[2] += rows  (utils/tools.py:84-98; device int64 [3])."""
+    _chk(logits, torch.float32, "logits"); _chk(target, torch.int64, "target"); _chk(hits, torch.int64, "hits")
+    if logits.dim() != 2 or target.numel() != logits.shape[0] or hits.numel() != 3:
+        raise _lib.RlcfError("accuracy_count: logits [n, C], target [n], hits [3]")
+    call("rlcf_accuracy_count", ptr(logits), ptr(target), logits.shape[0], logits.shape[1], ptr(hits), stream())
+    return hits
+
+
 def add_rows(a, a_stride, b, b_stride, n_sets, n, x):
     """x[g, :n] = a[g*a_stride : +n] + b[g*b_stride : +n]  (a, b base pointers of strided per-query vectors)."""
     _chk(a, torch.float32, "a", strided=True); _chk(b, torch.float32, "b", strided=True); _chk(x, torch.float32, "x")
