@@ -24,3 +24,18 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    """Measured parity errors of the GPU tests (tests/parity_log.py), printed even with -q and saved as JSON."""
+    try:
+        import parity_log
+    except Exception:  # pragma: no cover
+        return
+    lines = parity_log.summary_lines()
+    if not lines:
+        return
+    path = parity_log.dump()
+    terminalreporter.write_sep("-", f"measured parity errors ({len(lines)} records -> {path})")
+    for ln in lines:
+        terminalreporter.write_line(ln)
