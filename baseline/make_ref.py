@@ -38,6 +38,10 @@ def make_ref(src: str = SRC, dst: str = DST) -> bool:
                 manifest[os.path.relpath(p, dst)] = hashlib.sha256(fh.read()).hexdigest()
     with open(os.path.join(os.path.dirname(dst), "MANIFEST.json"), "w") as fh:
         json.dump({"source": src, "files": manifest}, fh, indent=1, sort_keys=True)
+    # OpenAI's BPE merge table (a data file, like the checkpoints): placed next to rlcf_b200's tokenizer, git-ignored
+    vocab = os.path.join(src, "clip", "bpe_simple_vocab_16e6.txt.gz")
+    if os.path.isfile(vocab):
+        shutil.copyfile(vocab, os.path.join(os.path.dirname(HERE), "rlcf_b200", "clip", "bpe_simple_vocab_16e6.txt.gz"))
     return True
 
 

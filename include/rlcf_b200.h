@@ -134,6 +134,10 @@ int rlcf_reward_loss(const float* logits, const int32_t* row_idx, const float* r
 /* TPT loss (config 1): marginal entropy of the S selected views (tpt_cls_rl.py:38-44) and its gradient. */
 int rlcf_avg_entropy_loss(const float* logits, const int32_t* row_idx, int n_img, int S, int C, float loss_scale,
                           float* dlogits, float* loss, void* stream);
+/* --min_entropy_reg (tpt_cls_rl.py:73-74): loss += weight * avg_entropy(output).  ACCUMULATES weight * loss_scale *
+ * d avg_entropy / d logits into dlogits and weight * avg_entropy into loss (both already hold the RLCF term). */
+int rlcf_avg_entropy_reg(const float* logits, const int32_t* row_idx, int n_img, int S, int C, float loss_scale,
+                         float weight, float* dlogits, float* loss, void* stream);
 
 /* Backward of rlcf_head_fwd for the S selected views of each image (one block per view):
  * dlogits -> d feat -> d(LN out) -> ln_post backward.  Writes dx into dres rows (row_idx as in head_fwd) and

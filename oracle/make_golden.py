@@ -47,6 +47,9 @@ CASES = {
     "tiny_rlcf_multi_reward_mean": dict(policy="tiny-A", reward=["tiny-B", "tiny-A", "tiny-B"], reward_seeds=[1, 5, 6],
                                         confidences=[5, 1, 3], weighted_scores=0, V=16, rho=0.25, K=3, C=10, steps=1,
                                         lr=5e-3, n_img=1),
+    # --min_entropy_reg 1 --min_entropy_w 0.5 (tpt_cls_rl.py:73-74)
+    "tiny_rlcf_min_entropy": dict(policy="tiny-A", reward="tiny-B", V=16, rho=0.25, K=3, C=10, steps=2, lr=5e-3, n_img=2,
+                                  min_entropy_w=0.5, view_seed=17),
     # round 2: full config-2 sizes with two DIFFERENT images (adapted in one launch sequence by the
     # CUDA path), config 3 (three steps: steps >= 1 reuse selected_idx, tpt_cls_rl.py:52-58) at ViT-B/16 + ViT-L/14
     "b16_l14_cfg2_2img": dict(policy="ViT-B/16", reward="ViT-L/14", V=64, rho=0.1, K=3, C=200, steps=1, lr=5e-3,
@@ -137,7 +140,8 @@ def run_case(name: str, cfg: dict, mods) -> dict:
         clip_reward.clip.load = fake_load(sd_reward)
 
     args = argparse.Namespace(
-        tta_steps=cfg["steps"], selection_p=cfg["rho"], min_entropy_reg=False, min_entropy_w=0.0,
+        tta_steps=cfg["steps"], selection_p=cfg["rho"], min_entropy_reg=int("min_entropy_w" in cfg),
+        min_entropy_w=cfg.get("min_entropy_w", 0.0),
         multiple_reward_models=0, reward_arch=cfg["reward"], reward_amplify=cfg.get("reward_amplify", 0),
         sample_k=cfg["K"], reward_process=cfg.get("reward_process", 1), process_batch=cfg.get("process_batch", 0))
     classnames = [f"class {i}" for i in range(cfg["C"])]

@@ -271,6 +271,7 @@ class OracleConfig:
     loss: str = "rlcf"        # "rlcf" | "tpt"
     reward_weights: tuple = ()    # ensemble of reward models (sd_reward / reward_cls are then lists): per-model weights
     weighted_scores: bool = True  # CLIPRewardsMultiple(weighted_scores=...): weighted sum, else plain mean
+    min_entropy_w: float = 0.0    # --min_entropy_reg 1: loss += min_entropy_w * avg_entropy(output) (tpt_cls_rl.py:73-74)
 
 
 def ln_param_names(sd: dict) -> list:
@@ -327,6 +328,8 @@ def adapt_one_image(sd_policy: dict, class_feat: torch.Tensor, views: torch.Tens
             rep = torch.repeat_interleave(output, cfg.sample_k, dim=0)
             all_loss = F.cross_entropy(rep, flat, reduction="none")                          # tpt_cls_rl.py:70
             loss = torch.mean(rewards * all_loss)                                            # tpt_cls_rl.py:71
+            if cfg.min_entropy_w:
+                loss = loss + cfg.min_entropy_w * avg_entropy(output)                        # tpt_cls_rl.py:73-74
             out.setdefault("topk_idx", []).append(index)
             out.setdefault("scores", []).append(score.reshape(bs, -1))
             out.setdefault("rewards", []).append(rewards.reshape(bs, -1))

@@ -44,6 +44,7 @@ _PROTOS = {
     "rlcf_reward_loss_multi": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _i, _i,
                                _i, _i, _f, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp],
     "rlcf_avg_entropy_loss": [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp],
+    "rlcf_avg_entropy_reg": [_vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp],
     "rlcf_head_bwd": [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _i,
                       _i64, _i64, _vp],
     "rlcf_head_bwd_ex": [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _f, _vp, _vp, _i, _i, _i, _i,

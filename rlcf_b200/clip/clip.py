@@ -27,12 +27,14 @@ _MODELS = {  # file names of the OpenAI release (clip.py:30-40); only ViT towers
     "ViT-L/14@336px": "ViT-L-14-336px.pt",
 }
 _tokenizer = None
+_synthetic_loaded = False   # set by load("synthetic:..."): only then may tokenize() use the byte-level fallback
 
 
 def _get_tokenizer():
+    """The BPE tokenizer (RuntimeError when OpenAI's merge table is missing, unless only synthetic weights are in use)."""
     global _tokenizer
     if _tokenizer is None:
-        _tokenizer = _Tokenizer()
+        _tokenizer = _Tokenizer(allow_byte_fallback=_synthetic_loaded)
     return _tokenizer
 
 
@@ -53,6 +55,8 @@ def load(name: str, device: Union[str, torch.device] = "cuda" if torch.cuda.is_a
     if jit:
         warnings.warn("jit=True is not supported by rlcf_b200 (the forward runs on its own CUDA kernels); ignoring")
     if name.startswith("synthetic:"):
+        global _synthetic_loaded
+        _synthetic_loaded = True
         parts = name.split(":")
         arch, seed = parts[1], int(parts[2]) if len(parts) > 2 else 0
         if arch not in synthetic.ARCHS:

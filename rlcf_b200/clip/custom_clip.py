@@ -3,9 +3,13 @@
 CLIPCLS_TTA (custom_clip.py:364-497): CLIP classification with test-time adaptation of the image encoder.  Class
 text features are computed once with the policy's text tower; `forward(image) -> logits[N, C]` runs the image
 tower on the CUDA kernels; `reset()`, `reset_classnames_and_state()`, `parameters()`, `train()/eval()`,
-`momentum_update_model()` keep the reference semantics.  The LayerNorm-only mode (`only_norm=True`, the
-`--tune_norm 1` recipe) is the one `test_time_tuning` can adapt on the GPU; full-encoder tuning (wgrad GEMMs + an
-86 M-parameter AdamW) is listed as the next step in DESIGN.md and raises NotImplementedError at tuning time.
+`momentum_update_model()` keep the reference semantics.  `test_time_tuning` adapts either mode on the GPU:
+LayerNorm-only (`only_norm=True`, the `--tune_norm 1` recipe; engine.RlcfEngine) or the whole image encoder
+(`only_norm=False`, scripts/rlcf-tune.sh; full_tune.FullTuneEngine: wgrad GEMMs + an 86 M-parameter AdamW per image).
+
+Engines are cached per model.  A cache entry keeps strong references to every object its key identifies (towers,
+class-feature tensors), so an `id()` / `data_ptr()` in the key can never be recycled by a new object while the entry
+is alive.
 """
 from __future__ import annotations
 
@@ -178,13 +182,13 @@ class ClipTestTimeTuning(nn.Module):
         pl = self.prompt_learner
         key = (id(vis), id(txt), _ids(rew), n_img, tuple(sorted(vars(cfg).items())), pl.tokenized_prompts.data_ptr(),
                _ptrs(rcls))
-        eng = self._engines.get(key)
-        if eng is None:
+        hit = self._engines.get(key)
+        if hit is None:
             self._engines.clear()
             eng = E.PromptEngine(vis, txt, pl.tokenized_prompts, pl.ctx.detach(), float(self.logit_scale.exp()), cfg,
                                  n_img, reward=rew, reward_class_feat=rcls)
-            self._engines[key] = eng
-        return eng
+            hit = self._engines[key] = (eng, (vis, txt, rew, rcls, pl.tokenized_prompts))   # refs pin the keyed ids
+        return hit[0]
 
 
 def get_coop(clip_arch, test_set, device, n_ctx, ctx_init, learned_cls=False, classnames=None, tokenized_prompts=None):
@@ -239,10 +243,9 @@ class CLIPCLS_TTA(nn.Module):
 
     @torch.no_grad()
     def forward(self, image):
-        image_features = self.clip_model.encode_image(image)
-        image_features = image_features / image_features.norm(dim=-1, keepdim=True)
-        logit_scale = self.clip_model.logit_scale.exp()
-        return logit_scale * image_features @ self.class_features.t()
+        """logits [N, C] = exp(logit_scale) * normalise(encode_image(image)) @ class_features^T  (custom_clip.py:423-432);
+        ln_post, projection, normalisation and the cosine logits are one rlcf_head_fwd launch."""
+        return self.clip_model.visual.logits(image, self.class_features, float(self.clip_model.logit_scale.exp()))
 
     @torch.no_grad()
     def reset_classnames_and_state(self, classnames, arch, tokenized_prompts=None):
@@ -311,15 +314,20 @@ class CLIPCLS_TTA(nn.Module):
             raise RlcfError("full image-encoder tuning needs a reward model with class features set")
         vis = self.clip_model.visual
         rew, rcls, cfg.reward_weights = _reward_inputs(reward_model)
-        key = ("full", vis._frozen_key(), _ids(rew), n_img, tuple(sorted(vars(cfg).items())),
+        # keyed on WHICH tensors hold the weights, not on their versions: reset() / the copy-back of adapted weights
+        # bump every version without changing the reset state, and the engine checks the contents itself
+        storage = tuple(p.data_ptr() for p in vis.parameters())
+        key = ("full", storage, _ids(rew), n_img, tuple(sorted(vars(cfg).items())),
                self.class_features.data_ptr(), _ptrs(rcls))
-        eng = self._engines.get(key)
-        if eng is None:
+        hit = self._engines.get(key)
+        if hit is None:
             self._engines.clear()
             eng = FT.FullTuneEngine(vis.state_dict(), self.class_features, float(self.clip_model.logit_scale.exp()), cfg,
                                     n_img, rew, rcls, prefix="")
-            self._engines[key] = eng
-        return eng
+            hit = self._engines[key] = (eng, (vis, rew, rcls, self.class_features))
+        else:
+            hit[0].sync_initial_state(vis.state_dict(), prefix="")
+        return hit[0]
 
     # ------------------------------------------------------------------ bridge to the batched CUDA engine
     def engine(self, cfg: E.RlcfConfig, n_img: int, reward_model=None) -> E.RlcfEngine:
@@ -333,10 +341,10 @@ class CLIPCLS_TTA(nn.Module):
         if reward_model is not None:
             rew, rcls, cfg.reward_weights = _reward_inputs(reward_model)
         key = (id(pol), _ids(rew), n_img, tuple(sorted(vars(cfg).items())), self.class_features.data_ptr(), _ptrs(rcls))
-        eng = self._engines.get(key)
-        if eng is None:
+        hit = self._engines.get(key)
+        if hit is None:
             self._engines.clear()
             eng = E.RlcfEngine(pol, self.class_features, float(self.clip_model.logit_scale.exp()), cfg, n_img,
                                reward=rew, reward_class_feat=rcls)
-            self._engines[key] = eng
-        return eng
+            hit = self._engines[key] = (eng, (pol, rew, rcls, self.class_features))   # refs pin the keyed ids
+        return hit[0]

@@ -135,6 +135,21 @@ class VisionTransformer(_KernelBacked, nn.Module):
         run.head(xs, n, t.ln_flat, feat=feat, inv_norm=inv)
         return feat / inv[:, None]     # head_fwd returns f/|f| and 1/|f|
 
+    @torch.no_grad()
+    def logits(self, x: torch.Tensor, class_feat: torch.Tensor, logit_scale: float) -> torch.Tensor:
+        """[N,3,H,W] -> cosine logits [N, C] against L2-normalised class features: tower forward + one rlcf_head_fwd
+        launch (ln_post, projection, normalisation, logit_scale * f . class_feat) -- custom_clip.py:423-432."""
+        t = self.tower()
+        x = x.float().contiguous()
+        n = x.shape[0]
+        run = getattr(self, "_runner", None)
+        if run is None or run.w is not t or run.max_seq < n:
+            run = self._runner = E.TowerRunner(t, n)
+        xs = run.forward(n, t.ln_flat, images=x)
+        out = torch.empty(n, class_feat.shape[0], dtype=torch.float32, device=x.device)
+        run.head(xs, n, t.ln_flat, class_feat=class_feat.float().contiguous(), logit_scale=logit_scale, logits=out)
+        return out
+
 
 class _TextTower(_KernelBacked, nn.Module):
     """Owns nothing: a view over CLIP's text-side parameters so they can be prepared as one tower."""

@@ -1,10 +1,14 @@
 """Byte-pair-encoding tokenizer compatible with CLIP's `bpe_simple_vocab_16e6.txt.gz`
 (interface of TPT/clip/simple_tokenizer.py: `SimpleTokenizer().encode(text) -> List[int]`, `.decode`, `.encoder`).
 
-The merge table is OpenAI's data file, not code, and is not redistributed here (like the checkpoints).  It is looked
-up in: $RLCF_BPE_VOCAB, this directory, ~/.cache/clip/.  Without it the tokenizer falls back to a byte-level
-vocabulary (no merges): sequences are still well-formed (SOT ... EOT, ids < 49408) so that synthetic-weight runs
-work offline, but they do not match OpenAI's ids -- a warning says so once.
+The merge table is OpenAI's data file, not code, and is kept out of the git history (like the checkpoints).  It is
+looked up in: an explicit `bpe_path`, $RLCF_BPE_VOCAB, this directory (where `__graft_entry__.build()` /
+`baseline/make_ref.py` place the copy that ships next to the reference, TPT/clip/bpe_simple_vocab_16e6.txt.gz),
+~/.cache/clip/.  Without it the tokenizer REFUSES to work (RuntimeError): token ids that do not match OpenAI's would
+silently produce wrong class features with a real checkpoint.  The only exception is the explicit
+`allow_byte_fallback=True` (set by clip.load("synthetic:...") for offline synthetic-weight runs, or
+RLCF_BPE_FALLBACK=1): a byte-level vocabulary without merges whose sequences are still well-formed
+(SOT ... EOT, ids < 49408).
 """
 from __future__ import annotations
 
@@ -53,10 +57,16 @@ def _clean(text: str) -> str:
 
 
 class SimpleTokenizer:
-    def __init__(self, bpe_path: str | None = None):
+    def __init__(self, bpe_path: str | None = None, allow_byte_fallback: bool = False):
         self.byte_encoder = bytes_to_unicode()
         self.byte_decoder = {v: k for k, v in self.byte_encoder.items()}
         bpe_path = bpe_path or _find_vocab()
+        if bpe_path is None and not (allow_byte_fallback or os.environ.get("RLCF_BPE_FALLBACK") == "1"):
+            raise RuntimeError(
+                f"{VOCAB_NAME} not found: set RLCF_BPE_VOCAB, put the file next to {os.path.abspath(__file__)} or in "
+                "~/.cache/clip/ (`python baseline/make_ref.py` copies it from the reference).  Tokenising without "
+                "OpenAI's merge table would give token ids that no CLIP checkpoint understands.")
+        self.byte_fallback = bpe_path is None
         base = list(self.byte_encoder.values())
         vocab = base + [v + "</w>" for v in base]
         merges = []

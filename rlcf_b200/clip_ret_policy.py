@@ -81,6 +81,12 @@ class CLIPRet_TTA(nn.Module):
 
     def set_image_features(self, images=None, image_features=None):
         self.image_features = self.get_image_features(images) if images is not None else image_features
+        self._retire_engine()
+
+    def _retire_engine(self):
+        """The gallery changed: the engine must be rebuilt, but its momentum state is carried into the next one."""
+        if self._engine is not None:
+            self._retired_engine = self._engine
         self._engine = None
 
     def set_text_features(self, text=None, tokenized_prompts=None, text_features=None):
@@ -90,7 +96,7 @@ class CLIPRet_TTA(nn.Module):
             if text_features is None:
                 raise RlcfError("set_text_features needs text, tokenized_prompts or text_features")
             self.text_features = text_features
-        self._engine = None
+        self._retire_engine()
 
     @torch.no_grad()
     def forward(self, images=None, text=None, tokenized_prompts=None):
@@ -105,15 +111,17 @@ class CLIPRet_TTA(nn.Module):
     def engine(self, reward_model, args, n_query):
         """The query engine for this model / reward model / hyper-parameters (rebuilt when any of them changes)."""
         n_query = 1 if self.momentum_update else n_query
-        key = (id(reward_model), n_query, args.tta_steps, args.lr, args.weight_decay, reward_model.sample_k)
-        if self._engine is not None and self._engine_key == key:
-            return self._engine
         cfg = R.RetrievalConfig(tta_steps=args.tta_steps, sample_k=reward_model.sample_k, lr=args.lr,
                                 weight_decay=args.weight_decay, reward_process=bool(reward_model.reward_process),
                                 process_batch=bool(reward_model.process_batch),
                                 reward_amplify=bool(reward_model.amplify_rewards),
                                 clipscore_weight=reward_model.clipscore_weight, momentum_update=bool(self.momentum_update),
                                 update_freq=self.update_freq, update_w=self.update_w, momentum=self.momentum)
+        # every hyper-parameter the engine bakes in is part of the key; the reward model is pinned by the reference kept
+        # next to the engine (so its id() cannot be recycled while the entry is alive)
+        key = (id(reward_model), n_query, tuple(sorted(vars(cfg).items())))
+        if self._engine is not None and self._engine_key == key:
+            return self._engine
         if self.only_visual:
             if self.text_features is None or reward_model.text_features is None:
                 raise RlcfError("image->text: set_text_features on the model and the reward model first")
@@ -124,7 +132,17 @@ class CLIPRet_TTA(nn.Module):
                 raise RlcfError("text->image: set_image_features on the model and the reward model first")
             eng = R.TextQueryEngine(self.state, self.image_features, cfg, n_query, reward_model.text_tower(),
                                     reward_model.image_features)
-        self._engine, self._engine_key = eng, key
+        # the momentum (EMA) state belongs to the MODEL in the reference (custom_models.py: momentum_state_dict,
+        # update_counter live on CLIPRet_TTA) and must survive an engine rebuild
+        old = self._engine if self._engine is not None else getattr(self, "_retired_engine", None)
+        if old is not None and self.momentum_update and type(old) is type(eng):
+            for name in ("ema_ln", "ema_rest", "ema_tab", "init_ln", "init_rest", "init_tab"):
+                a, b = getattr(eng, name, None), getattr(old, name, None)
+                if a is not None and b is not None and a.shape == b.shape:
+                    a.copy_(b)
+            eng.update_counter = getattr(old, "update_counter", 0)
+        self._retired_engine = None
+        self._engine, self._engine_key, self._engine_refs = eng, key, (reward_model,)
         return eng
 
     def momentum_update_model(self):

@@ -94,7 +94,8 @@ int reward_loss(const float*, const int32_t*, const float*, const float*, int, i
 int reward_loss_multi(const float*, const int32_t*, int, const float* const*, const float* const*, const int*,
                       const float*, int, int, int, int, float, int, int, int, float, float*, int32_t*, float*, float*,
                       float*, cudaStream_t);
-int avg_entropy_loss(const float*, const int32_t*, int, int, int, float, float*, float*, cudaStream_t);
+int avg_entropy_loss(const float*, const int32_t*, int, int, int, float, float*, float*, cudaStream_t, float = 1.f,
+                     int = 0);
 int head_bwd(const float*, const float*, const int32_t*, long long, const float*, long long, const float*,
              const float*, float, const float*, const float*, int, int, int, int, int, float, float*, float*, int,
              long long, long long, long long, long long, long long, long long, const float*, float*, float*,
@@ -268,6 +269,12 @@ int rlcf_avg_entropy_loss(const float* logits, const int32_t* row_idx, int n_img
                           float* dlogits, float* loss, void* stream) {
   if (!logits || !dlogits) return set_error(RLCF_ERR_ARG, "avg_entropy_loss: null pointer");
   return avg_entropy_loss(logits, row_idx, n_img, S_, C, loss_scale, dlogits, loss, S(stream));
+}
+
+int rlcf_avg_entropy_reg(const float* logits, const int32_t* row_idx, int n_img, int S_, int C, float loss_scale,
+                         float weight, float* dlogits, float* loss, void* stream) {
+  if (!logits || !dlogits) return set_error(RLCF_ERR_ARG, "avg_entropy_reg: null pointer");
+  return avg_entropy_loss(logits, row_idx, n_img, S_, C, loss_scale, dlogits, loss, S(stream), weight, 1);
 }
 
 int rlcf_head_bwd(const float* dlogits, const float* x, const int32_t* row_idx, int64_t row_stride,

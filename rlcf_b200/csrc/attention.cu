@@ -343,13 +343,9 @@ int attention_fwd(const __half* qkv, int n_seq, int L, int heads, int causal, __
   const int Lp = (L + 15) / 16 * 16;
   const size_t smem = static_cast<size_t>(2 * Lp + kFwdWarps * 16) * kRowBytes;
   if (smem > 227 * 1024) return set_error(RLCF_ERR_ARG, "attention_fwd: sequence %d too long for one CTA", L);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-    if (e != cudaSuccess) return set_error(RLCF_ERR_CUDA, "attention_fwd attr: %s", cudaGetErrorString(e));
-    configured = smem;
-  }
+  static DynSmemState st;
+  if (cudaError_t e = ensure_dyn_smem(attn_fwd_kernel, smem, st))
+    return set_error(RLCF_ERR_CUDA, "attention_fwd attr: %s", cudaGetErrorString(e));
   dim3 grid((L + kFwdWarps * 16 - 1) / (kFwdWarps * 16), heads, n_seq);
   attn_fwd_kernel<<<grid, kFwdWarps * 32, smem, stream>>>(qkv, L, Lp, heads, causal, out, lse);
   RLCF_CHECK_LAUNCH("attention_fwd");
@@ -362,13 +358,9 @@ int attention_bwd(const __half* qkv, const __half* out, const __half* dout, cons
   const int Lp = (L + 15) / 16 * 16;
   const size_t smem = static_cast<size_t>(4 * Lp) * kRowBytes + 2 * Lp * sizeof(float);
   if (smem > 227 * 1024) return set_error(RLCF_ERR_ARG, "attention_bwd: sequence %d too long for one CTA", L);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-    if (e != cudaSuccess) return set_error(RLCF_ERR_CUDA, "attention_bwd attr: %s", cudaGetErrorString(e));
-    configured = smem;
-  }
+  static DynSmemState st;
+  if (cudaError_t e = ensure_dyn_smem(attn_bwd_kernel, smem, st))
+    return set_error(RLCF_ERR_CUDA, "attention_bwd attr: %s", cudaGetErrorString(e));
   dim3 grid(heads, n_seq);
   attn_bwd_kernel<<<grid, kBwdWarps * 32, smem, stream>>>(qkv, out, dout, lse, L, Lp, heads, causal, dqkv);
   RLCF_CHECK_LAUNCH("attention_bwd");

@@ -457,12 +457,9 @@ int attention_fwd_tc(const __half* qkv, int n_seq, int L, int heads, int causal,
   a.debug = debug;
   const size_t smem = 1024 + 2 * static_cast<size_t>(a.stage_bytes) + (2 * B_PER_TEAM + 8) * 8 + 16;
   auto kernel = attn_fwd_tc_kernel;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return set_error(RLCF_ERR_CUDA, "attention_fwd_tc attr: %s", cudaGetErrorString(e));
-    configured = smem;
-  }
+  static DynSmemState st;
+  if (cudaError_t e = ensure_dyn_smem(kernel, smem, st))
+    return set_error(RLCF_ERR_CUDA, "attention_fwd_tc attr: %s", cudaGetErrorString(e));
   CUtensorMap mq, mkv;
   const long long rows = static_cast<long long>(n_seq) * L;
   if (int rc = make_tmap_rows64(&mq, qkv, rows, 3 * heads * 64, 128)) return rc;

@@ -364,12 +364,9 @@ int augmix_views(const uint8_t* x_orig, int n_views, const int* vflag, const flo
                  float* out, cudaStream_t stream) {
   if (n_views <= 0 || n_views > 65535) return set_error(RLCF_ERR_ARG, "augmix_views: bad shape");
   const size_t smem = 2 * kPlane * kPlane + 512 * sizeof(int);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(augmix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return set_error(RLCF_ERR_CUDA, "augmix attr: %s", cudaGetErrorString(e));
-    configured = true;
-  }
+  static DynSmemState st;
+  if (cudaError_t e = ensure_dyn_smem(augmix_kernel, smem, st))
+    return set_error(RLCF_ERR_CUDA, "augmix attr: %s", cudaGetErrorString(e));
   dim3 grid(3, n_views);
   augmix_kernel<<<grid, 256, smem, stream>>>(x_orig, vflag, wts, omm, n_ops, ops, mats, mean[0], mean[1], mean[2],
                                              stdv[0], stdv[1], stdv[2], out);

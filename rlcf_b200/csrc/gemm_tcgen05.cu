@@ -410,11 +410,16 @@ template <int kCtaGroup, int kEpi, int kMc>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
   using Cfg = GemmCfg<kCtaGroup>;
   constexpr int kClusterCtas = kCtaGroup * kMc;
-  static bool configured = false;
-  static int max_clusters = 0;   // co-resident clusters: the kernel is persistent, so the grid must not exceed it
+  // per device (the attribute and the co-residency of clusters are properties of the device the launch goes to)
+  static DynSmemState st;
+  static int max_clusters_dev[32] = {};   // co-resident clusters: the kernel is persistent, so the grid must not exceed it
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 32) dev = 31;
+  int& max_clusters = max_clusters_dev[dev];
+  const bool configured = max_clusters > 0 && dev != 31;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<kCtaGroup, kEpi, kMc>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = ensure_dyn_smem(gemm_f16_kernel<kCtaGroup, kEpi, kMc>, Cfg::kSmemBytes, st);
     if (e != cudaSuccess) return set_error(RLCF_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
     max_clusters = sm_count() / kClusterCtas;
     if (kClusterCtas > 2) {
@@ -436,7 +441,6 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
       if (n > 0 && n < max_clusters) max_clusters = n;
       if (getenv("RLCF_GEMM_VERBOSE")) fprintf(stderr, "rlcf gemm: %d-CTA clusters, %d co-resident\n", kClusterCtas, n);
     }
-    configured = true;
   }
   const int tile_m = kBM * kClusterCtas;
   const int tiles = args.G * ((args.M + tile_m - 1) / tile_m) * ((args.N + kBN - 1) / kBN);

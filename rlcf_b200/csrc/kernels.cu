@@ -255,10 +255,10 @@ int embed_text(const long long* tokens, const float* tok_emb, const float* pos, 
 // registers per lane.  ln_bwd_kernel needs 168 registers, so only ONE 256-thread block fits an SM (8 warps, each with two
 // dependent memory round trips per row) and a 32-image launch runs 7 waves; ln_bwd_smem_kernel is bounded to 128
 // registers -> two blocks per SM.  Same additions in the same order per warp and the same slot reduction, so the
-// results are bit-identical.  Opt-in (RLCF_LN_BWD_SMEM=1; measured 197.7 -> 130.0 us per launch at the 32-image policy
-// geometry and bit-identical there for widths 768 / 1024, fp16 and fp32 dy -- scripts/dump_ln_bwd.py,
-// tests/test_kernels_gpu.py with RLCF_EXPERIMENTAL=1; it becomes the default once the whole GPU suite has run with it,
-// this round's GPU budget ended first).
+// results are bit-identical.  The shared-memory variant is the DEFAULT (measured 197.7 -> 130.0 us per launch at the
+// 32-image policy geometry; bit-identical for widths 768 / 1024, fp16 and fp32 dy -- scripts/dump_ln_bwd.py,
+// tests/test_kernels_gpu.py::test_layernorm_bwd_smem_variant_is_bit_identical); RLCF_LN_BWD_SMEM=0 selects the register
+// variant.
 template <int NV, bool kDyF32, bool kSmemAcc>
 __device__ __forceinline__ void ln_bwd_body(const void* __restrict__ dy_, long long lddy, const float* __restrict__ x,
                                             long long ldx, const float* __restrict__ gamma, long long pstride,
@@ -411,12 +411,8 @@ static cudaError_t launch_ln_bwd_smem(dim3 grid, cudaStream_t stream, const void
                                       float* dx, long long lddx, int accumulate, __half* dx16, float* partials,
                                       long long p_total, long long p_off) {
   constexpr int smem = 8 * 2 * NV * 128 * static_cast<int>(sizeof(float));
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ln_bwd_smem_kernel<NV, kDyF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static DynSmemState st;
+  if (cudaError_t e = ensure_dyn_smem(ln_bwd_smem_kernel<NV, kDyF32>, smem, st)) return e;
   ln_bwd_smem_kernel<NV, kDyF32><<<grid, 256, smem, stream>>>(dy, lddy, x, ldx, gamma, pstride, rows_per_set, eps, dx,
                                                                 lddx, accumulate, dx16, partials, p_total, p_off);
   return cudaSuccess;
@@ -431,7 +427,7 @@ int layernorm_bwd(const void* dy, int dy_is_f32, long long lddy, const float* x,
   if (partials == nullptr && dx == nullptr) return set_error(RLCF_ERR_ARG, "layernorm_bwd: nothing to compute");
   if (dx16 != nullptr && dx == nullptr) return set_error(RLCF_ERR_ARG, "layernorm_bwd: dx16 needs dx_accum");
   dim3 grid(n_slots, n_sets);
-  static const bool smem_acc = getenv("RLCF_LN_BWD_SMEM") != nullptr && atoi(getenv("RLCF_LN_BWD_SMEM")) != 0;
+  static const bool smem_acc = getenv("RLCF_LN_BWD_SMEM") == nullptr || atoi(getenv("RLCF_LN_BWD_SMEM")) != 0;
   if (smem_acc) {
     cudaError_t e = cudaSuccess;
     if (dy_is_f32) {
@@ -573,13 +569,10 @@ int head_fwd(const float* x, const int32_t* row_idx, long long row_stride, const
   if (smem > 227 * 1024) return set_error(RLCF_ERR_ARG, "head_fwd: width too large");
 #define RLCF_HEAD_LAUNCH(V)                                                                                       \
   {                                                                                                               \
-    static size_t configured = 0;                                                                                 \
-    if (smem > 48 * 1024 && smem > configured) {                                                                  \
-      cudaError_t e = cudaFuncSetAttribute(head_fwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                           static_cast<int>(smem));                                               \
-      if (e != cudaSuccess) return set_error(RLCF_ERR_CUDA, "head_fwd attr: %s", cudaGetErrorString(e));          \
-      configured = smem;                                                                                          \
-    }                                                                                                             \
+    static DynSmemState st;                                                                                       \
+    if (smem > 48 * 1024)                                                                                         \
+      if (cudaError_t e = ensure_dyn_smem(head_fwd_kernel<V>, smem, st))                                          \
+        return set_error(RLCF_ERR_CUDA, "head_fwd attr: %s", cudaGetErrorString(e));                              \
     head_fwd_kernel<V><<<(n + V - 1) / V, kHeadThreads, smem, stream>>>(                                          \
         x, row_idx, row_stride, gamma, beta, pstride, seqs_per_set, proj, cls_feat, logit_scale, n, d, E, C, eps, \
         feat, inv_norm, logits, proj_stride);                                                                     \
@@ -811,7 +804,8 @@ int reward_loss(const float* logits, const int32_t* row_idx, const float* r_img,
 // d loss / d x[s,c] = p[s,c] * (G_c / Pbar_c - sum_c' G_c' p[s,c'] / Pbar_c'),  G_c = -(1 + avg_c) * Pbar_c / S.
 __global__ void __launch_bounds__(256)
 avg_entropy_kernel(const float* __restrict__ logits, const int32_t* __restrict__ row_idx, int S, int C,
-                   float loss_scale, float* __restrict__ dlogits, float* __restrict__ loss_out) {
+                   float loss_scale, float* __restrict__ dlogits, float* __restrict__ loss_out, float loss_weight,
+                   int accumulate) {
   extern __shared__ float smf[];
   float* off = smf;        // [S]  max + lse per view
   float* q = off + S;      // [C]  G_c / Pbar_c
@@ -843,7 +837,7 @@ avg_entropy_kernel(const float* __restrict__ logits, const int32_t* __restrict__
     q[c] = pb > 0.f ? -(1.f + avg) / S : 0.f;
   }
   const float total = block_sum<256>(lsum, scratch);
-  if (threadIdx.x == 0 && loss_out) loss_out[img] = total;
+  if (threadIdx.x == 0 && loss_out) loss_out[img] = (accumulate ? loss_out[img] : 0.f) + loss_weight * total;
   __syncthreads();
   for (int s = warp; s < S; s += 8) {
     const int n = img * S + s;
@@ -858,15 +852,17 @@ avg_entropy_kernel(const float* __restrict__ logits, const int32_t* __restrict__
     const int n = img * S + s;
     const float* r = logits + static_cast<size_t>(row_idx ? row_idx[n] : n) * C;
     float* o = dlogits + static_cast<size_t>(n) * C;
-    for (int c = lane; c < C; c += 32) o[c] = loss_scale * expf(r[c] - off[s]) * (q[c] - t2[s]);
+    for (int c = lane; c < C; c += 32)
+      o[c] = (accumulate ? o[c] : 0.f) + loss_scale * expf(r[c] - off[s]) * (q[c] - t2[s]);
   }
 }
 
 int avg_entropy_loss(const float* logits, const int32_t* row_idx, int n_img, int S, int C, float loss_scale,
-                     float* dlogits, float* loss, cudaStream_t stream) {
+                     float* dlogits, float* loss, cudaStream_t stream, float weight, int accumulate) {
   if (n_img <= 0 || S <= 0 || C <= 0) return set_error(RLCF_ERR_ARG, "avg_entropy_loss: bad shape");
   const size_t smem = (static_cast<size_t>(2) * S + C + 16) * sizeof(float);
-  avg_entropy_kernel<<<n_img, 256, smem, stream>>>(logits, row_idx, S, C, loss_scale, dlogits, loss);
+  avg_entropy_kernel<<<n_img, 256, smem, stream>>>(logits, row_idx, S, C, loss_scale * weight, dlogits, loss, weight,
+                                                   accumulate);
   RLCF_CHECK_LAUNCH("avg_entropy_loss");
   return 0;
 }

@@ -56,6 +56,24 @@ int gemm_f16_grouped(const __half* A, int lda, long long a_gs, const __half* B, 
                      const __half* aux_in, __half* aux_out, void* out, int ldo, long long out_gs,
                      cudaStream_t stream, const AdamwEpi* adamw = nullptr);
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: the bookkeeping of "already raised
+// to at least `smem` bytes" is kept per device, so a process that drives a second GPU configures the kernel there too.
+struct DynSmemState {
+  size_t configured[32] = {};
+};
+template <typename Kernel>
+inline cudaError_t ensure_dyn_smem(Kernel kernel, size_t smem, DynSmemState& st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 32) dev = 31;   // beyond the table: always (re)configure
+  if (smem > st.configured[dev] || dev == 31) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    st.configured[dev] = smem;
+  }
+  return cudaSuccess;
+}
+
 // Checks the launch of the kernel that was just enqueued.
 #define RLCF_CHECK_LAUNCH(name)                                                                 \
   do {                                                                                          \

@@ -161,6 +161,23 @@ def prepare_text(sd: dict, need_grad: bool = False) -> TowerWeights:
     return w
 
 
+def copy_tower_(dst: TowerWeights, src: TowerWeights) -> TowerWeights:
+    """In-place refresh of kernel-ready weights (same architecture): every tensor of `dst` keeps its storage, so
+    workspaces, views and captured CUDA graphs that point at it stay valid."""
+    if (dst.kind, dst.d, dst.n_layers, dst.L, dst.E) != (src.kind, src.d, src.n_layers, src.L, src.E):
+        raise RlcfError("copy_tower_: architectures differ")
+    for name in ("proj", "ln_flat", "conv_w", "cls", "pos", "tok_emb"):
+        a, b = getattr(dst, name), getattr(src, name)
+        if a is not None and b is not None:
+            a.copy_(b)
+    for la, lb in zip(dst.layers, src.layers):
+        for name in ("wqkv", "bqkv", "wo", "bo", "wfc", "bfc", "wproj", "bproj", "wqkv_t", "wo_t", "wfc_t", "wproj_t"):
+            a, b = getattr(la, name), getattr(lb, name)
+            if a is not None and b is not None:
+                a.copy_(b)
+    return dst
+
+
 def linear(a, wt, out, M, epilogue=EPI_F16, bias=None, resid=None, aux_in=None, aux_out=None):
     """out[:M] = epilogue(a[:M] @ wt^T).  wt [N,K]: one weight for all rows.  wt [G,N,K]: per-sample weights, the M
     rows being G equal runs (one grouped launch)."""
@@ -389,6 +406,8 @@ class RlcfConfig:
     loss: str = "rlcf"           # "rlcf" (tpt_cls_rl.py:63-71) | "tpt" (avg_entropy, tpt_cls_rl.py:38-44)
     reward_weights: tuple = ()   # ensemble of reward models (CLIPRewardsMultiple, clip_reward.py:180-307): one weight
                                  # per model -- normalised confidences, or 1/n each for weighted_scores = False
+    min_entropy_w: float = 0.0   # --min_entropy_reg 1 --min_entropy_w w: loss += w * avg_entropy(output)
+                                 # (tpt_cls_rl.py:73-74); 0 = off
 
     @property
     def n_selected(self):
@@ -548,6 +567,9 @@ class RlcfEngine:
             if cfg.loss == "rlcf":
                 self.scorer.loss(self.logits_sel, B, S, K, C, self.dlogits, cfg, topk_idx=self.topk_idx,
                                  scores=self.scores, rewards=self.rewards, loss=self.loss[step - 1])
+                if cfg.min_entropy_w:                                                  # tpt_cls_rl.py:73-74
+                    ops.avg_entropy_reg(self.logits_sel, None, B, S, C, self.dlogits, cfg.min_entropy_w,
+                                        loss=self.loss[step - 1], loss_scale=cfg.loss_scale)
             else:
                 ops.avg_entropy_loss(self.logits_sel, None, B, S, C, self.dlogits, loss=self.loss[step - 1],
                                      loss_scale=cfg.loss_scale)
@@ -728,6 +750,9 @@ class PromptEngine:
             if cfg.loss == "rlcf":
                 self.scorer.loss(self.logits_sel, B, S, K, C, self.dlogits, cfg, topk_idx=self.topk_idx,
                                  scores=self.scores, rewards=self.rewards, loss=self.loss[step - 1])
+                if cfg.min_entropy_w:                                                  # tpt_cls_rl.py:73-74
+                    ops.avg_entropy_reg(self.logits_sel, None, B, S, C, self.dlogits, cfg.min_entropy_w,
+                                        loss=self.loss[step - 1], loss_scale=cfg.loss_scale)
             else:
                 ops.avg_entropy_loss(self.logits_sel, None, B, S, C, self.dlogits, loss=self.loss[step - 1],
                                      loss_scale=cfg.loss_scale)

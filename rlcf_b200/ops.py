@@ -208,6 +208,13 @@ def avg_entropy_loss(logits, row_idx, n_img, S, C, dlogits, loss=None, loss_scal
          stream())
 
 
+def avg_entropy_reg(logits, row_idx, n_img, S, C, dlogits, weight, loss=None, loss_scale=1.0):
+    """dlogits += weight * loss_scale * d avg_entropy/d logits; loss += weight * avg_entropy  (tpt_cls_rl.py:73-74)."""
+    _chk(logits, torch.float32, "logits"); _chk(dlogits, torch.float32, "dlogits")
+    call("rlcf_avg_entropy_reg", ptr(logits), ptr(row_idx), n_img, S, C, float(loss_scale), float(weight), ptr(dlogits),
+         ptr(loss), stream())
+
+
 def head_bwd(dlogits, x, gamma, proj, class_feat, logit_scale, feat, inv_norm, n_img, S, d, E, C, dres, partials,
              n_slots, p_total, p_off, row_idx=None, row_stride=1, param_stride=0, eps=1e-5):
     _chk(dlogits, torch.float32, "dlogits"); _chk(x, torch.float32, "x"); _chk(dres, torch.float32, "dres")

@@ -61,6 +61,9 @@ def build_parser():
     parser.add_argument("--synthetic", action="store_true", help="synthetic weights / views / labels (offline)")
     parser.add_argument("--synthetic_weights", action="store_true",
                         help="real images from DIR (views generated on the GPU) with seeded random-init CLIP weights")
+    parser.add_argument("--classnames", type=str, default=None,
+                        help="class-name table for test sets whose folders are ids (ImageNet wnids, ImageNetV2 "
+                             "integers): JSON {folder: name} / {set_id: ...} / [names] or LOC_synset_mapping.txt lines")
     parser.add_argument("--n_images", type=int, default=64, help="synthetic: test images per dataset")
     parser.add_argument("--n_classes", type=int, default=200, help="synthetic: classes per dataset")
     return parser

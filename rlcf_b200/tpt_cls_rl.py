@@ -41,8 +41,6 @@ def avg_entropy(outputs):
 
 def engine_config(args, optimizer, reward_model, loss="rlcf") -> E.RlcfConfig:
     g = optimizer.param_groups[0]
-    if getattr(args, "min_entropy_reg", 0):
-        raise NotImplementedError("--min_entropy_reg is an experimental reference feature that is not implemented")
     return E.RlcfConfig(
         n_views=args.batch_size, selection_p=args.selection_p, tta_steps=args.tta_steps,
         sample_k=reward_model.sample_k if reward_model is not None else 1, lr=g["lr"],
@@ -50,7 +48,8 @@ def engine_config(args, optimizer, reward_model, loss="rlcf") -> E.RlcfConfig:
         clipscore_weight=getattr(reward_model, "clipscore_weight", 2.5),
         reward_process=bool(getattr(reward_model, "reward_process", True)),
         process_batch=bool(getattr(reward_model, "process_batch", False)),
-        reward_amplify=bool(getattr(reward_model, "amplify_rewards", False)), loss=loss)
+        reward_amplify=bool(getattr(reward_model, "amplify_rewards", False)), loss=loss,
+        min_entropy_w=float(getattr(args, "min_entropy_w", 0.0)) if getattr(args, "min_entropy_reg", 0) else 0.0)
 
 
 def test_time_tuning(model, inputs, optimizer, scaler, args, reward_model=None, n_img: int = 1):

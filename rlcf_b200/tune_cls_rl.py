@@ -88,7 +88,11 @@ def test_time_adapt_eval(val_loader, model, optimizer, optim_state, scaler, args
         pend_views.clear()
         pend_targets.clear()
 
+    n_cls = getattr(model, "n_cls", None)
     for i, (images, target) in enumerate(val_loader):
+        if n_cls is not None and int(target.view(-1)[0]) >= n_cls:      # host-side label, no device sync
+            raise RuntimeError(f"label {int(target.view(-1)[0])} outside the model's {n_cls} classes: call "
+                               "model.reset_classnames_and_state(...) for this test set (tune_cls_rl.py:139)")
         pend_views.append(_stack_views(images, device))
         pend_targets.append(target.to(device, non_blocking=True).view(-1)[:1])
         if len(pend_views) == B:
@@ -155,6 +159,74 @@ class ImageFolderViews(torch.utils.data.Dataset):
         return (u8, plan), torch.tensor(label)
 
 
+def _collate_one(batch):
+    """DataLoader collate for batch_size 1 (module-level so that worker processes can pickle it)."""
+    return batch[0][0], batch[0][1].view(1)
+
+
+def load_classname_table(path):
+    """--classnames FILE: what the reference hard-codes in TPT/data/imagnet_prompts.py / cls_to_names.py and indexes
+    with the imagenet_{a,r,v}_mask tables (tune_cls_rl.py:122-141) -- here a user-supplied file, because those tables
+    are the reference's data.  Accepted: JSON {folder: name}, JSON {set_id: {folder: name} | [names]}, JSON [names]
+    (index = class id), or text lines "<folder> <name>[, synonyms]" (the format of ImageNet's LOC_synset_mapping.txt)."""
+    if path is None:
+        return None
+    with open(path) as f:
+        text = f.read()
+    try:
+        return json.loads(text)
+    except ValueError:
+        table = {}
+        for line in text.splitlines():
+            if line.strip():
+                folder, _, name = line.strip().partition(" ")
+                table[folder] = name.split(",")[0].strip()
+        return table
+
+
+def class_names_for(folders, table, set_id):
+    """Class names in ImageFolder label order for one test set.  Folder names that are WordNet ids (ImageNet, -A, -R,
+    -Sketch) or integers (ImageNetV2) carry no meaning: without a table they are an error, never a prompt."""
+    import re
+    if isinstance(table, dict) and set_id in table and isinstance(table[set_id], (dict, list)):
+        table = table[set_id]
+    opaque = all(re.fullmatch(r"n\d{8}|\d+", c) for c in folders)
+    if table is None:
+        if opaque:
+            raise SystemExit(f"test set {set_id}: folder names such as '{folders[0]}' are ids, not class names; pass "
+                             "--classnames FILE (JSON {folder: name} / [names], or LOC_synset_mapping.txt lines)")
+        return [c.replace("_", " ") for c in folders]
+    if isinstance(table, dict):
+        missing = [c for c in folders if c not in table]
+        if missing:
+            raise SystemExit(f"test set {set_id}: --classnames has no entry for folders {missing[:5]} ...")
+        return [str(table[c]) for c in folders]
+    if all(c.isdigit() for c in folders):                    # ImageNetV2: folder k holds class id k
+        if max(int(c) for c in folders) >= len(table):
+            raise SystemExit(f"test set {set_id}: --classnames lists {len(table)} names, folders go beyond that")
+        return [str(table[int(c)]) for c in folders]
+    if len(table) != len(folders):
+        raise SystemExit(f"test set {set_id}: --classnames lists {len(table)} names for {len(folders)} class folders")
+    return [str(t) for t in table]
+
+
+def _check_supported_flags(args):
+    """Reference flags this driver accepts for command-line compatibility but does not implement must not be dropped
+    silently (params.py:23-73)."""
+    if getattr(args, "hard_aug", 0):
+        raise NotImplementedError("--hard_aug (ColorJitter / blur views, data/datautils.py:75-85) is not implemented")
+    if getattr(args, "confidence_gap", 0):
+        raise NotImplementedError("--confidence_gap is an experimental reference feature that is not implemented")
+    if getattr(args, "multiple_reward_models", 0) and "," not in str(args.reward_arch):
+        raise NotImplementedError("--multiple_reward_models 1 needs --reward_arch 'ViT-L/14,ViT-B/16,...' (the "
+                                  "reference's hard-coded list includes RN50x64, a ResNet, which is out of scope)")
+    if not getattr(args, "tpt", False) and not getattr(args, "synthetic", False):
+        raise NotImplementedError("without --tpt the reference runs plain batched zero-shot evaluation "
+                                  "(tune_cls_rl.py:112-119); this driver implements the --tpt adaptation loop only")
+    if "RN" in str(args.arch):
+        raise NotImplementedError("ModifiedResNet policies are out of scope; use a ViT (-a ViT-B/16)")
+
+
 def _real_dataset_root(args, set_id):
     if set_id == "I":
         return os.path.join(args.data, ID_to_DIRNAME[set_id], "val")
@@ -174,19 +246,23 @@ def main_worker(gpu, args):
         raise SystemExit("rlcf_b200 needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(gpu)
     device = torch.device("cuda", gpu)
+    _check_supported_flags(args)
     real_data = args.data is not None and not args.synthetic
     if not real_data and not args.synthetic:
         raise SystemExit("give a dataset root (DIR, ImageFolder layout as in TPT/data/datautils.py) or --synthetic")
     synth_w = args.synthetic or getattr(args, "synthetic_weights", False)
     arch = "synthetic:" + args.arch + ":0" if synth_w else args.arch
     reward_arch = "synthetic:" + args.reward_arch + ":1" if synth_w else args.reward_arch
-    datasets_ = {}
-    if real_data:   # the class names come from the first dataset's folders (one model per run, as in the reference loop)
+    datasets_, set_classnames = {}, {}
+    if real_data:   # every test set has its own label space (tune_cls_rl.py:120-141)
+        table = load_classname_table(getattr(args, "classnames", None))
+        if getattr(args, "resolution", 224) != 224:
+            raise NotImplementedError("--resolution other than 224 is not implemented (the view kernels crop to 224)")
         for set_id in args.test_sets.split("/"):
             datasets_[set_id] = ImageFolderViews(_real_dataset_root(args, set_id), args.batch_size - 1,
                                                  augmix=len(set_id) > 1, rank=rank, world=world)   # tune_cls_rl.py:109-110
-        first = datasets_[args.test_sets.split("/")[0]]
-        classnames = [c.replace("_", " ") for c in first.classes]
+            set_classnames[set_id] = class_names_for(datasets_[set_id].classes, table, set_id)
+        classnames = set_classnames[args.test_sets.split("/")[0]]
         args.n_classes = len(classnames)
     else:
         classnames = [f"class {i}" for i in range(args.n_classes)]
@@ -213,13 +289,17 @@ def main_worker(gpu, args):
         if real_data:
             ds = datasets_[set_id]
             args.n_images = len(ds.folder)
+            # this set's label space: new class prompts for the policy and the reward model (tune_cls_rl.py:139-143)
+            args.n_classes = len(set_classnames[set_id])
+            model.reset_classnames_and_state(set_classnames[set_id], args.arch)
+            reward_model.set_class_features(tokenized_classes=model.tokenized_prompts)
             loader = torch.utils.data.DataLoader(ds, batch_size=1, shuffle=False, num_workers=args.workers,
-                                                 collate_fn=lambda b: (b[0][0], b[0][1].view(1)))
+                                                 collate_fn=_collate_one)
         else:
             ds = SyntheticViews(args.n_images, args.batch_size, args.resolution, args.n_classes, args.seed + 1000,
                                 rank, world)
             loader = torch.utils.data.DataLoader(ds, batch_size=1, shuffle=False, num_workers=0,
-                                                 collate_fn=lambda b: (b[0][0], b[0][1].view(1)))
+                                                 collate_fn=_collate_one)
         results[set_id] = test_time_adapt_eval(loader, model, optimizer, optim_state, scaler, args, device=device,
                                                reward_model=reward_model)
         if rank == 0:

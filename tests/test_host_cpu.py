@@ -60,30 +60,97 @@ def test_flat_layernorm_layout_and_flops():
     assert cfg.n_selected == 6 and E.RlcfConfig(n_views=8).n_selected == 0
 
 
+def _vocab_path():
+    from rlcf_b200.clip import simple_tokenizer as ST
+    return ST._find_vocab()
+
+
 def test_tokenizer_matches_reference_vectors():
-    vocab = "/root/reference/TPT/clip/bpe_simple_vocab_16e6.txt.gz"
-    if not os.path.exists(vocab):
+    """With OpenAI's merge table (shipped next to the tokenizer by build()), token ids equal the reference tokenizer's:
+    known ids, and every prompt of the fixture that the reference tokenised itself (tests/golden/b32_cfg1_exact.npz,
+    tiny_prompt_rlcf_2step.npz: `prompt_learner.tokenized_prompts`, custom_clip.py:140-150)."""
+    import numpy as np
+    vocab = _vocab_path()
+    if vocab is None:
         pytest.skip("OpenAI BPE vocabulary not available on this machine")
+    from rlcf_b200.clip import clip
     from rlcf_b200.clip.simple_tokenizer import SimpleTokenizer
     tok = SimpleTokenizer(vocab)
-    # ids produced by the reference tokenizer (TPT/clip/simple_tokenizer.py) for the same strings
+    assert not tok.byte_fallback
     assert tok.encode("a photo of a great white shark.") == [320, 1125, 539, 320, 830, 1579, 7980, 269]
     assert tok.encoder["<|startoftext|>"] == 49406 and tok.encoder["<|endoftext|>"] == 49407
     assert tok.decode(tok.encode("a photo of a tench.")).strip() == "a photo of a tench ."
+    g = os.path.join(ROOT, "tests", "golden")
+    z = np.load(os.path.join(g, "b32_cfg1_exact.npz"))
+    mine = clip.tokenize([f"a photo of a class {i}." for i in range(32)])
+    assert np.array_equal(mine.numpy(), z["tokens"])
+    z = np.load(os.path.join(g, "tiny_prompt_rlcf_2step.npz"))
+    names = ["tench", "goldfish", "great white shark", "tiger shark", "hammerhead", "electric ray", "stingray",
+             "cock", "hen", "ostrich", "brambling", "goldfinch"]
+    assert np.array_equal(clip.tokenize([f"a photo of a {n}." for n in names]).numpy(), z["tokens"])
+    with pytest.raises(RuntimeError):
+        clip.tokenize("word " * 100)                       # clip.py:230: too long for the context length
+    assert clip.tokenize("word " * 100, truncate=True)[0, -1] == 49407
 
 
-def test_fallback_tokenizer_is_well_formed():
-    from rlcf_b200.clip.simple_tokenizer import SimpleTokenizer
-    import warnings
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        os.environ.pop("RLCF_BPE_VOCAB", None)
-        tok = SimpleTokenizer(bpe_path=None) if not os.path.exists(
-            os.path.expanduser("~/.cache/clip/bpe_simple_vocab_16e6.txt.gz")) else None
-    if tok is None:
-        pytest.skip("a real vocabulary is installed")
+def test_missing_vocabulary_is_a_hard_error(monkeypatch):
+    """No silent degraded path: without the merge table the tokenizer raises, unless the byte-level fallback was asked
+    for explicitly (synthetic-weight runs)."""
+    from rlcf_b200.clip import simple_tokenizer as ST
+    monkeypatch.setattr(ST, "_find_vocab", lambda: None)
+    monkeypatch.delenv("RLCF_BPE_FALLBACK", raising=False)
+    with pytest.raises(RuntimeError, match="bpe_simple_vocab"):
+        ST.SimpleTokenizer()
+    tok = ST.SimpleTokenizer(allow_byte_fallback=True)
+    assert tok.byte_fallback
     ids = tok.encode("a photo of a dog.")
     assert ids and max(ids) < 49406
+
+
+def _script_archive(sd, path):
+    """An OpenAI-style TorchScript archive: a scripted module whose hierarchy reproduces the state-dict keys, plus the
+    three metadata buffers the real archives carry (clip.py:126-142 / model.py:430-432 drop them)."""
+    import torch.nn as nn
+
+    class Holder(nn.Module):
+        def forward(self, x):
+            return x
+
+    root = Holder()
+    for key, val in sd.items():
+        mod, parts = root, key.split(".")
+        for part in parts[:-1]:
+            if not hasattr(mod, part):
+                mod.add_module(part, Holder())
+            mod = getattr(mod, part)
+        mod.register_parameter(parts[-1], nn.Parameter(val.clone(), requires_grad=False))
+    root.register_buffer("input_resolution", torch.tensor(64))
+    root.register_buffer("context_length", torch.tensor(77))
+    root.register_buffer("vocab_size", torch.tensor(512))
+    torch.jit.save(torch.jit.script(root), path)
+
+
+def test_clip_load_reads_torchscript_archives_and_state_dicts(tmp_path):
+    """clip.load(path) (TPT/clip/clip.py:121-142): TorchScript archive -> state_dict -> build_model -> fp32 model,
+    3-tuple result; a plain state_dict file and a {'state_dict': ...} checkpoint load the same weights."""
+    from rlcf_b200 import synthetic
+    from rlcf_b200.clip import clip
+    sd = synthetic.make_state_dict("tiny-A", 4)
+    jit_path, sd_path, ck_path = (str(tmp_path / n) for n in ("tiny.pt", "tiny_sd.pt", "tiny_ck.pt"))
+    _script_archive(sd, jit_path)
+    torch.save(sd, sd_path)
+    torch.save({"state_dict": sd}, ck_path)
+    assert set(torch.jit.load(jit_path).state_dict()) == set(sd) | {"input_resolution", "context_length", "vocab_size"}
+    for path in (jit_path, sd_path, ck_path):
+        model, embed_dim, preprocess = clip.load(path, device="cpu")
+        assert embed_dim == 128 and model.visual.input_resolution == 64 and callable(preprocess)
+        got = model.state_dict()
+        assert set(got) == set(sd)
+        assert all(torch.equal(got[k], sd[k]) and got[k].dtype == torch.float32 for k in sd)
+    with pytest.raises(RuntimeError):
+        clip.load("no-such-model", device="cpu")
+    with pytest.raises(RuntimeError):
+        clip.load("ViT-B/16", device="cpu", download_root=str(tmp_path))   # known name, file absent, no network
 
 
 def test_synthetic_dataset_sharding():
@@ -216,3 +283,39 @@ def test_momentum_update_model_follows_the_reference_formula():
     off = _stub_cls_tta(False, False)
     off.momentum_update_model()
     assert off.update_counter == 0
+
+
+def test_class_names_per_test_set(tmp_path):
+    """folder names that are ids never become prompts; every test set gets its own label space."""
+    import json
+    from rlcf_b200.tune_cls_rl import class_names_for, load_classname_table
+    assert class_names_for(["golden_retriever", "tabby_cat"], None, "pets") == ["golden retriever", "tabby cat"]
+    with pytest.raises(SystemExit):
+        class_names_for(["n01440764", "n01443537"], None, "A")
+    with pytest.raises(SystemExit):
+        class_names_for(["0", "1", "10"], None, "V")
+    p = tmp_path / "map.txt"
+    p.write_text("n01440764 tench, Tinca tinca\nn01443537 goldfish, Carassius auratus\n")
+    table = load_classname_table(str(p))
+    assert class_names_for(["n01443537", "n01440764"], table, "A") == ["goldfish", "tench"]
+    with pytest.raises(SystemExit):
+        class_names_for(["n01443537", "n09999999"], table, "A")
+    p = tmp_path / "names.json"
+    p.write_text(json.dumps({"V": ["zero", "one", "two"] + [f"c{i}" for i in range(3, 11)], "A": {"n01440764": "tench"}}))
+    table = load_classname_table(str(p))
+    assert class_names_for(["0", "1", "10", "2"], table, "V") == ["zero", "one", "c10", "two"]   # ImageFolder sorts as text
+    assert class_names_for(["n01440764"], table, "A") == ["tench"]
+
+
+def test_unsupported_reference_flags_raise():
+    from rlcf_b200.params import build_parser
+    from rlcf_b200.tune_cls_rl import _check_supported_flags
+    base = ["DATA", "--tpt", "-a", "ViT-B/16"]
+    _check_supported_flags(build_parser().parse_args(base))
+    for extra in (["--hard_aug", "1"], ["--confidence_gap", "1"], ["--multiple_reward_models", "1"]):
+        with pytest.raises(NotImplementedError):
+            _check_supported_flags(build_parser().parse_args(base + extra))
+    with pytest.raises(NotImplementedError):
+        _check_supported_flags(build_parser().parse_args(["DATA", "-a", "ViT-B/16"]))        # no --tpt
+    with pytest.raises(NotImplementedError):
+        _check_supported_flags(build_parser().parse_args(["DATA", "--tpt"]))                 # default arch RN50

@@ -178,10 +178,10 @@ def test_layernorm_fwd_bwd(d):
     assert _rel(dx, xr.grad.view(M, d)) < 2e-5
 
 
-@pytest.mark.skipif(os.environ.get("RLCF_EXPERIMENTAL") != "1", reason="opt-in kernel variants (RLCF_EXPERIMENTAL=1)")
 def test_layernorm_bwd_smem_variant_is_bit_identical(tmp_path):
-    """RLCF_LN_BWD_SMEM=1 (accumulators in shared memory, two blocks per SM) must reproduce the default kernel bit for
-    bit: same additions in the same order.  The switch is read once per process, hence two subprocesses."""
+    """The default LayerNorm backward (accumulators in shared memory, two blocks per SM) must reproduce the register
+    variant (RLCF_LN_BWD_SMEM=0) bit for bit: same additions in the same order.  The switch is read once per process,
+    hence two subprocesses."""
     import subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []

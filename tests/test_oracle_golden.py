@@ -12,7 +12,7 @@ from oracle import rlcf_oracle as O
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 POLICY_SEED, REWARD_SEED, VIEW_SEED, TOKEN_SEED = 0, 1, 11, 7
 FAST = ["tiny_rlcf_1step", "tiny_rlcf_3step_amplify", "tiny_rlcf_process_batch", "b32_cfg1_shape",
-        "tiny_rlcf_multi_reward", "tiny_rlcf_multi_reward_mean", "tiny_rlcf_reward_resize"]
+        "tiny_rlcf_multi_reward", "tiny_rlcf_multi_reward_mean", "tiny_rlcf_reward_resize", "tiny_rlcf_min_entropy"]
 SLOW = ["b16_l14_cfg2", "b16_l14_cfg2_2img", "b16_l14_cfg3_3step"]   # full config-2 / config-3 sizes (ViT-B/16 + ViT-L/14)
 FULL = ["tiny_full_tune_2step", "b32_full_tune_3step"]                # only_norm=False (custom_clip.py:477-479)
 
@@ -43,7 +43,8 @@ def oracle_setup(cfg):
                           process_batch=bool(cfg.get("process_batch", 0)),
                           reward_amplify=bool(cfg.get("reward_amplify", 0)),
                           reward_weights=tuple(O.ensemble_weights(cfg["confidences"])) if multi else (),
-                          weighted_scores=bool(cfg.get("weighted_scores", 1)))
+                          weighted_scores=bool(cfg.get("weighted_scores", 1)),
+                          min_entropy_w=float(cfg.get("min_entropy_w", 0.0)))
     return sd_p, sd_r, tok_p, tok_r, views, ocfg
 
 

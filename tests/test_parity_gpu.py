@@ -62,7 +62,8 @@ def build_engine(cfg, n_img, loss="rlcf", cuda_text=False):
     rcfg = E.RlcfConfig(n_views=cfg["V"], selection_p=cfg["rho"], tta_steps=cfg["steps"], sample_k=cfg["K"],
                         lr=cfg["lr"], reward_process=bool(cfg.get("reward_process", 1)),
                         process_batch=bool(cfg.get("process_batch", 0)),
-                        reward_amplify=bool(cfg.get("reward_amplify", 0)), loss=loss, reward_weights=weights)
+                        reward_amplify=bool(cfg.get("reward_amplify", 0)), loss=loss, reward_weights=weights,
+                        min_entropy_w=float(cfg.get("min_entropy_w", 0.0)))
     eng = E.RlcfEngine(pol, cf, float(sd_p["logit_scale"].exp()), rcfg, n_img, reward=rew, reward_class_feat=rc)
     return eng, (sd_p, sd_r, tok_p, tok_r, cf, rc)
 
