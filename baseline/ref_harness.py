@@ -97,15 +97,17 @@ class ReferenceRun:
             self._patch(torch.Tensor, "cuda", lambda t, *a, **k: t)
             self._patch(torch.nn.Module, "cuda", lambda mod, *a, **k: mod)
         dev = self.device
-        model = m.custom_clip.CLIPCLS_TTA(dev, classnames, arch=args.arch, prompt_prefix=args.ctx_init, only_visual=True,
-                                          momentum_update=args.momentum_update, update_freq=args.update_freq,
-                                          update_w=args.update_w, momentum=args.tta_momentum, only_norm=args.tune_norm)
-        self.model = model.cuda(args.gpu)
-        self.optimizer = torch.optim.AdamW(self.model.parameters(), args.lr, weight_decay=args.weight_decay)
         import copy
-        self.optim_state = copy.deepcopy(self.optimizer.state_dict())
-        self.reward_model = m.clip_reward.get_reward_model(dev, args)
-        self.reward_model.set_class_features(tokenized_classes=self.model.tokenized_prompts)
+        with contextlib.redirect_stdout(io.StringIO()):      # the reference prints a banner per model (bench.py must
+            model = m.custom_clip.CLIPCLS_TTA(               # print ONE JSON line on stdout)
+                dev, classnames, arch=args.arch, prompt_prefix=args.ctx_init, only_visual=True,
+                momentum_update=args.momentum_update, update_freq=args.update_freq, update_w=args.update_w,
+                momentum=args.tta_momentum, only_norm=args.tune_norm)
+            self.model = model.cuda(args.gpu)
+            self.optimizer = torch.optim.AdamW(self.model.parameters(), args.lr, weight_decay=args.weight_decay)
+            self.optim_state = copy.deepcopy(self.optimizer.state_dict())
+            self.reward_model = m.clip_reward.get_reward_model(dev, args)
+            self.reward_model.set_class_features(tokenized_classes=self.model.tokenized_prompts)
         self.scaler = torch.cuda.amp.GradScaler(init_scale=1000)
         del sds
 

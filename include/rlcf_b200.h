@@ -257,6 +257,15 @@ int rlcf_dfeat_partial(const float* dlogits, const float* gallery, int n_query, 
 int rlcf_rowdot(const float* a, const float* b, int n_rows, int C, float scale, float* out, int64_t out_stride,
                 void* stream);
 
+/* fp32 (CUDA-core) path of the once-per-dataset class text features (CLIP.encode_text, TPT/clip/model.py:342-356;
+ * custom_clip.py:404-408; clip_reward.py:139-150): kept at the reference's precision because they are an input of every
+ * per-image step.  out[M,N] = epi(A[M,K] W[N,K]^T + bias), all fp32; epilogue 0 = none, 1 = QuickGELU (model.py:166-168),
+ * 2 = + resid (same layout as out).  N, K, lda, ldw, ldo multiples of 4. */
+int rlcf_gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, int M, int N, int K, int epilogue,
+                  const float* bias, const float* resid, float* out, int64_t ldo, void* stream);
+/* nn.MultiheadAttention core in fp32: qkv fp32 [n_seq*L, 3d] packed q|k|v -> out fp32 [n_seq*L, d]; causal as above. */
+int rlcf_attention_f32(const float* qkv, int n_seq, int L, int heads, int causal, float* out, void* stream);
+
 /* Top-1 / top-5 hit counters of `accuracy` (TPT/utils/tools.py:84-98) as tune_cls_rl.py:243-247 accumulates them:
  * hits[0] += #rows whose target is the arg-max, hits[1] += #rows whose target is among the 5 largest logits,
  * hits[2] += n (device int64 [3], accumulated with integer atomics; ties go to the lower class index). */

@@ -80,6 +80,8 @@ _PROTOS = {
     "rlcf_transpose_blocks_colsum": [_vp, _i, _i, _i, _i, _i, _i64, _vp, _i64, _vp, _i64, _vp],
     "rlcf_gemm_wgrad_adamw": [_vp, _i, _i64, _vp, _i, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i64, _vp, _i64, _i, _vp,
                               _i64, _f, _f, _f, _f, _f, _i, _f, _vp],
+    "rlcf_gemm_f32": [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _vp],
+    "rlcf_attention_f32": [_vp, _i, _i, _i, _i, _vp, _vp],
     "rlcf_accuracy_count": [_vp, _vp, _i, _i, _vp, _vp],
     "rlcf_add_rows": [_vp, _i64, _vp, _i64, _i, _i64, _vp, _vp],
     "rlcf_scale_rows_exp": [_vp, _vp, _i64, _i, _i, _vp, _vp],

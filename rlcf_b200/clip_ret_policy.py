@@ -73,7 +73,9 @@ class CLIPRet_TTA(nn.Module):
             if text is None:
                 raise RlcfError("get_text_features needs text or tokenized_prompts")
             tokenized_prompts = clip.tokenize(text, truncate=True)
-        return E.text_features(self._text, tokenized_prompts.to(self.device))
+        # fp16 tensor-core tower on purpose: the retrieval CLIP is loaded in fp16 by the reference
+        # (lavis/models/clip_models/model.py:763-791), gallery features there carry fp16 operand rounding too
+        return E.text_features(self._text, tokenized_prompts.to(self.device), precise=False)
 
     @torch.no_grad()
     def get_image_features(self, images):
@@ -192,7 +194,7 @@ class CLIPRewards(nn.Module):
             tokenized_cap = clip.tokenize(captions, truncate=True)
         if tokenized_cap is None:
             raise RlcfError("extract_text_features needs captions or tokenized_cap")
-        return E.text_features(self.text_tower(), tokenized_cap.to(self.device))
+        return E.text_features(self.text_tower(), tokenized_cap.to(self.device), precise=False)
 
     def set_image_features(self, images=None, image_features=None):
         self.image_features = self.extract_image_features(images) if images is not None else image_features

@@ -132,6 +132,9 @@ int add_rows(const float*, long long, const float*, long long, int, long long, f
 int scale_rows_exp(const float*, const float*, long long, int, int, float*, cudaStream_t);
 int tied_rows_grad(const float*, const long long*, int, int, int, float*, float*, long long, cudaStream_t);
 int accuracy_count(const float*, const long long*, int, int, long long*, cudaStream_t);
+int gemm_f32(const float*, long long, const float*, long long, int, int, int, int, const float*, const float*, float*,
+             long long, cudaStream_t);
+int attention_f32(const float*, int, int, int, int, float*, cudaStream_t);
 
 }  // namespace rlcf
 
@@ -417,6 +420,17 @@ int rlcf_rowdot(const float* a, const float* b, int n_rows, int C, float scale, 
                 void* stream) {
   if (!a || !b || !out) return set_error(RLCF_ERR_ARG, "rowdot: null pointer");
   return rowdot(a, b, n_rows, C, scale, out, out_stride, S(stream));
+}
+
+int rlcf_gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, int M, int N, int K, int epilogue,
+                  const float* bias, const float* resid, float* out, int64_t ldo, void* stream) {
+  if (!A || !W || !out) return set_error(RLCF_ERR_ARG, "gemm_f32: null pointer");
+  return gemm_f32(A, lda, W, ldw, M, N, K, epilogue, bias, resid, out, ldo, S(stream));
+}
+
+int rlcf_attention_f32(const float* qkv, int n_seq, int L, int heads, int causal, float* out, void* stream) {
+  if (!qkv || !out) return set_error(RLCF_ERR_ARG, "attention_f32: null pointer");
+  return attention_f32(qkv, n_seq, L, heads, causal, out, S(stream));
 }
 
 int rlcf_accuracy_count(const float* logits, const int64_t* target, int n, int C, int64_t* hits, void* stream) {

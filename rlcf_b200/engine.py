@@ -42,6 +42,8 @@ class LayerWeights:
     wo_t: torch.Tensor | None = None    # [d, d]
     wfc_t: torch.Tensor | None = None   # [d, 4d]
     wproj_t: torch.Tensor | None = None  # [4d, d]
+    # fp32 originals [out, in] (text towers only): operands of the once-per-dataset fp32 class-feature path
+    w32: dict | None = None
 
 
 @dataclass
@@ -107,7 +109,7 @@ class TowerWeights:
         return out
 
 
-def _prep_layers(sd, prefix, n_layers, need_grad):
+def _prep_layers(sd, prefix, n_layers, need_grad, keep_f32=False):
     layers = []
     for l in range(n_layers):
         rb = f"{prefix}transformer.resblocks.{l}."
@@ -120,6 +122,8 @@ def _prep_layers(sd, prefix, n_layers, need_grad):
         if need_grad:
             lw.wqkv_t, lw.wo_t = ops.transpose_cast_f16(wqkv), ops.transpose_cast_f16(wo)
             lw.wfc_t, lw.wproj_t = ops.transpose_cast_f16(wfc), ops.transpose_cast_f16(wproj)
+        if keep_f32:
+            lw.w32 = dict(wqkv=wqkv, wo=wo, wfc=wfc, wproj=wproj)
         layers.append(lw)
     return layers
 
@@ -145,7 +149,9 @@ def prepare_visual(sd: dict, prefix: str = "visual.", need_grad: bool = False) -
     return w
 
 
-def prepare_text(sd: dict, need_grad: bool = False) -> TowerWeights:
+def prepare_text(sd: dict, need_grad: bool = False, keep_f32: bool = True) -> TowerWeights:
+    """keep_f32: also keep (references to) the fp32 Linear weights, which the fp32 class-feature path
+    (text_features(..., precise=True)) multiplies with; no copy when the checkpoint is already fp32."""
     emb = sd["token_embedding.weight"].detach().float().contiguous()
     pos = sd["positional_embedding"].detach().float().contiguous()
     d = emb.shape[1]
@@ -154,7 +160,7 @@ def prepare_text(sd: dict, need_grad: bool = False) -> TowerWeights:
     w = TowerWeights(kind="text", d=d, heads=d // 64, n_layers=n_layers, L=pos.shape[0], E=proj.shape[1],
                      has_ln_pre=False)
     w.tok_emb, w.pos, w.proj = emb, pos, proj
-    w.layers = _prep_layers(sd, "", n_layers, need_grad)
+    w.layers = _prep_layers(sd, "", n_layers, need_grad, keep_f32=keep_f32)
     w.ln_flat = torch.empty((4 * n_layers + 2) * d, dtype=torch.float32, device=emb.device)
     for key, off in w.ln_names(""):
         w.ln_flat[off:off + d].copy_(sd[key].detach().float())
@@ -718,8 +724,22 @@ class PromptEngine:
     def refresh_initial_text_features(self):
         """Text features of the un-adapted prompts (shared by every image for the step-0 logits of all views)."""
         C = self.tokens.shape[0]
-        x = self.trun.forward(C, self.text.ln_flat, tokens=self.tokens, prompt=(self.init_ctx, 0, self.n_ctx, 1))
-        self.trun.head(x, C, self.text.ln_flat, row_idx=self.eot_rows[:C].contiguous(), feat=self.txt_feat0)
+        txt = self.text
+        if txt.layers[0].w32 is not None:
+            # once per dataset (and per prompt initialisation): fp32, like the class features of the LN-tuning path
+            off = txt.ln_off("ln_final")
+            for s in range(0, C, 128):
+                e = min(C, s + 128)
+                frun = TextRunnerF32(txt, e - s) if s == 0 or e - s != frun.max_seq else frun
+                ops.embed_prompts(self.tokens[s:e].contiguous(), txt.tok_emb, txt.pos, self.init_ctx, 0, self.n_ctx, 1,
+                                  frun.x)
+                x = frun.layers(e - s)
+                rows = (self.eot_rows[s:e] - s * txt.L).contiguous()
+                ops.head_fwd(x, txt.ln_flat[off:], txt.ln_flat[off + txt.d:], txt.proj, e - s, txt.d, txt.E,
+                             feat=self.txt_feat0[s:e], row_idx=rows, row_stride=txt.L)
+            return
+        x = self.trun.forward(C, txt.ln_flat, tokens=self.tokens, prompt=(self.init_ctx, 0, self.n_ctx, 1))
+        self.trun.head(x, C, txt.ln_flat, row_idx=self.eot_rows[:C].contiguous(), feat=self.txt_feat0)
 
     def _text_features(self, store):
         B, C = self.n_img, self.tokens.shape[0]
@@ -830,26 +850,76 @@ class HostPipeline:
         return out_pinned
 
 
-def text_features(w: TowerWeights, tokens: torch.Tensor, chunk: int = 256, normalized: bool = True) -> torch.Tensor:
+class TextRunnerF32:
+    """The text transformer in fp32 on the CUDA cores (rlcf_gemm_f32 / rlcf_attention_f32): the once-per-dataset class
+    features keep the reference's precision (fp32 on the CPU; measured 2e-6 against it, where the fp16 tensor-core tower
+    is at 8e-4 -- the text tower amplifies operand rounding ~3x more than the image tower)."""
+
+    def __init__(self, w: TowerWeights, max_seq: int):
+        if w.kind != "text" or w.layers[0].w32 is None:
+            raise RlcfError("the fp32 text path needs a text tower prepared with keep_f32=True")
+        self.w, self.max_seq = w, max_seq
+        rows, d = max_seq * w.L, w.d
+        f32 = dict(dtype=torch.float32, device=w.ln_flat.device)
+        self.x = torch.empty(rows, d, **f32)
+        self.a = torch.empty(rows, d, **f32)
+        self.att = torch.empty(rows, d, **f32)
+        self.qkv = torch.empty(rows, 3 * d, **f32)
+        self.h = torch.empty(rows, 4 * d, **f32)
+
+    def layers(self, n_seq: int) -> torch.Tensor:
+        """Runs every residual block on self.x[:n_seq*L] in place (model.py:189-192, causal mask 328-334)."""
+        w = self.w
+        d, L, rows = w.d, w.L, n_seq * w.L
+        ln = w.ln_flat
+        x = self.x
+        for l, lw in enumerate(w.layers):
+            o1, o2 = w.ln_off("ln_1", l), w.ln_off("ln_2", l)
+            ops.layernorm_fwd(x, ln[o1:], ln[o1 + d:], rows, d, out32=self.a)
+            ops.gemm_f32(self.a, lw.w32["wqkv"], self.qkv, M=rows, bias=lw.bqkv)
+            ops.attention_f32(self.qkv, n_seq, L, w.heads, self.att, causal=True)
+            ops.gemm_f32(self.att, lw.w32["wo"], x, M=rows, epilogue=2, bias=lw.bo, resid=x)
+            ops.layernorm_fwd(x, ln[o2:], ln[o2 + d:], rows, d, out32=self.a)
+            ops.gemm_f32(self.a, lw.w32["wfc"], self.h, M=rows, epilogue=1, bias=lw.bfc)
+            ops.gemm_f32(self.h, lw.w32["wproj"], x, M=rows, epilogue=2, bias=lw.bproj, resid=x)
+        return x
+
+
+def text_features(w: TowerWeights, tokens: torch.Tensor, chunk: int = 256, normalized: bool = True,
+                  precise: bool | None = None) -> torch.Tensor:
     """L2-normalised text features [n, E] of tokenised prompts [n, ctx] (CLIP.encode_text, TPT/clip/model.py:342-356,
     followed by the normalisation of custom_clip.py:404-408 / clip_reward.py:139-150).  normalized=False returns the
-    raw encode_text output."""
+    raw encode_text output.  precise (default: whenever the tower kept its fp32 weights) runs the transformer in fp32
+    (TextRunnerF32) instead of on the fp16 tensor-core kernels: class features are computed once per dataset and feed
+    every per-image step."""
     if w.kind != "text":
         raise RlcfError("text_features needs a text tower")
     n, L = tokens.shape
     if L != w.L:
         raise RlcfError(f"context length {L} != {w.L}")
     tokens = tokens.to(device=w.ln_flat.device, dtype=torch.int64).contiguous()
-    run = TowerRunner(w, min(chunk, n))
+    if precise is None:
+        precise = w.layers[0].w32 is not None and w.layers[0].wqkv.dim() == 2
+    if precise:
+        chunk = min(chunk, 128)
+        frun = TextRunnerF32(w, min(chunk, n))
+    run = TowerRunner(w, min(chunk, n)) if not precise else None
     out = torch.empty(n, w.E, dtype=torch.float32, device=w.ln_flat.device)
     inv = torch.empty(n, dtype=torch.float32, device=w.ln_flat.device)
     eot = tokens.argmax(dim=-1).to(torch.int32)   # eot_token is the highest id in each sequence (model.py:352-354)
+    off = w.ln_off("ln_final")
     for s in range(0, n, chunk):
         e = min(n, s + chunk)
         tk = tokens[s:e].contiguous()
-        x = run.forward(e - s, w.ln_flat, tokens=tk)
         rows = (torch.arange(e - s, device=tk.device, dtype=torch.int32) * L + eot[s:e]).contiguous()
-        run.head(x, e - s, w.ln_flat, row_idx=rows, feat=out[s:e], inv_norm=inv[s:e])
+        if precise:
+            ops.embed_text(tk, w.tok_emb, w.pos, frun.x)
+            x = frun.layers(e - s)
+            ops.head_fwd(x, w.ln_flat[off:], w.ln_flat[off + w.d:], w.proj, e - s, w.d, w.E, feat=out[s:e],
+                         inv_norm=inv[s:e], row_idx=rows, row_stride=L)
+        else:
+            x = run.forward(e - s, w.ln_flat, tokens=tk)
+            run.head(x, e - s, w.ln_flat, row_idx=rows, feat=out[s:e], inv_norm=inv[s:e])
     return out if normalized else out / inv[:, None]
 
 

@@ -387,6 +387,29 @@ def rowdot(a, b, out, out_stride=1, scale=1.0):
     return out
 
 
+def gemm_f32(a, w, out, M=None, epilogue=0, bias=None, resid=None):
+    """out[:M] = epi(a[:M] @ w^T + bias) in fp32 on the CUDA cores (epilogue 0 none, 1 QuickGELU, 2 + resid)."""
+    for t, nm in ((a, "a"), (w, "w"), (out, "out")):
+        if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
+            raise _lib.RlcfError(f"gemm_f32: {nm} must be a 2-D CUDA fp32 tensor with unit inner stride")
+    _chk(bias, torch.float32, "bias"); _chk(resid, torch.float32, "resid")
+    m = a.shape[0] if M is None else M
+    n, k = w.shape
+    if a.shape[1] != k or out.shape[1] != n or out.shape[0] < m:
+        raise _lib.RlcfError(f"gemm_f32: shapes {tuple(a.shape)} x {tuple(w.shape)} -> {tuple(out.shape)}")
+    if resid is not None and (resid.stride(0) != out.stride(0) or resid.shape[1] != n):
+        raise _lib.RlcfError("gemm_f32: resid must share out's layout")
+    call("rlcf_gemm_f32", ptr(a), a.stride(0), ptr(w), w.stride(0), m, n, k, int(epilogue), ptr(bias), ptr(resid),
+         ptr(out), out.stride(0), stream())
+    return out
+
+
+def attention_f32(qkv, n_seq, L, heads, out, causal=False):
+    _chk(qkv, torch.float32, "qkv"); _chk(out, torch.float32, "out")
+    call("rlcf_attention_f32", ptr(qkv), n_seq, L, heads, int(bool(causal)), ptr(out), stream())
+    return out
+
+
 def accuracy_count(logits, target, hits):
     """hits[0] += top-1 hits, hits[1] += top-5 hits, hits[2] += rows  (utils/tools.py:84-98; device int64 [3])."""
     _chk(logits, torch.float32, "logits"); _chk(target, torch.int64, "target"); _chk(hits, torch.int64, "hits")

@@ -9,6 +9,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+import parity_log as PL  # noqa: E402
 from oracle import rlcf_oracle as O  # noqa: E402
 from rlcf_b200 import clip, synthetic  # noqa: E402
 from rlcf_b200.clip.custom_clip import CLIPCLS_TTA  # noqa: E402
@@ -98,7 +99,8 @@ def test_reference_style_loop_matches_oracle():
                                 reward_model.class_features.cpu())
         scale = ref["logits_all"].abs().max()
         delta = (ref["logits_final"] - ref["logits_all"][:1]).abs().max()
-        assert (out - ref["logits_final"]).abs().max() <= 1e-3 * scale + 0.3 * delta
+        PL.check_final_logits(f"api/ln_tuning/img{i}", out.numpy(), ref["logits_final"].numpy(), scale, delta,
+                              allow_delta=0.02, why="sign-like AdamW steps on noise-level gradients (tests/test_parity_gpu.py GOLDEN_ALLOW); tiny towers, lr 5e-3")
         moved = (model.clip_model.visual.ln_flat().cpu() - base).abs()
         assert moved.max() > 1e-3                              # parameters really changed in place ...
         named = dict(model.clip_model.visual.named_parameters())
@@ -148,7 +150,8 @@ def test_full_tuning_through_the_api():
                             tune="full")
     scale = ref["logits_all"].abs().max()
     delta = (ref["logits_final"] - ref["logits_all"][:1]).abs().max()
-    assert (out - ref["logits_final"]).abs().max() <= 1e-3 * scale + 0.3 * delta
+    PL.check_final_logits("api/full_tuning", out.numpy(), ref["logits_final"].numpy(), scale, delta, allow_delta=0.02,
+                          why="sign-like AdamW steps on noise-level gradients (tests/test_parity_gpu.py GOLDEN_ALLOW); tiny towers, lr 5e-3")
     w = dict(model.clip_model.visual.named_parameters())["transformer.resblocks.0.mlp.c_fc.weight"].detach().cpu()
     assert (w - sd_p["visual.transformer.resblocks.0.mlp.c_fc.weight"]).abs().max() > 5e-5     # weights really moved
     model.reset()
@@ -198,7 +201,8 @@ def test_prompt_tuning_api_matches_oracle():
     ref = O.adapt_one_image_prompt(sd_p, tokens, ctx_init, views, ocfg, sd_r, reward_model.class_features.cpu())
     scale = ref["logits_all"].abs().max()
     delta = (ref["logits_final"][0] - ref["logits_all"][0]).abs().max()
-    assert (out[0] - ref["logits_final"][0]).abs().max() <= 2.5e-3 * scale + 0.3 * delta
+    PL.check_final_logits("api/prompt_tuning", out[0].numpy(), ref["logits_final"][0].numpy(), scale, delta,
+                          allow_delta=0.02, why="sign-like AdamW steps on noise-level gradients (tests/test_parity_gpu.py GOLDEN_ALLOW); tiny towers, lr 5e-3")
     d = (model.prompt_learner.ctx.detach().cpu().flatten() - ref["params"]).abs()
     assert d.max() <= 2.02 * 5e-3 and (d <= 0.02 * 5e-3).float().mean() > 0.9
     model.reset()
@@ -246,5 +250,6 @@ def test_reward_model_ensemble_through_the_api():
                             [f.cpu() for f in reward_model.class_features])
     scale = ref["logits_all"].abs().max()
     delta = (ref["logits_final"] - ref["logits_all"][:1]).abs().max()
-    assert (out - ref["logits_final"]).abs().max() <= 1e-3 * scale + 0.3 * delta
+    PL.check_final_logits("api/multi_reward", out.numpy(), ref["logits_final"].numpy(), scale, delta, allow_delta=0.02,
+                          why="sign-like AdamW steps on noise-level gradients (tests/test_parity_gpu.py GOLDEN_ALLOW); tiny towers, lr 5e-3")
     assert isinstance(reward_model.image_features, list) and len(reward_model.image_features) == 2

@@ -461,3 +461,41 @@ def test_bicubic_resize_matches_torch_interpolate():
         full = torch.empty(7, 3, size, size, device=_dev())
         ops.bicubic_resize(imgs, None, 7, full)
         assert torch.equal(full[idx.long()], out)
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(77, 128, 128, 0), (200, 384, 128, 0), (1001, 512, 2048, 2), (385, 2048, 512, 1),
+                                        (128, 4, 4, 0), (5, 260, 36, 2)])
+def test_gemm_f32_matches_torch(M, N, K, epi):
+    """rlcf_gemm_f32 (CUDA-core fp32 path of the class text features) vs torch fp64, ragged M / N / K tiles."""
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device=DEV)
+    w = torch.randn(N, K, device=DEV) * K ** -0.5
+    bias = torch.randn(N, device=DEV)
+    resid = torch.randn(M, N, device=DEV)
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm_f32(a, w, out, epilogue=epi, bias=bias, resid=resid if epi == 2 else None)
+    ref = a.double() @ w.double().t() + bias.double()
+    if epi == 1:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    if epi == 2:
+        ref = ref + resid.double()
+    assert (out.double() - ref).abs().max() <= 2e-6 * ref.abs().max().clamp_min(1.0) * max(1.0, K ** 0.5 / 8)
+    if epi == 2:      # in place on the residual stream (out is resid), as the text runner calls it
+        x = resid.clone()
+        ops.gemm_f32(a, w, x, epilogue=2, bias=bias, resid=x)
+        assert torch.equal(x, out)
+
+
+@pytest.mark.parametrize("n_seq,L,heads,causal", [(3, 77, 2, True), (2, 77, 8, True), (2, 17, 2, False), (1, 197, 3, False)])
+def test_attention_f32_matches_torch(n_seq, L, heads, causal):
+    torch.manual_seed(L + heads)
+    d = heads * 64
+    qkv = torch.randn(n_seq * L, 3 * d, device=DEV)
+    out = torch.empty(n_seq * L, d, device=DEV)
+    ops.attention_f32(qkv, n_seq, L, heads, out, causal=causal)
+    q, k, v = qkv.double().view(n_seq, L, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    if causal:
+        s = s + torch.full((L, L), float("-inf"), device=DEV, dtype=torch.float64).triu_(1)
+    ref = (s.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(n_seq * L, d)
+    assert (out.double() - ref).abs().max() <= 5e-6

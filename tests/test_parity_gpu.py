@@ -160,9 +160,23 @@ def golden_cases():
             and not f.startswith(("ret_", "agree_")) and "full_tune" not in f and "cfg1_exact" not in f]
 
 
-# Cases whose direct final-logit comparison keeps an adaptation-proportional allowance, each with its measured reason
-# (profiles/r2_parity.json).  Everything else is held to 1e-3 * max|logit| directly.
-GOLDEN_ALLOW: dict = {}
+# Cases whose DIRECT final-logit comparison keeps an adaptation-proportional allowance -- 2 % of what adaptation changed
+# (round 1 allowed 30 % everywhere) -- each with its measured numbers from the first round-2 GPU run (gpurun_out /
+# profiles/r2_parity.json).  Every other case is held to 1e-3 * max|logit| directly, and ALL cases are additionally held
+# to 1e-3 for the forward at identical parameters.  Why an allowance exists at all: AdamW's first steps are sign-like
+# (p -= lr * g / (|g| + 1e-8)), so a LayerNorm entry whose gradient is rounding noise moves +lr in one implementation
+# and -lr in the other -- in ANY two implementations, the reference on CPU vs the reference on GPU included; a handful
+# of such entries (<= 0.2 % of them, see */params records) shift the adapted logits by a small fraction of delta.
+def _flip(err, delta):
+    return dict(allow_delta=0.02, why=f"sign-like AdamW steps on noise-level gradients: measured direct error {err:.2e} "
+                                      f"of max|logit| while adaptation moved the logits by {delta:.2e} of it")
+
+
+GOLDEN_ALLOW: dict = {
+    "b16_l14_cfg2_2img": _flip(1.09e-3, 0.302),
+    "tiny_rlcf_min_entropy": _flip(1.43e-3, 0.259),
+    "tiny_rlcf_reward_resize": _flip(1.65e-3, 0.115),
+}
 
 
 @pytest.mark.parametrize("name", golden_cases())
@@ -188,7 +202,8 @@ def test_cuda_matches_reference_golden(name):
 
 
 @pytest.mark.parametrize("cfg", [
-    dict(policy="tiny-A", reward="tiny-B", V=16, rho=0.25, K=3, C=10, steps=2, lr=5e-3, n_img=3),
+    dict(policy="tiny-A", reward="tiny-B", V=16, rho=0.25, K=3, C=10, steps=2, lr=5e-3, n_img=3,
+         allow=_flip(4.05e-3, 0.246)),
     dict(policy="tiny-B", reward="tiny-A", V=8, rho=0.5, K=2, C=37, steps=1, lr=1e-3, n_img=2, reward_amplify=1),
     dict(policy="ViT-B/32", reward="ViT-B/32", V=8, rho=0.5, K=3, C=200, steps=1, lr=5e-3, n_img=2),
 ], ids=["tinyA-3img-2step", "tinyB-amplify", "b32-2img"])
@@ -212,7 +227,8 @@ def test_cuda_matches_oracle_batched(cfg):
     torch.cuda.synchronize()
     eager = eng.logits_final.clone()
     for i in range(cfg["n_img"]):
-        check_image(eng, i, refs[i], cfg, f"batched-{cfg['policy']}-{cfg['n_img']}img-{cfg['steps']}step/img{i}")
+        check_image(eng, i, refs[i], cfg, f"batched-{cfg['policy']}-{cfg['n_img']}img-{cfg['steps']}step/img{i}",
+                    **cfg.get("allow", {}))
     if cfg["steps"] == 1:
         # gradient of the LayerNorm slice vs autograd (relative to its largest entry)
         for i in range(cfg["n_img"]):
@@ -235,8 +251,14 @@ def test_text_and_image_towers_match_oracle():
         tok[0, 1:76] = 5
         tok[0, 76] = O.ARCHS[arch][6] - 1      # a prompt that fills the whole context (EOT in the last slot)
         ref_t = O.class_features(sd, tok)
-        got_t = E.text_features(E.prepare_text(to_dev(sd)), tok)
-        assert (got_t.cpu() - ref_t).abs().max() < 2e-3
+        tw = E.prepare_text(to_dev(sd))
+        got_t = E.text_features(tw, tok)                       # default: the fp32 class-feature path
+        err32 = (got_t.cpu() - ref_t).abs().max().item()
+        err16 = (E.text_features(tw, tok, precise=False).cpu() - ref_t).abs().max().item()
+        PL.record(f"text_features/{arch}", fp32_path_max_abs_err=err32, fp16_tensor_core_path_max_abs_err=err16,
+                  feature_rms=float(ref_t.pow(2).mean().sqrt()))
+        assert err32 < 2e-5, f"{arch}: fp32 class features differ from the oracle by {err32:.2e}"
+        assert err16 < 2e-3
         img = O.make_views(1, 5, O.ARCHS[arch][1], 5)
         with torch.no_grad():
             f = O.encode_image(sd, img)
@@ -246,18 +268,22 @@ def test_text_and_image_towers_match_oracle():
 
 
 def test_end_to_end_with_cuda_text_features():
-    """Drop-in behaviour including the once-per-dataset class features from the CUDA text tower.  The text tower
-    (width 512, L=77) is ~3x more sensitive to fp16 operand rounding than the image tower (measured feature error
-    8e-4 vs 3e-4, identical in a CPU emulation of the same roundings), so the logit bound here is 2.5e-3."""
+    """Drop-in behaviour including the once-per-dataset class features from the CUDA text tower (fp32 path,
+    engine.TextRunnerF32): same 1e-3 bound on the adapted logits as with the oracle's class features."""
     z = np.load(os.path.join(GOLDEN, "b32_cfg1_shape.npz"))
     cfg = ast.literal_eval(str(z["meta"]))
     eng, (_, _, _, _, cf, rc) = build_engine(cfg, 1, cuda_text=True)
-    assert np.abs(cf.cpu().numpy() - z["class_feat"]).max() < 2e-3
+    assert np.abs(cf.cpu().numpy() - z["class_feat"]).max() < 2e-5
+    assert np.abs(rc.cpu().numpy() - z["reward_cls"]).max() < 2e-5
     views = O.make_views(1, cfg["V"], 224, VIEW_SEED).to(DEV)
     eng.adapt(views)
     scale = np.abs(z["img0.logits_all"]).max()
-    assert np.abs(eng.logits_all.cpu().numpy() - z["img0.logits_all"]).max() <= 2.5e-3 * scale
-    assert np.abs(eng.logits_final.cpu().numpy() - z["img0.logits_final"]).max() <= 2.5e-3 * scale
+    e0 = np.abs(eng.logits_all.cpu().numpy() - z["img0.logits_all"]).max()
+    delta = np.abs(z["img0.logits_final"][0] - z["img0.logits_all"][0]).max()
+    PL.record("cuda_text_end_to_end/step0", logits_all_max_err_rel=e0 / scale)
+    assert e0 <= LOGIT_TOL_ALL * scale
+    PL.check_final_logits("cuda_text_end_to_end/final", eng.logits_final.cpu().numpy()[0], z["img0.logits_final"][0],
+                          scale, delta, tol=LOGIT_TOL)
 
 
 def test_tpt_entropy_loss_path():
@@ -308,14 +334,18 @@ def test_prompt_tuning_matches_reference_golden_and_oracle():
     ocfg = O.OracleConfig(n_views=V, selection_p=cfg["rho"], tta_steps=1, sample_k=cfg["K"], lr=cfg["lr"])
     for i in range(cfg["n_img"]):
         scale = np.abs(z[f"img{i}.logits_all"]).max()
-        # the text tower is ~3x more sensitive to fp16 operand rounding than the image tower
-        assert np.abs(eng.logits_all[i * V:(i + 1) * V].cpu().numpy() - z[f"img{i}.logits_all"]).max() <= 2.5e-3 * scale
+        # step-0 text features come from the fp32 path (computed once per dataset): image-tower tolerance applies
+        e0 = np.abs(eng.logits_all[i * V:(i + 1) * V].cpu().numpy() - z[f"img{i}.logits_all"]).max()
+        PL.record(f"tiny_prompt_rlcf_2step/img{i}/step0", logits_all_max_err_rel=e0 / scale)
+        assert e0 <= LOGIT_TOL_ALL * scale
         assert np.array_equal(eng.sel[i].cpu().numpy(), z[f"img{i}.selected_idx"])
         assert np.array_equal(eng.topk_idx[i * S:(i + 1) * S].cpu().numpy(), z[f"img{i}.topk_idx"][-1])
         rw = z[f"img{i}.rewards"][-1]
         assert np.abs(eng.rewards[i * S:(i + 1) * S].cpu().numpy() - rw).max() <= 2e-3 * max(1.0, np.abs(rw).max())
         delta = np.abs(z[f"img{i}.logits_final"][0] - z[f"img{i}.logits_all"][0]).max()
-        assert np.abs(out[i].numpy() - z[f"img{i}.logits_final"][0]).max() <= 2.5e-3 * scale + 0.3 * delta
+        PL.check_final_logits(f"tiny_prompt_rlcf_2step/img{i}/final", out[i].numpy(), z[f"img{i}.logits_final"][0], scale,
+                              delta, tol=LOGIT_TOL, allow_delta=0.02, why="prompt tuning on tiny towers, lr 5e-3 on "
+                              "context entries of magnitude 0.02: sign-like AdamW steps (see GOLDEN_ALLOW)")
         check_params(eng.ctx[i].cpu().numpy(), z[f"img{i}.params"], None, cfg["lr"], cfg["steps"], f"prompt/img{i}")
     # one-step gradient of the context vectors against autograd
     eng1, *_ = _prompt_engine(dict(cfg, steps=1), tokens, ctx_init, cfg["n_img"])
@@ -341,7 +371,8 @@ def test_prompt_tuning_tpt_entropy_config1_shape():
         assert abs(eng.loss[0, i].item() - o["losses"][0]) < 3e-3 * max(1.0, abs(o["losses"][0]))
         scale = o["logits_all"].abs().max()
         delta = (o["logits_final"][0] - o["logits_all"][0]).abs().max()
-        assert (out[i] - o["logits_final"][0]).abs().max() <= 2.5e-3 * scale + 0.3 * delta
+        PL.check_final_logits(f"tpt-prompt/img{i}/final", out[i].numpy(), o["logits_final"][0].numpy(), scale, delta,
+                              tol=LOGIT_TOL, allow_delta=0.02, why="prompt tuning on tiny towers (see GOLDEN_ALLOW)")
         check_params(eng.ctx[i].cpu().numpy(), o["params"].numpy(), o["grads"], 5e-3, 1, f"tpt-prompt/img{i}")
 
 
@@ -394,8 +425,8 @@ def test_full_encoder_tuning_matches_oracle(steps):
         scale = o["logits_all"].abs().max()
         delta = (o["logits_final"][0] - o["logits_all"][0]).abs().max()
         err = (out[i] - o["logits_final"][0]).abs().max()
-        print(f"full/{steps} img{i}: final logits err {err / scale:.2e} (adaptation delta {delta / scale:.2e})")
-        assert err <= LOGIT_TOL * scale + 0.3 * delta
+        PL.check_final_logits(f"full-oracle-{steps}step/img{i}/final", out[i].numpy(), o["logits_final"][0].numpy(), scale,
+                              delta, tol=LOGIT_TOL, allow_delta=0.02, why="full tuning, tiny towers (see GOLDEN_ALLOW)")
         got = eng.export_params(i)
         if steps == 1:
             # one-step gradients of every parameter tensor against autograd (relative to the tensor's largest entry)
@@ -427,11 +458,12 @@ def test_full_encoder_tuning_matches_oracle(steps):
     dict(K=1),                                  # a single sampled class: rewards are returned unprocessed (clip_reward.py:157)
     dict(K=4, reward_process=0),                # raw CLIPScores as rewards (no baseline): dlogits keeps its softmax term
     dict(V=5, rho=0.4, C=1000, K=5),            # odd view count, 2 selected views, ImageNet-sized label space, default K
-    dict(V=3, rho=1.0, K=2, steps=3),           # every view selected, several steps
+    dict(V=3, rho=1.0, K=2, steps=3, allow=_flip(1.43e-3, 0.348)),   # every view selected, several steps
 ], ids=["K1", "raw-rewards", "odd-views-C1000", "all-selected-3step"])
 def test_edge_configurations_match_oracle(kw):
     cfg = dict(policy="tiny-A", reward="tiny-B", V=16, rho=0.25, K=3, C=10, steps=1, lr=5e-3, n_img=2)
     cfg.update(kw)
+    allow = cfg.pop("allow", {})
     eng, (sd_p, sd_r, tok_p, tok_r, cf, rc) = build_engine(cfg, cfg["n_img"])
     V = cfg["V"]
     views = O.make_views(cfg["n_img"], V, 64, VIEW_SEED + 7)
@@ -443,7 +475,8 @@ def test_edge_configurations_match_oracle(kw):
         ref = dict(logits_all=o["logits_all"].numpy(), selected_idx=o["selected_idx"].numpy(),
                    topk_idx=torch.stack(o["topk_idx"]).numpy(), rewards=torch.stack(o["rewards"]).numpy(),
                    logits_final=o["logits_final"].numpy(), params=o["params"].numpy(), grads=o["grads"])
-        check_image(eng, i, ref, cfg, f"edge/img{i}", sd_p, cf.cpu(), views[i * V:i * V + 1])
+        check_image(eng, i, ref, cfg, f"edge-V{V}-K{cfg['K']}-C{cfg['C']}-{cfg['steps']}step/img{i}", sd_p, cf.cpu(),
+                    views[i * V:i * V + 1], **allow)
 
 
 def test_bad_inputs_are_rejected():
@@ -502,7 +535,8 @@ def test_full_encoder_tuning_matches_reference_golden(name):
         rw = z[f"img{i}.rewards"][-1]
         assert np.abs(eng.rewards[i * S:(i + 1) * S].cpu().numpy() - rw).max() <= 2e-3 * max(1.0, np.abs(rw).max())
         delta = np.abs(z[f"img{i}.logits_final"][0] - la[0]).max()
-        PL.check_final_logits(tag + "/final", out[i], z[f"img{i}.logits_final"][0], scale, delta, tol=LOGIT_TOL)
+        PL.check_final_logits(tag + "/final", out[i], z[f"img{i}.logits_final"][0], scale, delta, tol=LOGIT_TOL,
+                              **FULL_ALLOW.get(name, {}))
         assert out[i].argmax() == z[f"img{i}.logits_final"][0].argmax()
         got = eng.export_params(i)
         fracs = []
@@ -513,6 +547,11 @@ def test_full_encoder_tuning_matches_reference_golden(name):
         PL.record(tag + "/params", tensors=len(fracs), min_frac_within_5pct_of_a_step=min(fracs),
                   mean_frac_within_5pct_of_a_step=float(np.mean(fracs)))
         assert np.mean(fracs) >= 0.90, f"{tag}: only {100 * np.mean(fracs):.1f}% of entries within 5% of a step"
+
+
+FULL_ALLOW = {   # three steps at lr 1e-5 over 86 M parameters move the logits by 2.3x their own scale
+    "b32_full_tune_3step": _flip(2.00e-3, 2.32),
+}
 
 
 def _prompt_golden(name, loss):
@@ -565,7 +604,9 @@ def test_prompt_tuning_at_vit_b32_matches_reference_golden(name, loss):
         assert frac >= 0.90, f"{tag}: only {100 * frac:.1f}% of the context entries within 5% of a step"
 
 
-PROMPT_ALLOW: dict = {}
+PROMPT_ALLOW = {   # lr 5e-3 on context entries of magnitude 0.02 (token-embedding scale): each step moves an entry by 25 %
+    "b32_cfg1_exact": _flip(1.10e-2, 1.04),
+}
 
 
 def test_top1_agreement_over_image_stream():
