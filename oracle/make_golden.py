@@ -70,15 +70,18 @@ AGREE_CASES = {
 }
 PROMPT_CASES = {
     # prompt tuning (TPT/tpt_cls_rl.py + ClipTestTimeTuning): real BPE tokenizer, ctx_init "a_photo_of_a" (4 tokens)
+    # reward seeds: chosen so that the CLIPScores of the sampled classes are POSITIVE (with seed 1 every cosine is
+    # negative, every score is clipped to 0, all rewards vanish and nothing is adapted -- the round-1 fixture was that
+    # degenerate case)
     "tiny_prompt_rlcf_2step": dict(policy="tiny-P", reward="tiny-Q", V=16, rho=0.25, K=3, C=12, steps=2, lr=5e-3,
-                                   n_img=2, ctx_init="a_photo_of_a", loss="rlcf"),
+                                   n_img=2, ctx_init="a_photo_of_a", loss="rlcf", reward_seed=6),
     # BASELINE.json configs[0] exactly: ViT-B/32, get_coop's model, TPT entropy loss of
     # TPT/tpt_cls.py:49-78, 8 views, selection_p 0.5, 4 images, C = 32 synthetic class names "class i", lr 5e-3, 1 step
     "b32_cfg1_exact": dict(policy="ViT-B/32", reward=None, V=8, rho=0.5, K=3, C=32, steps=1, lr=5e-3, n_img=4,
                            ctx_init="a_photo_of_a", loss="tpt", classnames="class_i", policy_seed=2, view_seed=1),
     # prompt-mode RLCF at the real text-tower size (width 512, 12 layers, 8 heads): VERDICT r1 item 6
     "b32_prompt_rlcf": dict(policy="ViT-B/32", reward="ViT-B/32", V=8, rho=0.5, K=3, C=16, steps=1, lr=5e-3, n_img=2,
-                            ctx_init="a_photo_of_a", loss="rlcf", reward_seed=3, view_seed=16),
+                            ctx_init="a_photo_of_a", loss="rlcf", reward_seed=4, view_seed=16),
 }
 POLICY_SEED, REWARD_SEED, VIEW_SEED, TOKEN_SEED = 0, 1, 11, 7
 CLASSNAMES = ["tench", "goldfish", "great white shark", "tiger shark", "hammerhead", "electric ray", "stingray",

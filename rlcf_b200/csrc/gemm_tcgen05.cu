@@ -55,6 +55,7 @@ struct GemmArgs {
   int ldo;               // leading dimension of out / resid / aux (elements)
   float alpha;           // scale applied to the accumulator before the epilogue
   int debug_nostore;     // RLCF_GEMM_DEBUG_NOSTORE=1: skip the epilogue's global traffic (timing probe only)
+  int resid_prefetch;    // EPI_RESID_F32: the producer prefetches each tile's residual rows into L2 (RLCF_GEMM_RESID_PREFETCH=1; slower)
   AdamwEpi opt;          // EPI_ADAMW only
 };
 
@@ -129,7 +130,28 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int m_blk = tg / n_tiles, n_blk = tg % n_tiles;
         const int m0 = m_blk * tile_m + static_cast<int>(pair) * kBM * kCtaGroup + static_cast<int>(cta_rank) * kBM;
         const int n0 = n_blk * kBN + static_cast<int>(cta_rank) * Cfg::kBRows;
+        // EPI_RESID_F32, opt-in experiment (RLCF_GEMM_RESID_PREFETCH=1): the epilogue of this tile reads 128 rows x 1 KB
+        // of the fp32 residual stream, 4 KB per warp at a time with a DRAM round trip in front of every chunk.  Here the
+        // producer asks L2 for those rows while it streams the operands (one 1 KB cp.async.bulk.prefetch.L2 per row, spread
+        // over the first half of the K loop).  MEASURED SLOWER and therefore off by default: out_proj 635 -> 716 us,
+        // c_proj 1462 -> 1782 us at M = 403 456 (profiles/r2_gemm_resid_prefetch.txt) -- the K = 768 main loop is already
+        // L2-bandwidth-bound, and the prefetched lines compete with the operand tiles for it.
+        int pf_row = 0, pf_rows = 0, pf_per_kb = 0;
+        uint32_t pf_bytes = 0;
+        const float* pf_base = nullptr;
+        if constexpr (kEpi == EPI_RESID_F32) {
+          if (p.resid_prefetch && m0 < p.M) {
+            pf_rows = min(kBM, p.M - m0);
+            pf_bytes = static_cast<uint32_t>(min(kBN, p.N - n_blk * kBN)) * 4u;
+            pf_per_kb = (kBM + max(1, num_kb / 2) - 1) / max(1, num_kb / 2);
+            pf_base = p.resid + static_cast<size_t>(g * p.out_gs) + static_cast<size_t>(m0) * p.ldo + n_blk * kBN;
+          }
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
+          if constexpr (kEpi == EPI_RESID_F32) {
+            const int pf_end = min(pf_rows, pf_row + pf_per_kb);
+            for (; pf_row < pf_end; ++pf_row) l2_prefetch_bulk(pf_base + static_cast<size_t>(pf_row) * p.ldo, pf_bytes);
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
@@ -491,8 +513,11 @@ int gemm_f16_grouped(const __half* A, int lda, long long a_gs, const __half* B, 
   if (int rc = make_tmap_f16(&ta, A, M, K, lda, G, a_gs, kBM)) return rc;
   if (int rc = make_tmap_f16(&tb, B, N, K, ldb, G, b_gs, kBN / cg)) return rc;
   static const int debug_nostore = getenv("RLCF_GEMM_DEBUG_NOSTORE") != nullptr;
+  static const int resid_prefetch = getenv("RLCF_GEMM_RESID_PREFETCH") != nullptr && atoi(getenv("RLCF_GEMM_RESID_PREFETCH")) != 0;
+  // bulk prefetches need 16-byte aligned rows: resid rows are ldo floats apart (ldo % 8 == 0) from a 16-byte aligned base
+  const int pf = resid_prefetch && epi == EPI_RESID_F32 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0;
   GemmArgs args{M, N, K, G, G > 1 ? out_gs : 0, G > 1 ? bias_gs : 0, epi, bias, resid, aux_in, aux_out, out, ldo,
-                alpha, debug_nostore, adamw != nullptr ? *adamw : AdamwEpi{}};
+                alpha, debug_nostore, pf, adamw != nullptr ? *adamw : AdamwEpi{}};
   if (G == 1) { args.opt.p_in_gs = 0; args.opt.w16_gs = 0; }
   // multicast pays once there are at least two 256-row tiles per cluster slot; tiny problems keep 2-CTA clusters
   const bool mc = cg == 2 && gemm_multicast() && M > 2 * kBM * 2;

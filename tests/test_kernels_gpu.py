@@ -463,6 +463,9 @@ def test_bicubic_resize_matches_torch_interpolate():
         assert torch.equal(full[idx.long()], out)
 
 
+DEV = "cuda:0"
+
+
 @pytest.mark.parametrize("M,N,K,epi", [(77, 128, 128, 0), (200, 384, 128, 0), (1001, 512, 2048, 2), (385, 2048, 512, 1),
                                         (128, 4, 4, 0), (5, 260, 36, 2)])
 def test_gemm_f32_matches_torch(M, N, K, epi):

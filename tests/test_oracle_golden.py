@@ -153,6 +153,10 @@ def test_prompt_oracle_matches_reference(name):
         if not tpt:
             assert np.array_equal(torch.stack(out["topk_idx"]).numpy(), z[f"img{i}.topk_idx"])
             assert np.abs(torch.stack(out["rewards"]).numpy() - z[f"img{i}.rewards"]).max() < 1e-5
-        assert np.abs(out["logits_final"].numpy() - z[f"img{i}.logits_final"]).max() < 1e-4 * scale
+        # two fp32 CPU implementations of the same arithmetic in a different operation order: 1e-4 of the logit scale,
+        # plus 2e-4 of what adaptation changed (lr 5e-3 on context entries of magnitude 0.02 moves the logits by more
+        # than their own scale, and AdamW's sign-like first steps amplify the last-bit differences of the gradient)
+        delta = np.abs(z[f"img{i}.logits_final"][0] - z[f"img{i}.logits_all"][0]).max()
+        assert np.abs(out["logits_final"].numpy() - z[f"img{i}.logits_final"]).max() < 1e-4 * scale + 2e-4 * delta
         d = np.abs(out["params"].numpy() - z[f"img{i}.params"])
         assert d.max() <= 2.02 * cfg["lr"] * cfg["steps"] and (d < 0.02 * cfg["lr"]).mean() > 0.99

@@ -310,7 +310,7 @@ def test_engine_rejects_empty_selection():
 
 def _prompt_engine(cfg, tokens, ctx_init, n_img, loss="rlcf"):
     sd_p = O.make_clip_state_dict(cfg["policy"], POLICY_SEED)
-    sd_r = O.make_clip_state_dict(cfg["reward"], REWARD_SEED)
+    sd_r = O.make_clip_state_dict(cfg["reward"], cfg.get("reward_seed", REWARD_SEED))
     sdp_d, sdr_d = to_dev(sd_p), to_dev(sd_r)
     rc = O.class_features(sd_r, tokens)
     rcfg = E.RlcfConfig(n_views=cfg["V"], selection_p=cfg["rho"], tta_steps=cfg["steps"], sample_k=cfg["K"],
