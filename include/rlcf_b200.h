@@ -45,7 +45,8 @@ uint64_t rlcf_launch_count(void);
 int rlcf_set_gemm_cta_group(int cta_group);
 /* 1 = 4-CTA clusters: two CTA pairs share one weight tile through TMA multicast (512 x 256 cluster tile). */
 int rlcf_set_gemm_multicast(int on);
-/* Forward attention kernel: 0 = tcgen05/TMEM kernel (default), 1 = warp-level mma.sync kernel. Returns the value set. */
+/* Attention kernels (forward and backward): 0 = tcgen05/TMEM kernels (default; sequences beyond their TMEM layout --
+ * forward L > 272, backward L > 224 -- use the warp-level kernels), 1 = warp-level mma.sync kernels. Returns the value set. */
 int rlcf_set_attention_impl(int impl);
 
 /* D[M,N] = A[M,K] * B[N,K]^T, fp16 operands (K contiguous), fp32 accumulate on tcgen05 tensor cores.

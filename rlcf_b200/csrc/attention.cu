@@ -4,6 +4,8 @@
 // Replaces nn.MultiheadAttention's bmm + softmax + bmm (TPT/clip/model.py:185-187) and its autograd.
 // The whole sequence of a (view, head) fits one CTA's shared memory, so no KV tiling over HBM is needed:
 // qkv is read once, the output written once.
+#include <cstdlib>
+
 #include "ptx.cuh"
 #include "rlcf_internal.h"
 
@@ -352,9 +354,18 @@ int attention_fwd(const __half* qkv, int n_seq, int L, int heads, int causal, __
   return 0;
 }
 
+int attention_bwd_tc(const __half* qkv, const __half* out, const __half* dout, const float* lse, int n_seq, int L,
+                     int heads, int causal, __half* dqkv, cudaStream_t stream);
+
 int attention_bwd(const __half* qkv, const __half* out, const __half* dout, const float* lse, int n_seq, int L,
                   int heads, int causal, __half* dqkv, cudaStream_t stream) {
   if (n_seq <= 0 || L <= 0 || heads <= 0 || lse == nullptr) return set_error(RLCF_ERR_ARG, "attention_bwd: bad args");
+  // tcgen05 kernel for every sequence that fits its TMEM layout (L <= 224); rlcf_set_attention_impl(1) /
+  // RLCF_ATTN_IMPL=1 forces the warp-MMA kernels (forward and backward)
+  if (attention_impl() == 0) {
+    const int rc = attention_bwd_tc(qkv, out, dout, lse, n_seq, L, heads, causal, dqkv, stream);
+    if (rc != -1) return rc;
+  }
   const int Lp = (L + 15) / 16 * 16;
   const size_t smem = static_cast<size_t>(4 * Lp) * kRowBytes + 2 * Lp * sizeof(float);
   if (smem > 227 * 1024) return set_error(RLCF_ERR_ARG, "attention_bwd: sequence %d too long for one CTA", L);

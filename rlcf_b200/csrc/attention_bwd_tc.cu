@@ -1,0 +1,337 @@
+// tcgen05 / TMEM backward of the fused attention core for CLIP towers (head_dim 64, L <= 224 tokens): dQ, dK, dV of
+// one (sequence, head) unit from Q, K, V, the forward output O, its gradient dO and the saved log-sum-exp.
+// Replaces autograd's backward of nn.MultiheadAttention's bmm-softmax-bmm (TPT/clip/model.py:185-187 under
+// TPT/tpt_cls_rl.py:77) and the warp-MMA kernel of attention.cu for every tower whose sequence fits (ViT-B/32, ViT-B/16,
+// the text towers); longer sequences (ViT-L/14: 257 tokens) keep the warp-MMA kernel.
+//
+// Per unit the four [Lk x 64] fp16 tiles Q, K, V, dO are TMA-loaded once (128-byte swizzle) and every contraction runs
+// on the tensor core with fp32 accumulators in TMEM.  With P = exp(S/8 - lse), D_i = sum_c dO_ic O_ic and
+// dS = P o (dP - D) / 8:
+//   phase A (rows = 128 queries):  S = Q K^T, dP = dO V^T (SS)  ->  threads: dS (fp16, back into TMEM)  ->  dQ = dS K (TS)
+//   phase B (rows = 128 keys):     S^T = K Q^T, dP^T = V dO^T   ->  threads: P^T, dS^T                 ->  dV = P^T dO, dK = dS^T Q
+// (the scores are recomputed in both orientations, as in the warp-MMA kernel: a TMEM accumulator cannot be transposed).
+// One thread owns one accumulator row (lane); P / dS are packed to fp16 into TMEM columns that the row has already
+// consumed, exactly like P in the forward kernel (attention_tc.cu).
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 TMEM allocation + MMA issuer, warps 2-5 the 128 accumulator rows.
+// TMEM columns: [0,224) S / packed P, [224,448) dP / packed dS + dK accumulator, [448,512) dQ or dV accumulator.
+#include <cstdlib>
+
+#include "ptx.cuh"
+#include "rlcf_internal.h"
+
+namespace rlcf {
+
+struct AttnBwdArgs {
+  int L, Lk, heads, causal, n_units, n_rt;   // n_rt = row tiles of 128 per unit (1 or 2)
+  int tile_bytes;                            // smem bytes reserved per operand tile (n_rt * 128 rows)
+  const __half* out;                         // forward output O  [n_seq*L, d]
+  const __half* dout;                        // dO                [n_seq*L, d]
+  const float* lse;                          // [n_seq, heads, L]
+  __half* dqkv;                              // [n_seq*L, 3d]
+};
+
+constexpr int kBwdTcThreads = 192;
+constexpr int kColS = 0, kColDP = 224, kColOut = 448, kColDK = 352;   // TMEM column map (see header)
+enum { BB_FULL = 0, BB_FREE = 1, BB_SREADY = 2, BB_PREADY = 3, BB_OREADY = 4, BB_TMEMFREE = 5, BB_COUNT = 6 };
+
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_fence() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_rows() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // warps 2-5
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// 64 fp32 accumulator columns of this thread's row -> 64 fp16 = 128 contiguous bytes in global memory
+__device__ __forceinline__ void store_row64(__half* dst, const uint32_t (&lo)[32], const uint32_t (&hi)[32]) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    d4[j] = make_uint4(pack2(__uint_as_float(lo[8 * j]), __uint_as_float(lo[8 * j + 1])),
+                       pack2(__uint_as_float(lo[8 * j + 2]), __uint_as_float(lo[8 * j + 3])),
+                       pack2(__uint_as_float(lo[8 * j + 4]), __uint_as_float(lo[8 * j + 5])),
+                       pack2(__uint_as_float(lo[8 * j + 6]), __uint_as_float(lo[8 * j + 7])));
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    d4[4 + j] = make_uint4(pack2(__uint_as_float(hi[8 * j]), __uint_as_float(hi[8 * j + 1])),
+                           pack2(__uint_as_float(hi[8 * j + 2]), __uint_as_float(hi[8 * j + 3])),
+                           pack2(__uint_as_float(hi[8 * j + 4]), __uint_as_float(hi[8 * j + 5])),
+                           pack2(__uint_as_float(hi[8 * j + 6]), __uint_as_float(hi[8 * j + 7])));
+}
+
+__global__ void __launch_bounds__(kBwdTcThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ CUtensorMap mapDO, AttnBwdArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + p.tile_bytes;
+  uint8_t* sV = sK + p.tile_bytes;
+  uint8_t* sdO = sV + p.tile_bytes;
+  float* sLse = reinterpret_cast<float*>(sdO + p.tile_bytes);   // [256] lse * log2(e); 0 beyond L
+  float* sD = sLse + 256;                                        // [256] D_i = sum_c dO_ic O_ic; 0 beyond L
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 256);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BB_COUNT);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int d = p.heads * 64;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&mapQKV);
+    tma_prefetch_desc(&mapDO);
+    for (int i = 0; i < BB_COUNT; ++i) mbar_init(&bars[i], 1);
+    mbar_init(&bars[BB_PREADY], 4);     // one arrive per row warp
+    mbar_init(&bars[BB_TMEMFREE], 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int tiles_per_unit = 2 * p.n_rt;     // phase A row tiles, then phase B row tiles
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t uc = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++uc) {
+        const int h = u % p.heads, seq = u / p.heads;
+        const int row = seq * p.L;
+        mbar_wait(&bars[BB_FREE], (uc & 1) ^ 1);          // every MMA that read the previous unit's tiles has retired
+        mbar_expect_tx(&bars[BB_FULL], 4 * p.Lk * 128);
+        tma_load_2d(sQ, &mapQKV, &bars[BB_FULL], h * 64, row);
+        tma_load_2d(sK, &mapQKV, &bars[BB_FULL], d + h * 64, row);
+        tma_load_2d(sV, &mapQKV, &bars[BB_FULL], 2 * d + h * 64, row);
+        tma_load_2d(sdO, &mapDO, &bars[BB_FULL], h * 64, row);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_f16(128, p.Lk);
+      const uint32_t idesc_o = umma_idesc_f16(128, 64) | (1u << 16);   // B operand is MN-major ([k][64] rows)
+      const int ksteps = p.Lk >> 4;
+      uint32_t uc = 0, it = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++uc) {
+        mbar_wait(&bars[BB_FULL], uc & 1);
+        tc_fence_after();
+        for (int t = 0; t < tiles_per_unit; ++t, ++it) {
+          const bool phase_b = t >= p.n_rt;
+          const int r0 = (phase_b ? t - p.n_rt : t) * 128;
+          const uint32_t ph = it & 1;
+          // scores: A = this tile's 128 rows of (Q | K), B = all Lk rows of (K | Q); dP alike with (dO | V) x (V | dO)
+          const uint64_t a_s = umma_desc_k_sw128(smem_u32((phase_b ? sK : sQ) + r0 * 128));
+          const uint64_t b_s = umma_desc_k_sw128(smem_u32(phase_b ? sQ : sK));
+          const uint64_t a_p = umma_desc_k_sw128(smem_u32((phase_b ? sV : sdO) + r0 * 128));
+          const uint64_t b_p = umma_desc_k_sw128(smem_u32(phase_b ? sdO : sV));
+          mbar_wait(&bars[BB_TMEMFREE], ph ^ 1);          // the previous tile's accumulators have been read out
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_ss<1>(tmem + kColS, a_s + 2 * k, b_s + 2 * k, idesc_s, k != 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_ss<1>(tmem + kColDP, a_p + 2 * k, b_p + 2 * k, idesc_s, k != 0);
+          umma_commit(&bars[BB_SREADY]);
+          mbar_wait(&bars[BB_PREADY], ph);                // packed dS (and P^T) are in TMEM
+          tc_fence_after();
+          if (!phase_b) {
+            const uint64_t bk = umma_desc_k_sw128(smem_u32(sK));
+            for (int j = 0; j < ksteps; ++j) umma_ts(tmem + kColOut, tmem + kColS + 8 * j, bk + 128 * j, idesc_o, j != 0);
+          } else {
+            const uint64_t bdo = umma_desc_k_sw128(smem_u32(sdO));
+            const uint64_t bq = umma_desc_k_sw128(smem_u32(sQ));
+            for (int j = 0; j < ksteps; ++j) umma_ts(tmem + kColOut, tmem + kColS + 8 * j, bdo + 128 * j, idesc_o, j != 0);
+            for (int j = 0; j < ksteps; ++j) umma_ts(tmem + kColDK, tmem + kColDP + 8 * j, bq + 128 * j, idesc_o, j != 0);
+          }
+          umma_commit(&bars[BB_OREADY]);
+          if (t == tiles_per_unit - 1) umma_commit(&bars[BB_FREE]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ accumulator rows: thread = one TMEM lane
+    const int q4 = warp & 3;                              // TMEM lane quarter this warp may access
+    const int r = q4 * 32 + lane;
+    const int rt_id = tid - 64;                           // 0..127 among the row threads
+    const uint32_t trow = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
+    const float scale = 0.125f;
+    const float c = scale * 1.4426950408889634f;
+    const int n_chunks = (p.Lk + 31) >> 5;
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int h = u % p.heads, seq = u / p.heads;
+      const size_t row_base = static_cast<size_t>(seq) * p.L;
+      // D and lse of every row of this unit (the previous unit's values are dead: its last phase has been read out)
+      bar_sync_rows();
+      for (int rr = rt_id; rr < 256; rr += 128) {
+        float dsum = 0.f, lv = 0.f;
+        if (rr < p.L) {
+          const uint4* po = reinterpret_cast<const uint4*>(p.out + (row_base + rr) * d + h * 64);
+          const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (row_base + rr) * d + h * 64);
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            const uint4 a = po[c8], b = pd[c8];
+            const __half2* ha = reinterpret_cast<const __half2*>(&a);
+            const __half2* hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 fa = __half22float2(ha[e]), fb = __half22float2(hb[e]);
+              dsum = fmaf(fa.x, fb.x, fmaf(fa.y, fb.y, dsum));
+            }
+          }
+          lv = p.lse[(static_cast<size_t>(seq) * p.heads + h) * p.L + rr] * 1.4426950408889634f;
+        }
+        sD[rr] = dsum;
+        sLse[rr] = lv;
+      }
+      bar_sync_rows();
+      for (int t = 0; t < tiles_per_unit; ++t, ++it) {
+        const bool phase_b = t >= p.n_rt;
+        const int r0 = (phase_b ? t - p.n_rt : t) * 128;
+        const int grow = r0 + r;                          // query (phase A) or key (phase B) of this thread
+        const uint32_t ph = it & 1;
+        const float lse_r = sLse[grow & 255], d_r = sD[grow & 255];
+        mbar_wait(&bars[BB_SREADY], ph);
+        tc_fence_after();
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          uint32_t s[32], dp[32], pk_ds[16], pk_p[16];
+          tmem_ld_32x32(trow + kColS + ch * 32, s);
+          tmem_ld_32x32(trow + kColDP + ch * 32, dp);
+          tmem_ld_wait();
+          if (!phase_b) {
+            // columns = keys; this row's query is `grow`
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float v2[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int key = ch * 32 + 2 * j + e;
+                const bool ok = key < p.L && (!p.causal || key <= grow);
+                const float pr = ex2_approx(fmaf(__uint_as_float(s[2 * j + e]), c, -lse_r));
+                v2[e] = ok ? pr * (__uint_as_float(dp[2 * j + e]) - d_r) * scale : 0.f;
+              }
+              pk_ds[j] = pack2(v2[0], v2[1]);
+            }
+            tmem_st16(trow + kColS + ch * 16, pk_ds);
+          } else {
+            // columns = queries; this row's key is `grow`
+            const float4* l4 = reinterpret_cast<const float4*>(sLse + ch * 32);
+            const float4* d4 = reinterpret_cast<const float4*>(sD + ch * 32);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 lq = l4[j4], dq = d4[j4];
+              const float lqa[4] = {lq.x, lq.y, lq.z, lq.w}, dqa[4] = {dq.x, dq.y, dq.z, dq.w};
+              float pv[4], dv[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int q = ch * 32 + 4 * j4 + e;
+                const bool ok = q < p.L && (!p.causal || grow <= q);
+                const float pr = ex2_approx(fmaf(__uint_as_float(s[4 * j4 + e]), c, -lqa[e]));
+                pv[e] = ok ? pr : 0.f;
+                dv[e] = ok ? pr * (__uint_as_float(dp[4 * j4 + e]) - dqa[e]) * scale : 0.f;
+              }
+              pk_p[2 * j4] = pack2(pv[0], pv[1]);
+              pk_p[2 * j4 + 1] = pack2(pv[2], pv[3]);
+              pk_ds[2 * j4] = pack2(dv[0], dv[1]);
+              pk_ds[2 * j4 + 1] = pack2(dv[2], dv[3]);
+            }
+            tmem_st16(trow + kColS + ch * 16, pk_p);
+            tmem_st16(trow + kColDP + ch * 16, pk_ds);
+          }
+        }
+        tmem_st_fence();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[BB_PREADY]);
+        // ---- read the output accumulators of this tile
+        mbar_wait(&bars[BB_OREADY], ph);
+        tc_fence_after();
+        {
+          uint32_t lo[32], hi[32];
+          tmem_ld_32x32(trow + kColOut, lo);
+          tmem_ld_32x32(trow + kColOut + 32, hi);
+          tmem_ld_wait();
+          __half* dst = p.dqkv + (row_base + grow) * (3 * static_cast<size_t>(d)) + h * 64;
+          if (grow < p.L) store_row64(dst + (phase_b ? 2 * d : 0), lo, hi);     // dV (phase B) or dQ (phase A)
+          if (phase_b) {
+            tmem_ld_32x32(trow + kColDK, lo);
+            tmem_ld_32x32(trow + kColDK + 32, hi);
+            tmem_ld_wait();
+            if (grow < p.L) store_row64(dst + d, lo, hi);                        // dK
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[BB_TMEMFREE]);
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc<1>(tmem, 512);
+}
+
+static int make_tmap_rows64_bwd(CUtensorMap* map, const void* base, long long rows, int cols, int box_rows) {
+  static PFN_encodeTiled encode = get_encode_tiled();
+  if (encode == nullptr) return set_error(RLCF_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(RLCF_ERR_DRIVER, "cuTensorMapEncodeTiled(attention bwd) failed (%d)", static_cast<int>(r));
+  return 0;
+}
+
+// Returns -1 when the shape is outside what this kernel covers (the caller falls back to the warp-MMA kernel).
+int attention_bwd_tc(const __half* qkv, const __half* out, const __half* dout, const float* lse, int n_seq, int L,
+                     int heads, int causal, __half* dqkv, cudaStream_t stream) {
+  const int Lk = (L + 15) / 16 * 16;
+  if (Lk > 224 || Lk < 16) return -1;
+  if (((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dout) |
+        reinterpret_cast<uintptr_t>(dqkv)) & 15) != 0)
+    return -1;
+  AttnBwdArgs a{};
+  a.L = L; a.Lk = Lk; a.heads = heads; a.causal = causal; a.n_units = heads * n_seq;
+  a.n_rt = (L + 127) / 128;
+  a.tile_bytes = a.n_rt * 128 * 128;     // a row tile reads 128 rows from its start: rows beyond Lk are never stored
+  a.out = out; a.dout = dout; a.lse = lse; a.dqkv = dqkv;
+  const size_t smem = 1024 + 4 * static_cast<size_t>(a.tile_bytes) + 2 * 256 * sizeof(float) + BB_COUNT * 8 + 16;
+  static DynSmemState st;
+  if (cudaError_t e = ensure_dyn_smem(attn_bwd_tc_kernel, smem, st))
+    return set_error(RLCF_ERR_CUDA, "attention_bwd_tc attr: %s", cudaGetErrorString(e));
+  CUtensorMap mqkv, mdo;
+  const long long rows = static_cast<long long>(n_seq) * L;
+  if (int rc = make_tmap_rows64_bwd(&mqkv, qkv, rows, 3 * heads * 64, Lk)) return rc;
+  if (int rc = make_tmap_rows64_bwd(&mdo, dout, rows, heads * 64, Lk)) return rc;
+  const int grid = a.n_units < sm_count() ? a.n_units : sm_count();
+  attn_bwd_tc_kernel<<<grid, kBwdTcThreads, smem, stream>>>(mqkv, mdo, a);
+  RLCF_CHECK_LAUNCH("attention_bwd_tc");
+  return 0;
+}
+
+}  // namespace rlcf

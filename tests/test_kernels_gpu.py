@@ -231,6 +231,33 @@ def test_attention_fwd_bwd(L, heads, causal, impl):
     _lib.set_attention_impl(0)
 
 
+@pytest.mark.parametrize("n_seq,L,heads,causal", [(40, 197, 12, False), (64, 77, 8, True), (200, 50, 2, False)])
+def test_attention_bwd_persistent_many_units(n_seq, L, heads, causal):
+    """More (sequence, head) units than SMs: every CTA of the persistent tcgen05 backward walks several units (tile
+    reloads, barrier phases, TMEM reuse); the warp-MMA kernel must agree with it to fp16 rounding of the outputs."""
+    torch.manual_seed(n_seq + L)
+    d = heads * 64
+    qkv = torch.randn(n_seq * L, 3 * d, device=_dev()).half()
+    dout = (torch.randn(n_seq * L, d, device=_dev()) * 0.1).half()
+    out = torch.empty(n_seq * L, d, device=_dev(), dtype=torch.float16)
+    lse = torch.empty(n_seq, heads, L, device=_dev())
+    ops.attention_fwd(qkv, n_seq, L, heads, out, causal=causal, lse=lse)
+    res = []
+    for impl in (0, 1):
+        assert _lib.set_attention_impl(impl) == impl
+        dqkv = torch.full((n_seq * L, 3 * d), float("nan"), device=_dev(), dtype=torch.float16)
+        for _ in range(2):      # twice: the second launch sees TMEM / barriers left by the first
+            ops.attention_bwd(qkv, out, dout, lse, n_seq, L, heads, dqkv, causal=causal)
+        res.append(dqkv)
+    _lib.set_attention_impl(0)
+    assert torch.isfinite(res[0]).all()
+    qf = qkv.float().requires_grad_(True)
+    ref, _ = _ref_attention(qf, n_seq, L, heads, causal)
+    ref.backward(dout.float())
+    assert _rel(res[0], qf.grad) < 5e-3 and _rel(res[1], qf.grad) < 5e-3
+    assert _rel(res[0], res[1].float()) < 3e-3
+
+
 def test_attention_forward_at_336_pixel_sequence_length():
     """577 tokens (ViT-L/14@336px as a reward model, clip_reward.py:22-27): beyond the single-tile tcgen05 kernel, served
     by the warp-MMA kernel; forward only (reward models are frozen)."""
