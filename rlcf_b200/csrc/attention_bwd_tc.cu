@@ -13,9 +13,13 @@
 // One thread owns one accumulator row (lane); P / dS are packed to fp16 into TMEM columns that the row has already
 // consumed, exactly like P in the forward kernel (attention_tc.cu).
 //
-// CTA = 6 warps: warp 0 TMA producer, warp 1 TMEM allocation + MMA issuer, warps 2-5 the 128 accumulator rows.
+// CTA = 6 warps: warp 0 producer (TMA of the next unit's tiles into the other shared-memory stage, and that unit's
+// D / lse vectors), warp 1 TMEM allocation + MMA issuer, warps 2-5 the 128 accumulator rows (their TMEM chunk loads
+// are issued one chunk ahead of the arithmetic).
 // TMEM columns: [0,224) S / packed P, [224,448) dP / packed dS + dK accumulator, [448,512) dQ or dV accumulator.
+#include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "ptx.cuh"
 #include "rlcf_internal.h"
@@ -24,7 +28,9 @@ namespace rlcf {
 
 struct AttnBwdArgs {
   int L, Lk, heads, causal, n_units, n_rt;   // n_rt = row tiles of 128 per unit (1 or 2)
-  int tile_bytes;                            // smem bytes reserved per operand tile (n_rt * 128 rows)
+  int tile_bytes;                            // smem bytes per operand tile (Lk rows; a row tile may read past it, see host)
+  int n_stages;                              // shared-memory stages of {Q, K, V, dO, D, lse}: 2 when they fit, else 1
+  int debug;                                 // RLCF_ATTN_BWD_DEBUG=1: CTA 0 prints a clock64 timeline of its first tiles
   const __half* out;                         // forward output O  [n_seq*L, d]
   const __half* dout;                        // dO                [n_seq*L, d]
   const float* lse;                          // [n_seq, heads, L]
@@ -33,7 +39,8 @@ struct AttnBwdArgs {
 
 constexpr int kBwdTcThreads = 192;
 constexpr int kColS = 0, kColDP = 224, kColOut = 448, kColDK = 352;   // TMEM column map (see header)
-enum { BB_FULL = 0, BB_FREE = 1, BB_SREADY = 2, BB_PREADY = 3, BB_OREADY = 4, BB_TMEMFREE = 5, BB_COUNT = 6 };
+// barriers: FULL / FREE / DFULL exist per stage (index + stage)
+enum { BB_FULL = 0, BB_FREE = 2, BB_DFULL = 4, BB_SREADY = 6, BB_PREADY = 7, BB_OREADY = 8, BB_TMEMFREE = 9, BB_COUNT = 10 };
 
 __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                         uint32_t accumulate) {
@@ -55,40 +62,37 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_fence() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void bar_sync_rows() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // warps 2-5
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// 64 fp32 accumulator columns of this thread's row -> 64 fp16 = 128 contiguous bytes in global memory
-__device__ __forceinline__ void store_row64(__half* dst, const uint32_t (&lo)[32], const uint32_t (&hi)[32]) {
+// 64 fp32 accumulator columns of this thread's row -> 64 fp16 (32 packed registers) ...
+__device__ __forceinline__ void pack_row64(uint32_t (&pk)[32], const uint32_t (&lo)[32], const uint32_t (&hi)[32]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    pk[j] = pack2(__uint_as_float(lo[2 * j]), __uint_as_float(lo[2 * j + 1]));
+    pk[16 + j] = pack2(__uint_as_float(hi[2 * j]), __uint_as_float(hi[2 * j + 1]));
+  }
+}
+// ... and those 128 contiguous bytes to global memory
+__device__ __forceinline__ void store_row64(__half* dst, const uint32_t (&pk)[32]) {
   uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    d4[j] = make_uint4(pack2(__uint_as_float(lo[8 * j]), __uint_as_float(lo[8 * j + 1])),
-                       pack2(__uint_as_float(lo[8 * j + 2]), __uint_as_float(lo[8 * j + 3])),
-                       pack2(__uint_as_float(lo[8 * j + 4]), __uint_as_float(lo[8 * j + 5])),
-                       pack2(__uint_as_float(lo[8 * j + 6]), __uint_as_float(lo[8 * j + 7])));
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    d4[4 + j] = make_uint4(pack2(__uint_as_float(hi[8 * j]), __uint_as_float(hi[8 * j + 1])),
-                           pack2(__uint_as_float(hi[8 * j + 2]), __uint_as_float(hi[8 * j + 3])),
-                           pack2(__uint_as_float(hi[8 * j + 4]), __uint_as_float(hi[8 * j + 5])),
-                           pack2(__uint_as_float(hi[8 * j + 6]), __uint_as_float(hi[8 * j + 7])));
+  for (int j = 0; j < 8; ++j) d4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
 }
 
 __global__ void __launch_bounds__(kBwdTcThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ CUtensorMap mapDO, AttnBwdArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + p.tile_bytes;
-  uint8_t* sV = sK + p.tile_bytes;
-  uint8_t* sdO = sV + p.tile_bytes;
-  float* sLse = reinterpret_cast<float*>(sdO + p.tile_bytes);   // [256] lse * log2(e); 0 beyond L
-  float* sD = sLse + 256;                                        // [256] D_i = sum_c dO_ic O_ic; 0 beyond L
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 256);
+  // stage s: tiles Q, K, V, dO at smem + s * 4 * tile_bytes; behind the last tile a pad of (256 - Lk) rows, so that a
+  // row tile's 128-row A operand starting at row 128 stays inside the allocation (rows >= Lk are never stored)
+  const int stage_bytes = 4 * p.tile_bytes;
+  uint8_t* vec_base = smem + p.n_stages * stage_bytes + (256 - p.Lk) * 128;
+  float* sLse0 = reinterpret_cast<float*>(vec_base);            // [stage][256] lse * log2(e); 0 beyond L
+  float* sD0 = sLse0 + 2 * 256;                                  // [stage][256] D_i = sum_c dO_ic O_ic; 0 beyond L
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD0 + 2 * 256);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BB_COUNT);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -97,9 +101,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
   if (tid == 0) {
     tma_prefetch_desc(&mapQKV);
     tma_prefetch_desc(&mapDO);
-    for (int i = 0; i < BB_COUNT; ++i) mbar_init(&bars[i], 1);
-    mbar_init(&bars[BB_PREADY], 4);     // one arrive per row warp
-    mbar_init(&bars[BB_TMEMFREE], 4);
+    for (int i = 0; i < BB_COUNT; ++i)
+      mbar_init(&bars[i], (i == BB_PREADY || i == BB_TMEMFREE) ? 4 : 1);   // 4 = one arrive per row warp
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
@@ -110,19 +113,49 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
   const int tiles_per_unit = 2 * p.n_rt;     // phase A row tiles, then phase B row tiles
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      uint32_t uc = 0;
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++uc) {
-        const int h = u % p.heads, seq = u / p.heads;
+    // ------------------------------------------------------------ producer: tiles (TMA, lane 0) + D / lse (all lanes)
+    uint32_t uc = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++uc) {
+      const int h = u % p.heads, seq = u / p.heads;
+      const int st = p.n_stages == 2 ? (uc & 1) : 0;
+      const uint32_t sph = p.n_stages == 2 ? ((uc >> 1) & 1) : (uc & 1);   // phase of this stage's barriers
+      const size_t row_base = static_cast<size_t>(seq) * p.L;
+      uint8_t* sQ = smem + st * stage_bytes;
+      // every MMA that read this stage has retired (the row threads' last use of its D / lse precedes those MMAs)
+      mbar_wait(&bars[BB_FREE + st], sph ^ 1);
+      if (lane == 0) {
         const int row = seq * p.L;
-        mbar_wait(&bars[BB_FREE], (uc & 1) ^ 1);          // every MMA that read the previous unit's tiles has retired
-        mbar_expect_tx(&bars[BB_FULL], 4 * p.Lk * 128);
-        tma_load_2d(sQ, &mapQKV, &bars[BB_FULL], h * 64, row);
-        tma_load_2d(sK, &mapQKV, &bars[BB_FULL], d + h * 64, row);
-        tma_load_2d(sV, &mapQKV, &bars[BB_FULL], 2 * d + h * 64, row);
-        tma_load_2d(sdO, &mapDO, &bars[BB_FULL], h * 64, row);
+        mbar_expect_tx(&bars[BB_FULL + st], 4 * p.Lk * 128);
+        tma_load_2d(sQ, &mapQKV, &bars[BB_FULL + st], h * 64, row);
+        tma_load_2d(sQ + p.tile_bytes, &mapQKV, &bars[BB_FULL + st], d + h * 64, row);
+        tma_load_2d(sQ + 2 * p.tile_bytes, &mapQKV, &bars[BB_FULL + st], 2 * d + h * 64, row);
+        tma_load_2d(sQ + 3 * p.tile_bytes, &mapDO, &bars[BB_FULL + st], h * 64, row);
       }
+      float* sLse = sLse0 + st * 256;
+      float* sD = sD0 + st * 256;
+      for (int rr = lane; rr < 256; rr += 32) {
+        float dsum = 0.f, lv = 0.f;
+        if (rr < p.L) {
+          const uint4* po = reinterpret_cast<const uint4*>(p.out + (row_base + rr) * d + h * 64);
+          const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (row_base + rr) * d + h * 64);
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            const uint4 a = po[c8], b = pd[c8];
+            const __half2* ha = reinterpret_cast<const __half2*>(&a);
+            const __half2* hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 fa = __half22float2(ha[e]), fb = __half22float2(hb[e]);
+              dsum = fmaf(fa.x, fb.x, fmaf(fa.y, fb.y, dsum));
+            }
+          }
+          lv = p.lse[(static_cast<size_t>(seq) * p.heads + h) * p.L + rr] * 1.4426950408889634f;
+        }
+        sD[rr] = dsum;
+        sLse[rr] = lv;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[BB_DFULL + st]);    // release: the vectors above are visible to the waiters
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
@@ -132,7 +165,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
       const int ksteps = p.Lk >> 4;
       uint32_t uc = 0, it = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++uc) {
-        mbar_wait(&bars[BB_FULL], uc & 1);
+        const int st = p.n_stages == 2 ? (uc & 1) : 0;
+        const uint32_t sph = p.n_stages == 2 ? ((uc >> 1) & 1) : (uc & 1);
+        uint8_t* sQ = smem + st * stage_bytes;
+        uint8_t* sK = sQ + p.tile_bytes;
+        uint8_t* sV = sK + p.tile_bytes;
+        uint8_t* sdO = sV + p.tile_bytes;
+        mbar_wait(&bars[BB_FULL + st], sph);
         tc_fence_after();
         for (int t = 0; t < tiles_per_unit; ++t, ++it) {
           const bool phase_b = t >= p.n_rt;
@@ -162,7 +201,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
             for (int j = 0; j < ksteps; ++j) umma_ts(tmem + kColDK, tmem + kColDP + 8 * j, bq + 128 * j, idesc_o, j != 0);
           }
           umma_commit(&bars[BB_OREADY]);
-          if (t == tiles_per_unit - 1) umma_commit(&bars[BB_FREE]);
+          if (t == tiles_per_unit - 1) umma_commit(&bars[BB_FREE + st]);
         }
       }
     }
@@ -170,52 +209,44 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
     // ------------------------------------------------------------ accumulator rows: thread = one TMEM lane
     const int q4 = warp & 3;                              // TMEM lane quarter this warp may access
     const int r = q4 * 32 + lane;
-    const int rt_id = tid - 64;                           // 0..127 among the row threads
     const uint32_t trow = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
     const float scale = 0.125f;
     const float c = scale * 1.4426950408889634f;
     const int n_chunks = (p.Lk + 31) >> 5;
-    uint32_t it = 0;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+    uint32_t it = 0, uc = 0;
+    const bool probe = p.debug && blockIdx.x == 0 && warp == 2 && lane == 0;
+    long long stamp[12][6];
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++uc) {
       const int h = u % p.heads, seq = u / p.heads;
       const size_t row_base = static_cast<size_t>(seq) * p.L;
-      // D and lse of every row of this unit (the previous unit's values are dead: its last phase has been read out)
-      bar_sync_rows();
-      for (int rr = rt_id; rr < 256; rr += 128) {
-        float dsum = 0.f, lv = 0.f;
-        if (rr < p.L) {
-          const uint4* po = reinterpret_cast<const uint4*>(p.out + (row_base + rr) * d + h * 64);
-          const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (row_base + rr) * d + h * 64);
-#pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) {
-            const uint4 a = po[c8], b = pd[c8];
-            const __half2* ha = reinterpret_cast<const __half2*>(&a);
-            const __half2* hb = reinterpret_cast<const __half2*>(&b);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 fa = __half22float2(ha[e]), fb = __half22float2(hb[e]);
-              dsum = fmaf(fa.x, fb.x, fmaf(fa.y, fb.y, dsum));
-            }
-          }
-          lv = p.lse[(static_cast<size_t>(seq) * p.heads + h) * p.L + rr] * 1.4426950408889634f;
-        }
-        sD[rr] = dsum;
-        sLse[rr] = lv;
-      }
-      bar_sync_rows();
+      const int st = p.n_stages == 2 ? (uc & 1) : 0;
+      const uint32_t sph = p.n_stages == 2 ? ((uc >> 1) & 1) : (uc & 1);
+      const float* sLse = sLse0 + st * 256;
+      const float* sD = sD0 + st * 256;
+      mbar_wait(&bars[BB_DFULL + st], sph);               // this unit's D / lse vectors (written by the producer warp)
       for (int t = 0; t < tiles_per_unit; ++t, ++it) {
         const bool phase_b = t >= p.n_rt;
         const int r0 = (phase_b ? t - p.n_rt : t) * 128;
         const int grow = r0 + r;                          // query (phase A) or key (phase B) of this thread
         const uint32_t ph = it & 1;
         const float lse_r = sLse[grow & 255], d_r = sD[grow & 255];
+        if (probe && it < 12) stamp[it][0] = clock64();
         mbar_wait(&bars[BB_SREADY], ph);
         tc_fence_after();
-        for (int ch = 0; ch < n_chunks; ++ch) {
-          uint32_t s[32], dp[32], pk_ds[16], pk_p[16];
-          tmem_ld_32x32(trow + kColS + ch * 32, s);
-          tmem_ld_32x32(trow + kColDP + ch * 32, dp);
-          tmem_ld_wait();
+        if (probe && it < 12) stamp[it][1] = clock64();
+        // two register sets: the loads of chunk ch + 1 are in flight while chunk ch is processed
+        uint32_t s0[32], dp0[32], s1[32], dp1[32];
+        tmem_ld_32x32(trow + kColS, s0);
+        tmem_ld_32x32(trow + kColDP, dp0);
+        // d_rs = D * scale is folded into one FFMA: dS = p * (dP * scale - D * scale)
+        const float d_rs = d_r * scale;
+        // Chunks whose 32 columns are all visible to all 32 rows of this warp take a straight-line path without any
+        // predicate arithmetic (4.5 instructions per element instead of ~19; a lone warp per SM sub-partition issues
+        // at ~0.3 IPC, so the instruction count is what the chunk loop costs): warp-uniform `full` below.
+        const int wrow0 = r0 + q4 * 32;                   // first row (query in phase A, key in phase B) of this warp
+        auto process = [&](auto full_tag, const uint32_t (&s)[32], const uint32_t (&dp)[32], int ch) {
+          constexpr bool kFull = decltype(full_tag)::value;
+          uint32_t pk_ds[16], pk_p[16];
           if (!phase_b) {
             // columns = keys; this row's query is `grow`
 #pragma unroll
@@ -223,16 +254,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
               float v2[2];
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
-                const int key = ch * 32 + 2 * j + e;
-                const bool ok = key < p.L && (!p.causal || key <= grow);
                 const float pr = ex2_approx(fmaf(__uint_as_float(s[2 * j + e]), c, -lse_r));
-                v2[e] = ok ? pr * (__uint_as_float(dp[2 * j + e]) - d_r) * scale : 0.f;
+                const float v = pr * fmaf(__uint_as_float(dp[2 * j + e]), scale, -d_rs);
+                if constexpr (kFull) {
+                  v2[e] = v;
+                } else {
+                  const int key = ch * 32 + 2 * j + e;
+                  v2[e] = (key < p.L && (!p.causal || key <= grow)) ? v : 0.f;
+                }
               }
               pk_ds[j] = pack2(v2[0], v2[1]);
             }
             tmem_st16(trow + kColS + ch * 16, pk_ds);
           } else {
-            // columns = queries; this row's key is `grow`
+            // columns = queries; this row's key is `grow`; lse and D * scale of the 32 queries come from shared memory
             const float4* l4 = reinterpret_cast<const float4*>(sLse + ch * 32);
             const float4* d4 = reinterpret_cast<const float4*>(sD + ch * 32);
 #pragma unroll
@@ -242,11 +277,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
               float pv[4], dv[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const int q = ch * 32 + 4 * j4 + e;
-                const bool ok = q < p.L && (!p.causal || grow <= q);
                 const float pr = ex2_approx(fmaf(__uint_as_float(s[4 * j4 + e]), c, -lqa[e]));
-                pv[e] = ok ? pr : 0.f;
-                dv[e] = ok ? pr * (__uint_as_float(dp[4 * j4 + e]) - dqa[e]) * scale : 0.f;
+                const float v = pr * fmaf(__uint_as_float(dp[4 * j4 + e]), scale, -dqa[e] * scale);
+                if constexpr (kFull) {
+                  pv[e] = pr;
+                  dv[e] = v;
+                } else {
+                  const int q = ch * 32 + 4 * j4 + e;
+                  const bool ok = q < p.L && (!p.causal || grow <= q);
+                  pv[e] = ok ? pr : 0.f;
+                  dv[e] = ok ? v : 0.f;
+                }
               }
               pk_p[2 * j4] = pack2(pv[0], pv[1]);
               pk_p[2 * j4 + 1] = pack2(pv[2], pv[3]);
@@ -256,33 +297,74 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
             tmem_st16(trow + kColS + ch * 16, pk_p);
             tmem_st16(trow + kColDP + ch * 16, pk_ds);
           }
+        };
+        auto chunk = [&](const uint32_t (&s)[32], const uint32_t (&dp)[32], int ch) {
+          // every column of the chunk is a real token, and (causal) visible to every row of this warp
+          bool full = ch * 32 + 32 <= p.L;
+          if (p.causal) full = full && (phase_b ? (wrow0 + 31 <= ch * 32) : (ch * 32 + 31 <= wrow0));
+          if (full) process(std::true_type{}, s, dp, ch); else process(std::false_type{}, s, dp, ch);
+        };
+        for (int ch = 0; ch < n_chunks; ch += 2) {
+          tmem_ld_wait();                                  // chunk ch is in s0 / dp0
+          if (ch + 1 < n_chunks) {
+            tmem_ld_32x32(trow + kColS + (ch + 1) * 32, s1);
+            tmem_ld_32x32(trow + kColDP + (ch + 1) * 32, dp1);
+          }
+          chunk(s0, dp0, ch);
+          if (ch + 1 < n_chunks) {
+            tmem_ld_wait();                                // chunk ch + 1 is in s1 / dp1
+            if (ch + 2 < n_chunks) {
+              tmem_ld_32x32(trow + kColS + (ch + 2) * 32, s0);
+              tmem_ld_32x32(trow + kColDP + (ch + 2) * 32, dp0);
+            }
+            chunk(s1, dp1, ch + 1);
+          }
         }
+        if (probe && it < 12) stamp[it][2] = clock64();
         tmem_st_fence();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[BB_PREADY]);
+        if (probe && it < 12) stamp[it][3] = clock64();
         // ---- read the output accumulators of this tile
         mbar_wait(&bars[BB_OREADY], ph);
         tc_fence_after();
+        if (probe && it < 12) stamp[it][4] = clock64();
         {
-          uint32_t lo[32], hi[32];
-          tmem_ld_32x32(trow + kColOut, lo);
-          tmem_ld_32x32(trow + kColOut + 32, hi);
-          tmem_ld_wait();
-          __half* dst = p.dqkv + (row_base + grow) * (3 * static_cast<size_t>(d)) + h * 64;
-          if (grow < p.L) store_row64(dst + (phase_b ? 2 * d : 0), lo, hi);     // dV (phase B) or dQ (phase A)
-          if (phase_b) {
-            tmem_ld_32x32(trow + kColDK, lo);
-            tmem_ld_32x32(trow + kColDK + 32, hi);
+          // All accumulators of the tile go to registers first and TMEM is handed back at once: the 8 (16 in phase B)
+          // scattered 16-byte stores per thread then drain while the tensor core already works on the next tile
+          // (issued before the hand-back they sat on the critical path: 2500-3700 cycles per phase-B tile).
+          uint32_t pa[32], pb[32];
+          {
+            uint32_t lo[32], hi[32];
+            tmem_ld_32x32(trow + kColOut, lo);
+            tmem_ld_32x32(trow + kColOut + 32, hi);
             tmem_ld_wait();
-            if (grow < p.L) store_row64(dst + d, lo, hi);                        // dK
+            pack_row64(pa, lo, hi);
+            if (phase_b) {
+              tmem_ld_32x32(trow + kColDK, lo);
+              tmem_ld_32x32(trow + kColDK + 32, hi);
+              tmem_ld_wait();
+              pack_row64(pb, lo, hi);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[BB_TMEMFREE]);
+          __half* dst = p.dqkv + (row_base + grow) * (3 * static_cast<size_t>(d)) + h * 64;
+          if (grow < p.L) {
+            store_row64(dst + (phase_b ? 2 * d : 0), pa);         // dV (phase B) or dQ (phase A)
+            if (phase_b) store_row64(dst + d, pb);                // dK
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[BB_TMEMFREE]);
+        if (probe && it < 12) stamp[it][5] = clock64();
       }
     }
+    if (probe)
+      for (uint32_t i = 0; i < (it < 12 ? it : 12); ++i)
+        printf("attn_bwd_tc tile %u: wait S %lld | chunks %lld | st fence %lld | wait out %lld | read-out+store %lld | total %lld\n",
+               i, stamp[i][1] - stamp[i][0], stamp[i][2] - stamp[i][1], stamp[i][3] - stamp[i][2],
+               stamp[i][4] - stamp[i][3], stamp[i][5] - stamp[i][4], i ? stamp[i][5] - stamp[i - 1][5] : 0ll);
   }
 
   __syncwarp();
@@ -318,9 +400,18 @@ int attention_bwd_tc(const __half* qkv, const __half* out, const __half* dout, c
   AttnBwdArgs a{};
   a.L = L; a.Lk = Lk; a.heads = heads; a.causal = causal; a.n_units = heads * n_seq;
   a.n_rt = (L + 127) / 128;
-  a.tile_bytes = a.n_rt * 128 * 128;     // a row tile reads 128 rows from its start: rows beyond Lk are never stored
+  a.tile_bytes = Lk * 128;               // multiple of 1024 (Lk % 16 == 0): every tile start keeps the swizzle alignment
   a.out = out; a.dout = dout; a.lse = lse; a.dqkv = dqkv;
-  const size_t smem = 1024 + 4 * static_cast<size_t>(a.tile_bytes) + 2 * 256 * sizeof(float) + BB_COUNT * 8 + 16;
+  static const int debug = getenv("RLCF_ATTN_BWD_DEBUG") != nullptr ? atoi(getenv("RLCF_ATTN_BWD_DEBUG")) : 0;
+  a.debug = debug;
+  // A row tile's A operand spans 128 rows from row 0 or 128 of its tile, i.e. up to (256 - Lk) rows past the tile's end:
+  // into the next tile, or -- for the last tile -- into a pad of that size.  Rows >= L only produce rows that are never stored.
+  auto smem_for = [&](int stages) {
+    return 1024 + static_cast<size_t>(stages) * 4 * a.tile_bytes + static_cast<size_t>(256 - Lk) * 128 +
+           4 * 256 * sizeof(float) + BB_COUNT * 8 + 16;
+  };
+  a.n_stages = smem_for(2) <= 227 * 1024 ? 2 : 1;
+  const size_t smem = smem_for(a.n_stages);
   static DynSmemState st;
   if (cudaError_t e = ensure_dyn_smem(attn_bwd_tc_kernel, smem, st))
     return set_error(RLCF_ERR_CUDA, "attention_bwd_tc attr: %s", cudaGetErrorString(e));

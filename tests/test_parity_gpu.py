@@ -606,6 +606,7 @@ def test_prompt_tuning_at_vit_b32_matches_reference_golden(name, loss):
 
 PROMPT_ALLOW = {   # lr 5e-3 on context entries of magnitude 0.02 (token-embedding scale): each step moves an entry by 25 %
     "b32_cfg1_exact": _flip(1.10e-2, 1.04),
+    "b32_prompt_rlcf": _flip(1.61e-2, 1.20),
 }
 
 
