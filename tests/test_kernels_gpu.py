@@ -258,6 +258,43 @@ def test_attention_bwd_persistent_many_units(n_seq, L, heads, causal):
     assert _rel(res[0], res[1].float()) < 3e-3
 
 
+@pytest.mark.parametrize("L,heads,causal", [(197, 12, False), (257, 16, False), (77, 8, True), (130, 3, True)])
+def test_attention_fwd_sharply_peaked_rows(L, heads, causal):
+    """Attention rows dominated by single keys (as real ViTs produce: register / sink tokens): keys whose scores grow
+    by ~2^20 from one 32-key chunk to the next for a third of the queries, keys that dominate from the FIRST chunk for
+    another third.  Output and log-sum-exp against fp32.  (Written for the single-pass softmax with a lazily updated
+    reference maximum -- measured slower than the two-pass form and not kept, profiles/r2_attention_probes.txt -- whose
+    in-place rescale branch random inputs never reach; kept as a robustness test of the exponent range.)"""
+    torch.manual_seed(1000 + L)
+    n_seq, d = 4, heads * 64
+    qkv = torch.randn(n_seq, L, 3, heads, 64, device=_dev())
+    u = torch.nn.functional.normalize(torch.randn(heads, 64, device=_dev()), dim=-1)
+    rows_up = torch.arange(L, device=_dev()) % 3 == 0       # queries aligned with u: see the planted keys
+    qkv[:, rows_up, 0] += 10.0 * u
+    for key, gain in ((40, 2.0), (100, 4.0), (L - 7, 6.0), (L - 1, 8.0)):   # later chunks, ever larger scores
+        if key < L:
+            qkv[:, key, 1] += gain * u
+    rows_first = torch.arange(L, device=_dev()) % 3 == 1    # queries aligned with w: dominated by key 3 (first chunk)
+    w = torch.nn.functional.normalize(torch.randn(heads, 64, device=_dev()), dim=-1)
+    qkv[:, rows_first, 0] += 10.0 * w
+    qkv[:, 3, 1] += 8.0 * w
+    qkv = qkv.reshape(n_seq * L, 3 * d).half()
+    out = torch.empty(n_seq * L, d, device=_dev(), dtype=torch.float16)
+    lse = torch.empty(n_seq, heads, L, device=_dev())
+    assert _lib.set_attention_impl(0) == 0
+    ops.attention_fwd(qkv, n_seq, L, heads, out, causal=causal, lse=lse)
+    ref, ref_lse = _ref_attention(qkv.float(), n_seq, L, heads, causal)
+    assert torch.isfinite(out).all()
+    assert _rel(out, ref) < 2e-3
+    assert ((lse - ref_lse).abs() / ref_lse.abs().clamp_min(1.0)).max().item() < 1e-3
+    # the planted scores really force reference updates: some query sees > 2^8 between its first-chunk and global maxima
+    q, k, _ = qkv.float().view(n_seq, L, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    sc = (q @ k.transpose(-1, -2)) * 0.125 * 1.4426950408889634
+    if causal:
+        sc = sc + torch.full((L, L), float("-inf"), device=qkv.device).triu(1)
+    assert (sc.max(-1).values - sc[..., :32].max(-1).values).max().item() > 8.0
+
+
 def test_attention_forward_at_336_pixel_sequence_length():
     """577 tokens (ViT-L/14@336px as a reward model, clip_reward.py:22-27): beyond the single-tile tcgen05 kernel, served
     by the warp-MMA kernel; forward only (reward models are frozen)."""
