@@ -173,6 +173,18 @@ int rlcf_pair_logits(const float* img_feat, const float* txt_feat, int64_t txt_s
 /* dctx[g,i,:] = sum over the n_cls prompts of set g of dx[(g*n_cls + c)*L + 1 + i, :]  (gradient of the learnable
  * context vectors, tpt_cls_rl.py:103-105,119-120). */
 int rlcf_ctx_grad(const float* dx, int n_sets, int n_cls, int L, int n_ctx, int d, float* dctx, void* stream);
+/* PromptLearner.forward for every layout (custom_clip.py:198-289: class token at the end, in the middle or at the front
+ * of the context; learned class tokens, 209-221): src_map int32 [n_cls, L]: entry >= 0 = position inside the class's own
+ * token row whose frozen embedding is used, entry < 0 = learnable vector -1 - entry of the set (vec + g*vec_stride:
+ * context vectors, then one class vector per class).  x rows (g, c, t) = source + pos[t]. */
+int rlcf_embed_prompts_map(const int64_t* tokens, const float* tok_emb, const float* pos, const float* vec,
+                           int64_t vec_stride, const int32_t* src_map, int n_sets, int n_cls, int L, int d, float* x,
+                           void* stream);
+/* Its backward onto the learnable vectors: ctx_pos int32 [n_cls, n_ctx] = token position of context vector v in class c;
+ * cls_pos int32 [n_cls] (NULL without learned class tokens) = position of class c's own vector.
+ * dvec [n_sets, n_ctx (+ n_cls), d]. */
+int rlcf_vec_grad_map(const float* dx, const int32_t* ctx_pos, const int32_t* cls_pos, int n_sets, int n_cls, int L,
+                      int n_ctx, int d, float* dvec, void* stream);
 
 /* Fused gradient reduction + AdamW (torch.optim.AdamW semantics, tune_cls_rl.py:79-81, tpt_cls_rl.py:76-79):
  * g = sum over slots of partials / loss_scale; decoupled weight decay; bias-corrected moments.

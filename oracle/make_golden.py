@@ -79,6 +79,18 @@ PROMPT_CASES = {
     # TPT/tpt_cls.py:49-78, 8 views, selection_p 0.5, 4 images, C = 32 synthetic class names "class i", lr 5e-3, 1 step
     "b32_cfg1_exact": dict(policy="ViT-B/32", reward=None, V=8, rho=0.5, K=3, C=32, steps=1, lr=5e-3, n_img=4,
                            ctx_init="a_photo_of_a", loss="tpt", classnames="class_i", policy_seed=2, view_seed=1),
+    # class token in the middle / at the front of the context, "[CLS]" inside ctx_init, learned class tokens
+    # (custom_clip.py:198-289, 209-221): never used by the shipped scripts, pinned here for the drop-in surface
+    "tiny_prompt_middle": dict(policy="tiny-P", reward="tiny-Q", V=16, rho=0.25, K=3, C=12, steps=2, lr=2e-3, n_img=2,
+                               ctx_init="a_photo_of_a", loss="rlcf", reward_seed=6, ctx_position="middle", view_seed=21),
+    "tiny_prompt_front": dict(policy="tiny-P", reward="tiny-Q", V=16, rho=0.25, K=3, C=12, steps=1, lr=2e-3, n_img=1,
+                              ctx_init="a_photo_of_a", loss="rlcf", reward_seed=6, ctx_position="front", view_seed=22),
+    "tiny_prompt_cls_word": dict(policy="tiny-P", reward="tiny-Q", V=16, rho=0.25, K=3, C=12, steps=1, lr=2e-3, n_img=1,
+                                 ctx_init="a_[CLS]_photo_of_a", loss="rlcf", reward_seed=6, view_seed=23),
+    # learned class tokens with the TPT entropy loss: under RLCF every class prompt reads "... X." for the reward model,
+    # all reward class features coincide, every reward is 0 up to rounding and AdamW would amplify pure noise
+    "tiny_prompt_learned_cls": dict(policy="tiny-P", reward=None, V=16, rho=0.25, K=3, C=12, steps=2, lr=2e-3,
+                                    n_img=2, ctx_init="a_photo_of_a", loss="tpt", learned_cls=True, view_seed=24),
     # prompt-mode RLCF at the real text-tower size (width 512, 12 layers, 8 heads): VERDICT r1 item 6
     "b32_prompt_rlcf": dict(policy="ViT-B/32", reward="ViT-B/32", V=8, rho=0.5, K=3, C=16, steps=1, lr=5e-3, n_img=2,
                             ctx_init="a_photo_of_a", loss="rlcf", reward_seed=4, view_seed=16),
@@ -265,8 +277,10 @@ def run_prompt_case(name: str, cfg: dict, mods) -> dict:
         process_batch=0, cocoop=False)
     classnames = ([f"class {i}" for i in range(cfg["C"])] if cfg.get("classnames") == "class_i"
                   else CLASSNAMES[:cfg["C"]])
+    torch.manual_seed(1234)          # learned class tokens are drawn from the global generator (custom_clip.py:131-132)
     model = custom_clip.ClipTestTimeTuning("cpu", classnames, None, arch=cfg["policy"], n_ctx=4,
-                                           ctx_init=cfg["ctx_init"])
+                                           ctx_init=cfg["ctx_init"], ctx_position=cfg.get("ctx_position", "end"),
+                                           learned_cls=cfg.get("learned_cls", False))
     for n, prm in model.named_parameters():                                          # tpt_cls_rl.py:103-105
         if "prompt_learner" not in n:
             prm.requires_grad_(False)
@@ -317,11 +331,16 @@ def run_prompt_case(name: str, cfg: dict, mods) -> dict:
             out[f"img{i}.topk_idx"] = torch.stack([t.reshape(S, K) for t in rec["topk_idx"]]).numpy()
             out[f"img{i}.rewards"] = torch.stack([t.reshape(S, K) for t in rec["rewards"]]).numpy()
             out[f"img{i}.logits_final"] = final.numpy()
-            out[f"img{i}.params"] = model.prompt_learner.ctx.detach().flatten().numpy().copy()
+            out[f"img{i}.params"] = torch.cat([p_.detach().flatten() for p_ in model.prompt_learner.parameters()]).numpy().copy()
     finally:
         tpt_cls_rl.select_confident_samples = orig_select
     out["tokens"] = model.prompt_learner.tokenized_prompts.numpy()
     out["ctx_init"] = model.prompt_learner.ctx_init_state.numpy()
+    if cfg.get("learned_cls"):
+        out["cls_init"] = model.prompt_learner.cls_init_state.numpy()
+    with torch.no_grad():
+        model.reset()
+        out["prompts0"] = model.prompt_learner().numpy()      # the assembled prompt embeddings [C, 77, d] at the reset state
     out["reward_cls"] = reward_model.class_features.numpy()
     out["meta"] = np.array(repr(cfg))
     return out
@@ -356,11 +375,16 @@ def run_tpt_prompt_loop(name, cfg, model, optimizer, optim_state, scaler, args) 
             out[f"img{i}.logits_all"] = rec["logits_all"].numpy()
             out[f"img{i}.selected_idx"] = rec["selected_idx"].numpy()
             out[f"img{i}.logits_final"] = final.numpy()
-            out[f"img{i}.params"] = model.prompt_learner.ctx.detach().flatten().numpy().copy()
+            out[f"img{i}.params"] = torch.cat([p_.detach().flatten() for p_ in model.prompt_learner.parameters()]).numpy().copy()
     finally:
         tpt_cls.select_confident_samples = orig_select
     out["tokens"] = model.prompt_learner.tokenized_prompts.numpy()
     out["ctx_init"] = model.prompt_learner.ctx_init_state.numpy()
+    if cfg.get("learned_cls"):
+        out["cls_init"] = model.prompt_learner.cls_init_state.numpy()
+    with torch.no_grad():
+        model.reset()
+        out["prompts0"] = model.prompt_learner().numpy()
     out["meta"] = np.array(repr(cfg))
     return out
 

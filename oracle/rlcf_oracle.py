@@ -355,31 +355,66 @@ def adapt_one_image(sd_policy: dict, class_feat: torch.Tensor, views: torch.Tens
     return out
 
 
-def prompt_text_features(sd: dict, tokens: torch.Tensor, ctx: torch.Tensor) -> torch.Tensor:
-    """PromptLearner.forward with the class token at the end (TPT/clip/custom_clip.py:198-232) followed by
-    ClipTestTimeTuning.get_text_features (315-323): L2-normalised text features [C, E], differentiable in ctx."""
+def prompt_source_map(tokens: torch.Tensor, n_ctx: int, position: str = "end", split_idx=None,
+                      learned_cls: bool = False) -> torch.Tensor:
+    """Where every position of every class prompt comes from in PromptLearner.forward (TPT/clip/custom_clip.py:198-289):
+    src[c, t] >= 0 = position in class c's own tokenised prompt (frozen embedding), src[c, t] < 0 = learnable vector
+    -1 - src (context vectors 0..n_ctx-1; with learned class tokens, custom_clip.py:209-221, vector n_ctx + c).
+    The tokenised prompt is [SOS, n_ctx placeholder words, class-name tokens, '.', EOS, padding]."""
+    C, L = tokens.shape
+    src = torch.arange(L).repeat(C, 1)
+    half = split_idx if split_idx is not None else n_ctx // 2
+    for c in range(C):
+        n = 1 if learned_cls else int(tokens[c].argmax()) - n_ctx - 2
+        name = [1 + n_ctx + k for k in range(n)]
+        ctx = [-1 - v for v in range(n_ctx)]
+        if position == "end":
+            order = ctx + ([-1 - (n_ctx + c)] if learned_cls else name)
+        elif position == "middle":
+            order = ctx[:half] + name + ctx[half:]
+        elif position == "front":
+            order = name + ctx
+        else:
+            raise ValueError(position)
+        src[c, 1:1 + len(order)] = torch.tensor(order)
+    return src
+
+
+def prompt_text_features(sd: dict, tokens: torch.Tensor, ctx: torch.Tensor, src_map: torch.Tensor | None = None,
+                         cls: torch.Tensor | None = None) -> torch.Tensor:
+    """PromptLearner.forward (TPT/clip/custom_clip.py:198-289; src_map=None: class token at the end, 229-246) followed
+    by ClipTestTimeTuning.get_text_features (315-323): L2-normalised text features [C, E], differentiable in ctx (and
+    in the learned class vectors `cls` [C, d])."""
     emb = sd["token_embedding.weight"][tokens]                         # frozen prefix (SOS) and suffix (class, EOS)
     n_ctx = ctx.shape[0]
-    prompts = torch.cat([emb[:, :1, :], ctx.unsqueeze(0).expand(tokens.shape[0], -1, -1), emb[:, 1 + n_ctx:, :]], dim=1)
+    if src_map is None:
+        prompts = torch.cat([emb[:, :1, :], ctx.unsqueeze(0).expand(tokens.shape[0], -1, -1), emb[:, 1 + n_ctx:, :]], dim=1)
+    else:
+        vecs = ctx if cls is None else torch.cat([ctx, cls.reshape(tokens.shape[0], -1)], dim=0)
+        frozen = torch.gather(emb, 1, src_map.clamp_min(0).unsqueeze(-1).expand(-1, -1, emb.shape[-1]))
+        prompts = torch.where((src_map < 0).unsqueeze(-1), vecs[(-1 - src_map).clamp_min(0)], frozen)
     t = text_from_embeddings(sd, prompts, tokens)
     return t / t.norm(dim=-1, keepdim=True)
 
 
 def adapt_one_image_prompt(sd_policy: dict, tokens: torch.Tensor, ctx_init: torch.Tensor, views: torch.Tensor,
                            cfg: OracleConfig, sd_reward: dict | None = None,
-                           reward_cls: torch.Tensor | None = None) -> dict:
+                           reward_cls: torch.Tensor | None = None, src_map: torch.Tensor | None = None,
+                           cls_init: torch.Tensor | None = None) -> dict:
     """One iteration of the per-image loop of TPT/tpt_cls_rl.py:219-279 (prompt tuning): reset the context vectors,
     test_time_tuning (47-79) with ClipTestTimeTuning.inference (custom_clip.py:325-335: image tower under no_grad,
     text tower differentiable), AdamW on ctx only (tpt_cls_rl.py:103-120), adapted prediction on views[0]."""
     ctx = ctx_init.clone().requires_grad_(True)                                              # prompt_learner.reset()
-    opt = torch.optim.AdamW([ctx], cfg.lr, weight_decay=cfg.weight_decay)
+    cls = None if cls_init is None else cls_init.clone().requires_grad_(True)                # learned class tokens
+    trainable = [ctx] if cls is None else [ctx, cls]                                         # prompt_learner.parameters()
+    opt = torch.optim.AdamW(trainable, cfg.lr, weight_decay=cfg.weight_decay)
     scale = sd_policy["logit_scale"].exp()
 
     def model(images):
         with torch.no_grad():
             f = encode_image(sd_policy, images)
         f = f / f.norm(dim=-1, keepdim=True)
-        return scale * f @ prompt_text_features(sd_policy, tokens, ctx).t()
+        return scale * f @ prompt_text_features(sd_policy, tokens, ctx, src_map, cls).t()
 
     out = {"losses": [], "grads": []}
     selected_idx = None
@@ -407,12 +442,12 @@ def adapt_one_image_prompt(sd_policy: dict, tokens: torch.Tensor, ctx_init: torc
             loss = avg_entropy(output)
         opt.zero_grad()
         loss.backward()
-        out["grads"].append(ctx.grad.flatten().clone())
+        out["grads"].append(torch.cat([p.grad.flatten() for p in trainable]).clone())
         opt.step()
         out["losses"].append(float(loss.detach()))
     with torch.no_grad():
         out["logits_final"] = model(views[:1])
-    out["params"] = ctx.detach().flatten().clone()
+    out["params"] = torch.cat([p.detach().flatten() for p in trainable]).clone()
     return out
 
 

@@ -57,6 +57,8 @@ _PROTOS = {
     "rlcf_embed_prompts": [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp],
     "rlcf_pair_logits": [_vp, _vp, _i64, _i, _i, _i, _i, _f, _vp, _vp],
     "rlcf_ctx_grad": [_vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "rlcf_embed_prompts_map": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _vp, _vp],
+    "rlcf_vec_grad_map": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "rlcf_adamw_step": [_vp, _vp, _vp, _vp, _i, _i, _i64, _f, _f, _f, _f, _f, _i, _f, _vp, _vp],
     "rlcf_reset_params": [_vp, _vp, _vp, _vp, _i, _i64, _vp],
     "rlcf_cast_f16": [_vp, _i64, _i64, _i64, _vp, _i64, _vp],

@@ -69,23 +69,35 @@ class TextEncoder(nn.Module):
 
 
 class PromptLearner(nn.Module):
-    """CoOp-style learnable context (custom_clip.py:76-289): prompts = [SOS | ctx (n_ctx x d) | class tokens, EOS].
-    Supported: class token at the end, shared context (`batch_size=None`), fixed class tokens (`learned_cls=False`)
-    -- the configuration of every RLCF / TPT script.  `tokenized_prompts` / `ctx_tokens` bypass the BPE tokenizer."""
+    """CoOp-style learnable context (custom_clip.py:76-289).  Prompts are assembled from the SOS embedding, the n_ctx
+    learnable context vectors, the class-name tokens and the rest (".", EOS, padding) with the class token at the
+    `end` ([SOS | ctx | class ...], every RLCF / TPT script), in the `middle` ([SOS | ctx[:h] | class | ctx[h:] | ...],
+    also selected by a "[CLS]" word inside `ctx_init`) or at the `front` ([SOS | class | ctx | ...]); `learned_cls`
+    replaces the class-name token by one learnable vector per class (custom_clip.py:209-221, position `end` only).
+    `batch_size` (one context per view, custom_clip.py:120-122) is not supported.  `tokenized_prompts` / `ctx_tokens`
+    bypass the BPE tokenizer (synthetic vocabularies); `cls_init` fixes the initial learned class vectors."""
 
     def __init__(self, clip_model, classnames, batch_size=None, n_ctx=16, ctx_init=None, ctx_position="end",
-                 learned_cls=False, tokenized_prompts=None, ctx_tokens=None):
+                 learned_cls=False, tokenized_prompts=None, ctx_tokens=None, cls_init=None):
         super().__init__()
-        if learned_cls or batch_size is not None or ctx_position != "end" or (ctx_init and "[CLS]" in ctx_init):
-            raise NotImplementedError("only ctx_position='end', batch_size=None, learned_cls=False are supported")
+        if batch_size is not None:
+            raise NotImplementedError("PromptLearner(batch_size=...) (one context per view) is not supported")
+        if ctx_position not in ("end", "middle", "front"):
+            raise ValueError(f"ctx_position {ctx_position!r}")
         self.learned_cls, self.batch_size = learned_cls, batch_size
         self.dtype = clip_model.dtype
         self.device = clip_model.visual.conv1.weight.device
         self.ctx_dim = clip_model.ln_final.weight.shape[0]
         object.__setattr__(self, "_clip", clip_model)
+        split_idx = None
         if ctx_init or ctx_tokens is not None:
-            if ctx_tokens is None:
+            if ctx_init:
                 ctx_init = ctx_init.replace("_", " ")
+                if "[CLS]" in ctx_init:                                   # custom_clip.py:93-99
+                    split_idx = ctx_init.split(" ").index("[CLS]")
+                    ctx_init = ctx_init.replace("[CLS] ", "")
+                    ctx_position = "middle"
+            if ctx_tokens is None:
                 n_ctx = len(ctx_init.split(" "))
                 ctx_tokens = tokenize(ctx_init)[0, 1:1 + n_ctx]
             n_ctx = len(ctx_tokens)
@@ -96,43 +108,129 @@ class PromptLearner(nn.Module):
             ctx_vectors = torch.empty(n_ctx, self.ctx_dim, dtype=self.dtype, device=self.device)
             nn.init.normal_(ctx_vectors, std=0.02)
             prompt_prefix = " ".join(["X"] * n_ctx)
-        self.prompt_prefix, self.split_idx = prompt_prefix, None
+        if learned_cls and ctx_position != "end":
+            raise AssertionError("learned_cls needs ctx_position='end' (custom_clip.py:227-228)")
+        self.prompt_prefix, self.split_idx = prompt_prefix, split_idx
         self.ctx_init_state = ctx_vectors.detach().clone()
         self.ctx = nn.Parameter(ctx_vectors.detach().clone())
         self.ctx_init, self.class_token_position, self.n_ctx = ctx_init, ctx_position, n_ctx
-        self._set_classes(classnames, tokenized_prompts)
+        self._set_classes(classnames, tokenized_prompts, cls_init)
 
-    def _set_classes(self, classnames, tokenized_prompts):
+    def _set_classes(self, classnames, tokenized_prompts, cls_init=None):
         self.n_cls = len(classnames)
         self.classnames = [name.replace("_", " ") for name in classnames]
+        if self.learned_cls:
+            # one learnable vector per class in place of the class-name token "X" (custom_clip.py:130-140)
+            if cls_init is None:
+                cls_init = torch.empty(self.n_cls, 1, self.ctx_dim, dtype=self.dtype, device=self.device)
+                nn.init.normal_(cls_init, std=0.02)
+            cls_init = cls_init.to(device=self.device, dtype=self.dtype).reshape(self.n_cls, 1, self.ctx_dim)
+            self.cls_init_state = cls_init.detach().clone()
+            if hasattr(self, "cls") and self.cls.shape == cls_init.shape:
+                with torch.no_grad():
+                    self.cls.copy_(cls_init)
+            else:
+                self.cls = nn.Parameter(cls_init.detach().clone())
         if tokenized_prompts is None:
-            prompts = [self.prompt_prefix + " " + name + "." for name in self.classnames]
+            names = ["X"] * self.n_cls if self.learned_cls else self.classnames
+            prompts = [self.prompt_prefix + " " + name + "." for name in names]
             tokenized_prompts = torch.cat([tokenize(p) for p in prompts])
         self.tokenized_prompts = tokenized_prompts.to(self.device)
-        self.name_lens = [int(t.argmax()) - 1 - self.n_ctx - 1 for t in self.tokenized_prompts]
+        # tokens: SOS, n_ctx placeholder words, the class name, ".", EOS -> name_len = eot - n_ctx - 2
+        self.name_lens = [1 if self.learned_cls else int(t.argmax()) - 1 - self.n_ctx - 1 for t in self.tokenized_prompts]
         with torch.no_grad():
             embedding = self._clip.token_embedding(self.tokenized_prompts).type(self.dtype)
         self.token_prefix = embedding[:, :1, :]                  # SOS
-        self.token_suffix = embedding[:, 1 + self.n_ctx:, :]     # class tokens, EOS, padding
+        skip = 1 if self.learned_cls else 0
+        self.token_suffix = embedding[:, 1 + self.n_ctx + skip:, :]     # class tokens, EOS, padding
+        self._layout = None
+
+    # ---- where every position of every class prompt comes from (custom_clip.py:229-289)
+    def source_map(self):
+        """(src_map [C, L], ctx_pos [C, n_ctx], cls_pos [C] | None) as int32 CPU tensors; see engine.PromptLayout."""
+        C, L, n_ctx = self.n_cls, self.tokenized_prompts.shape[1], self.n_ctx
+        src = torch.arange(L, dtype=torch.int32).repeat(C, 1)
+        ctx_pos = torch.empty(C, n_ctx, dtype=torch.int32)
+        cls_pos = torch.full((C,), 1 + n_ctx, dtype=torch.int32) if self.learned_cls else None
+        where = self.class_token_position
+        half = self.split_idx if self.split_idx is not None else n_ctx // 2
+        for c in range(C):
+            n = self.name_lens[c]
+            if where == "end":
+                order = [("ctx", v) for v in range(n_ctx)]
+                if self.learned_cls:
+                    order.append(("cls", c))
+                else:
+                    order += [("tok", 1 + n_ctx + k) for k in range(n)]
+            elif where == "middle":
+                order = ([("ctx", v) for v in range(half)] + [("tok", 1 + n_ctx + k) for k in range(n)]
+                         + [("ctx", v) for v in range(half, n_ctx)])
+            else:
+                order = [("tok", 1 + n_ctx + k) for k in range(n)] + [("ctx", v) for v in range(n_ctx)]
+            for t, (kind, v) in enumerate(order, start=1):
+                if kind == "ctx":
+                    src[c, t] = -1 - v
+                    ctx_pos[c, v] = t
+                elif kind == "cls":
+                    src[c, t] = -1 - (n_ctx + v)
+                else:
+                    src[c, t] = v
+        return src, ctx_pos, cls_pos
+
+    def layout(self):
+        """engine.PromptLayout on the device, or None for the default arrangement (served by the specialised kernels)."""
+        if self.class_token_position == "end" and not self.learned_cls:
+            return None
+        if self._layout is None:
+            src, ctx_pos, cls_pos = self.source_map()
+            dev = self.device
+            self._layout = E.PromptLayout(src.to(dev).contiguous(), ctx_pos.to(dev).contiguous(),
+                                          None if cls_pos is None else cls_pos.to(dev).contiguous(), self.n_ctx)
+        return self._layout
+
+    def learnable_flat(self):
+        """The trainable vectors as the engine's flat block: context vectors, then the learned class vectors."""
+        parts = [self.ctx.detach().reshape(-1)]
+        if self.learned_cls:
+            parts.append(self.cls.detach().reshape(-1))
+        return torch.cat(parts).float()
+
+    @torch.no_grad()
+    def load_flat(self, flat):
+        n = self.ctx.numel()
+        self.ctx.copy_(flat[:n].view_as(self.ctx))
+        if self.learned_cls:
+            self.cls.copy_(flat[n:n + self.cls.numel()].view_as(self.cls))
 
     @torch.no_grad()
     def reset(self):
         self.ctx.copy_(self.ctx_init_state)
+        if self.learned_cls:
+            self.cls.copy_(self.cls_init_state)
 
-    def reset_classnames(self, classnames, arch, tokenized_prompts=None):
-        self._set_classes(classnames, tokenized_prompts)
+    def reset_classnames(self, classnames, arch, tokenized_prompts=None, cls_init=None):
+        self._set_classes(classnames, tokenized_prompts, cls_init)
 
     def forward(self, init=None):
+        """Prompt embeddings [C, L, d] (custom_clip.py:198-289), assembled from the source map."""
         ctx = self.ctx if init is None else init
-        ctx = ctx.unsqueeze(0).expand(self.n_cls, -1, -1)
-        return torch.cat([self.token_prefix, ctx, self.token_suffix], dim=-2)
+        emb = self._clip.token_embedding(self.tokenized_prompts).type(self.dtype)
+        if self.class_token_position == "end" and not self.learned_cls:
+            return torch.cat([self.token_prefix, ctx.unsqueeze(0).expand(self.n_cls, -1, -1), self.token_suffix], dim=-2)
+        src, _, _ = self.source_map()
+        src = src.to(emb.device).long()
+        vecs = ctx if not self.learned_cls else torch.cat([ctx, self.cls.reshape(self.n_cls, -1)], dim=0)
+        out = torch.gather(emb, 1, src.clamp_min(0).unsqueeze(-1).expand(-1, -1, emb.shape[-1]))
+        learn = src < 0
+        out = torch.where(learn.unsqueeze(-1), vecs[(-1 - src).clamp_min(0)], out)
+        return out
 
 
 class ClipTestTimeTuning(nn.Module):
     """Prompt-tuning policy (custom_clip.py:292-344): frozen CLIP + PromptLearner; forward(image) -> logits [N, C]."""
 
     def __init__(self, device, classnames, batch_size, criterion="cosine", arch="ViT-L/14", n_ctx=16, ctx_init=None,
-                 ctx_position="end", learned_cls=False, tokenized_prompts=None, ctx_tokens=None):
+                 ctx_position="end", learned_cls=False, tokenized_prompts=None, ctx_tokens=None, cls_init=None):
         super().__init__()
         clip_model, _, _ = load(arch, device=device, download_root=DOWNLOAD_ROOT)
         object.__setattr__(self, "_clip", clip_model)
@@ -140,7 +238,7 @@ class ClipTestTimeTuning(nn.Module):
         self.text_encoder = TextEncoder(clip_model)
         self.logit_scale = clip_model.logit_scale.data
         self.prompt_learner = PromptLearner(clip_model, classnames, batch_size, n_ctx, ctx_init, ctx_position,
-                                            learned_cls, tokenized_prompts, ctx_tokens)
+                                            learned_cls, tokenized_prompts, ctx_tokens, cls_init)
         self.criterion = criterion
         self._engines = {}
 
@@ -180,14 +278,16 @@ class ClipTestTimeTuning(nn.Module):
         if reward_model is not None:
             rew, rcls, cfg.reward_weights = _reward_inputs(reward_model)
         pl = self.prompt_learner
+        layout = pl.layout()
         key = (id(vis), id(txt), _ids(rew), n_img, tuple(sorted(vars(cfg).items())), pl.tokenized_prompts.data_ptr(),
-               _ptrs(rcls))
+               _ptrs(rcls), id(layout))
         hit = self._engines.get(key)
         if hit is None:
             self._engines.clear()
-            eng = E.PromptEngine(vis, txt, pl.tokenized_prompts, pl.ctx.detach(), float(self.logit_scale.exp()), cfg,
-                                 n_img, reward=rew, reward_class_feat=rcls)
-            hit = self._engines[key] = (eng, (vis, txt, rew, rcls, pl.tokenized_prompts))   # refs pin the keyed ids
+            vecs = pl.learnable_flat().view(-1, pl.ctx_dim)
+            eng = E.PromptEngine(vis, txt, pl.tokenized_prompts, vecs, float(self.logit_scale.exp()), cfg,
+                                 n_img, reward=rew, reward_class_feat=rcls, layout=layout)
+            hit = self._engines[key] = (eng, (vis, txt, rew, rcls, pl.tokenized_prompts, layout))   # refs pin the keyed ids
         return hit[0]
 
 

@@ -110,6 +110,9 @@ int embed_prompts(const long long*, const float*, const float*, const float*, lo
                   float*, cudaStream_t);
 int pair_logits(const float*, const float*, long long, int, int, int, int, float, float*, cudaStream_t);
 int ctx_grad(const float*, int, int, int, int, int, float*, cudaStream_t);
+int embed_prompts_map(const long long*, const float*, const float*, const float*, long long, const int*, int, int, int,
+                      int, float*, cudaStream_t);
+int vec_grad_map(const float*, const int*, const int*, int, int, int, int, int, float*, cudaStream_t);
 int adamw_step(float*, float*, float*, const float*, int, int, long long, float, float, float, float, float, int,
                float, float*, const float*, long long, int, cudaStream_t);
 int reset_params(const float*, float*, float*, float*, int, long long, cudaStream_t);
@@ -329,6 +332,21 @@ int rlcf_pair_logits(const float* img_feat, const float* txt_feat, int64_t txt_s
                      int E, float logit_scale, float* logits, void* stream) {
   if (!img_feat || !txt_feat || !logits) return set_error(RLCF_ERR_ARG, "pair_logits: null pointer");
   return pair_logits(img_feat, txt_feat, txt_set_stride, n_sets, S_, C, E, logit_scale, logits, S(stream));
+}
+
+int rlcf_embed_prompts_map(const int64_t* tokens, const float* tok_emb, const float* pos, const float* vec,
+                           int64_t vec_stride, const int32_t* src_map, int n_sets, int n_cls, int L, int d, float* x,
+                           void* stream) {
+  if (!tokens || !tok_emb || !pos || !vec || !src_map || !x)
+    return set_error(RLCF_ERR_ARG, "embed_prompts_map: null pointer");
+  return embed_prompts_map(reinterpret_cast<const long long*>(tokens), tok_emb, pos, vec, vec_stride, src_map, n_sets,
+                           n_cls, L, d, x, S(stream));
+}
+
+int rlcf_vec_grad_map(const float* dx, const int32_t* ctx_pos, const int32_t* cls_pos, int n_sets, int n_cls, int L,
+                      int n_ctx, int d, float* dvec, void* stream) {
+  if (!dx || !ctx_pos || !dvec) return set_error(RLCF_ERR_ARG, "vec_grad_map: null pointer");
+  return vec_grad_map(dx, ctx_pos, cls_pos, n_sets, n_cls, L, n_ctx, d, dvec, S(stream));
 }
 
 int rlcf_ctx_grad(const float* dx, int n_sets, int n_cls, int L, int n_ctx, int d, float* dctx, void* stream) {

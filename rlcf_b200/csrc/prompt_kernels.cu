@@ -47,6 +47,87 @@ int embed_prompts(const long long* tokens, const float* tok_emb, const float* po
   return 0;
 }
 
+// General prompt layout (custom_clip.py:233-289: class token in the middle / at the front, custom_clip.py:209-221:
+// learnable class tokens): src_map[c][t] >= 0 takes the frozen embedding of tokens[c][src_map[c][t]], src_map[c][t] < 0
+// takes learnable vector v = -1 - src_map[c][t] of the parameter set, vec[g][v][:] (context vectors first, then -- with
+// learned class tokens -- one vector per class).  Row (g, c, t) = source + pos[t].
+__global__ void embed_prompts_map_kernel(const long long* __restrict__ tokens, const float* __restrict__ emb,
+                                         const float* __restrict__ pos, const float* __restrict__ vec,
+                                         long long vec_stride, const int* __restrict__ src_map, int n_cls, int L, int d4,
+                                         long long total, float* __restrict__ x) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % d4);
+    const long long row = i / d4;
+    const int t = static_cast<int>(row % L);
+    const long long seq = row / L;
+    const int c = static_cast<int>(seq % n_cls);
+    const long long g = seq / n_cls;
+    const int m = src_map[c * L + t];
+    float4 a;
+    if (m < 0) {
+      a = reinterpret_cast<const float4*>(vec + g * vec_stride)[static_cast<long long>(-1 - m) * d4 + c4];
+    } else {
+      const long long tok = tokens[static_cast<long long>(c) * L + m];
+      a = __ldg(reinterpret_cast<const float4*>(emb) + tok * d4 + c4);
+    }
+    const float4 b = __ldg(reinterpret_cast<const float4*>(pos) + static_cast<long long>(t) * d4 + c4);
+    reinterpret_cast<float4*>(x)[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+
+int embed_prompts_map(const long long* tokens, const float* tok_emb, const float* pos, const float* vec,
+                      long long vec_stride, const int* src_map, int n_sets, int n_cls, int L, int d, float* x,
+                      cudaStream_t stream) {
+  if (n_sets <= 0 || n_cls <= 0 || L <= 0 || d % 4) return set_error(RLCF_ERR_ARG, "embed_prompts_map: bad shape");
+  const long long total = static_cast<long long>(n_sets) * n_cls * L * (d / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  embed_prompts_map_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(tokens, tok_emb, pos, vec, vec_stride, src_map,
+                                                                         n_cls, L, d / 4, total, x);
+  RLCF_CHECK_LAUNCH("embed_prompts_map");
+  return 0;
+}
+
+// Gradient of the learnable vectors under a general layout: context vector v (< n_ctx) appears once in every class, at
+// token position ctx_pos[c][v]: d vec[g][v] = sum_c dx[g, c, ctx_pos[c][v]] (fixed order: deterministic); the class
+// vector of class c (learned class tokens, cls_pos != NULL) sits at cls_pos[c]: d vec[g][n_ctx + c] = dx[g, c, cls_pos[c]].
+__global__ void vec_grad_map_kernel(const float* __restrict__ dx, const int* __restrict__ ctx_pos,
+                                    const int* __restrict__ cls_pos, int n_cls, int L, int n_ctx, int n_vec, int d4,
+                                    long long total, float* __restrict__ dvec) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % d4);
+    const int v = static_cast<int>((i / d4) % n_vec);
+    const long long g = i / (static_cast<long long>(d4) * n_vec);
+    const float4* base = reinterpret_cast<const float4*>(dx) + (g * n_cls) * L * d4 + c4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (v < n_ctx) {
+      for (int c = 0; c < n_cls; ++c) {
+        const float4 u = base[(static_cast<long long>(c) * L + ctx_pos[c * n_ctx + v]) * d4];
+        acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
+      }
+    } else {
+      const int c = v - n_ctx;
+      acc = base[(static_cast<long long>(c) * L + cls_pos[c]) * d4];
+    }
+    reinterpret_cast<float4*>(dvec)[i] = acc;
+  }
+}
+
+int vec_grad_map(const float* dx, const int* ctx_pos, const int* cls_pos, int n_sets, int n_cls, int L, int n_ctx,
+                 int d, float* dvec, cudaStream_t stream) {
+  if (n_sets <= 0 || n_cls <= 0 || n_ctx <= 0 || d % 4) return set_error(RLCF_ERR_ARG, "vec_grad_map: bad shape");
+  const int n_vec = n_ctx + (cls_pos != nullptr ? n_cls : 0);
+  const long long total = static_cast<long long>(n_sets) * n_vec * (d / 4);
+  long long blocks = (total + 127) / 128;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  vec_grad_map_kernel<<<static_cast<int>(blocks), 128, 0, stream>>>(dx, ctx_pos, cls_pos, n_cls, L, n_ctx, n_vec, d / 4,
+                                                                    total, dvec);
+  RLCF_CHECK_LAUNCH("vec_grad_map");
+  return 0;
+}
+
 // logits[g, s, c] = logit_scale * <img[g, s, :], txt[g, c, :]>   (ClipTestTimeTuning.inference, custom_clip.py:325-335)
 // txt_stride = 0 shares one set of text features across images.  One warp per (g, s, c).
 __global__ void __launch_bounds__(256)

@@ -210,6 +210,21 @@ class EmbedRows:
     stride: int
 
 
+@dataclass
+class PromptLayout:
+    """Where the learnable vectors sit inside the class prompts (PromptLearner.forward, custom_clip.py:198-289) when it
+    is not the default [SOS | ctx | class tokens ...]: class token in the middle / at the front of the context, learned
+    class tokens.  Learnable vectors of one parameter set: n_ctx context vectors, then (cls_pos given) one per class."""
+    src_map: torch.Tensor          # int32 [C, L]: >= 0 position in the class's own token row, < 0 learnable vector -1-m
+    ctx_pos: torch.Tensor          # int32 [C, n_ctx]: token position of context vector v in class c
+    cls_pos: torch.Tensor | None   # int32 [C]: token position of class c's learnable class vector
+    n_ctx: int
+
+    @property
+    def n_vec(self):
+        return self.n_ctx + (0 if self.cls_pos is None else self.cls_pos.numel())
+
+
 class ActStore:
     """Activations one training-mode forward keeps for the backward (per layer, for `rows` token rows)."""
 
@@ -308,8 +323,12 @@ class TowerRunner:
             elif isinstance(prompt, torch.Tensor):   # ready-made prompt embeddings [n_seq, L, d] (TextEncoder.forward)
                 x[:n_seq * w.L].copy_((prompt.float() + w.pos).reshape(n_seq * w.L, w.d))
             elif prompt is not None:   # learnable context vectors spliced into the class prompts (PromptLearner)
-                ctx, ctx_stride, n_ctx, n_sets = prompt
-                ops.embed_prompts(tokens, w.tok_emb, w.pos, ctx, ctx_stride, n_ctx, n_sets, x)
+                ctx, ctx_stride, n_ctx, n_sets = prompt[:4]
+                layout = prompt[4] if len(prompt) > 4 else None
+                if layout is None:
+                    ops.embed_prompts(tokens, w.tok_emb, w.pos, ctx, ctx_stride, n_ctx, n_sets, x)
+                else:
+                    ops.embed_prompts_map(tokens, w.tok_emb, w.pos, ctx, ctx_stride, layout.src_map, n_sets, x)
             else:
                 ops.embed_text(tokens, w.tok_emb, w.pos, x)
         for l, lw in enumerate(w.layers):
@@ -665,21 +684,27 @@ class PromptEngine:
 
     def __init__(self, visual: TowerWeights, text: TowerWeights, tokens: torch.Tensor, ctx_init: torch.Tensor,
                  logit_scale: float, cfg: RlcfConfig, n_img: int, reward: TowerWeights | None = None,
-                 reward_class_feat: torch.Tensor | None = None):
+                 reward_class_feat: torch.Tensor | None = None, layout: PromptLayout | None = None):
+        """ctx_init: the learnable vectors [n_vec, d] -- the context vectors, followed (layout.cls_pos) by one learnable
+        class vector per class.  layout=None is the default arrangement [SOS | ctx | class tokens, EOS]."""
         if text.layers[0].wqkv_t is None:
             raise RlcfError("text tower must be prepared with need_grad=True")
+        self.layout = layout
+        if layout is not None and ctx_init.shape[0] != layout.n_vec:
+            raise RlcfError(f"{ctx_init.shape[0]} learnable vectors given, the layout has {layout.n_vec}")
         dev = text.ln_flat.device
         self.cfg, self.n_img, self.visual, self.text, self.reward = cfg, n_img, visual, text, reward
         self.logit_scale = float(logit_scale)
         self.tokens = tokens.to(device=dev, dtype=torch.int64).contiguous()
         C, L = self.tokens.shape
-        self.n_ctx, d = ctx_init.shape
+        n_vec, d = ctx_init.shape
+        self.n_ctx = n_vec if layout is None else layout.n_ctx
         B, V, S = n_img, cfg.n_views, cfg.n_selected
         if S < 1:
             raise RlcfError(f"int(n_views * selection_p) = {S}: no view would be selected (tpt_cls_rl.py:34)")
         if cfg.loss == "rlcf" and (reward is None or reward_class_feat is None):
             raise RlcfError("RLCF loss needs a reward tower and reward class features")
-        self.P = self.n_ctx * d
+        self.P = n_vec * d
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
         self.irun = TowerRunner(visual, B * V)
@@ -731,20 +756,24 @@ class PromptEngine:
             for s in range(0, C, 128):
                 e = min(C, s + 128)
                 frun = TextRunnerF32(txt, e - s) if s == 0 or e - s != frun.max_seq else frun
-                ops.embed_prompts(self.tokens[s:e].contiguous(), txt.tok_emb, txt.pos, self.init_ctx, 0, self.n_ctx, 1,
-                                  frun.x)
+                if self.layout is None:
+                    ops.embed_prompts(self.tokens[s:e].contiguous(), txt.tok_emb, txt.pos, self.init_ctx, 0, self.n_ctx,
+                                      1, frun.x)
+                else:      # class c's own vector index is absolute (n_ctx + c): the map rows carry it
+                    ops.embed_prompts_map(self.tokens[s:e].contiguous(), txt.tok_emb, txt.pos, self.init_ctx, 0,
+                                          self.layout.src_map[s:e].contiguous(), 1, frun.x)
                 x = frun.layers(e - s)
                 rows = (self.eot_rows[s:e] - s * txt.L).contiguous()
                 ops.head_fwd(x, txt.ln_flat[off:], txt.ln_flat[off + txt.d:], txt.proj, e - s, txt.d, txt.E,
                              feat=self.txt_feat0[s:e], row_idx=rows, row_stride=txt.L)
             return
-        x = self.trun.forward(C, txt.ln_flat, tokens=self.tokens, prompt=(self.init_ctx, 0, self.n_ctx, 1))
+        x = self.trun.forward(C, txt.ln_flat, tokens=self.tokens, prompt=(self.init_ctx, 0, self.n_ctx, 1, self.layout))
         self.trun.head(x, C, txt.ln_flat, row_idx=self.eot_rows[:C].contiguous(), feat=self.txt_feat0)
 
     def _text_features(self, store):
         B, C = self.n_img, self.tokens.shape[0]
         x = self.trun.forward(B * C, self.text.ln_flat, tokens=self.tokens, store=store,
-                              prompt=(self.ctx, self.P, self.n_ctx, B))
+                              prompt=(self.ctx, self.P, self.n_ctx, B, self.layout))
         self.trun.head(x, B * C, self.text.ln_flat, row_idx=self.eot_rows, feat=self.txt_feat, inv_norm=self.txt_inv)
         return x
 
@@ -783,7 +812,11 @@ class PromptEngine:
                             self.logit_scale, self.txt_feat, self.txt_inv, B, C, txt.d, E, S, self.trun.dres,
                             row_idx=self.eot_rows)
             self.trun.backward(self.tstore, B, C, txt.ln_flat, 0, None)
-            ops.ctx_grad(self.trun.dres, B, C, L, self.n_ctx, txt.d, self.dctx)
+            if self.layout is None:
+                ops.ctx_grad(self.trun.dres, B, C, L, self.n_ctx, txt.d, self.dctx)
+            else:
+                ops.vec_grad_map(self.trun.dres, self.layout.ctx_pos, self.layout.cls_pos, B, C, L, self.n_ctx, txt.d,
+                                 self.dctx)
             ops.adamw_step(self.ctx, self.m, self.v, self.dctx, B, 1, self.P, cfg.lr, step, beta1=cfg.betas[0],
                            beta2=cfg.betas[1], eps=cfg.eps, weight_decay=cfg.weight_decay,
                            loss_scale=cfg.loss_scale, grad_out=self.grad)

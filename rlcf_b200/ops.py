@@ -297,6 +297,25 @@ def embed_prompts(tokens, tok_emb, pos, ctx, ctx_stride, n_ctx, n_sets, x):
     return x
 
 
+def embed_prompts_map(tokens, tok_emb, pos, vec, vec_stride, src_map, n_sets, x):
+    """x[g, c, t] = (src_map[c, t] >= 0 ? tok_emb[tokens[c, src_map[c, t]]] : vec[g][-1 - src_map[c, t]]) + pos[t]."""
+    _chk(tokens, torch.int64, "tokens"); _chk(tok_emb, torch.float32, "tok_emb"); _chk(vec, torch.float32, "vec")
+    _chk(src_map, torch.int32, "src_map"); _chk(x, torch.float32, "x")
+    n_cls, L = tokens.shape
+    if tuple(src_map.shape) != (n_cls, L):
+        raise _lib.RlcfError("embed_prompts_map: src_map must be [n_cls, L]")
+    call("rlcf_embed_prompts_map", ptr(tokens), ptr(tok_emb), ptr(pos), ptr(vec), vec_stride, ptr(src_map), n_sets, n_cls,
+         L, tok_emb.shape[1], ptr(x), stream())
+    return x
+
+
+def vec_grad_map(dx, ctx_pos, cls_pos, n_sets, n_cls, L, n_ctx, d, dvec):
+    _chk(dx, torch.float32, "dx"); _chk(ctx_pos, torch.int32, "ctx_pos"); _chk(cls_pos, torch.int32, "cls_pos")
+    _chk(dvec, torch.float32, "dvec")
+    call("rlcf_vec_grad_map", ptr(dx), ptr(ctx_pos), ptr(cls_pos), n_sets, n_cls, L, n_ctx, d, ptr(dvec), stream())
+    return dvec
+
+
 def pair_logits(img_feat, txt_feat, txt_set_stride, n_sets, S, C, E, logit_scale, logits):
     _chk(img_feat, torch.float32, "img_feat"); _chk(txt_feat, torch.float32, "txt_feat")
     _chk(logits, torch.float32, "logits")

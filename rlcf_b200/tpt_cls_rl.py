@@ -65,12 +65,11 @@ def test_time_tuning(model, inputs, optimizer, scaler, args, reward_model=None, 
     eng = model.engine(cfg, n_img, reward_model)
     if hasattr(model, "prompt_learner"):           # prompt tuning: the trainable slice is prompt_learner.ctx
         pl = model.prompt_learner
-        eng.init_ctx.copy_(pl.ctx.detach().reshape(-1))
+        eng.init_ctx.copy_(pl.learnable_flat())      # context vectors (+ learned class vectors) of the reset state
         eng.refresh_initial_text_features()
         params = eng.tune(inputs.float().contiguous())
         if n_img == 1:
-            with torch.no_grad():
-                pl.ctx.copy_(params[0].view_as(pl.ctx))
+            pl.load_flat(params[0])
     elif hasattr(eng, "init_rest"):                # full image-encoder tuning (engine built from the current weights)
         params = eng.tune(inputs.float().contiguous())
         if n_img == 1:

@@ -170,12 +170,14 @@ def test_unsupported_modes_fail_loudly():
 def test_prompt_tuning_api_matches_oracle():
     """get_coop / ClipTestTimeTuning / PromptLearner driven like TPT/tpt_cls_rl.py:219-279."""
     from rlcf_b200.clip.custom_clip import get_coop
-    args = make_args(reward_arch="synthetic:tiny-Q:1", tta_steps=1)
+    # reward seed 6: every CLIPScore of the sampled classes is positive (with seed 1 most are clipped to 0 and the
+    # rewards -- hence the whole adaptation -- vanish: the round-1 form of this test compared two un-adapted models)
+    args = make_args(reward_arch="synthetic:tiny-Q:6", tta_steps=1)
     tokens = O.make_tokens(9, 49408)
     tokens[:, 1:5] = torch.tensor([320, 1125, 539, 320])     # every prompt starts with the 4 context tokens
     model = get_coop("synthetic:tiny-P:0", "synthetic", DEV, 4, None, classnames=[f"c{i}" for i in range(9)],
                      tokenized_prompts=tokens)
-    sd_p, sd_r = O.make_clip_state_dict("tiny-P", 0), O.make_clip_state_dict("tiny-Q", 1)
+    sd_p, sd_r = O.make_clip_state_dict("tiny-P", 0), O.make_clip_state_dict("tiny-Q", 6)
     with torch.no_grad():   # random ctx init in the model -> use it as the oracle's starting point
         ctx_init = model.prompt_learner.ctx.detach().cpu().clone()
     for n, p in model.named_parameters():
@@ -207,6 +209,56 @@ def test_prompt_tuning_api_matches_oracle():
     assert d.max() <= 2.02 * 5e-3 and (d <= 0.02 * 5e-3).float().mean() > 0.9
     model.reset()
     assert torch.equal(model.prompt_learner.ctx.detach().cpu(), ctx_init)
+
+
+@pytest.mark.parametrize("name", ["tiny_prompt_middle", "tiny_prompt_learned_cls"])
+def test_prompt_layouts_through_the_api(name):
+    """ClipTestTimeTuning(ctx_position="middle") and (learned_cls=True) through the reference-style loop
+    (tpt_cls_rl.py:219-279): PromptLearner builds the layout itself (real BPE tokens), test_time_tuning adapts the
+    context (and class) vectors in place; against the reference's own outputs (tests/golden, oracle/make_golden.py)."""
+    import ast
+    import os
+    from rlcf_b200.clip import simple_tokenizer as ST
+    from rlcf_b200.clip.custom_clip import ClipTestTimeTuning
+    if ST._find_vocab() is None:
+        pytest.skip("OpenAI BPE vocabulary not available on this machine")
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    cfg = ast.literal_eval(str(z["meta"]))
+    names = ["tench", "goldfish", "great white shark", "tiger shark", "hammerhead", "electric ray", "stingray",
+             "cock", "hen", "ostrich", "brambling", "goldfinch"][:cfg["C"]]
+    learned = bool(cfg.get("learned_cls", False))
+    model = ClipTestTimeTuning(DEV, names, None, arch="synthetic:" + cfg["policy"] + ":0", n_ctx=4,
+                               ctx_init=cfg["ctx_init"], ctx_position=cfg.get("ctx_position", "end"), learned_cls=learned,
+                               cls_init=torch.tensor(z["cls_init"]) if learned else None)
+    assert np.array_equal(model.prompt_learner.tokenized_prompts.cpu().numpy(), z["tokens"])
+    for n, p in model.named_parameters():
+        if "prompt_learner" not in n:
+            p.requires_grad_(False)
+    optimizer = torch.optim.AdamW(model.prompt_learner.parameters(), cfg["lr"], weight_decay=5e-4)
+    optim_state = deepcopy(optimizer.state_dict())
+    reward_model = None
+    if cfg["loss"] == "rlcf":
+        args = make_args(reward_arch=f"synthetic:{cfg['reward']}:{cfg['reward_seed']}", tta_steps=cfg["steps"])
+        reward_model = get_reward_model(DEV, args)
+        reward_model.set_class_features(tokenized_classes=model.prompt_learner.tokenized_prompts)
+    else:
+        args = make_args(tta_steps=cfg["steps"])
+    args.selection_p, args.batch_size = cfg["rho"], cfg["V"]
+    views = O.make_views(cfg["n_img"], cfg["V"], 64, cfg["view_seed"])[:cfg["V"]]
+    model.reset()
+    optimizer.load_state_dict(optim_state)
+    tpt_cls_rl.test_time_tuning(model, views.to(DEV), optimizer, None, args, reward_model=reward_model)
+    out = model(views[:1].to(DEV)).cpu().numpy()[0]
+    scale = np.abs(z["img0.logits_all"]).max()
+    delta = np.abs(z["img0.logits_final"][0] - z["img0.logits_all"][0]).max()
+    PL.check_final_logits(f"api/{name}", out, z["img0.logits_final"][0], scale, delta, allow_delta=0.02,
+                          why="prompt tuning on 128-wide towers (tests/test_parity_gpu.py PROMPT_ALLOW['tiny'])")
+    assert out.argmax() == z["img0.logits_final"][0].argmax()
+    d = (model.prompt_learner.learnable_flat().cpu() - torch.tensor(z["img0.params"])).abs()
+    assert d.max() <= 2.02 * cfg["lr"] * cfg["steps"] + 1e-7
+    assert (d <= 0.05 * cfg["lr"] * cfg["steps"]).float().mean() >= 0.9
+    model.reset()
+    assert torch.equal(model.prompt_learner.ctx.detach().cpu(), torch.tensor(z["ctx_init"]))
 
 
 def test_reward_model_ensemble_through_the_api():

@@ -319,3 +319,42 @@ def test_unsupported_reference_flags_raise():
         _check_supported_flags(build_parser().parse_args(["DATA", "-a", "ViT-B/16"]))        # no --tpt
     with pytest.raises(NotImplementedError):
         _check_supported_flags(build_parser().parse_args(["DATA", "--tpt"]))                 # default arch RN50
+
+
+@pytest.mark.parametrize("name", ["tiny_prompt_middle", "tiny_prompt_front", "tiny_prompt_cls_word",
+                                  "tiny_prompt_learned_cls", "tiny_prompt_rlcf_2step"])
+def test_prompt_learner_layouts_match_the_reference(name):
+    """PromptLearner's source map (class token at the end / in the middle / at the front, "[CLS]" inside ctx_init,
+    learned class tokens; custom_clip.py:198-289) assembles exactly the prompt embeddings the reference's PromptLearner
+    produced (tests/golden/*.npz `prompts0`, written by oracle/make_golden.py)."""
+    import ast
+    import numpy as np
+    if _vocab_path() is None:
+        pytest.skip("OpenAI BPE vocabulary not available on this machine")
+    from rlcf_b200.clip import clip
+    from rlcf_b200.clip.custom_clip import PromptLearner
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    cfg = ast.literal_eval(str(z["meta"]))
+    if "prompts0" not in z.files:
+        pytest.skip("fixture predates prompts0")
+    model, _, _ = clip.load("synthetic:" + cfg["policy"] + ":0", device="cpu")
+    names = ["tench", "goldfish", "great white shark", "tiger shark", "hammerhead", "electric ray", "stingray",
+             "cock", "hen", "ostrich", "brambling", "goldfinch"][:cfg["C"]]
+    learned = bool(cfg.get("learned_cls", False))
+    pl = PromptLearner(model, names, None, n_ctx=4, ctx_init=cfg["ctx_init"], ctx_position=cfg.get("ctx_position", "end"),
+                       learned_cls=learned, cls_init=torch.tensor(z["cls_init"]) if learned else None)
+    assert np.array_equal(pl.tokenized_prompts.numpy(), z["tokens"])
+    assert torch.equal(pl.ctx_init_state, torch.tensor(z["ctx_init"]))
+    with torch.no_grad():
+        assert torch.equal(pl(), torch.tensor(z["prompts0"]))
+    src, ctx_pos, cls_pos = pl.source_map()
+    for c in range(pl.n_cls):       # every context vector appears exactly once per class, where ctx_pos says
+        for v in range(pl.n_ctx):
+            assert src[c, ctx_pos[c, v]] == -1 - v and (src[c] == -1 - v).sum() == 1
+    assert (cls_pos is not None) == learned
+    flat = pl.learnable_flat()
+    assert flat.numel() == (4 + (pl.n_cls if learned else 0)) * 128
+    pl.load_flat(flat + 1.0)
+    assert torch.equal(pl.learnable_flat(), flat + 1.0)
+    pl.reset()
+    assert torch.equal(pl.learnable_flat(), flat)

@@ -125,7 +125,20 @@ def test_selection_edge_cases():
     assert torch.equal(O.rewards_post_process(s), s.flatten())
 
 
-@pytest.mark.parametrize("name", ["tiny_prompt_rlcf_2step", "b32_prompt_rlcf", "b32_cfg1_exact"])
+def prompt_layout_of(cfg, tokens, n_ctx):
+    """(src_map | None, position, split_idx, learned_cls) of a prompt fixture (PromptLearner.__init__, custom_clip.py:90-99)."""
+    position, split_idx = cfg.get("ctx_position", "end"), None
+    words = cfg["ctx_init"].replace("_", " ").split(" ")
+    if "[CLS]" in words:
+        split_idx, position = words.index("[CLS]"), "middle"
+    learned = bool(cfg.get("learned_cls", False))
+    if position == "end" and not learned:
+        return None, position, split_idx, learned
+    return O.prompt_source_map(tokens, n_ctx, position, split_idx, learned), position, split_idx, learned
+
+
+@pytest.mark.parametrize("name", ["tiny_prompt_rlcf_2step", "b32_prompt_rlcf", "b32_cfg1_exact", "tiny_prompt_middle",
+                                  "tiny_prompt_front", "tiny_prompt_cls_word", "tiny_prompt_learned_cls"])
 def test_prompt_oracle_matches_reference(name):
     """Prompt tuning (tpt_cls_rl.py / tpt_cls.py + ClipTestTimeTuning) -- oracle vs the reference's own outputs.
     b32_cfg1_exact is BASELINE.json configs[0] exactly (TPT entropy loss, TPT/tpt_cls.py:49-78)."""
@@ -144,9 +157,21 @@ def test_prompt_oracle_matches_reference(name):
     views = O.make_views(cfg["n_img"], cfg["V"], O.ARCHS[cfg["policy"]][1], cfg.get("view_seed", VIEW_SEED))
     ocfg = O.OracleConfig(n_views=cfg["V"], selection_p=cfg["rho"], tta_steps=cfg["steps"], sample_k=cfg["K"],
                           lr=cfg["lr"], loss="tpt" if tpt else "rlcf")
+    src_map, _, _, learned = prompt_layout_of(cfg, tokens, ctx_init.shape[0])
+    cls_init = torch.tensor(z["cls_init"]) if learned else None
+    if "prompts0" in z.files:       # the reference's assembled prompt embeddings: the layout itself, bit for bit
+        emb = sd_p["token_embedding.weight"][tokens]
+        if src_map is None:
+            mine = torch.cat([emb[:, :1], ctx_init.expand(tokens.shape[0], -1, -1), emb[:, 1 + ctx_init.shape[0]:]], 1)
+        else:
+            vecs = ctx_init if cls_init is None else torch.cat([ctx_init, cls_init.reshape(tokens.shape[0], -1)])
+            frozen = torch.gather(emb, 1, src_map.clamp_min(0).unsqueeze(-1).expand(-1, -1, emb.shape[-1]))
+            mine = torch.where((src_map < 0).unsqueeze(-1), vecs[(-1 - src_map).clamp_min(0)], frozen)
+        assert torch.equal(mine, torch.tensor(z["prompts0"]))
     V = cfg["V"]
     for i in range(cfg["n_img"]):
-        out = O.adapt_one_image_prompt(sd_p, tokens, ctx_init, views[i * V:(i + 1) * V], ocfg, sd_r, rc)
+        out = O.adapt_one_image_prompt(sd_p, tokens, ctx_init, views[i * V:(i + 1) * V], ocfg, sd_r, rc,
+                                       src_map=src_map, cls_init=cls_init)
         scale = np.abs(z[f"img{i}.logits_all"]).max()
         assert np.abs(out["logits_all"].numpy() - z[f"img{i}.logits_all"]).max() < 1e-4 * scale
         assert np.array_equal(out["selected_idx"].numpy(), z[f"img{i}.selected_idx"])

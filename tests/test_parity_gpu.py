@@ -568,13 +568,30 @@ def _prompt_golden(name, loss):
         kw = dict(reward=E.prepare_visual(to_dev(sd_r)), reward_class_feat=rc.to(DEV))
     rcfg = E.RlcfConfig(n_views=cfg["V"], selection_p=cfg["rho"], tta_steps=cfg["steps"], sample_k=cfg["K"],
                         lr=cfg["lr"], loss=loss)
-    eng = E.PromptEngine(E.prepare_visual(sdp_d), E.prepare_text(sdp_d, need_grad=True), tokens, ctx_init.to(DEV),
+    # prompt layout (class token position, "[CLS]" word, learned class tokens) from the oracle's restatement of
+    # PromptLearner.forward -- itself held bit for bit to the reference's assembled prompts (tests/test_oracle_golden.py)
+    from test_oracle_golden import prompt_layout_of
+    src_map, _, _, learned = prompt_layout_of(cfg, tokens, ctx_init.shape[0])
+    vecs = ctx_init
+    if src_map is not None:
+        n_ctx, C = ctx_init.shape[0], tokens.shape[0]
+        ctx_pos = torch.stack([torch.stack([(src_map[c] == -1 - v).nonzero()[0, 0] for v in range(n_ctx)])
+                               for c in range(C)]).to(torch.int32)
+        cls_pos = None
+        if learned:
+            cls_pos = torch.stack([(src_map[c] == -1 - (n_ctx + c)).nonzero()[0, 0] for c in range(C)]).to(torch.int32)
+            vecs = torch.cat([ctx_init, torch.tensor(z["cls_init"]).reshape(C, -1)])
+        kw["layout"] = E.PromptLayout(src_map.to(torch.int32).to(DEV).contiguous(), ctx_pos.to(DEV).contiguous(),
+                                      None if cls_pos is None else cls_pos.to(DEV).contiguous(), n_ctx)
+    eng = E.PromptEngine(E.prepare_visual(sdp_d), E.prepare_text(sdp_d, need_grad=True), tokens, vecs.to(DEV),
                          float(sd_p["logit_scale"].exp()), rcfg, cfg["n_img"], **kw)
     views = O.make_views(cfg["n_img"], cfg["V"], O.ARCHS[cfg["policy"]][1], cfg["view_seed"])
     return z, cfg, eng, views
 
 
-@pytest.mark.parametrize("name,loss", [("b32_cfg1_exact", "tpt"), ("b32_prompt_rlcf", "rlcf")])
+@pytest.mark.parametrize("name,loss", [("b32_cfg1_exact", "tpt"), ("b32_prompt_rlcf", "rlcf"),
+                                       ("tiny_prompt_middle", "rlcf"), ("tiny_prompt_front", "rlcf"),
+                                       ("tiny_prompt_cls_word", "rlcf"), ("tiny_prompt_learned_cls", "tpt")])
 def test_prompt_tuning_at_vit_b32_matches_reference_golden(name, loss):
     """b32_cfg1_exact = BASELINE.json configs[0] exactly (ViT-B/32, get_coop's ClipTestTimeTuning, the TPT entropy loss
     of TPT/tpt_cls.py:49-78, 8 views, selection_p 0.5, 4 images, real BPE tokens of "a photo of a class i");
@@ -597,7 +614,7 @@ def test_prompt_tuning_at_vit_b32_matches_reference_golden(name, loss):
             assert np.abs(eng.rewards[i * S:(i + 1) * S].cpu().numpy() - rw).max() <= 2e-3 * max(1.0, np.abs(rw).max())
         delta = np.abs(z[f"img{i}.logits_final"][0] - la[0]).max()
         PL.check_final_logits(tag + "/final", out[i], z[f"img{i}.logits_final"][0], scale, delta, tol=LOGIT_TOL,
-                              **PROMPT_ALLOW.get(name, {}))
+                              **PROMPT_ALLOW.get(name, PROMPT_ALLOW["tiny"] if name.startswith("tiny_") else {}))
         assert out[i].argmax() == z[f"img{i}.logits_final"][0].argmax(), f"{tag}: top-1 differs"
         frac = _flip_aware_param_check(eng.ctx[i], z[f"img{i}.params"], cfg["lr"], cfg["steps"], tag + "/ctx")
         PL.record(tag + "/ctx", frac_within_5pct_of_a_step=frac)
@@ -607,6 +624,10 @@ def test_prompt_tuning_at_vit_b32_matches_reference_golden(name, loss):
 PROMPT_ALLOW = {   # lr 5e-3 on context entries of magnitude 0.02 (token-embedding scale): each step moves an entry by 25 %
     "b32_cfg1_exact": _flip(1.10e-2, 1.04),
     "b32_prompt_rlcf": _flip(1.61e-2, 1.20),
+    # tiny towers (width 128): the fp16 text tower in the per-image loop alone is at 1.2e-3 .. 1.6e-3 on the adapted logits
+    # (tiny_prompt_rlcf_2step: 1.2e-3 with delta 1.39, 1.6e-3 with delta 3e-6 on the round-1 fixture)
+    "tiny": dict(allow_delta=0.02, why="prompt tuning on 128-wide towers: fp16 text tower per image and step (measured "
+                                       "1.2e-3 .. 1.6e-3 on the adapted logits) + sign-like AdamW steps"),
 }
 
 
