@@ -84,7 +84,9 @@ PROMPT_CASES = {
     "tiny_prompt_middle": dict(policy="tiny-P", reward="tiny-Q", V=16, rho=0.25, K=3, C=12, steps=2, lr=2e-3, n_img=2,
                                ctx_init="a_photo_of_a", loss="rlcf", reward_seed=6, ctx_position="middle", view_seed=21),
     "tiny_prompt_front": dict(policy="tiny-P", reward="tiny-Q", V=16, rho=0.25, K=3, C=12, steps=1, lr=2e-3, n_img=1,
-                              ctx_init="a_photo_of_a", loss="rlcf", reward_seed=6, ctx_position="front", view_seed=22),
+                              ctx_init="a_photo_of_a", loss="rlcf", reward_seed=6, ctx_position="front", view_seed=31),
+    # (view seed 22 puts the 3rd and 4th largest logits of one selected view 1e-4 of the logit scale apart: a coin flip
+    # for ANY implementation's top-K; seed 31 keeps every sampled class 0.14 clear of the next one)
     "tiny_prompt_cls_word": dict(policy="tiny-P", reward="tiny-Q", V=16, rho=0.25, K=3, C=12, steps=1, lr=2e-3, n_img=1,
                                  ctx_init="a_[CLS]_photo_of_a", loss="rlcf", reward_seed=6, view_seed=23),
     # learned class tokens with the TPT entropy loss: under RLCF every class prompt reads "... X." for the reward model,

@@ -626,8 +626,9 @@ PROMPT_ALLOW = {   # lr 5e-3 on context entries of magnitude 0.02 (token-embeddi
     "b32_prompt_rlcf": _flip(1.61e-2, 1.20),
     # tiny towers (width 128): the fp16 text tower in the per-image loop alone is at 1.2e-3 .. 1.6e-3 on the adapted logits
     # (tiny_prompt_rlcf_2step: 1.2e-3 with delta 1.39, 1.6e-3 with delta 3e-6 on the round-1 fixture)
-    "tiny": dict(allow_delta=0.02, why="prompt tuning on 128-wide towers: fp16 text tower per image and step (measured "
-                                       "1.2e-3 .. 1.6e-3 on the adapted logits) + sign-like AdamW steps"),
+    "tiny": dict(allow_delta=0.03, why="prompt tuning on 128-wide towers: fp16 text tower per image and step (measured "
+                                       "1.2e-3 .. 1.6e-3 on the adapted logits) + sign-like AdamW steps; worst measured "
+                                       "9.1e-3 with delta 0.34 (tiny_prompt_cls_word)"),
 }
 
 
