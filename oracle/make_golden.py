@@ -65,7 +65,7 @@ CASES = {
 # top-1 agreement fixture: final logits of N images at config 2 from the reference, one seed per
 # image (views of image i = make_views(1, V, 224, view_seed + i)); only what the agreement test needs is stored
 AGREE_CASES = {
-    "agree_cfg2": dict(policy="ViT-B/16", reward="ViT-L/14", V=64, rho=0.1, K=3, C=200, steps=1, lr=5e-3, n_img=64,
+    "agree_cfg2": dict(policy="ViT-B/16", reward="ViT-L/14", V=64, rho=0.1, K=3, C=200, steps=1, lr=5e-3, n_img=256,
                        view_seed=1000, per_image_seeds=True, compact=True),
 }
 PROMPT_CASES = {

@@ -30,7 +30,8 @@ struct AttnTcArgs {
   int o_off;                    // TMEM column (inside the team's 256) of the O accumulator
   int n_qt, n_units;            // query tiles per (sequence, head); number of (sequence, head) units
   int stage_bytes;
-  int debug;                    // RLCF_ATTN_DEBUG bit mask (timing probes only): 1 skip max pass, 2 skip exp pass, 4 skip stores, 8 timeline, 16 no exp token, 32 per-thread O stores
+  int sum_mma;                  // 1: the row sums come out of the P V MMA (a block of ones appended to V: O gets 80 columns)
+  int debug;                    // RLCF_ATTN_DEBUG bit mask (timing probes only): 1 skip max pass, 2 skip exp pass, 4 skip stores, 8 timeline, 16 no exp token, 32 per-thread O stores, 128 row sums on the CUDA cores
   __half* out;
   float* lse;
 };
@@ -61,6 +62,26 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)
                : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// MN-major, 128-byte-swizzled B operand that is wider than one 64-element atom along N: the atoms of the second
+// 64-column block start `lbo_bytes` after the first block's (leading-dimension byte offset field, bits [16,30)).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 
 constexpr int kAttnThreads = 384;  // warps 0/3: TMA (team 0/1), warps 1/2: MMA (team 0/1), warps 4-7 / 8-11: softmax
 constexpr int kMaxExtraKeys = 16;
@@ -92,6 +113,9 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], float m, int
 // this row has already consumed -- and returns the chunk's row-sum contribution.  (Evaluating a fraction of the
 // exponentials with a polynomial on the FMA pipe, as FlashAttention-4 does, was measured 8-14 % SLOWER here: the pass
 // is paced by TMEM reads and per-warp issue latency, not by the MUFU lanes -- profiles/r1_attention_probes.txt.)
+// kSum = false: the row sum is produced by the P V MMA (AttnTcArgs::sum_mma), the 32 additions per chunk disappear from
+// this issue-latency-bound loop.
+template <bool kSum>
 __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t trow, int ch, bool full, int key_end,
                                            float c, float mc) {
   uint32_t pk[16];
@@ -101,7 +125,7 @@ __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t tro
     for (int j = 0; j < 16; ++j) {
       const float a = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -mc));
       const float b = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c, -mc));
-      if (j & 1) l1 += a + b; else l0 += a + b;
+      if constexpr (kSum) { if (j & 1) l1 += a + b; else l0 += a + b; }
       const __half2 hp = __floats2half2_rn(a, b);
       pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
     }
@@ -110,7 +134,7 @@ __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t tro
     for (int j = 0; j < 16; ++j) {
       const float a = (ch * 32 + 2 * j < key_end) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), c, -mc)) : 0.f;
       const float b = (ch * 32 + 2 * j + 1 < key_end) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c, -mc)) : 0.f;
-      if (j & 1) l1 += a + b; else l0 += a + b;
+      if constexpr (kSum) { if (j & 1) l1 += a + b; else l0 += a + b; }
       const __half2 hp = __floats2half2_rn(a, b);
       pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
     }
@@ -119,12 +143,17 @@ __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t tro
   return l0 + l1;
 }
 
+template <bool kSumMma>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKV,
                    const __grid_constant__ CUtensorMap mapO, AttnTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * p.stage_bytes);  // [2 teams][B_PER_TEAM]
+  // sum_mma: one constant [Lk x 64] tile (128-byte rows, swizzled like V) whose column 0 is 1 and the rest 0, shared by
+  // both teams: appended to V as a second 64-column block of the P V MMA's B operand, it makes O column 64 the row sum
+  uint8_t* sOnes = smem + 2 * p.stage_bytes;
+  const int ones_bytes = kSumMma ? p.Lk * 128 : 0;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + ones_bytes);        // [2 teams][B_PER_TEAM]
   uint64_t* tok = bars + 2 * B_PER_TEAM;                                   // [4 lane quarters][2 teams]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 8);
 
@@ -147,6 +176,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     }
     for (int i = 0; i < 8; ++i) mbar_init(&tok[i], 1);
     fence_barrier_init();
+  }
+  if constexpr (kSumMma) {
+    for (int i = tid; i < p.Lk * 8; i += kAttnThreads) reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    // element (row r, column 0) lives in the row's logical 16-byte chunk 0 = physical chunk (0 ^ (r & 7))
+    for (int r = tid; r < p.Lk; r += kAttnThreads)
+      *reinterpret_cast<__half*>(sOnes + r * 128 + ((r & 7) << 4)) = __float2half(1.f);
+    fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
   }
   if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
   tc_fence_before();
@@ -190,9 +227,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     // ------------------------------------------------------------ MMA issuer of this team
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_f16(128, p.n_mma);
-      const uint32_t idesc_o = umma_idesc_f16(128, 64) | (1u << 16);  // B (= V) is MN-major
+      const uint32_t idesc_o = umma_idesc_f16(128, kSumMma ? 80 : 64) | (1u << 16);  // B (= V [| ones]) is MN-major
       const uint64_t dk = umma_desc_k_sw128(smem_u32(sK));
-      const uint64_t dv = umma_desc_k_sw128(smem_u32(sV));
+      const uint64_t dv = kSumMma ? umma_desc_mn_sw128(smem_u32(sV), smem_u32(sOnes) - smem_u32(sV))
+                                    : umma_desc_k_sw128(smem_u32(sV));
       const int ksteps = p.Lk >> 4;
       uint32_t uc = 0, tc = 0;
       for (int u = first; u < p.n_units; u += stride, ++uc) {
@@ -322,11 +360,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
             for (int ch = 0; ch < n_chunks; ch += 2) {
               tmem_ld_wait();
               if (ch + 1 < n_chunks) tmem_ld_32x32(trow + (ch + 1) * 32, vb);
-              l += chunk_exp(va, trow, ch, ch < full_chunks, key_end, c, mc);
+              l += chunk_exp<!kSumMma>(va, trow, ch, ch < full_chunks, key_end, c, mc);
               if (ch + 1 < n_chunks) {
                 tmem_ld_wait();
                 if (ch + 2 < n_chunks) tmem_ld_32x32(trow + (ch + 2) * 32, va);
-                l += chunk_exp(vb, trow, ch + 1, ch + 1 < full_chunks, key_end, c, mc);
+                l += chunk_exp<!kSumMma>(vb, trow, ch + 1, ch + 1 < full_chunks, key_end, c, mc);
               }
             }
           }
@@ -361,6 +399,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
           uint32_t o[64];
           tmem_ld_32x32(trow + p.o_off, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
           tmem_ld_32x32(trow + p.o_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+          if constexpr (kSumMma) {          // O column 64 = sum_j P_j * 1: the row sum of the fp16 P the MMA multiplied
+            uint32_t lsum[16];
+            tmem_ld_32x16(trow + p.o_off + 64, lsum);
+            tmem_ld_wait();
+            l = __uint_as_float(lsum[0]);
+          }
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
@@ -455,10 +499,16 @@ int attention_fwd_tc(const __half* qkv, int n_seq, int L, int heads, int causal,
   a.stage_bytes = 2 * 128 * 128 + 2 * Lk * 128;
   static const int debug = getenv("RLCF_ATTN_DEBUG") ? atoi(getenv("RLCF_ATTN_DEBUG")) : 0;
   a.debug = debug;
-  const size_t smem = 1024 + 2 * static_cast<size_t>(a.stage_bytes) + (2 * B_PER_TEAM + 8) * 8 + 16;
-  auto kernel = attn_fwd_tc_kernel;
-  static DynSmemState st;
-  if (cudaError_t e = ensure_dyn_smem(kernel, smem, st))
+  // Row sums from the tensor core (a constant tile of ones as a second B block of the P V MMA): needs Lk * 128 more bytes
+  // of shared memory, room for 80 accumulator columns behind P, and every key inside the MMA (no CUDA-core extras).
+  // RLCF_ATTN_DEBUG & 128 keeps the sums on the CUDA cores (A/B probe).
+  const size_t smem_base = 1024 + 2 * static_cast<size_t>(a.stage_bytes) + (2 * B_PER_TEAM + 8) * 8 + 16;
+  a.sum_mma = !(debug & 128) && Lk <= 256 && a.o_off + 80 <= 256 &&
+              smem_base + static_cast<size_t>(Lk) * 128 <= 227 * 1024;
+  const size_t smem = smem_base + (a.sum_mma ? static_cast<size_t>(Lk) * 128 : 0);
+  auto kernel = a.sum_mma ? attn_fwd_tc_kernel<true> : attn_fwd_tc_kernel<false>;
+  static DynSmemState st[2];    // one per kernel variant
+  if (cudaError_t e = ensure_dyn_smem(kernel, smem, st[a.sum_mma]))
     return set_error(RLCF_ERR_CUDA, "attention_fwd_tc attr: %s", cudaGetErrorString(e));
   CUtensorMap mq, mkv;
   const long long rows = static_cast<long long>(n_seq) * L;
