@@ -358,3 +358,28 @@ def test_prompt_learner_layouts_match_the_reference(name):
     assert torch.equal(pl.learnable_flat(), flat + 1.0)
     pl.reset()
     assert torch.equal(pl.learnable_flat(), flat)
+
+
+def test_bench_arms_build_the_same_config():
+    """bench.py: the b200 arm and the reference arm describe the workload with the same `config` object -- identical
+    except for images_per_step -- and the reference arm prefers the unmodified reference copy (kind "reference")."""
+    import argparse
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for config in (2, 3, 5):
+        wl = bench.workload_of(argparse.Namespace(config=config))
+        a, b = bench.make_config(wl, "ln", config, 32, 1), bench.make_config(wl, "ln", config, 1, 1)
+        assert set(a) == set(b)
+        assert {k for k in a if a[k] != b[k]} == {"images_per_step"}
+        assert a["workload"].startswith(wl["policy"]) and f"(config {config})" in a["workload"]
+    assert bench.workload_of(argparse.Namespace(config=3))["tta_steps"] == 3
+    from baseline import ref_harness
+    if os.path.isdir("/root/reference/TPT"):
+        from baseline import make_ref
+        assert make_ref.make_ref() and ref_harness.available()
+        import json
+        with open(os.path.join(ROOT, "baseline", "_ref", "MANIFEST.json")) as f:
+            man = json.load(f)
+        assert "tune_cls_rl.py" in man["files"] and "tpt_cls_rl.py" in man["files"] and "clip_reward.py" in man["files"]
