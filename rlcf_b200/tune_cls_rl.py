@@ -198,9 +198,10 @@ def class_names_for(folders, table, set_id):
         return [c.replace("_", " ") for c in folders]
     if isinstance(table, dict):
         missing = [c for c in folders if c not in table]
-        if missing:
+        if missing and opaque:
             raise SystemExit(f"test set {set_id}: --classnames has no entry for folders {missing[:5]} ...")
-        return [str(table[c]) for c in folders]
+        # a table of ids (e.g. wnid -> name) does not have to know the folders of sets that are named in clear
+        return [str(table[c]) if c in table else c.replace("_", " ") for c in folders]
     if all(c.isdigit() for c in folders):                    # ImageNetV2: folder k holds class id k
         if max(int(c) for c in folders) >= len(table):
             raise SystemExit(f"test set {set_id}: --classnames lists {len(table)} names, folders go beyond that")

@@ -61,9 +61,10 @@ class ProgressMeter:
 
 
 def accuracy(output, target, topk=(1,)):
-    """Percentage of rows whose target is among the k highest logits (tools.py:84-98)."""
+    """Percentage of rows whose target is among the k highest logits (tools.py:84-98).  With fewer than k classes the
+    reference's `topk` raises; here k is clamped to the number of classes (top-5 of a 3-class set is a certain hit)."""
     with torch.no_grad():
-        maxk = max(topk)
+        maxk = min(max(topk), output.size(1))
         batch_size = target.size(0)
         _, pred = output.topk(maxk, 1, True, True)
         correct = pred.t().eq(target.view(1, -1).expand(maxk, batch_size))

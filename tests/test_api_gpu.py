@@ -305,3 +305,48 @@ def test_reward_model_ensemble_through_the_api():
     PL.check_final_logits("api/multi_reward", out.numpy(), ref["logits_final"].numpy(), scale, delta, allow_delta=0.02,
                           why="sign-like AdamW steps on noise-level gradients (tests/test_parity_gpu.py GOLDEN_ALLOW); tiny towers, lr 5e-3")
     assert isinstance(reward_model.image_features, list) and len(reward_model.image_features) == 2
+
+
+def test_eval_driver_rebuilds_class_prompts_per_test_set(tmp_path):
+    """ADVICE r1 (medium), on the device: the ImageFolder driver gives every test set its own label space -- class
+    names from a --classnames table where the folders are WordNet ids, from the folder names otherwise -- by calling
+    model.reset_classnames_and_state + reward_model.set_class_features per set (tune_cls_rl.py:120-143), generates the
+    views on the GPU, adapts a ragged stream (6 images, 4 per launch sequence) and refuses id folders without a table."""
+    import json
+    import os
+    from PIL import Image
+    from rlcf_b200.clip import simple_tokenizer as ST
+    from rlcf_b200.params import get_args
+    if ST._find_vocab() is None:
+        pytest.skip("OpenAI BPE vocabulary not available on this machine")
+    rng = np.random.default_rng(0)
+    root = tmp_path / "data"
+    layout = {"imagenet-a": ["n01440764", "n01443537", "n01484850"], "oxford_pets": ["golden_retriever", "tabby_cat"]}
+    for d, classes in layout.items():
+        for c in classes:
+            os.makedirs(root / d / c)
+            for k in range(2 if d == "imagenet-a" else 3):
+                arr = rng.integers(0, 255, size=(96 + 8 * k, 120, 3), dtype=np.uint8)
+                Image.fromarray(arr).save(root / d / c / f"{k}.png")
+    table = tmp_path / "names.json"
+    table.write_text(json.dumps({"n01440764": "tench", "n01443537": "goldfish", "n01484850": "great white shark"}))
+    argv = [str(root), "--test_sets", "A/pets", "-a", "ViT-B/32", "--reward_arch", "ViT-B/32", "--tpt", "--tune_norm", "1",
+            "--batch_size", "8", "--selection_p", "0.5", "--tta_steps", "1", "--sample_k", "2", "--synthetic_weights",
+            "--images_per_step", "4", "--workers", "0", "--output", str(tmp_path / "out"), "--ctx_init", "a_photo_of_a"]
+    seen = []
+    from rlcf_b200.clip import custom_clip
+    orig = custom_clip.CLIPCLS_TTA.reset_classnames_and_state
+
+    def spy(self, classnames, arch, tokenized_prompts=None):
+        seen.append(list(classnames))
+        return orig(self, classnames, arch, tokenized_prompts)
+
+    custom_clip.CLIPCLS_TTA.reset_classnames_and_state = spy
+    try:
+        results = tune_cls_rl.main_worker(0, get_args(argv + ["--classnames", str(table)]))
+    finally:
+        custom_clip.CLIPCLS_TTA.reset_classnames_and_state = orig
+    assert set(results) == {"A", "pets"} and all(len(v) == 2 for v in results.values())
+    assert seen == [["tench", "goldfish", "great white shark"], ["golden retriever", "tabby cat"]]
+    with pytest.raises(SystemExit):
+        tune_cls_rl.main_worker(0, get_args(argv))          # wnid folders, no table: never "a photo of a n01440764."

@@ -300,6 +300,7 @@ def test_class_names_per_test_set(tmp_path):
     assert class_names_for(["n01443537", "n01440764"], table, "A") == ["goldfish", "tench"]
     with pytest.raises(SystemExit):
         class_names_for(["n01443537", "n09999999"], table, "A")
+    assert class_names_for(["tabby_cat", "pug"], table, "pets") == ["tabby cat", "pug"]      # named in clear: no entry needed
     p = tmp_path / "names.json"
     p.write_text(json.dumps({"V": ["zero", "one", "two"] + [f"c{i}" for i in range(3, 11)], "A": {"n01440764": "tench"}}))
     table = load_classname_table(str(p))
