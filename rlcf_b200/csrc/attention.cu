@@ -360,7 +360,7 @@ int attention_bwd_tc(const __half* qkv, const __half* out, const __half* dout, c
 int attention_bwd(const __half* qkv, const __half* out, const __half* dout, const float* lse, int n_seq, int L,
                   int heads, int causal, __half* dqkv, cudaStream_t stream) {
   if (n_seq <= 0 || L <= 0 || heads <= 0 || lse == nullptr) return set_error(RLCF_ERR_ARG, "attention_bwd: bad args");
-  // tcgen05 kernel for every sequence that fits its TMEM layout (L <= 224); rlcf_set_attention_impl(1) /
+  // tcgen05 kernel for every sequence it covers (L <= 384); rlcf_set_attention_impl(1) /
   // RLCF_ATTN_IMPL=1 forces the warp-MMA kernels (forward and backward)
   if (attention_impl() == 0) {
     const int rc = attention_bwd_tc(qkv, out, dout, lse, n_seq, L, heads, causal, dqkv, stream);

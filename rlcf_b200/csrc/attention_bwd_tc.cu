@@ -1,8 +1,8 @@
-// tcgen05 / TMEM backward of the fused attention core for CLIP towers (head_dim 64, L <= 224 tokens): dQ, dK, dV of
+// tcgen05 / TMEM backward of the fused attention core for CLIP towers (head_dim 64, L <= 384 tokens): dQ, dK, dV of
 // one (sequence, head) unit from Q, K, V, the forward output O, its gradient dO and the saved log-sum-exp.
 // Replaces autograd's backward of nn.MultiheadAttention's bmm-softmax-bmm (TPT/clip/model.py:185-187 under
-// TPT/tpt_cls_rl.py:77) and the warp-MMA kernel of attention.cu for every tower whose sequence fits (ViT-B/32, ViT-B/16,
-// the text towers); longer sequences (ViT-L/14: 257 tokens) keep the warp-MMA kernel.
+// TPT/tpt_cls_rl.py:77) and the warp-MMA kernel of attention.cu for every tower that is ever tuned (ViT-B/32, ViT-B/16,
+// the text towers, ViT-L/14 with its 257 tokens).
 //
 // Per unit the four [Lk x 64] fp16 tiles Q, K, V, dO are TMA-loaded once (128-byte swizzle) and every contraction runs
 // on the tensor core with fp32 accumulators in TMEM.  With P = exp(S/8 - lse), D_i = sum_c dO_ic O_ic and
@@ -17,6 +17,8 @@
 // D / lse vectors), warp 1 TMEM allocation + MMA issuer, warps 2-5 the 128 accumulator rows (their TMEM chunk loads
 // are issued one chunk ahead of the arithmetic).
 // TMEM columns: [0,224) S / packed P, [224,448) dP / packed dS + dK accumulator, [448,512) dQ or dV accumulator.
+// Sequences beyond 224 tokens do not fit S and dP side by side: their score columns are processed in blocks of 128
+// (S in [0,128), dP in [224,352)) and the output MMAs accumulate over the blocks; everything else is unchanged.
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
@@ -27,7 +29,10 @@
 namespace rlcf {
 
 struct AttnBwdArgs {
-  int L, Lk, heads, causal, n_units, n_rt;   // n_rt = row tiles of 128 per unit (1 or 2)
+  int L, Lk, heads, causal, n_units, n_rt;   // n_rt = row tiles of 128 per unit (1..3)
+  int n_cb, cb_w;                            // score-column blocks per tile and their width (Lk, or 128 when Lk > 224)
+  int vec_n;                                 // entries of the per-stage D / lse vectors (n_rt * 128, at least 256)
+  int box_rows, n_boxes;                     // TMA boxes covering the Lk rows of a tile (a box has at most 256 rows)
   int tile_bytes;                            // smem bytes per operand tile (Lk rows; a row tile may read past it, see host)
   int n_stages;                              // shared-memory stages of {Q, K, V, dO, D, lse}: 2 when they fit, else 1
   int debug;                                 // RLCF_ATTN_BWD_DEBUG=1: CTA 0 prints a clock64 timeline of its first tiles
@@ -82,17 +87,19 @@ __device__ __forceinline__ void store_row64(__half* dst, const uint32_t (&pk)[32
   for (int j = 0; j < 8; ++j) d4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
 }
 
+// kBlocks = false: the whole score row is one block (L <= 224; block loop and column offsets fold away).
+template <bool kBlocks>
 __global__ void __launch_bounds__(kBwdTcThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ CUtensorMap mapDO, AttnBwdArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // stage s: tiles Q, K, V, dO at smem + s * 4 * tile_bytes; behind the last tile a pad of (256 - Lk) rows, so that a
-  // row tile's 128-row A operand starting at row 128 stays inside the allocation (rows >= Lk are never stored)
+  // stage s: tiles Q, K, V, dO at smem + s * 4 * tile_bytes; behind the last tile a pad of (n_rt * 128 - Lk) rows, so that a
+  // row tile's 128-row A operand starting at row 128 / 256 stays inside the allocation (rows >= Lk are never stored)
   const int stage_bytes = 4 * p.tile_bytes;
-  uint8_t* vec_base = smem + p.n_stages * stage_bytes + (256 - p.Lk) * 128;
-  float* sLse0 = reinterpret_cast<float*>(vec_base);            // [stage][256] lse * log2(e); 0 beyond L
-  float* sD0 = sLse0 + 2 * 256;                                  // [stage][256] D_i = sum_c dO_ic O_ic; 0 beyond L
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sD0 + 2 * 256);
+  uint8_t* vec_base = smem + p.n_stages * stage_bytes + (p.n_rt * 128 - p.Lk) * 128;
+  float* sLse0 = reinterpret_cast<float*>(vec_base);            // [stage][vec_n] lse * log2(e); 0 beyond L
+  float* sD0 = sLse0 + 2 * p.vec_n;                              // [stage][vec_n] D_i = sum_c dO_ic O_ic; 0 beyond L
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD0 + 2 * p.vec_n);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BB_COUNT);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -111,6 +118,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int tiles_per_unit = 2 * p.n_rt;     // phase A row tiles, then phase B row tiles
+  const int n_cb = kBlocks ? p.n_cb : 1;     // score-column blocks per tile
+  const int cb_w = kBlocks ? p.cb_w : p.Lk;  // and their width
 
   if (warp == 0) {
     // ------------------------------------------------------------ producer: tiles (TMA, lane 0) + D / lse (all lanes)
@@ -126,14 +135,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
       if (lane == 0) {
         const int row = seq * p.L;
         mbar_expect_tx(&bars[BB_FULL + st], 4 * p.Lk * 128);
-        tma_load_2d(sQ, &mapQKV, &bars[BB_FULL + st], h * 64, row);
-        tma_load_2d(sQ + p.tile_bytes, &mapQKV, &bars[BB_FULL + st], d + h * 64, row);
-        tma_load_2d(sQ + 2 * p.tile_bytes, &mapQKV, &bars[BB_FULL + st], 2 * d + h * 64, row);
-        tma_load_2d(sQ + 3 * p.tile_bytes, &mapDO, &bars[BB_FULL + st], h * 64, row);
+        for (int b = 0; b < p.n_boxes; ++b) {
+          const int ro = b * p.box_rows;
+          tma_load_2d(sQ + ro * 128, &mapQKV, &bars[BB_FULL + st], h * 64, row + ro);
+          tma_load_2d(sQ + p.tile_bytes + ro * 128, &mapQKV, &bars[BB_FULL + st], d + h * 64, row + ro);
+          tma_load_2d(sQ + 2 * p.tile_bytes + ro * 128, &mapQKV, &bars[BB_FULL + st], 2 * d + h * 64, row + ro);
+          tma_load_2d(sQ + 3 * p.tile_bytes + ro * 128, &mapDO, &bars[BB_FULL + st], h * 64, row + ro);
+        }
       }
-      float* sLse = sLse0 + st * 256;
-      float* sD = sD0 + st * 256;
-      for (int rr = lane; rr < 256; rr += 32) {
+      float* sLse = sLse0 + st * p.vec_n;
+      float* sD = sD0 + st * p.vec_n;
+      for (int rr = lane; rr < p.vec_n; rr += 32) {
         float dsum = 0.f, lv = 0.f;
         if (rr < p.L) {
           const uint4* po = reinterpret_cast<const uint4*>(p.out + (row_base + rr) * d + h * 64);
@@ -160,10 +172,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_f16(128, p.Lk);
       const uint32_t idesc_o = umma_idesc_f16(128, 64) | (1u << 16);   // B operand is MN-major ([k][64] rows)
-      const int ksteps = p.Lk >> 4;
-      uint32_t uc = 0, it = 0;
+      uint32_t uc = 0, it = 0, ib = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++uc) {
         const int st = p.n_stages == 2 ? (uc & 1) : 0;
         const uint32_t sph = p.n_stages == 2 ? ((uc >> 1) & 1) : (uc & 1);
@@ -176,29 +186,39 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         for (int t = 0; t < tiles_per_unit; ++t, ++it) {
           const bool phase_b = t >= p.n_rt;
           const int r0 = (phase_b ? t - p.n_rt : t) * 128;
-          const uint32_t ph = it & 1;
-          // scores: A = this tile's 128 rows of (Q | K), B = all Lk rows of (K | Q); dP alike with (dO | V) x (V | dO)
+          // scores: A = this tile's 128 rows of (Q | K), B = a block of rows of (K | Q); dP alike with (dO | V) x (V | dO)
           const uint64_t a_s = umma_desc_k_sw128(smem_u32((phase_b ? sK : sQ) + r0 * 128));
-          const uint64_t b_s = umma_desc_k_sw128(smem_u32(phase_b ? sQ : sK));
           const uint64_t a_p = umma_desc_k_sw128(smem_u32((phase_b ? sV : sdO) + r0 * 128));
-          const uint64_t b_p = umma_desc_k_sw128(smem_u32(phase_b ? sdO : sV));
-          mbar_wait(&bars[BB_TMEMFREE], ph ^ 1);          // the previous tile's accumulators have been read out
+          mbar_wait(&bars[BB_TMEMFREE], (it & 1) ^ 1);    // the previous tile's accumulators have been read out
           tc_fence_after();
+          for (int cb = 0; cb < n_cb; ++cb, ++ib) {
+            const int c0 = kBlocks ? cb * cb_w : 0;                   // first score column (key in phase A, query in phase B)
+            const int w = kBlocks ? min(cb_w, p.Lk - c0) : p.Lk;   // multiple of 16
+            const uint32_t idesc_s = umma_idesc_f16(128, w);
+            const uint64_t b_s = umma_desc_k_sw128(smem_u32((phase_b ? sQ : sK) + c0 * 128));
+            const uint64_t b_p = umma_desc_k_sw128(smem_u32((phase_b ? sdO : sV) + c0 * 128));
+            // (cb > 0: these overwrite the packed operands of the previous block's output MMAs, which the tensor core
+            // executes first -- MMAs of one thread run in issue order -- and whose inputs the row threads have finished)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss<1>(tmem + kColS, a_s + 2 * k, b_s + 2 * k, idesc_s, k != 0);
+            for (int k = 0; k < 4; ++k) umma_f16_ss<1>(tmem + kColS, a_s + 2 * k, b_s + 2 * k, idesc_s, k != 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss<1>(tmem + kColDP, a_p + 2 * k, b_p + 2 * k, idesc_s, k != 0);
-          umma_commit(&bars[BB_SREADY]);
-          mbar_wait(&bars[BB_PREADY], ph);                // packed dS (and P^T) are in TMEM
-          tc_fence_after();
-          if (!phase_b) {
-            const uint64_t bk = umma_desc_k_sw128(smem_u32(sK));
-            for (int j = 0; j < ksteps; ++j) umma_ts(tmem + kColOut, tmem + kColS + 8 * j, bk + 128 * j, idesc_o, j != 0);
-          } else {
-            const uint64_t bdo = umma_desc_k_sw128(smem_u32(sdO));
-            const uint64_t bq = umma_desc_k_sw128(smem_u32(sQ));
-            for (int j = 0; j < ksteps; ++j) umma_ts(tmem + kColOut, tmem + kColS + 8 * j, bdo + 128 * j, idesc_o, j != 0);
-            for (int j = 0; j < ksteps; ++j) umma_ts(tmem + kColDK, tmem + kColDP + 8 * j, bq + 128 * j, idesc_o, j != 0);
+            for (int k = 0; k < 4; ++k) umma_f16_ss<1>(tmem + kColDP, a_p + 2 * k, b_p + 2 * k, idesc_s, k != 0);
+            umma_commit(&bars[BB_SREADY]);
+            mbar_wait(&bars[BB_PREADY], ib & 1);          // packed dS (and P^T) of this block are in TMEM
+            tc_fence_after();
+            const int ksteps = w >> 4, k0 = c0 >> 4;      // output MMAs accumulate over the blocks
+            if (!phase_b) {
+              const uint64_t bk = umma_desc_k_sw128(smem_u32(sK));
+              for (int j = 0; j < ksteps; ++j)
+                umma_ts(tmem + kColOut, tmem + kColS + 8 * j, bk + 128 * (k0 + j), idesc_o, (cb | j) != 0);
+            } else {
+              const uint64_t bdo = umma_desc_k_sw128(smem_u32(sdO));
+              const uint64_t bq = umma_desc_k_sw128(smem_u32(sQ));
+              for (int j = 0; j < ksteps; ++j)
+                umma_ts(tmem + kColOut, tmem + kColS + 8 * j, bdo + 128 * (k0 + j), idesc_o, (cb | j) != 0);
+              for (int j = 0; j < ksteps; ++j)
+                umma_ts(tmem + kColDK, tmem + kColDP + 8 * j, bq + 128 * (k0 + j), idesc_o, (cb | j) != 0);
+            }
           }
           umma_commit(&bars[BB_OREADY]);
           if (t == tiles_per_unit - 1) umma_commit(&bars[BB_FREE + st]);
@@ -212,8 +232,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
     const uint32_t trow = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
     const float scale = 0.125f;
     const float c = scale * 1.4426950408889634f;
-    const int n_chunks = (p.Lk + 31) >> 5;
-    uint32_t it = 0, uc = 0;
+    uint32_t it = 0, uc = 0, ib = 0;
     const bool probe = p.debug && blockIdx.x == 0 && warp == 2 && lane == 0;
     long long stamp[12][6];
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++uc) {
@@ -221,111 +240,121 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
       const size_t row_base = static_cast<size_t>(seq) * p.L;
       const int st = p.n_stages == 2 ? (uc & 1) : 0;
       const uint32_t sph = p.n_stages == 2 ? ((uc >> 1) & 1) : (uc & 1);
-      const float* sLse = sLse0 + st * 256;
-      const float* sD = sD0 + st * 256;
+      const float* sLse = sLse0 + st * p.vec_n;
+      const float* sD = sD0 + st * p.vec_n;
       mbar_wait(&bars[BB_DFULL + st], sph);               // this unit's D / lse vectors (written by the producer warp)
       for (int t = 0; t < tiles_per_unit; ++t, ++it) {
         const bool phase_b = t >= p.n_rt;
         const int r0 = (phase_b ? t - p.n_rt : t) * 128;
         const int grow = r0 + r;                          // query (phase A) or key (phase B) of this thread
         const uint32_t ph = it & 1;
-        const float lse_r = sLse[grow & 255], d_r = sD[grow & 255];
-        if (probe && it < 12) stamp[it][0] = clock64();
-        mbar_wait(&bars[BB_SREADY], ph);
-        tc_fence_after();
-        if (probe && it < 12) stamp[it][1] = clock64();
-        // two register sets: the loads of chunk ch + 1 are in flight while chunk ch is processed
-        uint32_t s0[32], dp0[32], s1[32], dp1[32];
-        tmem_ld_32x32(trow + kColS, s0);
-        tmem_ld_32x32(trow + kColDP, dp0);
+        const float lse_r = sLse[grow], d_r = sD[grow];
         // d_rs = D * scale is folded into one FFMA: dS = p * (dP * scale - D * scale)
         const float d_rs = d_r * scale;
-        // Chunks whose 32 columns are all visible to all 32 rows of this warp take a straight-line path without any
-        // predicate arithmetic (4.5 instructions per element instead of ~19; a lone warp per SM sub-partition issues
-        // at ~0.3 IPC, so the instruction count is what the chunk loop costs): warp-uniform `full` below.
         const int wrow0 = r0 + q4 * 32;                   // first row (query in phase A, key in phase B) of this warp
-        auto process = [&](auto full_tag, const uint32_t (&s)[32], const uint32_t (&dp)[32], int ch) {
-          constexpr bool kFull = decltype(full_tag)::value;
-          uint32_t pk_ds[16], pk_p[16];
-          if (!phase_b) {
-            // columns = keys; this row's query is `grow`
+        // rows >= L only produce accumulator rows that are never stored (every MMA here is row-independent in A): a warp
+        // without a live row skips the arithmetic (the last row tile of ViT-L/14's 257 tokens holds ONE live row)
+        const bool warp_live = wrow0 < p.L;
+        if (probe && it < 12) stamp[it][0] = clock64();
+        for (int cb = 0; cb < n_cb; ++cb, ++ib) {
+          const int c0 = kBlocks ? cb * cb_w : 0;                     // first score column of this block
+          const int n_chunks = ((kBlocks ? min(cb_w, p.Lk - c0) : p.Lk) + 31) >> 5;
+          mbar_wait(&bars[BB_SREADY], ib & 1);
+          tc_fence_after();
+          if (probe && it < 12 && cb == 0) stamp[it][1] = clock64();
+          if (warp_live) {
+            // two register sets: the loads of chunk ch + 1 are in flight while chunk ch is processed
+            uint32_t s0[32], dp0[32], s1[32], dp1[32];
+            tmem_ld_32x32(trow + kColS, s0);
+            tmem_ld_32x32(trow + kColDP, dp0);
+            // Chunks whose 32 columns are all visible to all 32 rows of this warp take a straight-line path without any
+            // predicate arithmetic (4.5 instructions per element instead of ~19; a lone warp per SM sub-partition issues
+            // at ~0.3 IPC, so the instruction count is what the chunk loop costs): warp-uniform `full` below.
+            auto process = [&](auto full_tag, const uint32_t (&s)[32], const uint32_t (&dp)[32], int ch) {
+              constexpr bool kFull = decltype(full_tag)::value;
+              uint32_t pk_ds[16], pk_p[16];
+              const int col0 = c0 + ch * 32;              // global index of the chunk's first column
+              if (!phase_b) {
+                // columns = keys; this row's query is `grow`
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float v2[2];
+                for (int j = 0; j < 16; ++j) {
+                  float v2[2];
 #pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const float pr = ex2_approx(fmaf(__uint_as_float(s[2 * j + e]), c, -lse_r));
-                const float v = pr * fmaf(__uint_as_float(dp[2 * j + e]), scale, -d_rs);
-                if constexpr (kFull) {
-                  v2[e] = v;
-                } else {
-                  const int key = ch * 32 + 2 * j + e;
-                  v2[e] = (key < p.L && (!p.causal || key <= grow)) ? v : 0.f;
+                  for (int e = 0; e < 2; ++e) {
+                    const float pr = ex2_approx(fmaf(__uint_as_float(s[2 * j + e]), c, -lse_r));
+                    const float v = pr * fmaf(__uint_as_float(dp[2 * j + e]), scale, -d_rs);
+                    if constexpr (kFull) {
+                      v2[e] = v;
+                    } else {
+                      const int key = col0 + 2 * j + e;
+                      v2[e] = (key < p.L && (!p.causal || key <= grow)) ? v : 0.f;
+                    }
+                  }
+                  pk_ds[j] = pack2(v2[0], v2[1]);
                 }
-              }
-              pk_ds[j] = pack2(v2[0], v2[1]);
-            }
-            tmem_st16(trow + kColS + ch * 16, pk_ds);
-          } else {
-            // columns = queries; this row's key is `grow`; lse and D * scale of the 32 queries come from shared memory
-            const float4* l4 = reinterpret_cast<const float4*>(sLse + ch * 32);
-            const float4* d4 = reinterpret_cast<const float4*>(sD + ch * 32);
+                tmem_st16(trow + kColS + ch * 16, pk_ds);
+              } else {
+                // columns = queries; this row's key is `grow`; lse and D of the 32 queries come from shared memory
+                const float4* l4 = reinterpret_cast<const float4*>(sLse + col0);
+                const float4* d4 = reinterpret_cast<const float4*>(sD + col0);
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 lq = l4[j4], dq = d4[j4];
-              const float lqa[4] = {lq.x, lq.y, lq.z, lq.w}, dqa[4] = {dq.x, dq.y, dq.z, dq.w};
-              float pv[4], dv[4];
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 lq = l4[j4], dq = d4[j4];
+                  const float lqa[4] = {lq.x, lq.y, lq.z, lq.w}, dqa[4] = {dq.x, dq.y, dq.z, dq.w};
+                  float pv[4], dv[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float pr = ex2_approx(fmaf(__uint_as_float(s[4 * j4 + e]), c, -lqa[e]));
-                const float v = pr * fmaf(__uint_as_float(dp[4 * j4 + e]), scale, -dqa[e] * scale);
-                if constexpr (kFull) {
-                  pv[e] = pr;
-                  dv[e] = v;
-                } else {
-                  const int q = ch * 32 + 4 * j4 + e;
-                  const bool ok = q < p.L && (!p.causal || grow <= q);
-                  pv[e] = ok ? pr : 0.f;
-                  dv[e] = ok ? v : 0.f;
+                  for (int e = 0; e < 4; ++e) {
+                    const float pr = ex2_approx(fmaf(__uint_as_float(s[4 * j4 + e]), c, -lqa[e]));
+                    const float v = pr * fmaf(__uint_as_float(dp[4 * j4 + e]), scale, -dqa[e] * scale);
+                    if constexpr (kFull) {
+                      pv[e] = pr;
+                      dv[e] = v;
+                    } else {
+                      const int q = col0 + 4 * j4 + e;
+                      const bool ok = q < p.L && (!p.causal || grow <= q);
+                      pv[e] = ok ? pr : 0.f;
+                      dv[e] = ok ? v : 0.f;
+                    }
+                  }
+                  pk_p[2 * j4] = pack2(pv[0], pv[1]);
+                  pk_p[2 * j4 + 1] = pack2(pv[2], pv[3]);
+                  pk_ds[2 * j4] = pack2(dv[0], dv[1]);
+                  pk_ds[2 * j4 + 1] = pack2(dv[2], dv[3]);
                 }
+                tmem_st16(trow + kColS + ch * 16, pk_p);
+                tmem_st16(trow + kColDP + ch * 16, pk_ds);
               }
-              pk_p[2 * j4] = pack2(pv[0], pv[1]);
-              pk_p[2 * j4 + 1] = pack2(pv[2], pv[3]);
-              pk_ds[2 * j4] = pack2(dv[0], dv[1]);
-              pk_ds[2 * j4 + 1] = pack2(dv[2], dv[3]);
+            };
+            auto chunk = [&](const uint32_t (&s)[32], const uint32_t (&dp)[32], int ch) {
+              // every column of the chunk is a real token, and (causal) visible to every row of this warp
+              const int col0 = c0 + ch * 32;
+              bool full = col0 + 32 <= p.L;
+              if (p.causal) full = full && (phase_b ? (wrow0 + 31 <= col0) : (col0 + 31 <= wrow0));
+              if (full) process(std::true_type{}, s, dp, ch); else process(std::false_type{}, s, dp, ch);
+            };
+            for (int ch = 0; ch < n_chunks; ch += 2) {
+              tmem_ld_wait();                                // chunk ch is in s0 / dp0
+              if (ch + 1 < n_chunks) {
+                tmem_ld_32x32(trow + kColS + (ch + 1) * 32, s1);
+                tmem_ld_32x32(trow + kColDP + (ch + 1) * 32, dp1);
+              }
+              chunk(s0, dp0, ch);
+              if (ch + 1 < n_chunks) {
+                tmem_ld_wait();                              // chunk ch + 1 is in s1 / dp1
+                if (ch + 2 < n_chunks) {
+                  tmem_ld_32x32(trow + kColS + (ch + 2) * 32, s0);
+                  tmem_ld_32x32(trow + kColDP + (ch + 2) * 32, dp0);
+                }
+                chunk(s1, dp1, ch + 1);
+              }
             }
-            tmem_st16(trow + kColS + ch * 16, pk_p);
-            tmem_st16(trow + kColDP + ch * 16, pk_ds);
+            tmem_st_fence();
           }
-        };
-        auto chunk = [&](const uint32_t (&s)[32], const uint32_t (&dp)[32], int ch) {
-          // every column of the chunk is a real token, and (causal) visible to every row of this warp
-          bool full = ch * 32 + 32 <= p.L;
-          if (p.causal) full = full && (phase_b ? (wrow0 + 31 <= ch * 32) : (ch * 32 + 31 <= wrow0));
-          if (full) process(std::true_type{}, s, dp, ch); else process(std::false_type{}, s, dp, ch);
-        };
-        for (int ch = 0; ch < n_chunks; ch += 2) {
-          tmem_ld_wait();                                  // chunk ch is in s0 / dp0
-          if (ch + 1 < n_chunks) {
-            tmem_ld_32x32(trow + kColS + (ch + 1) * 32, s1);
-            tmem_ld_32x32(trow + kColDP + (ch + 1) * 32, dp1);
-          }
-          chunk(s0, dp0, ch);
-          if (ch + 1 < n_chunks) {
-            tmem_ld_wait();                                // chunk ch + 1 is in s1 / dp1
-            if (ch + 2 < n_chunks) {
-              tmem_ld_32x32(trow + kColS + (ch + 2) * 32, s0);
-              tmem_ld_32x32(trow + kColDP + (ch + 2) * 32, dp0);
-            }
-            chunk(s1, dp1, ch + 1);
-          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[BB_PREADY]);
         }
-        if (probe && it < 12) stamp[it][2] = clock64();
-        tmem_st_fence();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[BB_PREADY]);
-        if (probe && it < 12) stamp[it][3] = clock64();
+        if (probe && it < 12) stamp[it][2] = stamp[it][3] = clock64();
         // ---- read the output accumulators of this tile
         mbar_wait(&bars[BB_OREADY], ph);
         tc_fence_after();
@@ -393,34 +422,45 @@ static int make_tmap_rows64_bwd(CUtensorMap* map, const void* base, long long ro
 int attention_bwd_tc(const __half* qkv, const __half* out, const __half* dout, const float* lse, int n_seq, int L,
                      int heads, int causal, __half* dqkv, cudaStream_t stream) {
   const int Lk = (L + 15) / 16 * 16;
-  if (Lk > 224 || Lk < 16) return -1;
+  if (Lk > 384 || Lk < 16) return -1;
   if (((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dout) |
         reinterpret_cast<uintptr_t>(dqkv)) & 15) != 0)
     return -1;
   AttnBwdArgs a{};
   a.L = L; a.Lk = Lk; a.heads = heads; a.causal = causal; a.n_units = heads * n_seq;
   a.n_rt = (L + 127) / 128;
+  // S and dP (fp32, Lk columns each) sit side by side in TMEM up to Lk = 224; longer rows go in blocks of 128 columns
+  a.cb_w = Lk <= 224 ? Lk : 128;
+  a.n_cb = (Lk + a.cb_w - 1) / a.cb_w;
+  a.vec_n = a.n_rt * 128 < 256 ? 256 : a.n_rt * 128;
+  a.n_boxes = Lk <= 256 ? 1 : 2;
+  a.box_rows = Lk / a.n_boxes;           // Lk % 16 == 0: the halves of a 272-row tile are 136 rows (a multiple of 8)
+  if (a.box_rows * a.n_boxes != Lk || a.box_rows % 8 != 0) return -1;
   a.tile_bytes = Lk * 128;               // multiple of 1024 (Lk % 16 == 0): every tile start keeps the swizzle alignment
   a.out = out; a.dout = dout; a.lse = lse; a.dqkv = dqkv;
   static const int debug = getenv("RLCF_ATTN_BWD_DEBUG") != nullptr ? atoi(getenv("RLCF_ATTN_BWD_DEBUG")) : 0;
   a.debug = debug;
-  // A row tile's A operand spans 128 rows from row 0 or 128 of its tile, i.e. up to (256 - Lk) rows past the tile's end:
-  // into the next tile, or -- for the last tile -- into a pad of that size.  Rows >= L only produce rows that are never stored.
+  // A row tile's A operand spans 128 rows from row 0 / 128 / 256 of its tile, i.e. up to (n_rt * 128 - Lk) rows past the
+  // tile's end: into the next tile, or -- for the last tile -- into a pad of that size.  Rows >= L only produce rows that
+  // are never stored.
   auto smem_for = [&](int stages) {
-    return 1024 + static_cast<size_t>(stages) * 4 * a.tile_bytes + static_cast<size_t>(256 - Lk) * 128 +
-           4 * 256 * sizeof(float) + BB_COUNT * 8 + 16;
+    return 1024 + static_cast<size_t>(stages) * 4 * a.tile_bytes + static_cast<size_t>(a.n_rt * 128 - Lk) * 128 +
+           4 * static_cast<size_t>(a.vec_n) * sizeof(float) + BB_COUNT * 8 + 16;
   };
   a.n_stages = smem_for(2) <= 227 * 1024 ? 2 : 1;
   const size_t smem = smem_for(a.n_stages);
-  static DynSmemState st;
-  if (cudaError_t e = ensure_dyn_smem(attn_bwd_tc_kernel, smem, st))
+  if (smem > 227 * 1024) return -1;
+  const bool blocks = a.n_cb > 1;
+  auto kernel = blocks ? attn_bwd_tc_kernel<true> : attn_bwd_tc_kernel<false>;
+  static DynSmemState st[2];
+  if (cudaError_t e = ensure_dyn_smem(kernel, smem, st[blocks]))
     return set_error(RLCF_ERR_CUDA, "attention_bwd_tc attr: %s", cudaGetErrorString(e));
   CUtensorMap mqkv, mdo;
   const long long rows = static_cast<long long>(n_seq) * L;
-  if (int rc = make_tmap_rows64_bwd(&mqkv, qkv, rows, 3 * heads * 64, Lk)) return rc;
-  if (int rc = make_tmap_rows64_bwd(&mdo, dout, rows, heads * 64, Lk)) return rc;
+  if (int rc = make_tmap_rows64_bwd(&mqkv, qkv, rows, 3 * heads * 64, a.box_rows)) return rc;
+  if (int rc = make_tmap_rows64_bwd(&mdo, dout, rows, heads * 64, a.box_rows)) return rc;
   const int grid = a.n_units < sm_count() ? a.n_units : sm_count();
-  attn_bwd_tc_kernel<<<grid, kBwdTcThreads, smem, stream>>>(mqkv, mdo, a);
+  kernel<<<grid, kBwdTcThreads, smem, stream>>>(mqkv, mdo, a);
   RLCF_CHECK_LAUNCH("attention_bwd_tc");
   return 0;
 }

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from rlcf_b200 import ops, _lib
 dev = torch.device("cuda:0")
-for (n_seq, L, heads, causal) in [(192, 197, 12, False), (1600, 77, 8, True), (48, 197, 12, False)]:
+for (n_seq, L, heads, causal) in [(192, 197, 12, False), (1600, 77, 8, True), (48, 197, 12, False), (48, 257, 16, False)]:
     d = heads * 64
     qkv = torch.randn(n_seq * L, 3 * d, device=dev).half()
     dout = (torch.randn(n_seq * L, d, device=dev) * 0.1).half()

@@ -231,7 +231,8 @@ def test_attention_fwd_bwd(L, heads, causal, impl):
     _lib.set_attention_impl(0)
 
 
-@pytest.mark.parametrize("n_seq,L,heads,causal", [(40, 197, 12, False), (64, 77, 8, True), (200, 50, 2, False)])
+@pytest.mark.parametrize("n_seq,L,heads,causal", [(40, 197, 12, False), (64, 77, 8, True), (200, 50, 2, False),
+                                                  (20, 257, 16, False), (160, 256, 1, True), (60, 300, 3, False)])
 def test_attention_bwd_persistent_many_units(n_seq, L, heads, causal):
     """More (sequence, head) units than SMs: every CTA of the persistent tcgen05 backward walks several units (tile
     reloads, barrier phases, TMEM reuse); the warp-MMA kernel must agree with it to fp16 rounding of the outputs."""
