@@ -255,7 +255,11 @@ def test_attention_bwd_persistent_many_units(n_seq, L, heads, causal):
     qf = qkv.float().requires_grad_(True)
     ref, _ = _ref_attention(qf, n_seq, L, heads, causal)
     ref.backward(dout.float())
-    assert _rel(res[0], qf.grad) < 5e-3 and _rel(res[1], qf.grad) < 5e-3
+    import parity_log as PL
+    e_tc, e_mma = _rel(res[0], qf.grad), _rel(res[1], qf.grad)
+    PL.record(f"attention_bwd/{n_seq}x{L}x{heads}{'c' if causal else ''}", tcgen05_rel_err=e_tc, mma_sync_rel_err=e_mma,
+              tc_vs_mma_rel=_rel(res[0], res[1].float()))
+    assert e_tc < 5e-3 and e_mma < 5e-3
     assert _rel(res[0], res[1].float()) < 3e-3
 
 

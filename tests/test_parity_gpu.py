@@ -551,6 +551,9 @@ def test_full_encoder_tuning_matches_reference_golden(name):
 
 FULL_ALLOW = {   # three steps at lr 1e-5 over 86 M parameters move the logits by 2.3x their own scale
     "b32_full_tune_3step": _flip(2.00e-3, 2.32),
+    # 128-wide towers, two steps at lr 1e-4: 7.4e-4 with the warp-MMA attention backward, 1.04e-3 with the tcgen05 one
+    # (another rounding order of the same fp16 operands), against an adaptation delta of 0.61
+    "tiny_full_tune_2step": _flip(1.04e-3, 0.614),
 }
 
 
