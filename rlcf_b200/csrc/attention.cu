@@ -334,11 +334,20 @@ attn_bwd_kernel(const __half* __restrict__ qkv, const __half* __restrict__ out, 
 
 int attention_fwd_tc(const __half* qkv, int n_seq, int L, int heads, int causal, __half* out, float* lse,
                      cudaStream_t stream);
+int attention_fwd_tc8(const __half* qkv, int n_seq, int L, int heads, int causal, __half* out, float* lse,
+                      cudaStream_t stream);
 
 int attention_fwd(const __half* qkv, int n_seq, int L, int heads, int causal, __half* out, float* lse,
                   cudaStream_t stream) {
   if (n_seq <= 0 || L <= 0 || heads <= 0) return set_error(RLCF_ERR_ARG, "attention_fwd: bad shape");
-  if (attention_impl() == 0) {  // tcgen05 kernel (attention_tc.cu); -1 = shape not covered -> warp-MMA kernel below
+  if (attention_impl() == 0) {  // tcgen05 kernels; -1 = shape not covered -> next kernel
+    // eight softmax warps per team (attention_tc8.cu, L <= 208: 217 vs 243 us at 512 x 197 x 12) where the sequence
+    // fits, else four (attention_tc.cu, L <= 272); RLCF_ATTN_TC8=0 keeps the four-warp kernel everywhere
+    static const int tc8 = getenv("RLCF_ATTN_TC8") != nullptr ? atoi(getenv("RLCF_ATTN_TC8")) : 1;
+    if (tc8) {
+      const int rc8 = attention_fwd_tc8(qkv, n_seq, L, heads, causal, out, lse, stream);
+      if (rc8 != -1) return rc8;
+    }
     const int rc = attention_fwd_tc(qkv, n_seq, L, heads, causal, out, lse, stream);
     if (rc != -1) return rc;
   }
