@@ -342,7 +342,7 @@ int attention_fwd(const __half* qkv, int n_seq, int L, int heads, int causal, __
   if (n_seq <= 0 || L <= 0 || heads <= 0) return set_error(RLCF_ERR_ARG, "attention_fwd: bad shape");
   if (attention_impl() == 0) {  // tcgen05 kernels; -1 = shape not covered -> next kernel
     // eight softmax warps per team (attention_tc8.cu, L <= 208: 217 vs 243 us at 512 x 197 x 12) where the sequence
-    // fits, else four (attention_tc.cu, L <= 272); RLCF_ATTN_TC8=0 keeps the four-warp kernel everywhere
+    // fits (200 us with its token), else four (attention_tc.cu, L <= 272); RLCF_ATTN_TC8=0 keeps the four-warp kernel everywhere
     static const int tc8 = getenv("RLCF_ATTN_TC8") != nullptr ? atoi(getenv("RLCF_ATTN_TC8")) : 1;
     if (tc8) {
       const int rc8 = attention_fwd_tc8(qkv, n_seq, L, heads, causal, out, lse, stream);
