@@ -99,11 +99,16 @@ def _translate_y(img, level):
 AUGMENTATIONS = [_autocontrast, _equalize, _posterize, _rotate, _solarize, _shear_x, _shear_y, _translate_x, _translate_y]
 
 
-def make_transforms(resolution: int = 224):
-    """tune_cls_rl.py:102-108 and datautils.py:89-92 (hard_aug = False)."""
+def make_transforms(resolution: int = 224, hard_aug: bool = False, crop_min: float = 0.2):
+    """tune_cls_rl.py:102-108 and get_preaugment (datautils.py:76-92)."""
     base = T.Compose([T.Resize(resolution, interpolation=InterpolationMode.BICUBIC), T.CenterCrop(resolution)])
     pre = T.Compose([T.ToTensor(), T.Normalize(mean=MEAN, std=STD)])
-    preaug = T.Compose([T.RandomResizedCrop(224), T.RandomHorizontalFlip()])
+    if hard_aug:    # datautils.py:77-87
+        preaug = T.Compose([T.RandomResizedCrop(resolution, scale=(crop_min, 1.)),
+                            T.RandomApply([T.ColorJitter(0.4, 0.4, 0.2, 0.1)], p=0.5), T.RandomGrayscale(p=0.2),
+                            T.RandomApply([T.GaussianBlur(3, sigma=(0.1, 2.0))], p=0.1), T.RandomHorizontalFlip()])
+    else:
+        preaug = T.Compose([T.RandomResizedCrop(224), T.RandomHorizontalFlip()])
     return base, pre, preaug
 
 
@@ -124,10 +129,10 @@ def augmix_view(image, preaugment, preprocess, aug_list, severity=1):
     return m * x_processed + (1 - m) * mix
 
 
-def augmix_views(image, n_views: int, augmix: bool, severity: int = 1) -> torch.Tensor:
+def augmix_views(image, n_views: int, augmix: bool, severity: int = 1, hard_aug: bool = False) -> torch.Tensor:
     """AugMixAugmenter.__call__ (datautils.py:114-128): [image] + n_views augmented views, stacked [n_views+1,3,224,224].
     Randomness comes from the global torch and numpy generators, exactly as in the reference."""
-    base, pre, preaug = make_transforms()
+    base, pre, preaug = make_transforms(hard_aug=hard_aug)
     aug_list = AUGMENTATIONS if augmix else []
     out = [pre(base(image))]
     out += [augmix_view(image, preaug, pre, aug_list, severity) for _ in range(n_views)]

@@ -27,7 +27,9 @@ CASES = [dict(name="in_a_like", h=375, w=500, seed=3, n_views=7, augmix=False),
          dict(name="tall", h=640, w=427, seed=4, n_views=5, augmix=False),
          dict(name="small_upscale", h=150, w=200, seed=5, n_views=5, augmix=False),
          dict(name="flowers_like", h=500, w=667, seed=6, n_views=9, augmix=True),
-         dict(name="square_augmix", h=256, w=256, seed=7, n_views=12, augmix=True)]
+         dict(name="square_augmix", h=256, w=256, seed=7, n_views=12, augmix=True),
+         dict(name="hard_aug_plain", h=375, w=500, seed=8, n_views=15, augmix=False, hard_aug=True),
+         dict(name="hard_aug_augmix", h=333, w=250, seed=9, n_views=15, augmix=True, hard_aug=True)]
 
 
 def digest(t: torch.Tensor) -> str:
@@ -40,7 +42,7 @@ def main():
     for c in CASES:
         img = A.synthetic_image(c["h"], c["w"], c["seed"])
         base, pre, _ = A.make_transforms()
-        aug = AugMixAugmenter(base, pre, n_views=c["n_views"], augmix=c["augmix"])
+        aug = AugMixAugmenter(base, pre, n_views=c["n_views"], augmix=c["augmix"], hard_aug=c.get("hard_aug", False))
         torch.manual_seed(c["seed"]); np.random.seed(c["seed"])
         views = torch.stack(aug(img))
         out[c["name"]] = dict(c, shape=list(views.shape), sha256=digest(views),

@@ -103,6 +103,7 @@ class ViewPlan:
     geom: np.ndarray | None = None   # int32 [V,8] in_w, in_h, res_w, res_h, lo_x, lo_y, filter: taps are then computed
     ks_h: int = 0                    # on the device (hb/hk/vb/vk are None) with these tap-count bounds
     ks_v: int = 0
+    x_pre: np.ndarray | None = None  # uint8 [V-1,224,224,3]: hard_aug pre-augmented crops made on the host (views 1..)
 
 
 def _window(vb):
@@ -162,6 +163,65 @@ def _sample_op(name: str, severity):
     raise KeyError(name)
 
 
+def _sample_augmix(v, severity, vflag, wts, omm, n_ops, op_codes, mats):
+    """The numpy draws of augmix() for view v (datautils.py:95-111), written into row v of the plan tables."""
+    vflag[v] = 1
+    ws = np.float32(np.random.dirichlet([1.0, 1.0, 1.0]))
+    m = np.float32(np.random.beta(1.0, 1.0))
+    wts[v, :3], wts[v, 3] = ws, m
+    omm[v] = 1 - m
+    for c in range(3):
+        depth = np.random.randint(1, 4)
+        k = 0
+        for _ in range(depth):
+            name = AUG_NAMES[np.random.choice(len(AUG_NAMES))]
+            t, p, mat = _sample_op(name, severity)
+            if t < 0:          # rotate by 0 degrees: Image.rotate returns a copy
+                continue
+            op_codes[v, c, k] = (t, p)
+            if mat is not None:
+                mats[v, c, k] = mat
+            k += 1
+        n_ops[v, c] = k
+
+
+def hard_preaugment(resolution: int = OUT, crop_min: float = 0.2):
+    """get_preaugment(hard_aug=True) (datautils.py:76-87): the BYOL recipe.  It is PIL work on the data-loader side
+    (colour jitter in HSV, grayscale, Gaussian blur), so it stays torchvision on the host -- same calls, same draws
+    from the global torch generator as the reference; the AugMix chains and the normalisation still run on the GPU."""
+    import torchvision.transforms as T
+    return T.Compose([T.RandomResizedCrop(resolution, scale=(crop_min, 1.)),
+                      T.RandomApply([T.ColorJitter(0.4, 0.4, 0.2, 0.1)], p=0.5),
+                      T.RandomGrayscale(p=0.2),
+                      T.RandomApply([T.GaussianBlur(3, sigma=(0.1, 2.0))], p=0.1),
+                      T.RandomHorizontalFlip()])
+
+
+def sample_plan_hard(image, n_views: int, augmix: bool, severity: int = 1, host_taps: bool = True) -> ViewPlan:
+    """sample_plan for AugMixAugmenter(hard_aug=True): `image` is the PIL image; views 1.. are pre-augmented on the
+    host (hard_preaugment) into plan.x_pre, view 0 and everything after the pre-augmentation is device work."""
+    from PIL import Image
+    if not isinstance(image, Image.Image):
+        image = Image.fromarray(_to_u8_hwc(image).numpy())
+    image = image.convert("RGB")
+    plan = sample_plan(image.size[0], image.size[1], 0, False, severity, host_taps)       # view 0: no random draws
+    V = n_views + 1
+    pre = hard_preaugment()
+    x_pre = np.zeros((n_views, OUT, OUT, 3), dtype=np.uint8)
+    vflag = np.zeros(V, dtype=np.int32)
+    wts = np.zeros((V, 4), dtype=np.float32)
+    omm = np.zeros(V, dtype=np.float32)
+    n_ops = np.zeros((V, 3), dtype=np.int32)
+    op_codes = np.zeros((V, 3, 3, 2), dtype=np.int32)
+    mats = np.zeros((V, 3, 3, 6), dtype=np.float64)
+    for v in range(1, V):
+        x_pre[v - 1] = np.asarray(pre(image))
+        if augmix:
+            _sample_augmix(v, severity, vflag, wts, omm, n_ops, op_codes, mats)
+    plan.vflag, plan.wts, plan.omm, plan.n_ops, plan.ops, plan.mats, plan.x_pre = vflag, wts, omm, n_ops, op_codes, mats, x_pre
+    return plan
+
+
 def _ksize(in_sizes, res_sizes, support0):
     """Largest tap count of a set of resizes: ceil(support * max(scale, 1)) * 2 + 1 (precompute_coeffs)."""
     scale = np.asarray(in_sizes, dtype=np.float64) / np.asarray(res_sizes, dtype=np.float64)
@@ -202,25 +262,7 @@ def sample_plan(img_w: int, img_h: int, n_views: int, augmix: bool, severity: in
         crop_w[v - 1], crop_h[v - 1] = w, h
         if not augmix:
             continue
-        # augmix()                                                            (datautils.py:95-111)
-        vflag[v] = 1
-        ws = np.float32(np.random.dirichlet([1.0, 1.0, 1.0]))
-        m = np.float32(np.random.beta(1.0, 1.0))
-        wts[v, :3], wts[v, 3] = ws, m
-        omm[v] = 1 - m
-        for c in range(3):
-            depth = np.random.randint(1, 4)
-            k = 0
-            for _ in range(depth):
-                name = AUG_NAMES[np.random.choice(len(AUG_NAMES))]
-                t, p, mat = _sample_op(name, severity)
-                if t < 0:          # rotate by 0 degrees: Image.rotate returns a copy
-                    continue
-                op_codes[v, c, k] = (t, p)
-                if mat is not None:
-                    mats[v, c, k] = mat
-                k += 1
-            n_ops[v, c] = k
+        _sample_augmix(v, severity, vflag, wts, omm, n_ops, op_codes, mats)
     if not host_taps:
         geom = np.zeros((V, 8), dtype=np.int32)
         geom[0, :7] = (img_w, img_h, new_w, new_h, left, top, 1)
@@ -270,18 +312,21 @@ def run_plan(image_u8: torch.Tensor, plan: ViewPlan, device, out: torch.Tensor |
     e.g. this image's slice of an engine's input batch)."""
     dev = torch.device(device)
     src = image_u8.to(dev, non_blocking=True)
-    V = plan.hdr.shape[0]
+    Vr = plan.hdr.shape[0]                          # views the resampling kernels produce (1 with hard_aug)
+    V = Vr if plan.x_pre is None else 1 + plan.x_pre.shape[0]
 
     def d(a):
         return torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
-    tmp = torch.empty(V, plan.tmp_rows, OUT, 3, dtype=torch.uint8, device=dev)
+    tmp = torch.empty(Vr, plan.tmp_rows, OUT, 3, dtype=torch.uint8, device=dev)
     x_orig = torch.empty(V, OUT, OUT, 3, dtype=torch.uint8, device=dev)
     hdr = d(plan.hdr)
     if plan.geom is not None:
         hb, hk, vb, vk = ops.resample_taps(d(plan.geom), OUT, plan.ks_h, plan.ks_v, hdr)
     else:
         hb, hk, vb, vk = d(plan.hb), d(plan.hk), d(plan.vb), d(plan.vk)
-    ops.resample_u8(src, hdr, hb, hk, vb, vk, OUT, OUT, tmp, x_orig)
+    ops.resample_u8(src, hdr, hb, hk, vb, vk, OUT, OUT, tmp, x_orig[:Vr])
+    if plan.x_pre is not None and V > 1:
+        x_orig[1:].copy_(torch.from_numpy(plan.x_pre), non_blocking=True)
     if out is None:
         out = torch.empty(V, 3, OUT, OUT, dtype=torch.float32, device=dev)
     elif tuple(out.shape) != (V, 3, OUT, OUT) or out.dtype != torch.float32 or not out.is_contiguous():
@@ -294,17 +339,20 @@ def run_plan(image_u8: torch.Tensor, plan: ViewPlan, device, out: torch.Tensor |
 class AugMixAugmenter:
     """datautils.AugMixAugmenter (datautils.py:114-128) on the GPU.  `base_transform` / `preprocess` are accepted for
     signature compatibility; the fixed pipeline of tune_cls_rl.py:102-108 (Resize 224 bicubic + CenterCrop, ToTensor +
-    CLIP normalisation) is what the kernels implement.  hard_aug (BYOL-style colour jitter) is not supported."""
+    CLIP normalisation) is what the kernels implement.  With hard_aug the BYOL pre-augmentation (colour jitter, grayscale,
+    blur: PIL work of the data loader) runs on the host with the reference's torchvision calls; the rest is unchanged."""
 
     def __init__(self, base_transform=None, preprocess=None, n_views=2, augmix=False, severity=1, hard_aug=False,
                  device="cuda"):
-        if hard_aug:
-            raise NotImplementedError("hard_aug=True (ColorJitter / GaussianBlur pre-augmentation) is out of scope")
         self.n_views, self.augmix, self.severity, self.device = n_views, bool(augmix), severity, device
+        self.hard_aug = bool(hard_aug)
 
     def views(self, x) -> torch.Tensor:
         img = _to_u8_hwc(x)
-        plan = sample_plan(img.shape[1], img.shape[0], self.n_views, self.augmix, self.severity, host_taps=False)
+        if self.hard_aug:
+            plan = sample_plan_hard(x, self.n_views, self.augmix, self.severity, host_taps=False)
+        else:
+            plan = sample_plan(img.shape[1], img.shape[0], self.n_views, self.augmix, self.severity, host_taps=False)
         return run_plan(img, plan, self.device)
 
     def __call__(self, x):

@@ -142,12 +142,12 @@ class ImageFolderViews(torch.utils.data.Dataset):
     ((decoded uint8 image [H,W,3], ViewPlan), label).  The plan (random crops / flips / AugMix decisions and Pillow tap
     tables) is host work and parallelises over DataLoader workers; rank r of R sees indices r, r+R, ..."""
 
-    def __init__(self, root, n_views, augmix, rank=0, world=1, severity=1):
+    def __init__(self, root, n_views, augmix, rank=0, world=1, severity=1, hard_aug=False):
         from torchvision.datasets import ImageFolder
         self.folder = ImageFolder(root)
         self.classes = self.folder.classes
         self.idx = list(range(rank, len(self.folder), world))
-        self.n_views, self.augmix, self.severity = n_views, bool(augmix), severity
+        self.n_views, self.augmix, self.severity, self.hard_aug = n_views, bool(augmix), severity, bool(hard_aug)
 
     def __len__(self):
         return len(self.idx)
@@ -155,7 +155,11 @@ class ImageFolderViews(torch.utils.data.Dataset):
     def __getitem__(self, i):
         img, label = self.folder[self.idx[i]]
         u8 = datautils._to_u8_hwc(img)
-        plan = datautils.sample_plan(u8.shape[1], u8.shape[0], self.n_views, self.augmix, self.severity, host_taps=False)
+        if self.hard_aug:       # --hard_aug 1: BYOL pre-augmentation on the host (datautils.py:76-87), the rest on the GPU
+            plan = datautils.sample_plan_hard(img, self.n_views, self.augmix, self.severity, host_taps=False)
+        else:
+            plan = datautils.sample_plan(u8.shape[1], u8.shape[0], self.n_views, self.augmix, self.severity,
+                                         host_taps=False)
         return (u8, plan), torch.tensor(label)
 
 
@@ -214,8 +218,6 @@ def class_names_for(folders, table, set_id):
 def _check_supported_flags(args):
     """Reference flags this driver accepts for command-line compatibility but does not implement must not be dropped
     silently (params.py:23-73)."""
-    if getattr(args, "hard_aug", 0):
-        raise NotImplementedError("--hard_aug (ColorJitter / blur views, data/datautils.py:75-85) is not implemented")
     if getattr(args, "confidence_gap", 0):
         raise NotImplementedError("--confidence_gap is an experimental reference feature that is not implemented")
     if getattr(args, "multiple_reward_models", 0) and "," not in str(args.reward_arch):
@@ -261,7 +263,8 @@ def main_worker(gpu, args):
             raise NotImplementedError("--resolution other than 224 is not implemented (the view kernels crop to 224)")
         for set_id in args.test_sets.split("/"):
             datasets_[set_id] = ImageFolderViews(_real_dataset_root(args, set_id), args.batch_size - 1,
-                                                 augmix=len(set_id) > 1, rank=rank, world=world)   # tune_cls_rl.py:109-110
+                                                 augmix=len(set_id) > 1, rank=rank, world=world,   # tune_cls_rl.py:109-110
+                                                 hard_aug=bool(getattr(args, "hard_aug", 0)))
             set_classnames[set_id] = class_names_for(datasets_[set_id].classes, table, set_id)
         classnames = set_classnames[args.test_sets.split("/")[0]]
         args.n_classes = len(classnames)

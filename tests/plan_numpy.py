@@ -118,4 +118,7 @@ def augmix(x_orig, plan):
 
 
 def execute(image_u8, plan):
-    return augmix(resample(image_u8, plan), plan)
+    x_orig = resample(image_u8, plan)
+    if getattr(plan, "x_pre", None) is not None:        # hard_aug: views 1.. were pre-augmented on the host
+        x_orig = np.concatenate([x_orig[:1], plan.x_pre], axis=0)
+    return augmix(x_orig, plan)

@@ -22,9 +22,10 @@ def test_views_are_bit_exact_with_the_reference_pipeline(name):
     c = CASES[name]
     img = A.synthetic_image(c["h"], c["w"], c["seed"])
     torch.manual_seed(c["seed"]); np.random.seed(c["seed"])
-    ref = A.augmix_views(img, c["n_views"], bool(c["augmix"]))
+    hard = bool(c.get("hard_aug", False))
+    ref = A.augmix_views(img, c["n_views"], bool(c["augmix"]), hard_aug=hard)
     torch.manual_seed(c["seed"]); np.random.seed(c["seed"])
-    aug = D.AugMixAugmenter(None, None, n_views=c["n_views"], augmix=bool(c["augmix"]), device=DEV)
+    aug = D.AugMixAugmenter(None, None, n_views=c["n_views"], augmix=bool(c["augmix"]), hard_aug=hard, device=DEV)
     views = aug(img)
     assert isinstance(views, list) and len(views) == c["n_views"] + 1 and views[0].is_cuda
     got = torch.stack(views).cpu()
@@ -49,13 +50,12 @@ def test_sixty_four_views_feed_the_engine_shape():
 def test_bad_inputs_are_rejected():
     from rlcf_b200 import datautils as D
     from rlcf_b200._lib import RlcfError
-    with pytest.raises(NotImplementedError):
-        D.AugMixAugmenter(n_views=3, hard_aug=True)
     with pytest.raises(RlcfError):
         D.AugMixAugmenter(n_views=3, device=DEV).views(torch.zeros(10, 10, 3))   # not uint8
 
 
-def test_driver_on_an_image_folder_with_gpu_views(tmp_path):
+@pytest.mark.parametrize("hard_aug", [0, 1])
+def test_driver_on_an_image_folder_with_gpu_views(tmp_path, hard_aug):
     """tune_cls_rl.main_worker on a real ImageFolder (PNG files decoded by PIL, views generated on the GPU, batched
     LayerNorm-tuning RLCF) with seeded random-init ViT-B/32 weights: the whole reference flow minus the checkpoints."""
     from rlcf_b200 import params, tune_cls_rl
@@ -67,7 +67,8 @@ def test_driver_on_an_image_folder_with_gpu_views(tmp_path):
     args = params.build_parser().parse_args([
         str(tmp_path / "data"), "--test_sets", "A", "-a", "ViT-B/32", "--reward_arch", "ViT-B/32", "--tpt",
         "--tune_norm", "1", "--batch_size", "8", "--selection_p", "0.5", "--tta_steps", "1", "--sample_k", "2",
-        "--synthetic_weights", "--images_per_step", "2", "--workers", "0", "--output", str(tmp_path / "out")])
+        "--synthetic_weights", "--images_per_step", "2", "--workers", "0", "--output", str(tmp_path / "out"),
+        "--hard_aug", str(hard_aug)])
     os.makedirs(args.output, exist_ok=True)
     res = tune_cls_rl.main_worker(0, args)
     top1, top5 = res["A"]

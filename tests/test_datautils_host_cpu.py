@@ -21,9 +21,13 @@ def test_plan_reproduces_the_reference_views(name):
     c = CASES[name]
     img = A.synthetic_image(c["h"], c["w"], c["seed"])
     torch.manual_seed(c["seed"]); np.random.seed(c["seed"])
-    ref = A.augmix_views(img, c["n_views"], bool(c["augmix"])).numpy()
+    hard = bool(c.get("hard_aug", False))
+    ref = A.augmix_views(img, c["n_views"], bool(c["augmix"]), hard_aug=hard).numpy()
     torch.manual_seed(c["seed"]); np.random.seed(c["seed"])
-    plan = D.sample_plan(c["w"], c["h"], c["n_views"], bool(c["augmix"]))
+    if hard:
+        plan = D.sample_plan_hard(img, c["n_views"], bool(c["augmix"]))
+    else:
+        plan = D.sample_plan(c["w"], c["h"], c["n_views"], bool(c["augmix"]))
     got = PN.execute(np.asarray(img), plan)
     bad = np.argwhere((got != ref).reshape(got.shape[0], -1).any(axis=1)).ravel().tolist()
     assert not bad, f"views {bad} differ; max |diff| {np.abs(got - ref).max():.3e}"

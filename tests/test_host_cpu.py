@@ -313,7 +313,8 @@ def test_unsupported_reference_flags_raise():
     from rlcf_b200.tune_cls_rl import _check_supported_flags
     base = ["DATA", "--tpt", "-a", "ViT-B/16"]
     _check_supported_flags(build_parser().parse_args(base))
-    for extra in (["--hard_aug", "1"], ["--confidence_gap", "1"], ["--multiple_reward_models", "1"]):
+    _check_supported_flags(build_parser().parse_args(base + ["--hard_aug", "1"]))            # host pre-augmentation
+    for extra in (["--confidence_gap", "1"], ["--multiple_reward_models", "1"]):
         with pytest.raises(NotImplementedError):
             _check_supported_flags(build_parser().parse_args(base + extra))
     with pytest.raises(NotImplementedError):

@@ -23,7 +23,7 @@ def test_view_generation_oracle_is_bit_exact_with_reference(name):
     c = cases()[name]
     img = A.synthetic_image(c["h"], c["w"], c["seed"])
     torch.manual_seed(c["seed"]); np.random.seed(c["seed"])
-    views = A.augmix_views(img, c["n_views"], bool(c["augmix"]))
+    views = A.augmix_views(img, c["n_views"], bool(c["augmix"]), hard_aug=bool(c.get("hard_aug", False)))
     assert list(views.shape) == c["shape"]
     per_view = [hashlib.sha256(v.contiguous().numpy().tobytes()).hexdigest()[:16] for v in views]
     assert per_view == c["per_view"]
