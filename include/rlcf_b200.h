@@ -46,7 +46,7 @@ int rlcf_set_gemm_cta_group(int cta_group);
 /* 1 = 4-CTA clusters: two CTA pairs share one weight tile through TMA multicast (512 x 256 cluster tile). */
 int rlcf_set_gemm_multicast(int on);
 /* Attention kernels (forward and backward): 0 = tcgen05/TMEM kernels (default; sequences beyond their TMEM layout --
- * forward L > 272, backward L > 384 -- use the warp-level kernels), 1 = warp-level mma.sync kernels. Returns the value set. */
+ * forward L > 640 or causal L > 272, backward L > 384 -- use the warp-level kernels), 1 = warp-level mma.sync kernels. Returns the value set. */
 int rlcf_set_attention_impl(int impl);
 
 /* D[M,N] = A[M,K] * B[N,K]^T, fp16 operands (K contiguous), fp32 accumulate on tcgen05 tensor cores.

@@ -336,6 +336,8 @@ int attention_fwd_tc(const __half* qkv, int n_seq, int L, int heads, int causal,
                      cudaStream_t stream);
 int attention_fwd_tc8(const __half* qkv, int n_seq, int L, int heads, int causal, __half* out, float* lse,
                       cudaStream_t stream);
+int attention_fwd_tcl(const __half* qkv, int n_seq, int L, int heads, int causal, __half* out, float* lse,
+                      cudaStream_t stream);
 
 int attention_fwd(const __half* qkv, int n_seq, int L, int heads, int causal, __half* out, float* lse,
                   cudaStream_t stream) {
@@ -344,12 +346,23 @@ int attention_fwd(const __half* qkv, int n_seq, int L, int heads, int causal, __
     // eight softmax warps per team (attention_tc8.cu, L <= 208: 217 vs 243 us at 512 x 197 x 12) where the sequence
     // fits (200 us with its token), else four (attention_tc.cu, L <= 272); RLCF_ATTN_TC8=0 keeps the four-warp kernel everywhere
     static const int tc8 = getenv("RLCF_ATTN_TC8") != nullptr ? atoi(getenv("RLCF_ATTN_TC8")) : 1;
+    // key-block kernel (attention_tcl.cu) for what the two above do not cover: 272 < L <= 640, not causal (ViT-L/14@336px:
+    // 577 tokens).  RLCF_ATTN_TCL=0 leaves those to the mma.sync kernel, =2 tries it FIRST for every shape (A/B probe)
+    static const int tcl = getenv("RLCF_ATTN_TCL") != nullptr ? atoi(getenv("RLCF_ATTN_TCL")) : 1;
+    if (tcl == 2) {
+      const int rcl = attention_fwd_tcl(qkv, n_seq, L, heads, causal, out, lse, stream);
+      if (rcl != -1) return rcl;
+    }
     if (tc8) {
       const int rc8 = attention_fwd_tc8(qkv, n_seq, L, heads, causal, out, lse, stream);
       if (rc8 != -1) return rc8;
     }
     const int rc = attention_fwd_tc(qkv, n_seq, L, heads, causal, out, lse, stream);
     if (rc != -1) return rc;
+    if (tcl == 1) {
+      const int rcl = attention_fwd_tcl(qkv, n_seq, L, heads, causal, out, lse, stream);
+      if (rcl != -1) return rcl;
+    }
   }
   const int Lp = (L + 15) / 16 * 16;
   const size_t smem = static_cast<size_t>(2 * Lp + kFwdWarps * 16) * kRowBytes;

@@ -6,7 +6,7 @@ from rlcf_b200 import ops, _lib
 dev = torch.device("cuda:0")
 for impl in ([0, 1] if len(sys.argv) < 2 else [int(sys.argv[1])]):
     _lib.set_attention_impl(impl)
-    for (n_seq, L, heads) in [(512, 197, 12), (48, 257, 16), (48, 197, 12)]:
+    for (n_seq, L, heads) in [(512, 197, 12), (48, 257, 16), (384, 257, 16), (48, 197, 12), (48, 577, 16), (384, 577, 16)]:
         d = heads * 64
         qkv = torch.randn(n_seq * L, 3 * d, device=dev).half()
         out = torch.empty(n_seq * L, d, device=dev, dtype=torch.float16)

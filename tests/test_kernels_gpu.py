@@ -300,11 +300,38 @@ def test_attention_fwd_sharply_peaked_rows(L, heads, causal):
     assert (sc.max(-1).values - sc[..., :32].max(-1).values).max().item() > 8.0
 
 
-def test_attention_forward_at_336_pixel_sequence_length():
-    """577 tokens (ViT-L/14@336px as a reward model, clip_reward.py:22-27): beyond the single-tile tcgen05 kernel, served
-    by the warp-MMA kernel; forward only (reward models are frozen)."""
-    torch.manual_seed(577)
-    n_seq, L, heads = 2, 577, 16
+@pytest.mark.parametrize("n_seq,L,heads", [(2, 577, 16), (40, 577, 16), (3, 300, 2), (2, 416, 3), (2, 417, 1),
+                                          (5, 640, 2), (3, 273, 4)])
+def test_attention_forward_long_sequences(n_seq, L, heads):
+    """272 < L <= 640 (577 tokens = ViT-L/14@336px as a reward model, clip_reward.py:22-27): the key-block tcgen05 kernel
+    (csrc/attention_tcl.cu; two passes over blocks of <= 208 keys, no online rescaling).  Output and log-sum-exp against
+    fp32; (40, 577, 16) gives every persistent CTA several units, so the barrier phases wrap; a third of the rows are
+    dominated by single keys in late blocks, so the cross-block maximum matters."""
+    torch.manual_seed(L + n_seq)
+    d = heads * 64
+    qkv = torch.randn(n_seq, L, 3, heads, 64, device=_dev())
+    u = torch.nn.functional.normalize(torch.randn(heads, 64, device=_dev()), dim=-1)
+    qkv[:, torch.arange(L, device=_dev()) % 3 == 0, 0] += 10.0 * u
+    for key, gain in ((40, 2.0), (L // 2, 4.0), (L - 7, 6.0), (L - 1, 8.0)):
+        qkv[:, key, 1] += gain * u
+    qkv = qkv.reshape(n_seq * L, 3 * d).half()
+    out = torch.full((n_seq * L, d), float("nan"), device=_dev(), dtype=torch.float16)
+    lse = torch.empty(n_seq, heads, L, device=_dev())
+    assert _lib.set_attention_impl(0) == 0
+    ops.attention_fwd(qkv, n_seq, L, heads, out, lse=lse)
+    ref, ref_lse = _ref_attention(qkv.float(), n_seq, L, heads, False)
+    assert torch.isfinite(out).all()
+    assert _rel(out, ref) < 2e-3
+    assert ((lse - ref_lse).abs() / ref_lse.abs().clamp_min(1.0)).max().item() < 1e-3
+    out2 = torch.empty_like(out)
+    ops.attention_fwd(qkv, n_seq, L, heads, out2)            # no log-sum-exp requested (frozen reward tower)
+    assert torch.equal(out, out2)
+
+
+def test_attention_forward_beyond_the_tcgen05_kernels():
+    """L = 700 (> 640: K and V of a unit no longer fit in shared memory next to the tiles) falls back to the warp-MMA kernel."""
+    torch.manual_seed(700)
+    n_seq, L, heads = 2, 700, 2
     d = heads * 64
     qkv = torch.randn(n_seq * L, 3 * d, device=_dev()).half()
     out = torch.empty(n_seq * L, d, device=_dev(), dtype=torch.float16)
