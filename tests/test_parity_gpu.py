@@ -267,6 +267,31 @@ def test_text_and_image_towers_match_oracle():
         assert (got_i.cpu() - ref_i).abs().max() < 2e-3
 
 
+def test_reward_features_at_336_pixels():
+    """ViT-L/14@336px as the reward model (the strongest single model the reference lists, clip_reward.py:22-27): the
+    224-pixel views are resized on the device (bicubic, align_corners, clip_reward.py:133-134) and run through 24 layers
+    of 577-token attention -- the key-block tcgen05 kernel (csrc/attention_tcl.cu).  Against the oracle in fp32 (run on
+    the GPU with TF32 off: the tower has 0.3 G parameters), unit-norm features of three selected views."""
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sd = to_dev(O.make_clip_state_dict("ViT-L/14@336px", 5))
+        views = O.make_views(1, 6, 224, 17).to(DEV)
+        idx = torch.tensor([4, 0, 3], device=DEV, dtype=torch.int32)
+        ref = O.reward_image_features(sd, views[idx.long()])
+        tower = E.prepare_visual(sd)
+        assert tower.resolution == 336
+        scorer = E.RewardScorer(tower, torch.zeros(7, tower.E, device=DEV), 3)
+        scorer.features(views, idx, 3)
+        got = scorer.feats[0][:3]
+        err = (got - ref).abs().max().item()
+        cos = (got * ref).sum(-1).min().item()
+        PL.record("reward_features/ViT-L/14@336px", max_abs_err_unit_features=err, min_cosine=cos, tokens=577)
+        assert err < 2e-3 and cos > 0.9999, (err, cos)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
 def test_end_to_end_with_cuda_text_features():
     """Drop-in behaviour including the once-per-dataset class features from the CUDA text tower (fp32 path,
     engine.TextRunnerF32): same 1e-3 bound on the adapted logits as with the oracle's class features."""
