@@ -478,8 +478,12 @@ def gemm_roofline(eng, batch, ms_per_step, B, value, world, args):
         "peak_source": pk["source"] + " (sustained bf16 dense, of measured)",
         "avg_launch_us": 1e3 * g_ms / len(recs), "gemm_share_of_step": g_ms / ms_per_step,
         "flops_per_launch": g_flops / len(recs),
-        "whole_step": {"algorithmic_gflop_per_image": flops_img / 1e9, "achieved_tflops": step_tflops,
-                       "frac": step_tflops / pk["tflops_sustained"]},
+        # algorithmic = what the algorithm needs: the last block of an inference forward only feeds the class token into
+        # ln_post, so its out_proj / MLP / attention rows of the other tokens are not computed (and not counted);
+        # reference_gflop_per_image = SURVEY.md 8(d)'s count with every block on every token, as the reference runs it
+        "whole_step": {"algorithmic_gflop_per_image": flops_img / 1e9,
+                       "reference_gflop_per_image": eng.reference_flops_per_image() / 1e9,
+                       "achieved_tflops": step_tflops, "frac": step_tflops / pk["tflops_sustained"]},
     }
 
 

@@ -332,6 +332,116 @@ attn_bwd_kernel(const __half* __restrict__ qkv, const __half* __restrict__ out, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Attention output of ONE query row per sequence (the class token).  In the LAST block of a ViT only the class
+// token's row feeds ln_post and the projection (TPT/clip/model.py:235-238), so an inference forward needs the last
+// block's attention, out_proj, ln_2 and MLP for that row alone; K and V still come from every token.  One warp per
+// (sequence, head), fp32 throughout: lane j scores keys j, j+32, ...; then the lanes own two output dimensions each
+// and walk the keys together.  Optionally copies the row of the fp32 residual stream to a compact [n_seq, d] buffer
+// (the residual operand of the out_proj GEMM on those rows).
+constexpr int kRowMaxT = 21;   // key slots per lane: L <= 672
+
+__global__ void __launch_bounds__(128) attn_row_fwd_kernel(const __half* __restrict__ qkv, int n_units, int L, int heads,
+                                                           int q_row, __half* __restrict__ out,
+                                                           const float* __restrict__ x, float* __restrict__ x_row) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u = blockIdx.x * 4 + warp;
+  if (u >= n_units) return;
+  const int h = u % heads, seq = u / heads;
+  const int d = heads * kHd;
+  const long long ld = 3LL * d;
+  const __half* base = qkv + static_cast<long long>(seq) * L * ld + h * kHd;
+  // the query row, whole, in every lane
+  float2 q[32];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(base + q_row * ld);
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) {
+      const uint4 v = qp[c8];
+      const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) q[c8 * 4 + e] = __half22float2(hv[e]);
+    }
+  }
+  float s[kRowMaxT];
+  float m = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < kRowMaxT; ++t) {
+    const int j = t * 32 + lane;
+    float acc = -INFINITY;
+    if (t * 32 < L && j < L) {
+      const uint4* kp = reinterpret_cast<const uint4*>(base + j * ld + d);
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        const uint4 v = kp[c8];
+        const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 kf = __half22float2(hv[e]);
+          a0 = fmaf(q[c8 * 4 + e].x, kf.x, a0);
+          a1 = fmaf(q[c8 * 4 + e].y, kf.y, a1);
+        }
+      }
+      acc = a0 + a1;
+    }
+    s[t] = acc;
+    m = fmaxf(m, acc);
+  }
+  m = warp_max(m);
+  const float c = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
+  float l = 0.f;
+#pragma unroll
+  for (int t = 0; t < kRowMaxT; ++t) {
+    s[t] = (t * 32 + lane < L) ? exp2f((s[t] - m) * c) : 0.f;
+    l += s[t];
+  }
+  l = warp_sum(l);
+  float o0 = 0.f, o1 = 0.f;
+  const __half* vbase = base + 2 * d + 2 * lane;
+#pragma unroll
+  for (int t = 0; t < kRowMaxT; ++t) {
+    if (t * 32 < L) {
+      const int n = min(32, L - t * 32);
+      if (n == 32) {
+#pragma unroll 8
+        for (int jj = 0; jj < 32; ++jj) {
+          const float pj = __shfl_sync(0xffffffffu, s[t], jj);
+          const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(vbase + (t * 32 + jj) * ld));
+          o0 = fmaf(pj, vf.x, o0);
+          o1 = fmaf(pj, vf.y, o1);
+        }
+      } else {
+        for (int jj = 0; jj < n; ++jj) {
+          const float pj = __shfl_sync(0xffffffffu, s[t], jj);
+          const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(vbase + (t * 32 + jj) * ld));
+          o0 = fmaf(pj, vf.x, o0);
+          o1 = fmaf(pj, vf.y, o1);
+        }
+      }
+    }
+  }
+  const float inv = 1.f / l;
+  *reinterpret_cast<__half2*>(out + static_cast<long long>(seq) * d + h * kHd + 2 * lane) = __floats2half2_rn(o0 * inv, o1 * inv);
+  if (x_row != nullptr) {
+    const float2 xv = *reinterpret_cast<const float2*>(x + (static_cast<long long>(seq) * L + q_row) * d + h * kHd + 2 * lane);
+    *reinterpret_cast<float2*>(x_row + static_cast<long long>(seq) * d + h * kHd + 2 * lane) = xv;
+  }
+}
+
+int attention_row_fwd(const __half* qkv, int n_seq, int L, int heads, int q_row, __half* out, const float* x,
+                      float* x_row, cudaStream_t stream) {
+  if (n_seq <= 0 || L <= 0 || heads <= 0 || q_row < 0 || q_row >= L)
+    return set_error(RLCF_ERR_ARG, "attention_row_fwd: bad shape");
+  if (L > 32 * kRowMaxT) return set_error(RLCF_ERR_ARG, "attention_row_fwd: sequence %d longer than %d", L, 32 * kRowMaxT);
+  if ((x == nullptr) != (x_row == nullptr)) return set_error(RLCF_ERR_ARG, "attention_row_fwd: x and x_row go together");
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) != 0) return set_error(RLCF_ERR_ARG, "attention_row_fwd: qkv must be 16-byte aligned");
+  const int n_units = n_seq * heads;
+  attn_row_fwd_kernel<<<(n_units + 3) / 4, 128, 0, stream>>>(qkv, n_units, L, heads, q_row, out, x, x_row);
+  RLCF_CHECK_LAUNCH("attention_row_fwd");
+  return 0;
+}
+
 int attention_fwd_tc(const __half* qkv, int n_seq, int L, int heads, int causal, __half* out, float* lse,
                      cudaStream_t stream);
 int attention_fwd_tc8(const __half* qkv, int n_seq, int L, int heads, int causal, __half* out, float* lse,

@@ -13,6 +13,7 @@ Reference call stack being replaced: TPT/tpt_cls_rl.py:47-79 (test_time_tuning),
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -20,6 +21,7 @@ import torch
 from . import ops
 from ._lib import EPI_F16, EPI_F32, EPI_GELU_BWD_F16, EPI_GELU_F16, EPI_RESID_F32, RlcfError
 
+PRUNE_LAST = os.environ.get("RLCF_PRUNE_LAST", "1") != "0"   # TowerRunner: last block on the class-token rows only
 N_SLOTS = 32  # gradient partial slots per parameter set = LN-backward blocks per image (deterministic reduction)
 
 
@@ -265,6 +267,16 @@ class TowerRunner:
         if w.kind == "visual":
             self.patches = torch.empty(max_seq * (L - 1), w.k_pad, **f16)
             self.patch_out = torch.empty(max_seq * (L - 1), d, **f32)
+        # Inference forwards of a vision tower run the LAST block's attention / out_proj / ln_2 / MLP on the class-token
+        # rows only: nothing else of that block reaches ln_post (model.py:232-238).  Same values for those rows, 1/L of
+        # the block's work after the QKV GEMM (~6 % of a 12-layer forward).  RLCF_PRUNE_LAST=0 runs every row.
+        self.infer_row_stride = L
+        if w.kind == "visual" and PRUNE_LAST and L <= 672 and w.n_layers > 0:
+            self.infer_row_stride = 1
+            self.c_x = torch.empty(3, max_seq, d, **f32)       # class-token rows: block input, after attention, output
+            self.c_a = torch.empty(max_seq, d, **f16)
+            self.c_h = torch.empty(max_seq, 4 * d, **f16)
+        self._out, self._out_stride = None, L
         # backward workspaces are allocated lazily by reserve_backward()
         self.g16 = self.gh = self.gqkv = self.dres = self.dres16 = None
 
@@ -331,6 +343,8 @@ class TowerRunner:
                     ops.embed_prompts_map(tokens, w.tok_emb, w.pos, ctx, ctx_stride, layout.src_map, n_sets, x)
             else:
                 ops.embed_text(tokens, w.tok_emb, w.pos, x)
+        prune = store is None and w is self.w and self.infer_row_stride == 1 and not causal
+        self._out_stride = L
         for l, lw in enumerate(w.layers):
             qkv = store.qkv[l] if store is not None else self.qkv
             attn = store.attn[l] if store is not None else self.a
@@ -339,6 +353,19 @@ class TowerRunner:
             g, b = gb(w.ln_off("ln_1", l))
             ops.layernorm_fwd(x, g, b, rows, d, out16=a1, param_stride=pstride, rows_per_set=rows_per_set)
             linear(a1, lw.wqkv, qkv, rows, epilogue=EPI_F16, bias=lw.bqkv)
+            if prune and l == w.n_layers - 1:
+                # last block, class-token rows only (K and V of every token are in qkv)
+                cx, cmid, cout = self.c_x[0], self.c_x[1], self.c_x[2]
+                sets = n_seq if seqs_per_set is None else seqs_per_set
+                ops.attention_row_fwd(qkv, n_seq, L, w.heads, self.c_a, q_row=0, x=x, x_row=cx)
+                linear(self.c_a, lw.wo, cmid, n_seq, epilogue=EPI_RESID_F32, bias=lw.bo, resid=cx)
+                g, b = gb(w.ln_off("ln_2", l))
+                ops.layernorm_fwd(cmid, g, b, n_seq, d, out16=self.c_a, param_stride=pstride, rows_per_set=sets)
+                linear(self.c_a, lw.wfc, self.c_h, n_seq, epilogue=EPI_GELU_F16, bias=lw.bfc)
+                linear(self.c_h, lw.wproj, cout, n_seq, epilogue=EPI_RESID_F32, bias=lw.bproj, resid=cmid)
+                x = cout
+                self._out_stride = 1
+                break
             ops.attention_fwd(qkv, n_seq, L, w.heads, attn, causal=causal,
                               lse=None if store is None else store.lse[l])
             x_mid = store.x_mid[l] if store is not None else x
@@ -352,6 +379,7 @@ class TowerRunner:
             x_next = store.x_in[l + 1] if store is not None else x
             linear(h, lw.wproj, x_next, rows, epilogue=EPI_RESID_F32, bias=lw.bproj, resid=x_mid)
             x = x_next
+        self._out = x
         return x
 
     def head(self, x, n_seq, ln, pstride=0, seqs_per_set=None, row_idx=None, class_feat=None, logit_scale=1.0,
@@ -360,8 +388,10 @@ class TowerRunner:
         w = self.w if w is None else w
         lnv = ln.view(-1)
         off = w.ln_off("ln_post")
+        # x is either [n_seq*L, d] (one row of each sequence is used) or the class-token rows [n_seq, d] of a pruned forward
+        row_stride = self._out_stride if x is self._out else w.L
         ops.head_fwd(x, lnv[off:], lnv[off + w.d:], w.proj, n_seq, w.d, w.E, feat=feat, inv_norm=inv_norm,
-                     logits=logits, class_feat=class_feat, logit_scale=logit_scale, row_idx=row_idx, row_stride=w.L,
+                     logits=logits, class_feat=class_feat, logit_scale=logit_scale, row_idx=row_idx, row_stride=row_stride,
                      param_stride=pstride, seqs_per_set=seqs_per_set, proj_stride=w.proj_stride)
 
     # ------------------------------------------------------------------ backward (LayerNorm parameters only)
@@ -484,7 +514,7 @@ class RewardScorer:
             ops.reward_loss_multi(logits, None, self.feats, self.class_feats, self.weights, n_img, S, K, C, dlogits, **kw)
 
     def fwd_flops(self) -> float:
-        return float(sum(RlcfEngine.tower_fwd_flops(t) for t in self.towers))
+        return float(sum(RlcfEngine.tower_fwd_flops(t, cls_only_last=True) for t in self.towers))
 
 
 class RlcfEngine:
@@ -655,10 +685,16 @@ class RlcfEngine:
 
     # FLOP accounting (2*MACs), SURVEY.md 8(d)
     @staticmethod
-    def tower_fwd_flops(w: TowerWeights) -> float:
+    def tower_fwd_flops(w: TowerWeights, cls_only_last: bool = False) -> float:
+        """cls_only_last: the inference forward of a vision tower, whose last block runs out_proj / MLP and attention for
+        the class-token row only (TowerRunner.forward) -- count what is needed, not what the reference executes."""
         L, d, n, E = w.L, w.d, w.n_layers, w.E
         conv = 2 * (L - 1) * d * 3 * w.patch * w.patch if w.kind == "visual" else 0
-        return conv + n * (24 * L * d * d + 4 * L * L * d) + 2 * d * E
+        block = 24 * L * d * d + 4 * L * L * d
+        if cls_only_last and w.kind == "visual" and PRUNE_LAST and L <= 672 and n > 0:
+            last = 6 * L * d * d + 4 * L * d + 18 * d * d          # QKV of every token; one query row; one row of the rest
+            return conv + (n - 1) * block + last + 2 * d * E
+        return conv + n * block + 2 * d * E
 
     @staticmethod
     def tower_dgrad_flops(w: TowerWeights) -> float:
@@ -669,10 +705,22 @@ class RlcfEngine:
         cfg = self.cfg
         V, S = cfg.n_views, cfg.n_selected
         f = self.tower_fwd_flops(self.policy)
-        total = V * f + S * self.tower_dgrad_flops(self.policy) + f
+        fi = self.tower_fwd_flops(self.policy, cls_only_last=True)      # the V-view and the final inference forwards
+        total = V * fi + S * self.tower_dgrad_flops(self.policy) + fi
         total += (cfg.tta_steps - 1) * S * (f + self.tower_dgrad_flops(self.policy))
         if self.scorer is not None and cfg.loss == "rlcf":
             total += S * self.scorer.fwd_flops()
+        return float(total)
+
+    def reference_flops_per_image(self) -> float:
+        """SURVEY.md 8(d)'s figure: the same count with every block run on every token, as the reference executes it."""
+        cfg = self.cfg
+        V, S = cfg.n_views, cfg.n_selected
+        f = self.tower_fwd_flops(self.policy)
+        total = V * f + S * self.tower_dgrad_flops(self.policy) + f
+        total += (cfg.tta_steps - 1) * S * (f + self.tower_dgrad_flops(self.policy))
+        if self.scorer is not None and cfg.loss == "rlcf":
+            total += S * sum(self.tower_fwd_flops(t) for t in self.scorer.towers)
         return float(total)
 
 
@@ -789,7 +837,7 @@ class PromptEngine:
         self.irun.head(x, B * V, self.visual.ln_flat, feat=self.img_feat_all)
         ops.pair_logits(self.img_feat_all, self.txt_feat0, 0, 1, B * V, C, E, self.logit_scale, self.logits_all)
         ops.entropy_select(self.logits_all, B, V, C, S, self.sel, self.sel_global, self.entropy)
-        torch.mul(self.sel_global, self.visual.L, out=self.sel_rows)
+        torch.mul(self.sel_global, self.irun.infer_row_stride, out=self.sel_rows)   # class-token row of each selected view
         self.irun.head(x, B * S, self.visual.ln_flat, row_idx=self.sel_rows, feat=self.img_feat_sel)
         if cfg.loss == "rlcf":
             self.scorer.features(images, self.sel_global, B * S)
@@ -841,7 +889,7 @@ class PromptEngine:
 
     def algorithmic_flops_per_image(self) -> float:
         cfg, C = self.cfg, self.tokens.shape[0]
-        fi, ft = RlcfEngine.tower_fwd_flops(self.visual), RlcfEngine.tower_fwd_flops(self.text)
+        fi, ft = RlcfEngine.tower_fwd_flops(self.visual, cls_only_last=True), RlcfEngine.tower_fwd_flops(self.text)
         total = cfg.n_views * fi + fi + C * ft + cfg.tta_steps * C * (ft + RlcfEngine.tower_dgrad_flops(self.text))
         if self.scorer is not None and cfg.loss == "rlcf":
             total += cfg.n_selected * self.scorer.fwd_flops()

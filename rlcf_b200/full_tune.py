@@ -448,7 +448,8 @@ class FullTuneEngine:
         f = E.RlcfEngine.tower_fwd_flops(w)
         wgrad = w.n_layers * 24 * w.L * w.d * w.d + 2 * (w.L - 1) * w.d * 3 * w.patch * w.patch + 2 * w.d * w.E
         bwd = E.RlcfEngine.tower_dgrad_flops(w) + wgrad
-        total = V * f + S * bwd + f + (cfg.tta_steps - 1) * S * (f + bwd) + S * self.scorer.fwd_flops()
+        fi = E.RlcfEngine.tower_fwd_flops(w, cls_only_last=True)   # the V-view forward with the shared initial weights
+        total = V * fi + S * bwd + f + (cfg.tta_steps - 1) * S * (f + bwd) + S * self.scorer.fwd_flops()
         return float(total)
 
     def export_params(self, b: int, prefix: str = "visual.") -> dict:

@@ -138,6 +138,14 @@ def attention_fwd(qkv, n_seq, L, heads, out, causal=False, lse=None):
     return out
 
 
+def attention_row_fwd(qkv, n_seq, L, heads, out, q_row=0, x=None, x_row=None):
+    """Attention output of row q_row of every sequence ([n_seq, d]); optionally gathers that row of x into x_row."""
+    _chk(qkv, torch.float16, "qkv"); _chk(out, torch.float16, "out")
+    _chk(x, torch.float32, "x"); _chk(x_row, torch.float32, "x_row")
+    call("rlcf_attention_row_fwd", ptr(qkv), n_seq, L, heads, q_row, ptr(out), ptr(x), ptr(x_row), stream())
+    return out
+
+
 def attention_bwd(qkv, out, dout, lse, n_seq, L, heads, dqkv, causal=False):
     _chk(qkv, torch.float16, "qkv"); _chk(out, torch.float16, "out"); _chk(dout, torch.float16, "dout")
     _chk(lse, torch.float32, "lse"); _chk(dqkv, torch.float16, "dqkv")

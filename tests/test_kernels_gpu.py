@@ -300,6 +300,30 @@ def test_attention_fwd_sharply_peaked_rows(L, heads, causal):
     assert (sc.max(-1).values - sc[..., :32].max(-1).values).max().item() > 8.0
 
 
+@pytest.mark.parametrize("n_seq,L,heads,q_row", [(7, 197, 12, 0), (3, 257, 16, 0), (5, 50, 2, 0), (2, 577, 16, 0),
+                                                (4, 5, 1, 3), (3, 197, 3, 196), (2, 672, 1, 0)])
+def test_attention_row_fwd(n_seq, L, heads, q_row):
+    """One query row per sequence (the class token of a ViT's last block) against the same row of the fp32 reference;
+    the optional gather of that row of the residual stream is exact."""
+    torch.manual_seed(L + q_row)
+    d = heads * 64
+    qkv = torch.randn(n_seq * L, 3 * d, device=_dev()).half()
+    x = torch.randn(n_seq * L, d, device=_dev())
+    out = torch.full((n_seq, d), float("nan"), device=_dev(), dtype=torch.float16)
+    x_row = torch.empty(n_seq, d, device=_dev())
+    ops.attention_row_fwd(qkv, n_seq, L, heads, out, q_row=q_row, x=x, x_row=x_row)
+    ref, _ = _ref_attention(qkv.float(), n_seq, L, heads, False)
+    ref_rows = ref.view(n_seq, L, d)[:, q_row]
+    assert torch.isfinite(out).all()
+    assert _rel(out, ref_rows) < 1e-3
+    assert torch.equal(x_row, x.view(n_seq, L, d)[:, q_row])
+    out2 = torch.empty_like(out)
+    ops.attention_row_fwd(qkv, n_seq, L, heads, out2, q_row=q_row)
+    assert torch.equal(out, out2)
+    with pytest.raises(_lib.RlcfError):
+        ops.attention_row_fwd(qkv, n_seq, L, heads, out, q_row=L)
+
+
 @pytest.mark.parametrize("n_seq,L,heads", [(2, 577, 16), (40, 577, 16), (3, 300, 2), (2, 416, 3), (2, 417, 1),
                                           (5, 640, 2), (3, 273, 4)])
 def test_attention_forward_long_sequences(n_seq, L, heads):
