@@ -16,6 +16,7 @@
 // team is in its softmax, the other team's loads and MMAs proceed, so launch, allocation and load latencies are paid
 // once per CTA instead of once per tile.  Replaces the bmm-softmax-bmm of nn.MultiheadAttention
 // (TPT/clip/model.py:185-187).
+#include <cstdio>
 #include <cstdlib>
 
 #include "ptx.cuh"
@@ -30,8 +31,13 @@ struct AttnTcArgs {
   int o_off;                    // TMEM column (inside the team's 256) of the O accumulator
   int n_qt, n_units;            // query tiles per (sequence, head); number of (sequence, head) units
   int stage_bytes;
+  int q_start;                  // first query row the 128-row tiles cover (1 when row 0 is the producer warp's row job)
+  int row_job;                  // 1: L - 1 is a multiple of 128 (257 tokens): the tiles cover rows [1, L) exactly and the
+                                // team's otherwise idle TMA warp computes row 0 on the CUDA cores from the K / V tiles in
+                                // shared memory -- instead of a third tile with one live row out of 128
   int sum_mma;                  // 1: the row sums come out of the P V MMA (a block of ones appended to V: O gets 80 columns)
-  int debug;                    // RLCF_ATTN_DEBUG bit mask (timing probes only): 1 skip max pass, 2 skip exp pass, 4 skip stores, 8 timeline, 16 no exp token, 32 per-thread O stores, 128 row sums on the CUDA cores
+  int debug;                    // RLCF_ATTN_DEBUG bit mask (timing probes only): 1 skip max pass, 2 skip exp pass, 4 skip stores, 8 timeline, 16 no exp token, 32 per-thread O stores, 128 row sums on the CUDA cores; row job: 256 protocol only, 512 no P V, 1024 print its clock64 duration, 2048 release K / V before it
+  const __half* qkv;
   __half* out;
   float* lse;
 };
@@ -143,6 +149,108 @@ __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t tro
   return l0 + l1;
 }
 
+// ---- query row 0 of one (sequence, head) by ONE warp, from the 128-byte-swizzled K / V tiles in shared memory.
+// Warp-level tensor-core MMAs (mma.sync m16n8k16; the 16-row A operand carries the query in row 0 and zeros below it):
+// a scalar fp32 version spent its time converting K and V to fp32 -- 1 150 half2 conversions per unit at a quarter of
+// the FMA rate made the row take longer than the two tcgen05 tiles it rides along with (profiles/r2_attention_probes.txt).
+__device__ __forceinline__ uint32_t r0_sw(int row, int chunk) {       // TMA's SWIZZLE_128B: 16-byte chunk ^ (row & 7)
+  return static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(chunk ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ void r0_ldsm(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void r0_ldsm_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void r0_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int kRow0Blocks = (256 + kMaxExtraKeys) / 16;   // 16-key blocks of the K / V tiles
+
+// kFull: the tiles hold exactly kRow0Blocks blocks (257 tokens) -- no per-block branch, so the blocks' MMAs interleave
+template <bool kFull>
+__device__ __noinline__ void row0_attention(uint32_t sK, uint32_t sV, const __half* qg, int L, int Lk, int lane,
+                                            __half* out_row, float* lse_row, bool skip_pv) {
+  const int g = lane >> 2, t = lane & 3;
+  // A fragments of [q; 0; ...; 0] (16 x 64): row g of the fragment lives in lanes 4g .. 4g+3, so only lanes 0-3 load
+  uint32_t qa[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    qa[ks][0] = g == 0 ? *reinterpret_cast<const uint32_t*>(qg + ks * 16 + 2 * t) : 0u;
+    qa[ks][2] = g == 0 ? *reinterpret_cast<const uint32_t*>(qg + ks * 16 + 8 + 2 * t) : 0u;
+    qa[ks][1] = qa[ks][3] = 0u;
+  }
+  // scores of row g against keys kb*16 + {2t, 2t+1, 8+2t, 9+2t}: every block's MMAs are independent of the others'
+  float s[kRow0Blocks][4];
+  float m = -INFINITY;
+#pragma unroll
+  for (int kb = 0; kb < kRow0Blocks; ++kb) {
+    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+    if (kFull || kb * 16 < Lk) {
+      const int r = kb * 16 + (lane & 7) + (lane >> 4) * 8;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t b[4];
+        r0_ldsm(b, sK + r0_sw(r, ks * 2 + ((lane >> 3) & 1)));
+        r0_mma(c0, qa[ks], b[0], b[1]);
+        r0_mma(c1, qa[ks], b[2], b[3]);
+      }
+    }
+    const int key = kb * 16 + 2 * t;
+    s[kb][0] = key < L ? c0[0] : -INFINITY;
+    s[kb][1] = key + 1 < L ? c0[1] : -INFINITY;
+    s[kb][2] = key + 8 < L ? c1[0] : -INFINITY;
+    s[kb][3] = key + 9 < L ? c1[1] : -INFINITY;
+    m = fmaxf(fmaxf(m, fmaxf(s[kb][0], s[kb][1])), fmaxf(s[kb][2], s[kb][3]));
+  }
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+  const float c = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
+  const float mc = m * c;
+  float l = 0.f;
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+#pragma unroll
+  for (int kb = 0; kb < kRow0Blocks; ++kb) {
+    if (kFull || kb * 16 < Lk) {
+      float pv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        pv[e] = g == 0 ? ex2_approx(fmaf(s[kb][e], c, -mc)) : 0.f;      // masked keys: 2^-inf = 0
+        l += pv[e];
+      }
+      if (!skip_pv) {
+        __half2 h01 = __floats2half2_rn(pv[0], pv[1]), h23 = __floats2half2_rn(pv[2], pv[3]);
+        const uint32_t pa[4] = {*reinterpret_cast<uint32_t*>(&h01), 0u, *reinterpret_cast<uint32_t*>(&h23), 0u};
+        const int r = kb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          uint32_t b[4];
+          r0_ldsm_t(b, sV + r0_sw(r, np * 2 + (lane >> 4)));
+          r0_mma(o[2 * np], pa, b[0], b[1]);
+          r0_mma(o[2 * np + 1], pa, b[2], b[3]);
+        }
+      }
+    }
+  }
+  l += __shfl_xor_sync(0xffffffffu, l, 1);
+  l += __shfl_xor_sync(0xffffffffu, l, 2);
+  if (g == 0) {
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+      *reinterpret_cast<__half2*>(out_row + nt * 8 + 2 * t) = __floats2half2_rn(o[nt][0] * inv, o[nt][1] * inv);
+    if (t == 0 && lse_row != nullptr) *lse_row = m * 0.125f + logf(l);
+  }
+}
+
 template <bool kSumMma>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKV,
@@ -169,6 +277,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       for (int i = 0; i < B_PER_TEAM; ++i) mbar_init(&b[i], 1);
       mbar_init(&b[B_PREADY], 4);    // one arrive per softmax warp
       mbar_init(&b[B_TMEMFREE], 4);
+      if (p.row_job) mbar_init(&b[B_KVFREE], 2);   // the MMA commit and the producer warp's row job both read K / V
       if (!(p.debug & 32)) {         // the O tile is staged in the Q buffer: its TMA store must have read it too
         mbar_init(&b[B_QFREE], 5);
         mbar_init(&b[B_QFREE + 1], 5);
@@ -203,12 +312,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   const int first = blockIdx.x + team * gridDim.x, stride = 2 * gridDim.x;
 
   if (warp == 0 || warp == 3) {
-    // ------------------------------------------------------------ TMA producer of this team
-    if (lane == 0) {
-      uint32_t uc = 0, tc = 0;
-      for (int u = first; u < p.n_units; u += stride, ++uc) {
-        const int h = u % p.heads, seq = u / p.heads;
-        const int row_base = seq * p.L;
+    // ------------------------------------------------------------ TMA producer of this team (+ the row job)
+    uint32_t uc = 0, tc = 0;
+    for (int u = first; u < p.n_units; u += stride, ++uc) {
+      const int h = u % p.heads, seq = u / p.heads;
+      const int row_base = seq * p.L;
+      if (lane == 0) {
         mbar_wait(&tb[B_KVFREE], (uc & 1) ^ 1);
         mbar_expect_tx(&tb[B_KVFULL], 2 * p.Lk * 128);
         for (int b = 0; b < p.n_kv_boxes; ++b) {
@@ -219,8 +328,32 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
           const int buf = tc & 1;
           mbar_wait(&tb[B_QFREE + buf], ((tc >> 1) & 1) ^ 1);
           mbar_expect_tx(&tb[B_QFULL + buf], 128 * 128);
-          tma_load_2d(sQ + buf * 128 * 128, &mapQ, &tb[B_QFULL + buf], h * 64, row_base + qt * 128);
+          tma_load_2d(sQ + buf * 128 * 128, &mapQ, &tb[B_QFULL + buf], h * 64, row_base + p.q_start + qt * 128);
         }
+      }
+      if (p.row_job) {
+        // query row 0 of this unit, whole warp, fp32: lane j scores keys j, j + 32, ... from the swizzled K tile, then
+        // every lane owns two output dimensions and the warp walks the rows of the V tile together
+        __syncwarp();
+        mbar_wait(&tb[B_KVFULL], uc & 1);
+        if (p.debug & 256) {            // timing probe: barrier protocol only, row 0 is NOT computed
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tb[B_KVFREE]);
+          continue;
+        }
+        const __half* qg = reinterpret_cast<const __half*>(p.qkv) + static_cast<size_t>(row_base) * 3 * d + h * 64;
+        __half* out_row = p.out + static_cast<size_t>(row_base) * d + h * 64;
+        float* lse_row = (p.lse != nullptr && !(p.debug & 8)) ? p.lse + (static_cast<size_t>(seq) * p.heads + h) * p.L : nullptr;
+        if ((p.debug & 2048) && lane == 0) mbar_arrive(&tb[B_KVFREE]);   // timing probe: release K / V BEFORE the row job (results undefined)
+        const long long t_row0 = clock64();
+        if (p.Lk == kRow0Blocks * 16)
+          row0_attention<true>(smem_u32(sK), smem_u32(sV), qg, p.L, p.Lk, lane, out_row, lse_row, (p.debug & 512) != 0);
+        else
+          row0_attention<false>(smem_u32(sK), smem_u32(sV), qg, p.L, p.Lk, lane, out_row, lse_row, (p.debug & 512) != 0);
+        __syncwarp();
+        if ((p.debug & 1024) && blockIdx.x == 0 && lane == 0 && uc >= 2 && uc < 6)
+          printf("team %d unit %u: row job %lld cycles, started %lld\n", team, uc, clock64() - t_row0, t_row0);
+        if (lane == 0 && !(p.debug & 2048)) mbar_arrive(&tb[B_KVFREE]);     // this warp is done with the unit's K / V
       }
     }
   } else if (warp == 1 || warp == 2) {
@@ -282,7 +415,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       for (int qt = 0; qt < p.n_qt; ++qt, ++tc) {
         const uint32_t ph = tc & 1;
         const uint8_t* sQb = sQ + (tc & 1) * 128 * 128;
-        const int q0 = qt * 128, qrow = q0 + r;
+        const int q0 = p.q_start + qt * 128, qrow = q0 + r;
         const int key_end = p.causal ? min(p.L, qrow + 1) : p.L;  // keys [0, key_end) are visible to this row
         const bool warp_live = q0 + (warp & 3) * 32 < p.L;         // rows of a dead warp are never stored
         // chunks below `full_chunks` are visible to every row of this warp: no masking needed there
@@ -494,7 +627,12 @@ int attention_fwd_tc(const __half* qkv, int n_seq, int L, int heads, int causal,
   if (Lk <= 256) { a.kv_box_rows = Lk; a.n_kv_boxes = 1; }
   else { a.kv_box_rows = Lk / 2; a.n_kv_boxes = 2; }
   a.o_off = ((Lk / 2) + 31) / 32 * 32;   // behind P (Lk/2 packed columns), <= 160, so O ends at <= 224 < 256
-  a.n_qt = (L + 127) / 128;
+  a.qkv = qkv;
+  // 257 tokens = 2 x 128 + 1: the tiles take rows [1, L), the producer warp computes row 0 (RLCF_ATTN_ROWJOB=0: three tiles)
+  static const int row_job = getenv("RLCF_ATTN_ROWJOB") != nullptr ? atoi(getenv("RLCF_ATTN_ROWJOB")) : 1;
+  a.row_job = row_job && !causal && L > 128 && (L - 1) % 128 == 0;
+  a.q_start = a.row_job ? 1 : 0;
+  a.n_qt = (L - a.q_start + 127) / 128;
   a.n_units = heads * n_seq;
   a.stage_bytes = 2 * 128 * 128 + 2 * Lk * 128;
   static const int debug = getenv("RLCF_ATTN_DEBUG") ? atoi(getenv("RLCF_ATTN_DEBUG")) : 0;

@@ -300,6 +300,25 @@ def test_attention_fwd_sharply_peaked_rows(L, heads, causal):
     assert (sc.max(-1).values - sc[..., :32].max(-1).values).max().item() > 8.0
 
 
+@pytest.mark.parametrize("n_seq,L,heads", [(30, 257, 16), (2, 257, 1), (9, 129, 3)])
+def test_attention_forward_class_token_row_job(n_seq, L, heads):
+    """L = 128 k + 1 (ViT-L/14: 257 tokens): the 128-row tiles cover rows [1, L) and the TMA warp of each team computes
+    row 0 on the CUDA cores from the K / V tiles in shared memory (attention_tc.cu), instead of a tile with one live row.
+    Output and log-sum-exp of every row against fp32, many units per CTA."""
+    torch.manual_seed(L * 7 + n_seq)
+    d = heads * 64
+    qkv = torch.randn(n_seq * L, 3 * d, device=_dev()).half()
+    out = torch.full((n_seq * L, d), float("nan"), device=_dev(), dtype=torch.float16)
+    lse = torch.full((n_seq, heads, L), float("nan"), device=_dev())
+    assert _lib.set_attention_impl(0) == 0
+    ops.attention_fwd(qkv, n_seq, L, heads, out, lse=lse)
+    ref, ref_lse = _ref_attention(qkv.float(), n_seq, L, heads, False)
+    assert torch.isfinite(out).all() and torch.isfinite(lse).all()
+    assert _rel(out, ref) < 2e-3
+    assert _rel(out.view(n_seq, L, d)[:, 0], ref.view(n_seq, L, d)[:, 0]) < 1e-3      # the CUDA-core row
+    assert (lse - ref_lse).abs().max().item() < 1e-3
+
+
 @pytest.mark.parametrize("n_seq,L,heads,q_row", [(7, 197, 12, 0), (3, 257, 16, 0), (5, 50, 2, 0), (2, 577, 16, 0),
                                                 (4, 5, 1, 3), (3, 197, 3, 196), (2, 672, 1, 0)])
 def test_attention_row_fwd(n_seq, L, heads, q_row):
