@@ -21,6 +21,7 @@ import torch
 from . import ops
 from ._lib import EPI_F16, EPI_F32, EPI_GELU_BWD_F16, EPI_GELU_F16, EPI_RESID_F32, RlcfError
 
+TRUNCATE_TEXT = os.environ.get("RLCF_TEXT_TRUNCATE", "1") != "0"   # PromptEngine: drop the padding after the last EOT
 PRUNE_LAST = os.environ.get("RLCF_PRUNE_LAST", "1") != "0"   # TowerRunner: last block on the class-token rows only
 N_SLOTS = 32  # gradient partial slots per parameter set = LN-backward blocks per image (deterministic reduction)
 
@@ -744,6 +745,24 @@ class PromptEngine:
         self.cfg, self.n_img, self.visual, self.text, self.reward = cfg, n_img, visual, text, reward
         self.logit_scale = float(logit_scale)
         self.tokens = tokens.to(device=dev, dtype=torch.int64).contiguous()
+        # The text tower is causal (model.py:328-334) and only the EOT row of a prompt is read (model.py:352-354): the
+        # zero padding behind the EOT -- 60-odd of CLIP's 77 positions for "a photo of a <class>." -- cannot reach it.
+        # Run the tower on the first max(EOT) + 1 positions (rounded up to 8): same EOT rows, same context gradients,
+        # a fifth of the work the reference spends there.  RLCF_TEXT_TRUNCATE=0 keeps all 77.
+        L_full = self.tokens.shape[1]
+        need = int(self.tokens.argmax(dim=-1).max()) + 1
+        if layout is not None:       # source positions the assembled prefix reads from
+            need = max(need, int(layout.src_map[:, :need].max()) + 1)
+        L_eff = min(L_full, (need + 7) // 8 * 8)
+        if TRUNCATE_TEXT and L_eff < L_full:
+            import dataclasses
+            text = dataclasses.replace(text, L=L_eff, pos=text.pos[:L_eff].contiguous())
+            self.text = text
+            self.tokens = self.tokens[:, :L_eff].contiguous()
+            if layout is not None:
+                layout = dataclasses.replace(layout, src_map=layout.src_map[:, :L_eff].contiguous())
+                self.layout = layout
+        self.text_tokens = self.tokens.shape[1]
         C, L = self.tokens.shape
         n_vec, d = ctx_init.shape
         self.n_ctx = n_vec if layout is None else layout.n_ctx

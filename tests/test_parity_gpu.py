@@ -373,6 +373,34 @@ def _prompt_engine(cfg, tokens, ctx_init, n_img, loss="rlcf"):
     return eng, sd_p, sd_r, rc
 
 
+@pytest.mark.parametrize("golden", ["tiny_prompt_rlcf_2step", "tiny_prompt_front"])
+def test_text_tower_on_the_eot_prefix_equals_all_77_positions(golden, monkeypatch):
+    """PromptEngine runs the causal text tower on the positions up to the last EOT only (the padding behind it cannot
+    reach an EOT row: model.py:328-334, 352-354).  Same per-image text features and the same context gradient as with
+    all 77 positions (RLCF_TEXT_TRUNCATE=0), to the rounding of differently tiled attention."""
+    z = np.load(os.path.join(GOLDEN, golden + ".npz"), allow_pickle=True)
+    cfg = ast.literal_eval(str(z["meta"]))
+    cfg = dict(cfg, steps=1)
+    tokens, ctx_init = torch.tensor(z["tokens"]), torch.tensor(z["ctx_init"])
+    views = O.make_views(cfg["n_img"], cfg["V"], O.ARCHS[cfg["policy"]][1], VIEW_SEED).to(DEV)
+    res = {}
+    for trunc in (True, False):
+        monkeypatch.setattr(E, "TRUNCATE_TEXT", trunc)
+        eng, *_ = _prompt_engine(cfg, tokens, ctx_init, cfg["n_img"])
+        assert (eng.text_tokens < 77) == trunc and eng.text_tokens % 8 == 0 or eng.text_tokens == 77
+        eng._graph = None
+        eng.tune(views)
+        torch.cuda.synchronize()
+        res[trunc] = (eng.text_tokens, eng.txt_feat.clone().cpu(), eng.grad.clone().cpu(), eng.logits_all.clone().cpu())
+    (Lt, ft, gt, la), (Lf, ff, gf, lb) = res[True], res[False]
+    e_feat = (ft - ff).abs().max().item()
+    e_grad = ((gt - gf).abs().max() / gf.abs().max()).item()
+    PL.record(f"text_prefix/{golden}", text_tokens=Lt, of=Lf, txt_feat_max_abs_diff=e_feat, ctx_grad_rel_diff=e_grad)
+    assert Lt < Lf == 77
+    assert torch.equal(la, lb)                     # step-0 logits do not involve the per-image text tower
+    assert e_feat < 2e-4 and e_grad < 5e-3, (e_feat, e_grad)
+
+
 def test_prompt_tuning_matches_reference_golden_and_oracle():
     """Prompt tuning: backward through the TEXT tower to the context vectors, n images batched."""
     z = np.load(os.path.join(GOLDEN, "tiny_prompt_rlcf_2step.npz"))
