@@ -507,6 +507,8 @@ def other_modes_leg(dev, rank):
                          "frac_of_sustained_tensor_peak": fl * m["value"] / 1e12 / pk["tflops_sustained"],
                          "workload": make_config(wl, mode, config, B, 1)["workload"],
                          "clocks": {k: m["clocks"].get(k) for k in ("sm_mhz", "reasons")}}
+            if hasattr(eng, "text_tokens"):     # prompt tuning: positions of CLIP's 77 the causal text tower runs on
+                out[name]["text_positions"] = f"{eng.text_tokens} of 77 (up to the last EOT; the padding cannot reach it)"
             del eng, m
         except Exception as e:   # informational leg: never take the headline line down with it
             out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
