@@ -232,6 +232,12 @@ int rlcf_reset_params(const float* init, float* params, float* m, float* v, int 
 /* fp32 -> fp16 with optional zero padding of each row from cols to ld_out (weight preparation). */
 int rlcf_cast_f16(const float* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
                   void* stream);
+/* dst[l][j] = src[l][idx[j]] for l < n_layers, j < n, in blocks of seq_bytes bytes (one sequence's rows of one activation
+ * tensor; sizes and pointers multiples of 4, 16-byte vectors when they allow).  The reference keeps the autograd graph of all 64 views and backpropagates
+ * through output[selected_idx] (tpt_cls_rl.py:57-71); here the 64-view pass writes its per-layer activations to a store
+ * and the selected views' are lifted out for the backward -- instead of running those views a second time. */
+int rlcf_gather_seqs(const void* src, const int32_t* idx, void* dst, int64_t seq_bytes, int64_t src_layer_bytes,
+                     int64_t dst_layer_bytes, int n_layers, int n, void* stream);
 /* out16[c, r] = in32[r, c]  (W^T copies used as the B operand of dgrad GEMMs). */
 int rlcf_transpose_cast_f16(const float* in, int rows, int cols, void* out, void* stream);
 

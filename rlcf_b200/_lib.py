@@ -63,6 +63,7 @@ _PROTOS = {
     "rlcf_adamw_step": [_vp, _vp, _vp, _vp, _i, _i, _i64, _f, _f, _f, _f, _f, _i, _f, _vp, _vp],
     "rlcf_reset_params": [_vp, _vp, _vp, _vp, _i, _i64, _vp],
     "rlcf_cast_f16": [_vp, _i64, _i64, _i64, _vp, _i64, _vp],
+    "rlcf_gather_seqs": [_vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _vp],
     "rlcf_transpose_cast_f16": [_vp, _i, _i, _vp, _vp],
     "rlcf_embed_lnpre_sets": [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _f, _vp, _vp, _vp],
     "rlcf_head_fwd_sets": [_vp, _vp, _i64, _vp, _vp, _i64, _i, _vp, _i64, _vp, _f, _i, _i, _i, _i, _f, _vp, _vp, _vp,

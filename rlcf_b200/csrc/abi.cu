@@ -118,6 +118,7 @@ int adamw_step(float*, float*, float*, const float*, int, int, long long, float,
                float, float*, const float*, long long, int, cudaStream_t);
 int reset_params(const float*, float*, float*, float*, int, long long, cudaStream_t);
 int cast_f16(const float*, long long, long long, long long, __half*, long long, cudaStream_t);
+int gather_seqs(const void*, const int*, void*, long long, long long, long long, int, int, cudaStream_t);
 int transpose_cast_f16(const float*, int, int, __half*, int, long long, long long, cudaStream_t);
 int retrieval_loss(const float*, long long, const float*, const float*, int, int, int, int, float, int, int, float,
                    float*, int32_t*, float*, float*, float*, cudaStream_t);
@@ -412,6 +413,12 @@ int rlcf_cast_f16(const float* in, int64_t rows, int64_t cols, int64_t ld_in, vo
                   void* stream) {
   if (!in || !out) return set_error(RLCF_ERR_ARG, "cast_f16: null pointer");
   return cast_f16(in, rows, cols, ld_in, H(out), ld_out, S(stream));
+}
+
+int rlcf_gather_seqs(const void* src, const int32_t* idx, void* dst, int64_t seq_bytes, int64_t src_layer_bytes,
+                     int64_t dst_layer_bytes, int n_layers, int n, void* stream) {
+  if (!src || !idx || !dst) return set_error(RLCF_ERR_ARG, "gather_seqs: null pointer");
+  return gather_seqs(src, idx, dst, seq_bytes, src_layer_bytes, dst_layer_bytes, n_layers, n, S(stream));
 }
 
 int rlcf_transpose_cast_f16(const float* in, int rows, int cols, void* out, void* stream) {

@@ -1184,6 +1184,44 @@ int cast_f16(const float* in, long long rows, long long cols, long long ld_in, _
   return 0;
 }
 
+// dst[layer][j] = src[layer][idx[j]] for blocks ("sequences") of seq_bytes bytes: the activations of the selected
+// views are lifted out of the all-views store of the 64-view pass, one launch per tensor (grid.y = layer).  16-byte
+// vectors when sizes and pointers allow, else 4-byte words (the log-sum-exp rows of small towers).
+template <typename T>
+__global__ void __launch_bounds__(256) gather_seqs_kernel(const T* __restrict__ src, const int* __restrict__ idx,
+                                                          T* __restrict__ dst, long long seq_vec, long long src_layer_vec,
+                                                          long long dst_layer_vec, int n) {
+  src += blockIdx.y * src_layer_vec;
+  dst += blockIdx.y * dst_layer_vec;
+  const long long total = static_cast<long long>(n) * seq_vec;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const long long j = i / seq_vec, o = i - j * seq_vec;
+    dst[i] = src[static_cast<long long>(idx[j]) * seq_vec + o];
+  }
+}
+
+int gather_seqs(const void* src, const int* idx, void* dst, long long seq_bytes, long long src_layer_bytes,
+                long long dst_layer_bytes, int n_layers, int n, cudaStream_t stream) {
+  if (n <= 0 || n_layers <= 0 || seq_bytes <= 0) return set_error(RLCF_ERR_ARG, "gather_seqs: bad shape");
+  const uintptr_t bits = static_cast<uintptr_t>(seq_bytes | src_layer_bytes | dst_layer_bytes) |
+                         reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst);
+  if (bits & 3) return set_error(RLCF_ERR_ARG, "gather_seqs: sizes and pointers must be multiples of 4 bytes");
+  const int vec = (bits & 15) ? 4 : 16;
+  const long long total = static_cast<long long>(n) * (seq_bytes / vec);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  const dim3 grid(static_cast<unsigned>(blocks), n_layers);
+  if (vec == 16)
+    gather_seqs_kernel<uint4><<<grid, 256, 0, stream>>>(static_cast<const uint4*>(src), idx, static_cast<uint4*>(dst),
+                                                        seq_bytes / 16, src_layer_bytes / 16, dst_layer_bytes / 16, n);
+  else
+    gather_seqs_kernel<uint32_t><<<grid, 256, 0, stream>>>(static_cast<const uint32_t*>(src), idx,
+                                                           static_cast<uint32_t*>(dst), seq_bytes / 4, src_layer_bytes / 4,
+                                                           dst_layer_bytes / 4, n);
+  RLCF_CHECK_LAUNCH("gather_seqs");
+  return 0;
+}
+
 __global__ void transpose_cast_kernel(const float* __restrict__ in, int rows, int cols, __half* __restrict__ out,
                                       long long in_stride, long long out_stride) {
   __shared__ float tile[32][33];

@@ -250,6 +250,33 @@ class ActStore:
         self.h = torch.empty(nl, rows, 4 * d, **f16) if full else None   # QuickGELU output (input of c_proj)
 
 
+class ViewStore:
+    """Per-layer activations of the all-views inference pass for a chunk of images, blocks 0 .. n_layers - 2 (the last
+    block of that pass only computes the class-token rows).  After the confident views are known, their slices are
+    lifted into the ActStore of the backward (TowerRunner.adopt) instead of running those views a second time: the
+    reference gets the same from autograd, which keeps the graph of all 64 views (tpt_cls_rl.py:55-71).  The QuickGELU
+    pre-activation -- a third of the bytes -- is not kept; TowerRunner.complete recomputes it for the selected views."""
+
+    def __init__(self, w: TowerWeights, n_seq: int, device):
+        d, L, nl = w.d, w.L, w.n_layers - 1
+        rows = n_seq * L
+        f32 = dict(dtype=torch.float32, device=device)
+        f16 = dict(dtype=torch.float16, device=device)
+        self.n_seq, self.rows, self.n_layers = n_seq, rows, nl
+        self.x_pre = torch.empty(rows, d, **f32) if w.has_ln_pre else None
+        self.x_in = torch.empty(nl + 1, rows, d, **f32)   # x_in[nl] = input of the last block
+        self.x_mid = torch.empty(nl, rows, d, **f32)
+        self.qkv = torch.empty(nl, rows, 3 * d, **f16)
+        self.attn = torch.empty(nl, rows, d, **f16)
+        self.lse = torch.empty(nl, n_seq, w.heads, L, **f32)
+        self.u = self.a1 = self.a2 = self.h = None
+
+    @staticmethod
+    def bytes_per_seq(w: TowerWeights) -> int:
+        nl = w.n_layers - 1
+        return w.L * w.d * (4 * (nl + 1 + nl + (1 if w.has_ln_pre else 0)) + 2 * 4 * nl) + 4 * nl * w.heads * w.L
+
+
 class TowerRunner:
     """Runs one tower's forward (and LayerNorm-parameter backward) on preallocated workspaces."""
 
@@ -344,21 +371,20 @@ class TowerRunner:
                     ops.embed_prompts_map(tokens, w.tok_emb, w.pos, ctx, ctx_stride, layout.src_map, n_sets, x)
             else:
                 ops.embed_text(tokens, w.tok_emb, w.pos, x)
-        prune = store is None and w is self.w and self.infer_row_stride == 1 and not causal
+        views = isinstance(store, ViewStore)
+        if views and not (w is self.w and self.infer_row_stride == 1 and not causal):
+            raise RlcfError("a ViewStore needs the class-token-only last block (vision tower, shared weights)")
+        prune = (store is None or views) and w is self.w and self.infer_row_stride == 1 and not causal
         self._out_stride = L
         for l, lw in enumerate(w.layers):
-            qkv = store.qkv[l] if store is not None else self.qkv
-            attn = store.attn[l] if store is not None else self.a
-            full = store is not None and store.a1 is not None
-            a1 = store.a1[l] if full else self.a
-            g, b = gb(w.ln_off("ln_1", l))
-            ops.layernorm_fwd(x, g, b, rows, d, out16=a1, param_stride=pstride, rows_per_set=rows_per_set)
-            linear(a1, lw.wqkv, qkv, rows, epilogue=EPI_F16, bias=lw.bqkv)
             if prune and l == w.n_layers - 1:
                 # last block, class-token rows only (K and V of every token are in qkv)
+                g, b = gb(w.ln_off("ln_1", l))
+                ops.layernorm_fwd(x, g, b, rows, d, out16=self.a, param_stride=pstride, rows_per_set=rows_per_set)
+                linear(self.a, lw.wqkv, self.qkv, rows, epilogue=EPI_F16, bias=lw.bqkv)
                 cx, cmid, cout = self.c_x[0], self.c_x[1], self.c_x[2]
                 sets = n_seq if seqs_per_set is None else seqs_per_set
-                ops.attention_row_fwd(qkv, n_seq, L, w.heads, self.c_a, q_row=0, x=x, x_row=cx)
+                ops.attention_row_fwd(self.qkv, n_seq, L, w.heads, self.c_a, q_row=0, x=x, x_row=cx)
                 linear(self.c_a, lw.wo, cmid, n_seq, epilogue=EPI_RESID_F32, bias=lw.bo, resid=cx)
                 g, b = gb(w.ln_off("ln_2", l))
                 ops.layernorm_fwd(cmid, g, b, n_seq, d, out16=self.c_a, param_stride=pstride, rows_per_set=sets)
@@ -367,20 +393,64 @@ class TowerRunner:
                 x = cout
                 self._out_stride = 1
                 break
-            ops.attention_fwd(qkv, n_seq, L, w.heads, attn, causal=causal,
-                              lse=None if store is None else store.lse[l])
-            x_mid = store.x_mid[l] if store is not None else x
-            linear(attn, lw.wo, x_mid, rows, epilogue=EPI_RESID_F32, bias=lw.bo, resid=x)
-            a2 = store.a2[l] if full else self.a
-            h = store.h[l] if full else self.h
-            g, b = gb(w.ln_off("ln_2", l))
-            ops.layernorm_fwd(x_mid, g, b, rows, d, out16=a2, param_stride=pstride, rows_per_set=rows_per_set)
-            linear(a2, lw.wfc, h, rows, epilogue=EPI_GELU_F16, bias=lw.bfc,
-                   aux_out=None if store is None else store.u[l])
-            x_next = store.x_in[l + 1] if store is not None else x
-            linear(h, lw.wproj, x_next, rows, epilogue=EPI_RESID_F32, bias=lw.bproj, resid=x_mid)
-            x = x_next
+            x = self._block(l, x, n_seq, lnv, pstride, rows_per_set, store, causal, w)
         self._out = x
+        return x
+
+    def _block(self, l, x, n_seq, lnv, pstride, rows_per_set, store, causal, w):
+        """One residual attention block (model.py:171-192) on every row of x; returns the block's output."""
+        d, L = w.d, w.L
+        rows = n_seq * L
+        lw = w.layers[l]
+        qkv = store.qkv[l] if store is not None else self.qkv
+        attn = store.attn[l] if store is not None else self.a
+        full = store is not None and store.a1 is not None
+        a1 = store.a1[l] if full else self.a
+        off = w.ln_off("ln_1", l)
+        ops.layernorm_fwd(x, lnv[off:], lnv[off + d:], rows, d, out16=a1, param_stride=pstride, rows_per_set=rows_per_set)
+        linear(a1, lw.wqkv, qkv, rows, epilogue=EPI_F16, bias=lw.bqkv)
+        ops.attention_fwd(qkv, n_seq, L, w.heads, attn, causal=causal, lse=None if store is None else store.lse[l])
+        x_mid = store.x_mid[l] if store is not None else x
+        linear(attn, lw.wo, x_mid, rows, epilogue=EPI_RESID_F32, bias=lw.bo, resid=x)
+        a2 = store.a2[l] if full else self.a
+        h = store.h[l] if full else self.h
+        off = w.ln_off("ln_2", l)
+        ops.layernorm_fwd(x_mid, lnv[off:], lnv[off + d:], rows, d, out16=a2, param_stride=pstride,
+                          rows_per_set=rows_per_set)
+        linear(a2, lw.wfc, h, rows, epilogue=EPI_GELU_F16, bias=lw.bfc,
+               aux_out=None if store is None or store.u is None else store.u[l])
+        x_next = store.x_in[l + 1] if store is not None else x
+        linear(h, lw.wproj, x_next, rows, epilogue=EPI_RESID_F32, bias=lw.bproj, resid=x_mid)
+        return x_next
+
+    def adopt(self, views: ViewStore, idx: torch.Tensor, n: int, store: ActStore, seq0: int = 0):
+        """Lifts the activations of sequences idx[0:n] of a ViewStore (blocks 0 .. n_layers - 2 and the input of the last
+        block) into sequences seq0 .. seq0 + n of the backward's ActStore."""
+        L, nl = self.w.L, views.n_layers
+        if self.w.has_ln_pre:
+            ops.gather_seqs(views.x_pre, idx, store.x_pre, n, L, seq0)
+        ops.gather_seqs(views.x_in, idx, store.x_in[:nl + 1], n, L, seq0)
+        ops.gather_seqs(views.x_mid, idx, store.x_mid[:nl], n, L, seq0)
+        ops.gather_seqs(views.qkv, idx, store.qkv[:nl], n, L, seq0)
+        ops.gather_seqs(views.attn, idx, store.attn[:nl], n, L, seq0)
+        ops.gather_seqs(views.lse.view(nl, views.n_seq, -1), idx, store.lse[:nl].view(nl, store.n_seq, -1), n, 1, seq0)
+
+    def complete(self, store: ActStore, n_seq, ln, pstride=0, seqs_per_set=None):
+        """What an adopted ActStore still lacks for the backward: the QuickGELU pre-activations of blocks 0 .. n - 2
+        (ln_2 + c_fc on the stored post-attention residual) and the whole last block, run in training mode from its
+        stored input.  Returns the tower output rows like a training-mode forward()."""
+        w = self.w
+        d, L, n = w.d, w.L, w.n_layers
+        rows = n_seq * L
+        rows_per_set = rows if seqs_per_set is None else seqs_per_set * L
+        lnv = ln.view(-1)
+        for l in range(n - 1):
+            off = w.ln_off("ln_2", l)
+            ops.layernorm_fwd(store.x_mid[l], lnv[off:], lnv[off + d:], rows, d, out16=self.a, param_stride=pstride,
+                              rows_per_set=rows_per_set)
+            linear(self.a, w.layers[l].wfc, self.h, rows, epilogue=EPI_GELU_F16, bias=w.layers[l].bfc, aux_out=store.u[l])
+        x = self._block(n - 1, store.x_in[n - 1], n_seq, lnv, pstride, rows_per_set, store, False, w)
+        self._out, self._out_stride = x, L
         return x
 
     def head(self, x, n_seq, ln, pstride=0, seqs_per_set=None, row_idx=None, class_feat=None, logit_scale=1.0,
@@ -547,6 +617,23 @@ class RlcfEngine:
         self.scorer = RewardScorer(reward, reward_class_feat, B * S, cfg.reward_weights) if reward is not None else None
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
+        # The all-views pass keeps its per-layer activations for a chunk of images (ViewStore) so that the selected
+        # views need no second, training-mode forward: their slices are lifted into self.store (autograd does the same
+        # for the reference by keeping the graph of all 64 views).  1.7 GB per image at ViT-B/16 x 64 views, so the
+        # images of a step go through in chunks that fit RLCF_VIEW_STORE_GB (default 48; 0 = run the selected views
+        # twice, as in round 1) and what the device has free.
+        self.views, self.view_chunk = None, 0
+        budget = float(os.environ.get("RLCF_VIEW_STORE_GB", "48")) * 2 ** 30
+        per_img = V * ViewStore.bytes_per_seq(policy)
+        if dev.type == "cuda":
+            budget = min(budget, torch.cuda.mem_get_info(dev)[0] - 16 * 2 ** 30)     # leave room for the other workspaces
+        if self.run.infer_row_stride == 1 and policy.n_layers > 1 and budget >= per_img:
+            n_chunks = -(-B // max(1, min(B, int(budget // per_img))))
+            self.view_chunk = -(-B // n_chunks)
+            self.views = ViewStore(policy, self.view_chunk * V, dev)
+            self.sel_local = torch.empty(B * S, **i32)
+            self.chunk_off = (torch.arange(B, device=dev, dtype=torch.int32) // self.view_chunk * (self.view_chunk * V)
+                              ).repeat_interleave(S).contiguous()
         self.init_params = policy.ln_flat.clone()
         self.params = torch.empty(B, P, **f32)
         self.m = torch.empty(B, P, **f32)
@@ -604,19 +691,37 @@ class RlcfEngine:
             raise RlcfError(f"expected {B * V} views, got {images.shape[0]}")
         # model.reset(); optimizer.load_state_dict(optim_state)      (tune_cls_rl.py:210-213)
         ops.reset_params(self.init_params, self.params, self.m, self.v, B, P)
-        # step 0: all views with the shared initial parameters       (tpt_cls_rl.py:57)
-        x = self.run.forward(B * V, self.init_params, images=images)
-        self.run.head(x, B * V, self.init_params, class_feat=self.class_feat, logit_scale=self.logit_scale,
-                      logits=self.logits_all)
-        # select_confident_samples                                    (tpt_cls_rl.py:58)
-        ops.entropy_select(self.logits_all, B, V, C, S, self.sel, self.sel_global, self.entropy)
+        if self.views is None:
+            # step 0: all views with the shared initial parameters       (tpt_cls_rl.py:57)
+            x = self.run.forward(B * V, self.init_params, images=images)
+            self.run.head(x, B * V, self.init_params, class_feat=self.class_feat, logit_scale=self.logit_scale,
+                          logits=self.logits_all)
+            # select_confident_samples                                    (tpt_cls_rl.py:58)
+            ops.entropy_select(self.logits_all, B, V, C, S, self.sel, self.sel_global, self.entropy)
+        else:
+            # the same per chunk of images, keeping the per-layer activations; the selected views' are adopted
+            for c0 in range(0, B, self.view_chunk):
+                n = min(self.view_chunk, B - c0)
+                x = self.run.forward(n * V, self.init_params, images=images[c0 * V:(c0 + n) * V], store=self.views)
+                self.run.head(x, n * V, self.init_params, class_feat=self.class_feat, logit_scale=self.logit_scale,
+                              logits=self.logits_all[c0 * V:(c0 + n) * V])
+                loc = self.sel_local[c0 * S:(c0 + n) * S]                  # view numbers inside the chunk
+                ops.entropy_select(self.logits_all[c0 * V:(c0 + n) * V], n, V, C, S, self.sel[c0:c0 + n], loc,
+                                   self.entropy[c0:c0 + n])
+                self.run.adopt(self.views, loc, n * S, self.store, seq0=c0 * S)
+            torch.add(self.sel_local, self.chunk_off, out=self.sel_global)  # view numbers inside the step's batch
         # reward_model.set_image_features(inputs[selected_idx])       (tpt_cls_rl.py:59)
         if cfg.loss == "rlcf":
             self.scorer.features(images, self.sel_global, B * S)
         for step in range(1, cfg.tta_steps + 1):
-            # training-mode forward of the selected views with each image's own parameters (tpt_cls_rl.py:55)
-            xs = self.run.forward(B * S, self.params, pstride=P, seqs_per_set=S, images=images,
-                                  view_idx=self.sel_global, store=self.store)
+            if step == 1 and self.views is not None:
+                # the parameters are still the initial ones: the adopted activations ARE this forward's; only the
+                # QuickGELU pre-activations and the last block (class-token rows only in the all-views pass) are run
+                xs = self.run.complete(self.store, B * S, self.params, pstride=P, seqs_per_set=S)
+            else:
+                # training-mode forward of the selected views with each image's own parameters (tpt_cls_rl.py:55)
+                xs = self.run.forward(B * S, self.params, pstride=P, seqs_per_set=S, images=images,
+                                      view_idx=self.sel_global, store=self.store)
             self.run.head(xs, B * S, self.params, pstride=P, seqs_per_set=S, class_feat=self.class_feat,
                           logit_scale=self.logit_scale, feat=self.feat_sel, inv_norm=self.inv_norm_sel,
                           logits=self.logits_sel)

@@ -354,6 +354,24 @@ def reset_params(init, params, m, v, n_sets, p_total):
     call("rlcf_reset_params", ptr(init), ptr(params), ptr(m), ptr(v), n_sets, p_total, stream())
 
 
+def gather_seqs(src, idx, dst, n, rows_per_seq, dst_seq0=0):
+    """dst[l, (dst_seq0 + j) * rows_per_seq + r] = src[l, idx[j] * rows_per_seq + r] for j < n: src / dst are [layers, rows,
+    width] (or [rows, width]) tensors of the same dtype and width; idx int32 sequence numbers."""
+    _chk(idx, torch.int32, "idx")
+    if src.dtype != dst.dtype or src.shape[-1] != dst.shape[-1] or not src.is_contiguous() or not dst.is_contiguous():
+        raise _lib.RlcfError("gather_seqs: src and dst must be contiguous tensors of one dtype and width")
+    layers = src.shape[0] if src.dim() == 3 else 1
+    if dst.dim() != src.dim() or (src.dim() == 3 and dst.shape[0] != layers):
+        raise _lib.RlcfError("gather_seqs: src and dst must have the same number of layers")
+    row_bytes = src.shape[-1] * src.element_size()
+    seq_bytes = rows_per_seq * row_bytes
+    if (dst_seq0 + n) * rows_per_seq > dst.shape[-2]:
+        raise _lib.RlcfError("gather_seqs: destination too small")
+    call("rlcf_gather_seqs", ptr(src), ptr(idx), dst.data_ptr() + dst_seq0 * seq_bytes, seq_bytes,
+         src.shape[-2] * row_bytes, dst.shape[-2] * row_bytes, layers, n, stream())
+    return dst
+
+
 def cast_f16(src, k_pad=None, out=None, rows=None):
     """fp32 [rows, cols] -> fp16 [rows, k_pad] (zero padded)."""
     _chk(src, torch.float32, "src"); _chk(out, torch.float16, "out")

@@ -294,6 +294,35 @@ def test_class_token_only_last_block_equals_the_full_forward(arch, monkeypatch):
     assert d_pf < 5e-4 and e_p < 2e-3 and e_f < 2e-3
 
 
+@pytest.mark.parametrize("arch,steps,n_img", [("tiny-A", 1, 5), ("tiny-A", 3, 3), ("ViT-B/32", 1, 3)])
+def test_adopted_activations_equal_a_second_forward(arch, steps, n_img, monkeypatch):
+    """The all-views pass keeps its per-layer activations (ViewStore) and the selected views' are lifted into the
+    backward's store instead of running those views again in training mode.  Every kernel computes a row from that
+    row's sequence alone, so the two routes must agree BIT for bit: adapted logits, parameters, gradients, selection.
+    The chunked route is forced through uneven chunks of two images."""
+    cfg = dict(policy=arch, reward="tiny-B" if arch.startswith("tiny") else "ViT-B/32", V=8, rho=0.5, K=2, C=7, lr=5e-3,
+               steps=steps)
+    views = O.make_views(n_img, cfg["V"], O.ARCHS[arch][1], VIEW_SEED).to(DEV)
+    res = {}
+    for mode in ("0", "chunks", "48"):
+        if mode == "chunks":
+            sd = O.make_clip_state_dict(arch, POLICY_SEED)
+            per_img = cfg["V"] * E.ViewStore.bytes_per_seq(E.prepare_visual(to_dev(sd)))
+            monkeypatch.setenv("RLCF_VIEW_STORE_GB", repr(2.5 * per_img / 2 ** 30))
+        else:
+            monkeypatch.setenv("RLCF_VIEW_STORE_GB", mode)
+        eng = build_engine(cfg, n_img)[0]
+        assert (eng.views is None) == (mode == "0")
+        if mode == "chunks":
+            assert eng.view_chunk == 2
+        out = eng.adapt(views).clone()
+        res[mode] = (out, eng.params.clone(), eng.grad.clone(), eng.sel.clone(), eng.sel_global.clone(),
+                     eng.logits_sel.clone())
+    for mode in ("chunks", "48"):
+        for a, b, what in zip(res["0"], res[mode], ("logits", "params", "grad", "sel", "sel_global", "logits_sel")):
+            assert torch.equal(a, b), f"{what} differ between the second-forward and the adopted route ({mode})"
+
+
 def test_reward_features_at_336_pixels():
     """ViT-L/14@336px as the reward model (the strongest single model the reference lists, clip_reward.py:22-27): the
     224-pixel views are resized on the device (bicubic, align_corners, clip_reward.py:133-134) and run through 24 layers
