@@ -551,7 +551,12 @@ def run_b200(args):
         "dtype": "f16", "data": "synthetic",
         "config": make_config(wl, args.mode, args.config, B, world),
         "impl_details": {"cuda_graph": not args.no_graph, "gemm_cta_group": _lib.set_gemm_cta_group(0),
-                         "resident_input_bytes": 2 * (m["in_bytes"] - B * 8)},
+                         "resident_input_bytes": 2 * (m["in_bytes"] - B * 8),
+                         "hbm_peak_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1),
+                         "view_store": (None if getattr(eng, "views", None) is None else
+                                        {"images_per_chunk": eng.view_chunk,
+                                         "gb": round(eng.view_chunk * wl["n_views"] *
+                                                     type(eng.views).bytes_per_seq(eng.policy) / 2 ** 30, 1)})},
         "clocks": m["clocks"],
         "e2e": {"value": m["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": m["in_bytes"],
                 "d2h_bytes_per_step": m["out_bytes"]},
