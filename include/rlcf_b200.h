@@ -111,10 +111,12 @@ int rlcf_attention_bwd(const void* qkv, const void* out, const void* dout, const
 /* Attention output of ONE query row per sequence (row q_row; 0 = the class token): out fp16 [n_seq, d].  The last block
  * of VisionTransformer.forward feeds only x[:, 0, :] into ln_post (model.py:232-238), so an inference forward runs that
  * block's attention / out_proj / ln_2 / MLP on the class-token rows alone -- same values, 1/L of the work.  K and V
- * are read from every token of qkv [n_seq*L, 3d]; no mask (vision towers).  x / x_row (both or neither): also copies
- * row q_row of each sequence of the fp32 residual stream x [n_seq*L, d] into x_row [n_seq, d].  L <= 672. */
-int rlcf_attention_row_fwd(const void* qkv, int n_seq, int L, int heads, int q_row, void* out, const float* x,
-                           float* x_row, void* stream);
+ * are read from every token of qkv [n_seq*L, 3d]; no mask (vision towers).  q_rows != NULL: the caller projected only
+ * that row's query (fp16 [n_seq, d]) and qkv is k | v alone, [n_seq*L, 2d] -- the in_proj rows of the other tokens'
+ * queries are not computed either.  x / x_row (both or neither): also copies row q_row of each sequence of the fp32
+ * residual stream x [n_seq*L, d] into x_row [n_seq, d].  L <= 672. */
+int rlcf_attention_row_fwd(const void* qkv, const void* q_rows, int n_seq, int L, int heads, int q_row, void* out,
+                           const float* x, float* x_row, void* stream);
 
 /* Head: LN(x[row]) @ proj -> L2 normalise -> logits = logit_scale * f . class_feat^T
  * (model.py:235-238, custom_clip.py:423-432 / clip_reward.py:130-137).

@@ -38,7 +38,7 @@ _PROTOS = {
                            _i64, _vp],
     "rlcf_attention_fwd": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "rlcf_attention_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
-    "rlcf_attention_row_fwd": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "rlcf_attention_row_fwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "rlcf_head_fwd": [_vp, _vp, _i64, _vp, _vp, _i64, _i, _vp, _vp, _f, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp],
     "rlcf_entropy_select": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "rlcf_reward_loss": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -84,7 +84,7 @@ int layernorm_fwd(const float*, long long, const float*, const float*, long long
 int layernorm_bwd(const void*, int, long long, const float*, long long, const float*, long long, int, int, int, float,
                   float*, long long, int, __half*, float*, int, long long, long long, cudaStream_t);
 int attention_fwd(const __half*, int, int, int, int, __half*, float*, cudaStream_t);
-int attention_row_fwd(const __half*, int, int, int, int, __half*, const float*, float*, cudaStream_t);
+int attention_row_fwd(const __half*, const __half*, int, int, int, int, __half*, const float*, float*, cudaStream_t);
 int attention_bwd(const __half*, const __half*, const __half*, const float*, int, int, int, int, __half*,
                   cudaStream_t);
 int head_fwd(const float*, const int32_t*, long long, const float*, const float*, long long, int, const float*,
@@ -235,10 +235,10 @@ int rlcf_attention_fwd(const void* qkv, int n_seq, int L, int heads, int causal,
   return attention_fwd(CH(qkv), n_seq, L, heads, causal, H(out), lse, S(stream));
 }
 
-int rlcf_attention_row_fwd(const void* qkv, int n_seq, int L, int heads, int q_row, void* out, const float* x,
-                           float* x_row, void* stream) {
+int rlcf_attention_row_fwd(const void* qkv, const void* q_rows, int n_seq, int L, int heads, int q_row, void* out,
+                           const float* x, float* x_row, void* stream) {
   if (!qkv || !out) return set_error(RLCF_ERR_ARG, "attention_row_fwd: null pointer");
-  return attention_row_fwd(CH(qkv), n_seq, L, heads, q_row, H(out), x, x_row, S(stream));
+  return attention_row_fwd(CH(qkv), q_rows ? CH(q_rows) : nullptr, n_seq, L, heads, q_row, H(out), x, x_row, S(stream));
 }
 
 int rlcf_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int n_seq, int L,

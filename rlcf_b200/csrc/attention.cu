@@ -341,20 +341,21 @@ attn_bwd_kernel(const __half* __restrict__ qkv, const __half* __restrict__ out, 
 // (the residual operand of the out_proj GEMM on those rows).
 constexpr int kRowMaxT = 21;   // key slots per lane: L <= 672
 
-__global__ void __launch_bounds__(128) attn_row_fwd_kernel(const __half* __restrict__ qkv, int n_units, int L, int heads,
-                                                           int q_row, __half* __restrict__ out,
+__global__ void __launch_bounds__(128) attn_row_fwd_kernel(const __half* __restrict__ qkv, long long ld, int k_off, int v_off,
+                                                           const __half* __restrict__ q_rows, int n_units, int L,
+                                                           int heads, int q_row, __half* __restrict__ out,
                                                            const float* __restrict__ x, float* __restrict__ x_row) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u = blockIdx.x * 4 + warp;
   if (u >= n_units) return;
   const int h = u % heads, seq = u / heads;
   const int d = heads * kHd;
-  const long long ld = 3LL * d;
   const __half* base = qkv + static_cast<long long>(seq) * L * ld + h * kHd;
-  // the query row, whole, in every lane
+  // the query row, whole, in every lane: from its own compact [n_seq, d] tensor when the caller projected only that row
   float2 q[32];
   {
-    const uint4* qp = reinterpret_cast<const uint4*>(base + q_row * ld);
+    const uint4* qp = reinterpret_cast<const uint4*>(q_rows != nullptr ? q_rows + static_cast<long long>(seq) * d + h * kHd
+                                                                       : base + q_row * ld);
 #pragma unroll
     for (int c8 = 0; c8 < 8; ++c8) {
       const uint4 v = qp[c8];
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(128) attn_row_fwd_kernel(const __half* __restr
     const int j = t * 32 + lane;
     float acc = -INFINITY;
     if (t * 32 < L && j < L) {
-      const uint4* kp = reinterpret_cast<const uint4*>(base + j * ld + d);
+      const uint4* kp = reinterpret_cast<const uint4*>(base + j * ld + k_off);
       float a0 = 0.f, a1 = 0.f;
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8) {
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(128) attn_row_fwd_kernel(const __half* __restr
   }
   l = warp_sum(l);
   float o0 = 0.f, o1 = 0.f;
-  const __half* vbase = base + 2 * d + 2 * lane;
+  const __half* vbase = base + v_off + 2 * lane;
 #pragma unroll
   for (int t = 0; t < kRowMaxT; ++t) {
     if (t * 32 < L) {
@@ -429,15 +430,19 @@ __global__ void __launch_bounds__(128) attn_row_fwd_kernel(const __half* __restr
   }
 }
 
-int attention_row_fwd(const __half* qkv, int n_seq, int L, int heads, int q_row, __half* out, const float* x,
-                      float* x_row, cudaStream_t stream) {
+int attention_row_fwd(const __half* qkv, const __half* q_rows, int n_seq, int L, int heads, int q_row, __half* out,
+                      const float* x, float* x_row, cudaStream_t stream) {
   if (n_seq <= 0 || L <= 0 || heads <= 0 || q_row < 0 || q_row >= L)
     return set_error(RLCF_ERR_ARG, "attention_row_fwd: bad shape");
   if (L > 32 * kRowMaxT) return set_error(RLCF_ERR_ARG, "attention_row_fwd: sequence %d longer than %d", L, 32 * kRowMaxT);
   if ((x == nullptr) != (x_row == nullptr)) return set_error(RLCF_ERR_ARG, "attention_row_fwd: x and x_row go together");
-  if ((reinterpret_cast<uintptr_t>(qkv) & 15) != 0) return set_error(RLCF_ERR_ARG, "attention_row_fwd: qkv must be 16-byte aligned");
-  const int n_units = n_seq * heads;
-  attn_row_fwd_kernel<<<(n_units + 3) / 4, 128, 0, stream>>>(qkv, n_units, L, heads, q_row, out, x, x_row);
+  if (((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(q_rows)) & 15) != 0)
+    return set_error(RLCF_ERR_ARG, "attention_row_fwd: qkv / q_rows must be 16-byte aligned");
+  const int n_units = n_seq * heads, d = heads * kHd;
+  // q_rows given: qkv holds k | v only ([n_seq*L, 2d]); else the packed q | k | v of rlcf_attention_fwd
+  const long long ld = q_rows != nullptr ? 2LL * d : 3LL * d;
+  attn_row_fwd_kernel<<<(n_units + 3) / 4, 128, 0, stream>>>(qkv, ld, q_rows != nullptr ? 0 : d, q_rows != nullptr ? d : 2 * d,
+                                                             q_rows, n_units, L, heads, q_row, out, x, x_row);
   RLCF_CHECK_LAUNCH("attention_row_fwd");
   return 0;
 }

@@ -303,7 +303,9 @@ class TowerRunner:
             self.infer_row_stride = 1
             self.c_x = torch.empty(3, max_seq, d, **f32)       # class-token rows: block input, after attention, output
             self.c_a = torch.empty(max_seq, d, **f16)
+            self.c_q = torch.empty(max_seq, d, **f16)          # queries of the class-token rows
             self.c_h = torch.empty(max_seq, 4 * d, **f16)
+            self.cls_rows = (torch.arange(max_seq, device=dev, dtype=torch.int32) * L).contiguous()
         self._out, self._out_stride = None, L
         # backward workspaces are allocated lazily by reserve_backward()
         self.g16 = self.gh = self.gqkv = self.dres = self.dres16 = None
@@ -381,10 +383,14 @@ class TowerRunner:
                 # last block, class-token rows only (K and V of every token are in qkv)
                 g, b = gb(w.ln_off("ln_1", l))
                 ops.layernorm_fwd(x, g, b, rows, d, out16=self.a, param_stride=pstride, rows_per_set=rows_per_set)
-                linear(self.a, lw.wqkv, self.qkv, rows, epilogue=EPI_F16, bias=lw.bqkv)
+                # in_proj: keys and values of every token, the query of the class token only
+                kv = self.qkv.view(-1)[:rows * 2 * d].view(rows, 2 * d)
+                linear(self.a, lw.wqkv[d:], kv, rows, epilogue=EPI_F16, bias=lw.bqkv[d:])
+                ops.gather_seqs(self.a, self.cls_rows, self.c_a, n_seq, 1)
+                linear(self.c_a, lw.wqkv[:d], self.c_q, n_seq, epilogue=EPI_F16, bias=lw.bqkv[:d])
                 cx, cmid, cout = self.c_x[0], self.c_x[1], self.c_x[2]
                 sets = n_seq if seqs_per_set is None else seqs_per_set
-                ops.attention_row_fwd(self.qkv, n_seq, L, w.heads, self.c_a, q_row=0, x=x, x_row=cx)
+                ops.attention_row_fwd(kv, n_seq, L, w.heads, self.c_a, q_row=0, x=x, x_row=cx, q_rows=self.c_q)
                 linear(self.c_a, lw.wo, cmid, n_seq, epilogue=EPI_RESID_F32, bias=lw.bo, resid=cx)
                 g, b = gb(w.ln_off("ln_2", l))
                 ops.layernorm_fwd(cmid, g, b, n_seq, d, out16=self.c_a, param_stride=pstride, rows_per_set=sets)
@@ -798,7 +804,7 @@ class RlcfEngine:
         conv = 2 * (L - 1) * d * 3 * w.patch * w.patch if w.kind == "visual" else 0
         block = 24 * L * d * d + 4 * L * L * d
         if cls_only_last and w.kind == "visual" and PRUNE_LAST and L <= 672 and n > 0:
-            last = 6 * L * d * d + 4 * L * d + 18 * d * d          # QKV of every token; one query row; one row of the rest
+            last = 4 * L * d * d + 4 * L * d + 20 * d * d          # K, V of every token; one query row; one row of the rest
             return conv + (n - 1) * block + last + 2 * d * E
         return conv + n * block + 2 * d * E
 

@@ -138,11 +138,12 @@ def attention_fwd(qkv, n_seq, L, heads, out, causal=False, lse=None):
     return out
 
 
-def attention_row_fwd(qkv, n_seq, L, heads, out, q_row=0, x=None, x_row=None):
-    """Attention output of row q_row of every sequence ([n_seq, d]); optionally gathers that row of x into x_row."""
-    _chk(qkv, torch.float16, "qkv"); _chk(out, torch.float16, "out")
+def attention_row_fwd(qkv, n_seq, L, heads, out, q_row=0, x=None, x_row=None, q_rows=None):
+    """Attention output of row q_row of every sequence ([n_seq, d]); optionally gathers that row of x into x_row.
+    q_rows [n_seq, d]: that row's queries, projected by the caller; qkv is then k | v only ([n_seq*L, 2d])."""
+    _chk(qkv, torch.float16, "qkv"); _chk(out, torch.float16, "out"); _chk(q_rows, torch.float16, "q_rows")
     _chk(x, torch.float32, "x"); _chk(x_row, torch.float32, "x_row")
-    call("rlcf_attention_row_fwd", ptr(qkv), n_seq, L, heads, q_row, ptr(out), ptr(x), ptr(x_row), stream())
+    call("rlcf_attention_row_fwd", ptr(qkv), ptr(q_rows), n_seq, L, heads, q_row, ptr(out), ptr(x), ptr(x_row), stream())
     return out
 
 

@@ -339,6 +339,12 @@ def test_attention_row_fwd(n_seq, L, heads, q_row):
     out2 = torch.empty_like(out)
     ops.attention_row_fwd(qkv, n_seq, L, heads, out2, q_row=q_row)
     assert torch.equal(out, out2)
+    # the same with the row's query handed in and k | v alone in the big tensor (what the pruned last block does)
+    kv = qkv[:, d:].contiguous()
+    q_rows = qkv.view(n_seq, L, 3 * d)[:, q_row, :d].contiguous()
+    out3 = torch.empty_like(out)
+    ops.attention_row_fwd(kv, n_seq, L, heads, out3, q_row=q_row, q_rows=q_rows)
+    assert torch.equal(out, out3)
     with pytest.raises(_lib.RlcfError):
         ops.attention_row_fwd(qkv, n_seq, L, heads, out, q_row=L)
 
