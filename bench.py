@@ -498,7 +498,7 @@ def other_modes_leg(dev, rank):
                                ("config5_ln", "ln", 5)):
         try:
             wl = workload_of(argparse.Namespace(config=config))
-            B = 8
+            B = 16      # short runs: a quarter of the headline's 64 images per step (config 3 at 64: profiles/r2_bench_config3_b64.json)
             eng = build_engine(mode, wl, B, dev, reward_seed=3 if config == 5 else 1)
             m = measure(eng, wl, B, 3, 3, dev, rank, 1, None, warm_seconds=1.0)
             fl = eng.algorithmic_flops_per_image()

@@ -441,20 +441,31 @@ class TowerRunner:
         ops.gather_seqs(views.attn, idx, store.attn[:nl], n, L, seq0)
         ops.gather_seqs(views.lse.view(nl, views.n_seq, -1), idx, store.lse[:nl].view(nl, store.n_seq, -1), n, 1, seq0)
 
-    def complete(self, store: ActStore, n_seq, ln, pstride=0, seqs_per_set=None):
+    def complete(self, store: ActStore, n_seq, ln, pstride=0, seqs_per_set=None, images=None, view_idx=None):
         """What an adopted ActStore still lacks for the backward: the QuickGELU pre-activations of blocks 0 .. n - 2
         (ln_2 + c_fc on the stored post-attention residual) and the whole last block, run in training mode from its
-        stored input.  Returns the tower output rows like a training-mode forward()."""
+        stored input.  A store that also keeps the Linear inputs for weight gradients (full tuning) gets those too:
+        the ln_1 / ln_2 outputs, the QuickGELU outputs and (images, view_idx given) the conv1 patches of its
+        sequences.  Returns the tower output rows like a training-mode forward()."""
         w = self.w
         d, L, n = w.d, w.L, w.n_layers
         rows = n_seq * L
         rows_per_set = rows if seqs_per_set is None else seqs_per_set * L
         lnv = ln.view(-1)
+        full = store.a1 is not None
+        if full and images is not None:
+            ops.im2col(images, view_idx, n_seq, w.patch, w.k_pad, self.patches)
         for l in range(n - 1):
+            if full:
+                off = w.ln_off("ln_1", l)
+                ops.layernorm_fwd(store.x_in[l], lnv[off:], lnv[off + d:], rows, d, out16=store.a1[l],
+                                  param_stride=pstride, rows_per_set=rows_per_set)
+            a2 = store.a2[l] if full else self.a
             off = w.ln_off("ln_2", l)
-            ops.layernorm_fwd(store.x_mid[l], lnv[off:], lnv[off + d:], rows, d, out16=self.a, param_stride=pstride,
+            ops.layernorm_fwd(store.x_mid[l], lnv[off:], lnv[off + d:], rows, d, out16=a2, param_stride=pstride,
                               rows_per_set=rows_per_set)
-            linear(self.a, w.layers[l].wfc, self.h, rows, epilogue=EPI_GELU_F16, bias=w.layers[l].bfc, aux_out=store.u[l])
+            linear(a2, w.layers[l].wfc, store.h[l] if full else self.h, rows, epilogue=EPI_GELU_F16,
+                   bias=w.layers[l].bfc, aux_out=store.u[l])
         x = self._block(n - 1, store.x_in[n - 1], n_seq, lnv, pstride, rows_per_set, store, False, w)
         self._out, self._out_stride = x, L
         return x
@@ -546,6 +557,46 @@ class RlcfConfig:
         return int(self.n_views * self.selection_p)  # tpt_cls_rl.py:34
 
 
+def setup_view_store(eng, policy: TowerWeights, run: "TowerRunner", B: int, V: int, S: int, dev):
+    """The all-views pass keeps its per-layer activations for a chunk of images (ViewStore) so that the selected views
+    need no second, training-mode forward: their slices are lifted into eng.store (autograd does the same for the
+    reference by keeping the graph of all 64 views).  1.7 GB per image at ViT-B/16 x 64 views, so the images of a step go
+    through in chunks that fit RLCF_VIEW_STORE_GB (default 48; 0 = run the selected views twice, as in round 1) and
+    what the device has free."""
+    eng.views, eng.view_chunk = None, 0
+    budget = float(os.environ.get("RLCF_VIEW_STORE_GB", "48")) * 2 ** 30
+    per_img = V * ViewStore.bytes_per_seq(policy)
+    if dev.type == "cuda":
+        budget = min(budget, torch.cuda.mem_get_info(dev)[0] - 16 * 2 ** 30)     # leave room for the other workspaces
+    if run.infer_row_stride == 1 and policy.n_layers > 1 and budget >= per_img:
+        n_chunks = -(-B // max(1, min(B, int(budget // per_img))))
+        eng.view_chunk = -(-B // n_chunks)
+        eng.views = ViewStore(policy, eng.view_chunk * V, dev)
+        eng.sel_local = torch.empty(B * S, dtype=torch.int32, device=dev)
+        eng.chunk_off = (torch.arange(B, device=dev, dtype=torch.int32) // eng.view_chunk * (eng.view_chunk * V)
+                         ).repeat_interleave(S).contiguous()
+
+
+def all_views_pass(eng, run: "TowerRunner", init_ln: torch.Tensor, images: torch.Tensor, B: int, V: int, S: int, C: int):
+    """Forward of all B x V views with the shared initial parameters, logits, entropy selection -- and, with a ViewStore,
+    adoption of the selected views' activations into eng.store, chunk of images by chunk."""
+    if eng.views is None:
+        x = run.forward(B * V, init_ln, images=images)
+        run.head(x, B * V, init_ln, class_feat=eng.class_feat, logit_scale=eng.logit_scale, logits=eng.logits_all)
+        ops.entropy_select(eng.logits_all, B, V, C, S, eng.sel, eng.sel_global, eng.entropy)
+        return
+    for c0 in range(0, B, eng.view_chunk):
+        n = min(eng.view_chunk, B - c0)
+        x = run.forward(n * V, init_ln, images=images[c0 * V:(c0 + n) * V], store=eng.views)
+        run.head(x, n * V, init_ln, class_feat=eng.class_feat, logit_scale=eng.logit_scale,
+                 logits=eng.logits_all[c0 * V:(c0 + n) * V])
+        loc = eng.sel_local[c0 * S:(c0 + n) * S]                  # view numbers inside the chunk
+        ops.entropy_select(eng.logits_all[c0 * V:(c0 + n) * V], n, V, C, S, eng.sel[c0:c0 + n], loc,
+                           eng.entropy[c0:c0 + n])
+        run.adopt(eng.views, loc, n * S, eng.store, seq0=c0 * S)
+    torch.add(eng.sel_local, eng.chunk_off, out=eng.sel_global)    # view numbers inside the step's batch
+
+
 class RewardScorer:
     """The frozen reward model(s) of one engine: image features of the selected views and the reward-weighted loss.
     One tower (CLIPRewards, clip_reward.py:43-178) or up to four (CLIPRewardsMultiple, clip_reward.py:180-307), each
@@ -623,23 +674,7 @@ class RlcfEngine:
         self.scorer = RewardScorer(reward, reward_class_feat, B * S, cfg.reward_weights) if reward is not None else None
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
-        # The all-views pass keeps its per-layer activations for a chunk of images (ViewStore) so that the selected
-        # views need no second, training-mode forward: their slices are lifted into self.store (autograd does the same
-        # for the reference by keeping the graph of all 64 views).  1.7 GB per image at ViT-B/16 x 64 views, so the
-        # images of a step go through in chunks that fit RLCF_VIEW_STORE_GB (default 48; 0 = run the selected views
-        # twice, as in round 1) and what the device has free.
-        self.views, self.view_chunk = None, 0
-        budget = float(os.environ.get("RLCF_VIEW_STORE_GB", "48")) * 2 ** 30
-        per_img = V * ViewStore.bytes_per_seq(policy)
-        if dev.type == "cuda":
-            budget = min(budget, torch.cuda.mem_get_info(dev)[0] - 16 * 2 ** 30)     # leave room for the other workspaces
-        if self.run.infer_row_stride == 1 and policy.n_layers > 1 and budget >= per_img:
-            n_chunks = -(-B // max(1, min(B, int(budget // per_img))))
-            self.view_chunk = -(-B // n_chunks)
-            self.views = ViewStore(policy, self.view_chunk * V, dev)
-            self.sel_local = torch.empty(B * S, **i32)
-            self.chunk_off = (torch.arange(B, device=dev, dtype=torch.int32) // self.view_chunk * (self.view_chunk * V)
-                              ).repeat_interleave(S).contiguous()
+        setup_view_store(self, policy, self.run, B, V, S, dev)
         self.init_params = policy.ln_flat.clone()
         self.params = torch.empty(B, P, **f32)
         self.m = torch.empty(B, P, **f32)
@@ -697,25 +732,8 @@ class RlcfEngine:
             raise RlcfError(f"expected {B * V} views, got {images.shape[0]}")
         # model.reset(); optimizer.load_state_dict(optim_state)      (tune_cls_rl.py:210-213)
         ops.reset_params(self.init_params, self.params, self.m, self.v, B, P)
-        if self.views is None:
-            # step 0: all views with the shared initial parameters       (tpt_cls_rl.py:57)
-            x = self.run.forward(B * V, self.init_params, images=images)
-            self.run.head(x, B * V, self.init_params, class_feat=self.class_feat, logit_scale=self.logit_scale,
-                          logits=self.logits_all)
-            # select_confident_samples                                    (tpt_cls_rl.py:58)
-            ops.entropy_select(self.logits_all, B, V, C, S, self.sel, self.sel_global, self.entropy)
-        else:
-            # the same per chunk of images, keeping the per-layer activations; the selected views' are adopted
-            for c0 in range(0, B, self.view_chunk):
-                n = min(self.view_chunk, B - c0)
-                x = self.run.forward(n * V, self.init_params, images=images[c0 * V:(c0 + n) * V], store=self.views)
-                self.run.head(x, n * V, self.init_params, class_feat=self.class_feat, logit_scale=self.logit_scale,
-                              logits=self.logits_all[c0 * V:(c0 + n) * V])
-                loc = self.sel_local[c0 * S:(c0 + n) * S]                  # view numbers inside the chunk
-                ops.entropy_select(self.logits_all[c0 * V:(c0 + n) * V], n, V, C, S, self.sel[c0:c0 + n], loc,
-                                   self.entropy[c0:c0 + n])
-                self.run.adopt(self.views, loc, n * S, self.store, seq0=c0 * S)
-            torch.add(self.sel_local, self.chunk_off, out=self.sel_global)  # view numbers inside the step's batch
+        # step 0: all views with the shared initial parameters (tpt_cls_rl.py:57), select_confident_samples (:58)
+        all_views_pass(self, self.run, self.init_params, images, B, V, S, C)
         # reward_model.set_image_features(inputs[selected_idx])       (tpt_cls_rl.py:59)
         if cfg.loss == "rlcf":
             self.scorer.features(images, self.sel_global, B * S)

@@ -327,6 +327,7 @@ class FullTuneEngine:
         self._graph = None
         self._static_images = None
         self.fused_adamw = FUSED_ADAMW
+        E.setup_view_store(self, pol, self.run, B, V, S, dev)     # step 1 adopts the all-views pass's activations
 
     def sync_initial_state(self, sd_visual: dict, prefix: str = "visual.") -> bool:
         """Makes the engine start from `sd_visual` (the model's current reset state).  A no-op -- one packed copy and
@@ -398,14 +399,15 @@ class FullTuneEngine:
         if images.shape[0] != B * V:
             raise RlcfError(f"expected {B * V} views, got {images.shape[0]}")
         ops.reset_params(self.init_ln, self.ln, self.ln_m, self.ln_v, B, P)
-        x = self.run.forward(B * V, self.init_ln, images=images)
-        self.run.head(x, B * V, self.init_ln, class_feat=self.class_feat, logit_scale=self.logit_scale,
-                      logits=self.logits_all)
-        ops.entropy_select(self.logits_all, B, V, C, S, self.sel, self.sel_global, self.entropy)
+        E.all_views_pass(self, self.run, self.init_ln, images, B, V, S, C)
         self.scorer.features(images, self.sel_global, B * S)
         # ---- step 1: all images on the shared initial weights
-        xs = self.run.forward(B * S, self.ln, pstride=P, seqs_per_set=S, images=images, view_idx=self.sel_global,
-                              store=self.store)
+        if self.views is not None:      # the selected views' activations were adopted from the all-views pass
+            xs = self.run.complete(self.store, B * S, self.ln, pstride=P, seqs_per_set=S, images=images,
+                                   view_idx=self.sel_global)
+        else:
+            xs = self.run.forward(B * S, self.ln, pstride=P, seqs_per_set=S, images=images, view_idx=self.sel_global,
+                                  store=self.store)
         self.partials.zero_()
         self._loss_and_head_bwd(1, xs, self.run, self.ln, P, B, pol)
         hk.bind(self.grads, B, self.run.patches, fused=self._fused(1))

@@ -323,6 +323,28 @@ def test_adopted_activations_equal_a_second_forward(arch, steps, n_img, monkeypa
             assert torch.equal(a, b), f"{what} differ between the second-forward and the adopted route ({mode})"
 
 
+@pytest.mark.parametrize("steps", [1, 2])
+def test_full_tuning_adopted_activations_equal_a_second_forward(steps, monkeypatch):
+    """The same for full image-encoder tuning: its first step also needs the Linear inputs (ln_1 / ln_2 / QuickGELU
+    outputs) and the conv1 patches of the selected views for the weight gradients; TowerRunner.complete rebuilds them."""
+    from rlcf_b200 import full_tune as FT
+    sd_p, sd_r = O.make_clip_state_dict("tiny-A", POLICY_SEED), O.make_clip_state_dict("tiny-B", REWARD_SEED)
+    tok = O.make_tokens(10, 512, seed=TOKEN_SEED)
+    cf, rc = O.class_features(sd_p, tok), O.class_features(sd_r, tok)
+    rcfg = E.RlcfConfig(n_views=16, selection_p=0.25, tta_steps=steps, sample_k=3, lr=1e-4)
+    views = O.make_views(3, 16, 64, VIEW_SEED + 3).to(DEV)
+    res = {}
+    for mode in ("0", "48"):
+        monkeypatch.setenv("RLCF_VIEW_STORE_GB", mode)
+        eng = FT.FullTuneEngine(to_dev(sd_p), cf.to(DEV), float(sd_p["logit_scale"].exp()), rcfg, 3,
+                                E.prepare_visual(to_dev(sd_r)), rc.to(DEV))
+        assert (eng.views is None) == (mode == "0")
+        out = eng.adapt(views).clone()
+        res[mode] = (out, eng.ln.clone(), eng.rest.clone(), eng.grads.clone(), eng.sel_global.clone())
+    for a, b, what in zip(res["0"], res["48"], ("logits", "LayerNorm parameters", "weights", "gradients", "sel_global")):
+        assert torch.equal(a, b), f"{what} differ between the second-forward and the adopted route"
+
+
 def test_reward_features_at_336_pixels():
     """ViT-L/14@336px as the reward model (the strongest single model the reference lists, clip_reward.py:22-27): the
     224-pixel views are resized on the device (bicubic, align_corners, clip_reward.py:133-134) and run through 24 layers
