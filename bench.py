@@ -482,7 +482,8 @@ def gemm_roofline(eng, batch, ms_per_step, B, value, world, args):
         # ln_post, so its out_proj / MLP / attention rows of the other tokens are not computed (and not counted);
         # reference_gflop_per_image = SURVEY.md 8(d)'s count with every block on every token, as the reference runs it
         "whole_step": {"algorithmic_gflop_per_image": flops_img / 1e9,
-                       "reference_gflop_per_image": eng.reference_flops_per_image() / 1e9,
+                       "reference_gflop_per_image": (eng.reference_flops_per_image() / 1e9
+                                                     if hasattr(eng, "reference_flops_per_image") else None),
                        "achieved_tflops": step_tflops, "frac": step_tflops / pk["tflops_sustained"]},
     }
 
@@ -554,9 +555,7 @@ def run_b200(args):
                          "resident_input_bytes": 2 * (m["in_bytes"] - B * 8),
                          "hbm_peak_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1),
                          "view_store": (None if getattr(eng, "views", None) is None else
-                                        {"images_per_chunk": eng.view_chunk,
-                                         "gb": round(eng.view_chunk * wl["n_views"] *
-                                                     type(eng.views).bytes_per_seq(eng.policy) / 2 ** 30, 1)})},
+                                        {"images_per_chunk": eng.view_chunk, "gb": round(eng.view_store_gb, 1)})},
         "clocks": m["clocks"],
         "e2e": {"value": m["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": m["in_bytes"],
                 "d2h_bytes_per_step": m["out_bytes"]},

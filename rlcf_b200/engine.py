@@ -563,7 +563,7 @@ def setup_view_store(eng, policy: TowerWeights, run: "TowerRunner", B: int, V: i
     reference by keeping the graph of all 64 views).  1.7 GB per image at ViT-B/16 x 64 views, so the images of a step go
     through in chunks that fit RLCF_VIEW_STORE_GB (default 48; 0 = run the selected views twice, as in round 1) and
     what the device has free."""
-    eng.views, eng.view_chunk = None, 0
+    eng.views, eng.view_chunk, eng.view_store_gb = None, 0, 0.0
     budget = float(os.environ.get("RLCF_VIEW_STORE_GB", "48")) * 2 ** 30
     per_img = V * ViewStore.bytes_per_seq(policy)
     if dev.type == "cuda":
@@ -572,6 +572,7 @@ def setup_view_store(eng, policy: TowerWeights, run: "TowerRunner", B: int, V: i
         n_chunks = -(-B // max(1, min(B, int(budget // per_img))))
         eng.view_chunk = -(-B // n_chunks)
         eng.views = ViewStore(policy, eng.view_chunk * V, dev)
+        eng.view_store_gb = eng.view_chunk * per_img / 2 ** 30
         eng.sel_local = torch.empty(B * S, dtype=torch.int32, device=dev)
         eng.chunk_off = (torch.arange(B, device=dev, dtype=torch.int32) // eng.view_chunk * (eng.view_chunk * V)
                          ).repeat_interleave(S).contiguous()
@@ -879,6 +880,7 @@ class PromptEngine:
         # Run the tower on the first max(EOT) + 1 positions (rounded up to 8): same EOT rows, same context gradients,
         # a fifth of the work the reference spends there.  RLCF_TEXT_TRUNCATE=0 keeps all 77.
         L_full = self.tokens.shape[1]
+        self.full_text_positions = L_full
         need = int(self.tokens.argmax(dim=-1).max()) + 1
         if layout is not None:       # source positions the assembled prefix reads from
             need = max(need, int(layout.src_map[:, :need].max()) + 1)
@@ -1041,6 +1043,19 @@ class PromptEngine:
         total = cfg.n_views * fi + fi + C * ft + cfg.tta_steps * C * (ft + RlcfEngine.tower_dgrad_flops(self.text))
         if self.scorer is not None and cfg.loss == "rlcf":
             total += cfg.n_selected * self.scorer.fwd_flops()
+        return float(total)
+
+    def reference_flops_per_image(self) -> float:
+        """The same count as the reference executes it: every block on every token of the image towers, the text tower
+        on all of CLIP's context positions (the padding behind the EOT included)."""
+        import dataclasses
+        cfg, C = self.cfg, self.tokens.shape[0]
+        fi = RlcfEngine.tower_fwd_flops(self.visual)
+        txt = dataclasses.replace(self.text, L=self.full_text_positions)
+        ft = RlcfEngine.tower_fwd_flops(txt)
+        total = cfg.n_views * fi + fi + C * ft + cfg.tta_steps * C * (ft + RlcfEngine.tower_dgrad_flops(txt))
+        if self.scorer is not None and cfg.loss == "rlcf":
+            total += cfg.n_selected * sum(RlcfEngine.tower_fwd_flops(t) for t in self.scorer.towers)
         return float(total)
 
 

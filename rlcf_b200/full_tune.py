@@ -454,6 +454,17 @@ class FullTuneEngine:
         total = V * fi + S * bwd + f + (cfg.tta_steps - 1) * S * (f + bwd) + S * self.scorer.fwd_flops()
         return float(total)
 
+    def reference_flops_per_image(self) -> float:
+        """The same count with every block of every forward on every token, as the reference executes it."""
+        cfg, w = self.cfg, self.base
+        V, S = cfg.n_views, cfg.n_selected
+        f = E.RlcfEngine.tower_fwd_flops(w)
+        wgrad = w.n_layers * 24 * w.L * w.d * w.d + 2 * (w.L - 1) * w.d * 3 * w.patch * w.patch + 2 * w.d * w.E
+        bwd = E.RlcfEngine.tower_dgrad_flops(w) + wgrad
+        total = V * f + S * bwd + f + (cfg.tta_steps - 1) * S * (f + bwd)
+        total += S * sum(E.RlcfEngine.tower_fwd_flops(t) for t in self.scorer.towers)
+        return float(total)
+
     def export_params(self, b: int, prefix: str = "visual.") -> dict:
         """Adapted parameters of image b under the reference's state-dict names (conv1 in its [d,3,p,p] shape)."""
         lay, pol = self.lay, self.base

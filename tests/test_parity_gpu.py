@@ -339,6 +339,7 @@ def test_full_tuning_adopted_activations_equal_a_second_forward(steps, monkeypat
         eng = FT.FullTuneEngine(to_dev(sd_p), cf.to(DEV), float(sd_p["logit_scale"].exp()), rcfg, 3,
                                 E.prepare_visual(to_dev(sd_r)), rc.to(DEV))
         assert (eng.views is None) == (mode == "0")
+        assert eng.reference_flops_per_image() >= eng.algorithmic_flops_per_image() > 0      # both used by bench.py
         out = eng.adapt(views).clone()
         res[mode] = (out, eng.ln.clone(), eng.rest.clone(), eng.grads.clone(), eng.sel_global.clone())
     for a, b, what in zip(res["0"], res["48"], ("logits", "LayerNorm parameters", "weights", "gradients", "sel_global")):
@@ -439,6 +440,7 @@ def test_text_tower_on_the_eot_prefix_equals_all_77_positions(golden, monkeypatc
         monkeypatch.setattr(E, "TRUNCATE_TEXT", trunc)
         eng, *_ = _prompt_engine(cfg, tokens, ctx_init, cfg["n_img"])
         assert (eng.text_tokens < 77) == trunc and eng.text_tokens % 8 == 0 or eng.text_tokens == 77
+        assert eng.reference_flops_per_image() >= eng.algorithmic_flops_per_image() > 0      # both used by bench.py
         eng._graph = None
         eng.tune(views)
         torch.cuda.synchronize()
