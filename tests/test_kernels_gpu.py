@@ -300,6 +300,28 @@ def test_attention_fwd_sharply_peaked_rows(L, heads, causal):
     assert (sc.max(-1).values - sc[..., :32].max(-1).values).max().item() > 8.0
 
 
+@pytest.mark.parametrize("dtype,width,rows_per_seq", [(torch.float16, 192, 17), (torch.float32, 64, 5),
+                                                      (torch.float32, 34, 1), (torch.float16, 6, 3)])
+def test_gather_seqs(dtype, width, rows_per_seq):
+    """dst[l, (seq0 + j) * R + r] = src[l, idx[j] * R + r]: 16-byte vectors when the sizes allow, 4-byte words otherwise
+    (the last two shapes), several layers per launch, destination offset, untouched rows stay untouched."""
+    torch.manual_seed(width)
+    layers, n_src, n, seq0, n_dst = 3, 11, 4, 2, 8
+    src = torch.randn(layers, n_src * rows_per_seq, width, device=_dev()).to(dtype)
+    idx = torch.tensor([7, 0, 10, 7], device=_dev(), dtype=torch.int32)
+    dst = torch.full((layers, n_dst * rows_per_seq, width), -3.0, device=_dev(), dtype=dtype)
+    ops.gather_seqs(src, idx, dst, n, rows_per_seq, seq0)
+    ref = torch.full_like(dst, -3.0)
+    s4 = src.view(layers, n_src, rows_per_seq, width)
+    ref.view(layers, n_dst, rows_per_seq, width)[:, seq0:seq0 + n] = s4[:, idx.long()]
+    assert torch.equal(dst, ref)
+    flat_src, flat_dst = src[0].contiguous(), torch.zeros(n_dst * rows_per_seq, width, device=_dev(), dtype=dtype)
+    ops.gather_seqs(flat_src, idx, flat_dst, n, rows_per_seq)          # 2-D form: one layer
+    assert torch.equal(flat_dst.view(n_dst, rows_per_seq, width)[:n], s4[0, idx.long()])
+    with pytest.raises(_lib.RlcfError):
+        ops.gather_seqs(src, idx, dst, n, rows_per_seq, n_dst - 1)     # would run past the destination
+
+
 @pytest.mark.parametrize("n_seq,L,heads", [(30, 257, 16), (2, 257, 1), (9, 129, 3)])
 def test_attention_forward_class_token_row_job(n_seq, L, heads):
     """L = 128 k + 1 (ViT-L/14: 257 tokens): the 128-row tiles cover rows [1, L) and the TMA warp of each team computes
