@@ -385,3 +385,30 @@ def test_bench_arms_build_the_same_config():
         with open(os.path.join(ROOT, "baseline", "_ref", "MANIFEST.json")) as f:
             man = json.load(f)
         assert "tune_cls_rl.py" in man["files"] and "tpt_cls_rl.py" in man["files"] and "clip_reward.py" in man["files"]
+
+
+def test_view_store_chunking(monkeypatch):
+    """setup_view_store: the images of a step are split into equal chunks whose all-views activation store fits the
+    budget; chunk_off turns view numbers inside a chunk into view numbers inside the step's batch."""
+    import types
+    import torch
+    from rlcf_b200 import engine as E
+    w = E.TowerWeights(kind="visual", d=64, heads=1, n_layers=3, L=5, E=8)
+    w.ln_flat = torch.zeros(4)
+    per_seq = E.ViewStore.bytes_per_seq(w)
+    # x_pre + x_in[3] + x_mid[2] fp32, qkv (3d) + attn (d) fp16 for 2 layers, lse for 2 layers
+    assert per_seq == 5 * 64 * (4 * 6 + 2 * 4 * 2) + 4 * 2 * 1 * 5
+    B, V, S = 5, 4, 2
+    run = types.SimpleNamespace(infer_row_stride=1)
+    eng = types.SimpleNamespace()
+    monkeypatch.setenv("RLCF_VIEW_STORE_GB", repr(2.5 * V * per_seq / 2 ** 30))      # room for two images
+    E.setup_view_store(eng, w, run, B, V, S, torch.device("cpu"))
+    assert eng.view_chunk == 2 and eng.views.n_seq == 2 * V and eng.views.n_layers == 2
+    assert eng.chunk_off.tolist() == [0, 0, 0, 0, 8, 8, 8, 8, 16, 16]
+    assert tuple(eng.views.x_in.shape) == (3, 2 * V * 5, 64) and eng.views.u is None
+    monkeypatch.setenv("RLCF_VIEW_STORE_GB", "0")
+    E.setup_view_store(eng, w, run, B, V, S, torch.device("cpu"))
+    assert eng.views is None and eng.view_chunk == 0
+    monkeypatch.setenv("RLCF_VIEW_STORE_GB", "48")
+    E.setup_view_store(eng, w, types.SimpleNamespace(infer_row_stride=5), B, V, S, torch.device("cpu"))
+    assert eng.views is None            # no class-token-only last block (RLCF_PRUNE_LAST=0): nothing to adopt from
