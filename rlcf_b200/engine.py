@@ -571,7 +571,11 @@ def setup_view_store(eng, policy: TowerWeights, run: "TowerRunner", B: int, V: i
     if run.infer_row_stride == 1 and policy.n_layers > 1 and budget >= per_img:
         n_chunks = -(-B // max(1, min(B, int(budget // per_img))))
         eng.view_chunk = -(-B // n_chunks)
-        eng.views = ViewStore(policy, eng.view_chunk * V, dev)
+        try:
+            eng.views = ViewStore(policy, eng.view_chunk * V, dev)
+        except torch.OutOfMemoryError:      # fragmented or shared device: the second-forward route needs no store
+            eng.views, eng.view_chunk = None, 0
+            return
         eng.view_store_gb = eng.view_chunk * per_img / 2 ** 30
         eng.sel_local = torch.empty(B * S, dtype=torch.int32, device=dev)
         eng.chunk_off = (torch.arange(B, device=dev, dtype=torch.int32) // eng.view_chunk * (eng.view_chunk * V)
